@@ -1,0 +1,46 @@
+/* krr_host_c.h -- C entry points of the C++17 host layer (kiraray_b200/host), for drivers that are
+ * not C++ (the Python tests and bench.py bind these with ctypes).  The host layer mirrors the
+ * reference's RenderApp/RenderPass/SceneImporter surface (src/main/renderer.cpp:84-122, 258-316;
+ * src/core/renderpass.h:138-273; src/scene/krrscene.cpp:8-349); loading a config touches no GPU. */
+#ifndef KRR_HOST_C_H
+#define KRR_HOST_C_H
+#include "krr_wfpt.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct KrrHostApp KrrHostApp;
+
+/* directory holding spectral_srgb.bin (colour-space tables) */
+int krr_host_set_data_dir(const char *dir);
+/* RenderApp::loadConfigFrom / loadConfig.  config: path to a JSON file (is_path != 0) or JSON text;
+ * asset_root: directory model paths are resolved against (NULL: the config's directory). */
+int krr_host_app_create(const char *config, int is_path, const char *asset_root, KrrHostApp **out);
+void krr_host_app_destroy(KrrHostApp *app);
+int krr_host_app_get_resolution(KrrHostApp *app, int32_t *w, int32_t *h);
+int krr_host_app_set_resolution(KrrHostApp *app, int32_t w, int32_t h);
+/* flat scene view (valid until the app is destroyed or the scene changes) */
+const KrrSceneDesc *krr_host_app_scene_desc(KrrHostApp *app);
+/* camera as the pass will receive it at the current resolution (Scene::update + aspect ratio) */
+int krr_host_app_get_camera(KrrHostApp *app, double time_seconds, KrrCameraData *out);
+/* WavefrontPathTracer params as JSON (integrator.h:86-94 keys + "spp"); returns length or <0 */
+int krr_host_app_get_wfpt_params(KrrHostApp *app, char *buf, int32_t capacity);
+int krr_host_app_set_wfpt_params(KrrHostApp *app, const char *params_json);
+/* GPU: RenderApp::initialize (first call) + n_frames x {++frameIndex; beginFrame; render; endFrame}
+ * over all enabled passes; then reads the film back (film_host may be NULL). */
+int krr_host_app_render_frames(KrrHostApp *app, int32_t n_frames, float *film_host);
+/* the pass's C-ABI handle (NULL before the first render) and frame counter */
+KrrWfpt *krr_host_app_wfpt_handle(KrrHostApp *app);
+uint64_t krr_host_app_frame_index(KrrHostApp *app);
+const char *krr_host_last_error(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,254 @@
+/* krr_wfpt.h -- C ABI of the B200-native WavefrontPathTracer pass.
+ *
+ * The reference (cuteday/KiRaRay) has NO C ABI: its pass is the C++ class `WavefrontPathTracer :
+ * RenderPass` (reference src/render/wavefront/integrator.h:24-104) driven through the RenderPass
+ * virtuals (src/core/renderpass.h:138-200).  BASELINE.json's north_star puts a thin C ABI *under*
+ * that class; each entry point below is derived 1:1 from the virtual (or member) it backs, cited
+ * at the declaration.  The C++17 host class that keeps the reference's plugin surface lives in
+ * kiraray_b200/host/ and calls ONLY these functions (see INTEGRATION.md for the binding a KiRaRay
+ * maintainer would add).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success
+ * and a negative KRR_E_* code on failure (never throws, never exits -- the reference's
+ * Log(Fatal)/CUDA_CHECK -> exit(1), src/core/logger.cpp:100, is replaced by error returns);
+ * krr_wfpt_last_error() gives the message.  A handle belongs to the CUDA device that was current
+ * at krr_wfpt_create(); it is not thread-safe; all work is enqueued on the caller's stream.
+ * Host arrays passed to set_* are copied before the call returns.
+ */
+#ifndef KRR_WFPT_H
+#define KRR_WFPT_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define KRR_WFPT_ABI_VERSION 1
+
+enum {
+	KRR_OK			  = 0,
+	KRR_E_INVALID	  = -1, /* bad argument / bad JSON */
+	KRR_E_CUDA		  = -2, /* CUDA runtime error (message has the cudaError string) */
+	KRR_E_STATE		  = -3, /* call order violated (e.g. render before set_scene/resize) */
+	KRR_E_UNSUPPORTED = -4,
+};
+
+/* MaterialType, reference src/core/raytracing.h:26-33 */
+enum { KRR_MAT_NULL = 0, KRR_MAT_DIFFUSE = 1, KRR_MAT_DIELECTRIC = 2, KRR_MAT_CONDUCTOR = 3, KRR_MAT_DISNEY = 4 };
+/* Material::ShadingModel, reference src/core/texture.h:124-127 */
+enum { KRR_SHADING_METALLIC_ROUGHNESS = 0, KRR_SHADING_SPECULAR_GLOSSINESS = 1 };
+/* Material::TextureType, reference src/core/texture.h:115-122 */
+enum { KRR_TEX_DIFFUSE = 0, KRR_TEX_SPECULAR = 1, KRR_TEX_EMISSIVE = 2, KRR_TEX_NORMAL = 3, KRR_TEX_TRANSMISSION = 4, KRR_TEX_COUNT = 5 };
+/* index of the light class in rt::Light's tagged-pointer type list, reference src/core/light.h:261-263 */
+enum { KRR_LIGHT_POINT = 0, KRR_LIGHT_DIRECTIONAL = 1, KRR_LIGHT_SPOT = 2, KRR_LIGHT_DIFFUSE_AREA = 3, KRR_LIGHT_INFINITE = 4 };
+/* spectrum kinds for spectral eta / k, reference src/render/spectrum.h:92-96 */
+enum { KRR_SPEC_NONE = 0, KRR_SPEC_CONSTANT = 1, KRR_SPEC_CAUCHY = 2, KRR_SPEC_SELLMEIER = 3, KRR_SPEC_TABULATED = 4 };
+enum { KRR_MEDIUM_HOMOGENEOUS = 0, KRR_MEDIUM_GRID = 1 };
+
+/* rt::TextureData, reference src/core/texture.h:184-204: constant value and/or an RGBA32F image
+ * (bilinear, wrap addressing, as texture.cpp:229-246). */
+typedef struct KrrTextureDesc {
+	int32_t		 valid;		/* TextureData::mValid */
+	float		 value[4];	/* TextureData::mValue */
+	const float *image;		/* optional RGBA32F texels, row-major, NULL = constant texture */
+	int32_t		 width, height;
+} KrrTextureDesc;
+
+typedef struct KrrSpectrumDesc {
+	int32_t		 kind;		/* KRR_SPEC_* */
+	float		 a[3], b[3];/* constant: a[0]; cauchy: a[0], b[0]; sellmeier: b = a[], c = b[] */
+	const float *lambdas;	/* tabulated (piecewise linear): n samples */
+	const float *values;
+	int32_t		 n;
+} KrrSpectrumDesc;
+
+/* rt::MaterialData, reference src/core/texture.h:206-224 (+ Material::MaterialParams :129-137) */
+typedef struct KrrMaterialDesc {
+	float			diffuse[4];
+	float			specular[4];
+	float			specular_transmission;
+	float			anisotropic;
+	float			ior;
+	KrrSpectrumDesc spectral_eta, spectral_k;
+	KrrTextureDesc	textures[KRR_TEX_COUNT];
+	int32_t			bsdf_type;	   /* KRR_MAT_* */
+	int32_t			shading_model; /* KRR_SHADING_* */
+	int32_t			color_space;   /* ColorSpaceType; only 0 (sRGB) is accepted */
+} KrrMaterialDesc;
+
+/* rt::MeshData, reference src/core/mesh.h:24-35 */
+typedef struct KrrMeshDesc {
+	const float	  *positions; /* 3 * n_vertices */
+	const float	  *normals;	  /* 3 * n_vertices or NULL */
+	const float	  *texcoords; /* 2 * n_vertices or NULL */
+	const float	  *tangents;  /* 3 * n_vertices or NULL */
+	const int32_t *indices;	  /* 3 * n_triangles */
+	int32_t		   n_vertices, n_triangles;
+	int32_t		   material;	   /* index into materials, -1 = null material (medium interface) */
+	int32_t		   medium_inside;  /* index into media or -1 */
+	int32_t		   medium_outside; /* index into media or -1 */
+	float		   Le[3];		   /* Mesh::Le, mesh-specific emission (pbrt import), src/core/mesh.h:92 */
+} KrrMeshDesc;
+
+/* one keyed SRT sample for motion blur / animation: scale, quaternion (x,y,z,w), translation
+ * (reference resamples node SRTs to regular steps, src/core/device/optix.cpp:400-471) */
+typedef struct KrrSRT { float s[3]; float q[4]; float t[3]; } KrrSRT;
+
+/* rt::InstanceData, reference src/core/mesh.h:37-58: mesh pointer + object->world transform
+ * (3x4 row-major, the layout of krr::Affine3f, src/core/math/include/krrmath/transform.h:12) */
+typedef struct KrrInstanceDesc {
+	int32_t		  mesh;
+	float		  transform[12];
+	int32_t		  n_motion_keys; /* 0/1 = static; >= 2: keys uniformly spaced over [starttime, endtime] */
+	const KrrSRT *motion_keys;
+} KrrInstanceDesc;
+
+/* analytic scene lights (point / directional / spot / infinite), reference src/core/light.h:30-259.
+ * Diffuse area lights are NOT listed here: like the reference (src/core/mesh.cpp:39-59) the pass
+ * creates one per triangle of every instance whose material has a constant emissive texture. */
+typedef struct KrrLightDesc {
+	int32_t		   type;  /* KRR_LIGHT_* (not DIFFUSE_AREA) */
+	float		   color[3];
+	float		   scale;
+	float		   transform[12]; /* node global transform: position = translation, direction = R * +Z */
+	float		   inner_cone_deg, outer_cone_deg;
+	float		   scene_radius;  /* root bounding-box diagonal length (src/core/light.cpp:20-21, 32-33) */
+	KrrTextureDesc texture;		  /* infinite light lat-long image (optional) */
+} KrrLightDesc;
+
+/* media: HomogeneousMedium / dense-grid stand-in for NanoVDBMedium<float>, reference src/render/media.h:108-227 */
+typedef struct KrrMediumDesc {
+	int32_t		 type; /* KRR_MEDIUM_* */
+	float		 sigma_t[3], albedo[3], Le[3];
+	float		 g;
+	/* grid medium */
+	float		 transform[12];	 /* medium -> world */
+	float		 bounds_min[3], bounds_max[3]; /* medium-space bounds of the density grid */
+	int32_t		 res[3];
+	const float *density;		 /* res[0]*res[1]*res[2], x fastest */
+	float		 scale;			 /* density scale */
+} KrrMediumDesc;
+
+/* OptixSceneParameters, reference src/core/device/scene.h:34-47 */
+typedef struct KrrSceneOptions {
+	int32_t animated, multilevel, motionblur;
+	float	starttime, endtime;
+} KrrSceneOptions;
+
+typedef struct KrrSceneDesc {
+	const KrrMeshDesc	  *meshes;	  int32_t n_meshes;
+	const KrrInstanceDesc *instances; int32_t n_instances;
+	const KrrMaterialDesc *materials; int32_t n_materials;
+	const KrrLightDesc	  *lights;	  int32_t n_lights;
+	const KrrMediumDesc	  *media;	  int32_t n_media;
+	KrrSceneOptions		   options;
+} KrrSceneDesc;
+
+/* rt::CameraData, reference src/core/camera.h:20-30 */
+typedef struct KrrCameraData {
+	float	film_size[2];
+	float	focal_length, focal_distance, lens_radius, aspect_ratio, shutter_open, shutter_time;
+	float	transform[12]; /* camera -> world, 3x4 row-major */
+	int32_t medium;		   /* index of the medium the camera is in, or -1 */
+} KrrCameraData;
+
+/* RGBColorSpace + RGBToSpectrumTable + CIE curves: global data the reference host application owns
+ * and hands to every pass (LaunchParameters::colorSpace, src/render/wavefront/wavefront.h:28;
+ * MaterialData::mColorSpace).  Layouts as reference src/render/color.h:113-114, spectrum.h:375-378. */
+typedef struct KrrColorSpaceData {
+	const float *cie_x, *cie_y, *cie_z; /* 471 samples, 360..830 nm, 1 nm step */
+	const float *illuminant;			/* 471 samples (normalised std illuminant, D65 for sRGB) */
+	float		 xyz_from_rgb[9], rgb_from_xyz[9]; /* row-major */
+	const float *z_nodes;				/* 64 */
+	const float *coeffs;				/* [3][64][64][64][3] */
+} KrrColorSpaceData;
+
+/* per-stage counters of the last render() (reference PROFILE() stage names, integrator.cpp:51-167) */
+#define KRR_MAX_DEPTH_STATS 64
+typedef struct KrrStats {
+	uint64_t camera_rays;
+	uint64_t closest_rays;	   /* items popped from the ray queues (primary + bounce) */
+	uint64_t shadow_rays;	   /* items popped from the shadow queue */
+	uint64_t scatter_items, hit_light_items, miss_items, medium_sample_items, medium_scatter_items;
+	uint64_t closest_by_depth[KRR_MAX_DEPTH_STATS];
+	uint64_t shadow_by_depth[KRR_MAX_DEPTH_STATS];
+	uint64_t kernel_launches;  /* kernels this handle launched in the last render()+begin_frame() */
+	uint64_t bvh_nodes, bvh_triangles, tlas_nodes;
+} KrrStats;
+
+typedef struct KrrWfpt KrrWfpt;
+
+/* WavefrontPathTracer() + from_json, integrator.h:29, 96-103.  params_json is the pass's "params"
+ * object: {"nee": true, "enable_medium": true, "max_depth": 10, "rr": 0.8, "enable_clamp": false,
+ * "clamp_max": 1000.0}; plus "spp" (samplesPerPixel, UI-only in the reference, integrator.h:80,
+ * integrator.cpp:271) -- NULL or "{}" gives the reference defaults. */
+int krr_wfpt_create(const char *params_json, KrrWfpt **out);
+void krr_wfpt_destroy(KrrWfpt *h);
+int krr_wfpt_set_params(KrrWfpt *h, const char *params_json);
+
+/* KRR_DEFAULT_COLORSPACE / spec::init, src/render/spectrum.cpp:107-157, 326-360 */
+int krr_wfpt_set_color_space(KrrWfpt *h, const KrrColorSpaceData *cs);
+
+/* WavefrontPathTracer::setScene, integrator.cpp:186-203 (scene upload device/scene.cpp:28-173 and
+ * acceleration-structure build device/optix.cpp:143-250, 357-398 happen inside). */
+int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *scene);
+
+/* WavefrontPathTracer::resize, integrator.cpp:181-184 */
+int krr_wfpt_resize(KrrWfpt *h, int32_t width, int32_t height);
+
+/* Scene::update -> RTScene::updateAccelStructure (TLAS refit), device/optix.cpp:346-354, 618-669.
+ * transforms: n x 12 floats (3x4 row-major). */
+int krr_wfpt_update_instances(KrrWfpt *h, const int32_t *instance_ids, const float *transforms, int32_t n, void *cuda_stream);
+
+/* WavefrontPathTracer::beginFrame, integrator.cpp:205-221.  frame_index is DeviceManager's frame
+ * counter (first frame is 1, src/core/window.cpp:457). */
+int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frame_index, const KrrCameraData *camera, void *cuda_stream);
+
+/* WavefrontPathTracer::render, integrator.cpp:223-267.  film: device pointer to width*height
+ * float4 (RGBA32F, alpha 1), row H-1-y like CudaRenderTarget::write (device/cuda.h:33-45). */
+int krr_wfpt_render(KrrWfpt *h, float *film_rgba_device, void *cuda_stream);
+
+/* Same, with a HOST film buffer: render + device->host copy + stream synchronise. */
+int krr_wfpt_render_to_host(KrrWfpt *h, float *film_rgba_host, void *cuda_stream);
+
+/* Multi-GPU work split by image tile (no reference counterpart: single device,
+ * device/context.cpp:37-40).  This handle renders pixel rows [row_begin,row_end) only; the other
+ * rows of the film are written as zeros, so films of disjoint tiles ADD to the full film.  The
+ * spp axis is split by FRAME: give each GPU its own frame_index (the reference accumulates spp
+ * across frames in AccumulatePass, accumulate.cu:30-79) and sum / average the films (NCCL). */
+int krr_wfpt_set_partition(KrrWfpt *h, int32_t row_begin, int32_t row_end);
+
+int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out);
+
+/* ---- parity / debug taps (read-only views of device state; used by tests and smoke) ---- */
+/* depth-0 hit per pixel of the LAST sample rendered: instance id and primitive id (-1 = miss) */
+int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *instance_ids_host, int32_t *prim_ids_host);
+/* PixelState after begin_frame (+ camera sample after render): sampler state (2 x u64), lambda[4],
+ * camera sample[5] per pixel; any pointer may be NULL */
+int krr_wfpt_debug_pixel_state(KrrWfpt *h, uint64_t *sampler_host, float *lambda_host, float *camera_sample_host);
+/* Capture integer fields of the queues at (sample_id, depth) during the next render(): call before
+ * render(); afterwards fetch with krr_wfpt_debug_queue.  queue: 0 ray(current), 1 miss, 2 hitLight,
+ * 3 scatter, 4 shadow, 5 next ray.  Fields per item: pixelId, depth, bsdfType, aux (light index /
+ * material type / -1).  Returns the item count (>= 0) or an error. */
+int krr_wfpt_debug_capture(KrrWfpt *h, int32_t sample_id, int32_t depth);
+int krr_wfpt_debug_queue(KrrWfpt *h, int32_t queue, int32_t *items4_host, int32_t capacity);
+
+/* ---- next row: AccumulatePass kernel, src/render/passes/accumulate/accumulate.cu:30-52 ----
+ * accum, film: device float4[n_pixels]; film is replaced by the running average. */
+int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,
+					   uint64_t max_accum_count, int32_t moving_average, void *cuda_stream);
+
+const char *krr_wfpt_last_error(void);
+int			krr_wfpt_abi_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRR_WFPT_H */

@@ -1,0 +1,365 @@
+"""ctypes mirror of include/krr_wfpt.h and include/krr_host_c.h (no logic, no fallback)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+KRR_MAX_DEPTH_STATS = 64
+KRR_TEX_COUNT = 5
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib_dir():
+    return os.path.join(_HERE, "lib")
+
+
+def data_dir():
+    return os.path.join(_HERE, "data")
+
+
+F, I32, U64, P = C.c_float, C.c_int32, C.c_uint64, C.c_void_p
+
+
+class KrrTextureDesc(C.Structure):
+    _fields_ = [("valid", I32), ("value", F * 4), ("image", C.POINTER(F)), ("width", I32), ("height", I32)]
+
+
+class KrrSpectrumDesc(C.Structure):
+    _fields_ = [("kind", I32), ("a", F * 3), ("b", F * 3), ("lambdas", C.POINTER(F)), ("values", C.POINTER(F)), ("n", I32)]
+
+
+class KrrMaterialDesc(C.Structure):
+    _fields_ = [("diffuse", F * 4), ("specular", F * 4), ("specular_transmission", F), ("anisotropic", F), ("ior", F),
+                ("spectral_eta", KrrSpectrumDesc), ("spectral_k", KrrSpectrumDesc), ("textures", KrrTextureDesc * KRR_TEX_COUNT),
+                ("bsdf_type", I32), ("shading_model", I32), ("color_space", I32)]
+
+
+class KrrMeshDesc(C.Structure):
+    _fields_ = [("positions", C.POINTER(F)), ("normals", C.POINTER(F)), ("texcoords", C.POINTER(F)), ("tangents", C.POINTER(F)),
+                ("indices", C.POINTER(I32)), ("n_vertices", I32), ("n_triangles", I32), ("material", I32),
+                ("medium_inside", I32), ("medium_outside", I32), ("Le", F * 3)]
+
+
+class KrrSRT(C.Structure):
+    _fields_ = [("s", F * 3), ("q", F * 4), ("t", F * 3)]
+
+
+class KrrInstanceDesc(C.Structure):
+    _fields_ = [("mesh", I32), ("transform", F * 12), ("n_motion_keys", I32), ("motion_keys", C.POINTER(KrrSRT))]
+
+
+class KrrLightDesc(C.Structure):
+    _fields_ = [("type", I32), ("color", F * 3), ("scale", F), ("transform", F * 12), ("inner_cone_deg", F),
+                ("outer_cone_deg", F), ("scene_radius", F), ("texture", KrrTextureDesc)]
+
+
+class KrrMediumDesc(C.Structure):
+    _fields_ = [("type", I32), ("sigma_t", F * 3), ("albedo", F * 3), ("Le", F * 3), ("g", F), ("transform", F * 12),
+                ("bounds_min", F * 3), ("bounds_max", F * 3), ("res", I32 * 3), ("density", C.POINTER(F)), ("scale", F)]
+
+
+class KrrSceneOptions(C.Structure):
+    _fields_ = [("animated", I32), ("multilevel", I32), ("motionblur", I32), ("starttime", F), ("endtime", F)]
+
+
+class KrrSceneDesc(C.Structure):
+    _fields_ = [("meshes", C.POINTER(KrrMeshDesc)), ("n_meshes", I32), ("instances", C.POINTER(KrrInstanceDesc)), ("n_instances", I32),
+                ("materials", C.POINTER(KrrMaterialDesc)), ("n_materials", I32), ("lights", C.POINTER(KrrLightDesc)), ("n_lights", I32),
+                ("media", C.POINTER(KrrMediumDesc)), ("n_media", I32), ("options", KrrSceneOptions)]
+
+
+class KrrCameraData(C.Structure):
+    _fields_ = [("film_size", F * 2), ("focal_length", F), ("focal_distance", F), ("lens_radius", F), ("aspect_ratio", F),
+                ("shutter_open", F), ("shutter_time", F), ("transform", F * 12), ("medium", I32)]
+
+
+class KrrColorSpaceData(C.Structure):
+    _fields_ = [("cie_x", C.POINTER(F)), ("cie_y", C.POINTER(F)), ("cie_z", C.POINTER(F)), ("illuminant", C.POINTER(F)),
+                ("xyz_from_rgb", F * 9), ("rgb_from_xyz", F * 9), ("z_nodes", C.POINTER(F)), ("coeffs", C.POINTER(F))]
+
+
+class KrrStats(C.Structure):
+    _fields_ = [("camera_rays", U64), ("closest_rays", U64), ("shadow_rays", U64), ("scatter_items", U64), ("hit_light_items", U64),
+                ("miss_items", U64), ("medium_sample_items", U64), ("medium_scatter_items", U64),
+                ("closest_by_depth", U64 * KRR_MAX_DEPTH_STATS), ("shadow_by_depth", U64 * KRR_MAX_DEPTH_STATS),
+                ("kernel_launches", U64), ("bvh_nodes", U64), ("bvh_triangles", U64), ("tlas_nodes", U64)]
+
+    def as_dict(self):
+        d = {k: int(getattr(self, k)) for k, _ in self._fields_ if not k.endswith("_by_depth")}
+        d["closest_by_depth"] = [int(v) for v in self.closest_by_depth]
+        d["shadow_by_depth"] = [int(v) for v in self.shadow_by_depth]
+        return d
+
+
+_wfpt = None
+_host = None
+
+
+def _load(name):
+    path = os.path.join(lib_dir(), name)
+    if not os.path.exists(path):
+        raise NativeLibraryMissing(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(the product has no CPU fallback)")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+def load_wfpt():
+    """libkrr_wfpt.so with argtypes set for every symbol include/krr_wfpt.h declares."""
+    global _wfpt
+    if _wfpt is not None:
+        return _wfpt
+    lib = _load("libkrr_wfpt.so")
+    lib.krr_wfpt_last_error.restype = C.c_char_p
+    sig = {
+        "krr_wfpt_create": [C.c_char_p, C.POINTER(P)],
+        "krr_wfpt_destroy": [P],
+        "krr_wfpt_set_params": [P, C.c_char_p],
+        "krr_wfpt_set_color_space": [P, C.POINTER(KrrColorSpaceData)],
+        "krr_wfpt_set_scene": [P, C.POINTER(KrrSceneDesc)],
+        "krr_wfpt_resize": [P, I32, I32],
+        "krr_wfpt_update_instances": [P, C.POINTER(I32), C.POINTER(F), I32, P],
+        "krr_wfpt_begin_frame": [P, U64, C.POINTER(KrrCameraData), P],
+        "krr_wfpt_render": [P, P, P],
+        "krr_wfpt_render_to_host": [P, P, P],
+        "krr_wfpt_set_partition": [P, I32, I32],
+        "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
+        "krr_wfpt_debug_first_hits": [P, P, P],
+        "krr_wfpt_debug_pixel_state": [P, P, P, P],
+        "krr_wfpt_debug_capture": [P, I32, I32],
+        "krr_wfpt_debug_queue": [P, I32, P, I32],
+        "krr_accumulate_f32": [P, P, C.c_int64, U64, U64, I32, P],
+        "krr_wfpt_abi_version": [],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = None if name == "krr_wfpt_destroy" else C.c_int
+    _wfpt = lib
+    return lib
+
+
+def load_host():
+    global _host
+    if _host is not None:
+        return _host
+    load_wfpt()
+    lib = _load("libkrr_host.so")
+    lib.krr_host_last_error.restype = C.c_char_p
+    lib.krr_host_app_create.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(P)]
+    lib.krr_host_app_destroy.argtypes = [P]
+    lib.krr_host_app_destroy.restype = None
+    lib.krr_host_app_get_resolution.argtypes = [P, C.POINTER(I32), C.POINTER(I32)]
+    lib.krr_host_app_set_resolution.argtypes = [P, I32, I32]
+    lib.krr_host_app_scene_desc.argtypes = [P]
+    lib.krr_host_app_scene_desc.restype = C.POINTER(KrrSceneDesc)
+    lib.krr_host_app_get_camera.argtypes = [P, C.c_double, C.POINTER(KrrCameraData)]
+    lib.krr_host_app_get_wfpt_params.argtypes = [P, C.c_char_p, I32]
+    lib.krr_host_app_set_wfpt_params.argtypes = [P, C.c_char_p]
+    lib.krr_host_app_render_frames.argtypes = [P, I32, P]
+    lib.krr_host_app_wfpt_handle.argtypes = [P]
+    lib.krr_host_app_wfpt_handle.restype = P
+    lib.krr_host_app_frame_index.argtypes = [P]
+    lib.krr_host_app_frame_index.restype = U64
+    lib.krr_host_set_data_dir.argtypes = [C.c_char_p]
+    lib.krr_host_set_data_dir(data_dir().encode())
+    _host = lib
+    return lib
+
+
+_cs_cache = None
+
+
+def color_space():
+    """sRGB colour-space tables (kiraray_b200/data/spectral_srgb.bin) as a KrrColorSpaceData."""
+    global _cs_cache
+    if _cs_cache is not None:
+        return _cs_cache[0]
+    path = os.path.join(data_dir(), "spectral_srgb.bin")
+    if not os.path.exists(path):
+        raise NativeLibraryMissing(f"{path} is missing (python oracle/build_oracle.py ref spectral)")
+    raw = np.fromfile(path, dtype=np.uint32, count=4)
+    assert raw[0] == 0x4B525253 and raw[2] == 471 and raw[3] == 64, "bad spectral_srgb.bin"
+    blob = np.fromfile(path, dtype=np.float32, offset=16)
+    cs = KrrColorSpaceData()
+    fp = lambda a: a.ctypes.data_as(C.POINTER(F))
+    parts = {"cie_x": blob[0:471], "cie_y": blob[471:942], "cie_z": blob[942:1413], "illuminant": blob[1413:1884]}
+    for k, v in parts.items():
+        setattr(cs, k, fp(v))
+    cs.xyz_from_rgb = (F * 9)(*blob[1884:1893])
+    cs.rgb_from_xyz = (F * 9)(*blob[1893:1902])
+    z = blob[1902:1966]
+    co = blob[1966:]
+    cs.z_nodes, cs.coeffs = fp(z), fp(co)
+    _cs_cache = (cs, blob)
+    return cs
+
+
+class HostApp:
+    """RenderApp of the C++ host layer (headless).  Loading a config touches no GPU."""
+
+    def __init__(self, config, asset_root=None):
+        self.lib = load_host()
+        self.h = P()
+        if isinstance(config, dict):
+            text, is_path = json.dumps(config).encode(), 0
+        else:
+            text, is_path = str(config).encode(), 1
+        root = asset_root.encode() if asset_root else (None if is_path else b".")
+        rc = self.lib.krr_host_app_create(text, is_path, root, C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError("krr_host_app_create: " + self.lib.krr_host_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.krr_host_app_destroy(self.h)
+            self.h = P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what}: {self.lib.krr_host_last_error().decode()}")
+        return rc
+
+    @property
+    def resolution(self):
+        w, h = I32(), I32()
+        self.lib.krr_host_app_get_resolution(self.h, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def set_resolution(self, w, h):
+        self._ck(self.lib.krr_host_app_set_resolution(self.h, w, h), "set_resolution")
+
+    def scene_desc(self):
+        p = self.lib.krr_host_app_scene_desc(self.h)
+        if not p:
+            raise RuntimeError(self.lib.krr_host_last_error().decode())
+        return p
+
+    def camera(self, time=0.0):
+        cam = KrrCameraData()
+        self._ck(self.lib.krr_host_app_get_camera(self.h, time, C.byref(cam)), "get_camera")
+        return cam
+
+    def wfpt_params(self):
+        buf = C.create_string_buffer(1024)
+        self._ck(self.lib.krr_host_app_get_wfpt_params(self.h, buf, 1024), "get_wfpt_params")
+        return json.loads(buf.value.decode())
+
+    def set_wfpt_params(self, **kw):
+        self._ck(self.lib.krr_host_app_set_wfpt_params(self.h, json.dumps(kw).encode()), "set_wfpt_params")
+
+    def render_frames(self, n=1):
+        w, h = self.resolution
+        film = np.empty((h, w, 4), dtype=np.float32)
+        self._ck(self.lib.krr_host_app_render_frames(self.h, n, film.ctypes.data_as(P)), "render_frames")
+        return film
+
+    def wfpt_handle(self):
+        return self.lib.krr_host_app_wfpt_handle(self.h)
+
+    @property
+    def frame_index(self):
+        return int(self.lib.krr_host_app_frame_index(self.h))
+
+
+class Wfpt:
+    """Thin wrapper over the C ABI handle (include/krr_wfpt.h)."""
+
+    def __init__(self, params=None, handle=None):
+        self.lib = load_wfpt()
+        self.owned = handle is None
+        self.h = P(handle) if handle is not None else P()
+        if handle is None:
+            text = json.dumps(params or {}).encode()
+            self._ck(self.lib.krr_wfpt_create(text, C.byref(self.h)), "create")
+            self._ck(self.lib.krr_wfpt_set_color_space(self.h, C.byref(color_space())), "set_color_space")
+        self.size = None
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"krr_wfpt_{what}: {self.lib.krr_wfpt_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if self.owned and self.h:
+            self.lib.krr_wfpt_destroy(self.h)
+        self.h = P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, **kw):
+        self._ck(self.lib.krr_wfpt_set_params(self.h, json.dumps(kw).encode()), "set_params")
+
+    def set_scene(self, desc_ptr):
+        self._ck(self.lib.krr_wfpt_set_scene(self.h, desc_ptr), "set_scene")
+
+    def resize(self, w, h):
+        self._ck(self.lib.krr_wfpt_resize(self.h, w, h), "resize")
+        self.size = (w, h)
+        self.rows = (0, h)
+
+    def set_partition(self, r0, r1):
+        self._ck(self.lib.krr_wfpt_set_partition(self.h, r0, r1), "set_partition")
+        self.rows = (r0, r1)
+
+    def begin_frame(self, frame_index, cam, stream=None):
+        self._ck(self.lib.krr_wfpt_begin_frame(self.h, frame_index, C.byref(cam), P(stream or 0)), "begin_frame")
+
+    def render(self, film_device_ptr, stream=None):
+        self._ck(self.lib.krr_wfpt_render(self.h, P(film_device_ptr), P(stream or 0)), "render")
+
+    def render_to_host(self, film=None, stream=None):
+        w, h = self.size
+        if film is None:
+            film = np.empty((h, w, 4), dtype=np.float32)
+        self._ck(self.lib.krr_wfpt_render_to_host(self.h, film.ctypes.data_as(P), P(stream or 0)), "render_to_host")
+        return film
+
+    def update_instances(self, ids, transforms, stream=None):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        xf = np.ascontiguousarray(transforms, dtype=np.float32).reshape(-1, 12)
+        self._ck(self.lib.krr_wfpt_update_instances(self.h, ids.ctypes.data_as(C.POINTER(I32)), xf.ctypes.data_as(C.POINTER(F)),
+                                                    len(ids), P(stream or 0)), "update_instances")
+
+    def stats(self):
+        s = KrrStats()
+        self._ck(self.lib.krr_wfpt_get_stats(self.h, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+    def _npix(self):
+        return (self.rows[1] - self.rows[0]) * self.size[0]
+
+    def first_hits(self):
+        n = self._npix()
+        inst, prim = np.empty(n, np.int32), np.empty(n, np.int32)
+        self._ck(self.lib.krr_wfpt_debug_first_hits(self.h, inst.ctypes.data_as(P), prim.ctypes.data_as(P)), "debug_first_hits")
+        return inst, prim
+
+    def pixel_state(self):
+        n = self._npix()
+        s, l, c = np.empty((n, 2), np.uint64), np.empty((n, 4), np.float32), np.empty((n, 5), np.float32)
+        self._ck(self.lib.krr_wfpt_debug_pixel_state(self.h, s.ctypes.data_as(P), l.ctypes.data_as(P), c.ctypes.data_as(P)), "debug_pixel_state")
+        return s, l, c
+
+    def capture(self, sample_id, depth):
+        self._ck(self.lib.krr_wfpt_debug_capture(self.h, sample_id, depth), "debug_capture")
+
+    def queue(self, q):
+        n = self._npix()
+        items = np.empty((n, 4), np.int32)
+        cnt = self._ck(self.lib.krr_wfpt_debug_queue(self.h, q, items.ctypes.data_as(P), n), "debug_queue")
+        return items[:cnt].copy()

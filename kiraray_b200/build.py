@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""In-tree build of the product libraries (sm_100a only).
+
+  kiraray_b200/lib/libkrr_wfpt.so  CUDA kernels + C ABI (include/krr_wfpt.h)          [nvcc]
+  kiraray_b200/lib/libkrr_host.so  C++17 host layer (RenderPass surface, importers)  [g++]
+  kiraray_b200/lib/krr_render      headless CLI driver (same JSON configs as the reference)
+
+nvcc cross-compiles without a GPU.  The .so files are git-ignored but travel to the GPU box.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "lib")
+OBJ = os.path.join(LIB, "obj")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("CXX", "g++")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda",
+                  "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v",
+                  "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
+CU_SRCS = ["api.cu", "bvh_build.cu"]
+HOST_SRCS = ["scene.cpp", "passes.cpp", "host_c_api.cpp"]
+
+
+def run(cmd, log=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log:
+        open(log, "w").write(r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout[-8000:] + "\n")
+        raise RuntimeError("build step failed: " + " ".join(cmd[-3:]))
+    return r.stdout
+
+
+def newer(dst, srcs):
+    if not os.path.exists(dst):
+        return False
+    t = os.path.getmtime(dst)
+    return all(os.path.getmtime(s) <= t for s in srcs if os.path.exists(s))
+
+
+def deps(dirs):
+    out = []
+    for d in dirs:
+        for f in os.listdir(d):
+            if f.endswith((".h", ".cuh", ".cu", ".cpp")):
+                out.append(os.path.join(d, f))
+    return out
+
+
+def build(force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = deps([os.path.join(HERE, "csrc"), os.path.join(HERE, "host"), os.path.join(ROOT, "include")])
+
+    def cu(src):
+        s = os.path.join(HERE, "csrc", src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or not newer(o, hdrs):
+            run([NVCC] + NVFLAGS + ["-c", s, "-o", o], log=os.path.join(OBJ, src + ".ptxas.log"))
+        return o
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(cu, CU_SRCS))
+    wfpt = os.path.join(LIB, "libkrr_wfpt.so")
+    if force or not newer(wfpt, objs):
+        run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o", wfpt] + objs)
+    # exported symbols: the C ABI only (visibility hidden + extern "C" default) -> mark explicitly
+    host = os.path.join(LIB, "libkrr_host.so")
+    hsrcs = [os.path.join(HERE, "host", s) for s in HOST_SRCS]
+    if force or not newer(host, hsrcs + hdrs + [wfpt]):
+        run([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
+             "-I", "/usr/local/cuda/include", "-o", host] + hsrcs +
+            ["-L", LIB, "-lkrr_wfpt", "-L", "/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-pthread",
+             "-Wl,-rpath,$ORIGIN"])
+    cli_src = os.path.join(HERE, "host", "krr_render.cpp")
+    cli = os.path.join(LIB, "krr_render")
+    if os.path.exists(cli_src) and (force or not newer(cli, [cli_src, host])):
+        run([CXX, "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", cli, cli_src,
+             "-L", LIB, "-lkrr_host", "-lkrr_wfpt", "-Wl,-rpath,$ORIGIN"])
+    return wfpt, host
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)
+    print("built", LIB)

@@ -1,0 +1,716 @@
+// api.cu -- handle, scene upload, stage driver and the C ABI (include/krr_wfpt.h).
+// Host code is C++17 compiled by nvcc's host compiler; everything the caller sees is extern "C".
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/json.h"
+#include "bvh_build.h"
+#include "krr_wfpt.h"
+#include "wavefront_kernels.cuh"
+
+using namespace krr;
+
+namespace {
+
+thread_local char gErr[512] = "";
+int fail(int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(gErr, sizeof gErr, fmt, ap);
+	va_end(ap);
+	return code;
+}
+#define CUDA_OK(x)                                                                                         \
+	do {                                                                                                   \
+		cudaError_t e_ = (x);                                                                              \
+		if (e_ != cudaSuccess) return fail(KRR_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));       \
+	} while (0)
+
+template <typename T> struct Buf {
+	T *p	 = nullptr;
+	size_t n = 0;
+	int alloc(size_t count) {
+		if (count == n && p) return KRR_OK;
+		release();
+		n = count;
+		if (cudaMalloc((void **) &p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) {
+			p = nullptr, n = 0;
+			cudaGetLastError();
+			return fail(KRR_E_CUDA, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+		}
+		return KRR_OK;
+	}
+	int upload(const std::vector<T> &h) {
+		int rc = alloc(h.size());
+		if (rc) return rc;
+		if (!h.empty()) CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+		return KRR_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	~Buf() { release(); }
+};
+
+// Affine inverse: cofactors in double, rounded once (the intersection spec; identical to
+// oracle/driver.cpp xfInverse so object-space rays agree bit-for-bit)
+Xf xfInverse(const Xf &t) {
+	double a = t.m[0], b = t.m[1], c = t.m[2], d = t.m[4], e = t.m[5], f = t.m[6], g = t.m[8], h = t.m[9], i = t.m[10];
+	double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+	double det = a * A + b * B + c * C;
+	double id  = 1.0 / det;
+	double r[9] = {A * id, -(b * i - c * h) * id, (b * f - c * e) * id, B * id, (a * i - c * g) * id, -(a * f - c * d) * id,
+				   C * id, -(a * h - b * g) * id, (a * e - b * d) * id};
+	double tx = t.m[3], ty = t.m[7], tz = t.m[11];
+	Xf o;
+	for (int k = 0; k < 3; k++) {
+		o.m[k * 4 + 0] = (float) r[k * 3 + 0];
+		o.m[k * 4 + 1] = (float) r[k * 3 + 1];
+		o.m[k * 4 + 2] = (float) r[k * 3 + 2];
+		o.m[k * 4 + 3] = (float) -(r[k * 3 + 0] * tx + r[k * 3 + 1] * ty + r[k * 3 + 2] * tz);
+	}
+	return o;
+}
+
+} // namespace
+
+struct KrrWfpt {
+	int device = 0;
+	// params (integrator.h:78-88)
+	int spp = 1, maxDepth = 10;
+	float probRR = 0.8f, clampMax = 1e3f;
+	bool nee = true, enableMedium = true, enableClamp = false;
+	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
+	bool haveScene = false, haveColorSpace = false, frameBegun = false;
+	uint64_t frameIndex = 0;
+	int numSMs = 148;
+
+	// colour space
+	Buf<float> csData;
+	ColorSpaceDev cs{};
+	std::vector<float> csHost; // host copy of zNodes + coeffs for upload-time conversions
+	// scene
+	Buf<float> positions, normals, texcoords, tangents, densityPool, spectrumTables, motionKeys;
+	Buf<int32_t> indices, infiniteLights;
+	Buf<MeshRec> meshes;
+	Buf<InstRec> instances;
+	Buf<MatRec> materials;
+	Buf<LightRec> lights;
+	Buf<TriLightRec> triLights;
+	Buf<AnalyticLightRec> analytic;
+	Buf<MediumRec> media;
+	Buf<float4> texels;
+	Buf<MotionRec> motions;
+	Buf<uint8_t> instFlags;
+	std::vector<InstRec> hInstances;
+	std::vector<MeshRec> hMeshes;
+	SceneDev scene{};
+	BvhBuilder bvh;
+	bool matTypePresent[MAT_COUNT] = {false, false, false, false, false};
+	bool sceneHasMedia = false;
+	// wavefront state
+	Buf<float4> L, pixel, rayBuf[2][7], shadowBuf[5];
+	Buf<uint64_t> rng;
+	Buf<float> lambda, cameraSample;
+	Buf<int4> hits, firstHits;
+	Buf<int32_t> missIdx, hitLightIdx, scatterIdx[MAT_COUNT], errorFlags;
+	Buf<DepthCounters> counters;
+	Buf<StatTotals> totals;
+	KrrCameraDev cam{};
+	bool debugState = true; // keep camera samples / first hits (16+20 B per pixel; negligible traffic)
+	// debug capture
+	int capSample = -1, capDepth = -1;
+	Buf<int4> capItems[6];
+	Buf<int32_t> capCounts;
+	uint64_t launches = 0;
+	cudaStream_t lastStream = nullptr;
+
+	int pixelCount() const { return (rowEnd - rowBegin) * width; }
+};
+
+namespace {
+
+int parseParams(KrrWfpt *h, const char *text) {
+	if (!text || !*text) return KRR_OK;
+	try {
+		Json j = Json::parse(text);
+		if (!j.isObject()) return fail(KRR_E_INVALID, "params must be a JSON object");
+		h->nee			= j.value("nee", h->nee);
+		h->enableMedium = j.value("enable_medium", h->enableMedium);
+		h->maxDepth		= j.value("max_depth", h->maxDepth);
+		h->probRR		= j.value("rr", h->probRR);
+		h->enableClamp	= j.value("enable_clamp", h->enableClamp);
+		h->clampMax		= j.value("clamp_max", h->clampMax);
+		h->spp			= j.value("spp", h->spp);
+	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
+	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
+	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
+	if (!(h->probRR > 0.f && h->probRR <= 1.f)) return fail(KRR_E_INVALID, "rr must be in (0, 1]");
+	return KRR_OK;
+}
+
+int allocState(KrrWfpt *h) {
+	const size_t n = (size_t) h->pixelCount();
+	int rc = 0;
+	rc |= h->L.alloc(n) | h->pixel.alloc(n) | h->rng.alloc(n) | h->lambda.alloc(n) | h->hits.alloc(n);
+	if (h->debugState) rc |= h->cameraSample.alloc(5 * n) | h->firstHits.alloc(n);
+	for (int q = 0; q < 2; q++) for (int a = 0; a < 7; a++) rc |= h->rayBuf[q][a].alloc(n);
+	for (int a = 0; a < 5; a++) rc |= h->shadowBuf[a].alloc(n);
+	rc |= h->missIdx.alloc(n) | h->hitLightIdx.alloc(n);
+	for (int m = 0; m < MAT_COUNT; m++) rc |= h->scatterIdx[m].alloc(n);
+	rc |= h->counters.alloc(kMaxDepthSlots) | h->totals.alloc(1) | h->errorFlags.alloc(4);
+	if (rc) return KRR_E_CUDA;
+	CUDA_OK(cudaMemset(h->counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
+	CUDA_OK(cudaMemset(h->totals.p, 0, sizeof(StatTotals)));
+	CUDA_OK(cudaMemset(h->errorFlags.p, 0, 16));
+	return KRR_OK;
+}
+
+TexRec makeTex(const KrrTextureDesc &t, std::vector<float4> &texels) {
+	TexRec r{};
+	memcpy(r.value, t.value, 16);
+	r.valid	 = t.valid;
+	r.texOff = -1;
+	if (t.valid && t.image && t.width > 0 && t.height > 0) {
+		r.texOff = (int32_t) texels.size();
+		r.width = t.width, r.height = t.height;
+		for (int i = 0; i < t.width * t.height; i++) texels.push_back(make_float4(t.image[4 * i], t.image[4 * i + 1], t.image[4 * i + 2], t.image[4 * i + 3]));
+	}
+	return r;
+}
+
+SpectrumRec makeSpectrum(const KrrSpectrumDesc &s, std::vector<float> &tables) {
+	SpectrumRec r{};
+	r.kind = s.kind;
+	memcpy(r.a, s.a, 12), memcpy(r.b, s.b, 12);
+	if (s.kind == KRR_SPEC_TABULATED && s.n > 0) {
+		r.tabOff = (int32_t) tables.size(), r.n = s.n;
+		tables.insert(tables.end(), s.lambdas, s.lambdas + s.n);
+		tables.insert(tables.end(), s.values, s.values + s.n);
+	}
+	return r;
+}
+
+Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
+	Wavefront wf{};
+	wf.p.width = h->width, wf.p.height = h->height;
+	wf.p.pixelBegin = h->rowBegin * h->width, wf.p.pixelCount = h->pixelCount();
+	wf.p.spp = h->spp, wf.p.maxDepth = h->maxDepth, wf.p.nee = h->nee;
+	wf.p.enableMedium = h->enableMedium && h->sceneHasMedia; // integrator.cpp:200
+	wf.p.enableClamp = h->enableClamp, wf.p.probRR = h->probRR, wf.p.clampMax = h->clampMax;
+	uint32_t seedIndex = (uint32_t) (h->frameIndex * (uint64_t) h->spp);
+	wf.p.rngInc		 = ((uint64_t) seedIndex << 1u) | 1u;
+	wf.p.sampleIndex = (uint32_t) sampleId;
+	wf.cam	 = h->cam;
+	wf.scene = h->scene;
+	wf.bvh	 = h->bvh.device();
+	wf.px.L = h->L.p, wf.px.pixel = h->pixel.p, wf.px.rng = h->rng.p, wf.px.lambda = h->lambda.p;
+	wf.px.cameraSample = h->debugState ? h->cameraSample.p : nullptr;
+	for (int q = 0; q < 2; q++) {
+		RayQueue &r = wf.rays[q];
+		r.o_time = h->rayBuf[q][0].p, r.d_medium = h->rayBuf[q][1].p, r.thp = h->rayBuf[q][2].p, r.pu = h->rayBuf[q][3].p;
+		r.pl = h->rayBuf[q][4].p, r.ctxP_pix = h->rayBuf[q][5].p, r.ctxN_dep = h->rayBuf[q][6].p;
+	}
+	wf.hits = h->hits.p;
+	wf.missIdx = h->missIdx.p, wf.hitLightIdx = h->hitLightIdx.p;
+	for (int m = 0; m < MAT_COUNT; m++) wf.scatterIdx[m] = h->scatterIdx[m].p;
+	wf.shadow.o_tmax = h->shadowBuf[0].p, wf.shadow.d_pix = h->shadowBuf[1].p, wf.shadow.contrib = h->shadowBuf[2].p;
+	wf.shadow.pu = h->shadowBuf[3].p, wf.shadow.pl = h->shadowBuf[4].p;
+	wf.counters	  = h->counters.p;
+	wf.firstHits  = h->debugState ? h->firstHits.p : nullptr;
+	wf.errorFlags = h->errorFlags.p;
+	wf.instFlags  = h->instFlags.p;
+	return wf;
+}
+
+template <typename K> int gridFor(KrrWfpt *h, K kernel, int block) {
+	int occ = 1;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0);
+	if (occ < 1) occ = 1;
+	return h->numSMs * occ; // a whole number of waves: every SM gets the same number of resident CTAs
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" const char *krr_wfpt_last_error(void) { return gErr; }
+extern "C" int krr_wfpt_abi_version(void) { return KRR_WFPT_ABI_VERSION; }
+
+extern "C" int krr_wfpt_create(const char *params_json, KrrWfpt **out) {
+	if (!out) return fail(KRR_E_INVALID, "out is null");
+	*out = nullptr;
+	int dev = 0;
+	CUDA_OK(cudaGetDevice(&dev));
+	KrrWfpt *h = new KrrWfpt();
+	h->device  = dev;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
+	int rc = parseParams(h, params_json);
+	if (rc) { delete h; return rc; }
+	*out = h;
+	return KRR_OK;
+}
+
+extern "C" void krr_wfpt_destroy(KrrWfpt *h) {
+	if (!h) return;
+	cudaDeviceSynchronize();
+	delete h;
+}
+
+extern "C" int krr_wfpt_set_params(KrrWfpt *h, const char *params_json) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	return parseParams(h, params_json);
+}
+
+extern "C" int krr_wfpt_set_color_space(KrrWfpt *h, const KrrColorSpaceData *c) {
+	if (!h || !c || !c->cie_x || !c->cie_y || !c->cie_z || !c->illuminant || !c->z_nodes || !c->coeffs)
+		return fail(KRR_E_INVALID, "null colour-space data");
+	const size_t nCo = (size_t) 3 * 64 * 64 * 64 * 3;
+	std::vector<float> blob(4 * 471 + 64 + nCo);
+	memcpy(&blob[0], c->cie_x, 471 * 4), memcpy(&blob[471], c->cie_y, 471 * 4), memcpy(&blob[942], c->cie_z, 471 * 4);
+	memcpy(&blob[1413], c->illuminant, 471 * 4);
+	memcpy(&blob[1884], c->z_nodes, 64 * 4), memcpy(&blob[1948], c->coeffs, nCo * 4);
+	int rc = h->csData.upload(blob);
+	if (rc) return rc;
+	h->cs.cieX = h->csData.p, h->cs.cieY = h->csData.p + 471, h->cs.cieZ = h->csData.p + 942, h->cs.illum = h->csData.p + 1413;
+	h->cs.zNodes = h->csData.p + 1884, h->cs.coeffs = h->csData.p + 1948;
+	memcpy(h->cs.rgbFromXyz, c->rgb_from_xyz, 36);
+	h->csHost.assign(blob.begin() + 1884, blob.end());
+	h->haveColorSpace = true;
+	h->scene.cs		  = h->cs;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
+	if (!h || !d) return fail(KRR_E_INVALID, "null argument");
+	if (!h->haveColorSpace) return fail(KRR_E_STATE, "krr_wfpt_set_color_space must be called before set_scene");
+	if (d->n_meshes <= 0 || d->n_instances <= 0) return fail(KRR_E_INVALID, "scene has no geometry");
+	CUDA_OK(cudaSetDevice(h->device));
+	const float *zn = h->csHost.data(), *co = h->csHost.data() + 64;
+	std::vector<float> P, N, UV, T, density, specTables, motionKeys;
+	std::vector<int32_t> I;
+	std::vector<float4> texels;
+	std::vector<MeshRec> meshes(d->n_meshes);
+	for (int i = 0; i < d->n_meshes; i++) {
+		const KrrMeshDesc &m = d->meshes[i];
+		if (!m.positions || !m.indices || m.n_vertices <= 0 || m.n_triangles <= 0) return fail(KRR_E_INVALID, "mesh %d is empty", i);
+		if (m.material >= d->n_materials) return fail(KRR_E_INVALID, "mesh %d: material index out of range", i);
+		for (int k = 0; k < 3 * m.n_triangles; k++)
+			if (m.indices[k] < 0 || m.indices[k] >= m.n_vertices) return fail(KRR_E_INVALID, "mesh %d: vertex index out of range", i);
+		MeshRec r{};
+		r.posOff = (int32_t) (P.size() / 3), r.idxOff = (int32_t) (I.size() / 3);
+		r.nrmOff = m.normals ? (int32_t) (N.size() / 3) : -1;
+		r.uvOff	 = m.texcoords ? (int32_t) (UV.size() / 2) : -1;
+		r.tanOff = m.tangents ? (int32_t) (T.size() / 3) : -1;
+		r.nTri = m.n_triangles, r.material = m.material, r.mediumIn = m.medium_inside, r.mediumOut = m.medium_outside;
+		P.insert(P.end(), m.positions, m.positions + 3 * (size_t) m.n_vertices);
+		if (m.normals) N.insert(N.end(), m.normals, m.normals + 3 * (size_t) m.n_vertices);
+		if (m.texcoords) UV.insert(UV.end(), m.texcoords, m.texcoords + 2 * (size_t) m.n_vertices);
+		if (m.tangents) T.insert(T.end(), m.tangents, m.tangents + 3 * (size_t) m.n_vertices);
+		I.insert(I.end(), m.indices, m.indices + 3 * (size_t) m.n_triangles);
+		meshes[i] = r;
+	}
+	// materials (MaterialData::getObjectData, texture.cpp:254-268)
+	std::vector<MatRec> mats(std::max(d->n_materials, 0));
+	for (int m = 0; m < MAT_COUNT; m++) h->matTypePresent[m] = false;
+	for (int i = 0; i < d->n_materials; i++) {
+		const KrrMaterialDesc &m = d->materials[i];
+		if (m.color_space != 0) return fail(KRR_E_UNSUPPORTED, "material %d: only the sRGB colour space is supported", i);
+		if (m.bsdf_type < 0 || m.bsdf_type >= MAT_COUNT) return fail(KRR_E_INVALID, "material %d: bad bsdf_type", i);
+		MatRec r{};
+		memcpy(r.diffuse, m.diffuse, 16), memcpy(r.specular, m.specular, 16);
+		r.specularTransmission = m.specular_transmission, r.anisotropic = m.anisotropic, r.ior = m.ior;
+		r.bsdfType = m.bsdf_type, r.shadingModel = m.shading_model;
+		for (int t = 0; t < 5; t++) r.tex[t] = makeTex(m.textures[t], texels);
+		r.eta = makeSpectrum(m.spectral_eta, specTables), r.k = makeSpectrum(m.spectral_k, specTables);
+		// constant diffuse/specular -> final RGBs and their sigmoid coefficients at upload
+		bool constD = !r.tex[0].valid || r.tex[0].texOff < 0, constS = !r.tex[1].valid || r.tex[1].texOff < 0;
+		r.constColours = constD && constS;
+		if (r.constColours) {
+			const float *dv = r.tex[0].valid ? r.tex[0].value : r.diffuse, *sv = r.tex[1].valid ? r.tex[1].value : r.specular;
+			memcpy(r.constDiffuse, dv, 12), memcpy(r.constSpecular, sv, 16);
+			float dr[3], sr[3];
+			if (r.shadingModel == KRR_SHADING_METALLIC_ROUGHNESS)
+				for (int k = 0; k < 3; k++) dr[k] = dv[k] * (1 - sv[2]) + 0.f * sv[2], sr[k] = 0.f * (1 - sv[2]) + dv[k] * sv[2];
+			else
+				for (int k = 0; k < 3; k++) dr[k] = dv[k], sr[k] = sv[k];
+			r.diffuseSpec  = makeBounded(zn, co, dr[0], dr[1], dr[2]);
+			r.specularSpec = makeBounded(zn, co, sr[0], sr[1], sr[2]);
+		}
+		h->matTypePresent[r.bsdfType] = true;
+		mats[i] = r;
+	}
+	// media
+	std::vector<MediumRec> media(std::max(d->n_media, 0));
+	for (int i = 0; i < d->n_media; i++) {
+		const KrrMediumDesc &m = d->media[i];
+		MediumRec r{};
+		r.type = m.type;
+		memcpy(r.sigma_t, m.sigma_t, 12), memcpy(r.albedo, m.albedo, 12), memcpy(r.Le, m.Le, 12);
+		r.g = m.g;
+		r.sigmaTSpec  = makeUnbounded(zn, co, m.sigma_t[0], m.sigma_t[1], m.sigma_t[2]);
+		r.albedoUSpec = makeUnbounded(zn, co, m.albedo[0], m.albedo[1], m.albedo[2]);
+		r.albedoBSpec = makeBounded(zn, co, m.albedo[0], m.albedo[1], m.albedo[2]);
+		r.LeSpec	  = makeUnbounded(zn, co, m.Le[0], m.Le[1], m.Le[2]);
+		memcpy(r.xf.m, m.transform, 48);
+		r.inv = xfInverse(r.xf);
+		memcpy(r.boundsMin, m.bounds_min, 12), memcpy(r.boundsMax, m.bounds_max, 12), memcpy(r.res, m.res, 12);
+		r.scale = m.scale;
+		r.densityOff = r.majorantOff = -1;
+		if (m.type == KRR_MEDIUM_GRID) {
+			if (!m.density || m.res[0] <= 0 || m.res[1] <= 0 || m.res[2] <= 0) return fail(KRR_E_INVALID, "medium %d: grid medium without density data", i);
+			r.densityOff = (int32_t) density.size();
+			density.insert(density.end(), m.density, m.density + (size_t) m.res[0] * m.res[1] * m.res[2]);
+		}
+		media[i] = r;
+	}
+	h->sceneHasMedia = d->n_media > 0;
+	// instances (InstanceData::getObjectData, mesh.cpp:16-63) + mesh lights (scene.cpp:91-112)
+	std::vector<InstRec> insts(d->n_instances);
+	std::vector<LightRec> lights;
+	std::vector<TriLightRec> triLights;
+	std::vector<uint8_t> flags(d->n_instances, 0);
+	std::vector<MotionRec> motions;
+	bool anyMotion = false;
+	for (int i = 0; i < d->n_instances; i++) {
+		const KrrInstanceDesc &in = d->instances[i];
+		if (in.mesh < 0 || in.mesh >= d->n_meshes) return fail(KRR_E_INVALID, "instance %d: mesh index out of range", i);
+		InstRec r{};
+		memcpy(r.xf.m, in.transform, 48);
+		r.inv = xfInverse(r.xf);
+		r.mesh = in.mesh, r.lightBase = -1, r.motion = -1;
+		if (d->options.motionblur && in.n_motion_keys >= 2 && in.motion_keys) {
+			r.motion = (int32_t) motions.size();
+			motions.push_back(MotionRec{(int32_t) (motionKeys.size() / 10), in.n_motion_keys});
+			for (int k = 0; k < in.n_motion_keys; k++) {
+				const KrrSRT &s = in.motion_keys[k];
+				motionKeys.insert(motionKeys.end(), s.s, s.s + 3);
+				motionKeys.insert(motionKeys.end(), s.q, s.q + 4);
+				motionKeys.insert(motionKeys.end(), s.t, s.t + 3);
+			}
+			anyMotion = true;
+		}
+		const KrrMeshDesc &m = d->meshes[in.mesh];
+		if (m.material < 0) flags[i] |= 1;
+		else if (d->materials[m.material].textures[KRR_TEX_TRANSMISSION].valid) flags[i] |= 2;
+		bool emissiveTex = m.material >= 0 && d->materials[m.material].textures[KRR_TEX_EMISSIVE].valid;
+		bool emissive	 = emissiveTex || m.Le[0] != 0 || m.Le[1] != 0 || m.Le[2] != 0;
+		if (emissive) {
+			r.lightBase = (int32_t) lights.size();
+			float Le[3];
+			if (emissiveTex) memcpy(Le, d->materials[m.material].textures[KRR_TEX_EMISSIVE].value, 12);
+			else memcpy(Le, m.Le, 12);
+			float scale = std::max(Le[0], std::max(Le[1], Le[2]));
+			// DiffuseAreaLight::L evaluates the emissive texture when it is valid (un-normalised
+			// colour), otherwise the normalised Le; both are multiplied by scale (light.h:183-188)
+			if (!emissiveTex) for (float &c : Le) c /= scale;
+			RgbSpectrum LeSpec = makeUnbounded(zn, co, Le[0], Le[1], Le[2]);
+			for (int t = 0; t < m.n_triangles; t++) {
+				TriLightRec tl{};
+				for (int c = 0; c < 3; c++) {
+					int v = m.indices[3 * t + c];
+					memcpy(tl.p[c], m.positions + 3 * v, 12);
+					if (m.normals) memcpy(tl.n[c], m.normals + 3 * v, 12);
+				}
+				tl.inst = i, tl.scale = scale, tl.LeSpec = LeSpec, tl.twoSided = 0, tl.hasNormals = m.normals ? 1 : 0;
+				memcpy(tl.Le, Le, 12);
+				lights.push_back(LightRec{LIGHT_DIFFUSE_AREA, (int32_t) triLights.size()});
+				triLights.push_back(tl);
+			}
+		}
+		insts[i] = r;
+	}
+	// analytic lights, after the mesh lights (scene.cpp:114-132)
+	std::vector<AnalyticLightRec> analytic;
+	std::vector<int32_t> infinite;
+	for (int i = 0; i < d->n_lights; i++) {
+		const KrrLightDesc &l = d->lights[i];
+		if (l.type == KRR_LIGHT_DIFFUSE_AREA || l.type < 0 || l.type > KRR_LIGHT_INFINITE) return fail(KRR_E_INVALID, "light %d: bad type", i);
+		AnalyticLightRec r{};
+		r.type = l.type;
+		memcpy(r.color, l.color, 12);
+		r.scale = l.scale;
+		r.position[0] = l.transform[3], r.position[1] = l.transform[7], r.position[2] = l.transform[11];
+		for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) r.rotation[a * 3 + b] = l.transform[a * 4 + b];
+		r.sceneRadius = l.scene_radius;
+		r.cosInner = std::cos(l.inner_cone_deg * 3.14159265358979323846f / 180.f);
+		r.cosOuter = std::cos(l.outer_cone_deg * 3.14159265358979323846f / 180.f);
+		memcpy(r.xf.m, l.transform, 48);
+		r.inv = xfInverse(r.xf);
+		r.image = makeTex(l.texture, texels);
+		float tint[3] = {l.color[0], l.color[1], l.color[2]};
+		if (l.type == KRR_LIGHT_INFINITE) {
+			// uploaded through the texture constructor: tint = 1, colour comes from the (constant)
+			// texture if there is one (light.cpp:28-41, light.h:213-216)
+			if (r.image.valid && r.image.texOff < 0) { tint[0] = r.image.value[0], tint[1] = r.image.value[1], tint[2] = r.image.value[2]; r.image.valid = 0; }
+			else if (!r.image.valid) tint[0] = tint[1] = tint[2] = 1.f;
+			else { r.color[0] = r.color[1] = r.color[2] = 1.f; }
+			infinite.push_back((int32_t) analytic.size());
+		}
+		r.colorSpec = makeUnbounded(zn, co, tint[0], tint[1], tint[2]);
+		lights.push_back(LightRec{l.type, (int32_t) analytic.size()});
+		analytic.push_back(r);
+	}
+	int rc = 0;
+	rc |= h->positions.upload(P) | h->normals.upload(N) | h->texcoords.upload(UV) | h->tangents.upload(T) | h->indices.upload(I);
+	rc |= h->densityPool.upload(density) | h->spectrumTables.upload(specTables) | h->motionKeys.upload(motionKeys) | h->motions.upload(motions);
+	rc |= h->texels.upload(texels) | h->materials.upload(mats) | h->media.upload(media);
+	rc |= h->lights.upload(lights) | h->triLights.upload(triLights) | h->analytic.upload(analytic) | h->infiniteLights.upload(infinite);
+	rc |= h->instFlags.upload(flags);
+	if (rc) return KRR_E_CUDA;
+	// acceleration structures
+	rc = h->instances.upload(insts);
+	if (rc) return rc;
+	char err[256] = "";
+	if (!h->bvh.build(h->positions.p, h->indices.p, meshes.data(), d->n_meshes, h->instances.p, insts.data(), d->n_instances, nullptr, err))
+		return fail(KRR_E_CUDA, "%s", err);
+	for (int i = 0; i < d->n_meshes; i++) meshes[i].blasRoot = h->bvh.blasRoot(i), meshes[i].triBase = h->bvh.triBase(i);
+	for (int i = 0; i < d->n_instances; i++) insts[i].blasRoot = meshes[insts[i].mesh].blasRoot;
+	rc = h->instances.upload(insts) | h->meshes.upload(meshes);
+	if (rc) return KRR_E_CUDA;
+	h->hInstances = insts, h->hMeshes = meshes;
+	SceneDev &s = h->scene;
+	s.positions = h->positions.p, s.normals = h->normals.p, s.texcoords = h->texcoords.p, s.tangents = h->tangents.p, s.indices = h->indices.p;
+	s.meshes = h->meshes.p, s.instances = h->instances.p, s.materials = h->materials.p, s.lights = h->lights.p;
+	s.triLights = h->triLights.p, s.analytic = h->analytic.p, s.infiniteLights = h->infiniteLights.p, s.media = h->media.p;
+	s.densityPool = h->densityPool.p, s.texels = h->texels.p, s.spectrumTables = h->spectrumTables.p;
+	s.motionKeys = h->motionKeys.p, s.motions = h->motions.p;
+	s.nMeshes = d->n_meshes, s.nInstances = d->n_instances, s.nMaterials = d->n_materials, s.nLights = (int32_t) lights.size();
+	s.nInfinite = (int32_t) infinite.size(), s.nMedia = d->n_media;
+	s.motionStart = d->options.starttime, s.motionEnd = d->options.endtime, s.hasMotion = anyMotion;
+	s.cs = h->cs;
+	if (anyMotion) return fail(KRR_E_UNSUPPORTED, "motion-blur instances are not supported by this build yet");
+	h->haveScene = true;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_resize(KrrWfpt *h, int32_t w, int32_t hgt) {
+	if (!h || w <= 0 || hgt <= 0) return fail(KRR_E_INVALID, "bad size");
+	if ((int64_t) w * hgt * 256 > 0x7fffffffLL) return fail(KRR_E_INVALID, "frame too large (256 * pixelId must fit in int32 as in the reference)");
+	CUDA_OK(cudaSetDevice(h->device));
+	CUDA_OK(cudaDeviceSynchronize()); // as the reference does before resizing queues (integrator.cpp:26)
+	h->width = w, h->height = hgt;
+	h->rowBegin = 0, h->rowEnd = hgt;
+	h->frameBegun = false;
+	return allocState(h);
+}
+
+extern "C" int krr_wfpt_set_partition(KrrWfpt *h, int32_t rb, int32_t re) {
+	if (!h || h->width <= 0) return fail(KRR_E_STATE, "resize first");
+	if (rb < 0 || re > h->height || rb >= re) return fail(KRR_E_INVALID, "bad row range");
+	CUDA_OK(cudaDeviceSynchronize());
+	h->rowBegin = rb, h->rowEnd = re;
+	h->frameBegun = false;
+	return allocState(h);
+}
+
+extern "C" int krr_wfpt_update_instances(KrrWfpt *h, const int32_t *ids, const float *xf, int32_t n, void *stream) {
+	if (!h || !h->haveScene) return fail(KRR_E_STATE, "no scene");
+	if (n <= 0) return KRR_OK;
+	if (!ids || !xf) return fail(KRR_E_INVALID, "null argument");
+	cudaStream_t st = (cudaStream_t) stream;
+	for (int i = 0; i < n; i++) {
+		if (ids[i] < 0 || ids[i] >= (int) h->hInstances.size()) return fail(KRR_E_INVALID, "instance id out of range");
+		InstRec &r = h->hInstances[ids[i]];
+		memcpy(r.xf.m, xf + 12 * i, 48);
+		r.inv = xfInverse(r.xf);
+		// updateAccelStructure memcpy's the changed transforms only (optix.cpp:618-643)
+		CUDA_OK(cudaMemcpyAsync(h->instances.p + ids[i], &r, sizeof(InstRec), cudaMemcpyHostToDevice, st));
+	}
+	char err[256] = "";
+	if (!h->bvh.refitTlas(h->instances.p, st, err)) return fail(KRR_E_CUDA, "%s", err);
+	h->launches += h->bvh.refitLaunches();
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCameraData *c, void *stream) {
+	if (!h || !c) return fail(KRR_E_INVALID, "null argument");
+	if (!h->haveScene) return fail(KRR_E_STATE, "set_scene first");
+	if (h->width <= 0) return fail(KRR_E_STATE, "resize first");
+	CUDA_OK(cudaSetDevice(h->device));
+	cudaStream_t st = (cudaStream_t) stream;
+	h->frameIndex = frameIndex;
+	KrrCameraDev &cam = h->cam;
+	memcpy(cam.filmSize, c->film_size, 8);
+	cam.focalLength = c->focal_length, cam.focalDistance = c->focal_distance, cam.lensRadius = c->lens_radius;
+	cam.aspectRatio = c->aspect_ratio, cam.shutterOpen = c->shutter_open, cam.shutterTime = c->shutter_time;
+	memcpy(cam.transform.m, c->transform, 48);
+	cam.medium = c->medium;
+	// fov = atan2(filmSize[1] * 0.5f, focalLength); tan(fov)  (camera.h:41,46): per-frame constants,
+	// evaluated once here with the host libm so that every pixel sees the oracle's exact value
+	float fov  = atan2f(c->film_size[1] * 0.5f, c->focal_length);
+	cam.tanFov = tanf(fov);
+	h->launches = 0;
+	CUDA_OK(cudaMemsetAsync(h->totals.p, 0, sizeof(StatTotals), st));
+	Wavefront wf = makeWavefront(h, 0);
+	uint32_t seedIndex = (uint32_t) (frameIndex * (uint64_t) h->spp);
+	int grid = gridFor(h, k_begin_frame, 256);
+	k_begin_frame<<<grid, 256, 0, st>>>(wf, seedIndex);
+	h->launches++;
+	CUDA_OK(cudaGetLastError());
+	h->frameBegun = true;
+	h->lastStream = st;
+	return KRR_OK;
+}
+
+namespace {
+template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st) {
+	static int grid = 0;
+	if (!grid) grid = gridFor(h, k_scatter<MT>, 128);
+	k_scatter<MT><<<grid, 128, 0, st>>>(wf, depth);
+	h->launches++;
+}
+
+int capture(KrrWfpt *h, const Wavefront &wf, int depth, int queue, cudaStream_t st) {
+	if (h->capItems[queue].alloc((size_t) h->pixelCount())) return KRR_E_CUDA;
+	k_capture<<<h->numSMs, 256, 0, st>>>(wf, depth, queue, h->capItems[queue].p, h->capCounts.p + queue);
+	return KRR_OK;
+}
+} // namespace
+
+extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
+	if (!h || !film) return fail(KRR_E_INVALID, "null argument");
+	if (!h->frameBegun) return fail(KRR_E_STATE, "begin_frame must precede render");
+	CUDA_OK(cudaSetDevice(h->device));
+	cudaStream_t st = (cudaStream_t) stream;
+	static int gridCam = 0, gridTrace = 0, gridHit = 0, gridShadow = 0, gridResolve = 0;
+	if (!gridCam) {
+		gridCam = gridFor(h, k_generate_camera_rays, 256), gridTrace = gridFor(h, k_trace_closest, 128);
+		gridHit = gridFor(h, k_handle_hit_miss, 128), gridShadow = gridFor(h, k_trace_shadow, 128), gridResolve = gridFor(h, k_resolve, 256);
+	}
+	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
+	const int nDepthSlots = h->maxDepth + 2;
+	for (int sampleId = 0; sampleId < h->spp; sampleId++) {
+		Wavefront wf = makeWavefront(h, sampleId);
+		// [1] primary rays.  Queue counters were cleared by k_fold_counters of the previous sample
+		k_generate_camera_rays<<<gridCam, 256, 0, st>>>(wf);
+		h->launches++;
+		for (int depth = 0; true; depth++) {
+			const bool cap = h->capSample == sampleId && h->capDepth == depth;
+			if (cap && capture(h, wf, depth, 0, st)) return KRR_E_CUDA;
+			// [2.1] closest hits
+			k_trace_closest<<<gridTrace, 128, 0, st>>>(wf, depth);
+			h->launches++;
+			if (cap) for (int q = 1; q <= 3; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
+			// [2.3] emitted / environment radiance
+			k_handle_hit_miss<<<gridHit, 128, 0, st>>>(wf, depth);
+			h->launches++;
+			if (depth == h->maxDepth) break;
+			// [2.4] BSDF sampling + NEE, one launch per material type present in the scene
+			if (h->matTypePresent[MAT_DISNEY]) launchScatter<MAT_DISNEY>(h, wf, depth, st);
+			if (h->matTypePresent[MAT_DIFFUSE]) launchScatter<MAT_DIFFUSE>(h, wf, depth, st);
+			if (h->matTypePresent[MAT_DIELECTRIC]) launchScatter<MAT_DIELECTRIC>(h, wf, depth, st);
+			if (h->matTypePresent[MAT_CONDUCTOR]) launchScatter<MAT_CONDUCTOR>(h, wf, depth, st);
+			if (h->matTypePresent[MAT_NULL]) launchScatter<MAT_NULL>(h, wf, depth, st);
+			if (cap) for (int q = 4; q <= 5; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
+			// [2.5] shadow rays
+			if (h->nee) {
+				k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth);
+				h->launches++;
+			}
+		}
+		k_resolve<<<gridResolve, 256, 0, st>>>(wf);
+		k_fold_counters<<<1, 128, 0, st>>>(h->counters.p, h->totals.p, nDepthSlots, h->pixelCount());
+		h->launches += 2;
+	}
+	Wavefront wf = makeWavefront(h, 0);
+	k_film<<<gridResolve, 256, 0, st>>>(wf, (float4 *) film, 1);
+	h->launches++;
+	CUDA_OK(cudaGetLastError());
+	h->lastStream = st;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_render_to_host(KrrWfpt *h, float *film_host, void *stream) {
+	if (!h || !film_host) return fail(KRR_E_INVALID, "null argument");
+	static thread_local Buf<float4> staging;
+	size_t n = (size_t) h->width * h->height;
+	if (staging.alloc(n)) return KRR_E_CUDA;
+	int rc = krr_wfpt_render(h, (float *) staging.p, stream);
+	if (rc) return rc;
+	CUDA_OK(cudaMemcpyAsync(film_host, staging.p, n * 16, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+	CUDA_OK(cudaStreamSynchronize((cudaStream_t) stream));
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out) {
+	if (!h || !out) return fail(KRR_E_INVALID, "null argument");
+	memset(out, 0, sizeof *out);
+	if (!h->totals.p) return KRR_OK;
+	CUDA_OK(cudaStreamSynchronize(h->lastStream));
+	StatTotals t;
+	CUDA_OK(cudaMemcpy(&t, h->totals.p, sizeof t, cudaMemcpyDeviceToHost));
+	int32_t flags[4];
+	CUDA_OK(cudaMemcpy(flags, h->errorFlags.p, 16, cudaMemcpyDeviceToHost));
+	if (flags[0]) return fail(KRR_E_CUDA, "BVH traversal stack overflow (scene deeper than %d entries)", kStackSize);
+	out->camera_rays = t.camera, out->closest_rays = t.closest, out->shadow_rays = t.shadow, out->scatter_items = t.scatter;
+	out->hit_light_items = t.hitLight, out->miss_items = t.miss, out->medium_sample_items = t.mediumSample, out->medium_scatter_items = t.mediumScatter;
+	for (int i = 0; i < 64; i++) out->closest_by_depth[i] = t.closestByDepth[i], out->shadow_by_depth[i] = t.shadowByDepth[i];
+	out->kernel_launches = h->launches;
+	out->bvh_nodes = h->bvh.nodeCount(), out->bvh_triangles = h->bvh.triCount(), out->tlas_nodes = h->bvh.tlasNodeCount();
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *inst, int32_t *prim) {
+	if (!h || !h->firstHits.p) return fail(KRR_E_STATE, "no state");
+	CUDA_OK(cudaDeviceSynchronize());
+	std::vector<int4> tmp(h->pixelCount());
+	CUDA_OK(cudaMemcpy(tmp.data(), h->firstHits.p, tmp.size() * 16, cudaMemcpyDeviceToHost));
+	for (size_t i = 0; i < tmp.size(); i++) {
+		if (inst) inst[i] = tmp[i].x;
+		if (prim) prim[i] = tmp[i].y;
+	}
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_debug_pixel_state(KrrWfpt *h, uint64_t *sampler, float *lambda, float *cameraSample) {
+	if (!h || !h->rng.p) return fail(KRR_E_STATE, "no state");
+	CUDA_OK(cudaDeviceSynchronize());
+	const size_t n = h->pixelCount();
+	if (sampler) {
+		std::vector<uint64_t> st(n);
+		CUDA_OK(cudaMemcpy(st.data(), h->rng.p, n * 8, cudaMemcpyDeviceToHost));
+		uint32_t seedIndex = (uint32_t) (h->frameIndex * (uint64_t) h->spp);
+		for (size_t i = 0; i < n; i++) sampler[2 * i] = st[i], sampler[2 * i + 1] = ((uint64_t) seedIndex << 1u) | 1u;
+	}
+	if (lambda) {
+		std::vector<float> l0(n);
+		CUDA_OK(cudaMemcpy(l0.data(), h->lambda.p, n * 4, cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < n; i++) {
+			Wavelengths w = expandWavelengths(l0[i]);
+			memcpy(lambda + 4 * i, w.lambda, 16);
+		}
+	}
+	if (cameraSample && h->cameraSample.p) CUDA_OK(cudaMemcpy(cameraSample, h->cameraSample.p, n * 20, cudaMemcpyDeviceToHost));
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_debug_capture(KrrWfpt *h, int32_t sampleId, int32_t depth) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	h->capSample = sampleId, h->capDepth = depth;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_debug_queue(KrrWfpt *h, int32_t queue, int32_t *items, int32_t capacity) {
+	if (!h || queue < 0 || queue > 5) return fail(KRR_E_INVALID, "bad queue");
+	if (!h->capCounts.p || !h->capItems[queue].p) return fail(KRR_E_STATE, "nothing captured");
+	CUDA_OK(cudaDeviceSynchronize());
+	int32_t n = 0;
+	CUDA_OK(cudaMemcpy(&n, h->capCounts.p + queue, 4, cudaMemcpyDeviceToHost));
+	if (items) {
+		if (n > capacity) return fail(KRR_E_INVALID, "capacity %d < %d items", capacity, n);
+		CUDA_OK(cudaMemcpy(items, h->capItems[queue].p, (size_t) n * 16, cudaMemcpyDeviceToHost));
+	}
+	return n;
+}
+
+extern "C" int krr_accumulate_f32(float *accum, float *film, int64_t n, uint64_t accumCount, uint64_t maxAccum, int32_t movingAverage, void *stream) {
+	if (!accum || !film || n <= 0) return fail(KRR_E_INVALID, "bad argument");
+	k_accumulate<<<148 * 4, 256, 0, (cudaStream_t) stream>>>((float4 *) accum, (float4 *) film, n, accumCount, maxAccum, movingAverage);
+	CUDA_OK(cudaGetLastError());
+	return KRR_OK;
+}

@@ -1,0 +1,33 @@
+// bvh_build.h -- host interface of the device BVH builder (see bvh_build.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "bvh.cuh"
+#include "scene.cuh"
+
+namespace krr {
+
+class BvhBuilder {
+public:
+	BvhBuilder();
+	~BvhBuilder();
+	BvhBuilder(const BvhBuilder &) = delete;
+	// Builds one BLAS per mesh (object space) and a TLAS over the instances.  dPositions / dIndices /
+	// dInstances are device arrays; hMeshes is the host copy of the mesh records (offsets, counts).
+	bool build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes, const InstRec *dInstances,
+			   const InstRec *hInstances, int nInstances, cudaStream_t stream, char *err);
+	// Re-fits the TLAS after instance transforms changed (topology kept); no host synchronisation.
+	bool refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err);
+	int refitLaunches() const;
+	BvhDev device() const;
+	int blasRoot(int mesh) const;
+	int triBase(int mesh) const;
+	int nodeCount() const;
+	int tlasNodeCount() const;
+	int triCount() const;
+
+private:
+	struct Impl;
+	Impl *m;
+};
+
+} // namespace krr

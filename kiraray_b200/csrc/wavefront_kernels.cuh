@@ -1,0 +1,771 @@
+// wavefront_kernels.cuh -- the stage kernels of the B200-native WavefrontPathTracer.
+//
+// Stage map (reference src/render/wavefront/integrator.cpp:223-267 loop; device.cu programs):
+//   k_begin_frame          beginFrame                 integrator.cpp:205-221
+//   k_generate_camera_rays generateCameraRays         integrator.cpp:166-179
+//   k_trace_closest        __raygen__/CH/AH/MS Closest device.cu:43-81
+//   k_handle_hit_miss      handleHit + handleMiss     integrator.cpp:78-108
+//   k_scatter<MT>          generateScatterRays        integrator.cpp:110-164 (+ prepareSurfaceInteraction,
+//                                                     shading.h:115-226, moved here from the CH program)
+//   k_trace_shadow         __raygen__/AH/MS Shadow    device.cu:83-100
+//   k_resolve / k_film     per-sample resolve, film   integrator.cpp:257-266, device/cuda.h:33-45
+//
+// Data layout (HBM), all arrays 16-byte vectorised SoA:
+//   * ray queues (ping-pong): 7 x float4 per item = 112 B (reference RayWorkItem: 120 B SoA)
+//   * the trace stage writes a 16-byte hit record next to the ray and pushes the SLOT INDEX (4 B)
+//     into the miss / hit-light / per-material scatter index queues; the 232-byte ScatterRayWorkItem
+//     of the reference is never materialised -- the scatter stage rebuilds the interaction from
+//     (instance, primitive, barycentrics), which are L2-resident mesh reads
+//   * scatter indices are binned by material type at push time (one counter per type), so the
+//     scatter kernel of each type runs a single BSDF: this is the "material sort", done for free
+//   * shadow queue: 3 x float4 = 48 B (ray, pixel, and the MIS-weighted contribution
+//     Ld/(pl+pu).mean() pre-divided), reference 92 B
+//   * per pixel: L (16 B) + rgb (16 B) + PCG state (8 B, inc is per-frame uniform) + lambda0 (4 B)
+//   * queue sizes live in a per-depth counter block on the device; kernels are launched with a fixed
+//     persistent grid (multiple of the SM count) and grid-stride over the live count, so there is
+//     no host synchronisation and no full-width launch over a nearly empty queue
+//   * pushes are warp-aggregated: one atomicAdd per warp per queue
+#pragma once
+#include "bsdf.cuh"
+#include "bvh.cuh"
+#include "lights.cuh"
+#include "sampler.cuh"
+#include "scene.cuh"
+#include "spectrum.cuh"
+
+namespace krr {
+
+constexpr int kMaxDepthSlots = 66;
+
+struct DepthCounters {	// one block per loop depth; 16 ints = 64 B
+	int32_t nRay;		// items in the ray queue consumed at this depth
+	int32_t nMiss, nHitLight;
+	int32_t nScatter[MAT_COUNT];
+	int32_t nShadow;
+	int32_t nMediumSample, nMediumScatter;
+	int32_t pad[5];
+};
+static_assert(sizeof(DepthCounters) == 64, "DepthCounters");
+
+struct RayQueue { // SoA, 7 x 16 B
+	float4 *o_time;	  // origin.xyz, ray time
+	float4 *d_medium; // dir.xyz, medium index (int bits, -1 = none)
+	float4 *thp, *pu, *pl;
+	float4 *ctxP_pix; // LightSampleContext::p, pixelId (int bits)
+	float4 *ctxN_dep; // LightSampleContext::n, depth | bsdfType << 8 (int bits)
+};
+
+struct ShadowQueue { // 3 x 16 B (+2 for the transmittance variant)
+	float4 *o_tmax;
+	float4 *d_pix;
+	float4 *contrib; // Ld / (pl + pu).mean()   (Ld itself when media are enabled)
+	float4 *pu, *pl; // media only
+};
+
+struct PixelState {
+	float4 *L;
+	float4 *pixel;
+	uint64_t *rng;
+	float *lambda;		 // lambda[0], sign bit = secondary wavelengths terminated
+	float *cameraSample; // 5 floats per pixel, debug builds of the state only (may be null)
+};
+
+struct Params {
+	int32_t width, height;
+	int32_t pixelBegin, pixelCount; // this handle's pixel range (row partition)
+	int32_t spp, maxDepth, nee, enableMedium, enableClamp;
+	float probRR, clampMax;
+	uint64_t rngInc; // PCG increment of this frame
+	uint32_t sampleIndex;
+};
+
+struct KrrCameraDev {
+	float filmSize[2];
+	float focalLength, focalDistance, lensRadius, aspectRatio, shutterOpen, shutterTime;
+	Xf transform;
+	int32_t medium;
+	float tanFov; // tan(atan2(filmSize[1] * 0.5, focalLength)) evaluated ONCE on the host (glibc), see api
+};
+
+struct Wavefront {
+	Params p;
+	KrrCameraDev cam;
+	SceneDev scene;
+	BvhDev bvh;
+	PixelState px;
+	RayQueue rays[2];
+	int4 *hits;			// per ray slot of the CURRENT queue: inst, prim, u bits, v bits
+	int32_t *missIdx, *hitLightIdx;
+	int32_t *scatterIdx[MAT_COUNT];
+	ShadowQueue shadow;
+	DepthCounters *counters; // [kMaxDepthSlots]
+	int4 *firstHits;		 // per pixel depth-0 hit (debug tap), may be null
+	int32_t *errorFlags;	 // [0] traversal stack overflow
+	const uint8_t *instFlags; // per instance: bit0 null material, bit1 has alpha (transmission) texture
+};
+
+// ---- warp-aggregated push: one atomicAdd per warp ----
+KRR_DEV int warpPush(int32_t *counter, bool pred) {
+	unsigned mask = __ballot_sync(__activemask(), pred);
+	if (!pred) return -1;
+	int lane   = threadIdx.x & 31;
+	int leader = __ffs(mask) - 1;
+	int base   = 0;
+	if (lane == leader) base = atomicAdd(counter, __popc(mask));
+	base = __shfl_sync(mask, base, leader);
+	return base + __popc(mask & ((1u << lane) - 1));
+}
+
+KRR_DEV float4 ldg4(const float4 *p) { return __ldg(p); }
+// streaming (read-once / write-once) queue traffic: keep it out of L1
+KRR_DEV float4 ldcs4(const float4 *p) { return __ldcs(p); }
+KRR_DEV void stcs4(float4 *p, float4 v) { __stcs(p, v); }
+
+// =================================================================================================
+__global__ void k_begin_frame(Wavefront wf, uint32_t seedIndex) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
+		int pixelId = wf.p.pixelBegin + i;
+		int px = pixelId % wf.p.width, py = pixelId / wf.p.width;
+		wf.px.L[i]	   = make_float4(0, 0, 0, 0);
+		wf.px.pixel[i] = make_float4(0, 0, 0, 0);
+		Pcg rng;
+		rng.setPixelSample((uint32_t) px, (uint32_t) py, seedIndex);
+		rng.advance((int64_t) (256 * pixelId));
+		wf.px.lambda[i] = sampleLambda0(rng.get1D());
+		wf.px.rng[i]	= rng.state;
+	}
+}
+
+// CameraData::generateSample + getRay, src/core/camera.h:32-58.  Bit-exact against the oracle: every
+// operation individually rounded, in Eigen's evaluation order.
+KRR_DEV void cameraRay(const KrrCameraDev &c, int px, int py, int W, int H, const float cs[5], V3 &o, V3 &d, float &time) {
+	float pxf = xadd(xadd((float) px, 0.5f), cs[0]), pyf = xadd(xadd((float) py, 0.5f), cs[1]);
+	float ndcx = xadd(xdiv(xmul(2.f, pxf), (float) W), -1.f), ndcy = xadd(xdiv(xmul(2.f, pyf), (float) H), -1.f);
+	time = xadd(c.shutterOpen, xmul(c.shutterTime, cs[4]));
+	V3 fd = mk3(xmul(xmul(c.tanFov, c.aspectRatio), ndcx), xmul(c.tanFov, ndcy), -1.f);
+	// Eigen normalized(): v / sqrt(squaredNorm); squaredNorm of a 3-vector reduces as x*x + (y*y + z*z)
+	float n2 = xadd(xmul(fd.x, fd.x), xadd(xmul(fd.y, fd.y), xmul(fd.z, fd.z)));
+	float nn = xsqrt(n2);
+	fd = mk3(xdiv(fd.x, nn), xdiv(fd.y, nn), xdiv(fd.z, nn));
+	V3 lo = mk3(0, 0, 0), ld = fd;
+	if (c.lensRadius > 1e-5f) {
+		float ax, ay;
+		uniformSampleDisk(cs[2], cs[3], ax, ay);
+		lo = mk3(c.lensRadius * ax, c.lensRadius * ay, 0.f);
+		ld = normalize(fd * c.focalDistance - lo);
+	}
+	// Transformation::operator()(ray): m * origin, linear(m) * dir (raytracing.h:95-97)
+	const float *m = c.transform.m;
+	auto row = [&](int r, V3 v) { return xadd(xmul(m[r * 4], v.x), xadd(xmul(m[r * 4 + 1], v.y), xmul(m[r * 4 + 2], v.z))); };
+	o = mk3(xadd(row(0, lo), m[3]), xadd(row(1, lo), m[7]), xadd(row(2, lo), m[11]));
+	d = mk3(row(0, ld), row(1, ld), row(2, ld));
+}
+
+__global__ void k_generate_camera_rays(Wavefront wf) {
+	RayQueue q = wf.rays[0];
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
+		int pixelId = wf.p.pixelBegin + i;
+		Pcg rng{wf.px.rng[i], wf.p.rngInc};
+		float cs[5];
+#pragma unroll
+		for (int k = 0; k < 5; k++) cs[k] = rng.get1D();
+		wf.px.rng[i] = rng.state;
+		if (wf.px.cameraSample)
+			for (int k = 0; k < 5; k++) wf.px.cameraSample[5 * (size_t) i + k] = cs[k];
+		V3 o, d;
+		float time;
+		cameraRay(wf.cam, pixelId % wf.p.width, pixelId / wf.p.width, wf.p.width, wf.p.height, cs, o, d, time);
+		// pushCameraRay, workqueue.h:180-189 (slot = pixel: every pixel spawns exactly one ray, so the
+		// queue is dense and the writes are coalesced without any atomic)
+		stcs4(q.o_time + i, make_float4(o.x, o.y, o.z, time));
+		stcs4(q.d_medium + i, make_float4(d.x, d.y, d.z, __int_as_float(wf.cam.medium)));
+		stcs4(q.thp + i, sp(1));
+		stcs4(q.pu + i, sp(1));
+		stcs4(q.pl + i, sp(1));
+		stcs4(q.ctxP_pix + i, make_float4(0, 0, 0, __int_as_float(i)));
+		stcs4(q.ctxN_dep + i, make_float4(0, 0, 0, __int_as_float(0)));
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) wf.counters[0].nRay = wf.p.pixelCount;
+}
+
+// alphaKilled, shading.h:89-113 + HashFloat (util/hash.h:117-133)
+KRR_DEV uint64_t murmur64A(const unsigned char *key, int len, uint64_t seed) {
+	const uint64_t m = 0xc6a4a7935bd1e995ull;
+	const int r = 47;
+	uint64_t h = seed ^ (len * m);
+	for (int i = 0; i < len / 8; i++) {
+		uint64_t k;
+		memcpy(&k, key + 8 * i, 8);
+		k *= m; k ^= k >> r; k *= m; h ^= k; h *= m;
+	}
+	h ^= h >> r; h *= m; h ^= h >> r; // len is a multiple of 8 here (24 bytes)
+	return h;
+}
+KRR_DEV bool alphaKilled(const Wavefront &wf, int inst, int prim, float u, float v, V3 o, V3 d) {
+	const MeshRec &mesh = wf.scene.meshes[wf.scene.instances[inst].mesh];
+	if (mesh.material < 0) return false;
+	const TexRec &t = wf.scene.materials[mesh.material].tex[4];
+	if (!t.valid) return false;
+	float uvx = 0, uvy = 0;
+	if (mesh.uvOff >= 0) {
+		const int32_t *idx = wf.scene.indices + 3 * ((size_t) mesh.idxOff + prim);
+		float b0 = 1 - u - v;
+		const float *uv = wf.scene.texcoords + 2 * (size_t) mesh.uvOff;
+		uvx = b0 * uv[2 * idx[0]] + u * uv[2 * idx[1]] + v * uv[2 * idx[2]];
+		uvy = b0 * uv[2 * idx[0] + 1] + u * uv[2 * idx[1] + 1] + v * uv[2 * idx[2] + 1];
+	}
+	float4 op	= sampleTex(t, wf.scene.texels, uvx, uvy, make_float4(1, 1, 1, 1));
+	float alpha = 1 - luminanceRGB(op.x, op.y, op.z);
+	if (alpha >= 1) return false;
+	if (alpha <= 0) return true;
+	float buf[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
+	float h = (uint32_t) murmur64A((const unsigned char *) buf, 24, 0) * 0x1p-32f;
+	return h > alpha;
+}
+
+// =================================================================================================
+// Closest stage: traverse, record the hit, route the slot index (device.cu:43-81)
+__global__ void __launch_bounds__(128) k_trace_closest(Wavefront wf, int depth) {
+	const RayQueue q	= wf.rays[depth & 1];
+	const RayQueue nq	= wf.rays[(depth & 1) ^ 1];
+	DepthCounters *dc	= wf.counters + depth;
+	const int n			= dc->nRay;
+	const int stride	= gridDim.x * blockDim.x;
+	const int nIter		= (n + stride - 1) / stride;
+	for (int it = 0; it < nIter; it++) {
+		int i		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+		bool active = i < n;
+		int route	= -1; // 0 miss, 1 scatter(+light), 2 null-material pass-through
+		int matType = 0;
+		bool light	= false;
+		Hit h;
+		h.inst = -1;
+		float4 o4, d4;
+		if (active) {
+			o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
+			V3 o = mk3(o4), d = mk3(d4);
+			int overflow = 0;
+			h = traverse<false>(wf.bvh, wf.scene.instances, o, d, kInf,
+				[&](int inst, int prim, float u, float v) {
+					if (!(wf.instFlags[inst] & 2)) return true;
+					return !alphaKilled(wf, inst, prim, u, v, o, d);
+				}, &overflow);
+			if (overflow) atomicExch(&wf.errorFlags[0], 1);
+			wf.hits[i] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
+			if (depth == 0 && wf.firstHits) {
+				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
+				wf.firstHits[pix] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
+			}
+			if (h.inst < 0) route = 0;
+			else {
+				const InstRec &in	= wf.scene.instances[h.inst];
+				const MeshRec &mesh = wf.scene.meshes[in.mesh];
+				if (mesh.material < 0) route = 2;
+				else {
+					route	= 1;
+					matType = wf.scene.materials[mesh.material].bsdfType;
+					light	= in.lightBase >= 0;
+				}
+			}
+		}
+		// (media: rays inside a medium are routed to the medium-sample queue by the media build)
+		int s;
+		s = warpPush(&dc->nMiss, route == 0);
+		if (s >= 0) wf.missIdx[s] = i;
+		s = warpPush(&dc->nHitLight, route == 1 && light);
+		if (s >= 0) wf.hitLightIdx[s] = i;
+#pragma unroll
+		for (int mt = 1; mt < MAT_COUNT; mt++) {
+			s = warpPush(&dc->nScatter[mt], route == 1 && matType == mt);
+			if (s >= 0) wf.scatterIdx[mt][s] = i;
+		}
+		s = warpPush(&dc->nScatter[MAT_NULL], route == 1 && matType == MAT_NULL);
+		if (s >= 0) wf.scatterIdx[MAT_NULL][s] = i;
+		// null material: re-queue the ray at the same item depth (device.cu:54-58)
+		s = warpPush(&dc[1].nRay, route == 2);
+		if (s >= 0) {
+			const InstRec &in	= wf.scene.instances[h.inst];
+			const MeshRec &mesh = wf.scene.meshes[in.mesh];
+			const int32_t *idx	= wf.scene.indices + 3 * ((size_t) mesh.idxOff + h.prim);
+			const float *P		= wf.scene.positions + 3 * (size_t) mesh.posOff;
+			V3 p0 = ld3(P + 3 * idx[0]), p1 = ld3(P + 3 * idx[1]), p2 = ld3(P + 3 * idx[2]);
+			float b0 = 1 - h.u - h.v;
+			V3 p = xfPoint(in.xf, b0 * p0 + h.u * p1 + h.v * p2);
+			V3 n;
+			if (mesh.nrmOff >= 0) {
+				const float *N = wf.scene.normals + 3 * (size_t) mesh.nrmOff;
+				n = normalize(b0 * ld3(N + 3 * idx[0]) + h.u * ld3(N + 3 * idx[1]) + h.v * ld3(N + 3 * idx[2]));
+			} else n = normalize(cross(p1 - p0, p2 - p0));
+			n = normalize(xfNormal(in.inv, n));
+			V3 d = mk3(d4);
+			V3 off = n * kRayEps;
+			if (dot(n, d) < 0.f) off = -off;
+			V3 no = p + off;
+			stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, o4.w));
+			stcs4(nq.d_medium + s, d4);
+			stcs4(nq.thp + s, ldcs4(q.thp + i));
+			stcs4(nq.pu + s, ldcs4(q.pu + i));
+			stcs4(nq.pl + s, ldcs4(q.pl + i));
+			stcs4(nq.ctxP_pix + s, ldcs4(q.ctxP_pix + i));
+			stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
+		}
+	}
+}
+
+// =================================================================================================
+// shared by the hit-light and scatter stages: rebuild the interaction geometry of a hit
+struct SurfaceGeom {
+	V3 p, n, tangent, bitangent, wo;
+	float uvx, uvy;
+	int inst, prim, mesh, material, light;
+};
+
+KRR_DEV void rebuildGeometry(const Wavefront &wf, int4 hit, V3 rayDir, SurfaceGeom &g) {
+	// getHitInfo (shading.h:78-87) + prepareSurfaceInteraction geometry part (shading.h:121-170)
+	const SceneDev &sc	= wf.scene;
+	g.inst = hit.x, g.prim = hit.y;
+	float u = __int_as_float(hit.z), v = __int_as_float(hit.w);
+	float b0 = 1 - u - v;
+	const InstRec &in	= sc.instances[g.inst];
+	const MeshRec &mesh = sc.meshes[in.mesh];
+	g.mesh = in.mesh, g.material = mesh.material;
+	const int32_t *idx = sc.indices + 3 * ((size_t) mesh.idxOff + g.prim);
+	int i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+	const float *P = sc.positions + 3 * (size_t) mesh.posOff;
+	V3 p0 = ld3(P + 3 * i0), p1 = ld3(P + 3 * i1), p2 = ld3(P + 3 * i2);
+	g.wo = normalize(-normalize(rayDir));
+	g.p	 = b0 * p0 + u * p1 + v * p2;
+	if (mesh.nrmOff >= 0) {
+		const float *N = sc.normals + 3 * (size_t) mesh.nrmOff;
+		g.n = normalize(b0 * ld3(N + 3 * i0) + u * ld3(N + 3 * i1) + v * ld3(N + 3 * i2));
+	} else g.n = normalize(cross(p1 - p0, p2 - p0));
+	if (mesh.tanOff >= 0) {
+		const float *T = sc.tangents + 3 * (size_t) mesh.tanOff;
+		g.tangent = normalize(b0 * ld3(T + 3 * i0) + u * ld3(T + 3 * i1) + v * ld3(T + 3 * i2));
+		g.tangent = normalize(g.tangent - g.n * dot(g.n, g.tangent));
+	} else { // getPerpendicular, util/math_utils.h:122-133
+		V3 a = mk3(fabsf(g.n.x), fabsf(g.n.y), fabsf(g.n.z));
+		uint32_t uyx = (a.x - a.y) < 0 ? 1 : 0, uzx = (a.x - a.z) < 0 ? 1 : 0, uzy = (a.y - a.z) < 0 ? 1 : 0;
+		uint32_t xm = uyx & uzx, ym = (1 ^ xm) & uzy, zm = 1 ^ (xm | ym);
+		g.tangent = normalize(cross(g.n, mk3((float) xm, (float) ym, (float) zm)));
+	}
+	g.bitangent = normalize(cross(g.n, g.tangent));
+	g.uvx = g.uvy = 0;
+	if (mesh.uvOff >= 0) {
+		const float *UV = sc.texcoords + 2 * (size_t) mesh.uvOff;
+		g.uvx = b0 * UV[2 * i0] + u * UV[2 * i1] + v * UV[2 * i2];
+		g.uvy = b0 * UV[2 * i0 + 1] + u * UV[2 * i1 + 1] + v * UV[2 * i2 + 1];
+	}
+	g.light = in.lightBase >= 0 ? in.lightBase + g.prim : -1;
+	g.p			= xfPoint(in.xf, g.p);
+	g.n			= normalize(xfNormal(in.inv, g.n));
+	g.tangent	= normalize(xfNormal(in.inv, g.tangent));
+	g.bitangent = normalize(xfNormal(in.inv, g.bitangent));
+}
+
+// material part of prepareSurfaceInteraction, shading.h:172-225
+KRR_DEV void evalMaterial(const Wavefront &wf, SurfaceGeom &g, const Wavelengths &wl, ShadingData &sd, bool &terminateSecondary) {
+	const SceneDev &sc = wf.scene;
+	const MatRec &mat  = sc.materials[g.material];
+	sd.bsdfType = mat.bsdfType;
+	sd.specularTransmission = mat.specularTransmission;
+	sd.IoR = mat.ior;
+	sd.hasEta = sd.hasK = 0;
+	terminateSecondary = false;
+	if (mat.eta.kind != 0) {
+		auto evalSpec = [&](const SpectrumRec &s, float lambda) -> float {
+			switch (s.kind) {
+				case 1: return s.a[0];
+				case 2: return s.a[0] + s.b[0] / pow2(lambda / 1000.f);						 // CauchyIoRSpectrum, spectrum.h:113
+				case 3: {																		 // SellmeierIoRSpectrum, spectrum.h:130-132
+					float l2 = pow2(lambda), sum = 0;
+					for (int k = 0; k < 3; k++) { float den = l2 - s.b[k]; sum += den == 0 ? 0.f : (l2 * s.a[k]) / den; }
+					return sqrtf(1 + sum);
+				}
+				default: { // piecewise linear table, spectrum.h:251-259
+					const float *L = sc.spectrumTables + s.tabOff, *V = L + s.n;
+					if (s.n == 0 || lambda < L[0] || lambda > L[s.n - 1]) return 0.f;
+					int o = 0;
+					while (o + 2 < s.n && L[o + 1] <= lambda) o++;
+					float t = (lambda - L[o]) / (L[o + 1] - L[o]);
+					return lerpf(V[o], V[o + 1], t);
+				}
+			}
+		};
+		sd.IoR = evalSpec(mat.eta, wl.lambda[0]);
+		if (mat.eta.kind != 1) terminateSecondary = true;
+		sd.hasEta  = 1;
+		sd.etaSpec = make_float4(evalSpec(mat.eta, wl.lambda[0]), evalSpec(mat.eta, wl.lambda[1]), evalSpec(mat.eta, wl.lambda[2]), evalSpec(mat.eta, wl.lambda[3]));
+	}
+	float diffuse[3], specular[3], spec3;
+	const MeshRec &mesh = sc.meshes[g.mesh];
+	if (mat.constColours) {
+		for (int k = 0; k < 3; k++) diffuse[k] = mat.constDiffuse[k], specular[k] = mat.constSpecular[k];
+		spec3 = mat.constSpecular[3];
+	} else {
+		float4 diff = sampleTex(mat.tex[0], sc.texels, g.uvx, g.uvy, make_float4(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], mat.diffuse[3]));
+		float4 spec = sampleTex(mat.tex[1], sc.texels, g.uvx, g.uvy, make_float4(mat.specular[0], mat.specular[1], mat.specular[2], mat.specular[3]));
+		diffuse[0] = diff.x, diffuse[1] = diff.y, diffuse[2] = diff.z;
+		specular[0] = spec.x, specular[1] = spec.y, specular[2] = spec.z, spec3 = spec.w;
+	}
+	if (mat.tex[3].valid && mesh.uvOff >= 0) { // normal map
+		float4 nv = sampleTex(mat.tex[3], sc.texels, g.uvx, g.uvy, make_float4(0, 0, 1, 0));
+		V3 nm = mk3(2 * nv.x - 1, 2 * nv.y - 1, 2 * nv.z - 1);
+		g.n	  = normalize(g.tangent * nm.x + g.bitangent * nm.y + g.n * nm.z);
+		g.tangent	= normalize(g.tangent - g.n * dot(g.tangent, g.n));
+		g.bitangent = normalize(cross(g.n, g.tangent));
+	}
+	float dr[3], srgb[3];
+	if (mat.shadingModel == 0) { // MetallicRoughness: [SPECULAR] G roughness, B metallic
+		for (int k = 0; k < 3; k++) {
+			dr[k]	= diffuse[k] * (1 - specular[2]) + 0.f * specular[2];
+			srgb[k] = 0.f * (1 - specular[2]) + diffuse[k] * specular[2];
+		}
+		sd.metallic	 = specular[2];
+		sd.roughness = specular[1];
+	} else { // SpecularGlossiness
+		for (int k = 0; k < 3; k++) dr[k] = diffuse[k], srgb[k] = specular[k];
+		sd.roughness = 1.f - spec3;
+		// getMetallic, shading.h:17-30
+		float d = luminanceRGB(dr[0], dr[1], dr[2]), s = luminanceRGB(srgb[0], srgb[1], srgb[2]);
+		if (s == 0) sd.metallic = 0;
+		else {
+			float b = s + d - 0.08f, c = 0.04f - s;
+			float root = sqrtf(b * b - 0.16f * c);
+			sd.metallic = fmaxf(0.f, (root - b) * 12.5f);
+		}
+	}
+	if (mat.constColours) {
+		sd.diffuse	= sampleBounded(mat.diffuseSpec, wl);
+		sd.specular = sampleBounded(mat.specularSpec, wl);
+	} else {
+		sd.diffuse	= sampleBounded(makeBounded(sc.cs.zNodes, sc.cs.coeffs, dr[0], dr[1], dr[2]), wl);
+		sd.specular = sampleBounded(makeBounded(sc.cs.zNodes, sc.cs.coeffs, srgb[0], srgb[1], srgb[2]), wl);
+	}
+	sd.anisotropic = mat.anisotropic;
+}
+
+// =================================================================================================
+// handleHit + handleMiss (integrator.cpp:78-108)
+__global__ void __launch_bounds__(128) k_handle_hit_miss(Wavefront wf, int depth) {
+	const RayQueue q  = wf.rays[depth & 1];
+	DepthCounters *dc = wf.counters + depth;
+	const int stride  = gridDim.x * blockDim.x;
+	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	const int nHit = dc->nHitLight;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nHit; k += stride) {
+		int i	  = wf.hitLightIdx[k];
+		int4 hit  = wf.hits[i];
+		float4 d4 = ldg4(q.d_medium + i);
+		SurfaceGeom g;
+		rebuildGeometry(wf, hit, mk3(d4), g);
+		float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
+		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
+		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
+		// normal map changes intr.n before the light is evaluated (the CH program prepares the full
+		// interaction before pushing): apply it when present
+		const MatRec &mat = wf.scene.materials[g.material];
+		if (mat.tex[3].valid && wf.scene.meshes[g.mesh].uvOff >= 0) {
+			float4 nv = sampleTex(mat.tex[3], wf.scene.texels, g.uvx, g.uvy, make_float4(0, 0, 1, 0));
+			g.n = normalize(g.tangent * (2 * nv.x - 1) + g.bitangent * (2 * nv.y - 1) + g.n * (2 * nv.z - 1));
+		}
+		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+		const LightRec lr	  = wf.scene.lights[g.light];
+		const TriLightRec &tl = wf.scene.triLights[lr.index];
+		Spec thp = ldg4(q.thp + i), pu = ldg4(q.pu + i);
+		Spec Le	 = areaLightL(tl, g.n, g.wo, wl, wf.scene.cs) * thp;
+		if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
+			Spec pl		   = ldg4(q.pl + i);
+			float lightPdf = areaLightPdfLi(tl, wf.scene.instances[tl.inst], g.p, g.n, mk3(cp)) * lightSelPdf;
+			Le = Le / mean(pl * lightPdf + pu);
+		} else Le = Le / mean(pu);
+		wf.px.L[pix] = Le + wf.px.L[pix]; // addRadiance (<= 1 item per pixel per stage: plain RMW)
+	}
+	const int nMiss = dc->nMiss;
+	if (wf.scene.nInfinite == 0) return;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nMiss; k += stride) {
+		int i	  = wf.missIdx[k];
+		float4 d4 = ldg4(q.d_medium + i);
+		float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
+		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
+		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
+		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+		Spec thp = ldg4(q.thp + i), pu = ldg4(q.pu + i), pl = ldg4(q.pl + i);
+		Spec L = sp(0);
+		for (int li = 0; li < wf.scene.nInfinite; li++) {
+			const AnalyticLightRec &light = wf.scene.analytic[wf.scene.infiniteLights[li]];
+			Spec Li = infiniteLi(light, mk3(d4), wl, wf.scene);
+			if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
+				float lightPdf = kInv4Pi * lightSelPdf;
+				L += Li / mean(pu + pl * lightPdf);
+			} else L += Li / mean(pu);
+		}
+		wf.px.L[pix] = thp * L + wf.px.L[pix];
+	}
+}
+
+// =================================================================================================
+// generateScatterRays (integrator.cpp:110-164), one launch per material type
+template <int MT>
+__global__ void __launch_bounds__(128) k_scatter(Wavefront wf, int depth) {
+	const RayQueue q  = wf.rays[depth & 1];
+	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
+	DepthCounters *dc = wf.counters + depth;
+	const int n		  = dc->nScatter[MT];
+	const int stride  = gridDim.x * blockDim.x;
+	const int nIter	  = (n + stride - 1) / stride;
+	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	for (int it = 0; it < nIter; it++) {
+		int k		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+		bool active = k < n;
+		bool pushShadow = false, pushNext = false;
+		// shadow item
+		V3 so, sdv;
+		Spec sContrib, sPu, sPl;
+		// next ray
+		V3 no, nd, ctxP, ctxN;
+		Spec nthp, npu, npl;
+		int pix = 0, itemDepth = 0, nflags = 0, medium = -1;
+		float time = 0;
+		if (active) {
+			int i	  = wf.scatterIdx[MT][k];
+			int4 hit  = wf.hits[i];
+			float4 o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
+			float4 cp = ldcs4(q.ctxP_pix + i), cn = ldcs4(q.ctxN_dep + i);
+			pix = __float_as_int(cp.w), itemDepth = __float_as_int(cn.w) & 0xff;
+			time = o4.w, medium = __float_as_int(d4.w);
+			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			// Russian roulette at every depth, including 0 (integrator.cpp:118-119)
+			bool alive = rng.get1D() < wf.p.probRR;
+			if (alive) {
+				Spec thp = ldcs4(q.thp + i) / wf.p.probRR, pu = ldcs4(q.pu + i);
+				SurfaceGeom g;
+				rebuildGeometry(wf, hit, mk3(d4), g);
+				float lam = wf.px.lambda[pix];
+				Wavelengths wl = expandWavelengths(lam);
+				ShadingData sd;
+				bool term;
+				evalMaterial(wf, g, wl, sd, term);
+				if (term && lam > 0) { // lambda.terminateSecondary() persists in the pixel state (shading.h:184-185)
+					wf.px.lambda[pix] = -lam;
+					wl = expandWavelengths(-lam);
+				}
+				auto toLocal = [&](V3 v) { return mk3(dot(g.tangent, v), dot(g.bitangent, v), dot(g.n, v)); };
+				V3 woLocal = toLocal(g.wo);
+				int bsdfType = getBsdfType(sd);
+				Bsdf<MT> bsdf;
+				BsdfSetupCtx ctx{g.wo, &wl, &wf.scene.cs};
+				bsdf.setup(sd, ctx);
+				if (wf.p.nee && (bsdfType & BSDF_SMOOTH)) {
+					float ul = rng.get1D();
+					uint32_t lightId = (uint32_t) (ul * wf.scene.nLights);
+					const LightRec lr = wf.scene.lights[lightId];
+					float u0 = rng.get1D(), u1 = rng.get1D();
+					LightSample ls;
+					bool delta = false;
+					if (lr.type == LIGHT_DIFFUSE_AREA) {
+						const TriLightRec &tl = wf.scene.triLights[lr.index];
+						ls = areaLightSampleLi(tl, wf.scene.instances[tl.inst], u0, u1, g.p, wl, wf.scene.cs);
+					} else {
+						const AnalyticLightRec &al = wf.scene.analytic[lr.index];
+						ls	  = analyticSampleLi(al, u0, u1, g.p, wl, wf.scene);
+						delta = al.type != LIGHT_INFINITE;
+					}
+					// spawnRayTo(ls.intr), raytracing.h:148-157
+					auto offs = [](V3 p, V3 n, V3 w) { V3 off = n * kRayEps; if (dot(n, w) < 0.f) off = -off; return p + off; };
+					V3 to  = offs(ls.p, ls.n, g.p - ls.p);
+					V3 p_o = offs(g.p, g.n, to - g.p);
+					V3 dd  = to - p_o;
+					V3 wiWorld = normalize(dd), wiLocal = toLocal(wiWorld);
+					float lightPdf = lightSelPdf * ls.pdf;
+					Spec bsdfVal   = bsdf.f(woLocal, wiLocal);
+					float bsdfPdf  = delta ? 0.f : bsdf.pdf(woLocal, wiLocal);
+					if (lightPdf > 0 && any(bsdfVal)) {
+						Spec Ld = ls.L * thp * bsdfVal * fabsf(wiLocal.z);
+						if (any(Ld)) {
+							pushShadow = true;
+							so = p_o, sdv = dd;
+							sPu = pu * bsdfPdf, sPl = pu * lightPdf;
+							sContrib = wf.p.enableMedium ? Ld : Ld / mean(sPl + sPu);
+						}
+					}
+				}
+				BSDFSample bs = bsdf.sample(woLocal, rng);
+				if (bs.pdf != 0 && any(bs.f)) {
+					V3 wiWorld = g.tangent * bs.wi.x + g.bitangent * bs.wi.y + g.n * bs.wi.z;
+					nthp = thp * bs.f * fabsf(bs.wi.z) / bs.pdf;
+					if (any(nthp)) {
+						pushNext = true;
+						nflags = bs.flags;
+						npu = pu, npl = pu / bs.pdf;
+						V3 off = g.n * kRayEps;
+						if (dot(g.n, wiWorld) < 0.f) off = -off;
+						no = g.p + off, nd = wiWorld;
+						ctxP = g.p, ctxN = g.n;
+						// Interaction::getMedium(dir), raytracing.h:163-167
+						const MeshRec &mesh = wf.scene.meshes[g.mesh];
+						if (mesh.mediumIn != mesh.mediumOut) medium = dot(wiWorld, g.n) > 0 ? mesh.mediumOut : mesh.mediumIn;
+					}
+				}
+			}
+			wf.px.rng[pix] = rng.state;
+		}
+		int s = warpPush(&dc->nShadow, pushShadow);
+		if (s >= 0) {
+			stcs4(wf.shadow.o_tmax + s, make_float4(so.x, so.y, so.z, 1.f));
+			stcs4(wf.shadow.d_pix + s, make_float4(sdv.x, sdv.y, sdv.z, __int_as_float(pix)));
+			stcs4(wf.shadow.contrib + s, sContrib);
+			if (wf.p.enableMedium) { stcs4(wf.shadow.pu + s, sPu); stcs4(wf.shadow.pl + s, sPl); }
+		}
+		s = warpPush(&dc[1].nRay, pushNext);
+		if (s >= 0) {
+			stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, time));
+			stcs4(nq.d_medium + s, make_float4(nd.x, nd.y, nd.z, __int_as_float(medium)));
+			stcs4(nq.thp + s, nthp);
+			stcs4(nq.pu + s, npu);
+			stcs4(nq.pl + s, npl);
+			stcs4(nq.ctxP_pix + s, make_float4(ctxP.x, ctxP.y, ctxP.z, __int_as_float(pix)));
+			stcs4(nq.ctxN_dep + s, make_float4(ctxN.x, ctxN.y, ctxN.z, __int_as_float((itemDepth + 1) | (nflags << 8))));
+		}
+	}
+}
+
+// =================================================================================================
+// Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean()
+__global__ void __launch_bounds__(128) k_trace_shadow(Wavefront wf, int depth) {
+	DepthCounters *dc = wf.counters + depth;
+	const int n		  = dc->nShadow;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float4 o4 = ldcs4(wf.shadow.o_tmax + i), d4 = ldcs4(wf.shadow.d_pix + i);
+		V3 o = mk3(o4), d = mk3(d4);
+		int overflow = 0;
+		Hit h = traverse<true>(wf.bvh, wf.scene.instances, o, d, o4.w,
+			[&](int inst, int prim, float u, float v) {
+				uint8_t f = wf.instFlags[inst];
+				if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
+				if (f & 2) return !alphaKilled(wf, inst, prim, u, v, o, d);
+				return true;
+			}, &overflow);
+		if (overflow) atomicExch(&wf.errorFlags[0], 1);
+		if (h.inst < 0) {
+			int pix = __float_as_int(d4.w);
+			wf.px.L[pix] = ldcs4(wf.shadow.contrib + i) + wf.px.L[pix];
+		}
+	}
+}
+
+// per-sample resolve (integrator.cpp:257-260).  Note the reference does NOT reset L between the
+// samples of one frame, so sample k adds the running sum; kept as is.
+__global__ void k_resolve(Wavefront wf) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
+		Wavelengths wl = expandWavelengths(wf.px.lambda[i]);
+		float rgb[3];
+		toRGB(wf.px.L[i], wl, wf.scene.cs, rgb);
+		float4 p = wf.px.pixel[i];
+		wf.px.pixel[i] = make_float4(p.x + rgb[0], p.y + rgb[1], p.z + rgb[2], 0.f);
+	}
+}
+
+// film write (integrator.cpp:262-266): /spp, optional clamp, alpha 1, row H-1-y (cuda.h:33-36)
+__global__ void k_film(Wavefront wf, float4 *film, int zeroOutside) {
+	const int N = wf.p.width * wf.p.height;
+	for (int pixelId = blockIdx.x * blockDim.x + threadIdx.x; pixelId < N; pixelId += gridDim.x * blockDim.x) {
+		int i = pixelId - wf.p.pixelBegin;
+		int x = pixelId % wf.p.width, y = pixelId / wf.p.width;
+		float4 *dst = film + (size_t) (wf.p.height - 1 - y) * wf.p.width + x;
+		if (i < 0 || i >= wf.p.pixelCount) {
+			if (zeroOutside) *dst = make_float4(0, 0, 0, 0);
+			continue;
+		}
+		float4 p  = wf.px.pixel[i];
+		float spp = (float) wf.p.spp;
+		float r = p.x / spp, g = p.y / spp, b = p.z / spp;
+		if (wf.p.enableClamp) {
+			r = fminf(fmaxf(r, 0.f), wf.p.clampMax), g = fminf(fmaxf(g, 0.f), wf.p.clampMax), b = fminf(fmaxf(b, 0.f), wf.p.clampMax);
+		}
+		*dst = make_float4(r, g, b, 1.f);
+	}
+}
+
+// end-of-sample bookkeeping: fold the per-depth counters into 64-bit totals and clear them
+struct StatTotals {
+	unsigned long long camera, closest, shadow, scatter, hitLight, miss, mediumSample, mediumScatter;
+	unsigned long long closestByDepth[64], shadowByDepth[64];
+};
+__global__ void k_fold_counters(DepthCounters *c, StatTotals *t, int nDepth, int cameraRays) {
+	int d = threadIdx.x;
+	if (d == 0) atomicAdd(&t->camera, (unsigned long long) cameraRays);
+	if (d >= nDepth) return;
+	DepthCounters dc = c[d];
+	int sc = 0;
+	for (int k = 0; k < MAT_COUNT; k++) sc += dc.nScatter[k];
+	atomicAdd(&t->closest, (unsigned long long) dc.nRay);
+	atomicAdd(&t->shadow, (unsigned long long) dc.nShadow);
+	atomicAdd(&t->scatter, (unsigned long long) sc);
+	atomicAdd(&t->hitLight, (unsigned long long) dc.nHitLight);
+	atomicAdd(&t->miss, (unsigned long long) dc.nMiss);
+	atomicAdd(&t->mediumSample, (unsigned long long) dc.nMediumSample);
+	atomicAdd(&t->mediumScatter, (unsigned long long) dc.nMediumScatter);
+	if (d < 64) { t->closestByDepth[d] += dc.nRay; t->shadowByDepth[d] += dc.nShadow; }
+	DepthCounters z = {};
+	c[d] = z;
+}
+
+// debug tap: integer fields of the queues at one (sample, depth)
+__global__ void k_capture(Wavefront wf, int depth, int queue, int4 *out, int32_t *outCount) {
+	const RayQueue q  = wf.rays[depth & 1];
+	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
+	DepthCounters *dc = wf.counters + depth;
+	int n = 0;
+	switch (queue) {
+		case 0: n = dc->nRay; break;
+		case 1: n = dc->nMiss; break;
+		case 2: n = dc->nHitLight; break;
+		case 3: for (int k = 0; k < MAT_COUNT; k++) n += dc->nScatter[k]; break;
+		case 4: n = dc->nShadow; break;
+		case 5: n = dc[1].nRay; break;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) *outCount = n;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		int4 r = make_int4(0, 0, 0, -1);
+		auto fromRay = [&](const RayQueue &rq, int i) {
+			int packed = __float_as_int(rq.ctxN_dep[i].w);
+			r.x = wf.p.pixelBegin + __float_as_int(rq.ctxP_pix[i].w), r.y = packed & 0xff, r.z = packed >> 8;
+		};
+		if (queue == 0) fromRay(q, k);
+		else if (queue == 5) fromRay(nq, k);
+		else if (queue == 1) fromRay(q, wf.missIdx[k]);
+		else if (queue == 2) {
+			int i = wf.hitLightIdx[k];
+			fromRay(q, i);
+			int4 hit = wf.hits[i];
+			r.w = wf.scene.instances[hit.x].lightBase + hit.y;
+		} else if (queue == 3) {
+			int kk = k, mt = 0;
+			while (kk >= dc->nScatter[mt]) kk -= dc->nScatter[mt], mt++;
+			int i = wf.scatterIdx[mt][kk];
+			fromRay(q, i);
+			r.w = mt;
+		} else if (queue == 4) {
+			r.x = wf.p.pixelBegin + __float_as_int(wf.shadow.d_pix[k].w), r.y = 0, r.z = 0;
+		}
+		out[k] = r;
+	}
+}
+
+// AccumulatePass kernel (src/render/passes/accumulate/accumulate.cu:30-52)
+__global__ void k_accumulate(float4 *accum, float4 *film, long long n, unsigned long long accumCount, unsigned long long maxAccum, int movingAverage) {
+	for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		float w	 = 1.f / (accumCount + 1);
+		float4 c = film[i], a;
+		if (accumCount > 0) {
+			a = accum[i];
+			if (movingAverage) a = make_float4(a.x * (1 - w) + c.x * w, a.y * (1 - w) + c.y * w, a.z * (1 - w) + c.z * w, a.w * (1 - w) + c.w * w);
+			else if (!maxAccum || accumCount < maxAccum) a = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+		} else a = c;
+		accum[i] = a;
+		film[i]	 = movingAverage ? a : make_float4(a.x * w, a.y * w, a.z * w, a.w * w);
+	}
+}
+
+} // namespace krr

@@ -1,0 +1,119 @@
+// host_c_api.cpp -- C entry points of the host layer (include/krr_host_c.h).
+#include "krr_host.h"
+#include "krr_host_c.h"
+
+#include <cstring>
+
+using namespace krr;
+
+struct KrrHostApp {
+	RenderApp app;
+};
+
+static thread_local std::string gErr;
+#define KRR_TRY try {
+#define KRR_CATCH } catch (const std::exception &e) { gErr = e.what(); return KRR_E_INVALID; } return KRR_OK;
+
+extern "C" const char *krr_host_last_error(void) { return gErr.c_str(); }
+
+extern "C" int krr_host_set_data_dir(const char *dir) { setDataDir(dir ? dir : ""); return KRR_OK; }
+
+extern "C" int krr_host_app_create(const char *config, int is_path, const char *asset_root, KrrHostApp **out) {
+	KRR_TRY
+	if (!config || !out) throw std::runtime_error("null argument");
+	auto *a = new KrrHostApp();
+	try {
+		if (is_path && !asset_root) a->app.loadConfigFrom(config);
+		else {
+			json j;
+			std::string base = asset_root ? asset_root : ".";
+			if (is_path) {
+				FILE *f = fopen(config, "rb");
+				if (!f) throw std::runtime_error(std::string("cannot open config ") + config);
+				std::string text;
+				char buf[4096];
+				size_t n;
+				while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+				fclose(f);
+				j = json::parse(text);
+			} else j = json::parse(config);
+			a->app.loadConfig(j, base);
+		}
+		if (!a->app.scene()) throw std::runtime_error("config has no scene");
+	} catch (...) { delete a; throw; }
+	*out = a;
+	KRR_CATCH
+}
+
+extern "C" void krr_host_app_destroy(KrrHostApp *app) { delete app; }
+
+extern "C" int krr_host_app_get_resolution(KrrHostApp *app, int32_t *w, int32_t *h) {
+	*w = app->app.frameSize().x, *h = app->app.frameSize().y;
+	return KRR_OK;
+}
+
+extern "C" int krr_host_app_set_resolution(KrrHostApp *app, int32_t w, int32_t h) {
+	KRR_TRY
+	if (w <= 0 || h <= 0) throw std::runtime_error("bad resolution");
+	// before initialize() this only records the size; afterwards it resizes film and passes
+	struct Peek : RenderApp { using RenderApp::RenderApp; };
+	if (app->app.context()->getColorDevice()) app->app.resize(Vector2i{w, h});
+	else {
+		json j = json::object();
+		json r = json::array();
+		r.push_back(json(w)), r.push_back(json(h));
+		j["resolution"] = r;
+		app->app.loadConfig(j, ".");
+	}
+	KRR_CATCH
+}
+
+extern "C" const KrrSceneDesc *krr_host_app_scene_desc(KrrHostApp *app) {
+	try { return &app->app.scene()->desc(); } catch (const std::exception &e) { gErr = e.what(); return nullptr; }
+}
+
+extern "C" int krr_host_app_get_camera(KrrHostApp *app, double t, KrrCameraData *out) {
+	KRR_TRY
+	auto s = app->app.scene();
+	s->setAspectRatio((float) app->app.frameSize().x / app->app.frameSize().y);
+	s->update(app->app.frameIndex(), t);
+	*out = s->camera;
+	KRR_CATCH
+}
+
+extern "C" int krr_host_app_get_wfpt_params(KrrHostApp *app, char *buf, int32_t cap) {
+	auto p = app->app.findPass<WavefrontPathTracer>();
+	if (!p) { gErr = "config has no WavefrontPathTracer pass"; return KRR_E_STATE; }
+	std::string s = p->toJson().dump();
+	if ((int) s.size() + 1 > cap) return KRR_E_INVALID;
+	memcpy(buf, s.c_str(), s.size() + 1);
+	return (int) s.size();
+}
+
+extern "C" int krr_host_app_set_wfpt_params(KrrHostApp *app, const char *params) {
+	KRR_TRY
+	auto p = app->app.findPass<WavefrontPathTracer>();
+	if (!p) throw std::runtime_error("config has no WavefrontPathTracer pass");
+	json cur = p->toJson(), upd = json::parse(params);
+	for (auto &kv : upd.members()) cur[kv.first] = kv.second;
+	p->fromJson(cur);
+	KRR_CATCH
+}
+
+extern "C" int krr_host_app_render_frames(KrrHostApp *app, int32_t n, float *film) {
+	KRR_TRY
+	for (int i = 0; i < n; i++) app->app.renderFrame(0.0);
+	if (film) {
+		std::vector<float> host;
+		app->app.readFilm(host);
+		memcpy(film, host.data(), host.size() * 4);
+	}
+	KRR_CATCH
+}
+
+extern "C" KrrWfpt *krr_host_app_wfpt_handle(KrrHostApp *app) {
+	auto p = app->app.findPass<WavefrontPathTracer>();
+	return p ? p->handle() : nullptr;
+}
+
+extern "C" uint64_t krr_host_app_frame_index(KrrHostApp *app) { return app->app.frameIndex(); }

@@ -1,0 +1,296 @@
+// krr_host.h -- C++17 host layer that keeps the reference's plugin surface for the
+// WavefrontPathTracer pass and talks to the CUDA kernels ONLY through the C ABI (include/krr_wfpt.h).
+//
+// Mirrors (same names, argument meaning and defaults):
+//   RenderPass / RenderPassFactory / KRR_REGISTER_PASS_DEC|DEF   reference src/core/renderpass.h:138-273
+//   RenderContext (film = RGBA32F colour target)                 src/core/renderpass.h:19-136
+//   WavefrontPathTracer + its JSON params                        src/render/wavefront/integrator.h:24-104
+//   RenderApp::loadConfig / render loop (headless)               src/main/renderer.cpp:84-122, 258-316
+//   SceneImporter (KRR JSON scene schema)                        src/scene/krrscene.cpp:8-349
+//   OBJ/MTL material mapping                                     src/scene/assimp.cpp:60-65, 93-226
+//   Camera / OrbitCameraController                               src/core/camera.{h,cpp}
+// Windowing, Vulkan interop, UI and the other importers are out of scope.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "json.h"
+#include "krr_wfpt.h"
+
+namespace krr {
+
+using json	 = Json;
+using string = std::string;
+
+struct Vector2i { int x = 0, y = 0; int operator[](int i) const { return i ? y : x; } };
+
+// ------------------------------------------------------------------------------------------------
+// Scene: flattened host scene graph (instances carry global transforms), owns all arrays the
+// KrrSceneDesc view points into.
+// ------------------------------------------------------------------------------------------------
+struct HostMesh {
+	string name;
+	std::vector<float> positions, normals, texcoords, tangents;
+	std::vector<int32_t> indices;
+	int material = -1, mediumInside = -1, mediumOutside = -1;
+	float Le[3]	 = {0, 0, 0};
+};
+
+struct HostInstance {
+	int mesh = 0;
+	float transform[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+	std::vector<KrrSRT> motionKeys;
+	// simple keyframe animation (reference src/core/animation.h): linear SRT keys over time
+	std::vector<float> animTimes;
+	std::vector<KrrSRT> animKeys;
+};
+
+struct HostMaterial {
+	string name;
+	KrrMaterialDesc desc{};
+	std::vector<float> etaLambdas, etaValues, kLambdas, kValues;
+	std::vector<std::vector<float>> images; // per texture slot
+};
+
+struct HostMedium {
+	string name;
+	KrrMediumDesc desc{};
+	std::vector<float> density;
+	float boundMin[3] = {0, 0, 0}, boundMax[3] = {0, 0, 0};
+	bool hasBound = false;
+};
+
+// OrbitCameraController::CameraControllerData, src/core/camera.h:149-156
+struct CameraControllerData {
+	float target[3] = {0, 0, 0};
+	float radius = 5, pitch = 0, yaw = 0;
+};
+
+class Scene {
+public:
+	using SharedPtr = std::shared_ptr<Scene>;
+
+	std::vector<HostMesh> meshes;
+	std::vector<HostInstance> instances;
+	std::vector<HostMaterial> materials;
+	std::vector<KrrLightDesc> lights;
+	std::vector<HostMedium> media;
+	KrrSceneOptions options{1, 0, 0, 0.f, 1.f};
+	KrrCameraData camera;
+	CameraControllerData cameraController;
+	bool hasCameraController = false;
+	bool animated			 = false;
+
+	Scene();
+	// Scene::update, src/core/scene.cpp:17-31: animate -> camera controller -> camera
+	bool update(size_t frameIndex, double currentTime);
+	void setAspectRatio(float aspect); // renderer.cpp:28 + Camera::update (camera.cpp:6-17)
+	// flat view for the C ABI; pointers stay valid until the scene is modified
+	const KrrSceneDesc &desc();
+	void boundingBox(float lo[3], float hi[3]) const;
+	uint64_t version() const { return mVersion; }
+	void touch() { mVersion++; }
+	// instance ids whose transform changed in the last update() (drives TLAS refit)
+	std::vector<int32_t> updatedInstances;
+
+private:
+	KrrSceneDesc mDesc{};
+	std::vector<KrrMeshDesc> mMeshDescs;
+	std::vector<KrrInstanceDesc> mInstanceDescs;
+	std::vector<KrrMaterialDesc> mMaterialDescs;
+	std::vector<KrrMediumDesc> mMediumDescs;
+	uint64_t mVersion = 1;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Importers
+// ------------------------------------------------------------------------------------------------
+class SceneImporter {
+public:
+	// src/scene/krrscene.cpp:253-305
+	static bool import(const json &j, Scene::SharedPtr scene, const string &baseDir);
+	static bool loadModel(const string &filepath, Scene::SharedPtr scene, const float nodeTransform[12],
+						  const string &baseDir);
+};
+bool loadObj(const string &filepath, Scene &scene, const float nodeTransform[12]);
+
+// ------------------------------------------------------------------------------------------------
+// RenderContext / RenderPass / factory
+// ------------------------------------------------------------------------------------------------
+class RenderContext {
+public:
+	// headless stand-in for RenderTexture/CudaRenderTarget (renderpass.h:19-136, device/cuda.h:17-53):
+	// a linear device buffer of float4[W*H], RGBA32F like renderpass.cpp:44
+	float *getColorDevice() const { return mColor; }
+	Vector2i getSize() const { return mSize; }
+	void *getStream() const { return mStream; }
+	void resize(Vector2i size);
+	void readback(std::vector<float> &host) const;
+	~RenderContext();
+
+private:
+	float *mColor = nullptr;
+	Vector2i mSize;
+	void *mStream = nullptr;
+};
+
+class RenderApp;
+
+class RenderPass {
+public:
+	using SharedPtr = std::shared_ptr<RenderPass>;
+	RenderPass()		  = default;
+	virtual ~RenderPass() = default;
+
+	virtual void resize(const Vector2i &size) { mFrameSize = size; }
+	virtual void setEnable(bool enable) { mEnable = enable; }
+	virtual void setScene(Scene::SharedPtr scene) { mScene = scene; }
+	virtual Scene::SharedPtr getScene() { return mScene; }
+	virtual void tick(float elapsedSeconds) {}
+	virtual void beginFrame(RenderContext *context) {}
+	virtual void render(RenderContext *context) {}
+	virtual void endFrame(RenderContext *context) {}
+	virtual void renderUI() {}
+	virtual void initialize() {}
+	virtual void finalize() {}
+	virtual bool isCudaPass() const { return true; }
+	virtual string getName() const { return "RenderPass"; }
+	virtual bool enabled() const { return mEnable; }
+	virtual json toJson() const { return json::object(); }
+	// the reference pulls these from DeviceManager (renderpass.cpp:120-126); the headless app sets them
+	void setFrameIndex(size_t i) { mFrameIndex = i; }
+
+protected:
+	size_t getFrameIndex() const { return mFrameIndex; }
+	Vector2i getFrameSize() const { return mFrameSize; }
+	bool mEnable = true;
+	Scene::SharedPtr mScene;
+	size_t mFrameIndex = 0;
+	Vector2i mFrameSize;
+};
+
+class RenderPassFactory {
+public:
+	typedef std::map<string, std::function<RenderPass::SharedPtr(void)>> map_type;
+	typedef std::map<string, std::function<RenderPass::SharedPtr(const json &)>> configured_map_type;
+	static RenderPass::SharedPtr createInstance(std::string const &s);
+	static RenderPass::SharedPtr deserizeInstance(std::string const &s, const json &serde);
+	static std::shared_ptr<map_type> getMap();
+	static std::shared_ptr<configured_map_type> getConfiguredMap();
+};
+
+template <typename T> class RenderPassRegister : RenderPassFactory {
+public:
+	RenderPassRegister(const string &s) {
+		getMap()->insert(std::make_pair(s, []() -> RenderPass::SharedPtr { return std::make_shared<T>(); }));
+		getConfiguredMap()->insert(std::make_pair(s, [](const json &j) -> RenderPass::SharedPtr {
+			auto p = std::make_shared<T>();
+			p->fromJson(j);
+			return p;
+		}));
+	}
+};
+#define KRR_REGISTER_PASS_DEC(name) static RenderPassRegister<name> reg;
+#define KRR_REGISTER_PASS_DEF(name) RenderPassRegister<name> name::reg(#name);
+
+// ------------------------------------------------------------------------------------------------
+// The pass (integrator.h:24-104).  Every method forwards to the C ABI.
+// ------------------------------------------------------------------------------------------------
+class WavefrontPathTracer : public RenderPass {
+public:
+	using SharedPtr = std::shared_ptr<WavefrontPathTracer>;
+	KRR_REGISTER_PASS_DEC(WavefrontPathTracer);
+
+	WavefrontPathTracer() = default;
+	~WavefrontPathTracer() override;
+
+	void resize(const Vector2i &size) override;
+	void setScene(Scene::SharedPtr scene) override;
+	void beginFrame(RenderContext *context) override;
+	void render(RenderContext *context) override;
+	void initialize() override;
+	string getName() const override { return "WavefrontPathTracer"; }
+
+	void fromJson(const json &j);
+	json toJson() const override;
+	KrrWfpt *handle() { return mHandle; }
+	KrrStats stats();
+
+	// path tracing parameters (integrator.h:78-88)
+	int samplesPerPixel{1};
+	int maxDepth{10};
+	float probRR{0.8f};
+	bool enableNEE{true};
+	bool enableMedium{true};
+	bool enableClamp{false};
+	float clampMax{1e3f};
+
+private:
+	void ensureHandle();
+	void pushParams();
+	KrrWfpt *mHandle = nullptr;
+	uint64_t mSceneVersion = 0;
+};
+
+// AccumulatePass: src/render/passes/accumulate/accumulate.{h,cu}
+class AccumulatePass : public RenderPass {
+public:
+	KRR_REGISTER_PASS_DEC(AccumulatePass);
+	enum class Mode { Accumulate, MovingAverage, Count };
+	void resize(const Vector2i &size) override;
+	void render(RenderContext *context) override;
+	void reset() { mAccumCount = 0; }
+	string getName() const override { return "AccumulatePass"; }
+	void fromJson(const json &j);
+	json toJson() const override;
+	~AccumulatePass() override;
+	size_t accumCount() const { return mAccumCount; }
+	size_t maxAccumCount = 0; // "spp": 0 = unlimited
+	Mode mode = Mode::Accumulate;
+
+private:
+	float *mAccum = nullptr;
+	size_t mAccumCount = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Headless RenderApp (renderer.cpp): loads the same JSON config, drives beginFrame/render/endFrame
+// ------------------------------------------------------------------------------------------------
+class RenderApp {
+public:
+	void loadConfigFrom(const string &path);
+	void loadConfig(const json &config, const string &baseDir);
+	void setScene(Scene::SharedPtr scene);
+	void resize(Vector2i size);
+	void initialize();
+	// one iteration of DeviceManager::runMessageLoop (window.cpp:450-485): ++frameIndex; tick; render
+	void renderFrame(double timeSeconds = 0);
+	void readFilm(std::vector<float> &rgba) { mContext.readback(rgba); }
+	RenderContext *context() { return &mContext; }
+	Scene::SharedPtr scene() { return mScene; }
+	std::vector<RenderPass::SharedPtr> &passes() { return mRenderPasses; }
+	template <typename T> std::shared_ptr<T> findPass() {
+		for (auto &p : mRenderPasses) if (auto t = std::dynamic_pointer_cast<T>(p)) return t;
+		return nullptr;
+	}
+	size_t frameIndex() const { return mFrameIndex; }
+	Vector2i frameSize() const { return mSize; }
+
+private:
+	std::vector<RenderPass::SharedPtr> mRenderPasses;
+	Scene::SharedPtr mScene;
+	RenderContext mContext;
+	Vector2i mSize{1280, 720};
+	size_t mFrameIndex = 0;
+	bool mInitialized  = false;
+	json mConfig;
+};
+
+// colour-space tables (kiraray_b200/data/spectral_srgb.bin); throws when missing
+const KrrColorSpaceData &defaultColorSpace();
+void setDataDir(const string &dir);
+
+} // namespace krr

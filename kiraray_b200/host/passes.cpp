@@ -1,0 +1,268 @@
+// passes.cpp -- RenderPass factory, the WavefrontPathTracer / AccumulatePass host classes and the
+// headless RenderApp.  Kernels are reached only through the C ABI (include/krr_wfpt.h).
+// Reference: src/core/renderpass.{h,cpp}, src/render/wavefront/integrator.{h,cpp},
+// src/render/passes/accumulate/accumulate.{h,cu}, src/main/renderer.cpp.
+#include "krr_host.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace krr {
+
+namespace {
+void check(int rc, const char *what) {
+	if (rc != KRR_OK) throw std::runtime_error(string(what) + ": " + krr_wfpt_last_error());
+}
+void cudaCheck(cudaError_t e, const char *what) {
+	if (e != cudaSuccess) throw std::runtime_error(string(what) + ": " + cudaGetErrorString(e));
+}
+string gDataDir;
+} // namespace
+
+// ---------------- colour-space tables ----------------
+void setDataDir(const string &dir) { gDataDir = dir; }
+
+const KrrColorSpaceData &defaultColorSpace() {
+	static KrrColorSpaceData cs{};
+	static std::vector<float> blob;
+	if (!blob.empty()) return cs;
+	string path = (gDataDir.empty() ? string("kiraray_b200/data") : gDataDir) + "/spectral_srgb.bin";
+	std::ifstream f(path, std::ios::binary);
+	if (!f.good())
+		throw std::runtime_error("colour-space tables not found at " + path +
+								 " (generate with `python oracle/build_oracle.py ref spectral`)");
+	uint32_t hdr[4];
+	f.read((char *) hdr, 16);
+	if (hdr[0] != 0x4b525253u || hdr[2] != 471 || hdr[3] != 64) throw std::runtime_error("bad spectral_srgb.bin header");
+	const size_t n = 4 * 471 + 18 + 64 + 3 * 64 * 64 * 64 * 3;
+	blob.resize(n);
+	f.read((char *) blob.data(), n * 4);
+	if (!f.good()) { blob.clear(); throw std::runtime_error("truncated spectral_srgb.bin"); }
+	const float *p = blob.data();
+	cs.cie_x = p, cs.cie_y = p + 471, cs.cie_z = p + 942, cs.illuminant = p + 1413;
+	p += 4 * 471;
+	memcpy(cs.xyz_from_rgb, p, 36), memcpy(cs.rgb_from_xyz, p + 9, 36);
+	p += 18;
+	cs.z_nodes = p, cs.coeffs = p + 64;
+	return cs;
+}
+
+// ---------------- RenderContext ----------------
+void RenderContext::resize(Vector2i size) {
+	if (size.x == mSize.x && size.y == mSize.y && mColor) return;
+	if (mColor) cudaFree(mColor);
+	mColor = nullptr;
+	mSize  = size;
+	cudaCheck(cudaMalloc((void **) &mColor, (size_t) size.x * size.y * 16), "cudaMalloc(film)");
+	cudaCheck(cudaMemset(mColor, 0, (size_t) size.x * size.y * 16), "cudaMemset(film)");
+	if (!mStream) {
+		cudaStream_t s;
+		cudaCheck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+		mStream = s;
+	}
+}
+void RenderContext::readback(std::vector<float> &host) const {
+	host.resize((size_t) mSize.x * mSize.y * 4);
+	cudaCheck(cudaMemcpyAsync(host.data(), mColor, host.size() * 4, cudaMemcpyDeviceToHost, (cudaStream_t) mStream), "film readback");
+	cudaCheck(cudaStreamSynchronize((cudaStream_t) mStream), "film readback sync");
+}
+RenderContext::~RenderContext() {
+	if (mColor) cudaFree(mColor);
+	if (mStream) cudaStreamDestroy((cudaStream_t) mStream);
+}
+
+// ---------------- factory ----------------
+std::shared_ptr<RenderPassFactory::map_type> RenderPassFactory::getMap() {
+	static std::shared_ptr<map_type> map(new map_type);
+	return map;
+}
+std::shared_ptr<RenderPassFactory::configured_map_type> RenderPassFactory::getConfiguredMap() {
+	static std::shared_ptr<configured_map_type> map(new configured_map_type);
+	return map;
+}
+RenderPass::SharedPtr RenderPassFactory::createInstance(std::string const &s) {
+	auto it = getMap()->find(s);
+	return it == getMap()->end() ? nullptr : it->second();
+}
+RenderPass::SharedPtr RenderPassFactory::deserizeInstance(std::string const &s, const json &serde) {
+	auto it = getConfiguredMap()->find(s);
+	return it == getConfiguredMap()->end() ? nullptr : it->second(serde);
+}
+
+// ---------------- WavefrontPathTracer ----------------
+KRR_REGISTER_PASS_DEF(WavefrontPathTracer);
+
+void WavefrontPathTracer::fromJson(const json &j) {
+	// from_json, integrator.h:96-103
+	enableNEE	 = j.value("nee", true);
+	enableMedium = j.value("enable_medium", true);
+	maxDepth	 = j.value("max_depth", 10);
+	probRR		 = j.value("rr", 0.8f);
+	enableClamp	 = j.value("enable_clamp", false);
+	clampMax	 = j.value("clamp_max", 1e3f);
+	// extension: samplesPerPixel is UI-only in the reference (integrator.cpp:271)
+	samplesPerPixel = j.value("spp", 1);
+}
+json WavefrontPathTracer::toJson() const {
+	json j = json::object();
+	j["nee"] = json(enableNEE), j["enable_medium"] = json(enableMedium), j["max_depth"] = json(maxDepth);
+	j["rr"] = json((double) probRR), j["enable_clamp"] = json(enableClamp), j["clamp_max"] = json((double) clampMax);
+	j["spp"] = json(samplesPerPixel);
+	return j;
+}
+WavefrontPathTracer::~WavefrontPathTracer() { if (mHandle) krr_wfpt_destroy(mHandle); }
+
+void WavefrontPathTracer::ensureHandle() {
+	if (mHandle) return;
+	check(krr_wfpt_create(toJson().dump().c_str(), &mHandle), "krr_wfpt_create");
+	check(krr_wfpt_set_color_space(mHandle, &defaultColorSpace()), "krr_wfpt_set_color_space");
+}
+void WavefrontPathTracer::pushParams() { check(krr_wfpt_set_params(mHandle, toJson().dump().c_str()), "krr_wfpt_set_params"); }
+void WavefrontPathTracer::initialize() { ensureHandle(); }
+
+void WavefrontPathTracer::resize(const Vector2i &size) {
+	RenderPass::resize(size);
+	ensureHandle();
+	check(krr_wfpt_resize(mHandle, size.x, size.y), "krr_wfpt_resize");
+}
+void WavefrontPathTracer::setScene(Scene::SharedPtr scene) {
+	mScene = scene;
+	ensureHandle();
+	check(krr_wfpt_set_scene(mHandle, &scene->desc()), "krr_wfpt_set_scene");
+	mSceneVersion = scene->version();
+}
+void WavefrontPathTracer::beginFrame(RenderContext *context) {
+	if (!mScene || !mHandle) return;
+	pushParams();
+	if (!mScene->updatedInstances.empty()) {
+		std::vector<float> xf(mScene->updatedInstances.size() * 12);
+		for (size_t i = 0; i < mScene->updatedInstances.size(); i++)
+			memcpy(&xf[12 * i], mScene->instances[mScene->updatedInstances[i]].transform, 48);
+		check(krr_wfpt_update_instances(mHandle, mScene->updatedInstances.data(), xf.data(),
+										(int32_t) mScene->updatedInstances.size(), context->getStream()),
+			  "krr_wfpt_update_instances");
+	}
+	check(krr_wfpt_begin_frame(mHandle, getFrameIndex(), &mScene->camera, context->getStream()), "krr_wfpt_begin_frame");
+}
+void WavefrontPathTracer::render(RenderContext *context) {
+	if (!mScene || !mHandle) return;
+	check(krr_wfpt_render(mHandle, context->getColorDevice(), context->getStream()), "krr_wfpt_render");
+}
+KrrStats WavefrontPathTracer::stats() {
+	KrrStats s{};
+	if (mHandle) check(krr_wfpt_get_stats(mHandle, &s), "krr_wfpt_get_stats");
+	return s;
+}
+
+// ---------------- AccumulatePass ----------------
+extern "C" int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,
+								  uint64_t max_accum_count, int32_t moving_average, void *stream);
+KRR_REGISTER_PASS_DEF(AccumulatePass);
+
+void AccumulatePass::fromJson(const json &j) {
+	maxAccumCount = (size_t) j.value("spp", 0);
+	mode		  = j.value("mode", "accumulate") == "moving average" ? Mode::MovingAverage : Mode::Accumulate;
+}
+json AccumulatePass::toJson() const {
+	json j	  = json::object();
+	j["spp"]  = json((long long) maxAccumCount);
+	j["mode"] = json(mode == Mode::MovingAverage ? "moving average" : "accumulate");
+	return j;
+}
+void AccumulatePass::resize(const Vector2i &size) {
+	RenderPass::resize(size);
+	if (mAccum) cudaFree(mAccum);
+	mAccum = nullptr;
+	cudaCheck(cudaMalloc((void **) &mAccum, (size_t) size.x * size.y * 16), "cudaMalloc(accum)");
+	reset();
+}
+void AccumulatePass::render(RenderContext *context) {
+	if (!mAccum) return;
+	check(krr_accumulate_f32(mAccum, context->getColorDevice(), (int64_t) mFrameSize.x * mFrameSize.y, mAccumCount,
+							 maxAccumCount, mode == Mode::MovingAverage, context->getStream()),
+		  "krr_accumulate_f32");
+	if (!maxAccumCount || mAccumCount < maxAccumCount) mAccumCount++;
+}
+AccumulatePass::~AccumulatePass() { if (mAccum) cudaFree(mAccum); }
+
+// ---------------- RenderApp ----------------
+void RenderApp::loadConfigFrom(const string &path) {
+	std::ifstream f(path);
+	if (!f.good()) throw std::runtime_error("cannot open config " + path);
+	std::stringstream ss;
+	ss << f.rdbuf();
+	size_t s = path.find_last_of('/');
+	loadConfig(json::parse(ss.str()), s == string::npos ? "." : path.substr(0, s));
+}
+
+void RenderApp::loadConfig(const json &config, const string &baseDir) {
+	// renderer.cpp:258-316
+	if (config.contains("passes")) {
+		for (const json &p : config.at("passes").items()) {
+			string name = p.at("name").asString();
+			RenderPass::SharedPtr pass;
+			if (p.contains("params")) pass = RenderPassFactory::deserizeInstance(name, p.value("params", json::object()));
+			else pass = RenderPassFactory::createInstance(name);
+			if (!pass) continue; // passes outside the hot path (ToneMapping, Denoise, ...) are not built here
+			pass->setEnable(p.value("enable", true));
+			mRenderPasses.push_back(pass);
+		}
+	}
+	Scene::SharedPtr scene = mScene;
+	string assetBase = config.value("asset_root", baseDir);
+	if (config.contains("model")) {
+		if (!scene) scene = std::make_shared<Scene>();
+		float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+		SceneImporter::loadModel(config.at("model").asString(), scene, I, assetBase);
+	}
+	if (config.contains("scene")) {
+		if (!scene) scene = std::make_shared<Scene>();
+		SceneImporter::import(config.at("scene"), scene, assetBase);
+	}
+	if (scene) mScene = scene;
+	if (config.contains("resolution")) {
+		mSize.x = (int) config.at("resolution").at(0).asNumber();
+		mSize.y = (int) config.at("resolution").at(1).asNumber();
+	}
+	mConfig = config;
+}
+
+void RenderApp::setScene(Scene::SharedPtr scene) {
+	mScene = scene;
+	for (auto &p : mRenderPasses) p->setScene(scene);
+}
+
+void RenderApp::resize(Vector2i size) {
+	mSize = size;
+	if (mScene) mScene->setAspectRatio((float) size.x / size.y); // renderer.cpp:26-30
+	mContext.resize(size);
+	for (auto &p : mRenderPasses) p->resize(size);
+}
+
+void RenderApp::initialize() {
+	// renderer.cpp:324-331: setScene, then initialize() on every pass; the back buffer is sized first
+	if (mScene) {
+		mScene->setAspectRatio((float) mSize.x / mSize.y);
+		mScene->update(0, 0);
+	}
+	for (auto &p : mRenderPasses) p->initialize();
+	setScene(mScene);
+	resize(mSize);
+	mInitialized = true;
+}
+
+void RenderApp::renderFrame(double t) {
+	if (!mInitialized) initialize();
+	++mFrameIndex; // the first rendered frame is #1 (window.cpp:457)
+	if (mScene) mScene->update(mFrameIndex, t);
+	for (auto &p : mRenderPasses) p->setFrameIndex(mFrameIndex);
+	for (auto &p : mRenderPasses) if (p->enabled()) p->beginFrame(&mContext);
+	for (auto &p : mRenderPasses) if (p->enabled()) p->render(&mContext);
+	for (auto &p : mRenderPasses) if (p->enabled()) p->endFrame(&mContext);
+}
+
+} // namespace krr

@@ -1,0 +1,797 @@
+/* driver.cpp -- TEST INFRASTRUCTURE ONLY (checker; never shipped, never on the product path).
+ *
+ * CPU restatement of the reference's WavefrontPathTracer stage bodies, run depth-first per pixel
+ * (each pixel's RNG stream and accumulator are private, so depth-first execution yields the same
+ * per-pixel results as the wavefront order -- SURVEY.md section 8d):
+ *   beginFrame            src/render/wavefront/integrator.cpp:205-221
+ *   generateCameraRays    integrator.cpp:166-179
+ *   Closest CH/AH/MS      src/render/wavefront/device.cu:43-81
+ *   prepareSurfaceInter.  src/render/shading.h:115-226   (getHitInfo :78-87)
+ *   handleHit / Miss      integrator.cpp:78-108
+ *   generateScatterRays   integrator.cpp:110-164
+ *   Shadow RG/AH/MS       device.cu:83-100
+ *   resolve + film write  integrator.cpp:257-266, src/core/device/cuda.h:33-45
+ *   scene upload          src/core/device/scene.cpp:28-173, src/core/mesh.cpp:16-63
+ * All leaf maths (sampler, camera, spectra, BSDFs, lights) comes through oracle_leaf.h, i.e. from
+ * the reference's own classes (backend_ref) or from the plain-C++ port (backend_port).
+ *
+ * Ray/triangle intersection and traversal are NOT in the reference (closed NVIDIA OptiX,
+ * device.cu:15); this build specifies its own routine (see DESIGN.md "Intersection spec") and the
+ * CUDA kernels implement the same arithmetic, so first-hit ids are comparable bit-for-bit.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include <atomic>
+#include <thread>
+
+#include "driver.h"
+#include "oracle_leaf.h"
+
+namespace {
+
+struct V3 {
+	float x, y, z;
+	float operator[](int i) const { return (&x)[i]; }
+	float &operator[](int i) { return (&x)[i]; }
+};
+inline V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 mk(const float *p) { return V3{p[0], p[1], p[2]}; }
+inline V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) {
+	return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+inline float length(V3 a) { return std::sqrt(dot(a, a)); }
+inline V3 normalize(V3 a) {
+	float z = dot(a, a);
+	return z > 0 ? a / std::sqrt(z) : a; /* Eigen normalized(): unchanged when the norm is 0 */
+}
+inline void st(float *o, V3 v) { o[0] = v.x, o[1] = v.y, o[2] = v.z; }
+
+struct Spec {
+	float v[4];
+	float operator[](int i) const { return v[i]; }
+	float &operator[](int i) { return v[i]; }
+};
+inline Spec sconst(float c) { return Spec{{c, c, c, c}}; }
+inline Spec operator*(Spec a, Spec b) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] * b.v[i]; return r; }
+inline Spec operator*(Spec a, float s) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] * s; return r; }
+inline Spec operator/(Spec a, float s) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] / s; return r; }
+inline Spec operator+(Spec a, Spec b) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline bool any(Spec a) { return a.v[0] != 0 || a.v[1] != 0 || a.v[2] != 0 || a.v[3] != 0; }
+/* Eigen mean() of 4 floats: redux order (a0+a1)+(a2+a3) (packet/halving reduction), then /4 */
+inline float mean(Spec a) { return ((a.v[0] + a.v[1]) + (a.v[2] + a.v[3])) / 4; }
+
+/* ---- 3x4 affine helpers ---- */
+struct Xf { float m[12]; };
+inline V3 xfPoint(const Xf &t, V3 p) {
+	return mk(t.m[0] * p.x + t.m[1] * p.y + t.m[2] * p.z + t.m[3],
+			  t.m[4] * p.x + t.m[5] * p.y + t.m[6] * p.z + t.m[7],
+			  t.m[8] * p.x + t.m[9] * p.y + t.m[10] * p.z + t.m[11]);
+}
+inline V3 xfVector(const Xf &t, V3 p) {
+	return mk(t.m[0] * p.x + t.m[1] * p.y + t.m[2] * p.z, t.m[4] * p.x + t.m[5] * p.y + t.m[6] * p.z,
+			  t.m[8] * p.x + t.m[9] * p.y + t.m[10] * p.z);
+}
+/* (M^-1)^T * n, given inv = M^-1 (Transformation::transposedInverse, raytracing.h:91-93) */
+inline V3 xfNormal(const Xf &inv, V3 n) {
+	return mk(inv.m[0] * n.x + inv.m[4] * n.y + inv.m[8] * n.z, inv.m[1] * n.x + inv.m[5] * n.y + inv.m[9] * n.z,
+			  inv.m[2] * n.x + inv.m[6] * n.y + inv.m[10] * n.z);
+}
+/* Affine inverse, cofactors in double, rounded once to float.  DESIGN.md "Intersection spec":
+ * the product's scene upload uses the identical routine so object-space rays match bit-for-bit. */
+Xf xfInverse(const Xf &t) {
+	double a = t.m[0], b = t.m[1], c = t.m[2], d = t.m[4], e = t.m[5], f = t.m[6], g = t.m[8], h = t.m[9], i = t.m[10];
+	double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+	double det = a * A + b * B + c * C;
+	double id  = 1.0 / det;
+	double r[9] = {A * id, -(b * i - c * h) * id, (b * f - c * e) * id,
+				   B * id, (a * i - c * g) * id,  -(a * f - c * d) * id,
+				   C * id, -(a * h - b * g) * id, (a * e - b * d) * id};
+	double tx = t.m[3], ty = t.m[7], tz = t.m[11];
+	Xf o;
+	for (int k = 0; k < 3; k++) {
+		o.m[k * 4 + 0] = (float) r[k * 3 + 0];
+		o.m[k * 4 + 1] = (float) r[k * 3 + 1];
+		o.m[k * 4 + 2] = (float) r[k * 3 + 2];
+		o.m[k * 4 + 3] = (float) -(r[k * 3 + 0] * tx + r[k * 3 + 1] * ty + r[k * 3 + 2] * tz);
+	}
+	return o;
+}
+
+/* ---- scene ---- */
+struct Mesh {
+	std::vector<V3> P, N, T;
+	std::vector<float> UV;
+	std::vector<int32_t> I;
+	int material, mediumIn, mediumOut;
+	V3 Le;
+	int ntri() const { return (int) I.size() / 3; }
+};
+struct Instance {
+	int mesh;
+	Xf xf, inv;
+	int lightBase; /* index of this instance's first triangle light in Scene::lights, -1 = none */
+};
+struct LightRef {
+	int type;	 /* KRR_LIGHT_* */
+	int inst, prim; /* diffuse area */
+	int analytic;	/* index into Scene::analytic */
+};
+struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
+
+} // namespace
+
+struct OrcScene {
+	std::vector<Mesh> meshes;
+	std::vector<Instance> instances;
+	std::vector<KrrMaterialDesc> materials;
+	std::vector<LightRef> lights;
+	std::vector<OlLight> analytic;
+	std::vector<int> infinite; /* indices into analytic */
+	/* flattened world-independent primitive list for the BVH: (instance, prim) in object space */
+	struct Prim { int inst, prim; };
+	std::vector<Prim> prims;
+	std::vector<BvhNode> bvh;
+	std::vector<Prim> bvhPrims;
+};
+
+namespace {
+
+/* ------------------------------------------------------------------------------------------------
+ * Intersection spec (shared with kiraray_b200/csrc/intersect.cuh -- keep the arithmetic identical):
+ *  - the world ray is moved to object space with the instance's inverse 3x4: o' = Minv*o (point),
+ *    d' = Minv*d (vector); t is therefore the world-space parameter (d is not renormalised)
+ *  - Moeller-Trumbore, every product and sum individually rounded (no FMA), in the order below
+ *  - accept 0 < t < tmax; among equal t the smaller (instance, primitive) wins, so the result is
+ *    independent of traversal order
+ * ---------------------------------------------------------------------------------------------- */
+inline bool triIntersect(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float tmax, float &t, float &u, float &v) {
+	V3 e1 = v1 - v0, e2 = v2 - v0;
+	V3 pv = cross(d, e2);
+	float det = dot(e1, pv);
+	if (det == 0.f) return false;
+	float inv = 1.f / det;
+	V3 tv = o - v0;
+	u = dot(tv, pv) * inv;
+	if (!(u >= 0.f && u <= 1.f)) return false;
+	V3 qv = cross(tv, e1);
+	v = dot(d, qv) * inv;
+	if (!(v >= 0.f && u + v <= 1.f)) return false;
+	t = dot(e2, qv) * inv;
+	return t > 0.f && t < tmax;
+}
+
+struct Hit { int inst = -1, prim = -1; float t = 0, u = 0, v = 0; };
+
+inline bool better(float t, int inst, int prim, const Hit &h) {
+	if (h.inst < 0) return true;
+	if (t != h.t) return t < h.t;
+	if (inst != h.inst) return inst < h.inst;
+	return prim < h.prim;
+}
+
+void testPrim(const OrcScene &s, int ii, int pi, V3 o, V3 d, float tmax, Hit &best) {
+	const Instance &in = s.instances[ii];
+	const Mesh &m	   = s.meshes[in.mesh];
+	V3 oo = xfPoint(in.inv, o), dd = xfVector(in.inv, d);
+	const int32_t *idx = &m.I[3 * pi];
+	float t, u, v;
+	if (triIntersect(oo, dd, m.P[idx[0]], m.P[idx[1]], m.P[idx[2]], tmax, t, u, v))
+		if (better(t, ii, pi, best)) best = Hit{ii, pi, t, u, v};
+}
+
+void primBounds(const OrcScene &s, const OrcScene::Prim &p, float lo[3], float hi[3]) {
+	const Instance &in = s.instances[p.inst];
+	const Mesh &m	   = s.meshes[in.mesh];
+	for (int k = 0; k < 3; k++) lo[k] = 1e30f, hi[k] = -1e30f;
+	for (int c = 0; c < 3; c++) {
+		V3 w = xfPoint(in.xf, m.P[m.I[3 * p.prim + c]]);
+		for (int k = 0; k < 3; k++) lo[k] = std::min(lo[k], w[k]), hi[k] = std::max(hi[k], w[k]);
+	}
+	/* pad: world-space boxes are only a culling aid for object-space tests; keep them conservative */
+	for (int k = 0; k < 3; k++) {
+		float e = 1e-4f * std::max(1.f, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+		lo[k] -= e, hi[k] += e;
+	}
+}
+
+int buildBvh(OrcScene &s, int first, int count) {
+	BvhNode n;
+	for (int k = 0; k < 3; k++) n.lo[k] = 1e30f, n.hi[k] = -1e30f;
+	float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+	for (int i = first; i < first + count; i++) {
+		float lo[3], hi[3];
+		primBounds(s, s.bvhPrims[i], lo, hi);
+		for (int k = 0; k < 3; k++) {
+			n.lo[k] = std::min(n.lo[k], lo[k]), n.hi[k] = std::max(n.hi[k], hi[k]);
+			float c = 0.5f * (lo[k] + hi[k]);
+			clo[k] = std::min(clo[k], c), chi[k] = std::max(chi[k], c);
+		}
+	}
+	n.left = n.right = -1, n.first = first, n.count = count;
+	int id = (int) s.bvh.size();
+	s.bvh.push_back(n);
+	if (count <= 4) return id;
+	int axis = 0;
+	for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+	if (chi[axis] - clo[axis] <= 0) return id;
+	int mid = first + count / 2;
+	std::nth_element(s.bvhPrims.begin() + first, s.bvhPrims.begin() + mid, s.bvhPrims.begin() + first + count,
+		[&](const OrcScene::Prim &a, const OrcScene::Prim &b) {
+			float lo[3], hi[3], lo2[3], hi2[3];
+			primBounds(s, a, lo, hi); primBounds(s, b, lo2, hi2);
+			return lo[axis] + hi[axis] < lo2[axis] + hi2[axis];
+		});
+	int l = buildBvh(s, first, mid - first);
+	int r = buildBvh(s, mid, first + count - mid);
+	s.bvh[id].left = l, s.bvh[id].right = r, s.bvh[id].count = 0;
+	return id;
+}
+
+inline bool boxHit(const BvhNode &n, V3 o, V3 invd, float tmax) {
+	float t0 = 0, t1 = tmax;
+	for (int k = 0; k < 3; k++) {
+		float a = (n.lo[k] - o[k]) * invd[k], b = (n.hi[k] - o[k]) * invd[k];
+		if (a > b) std::swap(a, b);
+		if (a != a || b != b) continue; /* NaN (0*inf): slab gives no information */
+		t0 = a > t0 ? a : t0;
+		t1 = b < t1 ? b : t1;
+	}
+	return t0 <= t1 * 1.0000004f + 1e-30f;
+}
+
+/* closest hit over the whole scene; `skipNull`/anyhit variants below */
+template <typename Accept>
+Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, Accept accept) {
+	Hit best;
+	if (!useBvh || s.bvh.empty()) {
+		for (int ii = 0; ii < (int) s.instances.size(); ii++) {
+			int nt = s.meshes[s.instances[ii].mesh].ntri();
+			for (int pi = 0; pi < nt; pi++) {
+				Hit h;
+				testPrim(s, ii, pi, o, d, best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), h);
+				if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
+			}
+		}
+		return best;
+	}
+	V3 invd = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
+	int stack[128], sp = 0;
+	stack[sp++] = 0;
+	while (sp) {
+		const BvhNode &n = s.bvh[stack[--sp]];
+		float lim = best.inst < 0 ? tmax : best.t;
+		if (!boxHit(n, o, invd, lim)) continue;
+		if (n.left < 0) {
+			for (int i = n.first; i < n.first + n.count; i++) {
+				Hit h;
+				testPrim(s, s.bvhPrims[i].inst, s.bvhPrims[i].prim, o, d,
+						 best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), h);
+				if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
+			}
+		} else {
+			stack[sp++] = n.left;
+			stack[sp++] = n.right;
+		}
+	}
+	return best;
+}
+
+/* ---- texture sampling: sampleTexture, shading.h:35-44 (constant, or bilinear wrap image) ---- */
+void sampleTex(const KrrTextureDesc &t, float u, float v, const float fallback[4], float out[4]) {
+	if (!t.valid) { memcpy(out, fallback, 16); return; }
+	if (!t.image) { memcpy(out, t.value, 16); return; }
+	/* cudaFilterModeLinear, normalized coords, wrap: x = u*W - 0.5 */
+	float x = u * t.width - 0.5f, y = v * t.height - 0.5f;
+	float fx = std::floor(x), fy = std::floor(y);
+	float ax = x - fx, ay = y - fy;
+	auto wrap = [](int i, int n) { i %= n; return i < 0 ? i + n : i; };
+	int x0 = wrap((int) fx, t.width), x1 = wrap((int) fx + 1, t.width);
+	int y0 = wrap((int) fy, t.height), y1 = wrap((int) fy + 1, t.height);
+	for (int c = 0; c < 4; c++) {
+		float a = t.image[(y0 * t.width + x0) * 4 + c], b = t.image[(y0 * t.width + x1) * 4 + c];
+		float cc = t.image[(y1 * t.width + x0) * 4 + c], dd = t.image[(y1 * t.width + x1) * 4 + c];
+		out[c] = (1 - ay) * ((1 - ax) * a + ax * b) + ay * ((1 - ax) * cc + ax * dd);
+	}
+}
+
+inline float luminanceRGB(const float c[3]) { return c[0] * 0.299f + c[1] * 0.587f + c[2] * 0.114f; }
+
+/* getPerpendicular, src/util/math_utils.h:122-133 */
+V3 getPerpendicular(V3 u) {
+	V3 a = mk(std::fabs(u.x), std::fabs(u.y), std::fabs(u.z));
+	uint32_t uyx = (a.x - a.y) < 0 ? 1 : 0, uzx = (a.x - a.z) < 0 ? 1 : 0, uzy = (a.y - a.z) < 0 ? 1 : 0;
+	uint32_t xm = uyx & uzx, ym = (1 ^ xm) & uzy, zm = 1 ^ (xm | ym);
+	return normalize(cross(u, mk((float) xm, (float) ym, (float) zm)));
+}
+
+struct SurfIntr {
+	V3 p, wo, n, tangent, bitangent;
+	float uv[2];
+	float time;
+	int material; /* -1 = null */
+	int light;	  /* index into Scene::lights or -1 */
+	int inst, prim;
+	OlShading sd;
+};
+
+/* offsetRayOrigin / spawnRayTowards / spawnRayTo: src/core/raytracing.h:106-160 */
+inline V3 offsetRayOrigin(V3 p, V3 n, V3 w) {
+	V3 off = n * 1e-4f;
+	if (dot(n, w) < 0.f) off = -off;
+	return p + off;
+}
+
+/* prepareSurfaceInteraction, shading.h:115-226 */
+void prepareInteraction(const OrcScene &s, const Hit &h, V3 rayDir, float rayTime, const float lambda[4],
+						const float pdf[4], SurfIntr &it) {
+	const Instance &in = s.instances[h.inst];
+	const Mesh &m	   = s.meshes[in.mesh];
+	float b[3]		   = {1 - h.u - h.v, h.u, h.v}; /* getHitInfo, shading.h:85 */
+	const int32_t *v   = &m.I[3 * h.prim];
+	it.inst = h.inst, it.prim = h.prim;
+	it.time = rayTime;
+	it.wo	= normalize(-normalize(rayDir)); /* hitInfo.wo = -normalize(dir); intr.wo = normalize(hitInfo.wo) */
+	V3 p0 = m.P[v[0]], p1 = m.P[v[1]], p2 = m.P[v[2]];
+	it.p = b[0] * p0 + b[1] * p1 + b[2] * p2;
+	if (!m.N.empty()) it.n = normalize(b[0] * m.N[v[0]] + b[1] * m.N[v[1]] + b[2] * m.N[v[2]]);
+	else it.n = normalize(cross(p1 - p0, p2 - p0));
+	if (!m.T.empty()) {
+		it.tangent = normalize(b[0] * m.T[v[0]] + b[1] * m.T[v[1]] + b[2] * m.T[v[2]]);
+		it.tangent = normalize(it.tangent - it.n * dot(it.n, it.tangent));
+	} else it.tangent = getPerpendicular(it.n);
+	it.bitangent = normalize(cross(it.n, it.tangent));
+	it.uv[0] = it.uv[1] = 0;
+	if (!m.UV.empty())
+		for (int k = 0; k < 2; k++)
+			it.uv[k] = b[0] * m.UV[2 * v[0] + k] + b[1] * m.UV[2 * v[1] + k] + b[2] * m.UV[2 * v[2] + k];
+	it.light	= in.lightBase >= 0 ? in.lightBase + h.prim : -1;
+	it.material = m.material;
+	/* object -> world */
+	it.p		 = xfPoint(in.xf, it.p);
+	it.n		 = normalize(xfNormal(in.inv, it.n));
+	it.tangent	 = normalize(xfNormal(in.inv, it.tangent));
+	it.bitangent = normalize(xfNormal(in.inv, it.bitangent));
+	if (it.material < 0) return;
+
+	const KrrMaterialDesc &mat = s.materials[it.material];
+	memset(&it.sd, 0, sizeof(it.sd));
+	it.sd.bsdfType			   = mat.bsdf_type;
+	it.sd.specularTransmission = mat.specular_transmission;
+	it.sd.IoR				   = mat.ior;
+	if (mat.spectral_eta.kind == KRR_SPEC_CONSTANT) {
+		it.sd.IoR = mat.spectral_eta.a[0];
+		it.sd.etaKind = 1, it.sd.etaValue[0] = mat.spectral_eta.a[0];
+	}
+	if (mat.spectral_k.kind == KRR_SPEC_CONSTANT) it.sd.kKind = 1, it.sd.kValue[0] = mat.spectral_k.a[0];
+	float diff[4], spec[4];
+	sampleTex(mat.textures[KRR_TEX_DIFFUSE], it.uv[0], it.uv[1], mat.diffuse, diff);
+	sampleTex(mat.textures[KRR_TEX_SPECULAR], it.uv[0], it.uv[1], mat.specular, spec);
+	const KrrTextureDesc &nt = mat.textures[KRR_TEX_NORMAL];
+	if (nt.valid && !m.UV.empty()) {
+		float fb[4] = {0, 0, 1, 0}, nv[4];
+		sampleTex(nt, it.uv[0], it.uv[1], fb, nv);
+		V3 nm = mk(2 * nv[0] - 1, 2 * nv[1] - 1, 2 * nv[2] - 1);
+		it.n  = normalize(it.tangent * nm.x + it.bitangent * nm.y + it.n * nm.z);
+		it.tangent	 = normalize(it.tangent - it.n * dot(it.tangent, it.n));
+		it.bitangent = normalize(cross(it.n, it.tangent));
+	}
+	float diffuse[3], specular[3];
+	if (mat.shading_model == KRR_SHADING_METALLIC_ROUGHNESS) {
+		for (int k = 0; k < 3; k++) {
+			/* lerp(a,b,t) = (1-t)*a + t*b  (krrmath/functors.h) */
+			diffuse[k]	= (1 - spec[2]) * diff[k] + spec[2] * 0.f;
+			specular[k] = (1 - spec[2]) * 0.f + spec[2] * diff[k];
+		}
+		it.sd.metallic	= spec[2];
+		it.sd.roughness = spec[1];
+	} else {
+		for (int k = 0; k < 3; k++) diffuse[k] = diff[k], specular[k] = spec[k];
+		it.sd.roughness = 1.f - spec[3];
+		it.sd.metallic	= ol_get_metallic(diffuse, specular);
+	}
+	ol_from_rgb(diffuse, 0, lambda, it.sd.diffuse);
+	ol_from_rgb(specular, 0, lambda, it.sd.specular);
+	it.sd.anisotropic = mat.anisotropic;
+	memcpy(it.sd.lambda, lambda, 16);
+	memcpy(it.sd.pdf, pdf, 16);
+	st(it.sd.woWorld, it.wo);
+}
+
+inline V3 toLocal(const SurfIntr &it, V3 v) { return mk(dot(it.tangent, v), dot(it.bitangent, v), dot(it.n, v)); }
+inline V3 toWorld(const SurfIntr &it, V3 v) { return it.tangent * v.x + it.bitangent * v.y + it.n * v.z; }
+
+/* alphaKilled, shading.h:89-113: only image/constant Transmission textures matter; HashFloat-based
+ * stochastic kill is restated with the same MurmurHash64A (src/util/hash.h:46-90, 117-133). */
+uint64_t murmur64A(const unsigned char *key, size_t len, uint64_t seed) {
+	const uint64_t m = 0xc6a4a7935bd1e995ull;
+	const int r = 47;
+	uint64_t h = seed ^ (len * m);
+	const unsigned char *end = key + 8 * (len / 8);
+	while (key != end) {
+		uint64_t k; memcpy(&k, key, 8); key += 8;
+		k *= m; k ^= k >> r; k *= m; h ^= k; h *= m;
+	}
+	switch (len & 7) {
+		case 7: h ^= uint64_t(key[6]) << 48; case 6: h ^= uint64_t(key[5]) << 40;
+		case 5: h ^= uint64_t(key[4]) << 32; case 4: h ^= uint64_t(key[3]) << 24;
+		case 3: h ^= uint64_t(key[2]) << 16; case 2: h ^= uint64_t(key[1]) << 8;
+		case 1: h ^= uint64_t(key[0]); h *= m;
+	}
+	h ^= h >> r; h *= m; h ^= h >> r;
+	return h;
+}
+bool alphaKilled(const OrcScene &s, const Hit &h, V3 o, V3 d) {
+	const Mesh &m = s.meshes[s.instances[h.inst].mesh];
+	if (m.material < 0) return false;
+	const KrrTextureDesc &t = s.materials[m.material].textures[KRR_TEX_TRANSMISSION];
+	if (!t.valid) return false;
+	float b[3] = {1 - h.u - h.v, h.u, h.v}, uv[2] = {0, 0};
+	const int32_t *v = &m.I[3 * h.prim];
+	if (!m.UV.empty())
+		for (int k = 0; k < 2; k++) uv[k] = b[0] * m.UV[2 * v[0] + k] + b[1] * m.UV[2 * v[1] + k] + b[2] * m.UV[2 * v[2] + k];
+	float fb[4] = {1, 1, 1, 1}, op[4];
+	sampleTex(t, uv[0], uv[1], fb, op);
+	float alpha = 1 - luminanceRGB(op);
+	if (alpha >= 1) return false;
+	if (alpha <= 0) return true;
+	float buf[6] = {o.x, o.y, o.z, d.x, d.y, d.z};
+	float u = uint32_t(murmur64A((const unsigned char *) buf, 24, 0)) * 0x1p-32f;
+	return u > alpha;
+}
+
+/* ---- light dispatch ---- */
+void fillTri(const OrcScene &s, const LightRef &lr, OlTriLight &tl) {
+	const Instance &in = s.instances[lr.inst];
+	const Mesh &m	   = s.meshes[in.mesh];
+	const int32_t *v   = &m.I[3 * lr.prim];
+	for (int c = 0; c < 3; c++) {
+		st(tl.p[c], m.P[v[c]]);
+		st(tl.n[c], m.N.empty() ? mk(0, 0, 0) : m.N[v[c]]);
+	}
+	memcpy(tl.xform, in.xf.m, 48);
+	/* mesh.cpp:39-59: Le = emissive constant (or Mesh::Le); scale = max; Le /= scale; one-sided.
+	 * DiffuseAreaLight::L (light.h:183-188) evaluates the (valid, constant) emissive TEXTURE, i.e.
+	 * the un-normalised colour, and still multiplies by scale -- kept as is. */
+	float Le[3];
+	bool hasTex = m.material >= 0 && s.materials[m.material].textures[KRR_TEX_EMISSIVE].valid;
+	if (hasTex) memcpy(Le, s.materials[m.material].textures[KRR_TEX_EMISSIVE].value, 12);
+	else st(Le, m.Le);
+	float scale = std::max(Le[0], std::max(Le[1], Le[2]));
+	if (!hasTex) for (int k = 0; k < 3; k++) Le[k] /= scale;
+	memcpy(tl.Le, Le, 12);
+	tl.scale	= scale;
+	tl.twoSided = 0;
+}
+
+struct PathStats {
+	uint64_t camera = 0, closest = 0, shadow = 0, scatter = 0, hitLight = 0, miss = 0;
+	uint64_t closestByDepth[KRR_MAX_DEPTH_STATS] = {0}, shadowByDepth[KRR_MAX_DEPTH_STATS] = {0};
+};
+
+struct Capture {
+	int sample, depth;
+	int32_t **items;
+	int32_t *counts;
+	void push(int q, int pixelId, int depth_, int bsdfType, int aux) {
+		int slot = __atomic_fetch_add(&counts[q], 1, __ATOMIC_RELAXED);
+		int32_t *o = items[q] + 4 * slot;
+		o[0] = pixelId, o[1] = depth_, o[2] = bsdfType, o[3] = aux;
+	}
+};
+
+} // namespace
+
+extern "C" int orc_intersect_triangle(const float o[3], const float d[3], const float v0[3], const float v1[3],
+									  const float v2[3], float tmax, float *t, float *u, float *v) {
+	return triIntersect(mk(o), mk(d), mk(v0), mk(v1), mk(v2), tmax, *t, *u, *v) ? 1 : 0;
+}
+
+extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
+	ol_init();
+	OrcScene *s = new OrcScene();
+	for (int i = 0; i < d->n_meshes; i++) {
+		const KrrMeshDesc &md = d->meshes[i];
+		Mesh m;
+		m.P.resize(md.n_vertices);
+		for (int k = 0; k < md.n_vertices; k++) m.P[k] = mk(md.positions + 3 * k);
+		if (md.normals) { m.N.resize(md.n_vertices); for (int k = 0; k < md.n_vertices; k++) m.N[k] = mk(md.normals + 3 * k); }
+		if (md.tangents) { m.T.resize(md.n_vertices); for (int k = 0; k < md.n_vertices; k++) m.T[k] = mk(md.tangents + 3 * k); }
+		if (md.texcoords) m.UV.assign(md.texcoords, md.texcoords + 2 * md.n_vertices);
+		m.I.assign(md.indices, md.indices + 3 * md.n_triangles);
+		m.material = md.material, m.mediumIn = md.medium_inside, m.mediumOut = md.medium_outside;
+		m.Le = mk(md.Le);
+		s->meshes.push_back(std::move(m));
+	}
+	s->materials.assign(d->materials, d->materials + d->n_materials);
+	for (int i = 0; i < d->n_instances; i++) {
+		Instance in;
+		in.mesh = d->instances[i].mesh;
+		memcpy(in.xf.m, d->instances[i].transform, 48);
+		in.inv		 = xfInverse(in.xf);
+		in.lightBase = -1;
+		s->instances.push_back(in);
+	}
+	/* uploadSceneLightData, device/scene.cpp:91-145: mesh lights first (instance order), then scene lights */
+	for (int i = 0; i < (int) s->instances.size(); i++) {
+		const Mesh &m = s->meshes[s->instances[i].mesh];
+		bool emissive = (m.material >= 0 && s->materials[m.material].textures[KRR_TEX_EMISSIVE].valid) ||
+						(m.Le.x != 0 || m.Le.y != 0 || m.Le.z != 0);
+		if (!emissive) continue;
+		s->instances[i].lightBase = (int) s->lights.size();
+		for (int t = 0; t < m.ntri(); t++) s->lights.push_back(LightRef{KRR_LIGHT_DIFFUSE_AREA, i, t, -1});
+	}
+	for (int i = 0; i < d->n_lights; i++) {
+		const KrrLightDesc &ld = d->lights[i];
+		OlLight l;
+		memset(&l, 0, sizeof(l));
+		l.type = ld.type;
+		memcpy(l.color, ld.color, 12);
+		l.scale = ld.scale;
+		l.position[0] = ld.transform[3], l.position[1] = ld.transform[7], l.position[2] = ld.transform[11];
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) l.rotation[r * 3 + c] = ld.transform[r * 4 + c];
+		l.sceneRadius = ld.scene_radius;
+		l.cosInner = std::cos(ld.inner_cone_deg * (float) M_PI / 180.f);
+		l.cosOuter = std::cos(ld.outer_cone_deg * (float) M_PI / 180.f);
+		memcpy(l.xform, ld.transform, 48);
+		Xf x; memcpy(x.m, ld.transform, 48);
+		Xf xi = xfInverse(x);
+		memcpy(l.xformInv, xi.m, 48);
+		if (ld.type == KRR_LIGHT_INFINITE) s->infinite.push_back((int) s->analytic.size());
+		s->lights.push_back(LightRef{ld.type, -1, -1, (int) s->analytic.size()});
+		s->analytic.push_back(l);
+	}
+	for (int i = 0; i < (int) s->instances.size(); i++)
+		for (int t = 0; t < s->meshes[s->instances[i].mesh].ntri(); t++) s->bvhPrims.push_back({i, t});
+	if (!s->bvhPrims.empty()) buildBvh(*s, 0, (int) s->bvhPrims.size());
+	return s;
+}
+
+extern "C" void orc_scene_destroy(OrcScene *s) { delete s; }
+extern "C" int32_t orc_scene_num_lights(const OrcScene *s) { return (int32_t) s->lights.size(); }
+
+extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCameraData *cam, int32_t W, int32_t H,
+							 uint64_t frameIndex, float *film, int32_t *firstHits, uint64_t *samplerState,
+							 float *lambdaOut, float *cameraSample, KrrStats *stats, int32_t capSample,
+							 int32_t capDepth, int32_t *capItems[6], int32_t capCounts[6]) {
+	const OrcScene &s = *sp;
+	ol_init();
+	OlCamera oc;
+	memcpy(oc.filmSize, cam->film_size, 8);
+	oc.focalLength = cam->focal_length, oc.focalDistance = cam->focal_distance, oc.lensRadius = cam->lens_radius;
+	oc.aspectRatio = cam->aspect_ratio, oc.shutterOpen = cam->shutter_open, oc.shutterTime = cam->shutter_time;
+	memcpy(oc.transform, cam->transform, 48);
+	const int spp	   = p->spp > 0 ? p->spp : 1;
+	const int row0 = p->row_end > 0 ? p->row_begin : 0, row1 = p->row_end > 0 ? p->row_end : H;
+	const int nLights  = (int) s.lights.size();
+	const bool useBvh  = p->use_bvh != 0;
+	Capture cap{capSample, capDepth, capItems, capCounts};
+	if (capSample >= 0) for (int q = 0; q < 6; q++) capCounts[q] = 0;
+	int nthreads = p->threads > 0 ? p->threads : (int) std::max(1u, std::thread::hardware_concurrency());
+	std::vector<PathStats> tstats(nthreads);
+	auto t0 = std::chrono::steady_clock::now();
+	/* pixels are independent (private RNG stream + accumulator): dynamic chunks over host threads */
+	std::atomic<int> nextChunk{row0 * W};
+	const int chunk = 256, pixelEnd = row1 * W;
+	auto worker = [&](int tid) {
+	PathStats &st_ = tstats[tid];
+	for (;;) {
+	const int c0 = nextChunk.fetch_add(chunk);
+	if (c0 >= pixelEnd) break;
+	for (int pixelId = c0; pixelId < std::min(c0 + chunk, pixelEnd); pixelId++) {
+		const int px = pixelId % W, py = pixelId / W;
+		/* beginFrame, integrator.cpp:213-220 */
+		Spec L = sconst(0);
+		float pixel[3] = {0, 0, 0};
+		OlSampler smp;
+		ol_pcg_set_pixel_sample(&smp, px, py, (uint32_t) (frameIndex * spp));
+		ol_pcg_advance(&smp, (int64_t) (256 * pixelId)); /* int arithmetic as the reference (256 * pixelId) */
+		float lambda[4], lpdf[4];
+		ol_sample_wavelengths(ol_pcg_get1d(&smp), lambda, lpdf);
+		if (samplerState) samplerState[2 * pixelId] = smp.state, samplerState[2 * pixelId + 1] = smp.inc;
+		if (lambdaOut) memcpy(lambdaOut + 4 * pixelId, lambda, 16);
+		int fhInst = -1, fhPrim = -1;
+
+		for (int sampleId = 0; sampleId < spp; sampleId++) {
+			const bool capS = capSample == sampleId;
+			/* generateCameraRays, integrator.cpp:166-179 */
+			float cs[5];
+			for (int k = 0; k < 5; k++) cs[k] = ol_pcg_get1d(&smp);
+			if (cameraSample) memcpy(cameraSample + 5 * pixelId, cs, 20);
+			float ro[3], rd[3], rtime;
+			ol_camera_ray(&oc, px, py, W, H, cs, ro, rd, &rtime);
+			st_.camera++;
+			/* RayWorkItem */
+			V3 rayO = mk(ro), rayD = mk(rd);
+			V3 ctxP = mk(0, 0, 0), ctxN = mk(0, 0, 0);
+			Spec thp = sconst(1), pu = sconst(1), pl = sconst(1);
+			int bsdfType = 0, depth = 0;
+			bool alive = true;
+
+			for (int loopDepth = 0; alive; loopDepth++) {
+				const bool capD = capS && capDepth == loopDepth;
+				if (capD) cap.push(0, pixelId, depth, bsdfType, -1);
+				/* [2.1] traceClosest: device.cu:43-81 */
+				st_.closest++;
+				if (loopDepth < KRR_MAX_DEPTH_STATS) st_.closestByDepth[loopDepth]++;
+				Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(),
+									 [&](const Hit &c) { return !alphaKilled(s, c, rayO, rayD); });
+				if (loopDepth == 0) fhInst = h.inst, fhPrim = h.prim;
+				alive = false; /* the ray item is consumed */
+				bool haveScatter = false, haveHitLight = false, haveMiss = false;
+				SurfIntr it;
+				if (h.inst < 0) {
+					haveMiss = true;
+				} else {
+					prepareInteraction(s, h, rayD, rtime, lambda, lpdf, it);
+					if (it.material < 0) {
+						/* null material: same-depth re-push, device.cu:54-58 */
+						rayO = offsetRayOrigin(it.p, it.n, rayD);
+						alive = true;
+						if (capD) cap.push(5, pixelId, depth, bsdfType, -1);
+					} else {
+						if (it.light >= 0) haveHitLight = true;
+						if (any(thp)) {
+							haveScatter = true;
+							st_.scatter++;
+							if (capD) cap.push(3, pixelId, depth, ol_bsdf_type(&it.sd), it.sd.bsdfType);
+						}
+					}
+				}
+				/* [2.3] handleHit, integrator.cpp:78-90 */
+				if (haveHitLight) {
+					st_.hitLight++;
+					if (capD) cap.push(2, pixelId, depth, bsdfType, it.light);
+					OlTriLight tl;
+					fillTri(s, s.lights[it.light], tl);
+					float pp[3], nn[3], ww[3], Le4[4];
+					st(pp, it.p), st(nn, it.n), st(ww, it.wo);
+					ol_arealight_L(&tl, pp, nn, ww, lambda, Le4);
+					Spec Le = Spec{{Le4[0], Le4[1], Le4[2], Le4[3]}} * thp;
+					if (p->nee && depth && !(bsdfType & (32 | 1))) { /* BSDF_DELTA = SPECULAR|NULL */
+						float cp[3], cn[3];
+						st(cp, ctxP), st(cn, ctxN);
+						float lightPdf = ol_arealight_pdf_li(&tl, pp, nn, cp, cn) * (1.f / nLights);
+						Le = Le / mean(pl * lightPdf + pu);
+					} else Le = Le / mean(pu);
+					L = Le + L; /* addRadiance: L[pixel] = L_val + L[pixel], workqueue.h:23-25 */
+				}
+				/* handleMiss, integrator.cpp:92-108 */
+				if (haveMiss) {
+					st_.miss++;
+					if (capD) cap.push(1, pixelId, depth, bsdfType, -1);
+					Spec Lm = sconst(0);
+					for (int li : s.infinite) {
+						float w[3], Li4[4];
+						st(w, rayD);
+						ol_inflight_Li(&s.analytic[li], w, lambda, Li4);
+						Spec Li = Spec{{Li4[0], Li4[1], Li4[2], Li4[3]}};
+						if (p->nee && depth && !(bsdfType & (32 | 1))) {
+							float lightPdf = 0.07957747154594767f /* M_INV_4PI */ * (1.f / nLights);
+							Lm = Lm + Li / mean(pu + pl * lightPdf);
+						} else Lm = Lm + Li / mean(pu);
+					}
+					L = (thp * Lm) + L;
+				}
+				if (loopDepth == p->max_depth) break;
+				/* [2.4] generateScatterRays, integrator.cpp:110-164 */
+				if (haveScatter) {
+					if (ol_pcg_get1d(&smp) >= p->rr) continue; /* alive == false: path ends */
+					thp = thp / p->rr;
+					V3 woLocal	  = toLocal(it, it.wo);
+					int bt		  = ol_bsdf_type(&it.sd);
+					float wo3[3];
+					st(wo3, woLocal);
+					if (p->nee && (bt & (8 | 16))) { /* BSDF_SMOOTH = DIFFUSE | GLOSSY */
+						float u1 = ol_pcg_get1d(&smp);
+						uint32_t sampleId_ = (uint32_t) (u1 * nLights);
+						const LightRef &lr = s.lights[sampleId_];
+						float u2[2];
+						u2[0] = ol_pcg_get1d(&smp), u2[1] = ol_pcg_get1d(&smp);
+						float lp[3], ln[3] = {0, 0, 0}, Ll[4], lpdfv;
+						float cp[3], cn[3];
+						st(cp, it.p), st(cn, it.n);
+						bool delta = lr.type != KRR_LIGHT_DIFFUSE_AREA && lr.type != KRR_LIGHT_INFINITE;
+						if (lr.type == KRR_LIGHT_DIFFUSE_AREA) {
+							OlTriLight tl;
+							fillTri(s, lr, tl);
+							ol_arealight_sample_li(&tl, u2, cp, cn, lambda, lp, ln, Ll, &lpdfv);
+						} else ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+						/* spawnRayTo(ls.intr): raytracing.h:148-157 */
+						V3 lP = mk(lp), lN = mk(ln);
+						V3 to  = offsetRayOrigin(lP, lN, it.p - lP);
+						V3 p_o = offsetRayOrigin(it.p, it.n, to - it.p);
+						V3 sd_ = to - p_o;
+						V3 wiWorld = normalize(sd_);
+						V3 wiLocal = toLocal(it, wiWorld);
+						float lightPdf = (1.f / nLights) * lpdfv;
+						float wi3[3], f4[4], bpdf;
+						st(wi3, wiLocal);
+						ol_bsdf_f_pdf(&it.sd, wo3, wi3, f4, &bpdf);
+						Spec bsdfVal = Spec{{f4[0], f4[1], f4[2], f4[3]}};
+						float bsdfPdf = delta ? 0 : bpdf;
+						if (lightPdf > 0 && any(bsdfVal)) {
+							Spec Ld = Spec{{Ll[0], Ll[1], Ll[2], Ll[3]}} * thp * bsdfVal * std::fabs(wiLocal.z);
+							Spec spu = pu * bsdfPdf, spl = pu * lightPdf;
+							if (any(Ld)) {
+								/* [2.5] traceShadow, device.cu:83-100 */
+								st_.shadow++;
+								if (loopDepth < KRR_MAX_DEPTH_STATS) st_.shadowByDepth[loopDepth]++;
+								if (capD) cap.push(4, pixelId, depth, 0, (int) sampleId_);
+								Hit sh = traceClosest(s, useBvh, p_o, sd_, 1.f, [&](const Hit &c) {
+									/* __anyhit__Shadow: ignore null-material and alpha-killed hits */
+									if (s.meshes[s.instances[c.inst].mesh].material < 0) return false;
+									return !alphaKilled(s, c, p_o, sd_);
+								});
+								if (sh.inst < 0) L = (Ld / mean(spl + spu)) + L;
+							}
+						}
+					}
+					/* sample BSDF */
+					float f4[4], wi3[3], spdf;
+					int flags;
+					ol_bsdf_sample(&it.sd, wo3, &smp, f4, wi3, &spdf, &flags);
+					Spec sf = Spec{{f4[0], f4[1], f4[2], f4[3]}};
+					if (spdf != 0 && any(sf)) {
+						V3 wiWorld = toWorld(it, mk(wi3));
+						Spec nthp  = thp * sf * std::fabs(wi3[2]) / spdf;
+						if (any(nthp)) {
+							bsdfType = flags;
+							pl		 = pu / spdf;
+							/* pu unchanged */
+							rayO	 = offsetRayOrigin(it.p, it.n, wiWorld);
+							rayD	 = wiWorld;
+							ctxP = it.p, ctxN = it.n;
+							depth	 = depth + 1;
+							thp		 = nthp;
+							alive	 = true;
+							if (capD) cap.push(5, pixelId, depth, bsdfType, -1);
+						}
+					}
+				}
+			}
+			/* per-sample resolve, integrator.cpp:257-260: pixel += L.toRGB (L is NOT reset between
+			 * samples of one frame -- it keeps accumulating, so sample k adds the running sum) */
+			float rgb[3];
+			ol_to_rgb(L.v, lambda, lpdf, rgb);
+			for (int k = 0; k < 3; k++) pixel[k] += rgb[k];
+		}
+		if (firstHits) firstHits[2 * pixelId] = fhInst, firstHits[2 * pixelId + 1] = fhPrim;
+		/* film write, integrator.cpp:262-266 + y flip of CudaRenderTarget::write (cuda.h:33-36) */
+		if (film) {
+			float o[4] = {pixel[0] / float(spp), pixel[1] / float(spp), pixel[2] / float(spp), 1.f};
+			if (p->enable_clamp) for (int k = 0; k < 3; k++) o[k] = std::min(std::max(o[k], 0.f), p->clamp_max);
+			int x = pixelId % W, y = pixelId / W;
+			memcpy(film + 4 * ((size_t) (H - 1 - y) * W + x), o, 16);
+		}
+	}
+	}
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, t);
+	worker(0);
+	for (auto &t : pool) t.join();
+	double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		for (auto &t : tstats) {
+			stats->camera_rays += t.camera, stats->closest_rays += t.closest, stats->shadow_rays += t.shadow;
+			stats->scatter_items += t.scatter, stats->hit_light_items += t.hitLight, stats->miss_items += t.miss;
+			for (int k = 0; k < KRR_MAX_DEPTH_STATS; k++)
+				stats->closest_by_depth[k] += t.closestByDepth[k], stats->shadow_by_depth[k] += t.shadowByDepth[k];
+		}
+		stats->bvh_triangles = s.bvhPrims.size(), stats->bvh_nodes = s.bvh.size();
+	}
+	return secs;
+}

@@ -1,0 +1,73 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for integers / indices / RNG state; radiance by relMSE (tolerance stated)."""
+import numpy as np
+import pytest
+
+import kiraray_b200 as krr
+import oracle_binding as ob
+from __graft_entry__ import relmse
+
+pytestmark = pytest.mark.gpu
+
+KIND = "reference" if ob.available("reference") else "port"
+
+
+def make_gpu(app, w, h):
+    gpu = krr.Wfpt(params=dict(app.wfpt_params()))
+    gpu.set_scene(app.scene_desc())
+    gpu.resize(w, h)
+    return gpu
+
+
+@pytest.fixture(scope="module")
+def cbox64(cbox_app):
+    w = h = 64
+    app = cbox_app(w, h, spp=1, max_depth=5)
+    cam = app.camera()
+    gpu = make_gpu(app, w, h)
+    gpu.begin_frame(1, cam)
+    state0 = gpu.pixel_state()
+    film = gpu.render_to_host()
+    orc = ob.Oracle(app.scene_desc(), KIND)
+    ref = orc.render(cam, w, h, frame_index=1, spp=1, max_depth=5, use_bvh=False)
+    return dict(app=app, cam=cam, gpu=gpu, film=film, ref=ref, state0=state0, orc=orc, w=w, h=h)
+
+
+def test_begin_frame_rng_and_wavelengths_bit_exact(cbox64):
+    s, lam, _ = cbox64["state0"]
+    ref = cbox64["ref"]
+    assert np.array_equal(s, ref["sampler"]), "PCG state after beginFrame differs"
+    assert np.array_equal(lam.view(np.uint32), ref["lambda"].view(np.uint32)), "sampled wavelengths differ"
+
+
+def test_camera_samples_bit_exact(cbox64):
+    _, _, cs = cbox64["gpu"].pixel_state()
+    assert np.array_equal(cs.view(np.uint32), cbox64["ref"]["camera_sample"].view(np.uint32))
+
+
+def test_first_hit_ids_bit_exact(cbox64):
+    inst, prim = cbox64["gpu"].first_hits()
+    ref = cbox64["ref"]["first_hits"]
+    assert np.array_equal(inst, ref[:, 0])
+    assert np.array_equal(prim, ref[:, 1])
+
+
+def test_depth0_queue_counts_exact(cbox64):
+    st, rs = cbox64["gpu"].stats(), cbox64["ref"]["stats"]
+    assert st["camera_rays"] == rs["camera_rays"] == 64 * 64
+    assert st["closest_by_depth"][0] == rs["closest_by_depth"][0]
+    # RR and light selection at depth 0 only depend on exact integers -> depth-1 ray count is exact up to
+    # float-level differences in BSDF sampling validity; allow 0.5 %
+    for d in range(1, 6):
+        a, b = st["closest_by_depth"][d], rs["closest_by_depth"][d]
+        assert abs(a - b) <= max(8, 0.02 * b), (d, a, b)
+
+
+def test_film_relmse(cbox64):
+    film, ref = cbox64["film"], cbox64["ref"]["film"]
+    assert np.isfinite(film).all()
+    assert np.all(film[..., 3] == 1.0)
+    # 1 spp images from the same RNG streams: paths agree except where libm differences flip a
+    # discrete decision; tolerance: relMSE <= 0.05 (two independent 1-spp renders give ~2)
+    err = relmse(film, ref)
+    assert err <= 0.05, err
