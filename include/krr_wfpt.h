@@ -224,6 +224,16 @@ int krr_wfpt_set_partition(KrrWfpt *h, int32_t row_begin, int32_t row_end);
 
 int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out);
 
+/* Per-stage device time, the counterpart of the reference's PROFILE("...") scopes
+ * (integrator.cpp:51,68,79,93,111,167; src/render/profiler/profiler.h:212-235): when enabled, every
+ * stage launch is bracketed by CUDA events on the launching stream.  get_stage_times synchronises
+ * on the last event and returns, per stage, the summed milliseconds and the number of launches
+ * since profiling was enabled (or since the last reset). */
+enum { KRR_STAGE_CAMERA = 0, KRR_STAGE_CLOSEST = 1, KRR_STAGE_HIT_MISS = 2, KRR_STAGE_SCATTER = 3, KRR_STAGE_SHADOW = 4,
+	   KRR_STAGE_RESOLVE = 5, KRR_STAGE_MEDIUM = 6, KRR_STAGE_COUNT = 7 };
+int krr_wfpt_set_profiling(KrrWfpt *h, int32_t enable);
+int krr_wfpt_get_stage_times(KrrWfpt *h, double *ms, int32_t *launches, int32_t reset);
+
 /* ---- parity / debug taps (read-only views of device state; used by tests and smoke) ---- */
 /* depth-0 hit per pixel of the LAST sample rendered: instance id and primitive id (-1 = miss) */
 int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *instance_ids_host, int32_t *prim_ids_host);

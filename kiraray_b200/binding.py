@@ -128,6 +128,8 @@ def load_wfpt():
         "krr_wfpt_render_to_host": [P, P, P],
         "krr_wfpt_set_partition": [P, I32, I32],
         "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
+        "krr_wfpt_set_profiling": [P, I32],
+        "krr_wfpt_get_stage_times": [P, C.POINTER(C.c_double), C.POINTER(I32), I32],
         "krr_wfpt_debug_first_hits": [P, P, P],
         "krr_wfpt_debug_pixel_state": [P, P, P, P],
         "krr_wfpt_debug_capture": [P, I32, I32],
@@ -339,6 +341,16 @@ class Wfpt:
         s = KrrStats()
         self._ck(self.lib.krr_wfpt_get_stats(self.h, C.byref(s)), "get_stats")
         return s.as_dict()
+
+    STAGES = ["camera", "closest", "hit_miss", "scatter", "shadow", "resolve", "medium"]
+
+    def set_profiling(self, on):
+        self._ck(self.lib.krr_wfpt_set_profiling(self.h, int(on)), "set_profiling")
+
+    def stage_times(self, reset=True):
+        ms, n = (C.c_double * 7)(), (I32 * 7)()
+        self._ck(self.lib.krr_wfpt_get_stage_times(self.h, ms, n, int(reset)), "get_stage_times")
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(self.STAGES)}
 
     def _npix(self):
         return (self.rows[1] - self.rows[0]) * self.size[0]

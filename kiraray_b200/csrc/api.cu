@@ -128,6 +128,16 @@ struct KrrWfpt {
 	Buf<int32_t> capCounts;
 	uint64_t launches = 0;
 	cudaStream_t lastStream = nullptr;
+	// optional per-stage timing (CUDA events on the launching stream)
+	bool profile = false;
+	std::vector<cudaEvent_t> evPool;
+	struct EvRec { int stage; cudaEvent_t a, b; };
+	std::vector<EvRec> evRecs;
+	size_t evUsed = 0;
+	cudaEvent_t nextEvent() {
+		if (evUsed == evPool.size()) { cudaEvent_t e; cudaEventCreate(&e); evPool.push_back(e); }
+		return evPool[evUsed++];
+	}
 
 	int pixelCount() const { return (rowEnd - rowBegin) * width; }
 };
@@ -558,9 +568,17 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 }
 
 namespace {
+struct StageTimer { // RAII: brackets one launch with events when profiling is on
+	KrrWfpt *h; cudaStream_t st; KrrWfpt::EvRec rec; bool on;
+	StageTimer(KrrWfpt *h_, int stage, cudaStream_t st_) : h(h_), st(st_), on(h_->profile) {
+		if (on) { rec.stage = stage; rec.a = h->nextEvent(); rec.b = h->nextEvent(); cudaEventRecord(rec.a, st); }
+	}
+	~StageTimer() { if (on) { cudaEventRecord(rec.b, st); h->evRecs.push_back(rec); } }
+};
 template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st) {
 	static int grid = 0;
 	if (!grid) grid = gridFor(h, k_scatter<MT>, 128);
+	StageTimer t(h, KRR_STAGE_SCATTER, st);
 	k_scatter<MT><<<grid, 128, 0, st>>>(wf, depth);
 	h->launches++;
 }
@@ -587,17 +605,17 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	for (int sampleId = 0; sampleId < h->spp; sampleId++) {
 		Wavefront wf = makeWavefront(h, sampleId);
 		// [1] primary rays.  Queue counters were cleared by k_fold_counters of the previous sample
-		k_generate_camera_rays<<<gridCam, 256, 0, st>>>(wf);
+		{ StageTimer t(h, KRR_STAGE_CAMERA, st); k_generate_camera_rays<<<gridCam, 256, 0, st>>>(wf); }
 		h->launches++;
 		for (int depth = 0; true; depth++) {
 			const bool cap = h->capSample == sampleId && h->capDepth == depth;
 			if (cap && capture(h, wf, depth, 0, st)) return KRR_E_CUDA;
 			// [2.1] closest hits
-			k_trace_closest<<<gridTrace, 128, 0, st>>>(wf, depth);
+			{ StageTimer t(h, KRR_STAGE_CLOSEST, st); k_trace_closest<<<gridTrace, 128, 0, st>>>(wf, depth); }
 			h->launches++;
 			if (cap) for (int q = 1; q <= 3; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.3] emitted / environment radiance
-			k_handle_hit_miss<<<gridHit, 128, 0, st>>>(wf, depth);
+			{ StageTimer t(h, KRR_STAGE_HIT_MISS, st); k_handle_hit_miss<<<gridHit, 128, 0, st>>>(wf, depth); }
 			h->launches++;
 			if (depth == h->maxDepth) break;
 			// [2.4] BSDF sampling + NEE, one launch per material type present in the scene
@@ -609,16 +627,16 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			if (cap) for (int q = 4; q <= 5; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.5] shadow rays
 			if (h->nee) {
-				k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth);
+				{ StageTimer t(h, KRR_STAGE_SHADOW, st); k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth); }
 				h->launches++;
 			}
 		}
-		k_resolve<<<gridResolve, 256, 0, st>>>(wf);
-		k_fold_counters<<<1, 128, 0, st>>>(h->counters.p, h->totals.p, nDepthSlots, h->pixelCount());
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_resolve<<<gridResolve, 256, 0, st>>>(wf); }
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_fold_counters<<<1, 128, 0, st>>>(h->counters.p, h->totals.p, nDepthSlots, h->pixelCount()); }
 		h->launches += 2;
 	}
 	Wavefront wf = makeWavefront(h, 0);
-	k_film<<<gridResolve, 256, 0, st>>>(wf, (float4 *) film, 1);
+	{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_film<<<gridResolve, 256, 0, st>>>(wf, (float4 *) film, 1); }
 	h->launches++;
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;
@@ -652,6 +670,27 @@ extern "C" int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out) {
 	for (int i = 0; i < 64; i++) out->closest_by_depth[i] = t.closestByDepth[i], out->shadow_by_depth[i] = t.shadowByDepth[i];
 	out->kernel_launches = h->launches;
 	out->bvh_nodes = h->bvh.nodeCount(), out->bvh_triangles = h->bvh.triCount(), out->tlas_nodes = h->bvh.tlasNodeCount();
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_set_profiling(KrrWfpt *h, int32_t enable) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	h->profile = enable != 0;
+	h->evRecs.clear();
+	h->evUsed = 0;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_get_stage_times(KrrWfpt *h, double *ms, int32_t *launches, int32_t reset) {
+	if (!h || !ms || !launches) return fail(KRR_E_INVALID, "null argument");
+	for (int i = 0; i < KRR_STAGE_COUNT; i++) ms[i] = 0, launches[i] = 0;
+	if (!h->evRecs.empty()) CUDA_OK(cudaEventSynchronize(h->evRecs.back().b));
+	for (auto &r : h->evRecs) {
+		float t = 0;
+		CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+		ms[r.stage] += t, launches[r.stage]++;
+	}
+	if (reset) { h->evRecs.clear(); h->evUsed = 0; }
 	return KRR_OK;
 }
 

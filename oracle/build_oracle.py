@@ -150,7 +150,9 @@ def build_ref():
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, units))
     so = os.path.join(REF_OUT, "libkrr_oracle_ref.so")
-    run([CXX, "-shared", "-pthread", "-o", so] + objs)
+    # -Bsymbolic: the fake CUDA runtime inside this .so must win over a real libcudart that the
+    # host process (torch) may already have loaded into the global scope
+    run([CXX, "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", so] + objs)
     print("[oracle] built", so)
     return True
 
@@ -170,7 +172,7 @@ def build_port():
     deps += [os.path.join(HERE, "port", f) for f in os.listdir(os.path.join(HERE, "port"))]
     if newer(so, deps):
         return True
-    run([CXX] + COMMON + ["-O2", "-shared", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-o", so] + srcs)
+    run([CXX] + COMMON + ["-O2", "-shared", "-Wl,-Bsymbolic", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-o", so] + srcs)
     print("[oracle] built", so)
     return True
 

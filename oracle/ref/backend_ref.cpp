@@ -151,7 +151,6 @@ extern "C" void ol_camera_ray(const OlCamera *cam, int px, int py, int w, int h,
 }
 
 /* ---------------- BSDF ---------------- */
-static rt::MaterialData *g_mat[3];
 static void fillIntr(SurfaceInteraction &intr, const OlShading *sd) {
 	ol_init();
 	intr.n		   = Vector3f(0, 0, 1);
@@ -167,14 +166,17 @@ static void fillIntr(SurfaceInteraction &intr, const OlShading *sd) {
 	intr.sd.anisotropic			 = sd->anisotropic;
 	intr.sd.bsdfType			 = (MaterialType) sd->bsdfType;
 	intr.lambda					 = SW(sd->lambda, sd->pdf);
-	/* material: only colour space and spectral eta/k are read by BSDF::setup */
-	rt::MaterialData *m = new rt::MaterialData(); /* leaked on purpose, as the reference does */
-	m->mColorSpace		= RGBColorSpace::sRGB;
-	if (sd->etaKind == 1)
-		m->mMaterialParams.spectralEta = g_alloc->new_object<ConstantSpectrum>(sd->etaValue[0]);
-	if (sd->kKind == 1)
-		m->mMaterialParams.spectralK = g_alloc->new_object<ConstantSpectrum>(sd->kValue[0]);
-	intr.material = m;
+	/* material: only colour space and spectral eta/k are read by BSDF::setup.  One scratch
+	 * MaterialData per host thread (no per-call allocation: this adapter must not slow the
+	 * reference's code down when it is timed as the CPU baseline). */
+	static thread_local rt::MaterialData mat;
+	static thread_local ConstantSpectrum etaC(1.5f), kC(0.f);
+	mat.mColorSpace = RGBColorSpace::sRGB;
+	mat.mMaterialParams.spectralEta = Spectra();
+	mat.mMaterialParams.spectralK	= Spectra();
+	if (sd->etaKind == 1) { etaC = ConstantSpectrum(sd->etaValue[0]); mat.mMaterialParams.spectralEta = &etaC; }
+	if (sd->kKind == 1) { kC = ConstantSpectrum(sd->kValue[0]); mat.mMaterialParams.spectralK = &kC; }
+	intr.material = &mat;
 }
 extern "C" int ol_bsdf_type(const OlShading *sd) {
 	BSDFData d;
@@ -190,7 +192,6 @@ extern "C" void ol_bsdf_f_pdf(const OlShading *sd, const float wo[3], const floa
 	BSDF bsdf(intr);
 	S4(f, bsdf.f(V3(wo), V3(wi)));
 	*pdf = bsdf.pdf(V3(wo), V3(wi));
-	delete intr.material;
 }
 extern "C" void ol_bsdf_sample(const OlShading *sd, const float wo[3], OlSampler *s, float f[4],
 							   float wi[3], float *pdf, int *flags) {
@@ -203,7 +204,6 @@ extern "C" void ol_bsdf_sample(const OlShading *sd, const float wo[3], OlSampler
 	S3(wi, bs.wi);
 	*pdf   = bs.pdf;
 	*flags = (int) bs.flags;
-	delete intr.material;
 }
 
 /* ---------------- area light ---------------- */
@@ -215,13 +215,18 @@ struct RefTriLight {
 };
 static RefTriLight *makeTri(const OlTriLight *l) {
 	ol_init();
-	RefTriLight *r = new RefTriLight();
-	std::vector<Vector3f> P{V3(l->p[0]), V3(l->p[1]), V3(l->p[2])};
-	std::vector<Vector3f> N{V3(l->n[0]), V3(l->n[1]), V3(l->n[2])};
-	std::vector<Vector3i> I{Vector3i(0, 1, 2)};
-	r->mesh.positions.alloc_and_copy_from_host(P);
-	r->mesh.normals.alloc_and_copy_from_host(N);
-	r->mesh.indices.alloc_and_copy_from_host(I);
+	/* one scratch one-triangle mesh per host thread, buffers allocated once (TypedBuffer never
+	 * frees -- device/buffer.h:123-127 -- so per-call allocation would leak) */
+	static thread_local RefTriLight *r = nullptr;
+	if (!r) {
+		r = new RefTriLight();
+		std::vector<Vector3f> Z(3, Vector3f(0, 0, 0));
+		std::vector<Vector3i> I{Vector3i(0, 1, 2)};
+		r->mesh.positions.alloc_and_copy_from_host(Z);
+		r->mesh.normals.alloc_and_copy_from_host(Z);
+		r->mesh.indices.alloc_and_copy_from_host(I);
+	}
+	for (int c = 0; c < 3; c++) r->mesh.positions[c] = V3(l->p[c]), r->mesh.normals[c] = V3(l->n[c]);
 	r->inst.mesh	  = &r->mesh;
 	r->inst.transform = Transformation(A12(l->xform));
 	r->tri			  = Triangle(0, &r->inst);
@@ -239,20 +244,17 @@ extern "C" void ol_arealight_sample_li(const OlTriLight *l, const float u[2], co
 	S3(n, ls.intr.n);
 	S4(L, ls.L);
 	*pdf = ls.pdf;
-	delete r;
 }
 extern "C" void ol_arealight_L(const OlTriLight *l, const float p[3], const float n[3],
 							   const float w[3], const float lambda[4], float L[4]) {
 	RefTriLight *r = makeTri(l);
 	S4(L, r->light.L(V3(p), V3(n), Vector2f(0, 0), V3(w), SW(lambda, nullptr)));
-	delete r;
 }
 extern "C" float ol_arealight_pdf_li(const OlTriLight *l, const float p[3], const float n[3],
 									 const float ctxP[3], const float ctxN[3]) {
 	RefTriLight *r = makeTri(l);
 	Interaction intr(V3(p), V3(n), Vector2f(0, 0));
 	float pdf = r->light.pdfLi(intr, {V3(ctxP), V3(ctxN)});
-	delete r;
 	return pdf;
 }
 
