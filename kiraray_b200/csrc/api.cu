@@ -253,14 +253,15 @@ extern "C" int krr_wfpt_abi_version(void) { return KRR_WFPT_ABI_VERSION; }
 extern "C" int krr_wfpt_create(const char *params_json, KrrWfpt **out) {
 	if (!out) return fail(KRR_E_INVALID, "out is null");
 	*out = nullptr;
-	int dev = 0;
-	CUDA_OK(cudaGetDevice(&dev));
 	KrrWfpt *h = new KrrWfpt();
-	h->device  = dev;
+	int rc = parseParams(h, params_json); // argument errors are reported before any CUDA call
+	if (rc) { delete h; return rc; }
+	int dev = 0;
+	cudaError_t ce = cudaGetDevice(&dev);
+	if (ce != cudaSuccess) { delete h; return fail(KRR_E_CUDA, "cudaGetDevice failed: %s (the pass has no CPU path)", cudaGetErrorString(ce)); }
+	h->device = dev;
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
-	int rc = parseParams(h, params_json);
-	if (rc) { delete h; return rc; }
 	*out = h;
 	return KRR_OK;
 }

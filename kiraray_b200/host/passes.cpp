@@ -207,7 +207,16 @@ void RenderApp::loadConfig(const json &config, const string &baseDir) {
 			RenderPass::SharedPtr pass;
 			if (p.contains("params")) pass = RenderPassFactory::deserizeInstance(name, p.value("params", json::object()));
 			else pass = RenderPassFactory::createInstance(name);
-			if (!pass) continue; // passes outside the hot path (ToneMapping, Denoise, ...) are not built here
+			if (!pass) {
+				// reference passes outside the hot path are recognised and skipped; any other name is
+				// the reference's Log(Fatal) "Could not find pass" (renderpass.h:216-220, 228-232)
+				static const char *kOutOfScope[] = {"ToneMappingPass", "DenoisePass", "ErrorMeasurePass", "MegakernelPathTracer", "BDPTIntegrator",
+													"PPGPathTracer", "GBufferPass", "BindlessRender", "RasterizePass"};
+				bool known = false;
+				for (const char *k : kOutOfScope) known |= name == k;
+				if (!known) throw std::runtime_error("unknown render pass \"" + name + "\"");
+				continue;
+			}
 			pass->setEnable(p.value("enable", true));
 			mRenderPasses.push_back(pass);
 		}

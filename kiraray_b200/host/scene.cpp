@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 
 namespace krr {
 
@@ -684,6 +685,9 @@ bool SceneImporter::loadModel(const string &filepath, Scene::SharedPtr scene, co
 	}
 	size_t dot = path.find_last_of('.');
 	string ext = dot == string::npos ? "" : path.substr(dot);
+	// the reference logs "Failed to load" and carries on with an empty scene, which then dies in the
+	// OptiX build; here a missing asset is an error the C entry point returns
+	if (!fileExists(path)) throw std::runtime_error("cannot open model " + path);
 	if (ext == ".obj") return loadObj(path, *scene, xf);
 	if (ext == ".json") {
 		std::ifstream f(path);
