@@ -247,6 +247,51 @@ int krr_wfpt_debug_pixel_state(KrrWfpt *h, uint64_t *sampler_host, float *lambda
 int krr_wfpt_debug_capture(KrrWfpt *h, int32_t sample_id, int32_t depth);
 int krr_wfpt_debug_queue(KrrWfpt *h, int32_t queue, int32_t *items4_host, int32_t capacity);
 
+/* ---- leaf-function taps: run the DEVICE implementations of the reference's KRR_CALLABLE leaf
+ * functions (BSDF variant src/render/bsdf.h:19-54 + materials/, lights src/core/light.h:30-259,
+ * colour src/render/spectrum.h:488-529, camera src/core/camera.h:32-58) on caller-supplied inputs,
+ * one CUDA thread per query.  They exist so that parity tests can compare every BSDF / light /
+ * colour routine with the reference's own code value by value; the render path never calls them. */
+typedef struct KrrLeafBsdfQuery {
+	float	 ior, diffuse[4], specular[4], specular_transmission, roughness, metallic, anisotropic;
+	int32_t	 bsdf_type;			 /* KRR_MAT_* */
+	float	 wo[3], wi[3];		 /* local shading frame (n = +z); wo doubles as the world-space wo */
+	float	 wavelength_u;		 /* SampledWavelengths::sampleUniform(u) */
+	uint32_t seed_px, seed_py, seed_index; /* PCGSampler::setPixelSample((px,py), index) for sample() */
+	int32_t	 eta_kind;			 /* 0 none, 1 constant spectral eta (conductor) */
+	float	 eta;
+} KrrLeafBsdfQuery;
+typedef struct KrrLeafBsdfResult {
+	int32_t type_flags;			 /* BSDFData::getBsdfType */
+	float	f[4], pdf;			 /* BSDF::f(wo, wi), BSDF::pdf(wo, wi) */
+	float	s_f[4], s_wi[3], s_pdf; /* BSDF::sample(wo, sampler) */
+	int32_t s_flags;
+} KrrLeafBsdfResult;
+int krr_wfpt_debug_eval_bsdf(KrrWfpt *h, const KrrLeafBsdfQuery *queries_host, int32_t n, KrrLeafBsdfResult *results_host);
+
+typedef struct KrrLeafLightQuery {
+	int32_t type;				 /* KRR_LIGHT_* ; DIFFUSE_AREA uses the triangle fields */
+	float	p[3][3], n[3][3];	 /* triangle, object space */
+	float	transform[12];		 /* object->world (triangle) / node transform (analytic) */
+	float	color[3], scale;	 /* area light: Le (already divided by its max) and scale */
+	int32_t two_sided;
+	float	scene_radius, cos_inner, cos_outer;
+	float	u[2], ctx_p[3], ctx_n[3], wi[3];
+	float	wavelength_u;
+} KrrLeafLightQuery;
+typedef struct KrrLeafLightResult {
+	float p[3], n[3], L[4], pdf; /* sampleLi */
+	float L_eval[4];			 /* area: L(p, n, uv, normalize(ctx_p - p)); infinite: Li(wi) */
+	float pdf_li;				 /* area: pdfLi(sampled point, ctx) */
+} KrrLeafLightResult;
+int krr_wfpt_debug_eval_light(KrrWfpt *h, const KrrLeafLightQuery *queries_host, int32_t n, KrrLeafLightResult *results_host);
+
+/* in: rgb[3], wavelength_u, spectrum[4]  (8 floats per query);
+ * out: fromRGB as RGBBounded[4], RGBUnbounded[4], RGBIlluminant[4], toRGB(spectrum)[3], lum(spectrum), lambda[4]  (20 floats) */
+int krr_wfpt_debug_eval_color(KrrWfpt *h, const float *in8_host, int32_t n, float *out20_host);
+/* CameraData::getRay: in px, py (as floats), camera sample[5] (7 floats); out origin[3], dir[3], time (7 floats) */
+int krr_wfpt_debug_camera_rays(KrrWfpt *h, const KrrCameraData *camera, int32_t width, int32_t height, const float *in7_host, int32_t n, float *out7_host);
+
 /* ---- next row: AccumulatePass kernel, src/render/passes/accumulate/accumulate.cu:30-52 ----
  * accum, film: device float4[n_pixels]; film is replaced by the running average. */
 int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,

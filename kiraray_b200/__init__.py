@@ -7,6 +7,6 @@ by the tests and bench.py; it contains no rendering logic and NO CPU fallback --
 libraries are missing it raises.
 """
 from .binding import (  # noqa: F401
-    HostApp, Wfpt, KrrSceneDesc, KrrCameraData, KrrStats, KrrColorSpaceData,
+    HostApp, Wfpt, KrrSceneDesc, KrrLeafBsdfQuery, KrrLeafLightQuery, KrrCameraData, KrrStats, KrrColorSpaceData,
     load_host, load_wfpt, lib_dir, data_dir, color_space, NativeLibraryMissing,
 )

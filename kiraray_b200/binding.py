@@ -96,6 +96,26 @@ class KrrStats(C.Structure):
         return d
 
 
+class KrrLeafBsdfQuery(C.Structure):
+    _fields_ = [("ior", F), ("diffuse", F * 4), ("specular", F * 4), ("specular_transmission", F), ("roughness", F), ("metallic", F),
+                ("anisotropic", F), ("bsdf_type", I32), ("wo", F * 3), ("wi", F * 3), ("wavelength_u", F),
+                ("seed_px", C.c_uint32), ("seed_py", C.c_uint32), ("seed_index", C.c_uint32), ("eta_kind", I32), ("eta", F)]
+
+
+class KrrLeafBsdfResult(C.Structure):
+    _fields_ = [("type_flags", I32), ("f", F * 4), ("pdf", F), ("s_f", F * 4), ("s_wi", F * 3), ("s_pdf", F), ("s_flags", I32)]
+
+
+class KrrLeafLightQuery(C.Structure):
+    _fields_ = [("type", I32), ("p", (F * 3) * 3), ("n", (F * 3) * 3), ("transform", F * 12), ("color", F * 3), ("scale", F),
+                ("two_sided", I32), ("scene_radius", F), ("cos_inner", F), ("cos_outer", F), ("u", F * 2), ("ctx_p", F * 3),
+                ("ctx_n", F * 3), ("wi", F * 3), ("wavelength_u", F)]
+
+
+class KrrLeafLightResult(C.Structure):
+    _fields_ = [("p", F * 3), ("n", F * 3), ("L", F * 4), ("pdf", F), ("L_eval", F * 4), ("pdf_li", F)]
+
+
 _wfpt = None
 _host = None
 
@@ -135,6 +155,10 @@ def load_wfpt():
         "krr_wfpt_debug_capture": [P, I32, I32],
         "krr_wfpt_debug_queue": [P, I32, P, I32],
         "krr_accumulate_f32": [P, P, C.c_int64, U64, U64, I32, P],
+        "krr_wfpt_debug_eval_bsdf": [P, C.POINTER(KrrLeafBsdfQuery), I32, C.POINTER(KrrLeafBsdfResult)],
+        "krr_wfpt_debug_eval_light": [P, C.POINTER(KrrLeafLightQuery), I32, C.POINTER(KrrLeafLightResult)],
+        "krr_wfpt_debug_eval_color": [P, C.POINTER(F), I32, C.POINTER(F)],
+        "krr_wfpt_debug_camera_rays": [P, C.POINTER(KrrCameraData), I32, I32, C.POINTER(F), I32, C.POINTER(F)],
         "krr_wfpt_abi_version": [],
     }
     for name, args in sig.items():
@@ -366,6 +390,32 @@ class Wfpt:
         s, l, c = np.empty((n, 2), np.uint64), np.empty((n, 4), np.float32), np.empty((n, 5), np.float32)
         self._ck(self.lib.krr_wfpt_debug_pixel_state(self.h, s.ctypes.data_as(P), l.ctypes.data_as(P), c.ctypes.data_as(P)), "debug_pixel_state")
         return s, l, c
+
+    # ---- leaf-function taps (parity tests) ----
+    def eval_bsdf(self, queries):
+        n = len(queries)
+        q, r = (KrrLeafBsdfQuery * n)(*queries), (KrrLeafBsdfResult * n)()
+        self._ck(self.lib.krr_wfpt_debug_eval_bsdf(self.h, q, n, r), "debug_eval_bsdf")
+        return list(r)
+
+    def eval_light(self, queries):
+        n = len(queries)
+        q, r = (KrrLeafLightQuery * n)(*queries), (KrrLeafLightResult * n)()
+        self._ck(self.lib.krr_wfpt_debug_eval_light(self.h, q, n, r), "debug_eval_light")
+        return list(r)
+
+    def eval_color(self, in8):
+        a = np.ascontiguousarray(in8, dtype=np.float32).reshape(-1, 8)
+        out = np.empty((len(a), 20), np.float32)
+        self._ck(self.lib.krr_wfpt_debug_eval_color(self.h, a.ctypes.data_as(C.POINTER(F)), len(a), out.ctypes.data_as(C.POINTER(F))), "debug_eval_color")
+        return out
+
+    def camera_rays(self, cam, w, h, in7):
+        a = np.ascontiguousarray(in7, dtype=np.float32).reshape(-1, 7)
+        out = np.empty((len(a), 7), np.float32)
+        self._ck(self.lib.krr_wfpt_debug_camera_rays(self.h, C.byref(cam), w, h, a.ctypes.data_as(C.POINTER(F)), len(a),
+                                                     out.ctypes.data_as(C.POINTER(F))), "debug_camera_rays")
+        return out
 
     def capture(self, sample_id, depth):
         self._ck(self.lib.krr_wfpt_debug_capture(self.h, sample_id, depth), "debug_capture")

@@ -13,6 +13,7 @@
 #include "bvh_build.h"
 #include "krr_wfpt.h"
 #include "wavefront_kernels.cuh"
+#include "leaf_debug.cuh"
 
 using namespace krr;
 
@@ -235,6 +236,20 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 	wf.errorFlags = h->errorFlags.p;
 	wf.instFlags  = h->instFlags.p;
 	return wf;
+}
+
+KrrCameraDev makeCamera(const KrrCameraData *c) {
+	KrrCameraDev cam{};
+	memcpy(cam.filmSize, c->film_size, 8);
+	cam.focalLength = c->focal_length, cam.focalDistance = c->focal_distance, cam.lensRadius = c->lens_radius;
+	cam.aspectRatio = c->aspect_ratio, cam.shutterOpen = c->shutter_open, cam.shutterTime = c->shutter_time;
+	memcpy(cam.transform.m, c->transform, 48);
+	cam.medium = c->medium;
+	// fov = atan2(filmSize[1] * 0.5f, focalLength); tan(fov)  (camera.h:41,46): per-frame constants,
+	// evaluated once here with the host libm so that every pixel sees the oracle's exact value
+	float fov  = atan2f(c->film_size[1] * 0.5f, c->focal_length);
+	cam.tanFov = tanf(fov);
+	return cam;
 }
 
 template <typename K> int gridFor(KrrWfpt *h, K kernel, int block) {
@@ -545,16 +560,7 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 	CUDA_OK(cudaSetDevice(h->device));
 	cudaStream_t st = (cudaStream_t) stream;
 	h->frameIndex = frameIndex;
-	KrrCameraDev &cam = h->cam;
-	memcpy(cam.filmSize, c->film_size, 8);
-	cam.focalLength = c->focal_length, cam.focalDistance = c->focal_distance, cam.lensRadius = c->lens_radius;
-	cam.aspectRatio = c->aspect_ratio, cam.shutterOpen = c->shutter_open, cam.shutterTime = c->shutter_time;
-	memcpy(cam.transform.m, c->transform, 48);
-	cam.medium = c->medium;
-	// fov = atan2(filmSize[1] * 0.5f, focalLength); tan(fov)  (camera.h:41,46): per-frame constants,
-	// evaluated once here with the host libm so that every pixel sees the oracle's exact value
-	float fov  = atan2f(c->film_size[1] * 0.5f, c->focal_length);
-	cam.tanFov = tanf(fov);
+	h->cam = makeCamera(c);
 	h->launches = 0;
 	CUDA_OK(cudaMemsetAsync(h->totals.p, 0, sizeof(StatTotals), st));
 	Wavefront wf = makeWavefront(h, 0);
@@ -753,4 +759,53 @@ extern "C" int krr_accumulate_f32(float *accum, float *film, int64_t n, uint64_t
 	k_accumulate<<<148 * 4, 256, 0, (cudaStream_t) stream>>>((float4 *) accum, (float4 *) film, n, accumCount, maxAccum, movingAverage);
 	CUDA_OK(cudaGetLastError());
 	return KRR_OK;
+}
+
+// ---- leaf-function taps (parity tests only) ----
+namespace {
+template <typename Q, typename R, typename Launch>
+int leafRun(const Q *q, int32_t n, size_t qElems, R *out, size_t rElems, Launch launch) {
+	if (!q || !out || n <= 0) return fail(KRR_E_INVALID, "bad argument");
+	Buf<Q> dq;
+	Buf<R> dr;
+	if (dq.alloc(qElems * n) || dr.alloc(rElems * n)) return KRR_E_CUDA;
+	CUDA_OK(cudaMemcpy(dq.p, q, sizeof(Q) * qElems * n, cudaMemcpyHostToDevice));
+	launch(dq.p, dr.p);
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaDeviceSynchronize());
+	CUDA_OK(cudaMemcpy(out, dr.p, sizeof(R) * rElems * n, cudaMemcpyDeviceToHost));
+	return KRR_OK;
+}
+} // namespace
+
+extern "C" int krr_wfpt_debug_eval_bsdf(KrrWfpt *h, const KrrLeafBsdfQuery *q, int32_t n, KrrLeafBsdfResult *out) {
+	if (!h || !h->haveColorSpace) return fail(KRR_E_STATE, "set_color_space first");
+	return leafRun(q, n, 1, out, 1, [&](const KrrLeafBsdfQuery *dq, KrrLeafBsdfResult *dr) { k_leaf_bsdf<<<(n + 63) / 64, 64>>>(dq, n, dr, h->cs); });
+}
+
+extern "C" int krr_wfpt_debug_eval_light(KrrWfpt *h, const KrrLeafLightQuery *q, int32_t n, KrrLeafLightResult *out) {
+	if (!h || !h->haveColorSpace) return fail(KRR_E_STATE, "set_color_space first");
+	if (!q || n <= 0) return fail(KRR_E_INVALID, "bad argument");
+	std::vector<Xf> inv(n);
+	for (int i = 0; i < n; i++) {
+		Xf t;
+		memcpy(t.m, q[i].transform, 48);
+		inv[i] = xfInverse(t);
+	}
+	Buf<Xf> dinv;
+	if (dinv.upload(inv)) return KRR_E_CUDA;
+	SceneDev sc{};
+	sc.cs = h->cs;
+	return leafRun(q, n, 1, out, 1, [&](const KrrLeafLightQuery *dq, KrrLeafLightResult *dr) { k_leaf_light<<<(n + 63) / 64, 64>>>(dq, dinv.p, n, dr, sc); });
+}
+
+extern "C" int krr_wfpt_debug_eval_color(KrrWfpt *h, const float *in, int32_t n, float *out) {
+	if (!h || !h->haveColorSpace) return fail(KRR_E_STATE, "set_color_space first");
+	return leafRun(in, n, 8, out, 20, [&](const float *dq, float *dr) { k_leaf_color<<<(n + 63) / 64, 64>>>(dq, n, dr, h->cs); });
+}
+
+extern "C" int krr_wfpt_debug_camera_rays(KrrWfpt *h, const KrrCameraData *c, int32_t W, int32_t H, const float *in, int32_t n, float *out) {
+	if (!h || !c || W <= 0 || H <= 0) return fail(KRR_E_INVALID, "bad argument");
+	KrrCameraDev cam = makeCamera(c);
+	return leafRun(in, n, 7, out, 7, [&](const float *dq, float *dr) { k_leaf_camera<<<(n + 63) / 64, 64>>>(cam, W, H, dq, n, dr); });
 }
