@@ -10,9 +10,11 @@ Metric: Mrays/s = (closest-hit rays + shadow rays popped from the queues) / devi
 (SURVEY.md section 8d).  `value` is timed with the film in HBM; `e2e` goes through the C ABI with
 HOST buffers (camera struct in, RGBA32F film out through pinned memory) inside the timed region.
 
-Multi-GPU (N ranks, one per GPU): the spp axis is split by FRAME -- rank r renders frame indices
-r+1, r+1+N, ... (the reference accumulates spp across frames) -- the scene is replicated, and the
-films are summed with one NCCL all-reduce per step inside the timed region.  scaling = "weak".
+Multi-GPU (N ranks, one per GPU; kiraray_b200/multigpu.py): the work is split by image tile and/or
+by spp slice (`--partition spp|tile|hybrid`, default spp: rank r renders frame indices r+1, r+1+N,
+... -- the reference accumulates spp across frames), the scene is replicated, and the films are
+summed with ONE NCCL reduce to rank 0 per step, inside the timed region.  With the spp split every
+GPU renders a full frame per step, so per-GPU work is fixed: scaling = "weak".
 
 `--impl reference`: the reference's own KRR_CALLABLE integrator code compiled host-side
 (oracle/_ref) driven by the CPU restatement of the wavefront stages, on all host cores, on a bounded
@@ -37,6 +39,15 @@ MAX_DEPTH, RR = 10, 0.8
 BYTES_PER_RAY = 752.0
 # per-stage split of that figure (DESIGN.md "Roofline accounting"), bytes per unit the stage processes
 STAGE_BYTES = {"closest": 120 + 32 + 232 + 244, "scatter": 232 + 32 + 32 + 92 + 120, "shadow": 92 + 32 + 244}
+
+
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
 
 
 def load_peaks():
@@ -150,6 +161,7 @@ def main():
     ap.add_argument("--spp", type=int, default=8, help="samples per pixel per frame (one step = one frame)")
     ap.add_argument("--ref-rows", type=int, default=0, help="rows of the frame the CPU reference renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -172,11 +184,15 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from kiraray_b200.multigpu import make_partition, reduce_film
+    part = make_partition(rank, world, H, args.partition)
     app = make_app(args.spp)
     cam = app.camera()
     gpu = krr.Wfpt(params=dict(app.wfpt_params()))
     gpu.set_scene(app.scene_desc())
     gpu.resize(W, H)
+    if part.tiles > 1:
+        gpu.set_partition(*part.rows)
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     film = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
@@ -184,13 +200,12 @@ def main():
     host_np = film_host.numpy()
 
     def frame_of(step):
-        return 1 + rank + step * world
+        return part.frame_index(step)
 
     def step_device(i):
         gpu.begin_frame(frame_of(i), cam, sptr)
         gpu.render(film.data_ptr(), sptr)
-        if dist is not None:
-            dist.all_reduce(film)  # film accumulation over NVLink (the one exchange step)
+        reduce_film(film, part, dist)  # film accumulation over NVLink (the one exchange step)
 
     def step_e2e(i):
         gpu.begin_frame(frame_of(i), cam, sptr)  # camera struct: host -> device (kernel arguments)
@@ -198,8 +213,9 @@ def main():
             gpu.render_to_host(host_np, sptr)    # render + D2H of the film + stream sync
         else:
             gpu.render(film.data_ptr(), sptr)
-            dist.all_reduce(film)
-            film_host.copy_(film, non_blocking=True)
+            reduce_film(film, part, dist)
+            if rank == 0:
+                film_host.copy_(film, non_blocking=True)
             stream.synchronize()
 
     def barrier():
@@ -247,13 +263,14 @@ def main():
     gpu.set_profiling(False)
     st = gpu.stats()
 
-    t = torch.tensor([ms, ms_e2e, float(rays)], dtype=torch.float64, device="cuda")
+    pixels = (part.rows[1] - part.rows[0]) * W
+    t = torch.tensor([ms, ms_e2e, float(rays), float(pixels)], dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, ms_e2e, rays = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        ms, ms_e2e, rays, pixels = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
     if rank == 0:
         peak, peak_src = load_peaks()
         value = rays / (ms * 1e-3) / 1e6
@@ -264,7 +281,8 @@ def main():
         total_ms = sum(v["ms"] for v in stages.values())
         dom_gbs = units * STAGE_BYTES[dom] / (stages[dom]["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"closest": "k_trace_closest", "scatter": "k_scatter<Disney>", "shadow": "k_trace_shadow"}[dom],
-                    "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                    "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom_gbs / peak,
+                    "traffic": load_traffic({"closest": "k_trace_closest", "scatter": "k_scatter", "shadow": "k_trace_shadow"}[dom]),
                     "algorithmic_bytes_per_unit": STAGE_BYTES[dom], "units_per_step": units, "launches_per_step": stages[dom]["launches"],
                     "avg_launch_ms": stages[dom]["ms"] / max(1, stages[dom]["launches"]),
                     "stage_share": {k: (v["ms"] / total_ms if total_ms else 0) for k, v in stages.items()},
@@ -273,12 +291,12 @@ def main():
         if not args.no_cpu_baseline:
             v, info = cpu_reference_rate(app, args.spp, args.ref_rows or 540)  # half the frame: ~10-20 s
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}
-        spp_s = args.spp * args.steps * world / (ms * 1e-3)
+        spp_s = args.spp * args.steps * (pixels / (W * H)) / (ms * 1e-3)  # full-frame samples per pixel per second, all ranks
         line = {"metric": "Mrays/s (primary+shadow+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "width": W, "height": H, "max_depth": MAX_DEPTH, "rr": RR, "nee": True,
-                           "spp_per_step": args.spp, "parallelism": f"spp-by-frame x{world}, scene replicated, film all-reduce",
+                           "spp_per_step": args.spp, "parallelism": part.describe(),
                            "l2": "per-step queue + pixel-state working set (~0.9 GB) exceeds the 126 MB L2", "spp_per_s": spp_s},
                 "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(krr.KrrCameraData), "d2h_bytes_per_step": W * H * 16},
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}

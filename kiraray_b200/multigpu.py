@@ -1,0 +1,74 @@
+"""Work partition of the WavefrontPathTracer pass across the GPUs of one box (one process per GPU).
+
+The reference is single-device (src/core/device/context.cpp:37-40); SURVEY.md section 8(e) derives
+the split from the path's own structure: pixels are independent (per-pixel RNG stream and
+accumulator, integrator.cpp:213-220) and frames are independent samples (the reference averages
+frames in AccumulatePass, accumulate.cu:30-52).  So the work is a T x S grid of
+  * T image tiles  -- contiguous row bands; a rank renders only its rows and writes zeros elsewhere
+                      (krr_wfpt_set_partition), so tile films ADD to the full film, and
+  * S spp slices   -- rank s renders frame indices  first + s, first + s + S, ...  (every frame index
+                      seeds a different PCG sequence: sampleIndex = frameIndex * spp),
+with the scene replicated.  The ONE exchange step is the film accumulation: a sum-reduce of the
+RGBA32F film to rank 0 (NCCL over NVLink on the GPUs, gloo in the CPU tests), then a division by S.
+No other collective is on the path.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Partition:
+    rank: int
+    world: int
+    tiles: int        # T
+    spp_slices: int   # S;  T * S == world
+    height: int
+
+    @property
+    def tile(self):
+        return self.rank % self.tiles
+
+    @property
+    def spp_slice(self):
+        return self.rank // self.tiles
+
+    @property
+    def rows(self):
+        """[begin, end) rows of this rank's tile; bands differ by at most one row."""
+        t, T, H = self.tile, self.tiles, self.height
+        return (t * H) // T, ((t + 1) * H) // T
+
+    def frame_index(self, step, first_frame=1):
+        """Frame index this rank renders at `step` (first frame is 1, src/core/window.cpp:457)."""
+        return first_frame + self.spp_slice + step * self.spp_slices
+
+    def describe(self):
+        return f"tile {self.tiles} x spp-by-frame {self.spp_slices}, scene replicated, film sum-reduce to rank 0"
+
+
+def make_partition(rank, world, height, mode="spp", tiles=None):
+    """mode 'spp': S = world; 'tile': T = world; 'hybrid': T = tiles (must divide world)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    if mode == "spp":
+        T = 1
+    elif mode == "tile":
+        T = world
+    elif mode == "hybrid":
+        T = tiles or (2 if world % 2 == 0 and world > 1 else 1)
+    else:
+        raise ValueError(f"unknown partition mode {mode!r}")
+    if world % T != 0:
+        raise ValueError(f"tiles={T} does not divide world={world}")
+    if T > height:
+        raise ValueError("more tiles than rows")
+    return Partition(rank, world, T, world // T, height)
+
+
+def reduce_film(film, part, dist=None, dst=0):
+    """Film accumulation: sum over ranks to `dst`, then the average over the spp slices.  `film` is a
+    torch tensor (H, W, 4) -- CUDA for NCCL, CPU for gloo; modified in place on dst."""
+    if dist is not None and part.world > 1:
+        dist.reduce(film, dst=dst)
+    if part.rank == dst and part.spp_slices > 1:
+        film /= part.spp_slices
+    return film
