@@ -14,7 +14,9 @@
 //     FMA-contracted), accept 0 < t < tmax, ties on t broken by (instance, primitive) so that the
 //     result does not depend on traversal order -> first-hit ids are bit-exact against the oracle's
 //     brute-force loop.
-//   * per-thread traversal with a short stack; hit internal children are pushed far-to-near.
+//   * warp-cooperative traversal (see Traverser below): phase-aligned stepping, shared-memory short
+//     stack, hit children sorted by entry distance with a sorting network, persistent warps that
+//     refill finished lanes from the queue.
 #pragma once
 #include "krr_math.cuh"
 #include "scene.cuh"
@@ -71,125 +73,182 @@ KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 }
 
 #ifdef __CUDACC__
-constexpr int kStackSize = 96;
-constexpr uint32_t kInstFlag = 0x80000000u;
+// ---- traversal state machine ---------------------------------------------------------------------
+// One lane = one ray.  The traversal is written as a STEP function so that the stage kernels can
+// run it warp-cooperatively: every trip of the warp's loop executes the three phases
+//     [enter instance] -> [wide node: 8 slab tests, sorting network, push] -> [leaf: triangle tests]
+// under per-lane predicates, so lanes that are in the same phase execute it together, and the
+// kernel refills lanes whose ray has terminated from the queue (persistent warps, one atomicAdd per
+// refill) instead of letting them idle until the slowest ray of the warp is done.
+//
+// Stack: entries are 32-bit tagged words + the entry distance of the box (for culling at pop time
+// once a closer hit is known).  The first kShortStack entries of every lane live in SHARED memory
+// (slot-major, so a warp's accesses are conflict-free); deeper entries spill to local memory.
+//   node     : index into the node pool                                     (bits 31,30 = 00)
+//   leaf     : kLeafFlag | (count-1) << 26 | first triangle                 (bits 31,30 = 01)
+//   instance : kInstFlag | instance id  (TLAS leaves hold ONE instance)      (bits 31,30 = 10)
+constexpr int kShortStack  = 12;
+constexpr int kLocalStack  = 52;
+constexpr int kStackSize   = kShortStack + kLocalStack;
+constexpr int kTraceBlock  = 128;
+constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kEmptyEntry = 0xffffffffu;
 
-// Accept(inst, prim, u, v) -> bool decides whether a candidate counts (any-hit programs: alpha
-// kill, null-material skip).  ANY = true: return at the first accepted hit (shadow rays).
-template <bool ANY, typename Accept>
-KRR_DEV Hit traverse(const BvhDev &bvh, const InstRec *__restrict__ instances, V3 o, V3 d, float tmax,
-					 Accept accept, int *overflow) {
+struct TraceSmem {
+	uint32_t id[kShortStack][kTraceBlock];
+	float tn[kShortStack][kTraceBlock];
+};
+
+#define KRR_CSWAP(a, b) { uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+
+template <bool ANY> struct Traverser {
+	// ray
+	V3 o, d;	  // world space
+	V3 ro, rd;	  // current space (world in the TLAS, object space inside a BLAS)
+	V3 idir;
+	float tmax;
 	Hit best;
-	best.inst = -1, best.prim = -1, best.t = tmax, best.u = best.v = 0;
-	uint32_t stack[kStackSize];
-	int sp = 0;
-	V3 ro = o, rd = d; // current-space ray (world in TLAS, object in BLAS)
-	V3 idir = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
-	int curInst = -1, blasBase = -1;
-	uint32_t cur = (uint32_t) bvh.tlasRoot;
-	bool have = true;
-	while (true) {
-		if (!have) {
-			if (sp == 0) break;
+	// control
+	uint32_t cur;
+	int sp, curInst, blasBase;
+	uint32_t lstack[kLocalStack];
+	float ltn[ANY ? 1 : kLocalStack];
+	int overflow;
+
+	KRR_DEV void setIdir() { idir = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z); }
+	KRR_DEV void begin(const BvhDev &bvh, V3 o_, V3 d_, float tmax_) {
+		o = ro = o_, d = rd = d_, tmax = tmax_;
+		setIdir();
+		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
+		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
+	}
+	KRR_DEV void push(TraceSmem &sm, uint32_t e, float tn) {
+		if (sp < kShortStack) {
+			sm.id[sp][threadIdx.x] = e;
+			if (!ANY) sm.tn[sp][threadIdx.x] = tn;
+		} else if (sp < kStackSize) {
+			lstack[sp - kShortStack] = e;
+			if (!ANY) ltn[sp - kShortStack] = tn;
+		} else { overflow = 1; return; }
+		sp++;
+	}
+	KRR_DEV uint32_t pop(TraceSmem &sm, float &tn) {
+		--sp;
+		if (sp < kShortStack) {
+			if (!ANY) tn = sm.tn[sp][threadIdx.x];
+			return sm.id[sp][threadIdx.x];
+		}
+		if (!ANY) tn = ltn[sp - kShortStack];
+		return lstack[sp - kShortStack];
+	}
+
+	// One trip.  Returns false when the ray is finished (result in `best`).
+	// Accept(inst, prim, u, v) -> bool: any-hit program (alpha kill, null-material skip).
+	template <typename Accept>
+	KRR_DEV bool step(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
+		// ---- next entry ----
+		if (cur == kEmptyEntry) {
 			if (curInst >= 0 && sp == blasBase) { // BLAS finished: back to world space
 				curInst = -1;
 				ro = o, rd = d;
-				idir = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
+				setIdir();
 			}
-			cur = stack[--sp];
-			if (cur & kInstFlag) {
-				curInst = (int) (cur & ~kInstFlag);
-				const InstRec &in = instances[curInst];
-				ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
-				idir	 = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
-				blasBase = sp;
-				cur		 = (uint32_t) in.blasRoot;
-			}
+			if (sp == 0) return false;
+			float tn = 0.f;
+			cur = pop(sm, tn);
+			if (!ANY && tn > best.t) cur = kEmptyEntry; // box entry beyond the closest hit so far
 		}
-		have = false;
-		// ---- fetch node (5 x 16 B) ----
-		const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + cur);
-		float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-		uint32_t ew	  = __float_as_uint(n0.w);
-		float sx	  = __uint_as_float((ew & 0xff) << 23), sy = __uint_as_float(((ew >> 8) & 0xff) << 23),
-			  sz	  = __uint_as_float(((ew >> 16) & 0xff) << 23);
-		uint32_t imask = ew >> 24;
-		uint32_t childBase = __float_as_uint(n1.x), primBase = __float_as_uint(n1.y);
-		uint32_t metaLo = __float_as_uint(n1.z), metaHi = __float_as_uint(n1.w);
-		// quantised planes: n2 = qlo[0][0..7], qlo[1][0..7]; n3 = qlo[2], qhi[0]; n4 = qhi[1], qhi[2]
-		uint32_t q[12] = {__float_as_uint(n2.x), __float_as_uint(n2.y), __float_as_uint(n2.z), __float_as_uint(n2.w),
-						  __float_as_uint(n3.x), __float_as_uint(n3.y), __float_as_uint(n3.z), __float_as_uint(n3.w),
-						  __float_as_uint(n4.x), __float_as_uint(n4.y), __float_as_uint(n4.z), __float_as_uint(n4.w)};
-		// ray in node-local units: t = (o_node + q*s - o) * idir = q * (s*idir) + (o_node - o)*idir
-		float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
-		float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
-		const float lim = best.t;
-		uint32_t keys[8];
-		int nk = 0;
-#pragma unroll
-		for (int i = 0; i < 8; i++) {
-			uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
-			bool internal = (imask >> i) & 1;
-			if (!internal && meta == 0) continue;
-			auto qb = [&](int row) { return (float) ((q[row * 2 + (i >> 2)] >> ((i & 3) * 8)) & 0xff); };
-			float lx = qb(0), ly = qb(1), lz = qb(2), hx = qb(3), hy = qb(4), hz = qb(5);
-			float t0x = lx * ax + bx, t1x = hx * ax + bx;
-			float t0y = ly * ay + by, t1y = hy * ay + by;
-			float t0z = lz * az + bz, t1z = hz * az + bz;
-			// fminf/fmaxf drop NaNs (0 * inf), which is the conservative answer for a degenerate slab
-			float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
-			float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), lim));
-			// conservative: boxes only cull, the exact decision is the triangle test
-			if (!(tn <= tf * 1.0000010f + 1e-30f)) continue;
-			if (internal) {
-				// key: distance in the high bits, slot in the low 3 -> one compare orders (tn, slot)
-				keys[nk++] = (__float_as_uint(tn) & ~7u) | (uint32_t) i;
-			} else {
-				uint32_t cnt = meta >> 5, off = meta & 31;
-				if (curInst < 0) {
-					// TLAS leaf: defer each instance (entered when popped)
-					for (uint32_t k = 0; k < cnt; k++) {
-						if (sp >= kStackSize) { *overflow = 1; continue; }
-						stack[sp++] = kInstFlag | (uint32_t) __ldg(bvh.tlasInst + primBase + off + k);
-					}
-				} else {
-					for (uint32_t k = 0; k < cnt; k++) {
-						const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + primBase + off + k);
-						float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-						float t, u, v;
-						if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
-							int prim = __float_as_int(a.w);
-							if (betterHit(t, curInst, prim, best) && accept(curInst, prim, u, v)) {
-								best.inst = curInst, best.prim = prim, best.t = t, best.u = u, best.v = v;
-								if (ANY) return best;
-							}
-						}
+		// ---- phase 1: enter an instance ----
+		if (cur != kEmptyEntry && (cur & kInstFlag)) {
+			curInst = (int) (cur & 0x3fffffffu);
+			const InstRec &in = instances[curInst];
+			ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
+			setIdir();
+			blasBase = sp;
+			cur		 = (uint32_t) in.blasRoot;
+		}
+		// ---- phase 2: wide node ----
+		if (cur < kLeafFlag) {
+			const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + cur);
+			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			uint32_t ew = __float_as_uint(n0.w);
+			float sx = __uint_as_float((ew & 0xff) << 23), sy = __uint_as_float(((ew >> 8) & 0xff) << 23),
+				  sz = __uint_as_float(((ew >> 16) & 0xff) << 23);
+			const uint32_t imask = ew >> 24;
+			const uint32_t childBase = __float_as_uint(n1.x), primBase = __float_as_uint(n1.y);
+			const uint32_t metaLo = __float_as_uint(n1.z), metaHi = __float_as_uint(n1.w);
+			// quantised planes: n2 = qlo[0][0..7], qlo[1][0..7]; n3 = qlo[2], qhi[0]; n4 = qhi[1], qhi[2]
+			const uint32_t q[12] = {__float_as_uint(n2.x), __float_as_uint(n2.y), __float_as_uint(n2.z), __float_as_uint(n2.w),
+									__float_as_uint(n3.x), __float_as_uint(n3.y), __float_as_uint(n3.z), __float_as_uint(n3.w),
+									__float_as_uint(n4.x), __float_as_uint(n4.y), __float_as_uint(n4.z), __float_as_uint(n4.w)};
+			// t = (o_node + q*s - o) * idir = q * (s*idir) + (o_node - o)*idir
+			const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
+			const float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
+			const float lim = best.t;
+			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
+			auto child = [&](int i) -> uint32_t {
+				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
+				bool internal = (imask >> i) & 1;
+				if (!internal && meta == 0) return kEmptyEntry;
+				auto qb = [&](int row) { return (float) ((q[row * 2 + (i >> 2)] >> ((i & 3) * 8)) & 0xff); };
+				float t0x = qb(0) * ax + bx, t1x = qb(3) * ax + bx;
+				float t0y = qb(1) * ay + by, t1y = qb(4) * ay + by;
+				float t0z = qb(2) * az + bz, t1z = qb(5) * az + bz;
+				// fminf/fmaxf drop NaNs (0 * inf), which is the conservative answer for a degenerate slab
+				float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+				float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), lim));
+				// conservative: boxes only cull, the exact decision is the triangle test
+				if (!(tn <= tf * 1.0000010f + 1e-30f)) return kEmptyEntry;
+				// key: entry distance in the high bits, slot in the low 3 -> one compare orders (tn, slot)
+				return (__float_as_uint(tn) & ~7u) | (uint32_t) i;
+			};
+			k0 = child(0), k1 = child(1), k2 = child(2), k3 = child(3), k4 = child(4), k5 = child(5), k6 = child(6), k7 = child(7);
+			// 19-comparator sorting network: ascending, misses (0xffffffff) sink to the end
+			KRR_CSWAP(k0, k1) KRR_CSWAP(k2, k3) KRR_CSWAP(k4, k5) KRR_CSWAP(k6, k7)
+			KRR_CSWAP(k0, k2) KRR_CSWAP(k1, k3) KRR_CSWAP(k4, k6) KRR_CSWAP(k5, k7)
+			KRR_CSWAP(k1, k2) KRR_CSWAP(k5, k6) KRR_CSWAP(k0, k4) KRR_CSWAP(k3, k7)
+			KRR_CSWAP(k1, k5) KRR_CSWAP(k2, k6)
+			KRR_CSWAP(k1, k4) KRR_CSWAP(k3, k6)
+			KRR_CSWAP(k2, k4) KRR_CSWAP(k3, k5)
+			KRR_CSWAP(k3, k4)
+			const bool tlas = curInst < 0;
+			auto entryOf = [&](uint32_t key) -> uint32_t {
+				uint32_t slot = key & 7u;
+				if ((imask >> slot) & 1) return childBase + __popc(imask & ((1u << slot) - 1));
+				uint32_t meta = ((slot < 4 ? metaLo : metaHi) >> ((slot & 3) * 8)) & 0xff;
+				uint32_t first = primBase + (meta & 31);
+				if (tlas) return kInstFlag | (uint32_t) __ldg(bvh.tlasInst + first); // one instance per TLAS leaf
+				return kLeafFlag | (((meta >> 5) - 1) << 26) | first;
+			};
+			// far-to-near onto the stack, nearest continues
+			if (k7 != kEmptyEntry) push(sm, entryOf(k7), __uint_as_float(k7 & ~7u));
+			if (k6 != kEmptyEntry) push(sm, entryOf(k6), __uint_as_float(k6 & ~7u));
+			if (k5 != kEmptyEntry) push(sm, entryOf(k5), __uint_as_float(k5 & ~7u));
+			if (k4 != kEmptyEntry) push(sm, entryOf(k4), __uint_as_float(k4 & ~7u));
+			if (k3 != kEmptyEntry) push(sm, entryOf(k3), __uint_as_float(k3 & ~7u));
+			if (k2 != kEmptyEntry) push(sm, entryOf(k2), __uint_as_float(k2 & ~7u));
+			if (k1 != kEmptyEntry) push(sm, entryOf(k1), __uint_as_float(k1 & ~7u));
+			cur = k0 != kEmptyEntry ? entryOf(k0) : kEmptyEntry;
+		}
+		// ---- phase 3: leaf (1..7 triangles) ----
+		if (cur != kEmptyEntry && (cur >> 30) == 1u) {
+			const uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
+			cur = kEmptyEntry;
+			for (uint32_t k = 0; k < cnt; k++) {
+				const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
+				float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t, u, v;
+				if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
+					int prim = __float_as_int(a.w);
+					if (betterHit(t, curInst, prim, best) && accept(curInst, prim, u, v)) {
+						best.inst = curInst, best.prim = prim, best.t = t, best.u = u, best.v = v;
+						if (ANY) return false;
 					}
 				}
 			}
 		}
-		if (nk) {
-			// sort far-to-near so the nearest child is popped first (insertion sort, nk <= 8)
-			for (int i = 1; i < nk; i++) {
-				uint32_t k = keys[i];
-				int j = i - 1;
-				while (j >= 0 && keys[j] < k) { keys[j + 1] = keys[j]; j--; }
-				keys[j + 1] = k;
-			}
-			// continue with the nearest, push the rest
-			for (int i = 0; i < nk - 1; i++) {
-				uint32_t slot = keys[i] & 7u;
-				if (sp >= kStackSize) { *overflow = 1; continue; }
-				stack[sp++] = childBase + __popc(imask & ((1u << slot) - 1));
-			}
-			uint32_t slot = keys[nk - 1] & 7u;
-			cur	 = childBase + __popc(imask & ((1u << slot) - 1));
-			have = true;
-		}
+		return true;
 	}
-	if (best.inst < 0) best.t = tmax;
-	return best;
-}
+};
 #endif // __CUDACC__
 
 } // namespace krr

@@ -43,7 +43,8 @@ struct DepthCounters {	// one block per loop depth; 16 ints = 64 B
 	int32_t nScatter[MAT_COUNT];
 	int32_t nShadow;
 	int32_t nMediumSample, nMediumScatter;
-	int32_t pad[5];
+	int32_t cursorRay, cursorShadow; // work cursors of the persistent trace kernels (next unclaimed item)
+	int32_t pad[3];
 };
 static_assert(sizeof(DepthCounters) == 64, "DepthCounters");
 
@@ -116,13 +117,25 @@ KRR_DEV int warpPush(int32_t *counter, bool pred) {
 	return base + __popc(mask & ((1u << lane) - 1));
 }
 
+// same, for code that runs with the whole warp converged (persistent trace kernels)
+KRR_DEV int warpPushFull(int32_t *counter, bool pred) {
+	unsigned mask = __ballot_sync(0xffffffffu, pred);
+	if (!mask) return -1;
+	int lane   = threadIdx.x & 31;
+	int leader = __ffs(mask) - 1;
+	int base   = 0;
+	if (lane == leader) base = atomicAdd(counter, __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return pred ? base + __popc(mask & ((1u << lane) - 1)) : -1;
+}
+
 KRR_DEV float4 ldg4(const float4 *p) { return __ldg(p); }
 // streaming (read-once / write-once) queue traffic: keep it out of L1
 KRR_DEV float4 ldcs4(const float4 *p) { return __ldcs(p); }
 KRR_DEV void stcs4(float4 *p, float4 v) { __stcs(p, v); }
 
 // =================================================================================================
-__global__ void k_begin_frame(Wavefront wf, uint32_t seedIndex) {
+__global__ void k_begin_frame(const __grid_constant__ Wavefront wf, uint32_t seedIndex) {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		int pixelId = wf.p.pixelBegin + i;
 		int px = pixelId % wf.p.width, py = pixelId / wf.p.width;
@@ -161,7 +174,7 @@ KRR_DEV void cameraRay(const KrrCameraDev &c, int px, int py, int W, int H, cons
 	d = mk3(row(0, ld), row(1, ld), row(2, ld));
 }
 
-__global__ void k_generate_camera_rays(Wavefront wf) {
+__global__ void k_generate_camera_rays(const __grid_constant__ Wavefront wf) {
 	RayQueue q = wf.rays[0];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		int pixelId = wf.p.pixelBegin + i;
@@ -201,7 +214,7 @@ KRR_DEV uint64_t murmur64A(const unsigned char *key, int len, uint64_t seed) {
 	h ^= h >> r; h *= m; h ^= h >> r; // len is a multiple of 8 here (24 bytes)
 	return h;
 }
-KRR_DEV bool alphaKilled(const Wavefront &wf, int inst, int prim, float u, float v, V3 o, V3 d) {
+__device__ __noinline__ bool alphaKilled(const Wavefront &wf, int inst, int prim, float u, float v, V3 o, V3 d) {
 	const MeshRec &mesh = wf.scene.meshes[wf.scene.instances[inst].mesh];
 	if (mesh.material < 0) return false;
 	const TexRec &t = wf.scene.materials[mesh.material].tex[4];
@@ -224,33 +237,87 @@ KRR_DEV bool alphaKilled(const Wavefront &wf, int inst, int prim, float u, float
 }
 
 // =================================================================================================
-// Closest stage: traverse, record the hit, route the slot index (device.cu:43-81)
-__global__ void __launch_bounds__(128) k_trace_closest(Wavefront wf, int depth) {
+// Closest stage: traverse, record the hit, route the slot index (device.cu:43-81).
+// Persistent warps: a warp claims rays from the queue with one atomicAdd, steps all its lanes
+// through the phase-aligned traversal (bvh.cuh), finalises the lanes whose ray terminated and
+// refills them as soon as kRefill lanes are idle -- SIMT lanes do not wait for the slowest ray.
+constexpr int kRefill = 8;
+
+// null-material hit: re-queue the ray behind the surface at the same item depth (device.cu:54-58)
+__device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4) {
+	const InstRec &in	= wf.scene.instances[h.inst];
+	const MeshRec &mesh = wf.scene.meshes[in.mesh];
+	const int32_t *idx	= wf.scene.indices + 3 * ((size_t) mesh.idxOff + h.prim);
+	const float *P		= wf.scene.positions + 3 * (size_t) mesh.posOff;
+	V3 p0 = ld3(P + 3 * idx[0]), p1 = ld3(P + 3 * idx[1]), p2 = ld3(P + 3 * idx[2]);
+	float b0 = 1 - h.u - h.v;
+	V3 p = xfPoint(in.xf, b0 * p0 + h.u * p1 + h.v * p2);
+	V3 n;
+	if (mesh.nrmOff >= 0) {
+		const float *N = wf.scene.normals + 3 * (size_t) mesh.nrmOff;
+		n = normalize(b0 * ld3(N + 3 * idx[0]) + h.u * ld3(N + 3 * idx[1]) + h.v * ld3(N + 3 * idx[2]));
+	} else n = normalize(cross(p1 - p0, p2 - p0));
+	n = normalize(xfNormal(in.inv, n));
+	V3 d = mk3(d4);
+	V3 off = n * kRayEps;
+	if (dot(n, d) < 0.f) off = -off;
+	V3 no = p + off;
+	stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, o4.w));
+	stcs4(nq.d_medium + s, d4);
+	stcs4(nq.thp + s, ldcs4(q.thp + i));
+	stcs4(nq.pu + s, ldcs4(q.pu + i));
+	stcs4(nq.pl + s, ldcs4(q.pl + i));
+	stcs4(nq.ctxP_pix + s, ldcs4(q.ctxP_pix + i));
+	stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
 	const RayQueue q	= wf.rays[depth & 1];
 	const RayQueue nq	= wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc	= wf.counters + depth;
 	const int n			= dc->nRay;
-	const int stride	= gridDim.x * blockDim.x;
-	const int nIter		= (n + stride - 1) / stride;
-	for (int it = 0; it < nIter; it++) {
-		int i		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-		bool active = i < n;
+	const unsigned FULL = 0xffffffffu;
+	const int lane		= threadIdx.x & 31;
+	Traverser<false> tr;
+	int ray		   = -1;	// queue slot this lane is tracing, -1 = idle
+	bool exhausted = false; // warp-uniform: the queue has no unclaimed rays left
+	float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+	while (true) {
+		unsigned idle = __ballot_sync(FULL, ray < 0);
+		if (!exhausted && __popc(idle) >= kRefill) {
+			const int cnt = __popc(idle);
+			int base	  = 0;
+			if (lane == 0) base = atomicAdd(&dc->cursorRay, cnt);
+			base = __shfl_sync(FULL, base, 0);
+			if (ray < 0) {
+				int r = base + __popc(idle & ((1u << lane) - 1));
+				if (r < n) {
+					ray = r;
+					o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
+					tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf);
+				}
+			}
+			exhausted = base + cnt >= n;
+			idle	  = __ballot_sync(FULL, ray < 0);
+		}
+		if (idle == FULL) break;
+		bool fin = false;
+		if (ray >= 0) {
+			fin = !tr.step(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+				if (!(wf.instFlags[inst] & 2)) return true;
+				return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
+			});
+		}
+		if (!__ballot_sync(FULL, fin)) continue;
+		// ---- finalise the lanes whose ray terminated (whole warp converged here) ----
 		int route	= -1; // 0 miss, 1 scatter(+light), 2 null-material pass-through
 		int matType = 0;
 		bool light	= false;
-		Hit h;
-		h.inst = -1;
-		float4 o4, d4;
-		if (active) {
-			o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
-			V3 o = mk3(o4), d = mk3(d4);
-			int overflow = 0;
-			h = traverse<false>(wf.bvh, wf.scene.instances, o, d, kInf,
-				[&](int inst, int prim, float u, float v) {
-					if (!(wf.instFlags[inst] & 2)) return true;
-					return !alphaKilled(wf, inst, prim, u, v, o, d);
-				}, &overflow);
-			if (overflow) atomicExch(&wf.errorFlags[0], 1);
+		const Hit h = tr.best;
+		const int i = ray;
+		if (fin) {
+			if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
 			wf.hits[i] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
 			if (depth == 0 && wf.firstHits) {
 				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
@@ -267,48 +334,21 @@ __global__ void __launch_bounds__(128) k_trace_closest(Wavefront wf, int depth) 
 					light	= in.lightBase >= 0;
 				}
 			}
+			ray = -1;
 		}
 		// (media: rays inside a medium are routed to the medium-sample queue by the media build)
 		int s;
-		s = warpPush(&dc->nMiss, route == 0);
+		s = warpPushFull(&dc->nMiss, route == 0);
 		if (s >= 0) wf.missIdx[s] = i;
-		s = warpPush(&dc->nHitLight, route == 1 && light);
+		s = warpPushFull(&dc->nHitLight, route == 1 && light);
 		if (s >= 0) wf.hitLightIdx[s] = i;
 #pragma unroll
-		for (int mt = 1; mt < MAT_COUNT; mt++) {
-			s = warpPush(&dc->nScatter[mt], route == 1 && matType == mt);
+		for (int mt = 0; mt < MAT_COUNT; mt++) {
+			s = warpPushFull(&dc->nScatter[mt], route == 1 && matType == mt);
 			if (s >= 0) wf.scatterIdx[mt][s] = i;
 		}
-		s = warpPush(&dc->nScatter[MAT_NULL], route == 1 && matType == MAT_NULL);
-		if (s >= 0) wf.scatterIdx[MAT_NULL][s] = i;
-		// null material: re-queue the ray at the same item depth (device.cu:54-58)
-		s = warpPush(&dc[1].nRay, route == 2);
-		if (s >= 0) {
-			const InstRec &in	= wf.scene.instances[h.inst];
-			const MeshRec &mesh = wf.scene.meshes[in.mesh];
-			const int32_t *idx	= wf.scene.indices + 3 * ((size_t) mesh.idxOff + h.prim);
-			const float *P		= wf.scene.positions + 3 * (size_t) mesh.posOff;
-			V3 p0 = ld3(P + 3 * idx[0]), p1 = ld3(P + 3 * idx[1]), p2 = ld3(P + 3 * idx[2]);
-			float b0 = 1 - h.u - h.v;
-			V3 p = xfPoint(in.xf, b0 * p0 + h.u * p1 + h.v * p2);
-			V3 n;
-			if (mesh.nrmOff >= 0) {
-				const float *N = wf.scene.normals + 3 * (size_t) mesh.nrmOff;
-				n = normalize(b0 * ld3(N + 3 * idx[0]) + h.u * ld3(N + 3 * idx[1]) + h.v * ld3(N + 3 * idx[2]));
-			} else n = normalize(cross(p1 - p0, p2 - p0));
-			n = normalize(xfNormal(in.inv, n));
-			V3 d = mk3(d4);
-			V3 off = n * kRayEps;
-			if (dot(n, d) < 0.f) off = -off;
-			V3 no = p + off;
-			stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, o4.w));
-			stcs4(nq.d_medium + s, d4);
-			stcs4(nq.thp + s, ldcs4(q.thp + i));
-			stcs4(nq.pu + s, ldcs4(q.pu + i));
-			stcs4(nq.pl + s, ldcs4(q.pl + i));
-			stcs4(nq.ctxP_pix + s, ldcs4(q.ctxP_pix + i));
-			stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
-		}
+		s = warpPushFull(&dc[1].nRay, route == 2);
+		if (s >= 0) requeueThroughNull(wf, q, nq, i, s, h, o4, d4);
 	}
 }
 
@@ -447,7 +487,7 @@ KRR_DEV void evalMaterial(const Wavefront &wf, SurfaceGeom &g, const Wavelengths
 
 // =================================================================================================
 // handleHit + handleMiss (integrator.cpp:78-108)
-__global__ void __launch_bounds__(128) k_handle_hit_miss(Wavefront wf, int depth) {
+__global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	DepthCounters *dc = wf.counters + depth;
 	const int stride  = gridDim.x * blockDim.x;
@@ -507,7 +547,7 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(Wavefront wf, int depth
 // =================================================================================================
 // generateScatterRays (integrator.cpp:110-164), one launch per material type
 template <int MT>
-__global__ void __launch_bounds__(128) k_scatter(Wavefront wf, int depth) {
+__global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc = wf.counters + depth;
@@ -631,32 +671,56 @@ __global__ void __launch_bounds__(128) k_scatter(Wavefront wf, int depth) {
 }
 
 // =================================================================================================
-// Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean()
-__global__ void __launch_bounds__(128) k_trace_shadow(Wavefront wf, int depth) {
-	DepthCounters *dc = wf.counters + depth;
-	const int n		  = dc->nShadow;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		float4 o4 = ldcs4(wf.shadow.o_tmax + i), d4 = ldcs4(wf.shadow.d_pix + i);
-		V3 o = mk3(o4), d = mk3(d4);
-		int overflow = 0;
-		Hit h = traverse<true>(wf.bvh, wf.scene.instances, o, d, o4.w,
-			[&](int inst, int prim, float u, float v) {
+// Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean().  Same persistent
+// warp scheme as the closest stage; the ray terminates at the first accepted hit.
+__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
+	DepthCounters *dc	= wf.counters + depth;
+	const int n			= dc->nShadow;
+	const unsigned FULL = 0xffffffffu;
+	const int lane		= threadIdx.x & 31;
+	Traverser<true> tr;
+	int ray = -1, pix = 0;
+	bool exhausted = false;
+	while (true) {
+		unsigned idle = __ballot_sync(FULL, ray < 0);
+		if (!exhausted && __popc(idle) >= kRefill) {
+			const int cnt = __popc(idle);
+			int base	  = 0;
+			if (lane == 0) base = atomicAdd(&dc->cursorShadow, cnt);
+			base = __shfl_sync(FULL, base, 0);
+			if (ray < 0) {
+				int r = base + __popc(idle & ((1u << lane) - 1));
+				if (r < n) {
+					ray = r;
+					float4 o4 = ldcs4(wf.shadow.o_tmax + r), d4 = ldcs4(wf.shadow.d_pix + r);
+					pix = __float_as_int(d4.w);
+					tr.begin(wf.bvh, mk3(o4), mk3(d4), o4.w);
+				}
+			}
+			exhausted = base + cnt >= n;
+			idle	  = __ballot_sync(FULL, ray < 0);
+		}
+		if (idle == FULL) break;
+		if (ray >= 0) {
+			bool more = tr.step(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
 				uint8_t f = wf.instFlags[inst];
 				if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
-				if (f & 2) return !alphaKilled(wf, inst, prim, u, v, o, d);
+				if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
 				return true;
-			}, &overflow);
-		if (overflow) atomicExch(&wf.errorFlags[0], 1);
-		if (h.inst < 0) {
-			int pix = __float_as_int(d4.w);
-			wf.px.L[pix] = ldcs4(wf.shadow.contrib + i) + wf.px.L[pix];
+			});
+			if (!more) {
+				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+				if (tr.best.inst < 0) wf.px.L[pix] = ldcs4(wf.shadow.contrib + ray) + wf.px.L[pix];
+				ray = -1;
+			}
 		}
 	}
 }
 
 // per-sample resolve (integrator.cpp:257-260).  Note the reference does NOT reset L between the
 // samples of one frame, so sample k adds the running sum; kept as is.
-__global__ void k_resolve(Wavefront wf) {
+__global__ void k_resolve(const __grid_constant__ Wavefront wf) {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		Wavelengths wl = expandWavelengths(wf.px.lambda[i]);
 		float rgb[3];
@@ -667,7 +731,7 @@ __global__ void k_resolve(Wavefront wf) {
 }
 
 // film write (integrator.cpp:262-266): /spp, optional clamp, alpha 1, row H-1-y (cuda.h:33-36)
-__global__ void k_film(Wavefront wf, float4 *film, int zeroOutside) {
+__global__ void k_film(const __grid_constant__ Wavefront wf, float4 *film, int zeroOutside) {
 	const int N = wf.p.width * wf.p.height;
 	for (int pixelId = blockIdx.x * blockDim.x + threadIdx.x; pixelId < N; pixelId += gridDim.x * blockDim.x) {
 		int i = pixelId - wf.p.pixelBegin;
@@ -712,7 +776,7 @@ __global__ void k_fold_counters(DepthCounters *c, StatTotals *t, int nDepth, int
 }
 
 // debug tap: integer fields of the queues at one (sample, depth)
-__global__ void k_capture(Wavefront wf, int depth, int queue, int4 *out, int32_t *outCount) {
+__global__ void k_capture(const __grid_constant__ Wavefront wf, int depth, int queue, int4 *out, int32_t *outCount) {
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc = wf.counters + depth;
