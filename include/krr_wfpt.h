@@ -233,6 +233,9 @@ enum { KRR_STAGE_CAMERA = 0, KRR_STAGE_CLOSEST = 1, KRR_STAGE_HIT_MISS = 2, KRR_
 	   KRR_STAGE_RESOLVE = 5, KRR_STAGE_MEDIUM = 6, KRR_STAGE_COUNT = 7 };
 int krr_wfpt_set_profiling(KrrWfpt *h, int32_t enable);
 int krr_wfpt_get_stage_times(KrrWfpt *h, double *ms, int32_t *launches, int32_t reset);
+/* the same events launch by launch, in issue order: stage id and milliseconds of each; returns the
+ * number of launches recorded (<= capacity are written) */
+int krr_wfpt_get_launch_times(KrrWfpt *h, int32_t *stage, float *ms, int32_t capacity);
 
 /* ---- parity / debug taps (read-only views of device state; used by tests and smoke) ---- */
 /* depth-0 hit per pixel of the LAST sample rendered: instance id and primitive id (-1 = miss) */

@@ -133,7 +133,8 @@ def load_wfpt():
     global _wfpt
     if _wfpt is not None:
         return _wfpt
-    lib = _load("libkrr_wfpt.so")
+    override = os.environ.get("KRR_WFPT_LIB")  # tuning aid: a variant built by build.py build_variant()
+    lib = C.CDLL(override, mode=C.RTLD_GLOBAL) if override else _load("libkrr_wfpt.so")
     lib.krr_wfpt_last_error.restype = C.c_char_p
     sig = {
         "krr_wfpt_create": [C.c_char_p, C.POINTER(P)],
@@ -150,6 +151,7 @@ def load_wfpt():
         "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
         "krr_wfpt_set_profiling": [P, I32],
         "krr_wfpt_get_stage_times": [P, C.POINTER(C.c_double), C.POINTER(I32), I32],
+        "krr_wfpt_get_launch_times": [P, C.POINTER(I32), C.POINTER(F), I32],
         "krr_wfpt_debug_first_hits": [P, P, P],
         "krr_wfpt_debug_pixel_state": [P, P, P, P],
         "krr_wfpt_debug_capture": [P, I32, I32],
@@ -375,6 +377,11 @@ class Wfpt:
         ms, n = (C.c_double * 7)(), (I32 * 7)()
         self._ck(self.lib.krr_wfpt_get_stage_times(self.h, ms, n, int(reset)), "get_stage_times")
         return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(self.STAGES)}
+
+    def launch_times(self, capacity=8192):
+        st, ms = (I32 * capacity)(), (F * capacity)()
+        n = self._ck(self.lib.krr_wfpt_get_launch_times(self.h, st, ms, capacity), "get_launch_times")
+        return [(self.STAGES[st[i]], ms[i]) for i in range(min(n, capacity))]
 
     def _npix(self):
         return (self.rows[1] - self.rows[0]) * self.size[0]

@@ -19,7 +19,11 @@ OBJ = os.path.join(LIB, "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda",
+# -prec-div/-prec-sqrt=false: `/` and sqrtf() compile to the 2-ulp / 1-ulp fast sequences (the reference
+# itself builds its device code with --use_fast_math, CMakeLists.txt:113).  Everything that is compared
+# BIT-FOR-BIT with the oracle (sampler, wavelengths, camera rays, ray/triangle test) is written with the
+# explicitly rounded intrinsics of krr_math.cuh (__fdiv_rn, __fsqrt_rn, ...), which these flags do not touch.
+NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda", "-prec-div=false", "-prec-sqrt=false",
                   "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v",
                   "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
 CU_SRCS = ["api.cu", "bvh_build.cu"]
@@ -52,9 +56,28 @@ def deps(dirs):
     return out
 
 
+def build_variant(name, extra_flags):
+    """Tuning aid: builds kiraray_b200/lib/libkrr_wfpt_<name>.so with extra nvcc flags (e.g. -DKRR_...=..).
+    Select it at run time with KRR_WFPT_LIB=<path> (kiraray_b200/binding.py)."""
+    obj = os.path.join(OBJ, name)
+    os.makedirs(obj, exist_ok=True)
+
+    def cu(src):
+        o = os.path.join(obj, src.replace(".cu", ".o"))
+        run([NVCC] + NVFLAGS + list(extra_flags) + ["-c", os.path.join(HERE, "csrc", src), "-o", o], log=os.path.join(obj, src + ".ptxas.log"))
+        return o
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(cu, CU_SRCS))
+    out = os.path.join(LIB, f"libkrr_wfpt_{name}.so")
+    run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o", out] + objs)
+    return out
+
+
 def build(force=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = deps([os.path.join(HERE, "csrc"), os.path.join(HERE, "host"), os.path.join(ROOT, "include")])
+    hdrs.append(os.path.abspath(__file__))
 
     def cu(src):
         s = os.path.join(HERE, "csrc", src)
@@ -85,5 +108,8 @@ def build(force=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
-    print("built", LIB)
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":
+        print("built", build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force="--force" in sys.argv)
+        print("built", LIB)

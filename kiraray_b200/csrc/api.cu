@@ -85,6 +85,7 @@ struct KrrWfpt {
 	int spp = 1, maxDepth = 10;
 	float probRR = 0.8f, clampMax = 1e3f;
 	bool nee = true, enableMedium = true, enableClamp = false;
+	bool rrInTrace = true; // "rr_in_trace": internal scheduling switch (not a reference parameter), see Params::rrInTrace
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
 	bool haveScene = false, haveColorSpace = false, frameBegun = false;
 	uint64_t frameIndex = 0;
@@ -157,6 +158,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->enableClamp	= j.value("enable_clamp", h->enableClamp);
 		h->clampMax		= j.value("clamp_max", h->clampMax);
 		h->spp			= j.value("spp", h->spp);
+		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
@@ -213,6 +215,7 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 	wf.p.spp = h->spp, wf.p.maxDepth = h->maxDepth, wf.p.nee = h->nee;
 	wf.p.enableMedium = h->enableMedium && h->sceneHasMedia; // integrator.cpp:200
 	wf.p.enableClamp = h->enableClamp, wf.p.probRR = h->probRR, wf.p.clampMax = h->clampMax;
+	wf.p.rrInTrace	 = h->rrInTrace && !wf.p.enableMedium; // with media the medium stage draws before the scatter stage
 	uint32_t seedIndex = (uint32_t) (h->frameIndex * (uint64_t) h->spp);
 	wf.p.rngInc		 = ((uint64_t) seedIndex << 1u) | 1u;
 	wf.p.sampleIndex = (uint32_t) sampleId;
@@ -699,6 +702,21 @@ extern "C" int krr_wfpt_get_stage_times(KrrWfpt *h, double *ms, int32_t *launche
 	}
 	if (reset) { h->evRecs.clear(); h->evUsed = 0; }
 	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_get_launch_times(KrrWfpt *h, int32_t *stage, float *ms, int32_t capacity) {
+	if (!h || !stage || !ms) return fail(KRR_E_INVALID, "null argument");
+	if (!h->evRecs.empty()) CUDA_OK(cudaEventSynchronize(h->evRecs.back().b));
+	int n = 0;
+	for (auto &r : h->evRecs) {
+		if (n < capacity) {
+			float t = 0;
+			CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+			stage[n] = r.stage, ms[n] = t;
+		}
+		n++;
+	}
+	return n;
 }
 
 extern "C" int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *inst, int32_t *prim) {

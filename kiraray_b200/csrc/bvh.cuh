@@ -141,33 +141,35 @@ template <bool ANY> struct Traverser {
 		return lstack[sp - kShortStack];
 	}
 
-	// One trip.  Returns false when the ray is finished (result in `best`).
-	// Accept(inst, prim, u, v) -> bool: any-hit program (alpha kill, null-material skip).
-	template <typename Accept>
-	KRR_DEV bool step(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
-		// ---- next entry ----
-		if (cur == kEmptyEntry) {
+	// What the lane has to do next: 0 = ray finished (result in `best`), 1 = enter an instance,
+	// 2 = wide node, 3 = leaf.  Pops the stack when the current entry is consumed.
+	enum { FINISHED = 0, ENTER = 1, NODE = 2, LEAF = 3 };
+	KRR_DEV int next(TraceSmem &sm) {
+		while (cur == kEmptyEntry) {
 			if (curInst >= 0 && sp == blasBase) { // BLAS finished: back to world space
 				curInst = -1;
 				ro = o, rd = d;
 				setIdir();
 			}
-			if (sp == 0) return false;
+			if (sp == 0) return FINISHED;
 			float tn = 0.f;
 			cur = pop(sm, tn);
 			if (!ANY && tn > best.t) cur = kEmptyEntry; // box entry beyond the closest hit so far
 		}
-		// ---- phase 1: enter an instance ----
-		if (cur != kEmptyEntry && (cur & kInstFlag)) {
-			curInst = (int) (cur & 0x3fffffffu);
-			const InstRec &in = instances[curInst];
-			ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
-			setIdir();
-			blasBase = sp;
-			cur		 = (uint32_t) in.blasRoot;
-		}
-		// ---- phase 2: wide node ----
-		if (cur < kLeafFlag) {
+		return cur < kLeafFlag ? NODE : ((cur & kInstFlag) ? ENTER : LEAF);
+	}
+	// ---- phase 1: enter an instance (object-space ray; t stays the world parameter) ----
+	KRR_DEV void enterInstance(const InstRec *__restrict__ instances, TraceSmem &sm) {
+		curInst = (int) (cur & 0x3fffffffu);
+		const InstRec &in = instances[curInst];
+		ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
+		setIdir();
+		blasBase = sp;
+		cur		 = (uint32_t) in.blasRoot;
+	}
+	// ---- phase 2: wide node: 8 slab tests, sort by entry distance, push far-to-near ----
+	KRR_DEV void node(const BvhDev &bvh, TraceSmem &sm) {
+		{
 			const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + cur);
 			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 			uint32_t ew = __float_as_uint(n0.w);
@@ -229,26 +231,61 @@ template <bool ANY> struct Traverser {
 			if (k1 != kEmptyEntry) push(sm, entryOf(k1), __uint_as_float(k1 & ~7u));
 			cur = k0 != kEmptyEntry ? entryOf(k0) : kEmptyEntry;
 		}
-		// ---- phase 3: leaf (1..7 triangles) ----
-		if (cur != kEmptyEntry && (cur >> 30) == 1u) {
-			const uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
-			cur = kEmptyEntry;
-			for (uint32_t k = 0; k < cnt; k++) {
-				const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
-				float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-				float t, u, v;
-				if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
-					int prim = __float_as_int(a.w);
-					if (betterHit(t, curInst, prim, best) && accept(curInst, prim, u, v)) {
-						best.inst = curInst, best.prim = prim, best.t = t, best.u = u, best.v = v;
-						if (ANY) return false;
-					}
+	}
+	// ---- phase 3: leaf (1..7 triangles).  Returns true when an any-hit ray terminated. ----
+	template <typename Accept> KRR_DEV bool leaf(const BvhDev &bvh, Accept accept) {
+		const uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
+		cur = kEmptyEntry;
+		for (uint32_t k = 0; k < cnt; k++) {
+			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
+			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			float t, u, v;
+			if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
+				int prim = __float_as_int(a.w);
+				if (betterHit(t, curInst, prim, best) && accept(curInst, prim, u, v)) {
+					best.inst = curInst, best.prim = prim, best.t = t, best.u = u, best.v = v;
+					if (ANY) return true;
 				}
 			}
 		}
-		return true;
+		return false;
+	}
+
+	// One warp-cooperative trip: lanes vote on the phase to run, so that a phase executes with as many
+	// lanes as possible; lanes whose phase lost the vote keep their entry and wait (they would have been
+	// masked off anyway).  Returns true for lanes whose ray finished during this trip.
+	// VOTE = false runs both phases every trip (a lane may test a node and then its nearest leaf in
+	// the same trip): fewer trips per ray, which wins for the short any-hit traversals of shadow rays.
+	template <bool VOTE, typename Accept>
+	KRR_DEV bool trip(bool active, const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
+		const unsigned FULL = 0xffffffffu;
+		int st = FINISHED;
+		bool fin = false;
+		if (active) {
+			st	= next(sm);
+			fin = st == FINISHED;
+		}
+		if (__any_sync(FULL, st == ENTER)) {
+			if (st == ENTER) { enterInstance(instances, sm); st = NODE; }
+		}
+		if (VOTE) {
+			const unsigned mN = __ballot_sync(FULL, st == NODE), mL = __ballot_sync(FULL, st == LEAF);
+			if (mN && __popc(mN) >= __popc(mL)) {
+				if (st == NODE) node(bvh, sm);
+			} else if (mL) {
+				if (st == LEAF) fin = leaf(bvh, accept);
+			}
+		} else {
+			if (st == NODE) {
+				node(bvh, sm);
+				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
+			}
+			if (st == LEAF) fin = leaf(bvh, accept);
+		}
+		return fin;
 	}
 };
+
 #endif // __CUDACC__
 
 } // namespace krr

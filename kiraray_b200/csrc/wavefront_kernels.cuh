@@ -44,7 +44,8 @@ struct DepthCounters {	// one block per loop depth; 16 ints = 64 B
 	int32_t nShadow;
 	int32_t nMediumSample, nMediumScatter;
 	int32_t cursorRay, cursorShadow; // work cursors of the persistent trace kernels (next unclaimed item)
-	int32_t pad[3];
+	int32_t nScatterKilled;			 // scatter items terminated by Russian roulette in the closest stage (rrInTrace)
+	int32_t pad[2];
 };
 static_assert(sizeof(DepthCounters) == 64, "DepthCounters");
 
@@ -75,6 +76,10 @@ struct Params {
 	int32_t width, height;
 	int32_t pixelBegin, pixelCount; // this handle's pixel range (row partition)
 	int32_t spp, maxDepth, nee, enableMedium, enableClamp;
+	// Russian roulette of generateScatterRays (integrator.cpp:118-119) evaluated by the closest stage
+	// when it routes a hit to the scatter queue: it is the NEXT draw of the pixel's stream either way,
+	// so films are identical; terminated paths never occupy a lane of the scatter kernel
+	int32_t rrInTrace;
 	float probRR, clampMax;
 	uint64_t rngInc; // PCG increment of this frame
 	uint32_t sampleIndex;
@@ -242,6 +247,44 @@ __device__ __noinline__ bool alphaKilled(const Wavefront &wf, int inst, int prim
 // through the phase-aligned traversal (bvh.cuh), finalises the lanes whose ray terminated and
 // refills them as soon as kRefill lanes are idle -- SIMT lanes do not wait for the slowest ray.
 constexpr int kRefill = 8;
+constexpr int kClaim  = 64; // rays a warp claims from the queue per atomicAdd once its static share is done
+
+// Work distribution of the persistent trace kernels.  Warp w starts with the static slice
+// [32 w, 32 w + 32) of the queue -- no atomic, and warps beyond a short queue exit at once -- and
+// afterwards claims kClaim items at a time from the shared cursor (which counts from 32 * #warps).
+struct WarpWork {
+	int next, end;	// private range still to hand out
+	int n, first;	// queue size, first dynamically claimed index
+	int32_t *cursor;
+	bool exhausted; // warp-uniform
+	int claim;
+	// per: items a warp starts with (one per lane); claim_: items per later atomic claim
+	KRR_DEV void init(int n_, int32_t *cursor_, int per = 32, int claim_ = kClaim) {
+		const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+		n = n_, cursor = cursor_, first = nWarps * per, claim = claim_;
+		next = warp * per, end = min(next + per, n_);
+		exhausted = false;
+	}
+	// hands one item to every lane of `idle` (lane order); -1 when the queue is exhausted
+	KRR_DEV int take(unsigned idle, int lane) {
+		const unsigned FULL = 0xffffffffu;
+		const int want = __popc(idle);
+		if (next >= end && !exhausted) { // private range used up: claim the next batch
+			int base = n;
+			if (first < n) { // (short queues are covered by the static slices alone: no atomic at all)
+				if (lane == 0) base = first + atomicAdd(cursor, claim);
+				base = __shfl_sync(FULL, base, 0);
+			}
+			next = base, end = min(base + claim, n);
+			if (base >= n) exhausted = true, next = end = 0;
+		}
+		const int rank = __popc(idle & ((1u << lane) - 1));
+		int r = -1;
+		if ((idle >> lane) & 1) { r = next + rank; if (r >= end) r = -1; }
+		next = min(next + want, end);
+		return r;
+	}
+};
 
 // null-material hit: re-queue the ray behind the surface at the same item depth (device.cu:54-58)
 __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4) {
@@ -280,40 +323,35 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
 	Traverser<false> tr;
-	int ray		   = -1;	// queue slot this lane is tracing, -1 = idle
-	bool exhausted = false; // warp-uniform: the queue has no unclaimed rays left
+	int ray = -1; // queue slot this lane is tracing, -1 = idle
+	WarpWork work;
+	work.init(n, &dc->cursorRay);
+	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
 	float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
 	while (true) {
 		unsigned idle = __ballot_sync(FULL, ray < 0);
-		if (!exhausted && __popc(idle) >= kRefill) {
-			const int cnt = __popc(idle);
-			int base	  = 0;
-			if (lane == 0) base = atomicAdd(&dc->cursorRay, cnt);
-			base = __shfl_sync(FULL, base, 0);
-			if (ray < 0) {
-				int r = base + __popc(idle & ((1u << lane) - 1));
-				if (r < n) {
-					ray = r;
-					o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
-					tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf);
-				}
+		if (!work.exhausted && __popc(idle) >= kRefill) {
+			int r = work.take(idle, lane);
+			if (r >= 0) {
+				ray = r;
+				o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
+				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf);
 			}
-			exhausted = base + cnt >= n;
-			idle	  = __ballot_sync(FULL, ray < 0);
+			idle = __ballot_sync(FULL, ray < 0);
 		}
-		if (idle == FULL) break;
-		bool fin = false;
-		if (ray >= 0) {
-			fin = !tr.step(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
-				if (!(wf.instFlags[inst] & 2)) return true;
-				return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
-			});
+		if (idle == FULL) {
+			if (work.exhausted) break;
+			continue; // private range ran dry mid-refill: claim again
 		}
+		const bool fin = tr.trip<true>(ray >= 0, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+			if (!(wf.instFlags[inst] & 2)) return true;
+			return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
+		});
 		if (!__ballot_sync(FULL, fin)) continue;
 		// ---- finalise the lanes whose ray terminated (whole warp converged here) ----
 		int route	= -1; // 0 miss, 1 scatter(+light), 2 null-material pass-through
 		int matType = 0;
-		bool light	= false;
+		bool light	= false, alive = true;
 		const Hit h = tr.best;
 		const int i = ray;
 		if (fin) {
@@ -334,6 +372,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 					light	= in.lightBase >= 0;
 				}
 			}
+			if (route == 1 && wf.p.rrInTrace && depth < wf.p.maxDepth) { // no scatter stage (hence no draw) at the last depth
+				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
+				Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+				alive		   = rng.get1D() < wf.p.probRR;
+				wf.px.rng[pix] = rng.state;
+			}
 			ray = -1;
 		}
 		// (media: rays inside a medium are routed to the medium-sample queue by the media build)
@@ -344,9 +388,11 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 		if (s >= 0) wf.hitLightIdx[s] = i;
 #pragma unroll
 		for (int mt = 0; mt < MAT_COUNT; mt++) {
-			s = warpPushFull(&dc->nScatter[mt], route == 1 && matType == mt);
+			s = warpPushFull(&dc->nScatter[mt], route == 1 && alive && matType == mt);
 			if (s >= 0) wf.scatterIdx[mt][s] = i;
 		}
+		unsigned killed = __ballot_sync(FULL, route == 1 && !alive);
+		if (killed && lane == 0) atomicAdd(&dc->nScatterKilled, __popc(killed));
 		s = warpPushFull(&dc[1].nRay, route == 2);
 		if (s >= 0) requeueThroughNull(wf, q, nq, i, s, h, o4, d4);
 	}
@@ -546,8 +592,11 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 
 // =================================================================================================
 // generateScatterRays (integrator.cpp:110-164), one launch per material type
+#ifndef KRR_SCATTER_MINB
+#define KRR_SCATTER_MINB 5
+#endif
 template <int MT>
-__global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
+__global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc = wf.counters + depth;
@@ -576,7 +625,7 @@ __global__ void __launch_bounds__(128) k_scatter(const __grid_constant__ Wavefro
 			time = o4.w, medium = __float_as_int(d4.w);
 			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
 			// Russian roulette at every depth, including 0 (integrator.cpp:118-119)
-			bool alive = rng.get1D() < wf.p.probRR;
+			bool alive = wf.p.rrInTrace ? true : rng.get1D() < wf.p.probRR;
 			if (alive) {
 				Spec thp = ldcs4(q.thp + i) / wf.p.probRR, pu = ldcs4(q.pu + i);
 				SurfaceGeom g;
@@ -681,39 +730,35 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	const int lane		= threadIdx.x & 31;
 	Traverser<true> tr;
 	int ray = -1, pix = 0;
-	bool exhausted = false;
+	WarpWork work;
+	work.init(n, &dc->cursorShadow);
+	if (work.next >= n) return;
 	while (true) {
 		unsigned idle = __ballot_sync(FULL, ray < 0);
-		if (!exhausted && __popc(idle) >= kRefill) {
-			const int cnt = __popc(idle);
-			int base	  = 0;
-			if (lane == 0) base = atomicAdd(&dc->cursorShadow, cnt);
-			base = __shfl_sync(FULL, base, 0);
-			if (ray < 0) {
-				int r = base + __popc(idle & ((1u << lane) - 1));
-				if (r < n) {
-					ray = r;
-					float4 o4 = ldcs4(wf.shadow.o_tmax + r), d4 = ldcs4(wf.shadow.d_pix + r);
-					pix = __float_as_int(d4.w);
-					tr.begin(wf.bvh, mk3(o4), mk3(d4), o4.w);
-				}
+		if (!work.exhausted && __popc(idle) >= kRefill) {
+			int r = work.take(idle, lane);
+			if (r >= 0) {
+				ray = r;
+				float4 o4 = ldcs4(wf.shadow.o_tmax + r), d4 = ldcs4(wf.shadow.d_pix + r);
+				pix = __float_as_int(d4.w);
+				tr.begin(wf.bvh, mk3(o4), mk3(d4), o4.w);
 			}
-			exhausted = base + cnt >= n;
-			idle	  = __ballot_sync(FULL, ray < 0);
+			idle = __ballot_sync(FULL, ray < 0);
 		}
-		if (idle == FULL) break;
-		if (ray >= 0) {
-			bool more = tr.step(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
-				uint8_t f = wf.instFlags[inst];
-				if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
-				if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
-				return true;
-			});
-			if (!more) {
-				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
-				if (tr.best.inst < 0) wf.px.L[pix] = ldcs4(wf.shadow.contrib + ray) + wf.px.L[pix];
-				ray = -1;
-			}
+		if (idle == FULL) {
+			if (work.exhausted) break;
+			continue;
+		}
+		const bool fin = tr.trip<false>(ray >= 0, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+			uint8_t f = wf.instFlags[inst];
+			if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
+			if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
+			return true;
+		});
+		if (fin) {
+			if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+			if (tr.best.inst < 0) wf.px.L[pix] = ldcs4(wf.shadow.contrib + ray) + wf.px.L[pix];
+			ray = -1;
 		}
 	}
 }
@@ -763,6 +808,7 @@ __global__ void k_fold_counters(DepthCounters *c, StatTotals *t, int nDepth, int
 	DepthCounters dc = c[d];
 	int sc = 0;
 	for (int k = 0; k < MAT_COUNT; k++) sc += dc.nScatter[k];
+	sc += dc.nScatterKilled;
 	atomicAdd(&t->closest, (unsigned long long) dc.nRay);
 	atomicAdd(&t->shadow, (unsigned long long) dc.nShadow);
 	atomicAdd(&t->scatter, (unsigned long long) sc);
@@ -809,6 +855,14 @@ __global__ void k_capture(const __grid_constant__ Wavefront wf, int depth, int q
 			while (kk >= dc->nScatter[mt]) kk -= dc->nScatter[mt], mt++;
 			int i = wf.scatterIdx[mt][kk];
 			fromRay(q, i);
+			// ScatterRayWorkItem carries the prepared interaction: report ITS BSDF type (shared.h:46-73)
+			SurfaceGeom g;
+			rebuildGeometry(wf, wf.hits[i], mk3(q.d_medium[i]), g);
+			Wavelengths wl = expandWavelengths(wf.px.lambda[r.x - wf.p.pixelBegin]);
+			ShadingData sd;
+			bool term;
+			evalMaterial(wf, g, wl, sd, term);
+			r.z = getBsdfType(sd);
 			r.w = mt;
 		} else if (queue == 4) {
 			r.x = wf.p.pixelBegin + __float_as_int(wf.shadow.d_pix[k].w), r.y = 0, r.z = 0;
