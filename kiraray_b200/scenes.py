@@ -1,0 +1,281 @@
+"""Synthetic scene descriptors (KrrSceneDesc) for the parity tests and the workload runs of
+BASELINE.json configs 3 and 5.  Input generation only: everything here produces
+the flat host arrays `krr_wfpt_set_scene` (and the CPU oracle) consume; no rendering logic.
+
+All randomness comes from numpy PCG64 seeded with KRR_DEFAULT_RND_SEED = 7272
+(reference src/core/config.in.h:19).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .binding import (F, I32, KrrInstanceDesc, KrrLightDesc, KrrMaterialDesc, KrrMediumDesc, KrrMeshDesc, KrrSceneDesc,
+                      KrrSRT)
+
+SEED = 7272
+IDENTITY = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(F))
+
+
+class SceneBuilder:
+    """Accumulates meshes / instances / materials / lights and builds a KrrSceneDesc whose pointers
+    stay valid as long as this object lives."""
+
+    def __init__(self):
+        self.meshes, self.instances, self.materials, self.lights, self.media = [], [], [], [], []
+        self.options = dict(animated=0, multilevel=0, motionblur=0, starttime=0.0, endtime=1.0)
+        self._keep = []
+
+    def add_material(self, diffuse=(0.7, 0.7, 0.7), specular=(0.0, 0.0, 0.0), roughness=1.0, bsdf_type=4, specular_transmission=0.0,
+                     ior=1.5, emissive=None, anisotropic=0.0):
+        """Disney by default, SpecularGlossiness shading model like an OBJ import (specular.a = 1 - roughness)."""
+        m = KrrMaterialDesc()
+        m.diffuse = (F * 4)(*diffuse, 1.0)
+        m.specular = (F * 4)(*specular, 1.0 - roughness)
+        m.specular_transmission, m.anisotropic, m.ior = specular_transmission, anisotropic, ior
+        m.bsdf_type, m.shading_model, m.color_space = bsdf_type, 1, 0
+        if emissive is not None:
+            m.textures[2].valid = 1
+            m.textures[2].value = (F * 4)(*emissive, 1.0)
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def add_mesh(self, positions, indices, normals=None, material=0, medium_inside=-1, medium_outside=-1):
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
+        n = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        self._keep += [p, i, n]
+        m = KrrMeshDesc()
+        m.positions, m.indices = _fp(p), i.ctypes.data_as(C.POINTER(I32))
+        if n is not None:
+            m.normals = _fp(n)
+        m.n_vertices, m.n_triangles, m.material = len(p), len(i), material
+        m.medium_inside, m.medium_outside = medium_inside, medium_outside
+        self.meshes.append(m)
+        return len(self.meshes) - 1
+
+    def add_instance(self, mesh, transform=IDENTITY, motion_keys=None):
+        """motion_keys: (K, 10) array of SRT keys (scale xyz, quaternion xyzw, translation xyz)."""
+        inst = KrrInstanceDesc()
+        inst.mesh = mesh
+        inst.transform = (F * 12)(*np.asarray(transform, np.float32).ravel())
+        if motion_keys is not None:
+            k = np.ascontiguousarray(motion_keys, np.float32).reshape(-1, 10)
+            self._keep.append(k)
+            inst.n_motion_keys = len(k)
+            inst.motion_keys = k.ctypes.data_as(C.POINTER(KrrSRT))
+        self.instances.append(inst)
+        return len(self.instances) - 1
+
+    def add_light(self, type_, color=(1, 1, 1), scale=1.0, transform=IDENTITY, scene_radius=10.0, inner=30.0, outer=45.0):
+        l = KrrLightDesc()
+        l.type, l.scale, l.scene_radius, l.inner_cone_deg, l.outer_cone_deg = type_, scale, scene_radius, inner, outer
+        l.color = (F * 3)(*color)
+        l.transform = (F * 12)(*np.asarray(transform, np.float32).ravel())
+        self.lights.append(l)
+        return len(self.lights) - 1
+
+    def add_medium(self, type_=0, sigma_t=(1, 1, 1), albedo=(0.8, 0.8, 0.8), Le=(0, 0, 0), g=0.0, transform=IDENTITY,
+                   bounds=((0, 0, 0), (1, 1, 1)), density=None, scale=1.0):
+        m = KrrMediumDesc()
+        m.type, m.g, m.scale = type_, g, scale
+        m.sigma_t, m.albedo, m.Le = (F * 3)(*sigma_t), (F * 3)(*albedo), (F * 3)(*Le)
+        m.transform = (F * 12)(*np.asarray(transform, np.float32).ravel())
+        m.bounds_min, m.bounds_max = (F * 3)(*bounds[0]), (F * 3)(*bounds[1])
+        if density is not None:
+            d = np.ascontiguousarray(density, np.float32)  # indexed [z][y][x]
+            self._keep.append(d)
+            m.res = (I32 * 3)(d.shape[2], d.shape[1], d.shape[0])
+            m.density = _fp(d)
+        self.media.append(m)
+        return len(self.media) - 1
+
+    def build(self):
+        d = KrrSceneDesc()
+
+        def arr(items, typ):
+            a = (typ * max(len(items), 1))(*items)
+            self._keep.append(a)
+            return a
+
+        d.meshes, d.n_meshes = arr(self.meshes, KrrMeshDesc), len(self.meshes)
+        d.instances, d.n_instances = arr(self.instances, KrrInstanceDesc), len(self.instances)
+        d.materials, d.n_materials = arr(self.materials, KrrMaterialDesc), len(self.materials)
+        d.lights, d.n_lights = arr(self.lights, KrrLightDesc), len(self.lights)
+        d.media, d.n_media = arr(self.media, KrrMediumDesc), len(self.media)
+        for k, v in self.options.items():
+            setattr(d.options, k, v)
+        self.desc = d
+        return C.pointer(d)
+
+    def triangle_count(self):
+        return sum(self.meshes[i.mesh].n_triangles for i in self.instances)
+
+
+# ---------------------------------------------------------------------------------------------------
+def translation(t, s=1.0):
+    m = IDENTITY.copy()
+    m[[0, 5, 10]] = s
+    m[[3, 7, 11]] = t
+    return m
+
+
+def quat_to_mat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def srt_to_mat(k):
+    """T * R * S of one SRT key (s[3], q[4] = xyzw, t[3]) as 12 floats -- the pass interpolates keys
+    the same way (scale and translation linearly, quaternion nlerp)."""
+    k = np.asarray(k, np.float64)
+    m = quat_to_mat(k[3:7] / np.linalg.norm(k[3:7])) * k[0:3][None, :]
+    return np.concatenate([m, k[7:10][:, None]], 1).astype(np.float32).ravel()
+
+
+def displaced_sphere(nu, nv, rng, amplitude=0.15):
+    """Closed lat-long sphere of 2*nu*(nv-1) triangles with smooth radial noise (a few random
+    low-frequency harmonics); returns positions, normals (from the displaced surface), indices."""
+    u = np.arange(nu) / nu * 2 * np.pi
+    v = (np.arange(1, nv)) / nv * np.pi
+    uu, vv = np.meshgrid(u, v, indexing="xy")  # (nv-1, nu)
+    d = np.stack([np.sin(vv) * np.cos(uu), np.cos(vv), np.sin(vv) * np.sin(uu)], -1).reshape(-1, 3)
+    d = np.concatenate([d, [[0, 1, 0], [0, -1, 0]]])
+    r = np.ones(len(d))
+    for _ in range(6):
+        f = rng.normal(size=3) * 3
+        r += amplitude / 6 * np.sin(d @ f + rng.uniform(0, 6.28)) * rng.uniform(0.5, 1.5)
+    p = d * r[:, None]
+    top, bot = len(d) - 2, len(d) - 1
+    idx = []
+    rows = nv - 1
+    i0 = (np.arange(rows - 1)[:, None] * nu + np.arange(nu)[None, :])
+    i1 = (np.arange(rows - 1)[:, None] * nu + (np.arange(nu)[None, :] + 1) % nu)
+    idx.append(np.stack([i0, i1, i0 + nu], -1).reshape(-1, 3))
+    idx.append(np.stack([i1, i1 + nu, i0 + nu], -1).reshape(-1, 3))
+    a = np.arange(nu)
+    idx.append(np.stack([np.full(nu, top), (a + 1) % nu, a], -1))
+    last = (rows - 1) * nu
+    idx.append(np.stack([np.full(nu, bot), last + a, last + (a + 1) % nu], -1))
+    idx = np.concatenate(idx).astype(np.int32)
+    # vertex normals: area-weighted face normals
+    fn = np.cross(p[idx[:, 1]] - p[idx[:, 0]], p[idx[:, 2]] - p[idx[:, 0]])
+    n = np.zeros_like(p)
+    for c in range(3):
+        np.add.at(n, idx[:, c], fn)
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-20)
+    flip = np.einsum("ij,ij->i", n, d) < 0
+    n[flip] *= -1
+    return p.astype(np.float32), n.astype(np.float32), idx
+
+
+def quad(p0, e1, e2):
+    p0, e1, e2 = (np.asarray(a, np.float32) for a in (p0, e1, e2))
+    p = np.stack([p0, p0 + e1, p0 + e1 + e2, p0 + e2])
+    n = np.cross(e1, e2)
+    n = np.tile(n / np.linalg.norm(n), (4, 1))
+    return p, n.astype(np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+
+
+def tessellated_scene(n_objects=200, tris_per_object=100_000, n_emissive=1000, seed=SEED):
+    """BASELINE.json config 3: a unit-cube arrangement of tessellated displaced spheres with Disney
+    materials (roughness ~ U(0.05,1), metallic p=.2, specular transmission p=.1, base colour U(.1,.9)^3),
+    a floor, and `n_emissive` emissive triangles (Le = 17,12,4) on a ceiling grid."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    b = SceneBuilder()
+    nv = max(4, int(round(np.sqrt(tris_per_object / 4))))
+    nu = max(3, int(round(tris_per_object / (2 * (nv - 1)))))
+    grid = int(np.ceil(n_objects ** (1 / 3)))
+    cell = 2.0 / grid
+    for o in range(n_objects):
+        metallic, trans = rng.random() < 0.2, rng.random() < 0.1
+        base = rng.uniform(0.1, 0.9, 3)
+        # SpecularGlossiness: a metal is a coloured specular with black diffuse (getMetallic, shading.h:17-30)
+        mat = b.add_material(diffuse=(0.02, 0.02, 0.02) if metallic else base, specular=base if metallic else (0.04, 0.04, 0.04),
+                             roughness=rng.uniform(0.05, 1.0), specular_transmission=1.0 if trans else 0.0)
+        p, n, idx = displaced_sphere(nu, nv, rng)
+        mesh = b.add_mesh(p, idx, n, mat)
+        c = np.array([o % grid, (o // grid) % grid, o // (grid * grid)]) * cell - 1 + cell / 2 + rng.uniform(-0.1, 0.1, 3) * cell
+        b.add_instance(mesh, translation(c, 0.42 * cell))
+    floor = b.add_material(diffuse=(0.6, 0.6, 0.6), roughness=0.9)
+    p, n, idx = quad((-3, -1.05, -3), (0, 0, 6), (6, 0, 0))
+    b.add_instance(b.add_mesh(p, idx, n, floor))
+    light = b.add_material(diffuse=(0, 0, 0), emissive=(17, 12, 4))
+    k = int(np.ceil(np.sqrt(n_emissive / 2)))
+    ps, ns, ids = [], [], []
+    for q in range((n_emissive + 1) // 2):
+        x, z = (q % k) / k * 4 - 2, (q // k) / k * 4 - 2
+        p, n, idx = quad((x, 1.6, z), (0.5 * 4 / k, 0, 0), (0, 0, 0.5 * 4 / k))  # normal points down (-y)
+        ids.append(idx + 4 * q), ps.append(p), ns.append(n)
+    b.add_instance(b.add_mesh(np.concatenate(ps), np.concatenate(ids)[:n_emissive], np.concatenate(ns), light))
+    return b
+
+
+def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100, motion=True, seed=SEED, n_keys=2):
+    """BASELINE.json config 5: `n_groups * per_group` instances of `n_blas` BLASes arranged as a two-level
+    graph (group transform x instance transform, flattened to world transforms as the reference's scene
+    graph update does), every instance with a `n_keys`-key SRT motion (group motion composed with its
+    own), a floor and an emissive ceiling quad.  Returns (builder, keys) where keys[i] is the (K, 10)
+    SRT key array of instance i (static transform = key 0)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    b = SceneBuilder()
+    nv = max(4, int(round(np.sqrt(tris_per_blas / 4))))
+    nu = max(3, int(round(tris_per_blas / (2 * (nv - 1)))))
+    meshes = []
+    for m in range(n_blas):
+        mat = b.add_material(diffuse=rng.uniform(0.1, 0.9, 3), roughness=rng.uniform(0.2, 1.0))
+        p, n, idx = displaced_sphere(nu, nv, rng, amplitude=0.3)
+        meshes.append(b.add_mesh(p, idx, n, mat))
+    g = int(np.ceil(np.sqrt(n_groups)))
+    s = int(np.ceil(per_group ** (1 / 3)))
+    all_keys = []
+    for gi in range(n_groups):
+        gc = np.array([(gi % g) / g * 8 - 4, 0.0, (gi // g) / g * 8 - 4])
+        gvel = rng.normal(size=3) * 0.15
+        for ii in range(per_group):
+            lc = np.array([ii % s, (ii // s) % s, ii // (s * s)]) / s * (8 / g) * 0.9
+            scale = (8 / g) / s * 0.35 * rng.uniform(0.7, 1.0)
+            q0 = rng.normal(size=4)
+            q0 /= np.linalg.norm(q0)
+            dq = rng.normal(size=4) * 0.15
+            vel = gvel + rng.normal(size=3) * 0.05
+            keys = []
+            for k in range(n_keys):
+                a = k / max(n_keys - 1, 1)
+                q = q0 + a * dq
+                keys.append(np.concatenate([[scale] * 3, q / np.linalg.norm(q), gc + lc + a * vel]))
+            keys = np.array(keys, np.float32)
+            all_keys.append(keys)
+            b.add_instance(meshes[(gi * per_group + ii) % n_blas], srt_to_mat(keys[0]), keys if motion else None)
+    floor = b.add_material(diffuse=(0.6, 0.6, 0.6), roughness=0.9)
+    p, n, idx = quad((-6, -0.6, -6), (0, 0, 12), (12, 0, 0))
+    b.add_instance(b.add_mesh(p, idx, n, floor))
+    light = b.add_material(diffuse=(0, 0, 0), emissive=(17, 12, 4))
+    p, n, idx = quad((-3, 4.0, -3), (6, 0, 0), (0, 0, 6))
+    b.add_instance(b.add_mesh(p, idx, n, light))
+    if motion:
+        b.options.update(motionblur=1, starttime=0.0, endtime=1.0)
+    return b, all_keys
+
+
+def look_at_camera(eye, target, aspect, focal_length=21.0, up=(0, 1, 0), shutter_open=0.0, shutter_time=0.0, lens_radius=0.0, focal_distance=10.0):
+    """rt::CameraData (reference src/core/camera.h:20-30): 24 mm film height, camera looks down -z."""
+    from .binding import KrrCameraData
+    eye, target, up = (np.asarray(a, np.float64) for a in (eye, target, up))
+    f = target - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, up)
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    m = np.concatenate([np.stack([r, u, -f], 1), eye[:, None]], 1).astype(np.float32).ravel()
+    cam = KrrCameraData()
+    cam.film_size = (F * 2)(24.0 * aspect, 24.0)
+    cam.focal_length, cam.focal_distance, cam.lens_radius, cam.aspect_ratio = focal_length, focal_distance, lens_radius, aspect
+    cam.shutter_open, cam.shutter_time, cam.medium = shutter_open, shutter_time, -1
+    cam.transform = (F * 12)(*m)
+    return cam

@@ -33,6 +33,32 @@ def to_us(v, unit):
     return {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(unit, v)
 
 
+def traffic(out, *reps):
+    """profiles/traffic.json: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over
+    the captured launches) of each kernel in the given `ncu --set full` reports; bench.py reads it."""
+    import json
+    import re
+    res = {}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for rep in reps:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            name = re.sub(r"^(void )?(krr::)?", "", d["Kernel Name"]).split("<")[0].split("(")[0]
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(d[k].replace(",", "")) * mult[units[hdr.index(k)]]
+            e = res.setdefault(name, {"launches": 0, "bytes": 0.0, "source": rep.split("/")[-1]})
+            e["launches"] += 1
+            e["bytes"] += tot
+    out_d = {k: {"dram_bytes_per_launch": v["bytes"] / v["launches"], "launches_captured": v["launches"], "source": v["source"],
+                 "note": "first launches of the stage (depth 0/1) of the bench workload; ncu replays run cold-cache"} for k, v in res.items()}
+    json.dump(out_d, open(out, "w"), indent=1)
+    print(json.dumps(out_d, indent=1))
+
+
 def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.OrderedDict()
@@ -66,4 +92,4 @@ def report(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
