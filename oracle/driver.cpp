@@ -129,6 +129,17 @@ struct LightRef {
 	int analytic;	/* index into Scene::analytic */
 };
 struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
+/* HomogeneousMedium / dense-grid stand-in for NanoVDBMedium<float> (src/render/media.h:108-227) */
+struct MediumData {
+	int type;
+	float sigma_t[3], albedo[3], Le[3], g;
+	Xf xf, inv;
+	float bmin[3], bmax[3];
+	int res[3];
+	std::vector<float> density;
+	float scale;
+	std::vector<float> majorant; /* 64^3 max-density grid, media.cpp:18-75 */
+};
 
 } // namespace
 
@@ -139,6 +150,7 @@ struct OrcScene {
 	std::vector<LightRef> lights;
 	std::vector<OlLight> analytic;
 	std::vector<int> infinite; /* indices into analytic */
+	std::vector<MediumData> media;
 	/* flattened world-independent primitive list for the BVH: (instance, prim) in object space */
 	struct Prim { int inst, prim; };
 	std::vector<Prim> prims;
@@ -323,6 +335,8 @@ struct SurfIntr {
 	int material; /* -1 = null */
 	int light;	  /* index into Scene::lights or -1 */
 	int inst, prim;
+	int medium; /* intr.medium = ray.medium, shading.h:126 */
+	int mesh;
 	OlShading sd;
 };
 
@@ -340,7 +354,8 @@ void prepareInteraction(const OrcScene &s, const Hit &h, V3 rayDir, float rayTim
 	const Mesh &m	   = s.meshes[in.mesh];
 	float b[3]		   = {1 - h.u - h.v, h.u, h.v}; /* getHitInfo, shading.h:85 */
 	const int32_t *v   = &m.I[3 * h.prim];
-	it.inst = h.inst, it.prim = h.prim;
+	it.inst = h.inst, it.prim = h.prim, it.mesh = in.mesh;
+	it.medium = -1;
 	it.time = rayTime;
 	it.wo	= normalize(-normalize(rayDir)); /* hitInfo.wo = -normalize(dir); intr.wo = normalize(hitInfo.wo) */
 	V3 p0 = m.P[v[0]], p1 = m.P[v[1]], p2 = m.P[v[2]];
@@ -475,8 +490,172 @@ void fillTri(const OrcScene &s, const LightRef &lr, OlTriLight &tl) {
 	tl.twoSided = 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Participating media.  HomogeneousMedium::samplePoint, MajorantIterator (DDA) and the HG phase
+ * function run through the leaf API (= the reference's own classes in the reference backend); the
+ * dense density grid (stand-in for NanoVDBMedium<float>: this build's scenes carry a dense float array
+ * instead of a .vdb file), its 64^3 majorant grid and the tracking loops are restated here.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int kMajRes = 64; /* majorantGridRes, media.h:223 */
+
+/* NanoVDBGrid<float>::getValue (util/volume.h:83-87): worldToIndexF + SampleFromVoxels<Tree, 1, false>
+ * = trilinear interpolation of the voxel lattice, background value 0 outside the grid */
+float gridDensity(const MediumData &m, V3 p) {
+	float idx[3], w[3];
+	int i0[3];
+	for (int k = 0; k < 3; k++) {
+		idx[k] = (p[k] - m.bmin[k]) / (m.bmax[k] - m.bmin[k]) * m.res[k];
+		float f = std::floor(idx[k]);
+		i0[k] = (int) f, w[k] = idx[k] - f;
+	}
+	auto at = [&](int x, int y, int z) -> float {
+		if (x < 0 || y < 0 || z < 0 || x >= m.res[0] || y >= m.res[1] || z >= m.res[2]) return 0.f;
+		return m.density[x + (size_t) m.res[0] * (y + (size_t) m.res[1] * z)];
+	};
+	auto lerp = [](float a, float b, float t) { return a + t * (b - a); }; /* nanovdb TrilinearSampler */
+	float c00 = lerp(at(i0[0], i0[1], i0[2]), at(i0[0] + 1, i0[1], i0[2]), w[0]);
+	float c10 = lerp(at(i0[0], i0[1] + 1, i0[2]), at(i0[0] + 1, i0[1] + 1, i0[2]), w[0]);
+	float c01 = lerp(at(i0[0], i0[1], i0[2] + 1), at(i0[0] + 1, i0[1], i0[2] + 1), w[0]);
+	float c11 = lerp(at(i0[0], i0[1] + 1, i0[2] + 1), at(i0[0] + 1, i0[1] + 1, i0[2] + 1), w[0]);
+	return lerp(lerp(c00, c10, w[1]), lerp(c01, c11, w[1]), w[2]);
+}
+
+/* initializeMajorantGrid, media.cpp:18-75 (index bbox of a dense grid = [0, res-1]) */
+void buildMajorant(MediumData &m) {
+	m.majorant.assign((size_t) kMajRes * kMajRes * kMajRes, 0.f);
+	for (int z = 0; z < kMajRes; z++)
+		for (int y = 0; y < kMajRes; y++)
+			for (int x = 0; x < kMajRes; x++) {
+				int c[3] = {x, y, z}, n0[3], n1[3];
+				for (int k = 0; k < 3; k++) {
+					float ext = m.bmax[k] - m.bmin[k];
+					float w0 = m.bmin[k] + ext * (float(c[k]) / kMajRes), w1 = m.bmin[k] + ext * (float(c[k] + 1) / kMajRes);
+					float i0 = (w0 - m.bmin[k]) / ext * m.res[k], i1 = (w1 - m.bmin[k]) / ext * m.res[k];
+					n0[k] = std::max(int(i0 - 1.f), 0), n1[k] = std::min(int(i1 + 1.f), m.res[k] - 1);
+				}
+				float mx = 0;
+				for (int nz = n0[2]; nz <= n1[2]; nz++)
+					for (int ny = n0[1]; ny <= n1[1]; ny++)
+						for (int nx = n0[0]; nx <= n1[0]; nx++)
+							mx = std::max(mx, m.density[nx + (size_t) m.res[0] * (ny + (size_t) m.res[1] * nz)]);
+				m.majorant[x + kMajRes * (y + kMajRes * z)] = mx;
+			}
+}
+
+struct MediumPoint { Spec sigma_a, sigma_s, Le; };
+Spec fromRGB(const float rgb[3], int type, const float lambda[4]) {
+	Spec r;
+	ol_from_rgb(rgb, type, lambda, r.v);
+	return r;
+}
+/* Medium::samplePoint: HomogeneousMedium media.h:121-126, NanoVDBMedium<float> media.h:161-173 */
+MediumPoint mediumSamplePoint(const MediumData &m, V3 p, const float lambda[4]) {
+	MediumPoint mp;
+	if (m.type == KRR_MEDIUM_HOMOGENEOUS) {
+		ol_homogeneous_sample_point(m.sigma_t, m.albedo, m.Le, lambda, mp.sigma_a.v, mp.sigma_s.v, mp.Le.v);
+		return mp;
+	}
+	V3 pm = xfPoint(m.inv, p);
+	Spec sigma_t = fromRGB(m.sigma_t, 1, lambda) * (gridDensity(m, pm) * m.scale); /* density * scale * fromRGB(sigma_t) */
+	Spec sigma_s = sigma_t * fromRGB(m.albedo, 0, lambda);								/* albedo: RGBBounded */
+	for (int i = 0; i < 4; i++) mp.sigma_a.v[i] = sigma_t.v[i] - sigma_s.v[i];
+	mp.sigma_s = sigma_s, mp.Le = sconst(0); /* no temperature grid */
+	return mp;
+}
+
+struct Segment { float tMin, tMax; Spec sigma_maj; };
+/* Medium::sampleRay: media.h:128-132 (homogeneous), 175-187 (grid; AABB::intersect krrmath/aabb.h:58-76) */
+int mediumSampleRay(const MediumData &m, V3 o, V3 d, float raytMax, const float lambda[4], Segment *segs, int cap) {
+	float out[6 * 256];
+	int n;
+	if (m.type == KRR_MEDIUM_HOMOGENEOUS) {
+		Spec st = fromRGB(m.sigma_t, 1, lambda);
+		float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+		n = ol_majorant_segments(m.bmin, m.bmax, m.res, nullptr, oo, dd, 0.f, raytMax, st.v, out, 256);
+	} else {
+		V3 lo = xfPoint(m.inv, o), ld = xfVector(m.inv, d);
+		float t0 = 0, t1 = raytMax;
+		for (int i = 0; i < 3; i++) {
+			float inv = 1 / ld[i];
+			float tn = (m.bmin[i] - lo[i]) * inv, tf = (m.bmax[i] - lo[i]) * inv;
+			if (tn > tf) std::swap(tn, tf);
+			t0 = tn > t0 ? tn : t0;
+			t1 = tf < t1 ? tf : t1;
+			if (t0 > t1) return 0;
+		}
+		Spec st = fromRGB(m.sigma_t, 1, lambda) * m.scale;
+		int res[3] = {kMajRes, kMajRes, kMajRes};
+		float oo[3] = {lo.x, lo.y, lo.z}, dd[3] = {ld.x, ld.y, ld.z};
+		n = ol_majorant_segments(m.bmin, m.bmax, res, m.majorant.data(), oo, dd, t0, t1, st.v, out, 256);
+	}
+	n = std::min(n, std::min(cap, 256));
+	for (int i = 0; i < n; i++) {
+		segs[i].tMin = out[6 * i], segs[i].tMax = out[6 * i + 1];
+		memcpy(segs[i].sigma_maj.v, out + 6 * i + 2, 16);
+	}
+	return n;
+}
+
+inline Spec expNeg(Spec s, float dt) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = std::exp(-dt * s.v[i]); return r; }
+inline Spec operator-(Spec a, Spec b) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline Spec cwiseMax0(Spec a) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = std::max(a.v[i], 0.f); return r; }
+inline Spec operator/(Spec a, Spec b) { Spec r; for (int i = 0; i < 4; i++) r.v[i] = a.v[i] / b.v[i]; return r; }
+inline float maxCoeff(Spec a) { return std::max(std::max(a.v[0], a.v[1]), std::max(a.v[2], a.v[3])); }
+inline bool hasNaN(Spec a) { return a.v[0] != a.v[0] || a.v[1] != a.v[1] || a.v[2] != a.v[2] || a.v[3] != a.v[3]; }
+
+/* sampleT_maj, wavefront.h:34-78.  callback(p, mp, sigma_maj, T_maj) -> continue? */
+template <typename F>
+Spec sampleT_maj(const MediumData &m, V3 o, V3 d, float tMax, OlSampler *smp, const float lambda[4], F callback) {
+	tMax *= length(d);
+	d = normalize(d);
+	Spec T_maj = sconst(1);
+	Segment segs[256];
+	int nseg = mediumSampleRay(m, o, d, tMax, lambda, segs, 256);
+	const int channel = 0; /* lambda.mainIndex() in the spectral build, spectrum.h:76-81 */
+	for (int si = 0; si < nseg; si++) {
+		const Segment &seg = segs[si];
+		if (seg.sigma_maj.v[channel] == 0) {
+			float dt = seg.tMax - seg.tMin;
+			if (std::isinf(dt)) dt = std::numeric_limits<float>::max();
+			T_maj = T_maj * expNeg(seg.sigma_maj, dt);
+			continue;
+		}
+		float tMin = seg.tMin;
+		while (true) {
+			float t = tMin + (-std::log(1 - ol_pcg_get1d(smp)) / seg.sigma_maj.v[channel]); /* sampleExponential */
+			if (t < seg.tMax) {
+				T_maj = T_maj * expNeg(seg.sigma_maj, t - tMin);
+				V3 p = o + d * t;
+				MediumPoint mp = mediumSamplePoint(m, p, lambda);
+				if (!callback(p, mp, seg.sigma_maj, T_maj)) return sconst(1);
+				T_maj = sconst(1);
+				tMin  = t;
+			} else {
+				float dt = seg.tMax - tMin;
+				if (std::isinf(dt)) dt = std::numeric_limits<float>::max();
+				T_maj = T_maj * expNeg(seg.sigma_maj, dt);
+				break;
+			}
+		}
+	}
+	return T_maj;
+}
+
+/* sampleDiscrete({a, b, c}, u), render/sampling.h:90-105 */
+int sampleDiscrete3(float w0, float w1, float w2, float u) {
+	float weights[3] = {w0, w1, w2};
+	float sumWeights = 0;
+	for (float w : weights) sumWeights += w;
+	float up = u * sumWeights;
+	if (up == sumWeights) up = std::nextafter(up, -std::numeric_limits<float>::infinity()); /* nextFloatDown */
+	int offset = 0;
+	float sum  = 0;
+	while (offset < 2 && sum + weights[offset] <= up) sum += weights[offset++]; /* (the reference's loop is unbounded) */
+	return offset;
+}
+
 struct PathStats {
-	uint64_t camera = 0, closest = 0, shadow = 0, scatter = 0, hitLight = 0, miss = 0;
+	uint64_t camera = 0, closest = 0, shadow = 0, scatter = 0, hitLight = 0, miss = 0, mediumSample = 0, mediumScatter = 0;
 	uint64_t closestByDepth[KRR_MAX_DEPTH_STATS] = {0}, shadowByDepth[KRR_MAX_DEPTH_STATS] = {0};
 };
 
@@ -552,6 +731,20 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		s->lights.push_back(LightRef{ld.type, -1, -1, (int) s->analytic.size()});
 		s->analytic.push_back(l);
 	}
+	for (int i = 0; i < d->n_media; i++) {
+		const KrrMediumDesc &md = d->media[i];
+		MediumData m;
+		m.type = md.type, m.g = md.g, m.scale = md.scale;
+		memcpy(m.sigma_t, md.sigma_t, 12), memcpy(m.albedo, md.albedo, 12), memcpy(m.Le, md.Le, 12);
+		memcpy(m.xf.m, md.transform, 48);
+		m.inv = xfInverse(m.xf);
+		memcpy(m.bmin, md.bounds_min, 12), memcpy(m.bmax, md.bounds_max, 12), memcpy(m.res, md.res, 12);
+		if (md.type == KRR_MEDIUM_GRID) {
+			m.density.assign(md.density, md.density + (size_t) md.res[0] * md.res[1] * md.res[2]);
+			buildMajorant(m);
+		}
+		s->media.push_back(std::move(m));
+	}
 	for (int i = 0; i < (int) s->instances.size(); i++)
 		for (int t = 0; t < s->meshes[s->instances[i].mesh].ntri(); t++) s->bvhPrims.push_back({i, t});
 	if (!s->bvhPrims.empty()) buildBvh(*s, 0, (int) s->bvhPrims.size());
@@ -576,6 +769,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 	const int row0 = p->row_end > 0 ? p->row_begin : 0, row1 = p->row_end > 0 ? p->row_end : H;
 	const int nLights  = (int) s.lights.size();
 	const bool useBvh  = p->use_bvh != 0;
+	const bool enableMedium = p->enable_medium && !s.media.empty(); /* integrator.cpp:200 */
 	Capture cap{capSample, capDepth, capItems, capCounts};
 	if (capSample >= 0) for (int q = 0; q < 6; q++) capCounts[q] = 0;
 	int nthreads = p->threads > 0 ? p->threads : (int) std::max(1u, std::thread::hardware_concurrency());
@@ -614,10 +808,79 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 			st_.camera++;
 			/* RayWorkItem */
 			V3 rayO = mk(ro), rayD = mk(rd);
+			int rayMedium = enableMedium ? cam->medium : -1;
 			V3 ctxP = mk(0, 0, 0), ctxN = mk(0, 0, 0);
 			Spec thp = sconst(1), pu = sconst(1), pl = sconst(1);
 			int bsdfType = 0, depth = 0;
 			bool alive = true;
+			/* Interaction::getMedium(w), raytracing.h:162-166 */
+			auto getMedium = [&](const SurfIntr &it, V3 w) -> int {
+				const Mesh &m = s.meshes[it.mesh];
+				if (m.mediumIn != m.mediumOut) return dot(w, it.n) > 0 ? m.mediumOut : m.mediumIn;
+				return it.medium;
+			};
+			auto alphaAccept = [&](V3 o_, V3 d_) { return [&s, o_, d_](const Hit &c) { return !alphaKilled(s, c, o_, d_); }; };
+			/* one shadow item: [2.5] traceShadow -> "Shadow" (device.cu:83-100) or "ShadowTr" (device.cu:102-128) */
+			auto traceShadowItem = [&](V3 so, V3 sdir, int sMedium, Spec Ld, Spec spu, Spec spl, int loopDepth, bool capD, int auxLight) {
+				st_.shadow++;
+				if (loopDepth < KRR_MAX_DEPTH_STATS) st_.shadowByDepth[loopDepth]++;
+				if (capD) cap.push(4, pixelId, depth, 0, auxLight);
+				if (!enableMedium) {
+					Hit sh = traceClosest(s, useBvh, so, sdir, 1.f, [&](const Hit &c) {
+						/* __anyhit__Shadow: ignore null-material and alpha-killed hits */
+						if (s.meshes[s.instances[c.inst].mesh].material < 0) return false;
+						return !alphaKilled(s, c, so, sdir);
+					});
+					if (sh.inst < 0) L = (Ld / mean(spl + spu)) + L;
+					return;
+				}
+				/* traceTransmittance, wavefront.h:80-139 (ratio tracking + null-interface stepping) */
+				const V3 srO = so, srD = sdir; /* the work item's ray: CH(ShadowTr) prepares intr from IT (device.cu:102-109) */
+				V3 ro_ = so, rd_ = sdir;
+				int rmed = sMedium;
+				const float tMax = 1.f;
+				const V3 pLight = so + sdir * tMax;
+				Spec T_ray = sconst(1), tpu = sconst(1), tpl = sconst(1);
+				SurfIntr sit;
+				sit.material = -1; /* SurfaceInteraction intr = {} */
+				auto isZeroV = [](V3 v, float prec) { return std::fabs(v.x) <= prec && std::fabs(v.y) <= prec && std::fabs(v.z) <= prec; };
+				while (!isZeroV(rd_, 1e-4f * 2)) {
+					Hit sh = traceClosest(s, useBvh, ro_, rd_, tMax, alphaAccept(ro_, rd_));
+					bool visible = sh.inst < 0;
+					if (!visible) {
+						prepareInteraction(s, sh, srD, rtime, lambda, lpdf, sit);
+						sit.medium = sMedium;
+					}
+					if (!visible && sit.material >= 0) { T_ray = sconst(0); break; }
+					if (rmed >= 0) {
+						float tEnd = visible ? tMax : length(sit.p - ro_) / length(rd_);
+						Spec T_maj = sampleT_maj(s.media[rmed], ro_, rd_, tEnd, &smp, lambda,
+							[&](V3, MediumPoint mp, Spec sigma_maj, Spec T_maj_) -> bool {
+								Spec sigma_n = cwiseMax0(sigma_maj - mp.sigma_a - mp.sigma_s);
+								float pr = T_maj_.v[0] * sigma_maj.v[0];
+								T_ray = T_ray * T_maj_ * sigma_n / pr;
+								tpl	  = tpl * T_maj_ * sigma_maj / pr;
+								tpu	  = tpu * T_maj_ * sigma_n / pr;
+								Spec Tr = T_ray / mean(tpu + tpl);
+								if (maxCoeff(Tr) < 0.05f) {
+									if (ol_pcg_get1d(&smp) < 0.75f) T_ray = sconst(0);
+									else T_ray = T_ray / 0.25f;
+								}
+								return any(T_ray);
+							});
+						T_ray = T_ray * T_maj / T_maj.v[0];
+						tpu	  = tpu * T_maj / T_maj.v[0];
+						tpl	  = tpl * T_maj / T_maj.v[0];
+					}
+					if (visible || !any(T_ray)) break;
+					/* ray = intr.spawnRayTo(pLight), raytracing.h:151-155 */
+					V3 p_o = offsetRayOrigin(sit.p, sit.n, pLight - sit.p);
+					rd_	   = pLight - p_o;
+					ro_	   = p_o;
+					rmed   = getMedium(sit, rd_);
+				}
+				if (any(T_ray)) L = (Ld * T_ray / mean(spu * tpu + spl * tpl)) + L;
+			};
 
 			for (int loopDepth = 0; alive; loopDepth++) {
 				const bool capD = capS && capDepth == loopDepth;
@@ -625,28 +888,96 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 				/* [2.1] traceClosest: device.cu:43-81 */
 				st_.closest++;
 				if (loopDepth < KRR_MAX_DEPTH_STATS) st_.closestByDepth[loopDepth]++;
-				Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(),
-									 [&](const Hit &c) { return !alphaKilled(s, c, rayO, rayD); });
+				Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(), alphaAccept(rayO, rayD));
 				if (loopDepth == 0) fhInst = h.inst, fhPrim = h.prim;
 				alive = false; /* the ray item is consumed */
-				bool haveScatter = false, haveHitLight = false, haveMiss = false;
+				bool haveScatter = false, haveHitLight = false, haveMiss = false, haveMediumScatter = false;
 				SurfIntr it;
-				if (h.inst < 0) {
-					haveMiss = true;
-				} else {
+				if (h.inst >= 0) {
 					prepareInteraction(s, h, rayD, rtime, lambda, lpdf, it);
-					if (it.material < 0) {
-						/* null material: same-depth re-push, device.cu:54-58 */
-						rayO = offsetRayOrigin(it.p, it.n, rayD);
-						alive = true;
-						if (capD) cap.push(5, pixelId, depth, bsdfType, -1);
+					it.medium = rayMedium;
+				}
+				/* MediumScatterWorkItem */
+				V3 msP = mk(0, 0, 0), msWo = mk(0, 0, 0);
+				Spec msThp = sconst(0), msPu = sconst(0);
+				int msMedium = -1;
+				auto passNull = [&]() {
+					/* null material: same-depth re-push of intr.spawnRayTowards(ray.dir), device.cu:54-58 / medium.cpp:88-93 */
+					rayO	  = offsetRayOrigin(it.p, it.n, rayD);
+					rayMedium = enableMedium ? getMedium(it, rayD) : -1;
+					alive	  = true;
+					if (capD) cap.push(5, pixelId, depth, bsdfType, -1);
+				};
+				if (enableMedium && rayMedium >= 0) {
+					/* [2.2] sampleMediumInteraction, medium.cpp:13-103 */
+					st_.mediumSample++;
+					const MediumData &med = s.media[rayMedium];
+					const float tMaxM = h.inst >= 0 ? h.t : std::numeric_limits<float>::infinity();
+					Spec Lm = sconst(0);
+					bool scattered = false;
+					Spec T_maj = sampleT_maj(med, rayO, rayD, tMaxM, &smp, lambda,
+						[&](V3 pm, MediumPoint mp, Spec sigma_maj, Spec T_maj_) -> bool {
+							if (depth < p->max_depth && any(mp.Le)) {
+								float pr = sigma_maj.v[0] * T_maj_.v[0];
+								Spec pe	 = pu * sigma_maj * T_maj_ / pr;
+								if (any(pe)) Lm = Lm + thp * mp.sigma_a * T_maj_ * mp.Le / (pr * mean(pe));
+							}
+							float pAbsorb  = mp.sigma_a.v[0] / sigma_maj.v[0];
+							float pScatter = mp.sigma_s.v[0] / sigma_maj.v[0];
+							float pNull	   = std::max(0.f, 1.f - pAbsorb - pScatter);
+							int mode	   = sampleDiscrete3(pAbsorb, pScatter, pNull, ol_pcg_get1d(&smp));
+							if (mode == 0) {
+								thp = sconst(0);
+								return false;
+							} else if (mode == 1) {
+								float pr = T_maj_.v[0] * mp.sigma_s.v[0];
+								thp		 = thp * T_maj_ * mp.sigma_s / pr;
+								pu		 = pu * T_maj_ * mp.sigma_s / pr;
+								if (any(thp) && any(pu)) {
+									haveMediumScatter = true;
+									msP = pm, msThp = thp, msPu = pu, msWo = -rayD, msMedium = rayMedium;
+								}
+								scattered = true;
+								return false;
+							} else {
+								Spec sigma_n = cwiseMax0(sigma_maj - mp.sigma_a - mp.sigma_s);
+								float pr	 = T_maj_.v[0] * sigma_n.v[0];
+								thp			 = thp * T_maj_ * sigma_n / pr;
+								if (pr == 0) thp = sconst(0);
+								pu = pu * T_maj_ * sigma_n / pr;
+								pl = pl * T_maj_ * sigma_maj / pr;
+								return any(thp) && any(pu);
+							}
+						});
+					if (any(Lm)) L = Lm + L;
+					if (!scattered && any(thp)) {
+						thp = thp * T_maj / T_maj.v[0];
+						pu	= pu * T_maj / T_maj.v[0];
+						pl	= pl * T_maj / T_maj.v[0];
+					}
+					if (haveMediumScatter) st_.mediumScatter++;
+					if (scattered || !any(thp) || !any(pu) || depth == p->max_depth) {
+						/* nothing else leaves this item */
+					} else if (h.inst < 0) {
+						haveMiss = true;
+					} else if (it.material < 0) {
+						passNull();
 					} else {
 						if (it.light >= 0) haveHitLight = true;
-						if (any(thp)) {
-							haveScatter = true;
-							st_.scatter++;
-							if (capD) cap.push(3, pixelId, depth, ol_bsdf_type(&it.sd), it.sd.bsdfType);
-						}
+						haveScatter = true;
+						st_.scatter++;
+						if (capD) cap.push(3, pixelId, depth, ol_bsdf_type(&it.sd), it.sd.bsdfType);
+					}
+				} else if (h.inst < 0) {
+					haveMiss = true;
+				} else if (it.material < 0) {
+					passNull();
+				} else {
+					if (it.light >= 0) haveHitLight = true;
+					if (any(thp)) {
+						haveScatter = true;
+						st_.scatter++;
+						if (capD) cap.push(3, pixelId, depth, ol_bsdf_type(&it.sd), it.sd.bsdfType);
 					}
 				}
 				/* [2.3] handleHit, integrator.cpp:78-90 */
@@ -685,6 +1016,67 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 					L = (thp * Lm) + L;
 				}
 				if (loopDepth == p->max_depth) break;
+				/* light sampling shared by the two scattering stages: lightSampler.sample + light.sampleLi */
+				auto sampleLight = [&](V3 cpv, V3 cnv, float lp[3], float ln[3], float Ll[4], float &lightPdf, bool &delta, int &lightId) {
+					float u1 = ol_pcg_get1d(&smp);
+					lightId	 = (int) (uint32_t) (u1 * nLights);
+					const LightRef &lr = s.lights[lightId];
+					float u2[2];
+					u2[0] = ol_pcg_get1d(&smp), u2[1] = ol_pcg_get1d(&smp);
+					float cp[3], cn[3], lpdfv;
+					st(cp, cpv), st(cn, cnv);
+					ln[0] = ln[1] = ln[2] = 0;
+					delta = lr.type != KRR_LIGHT_DIFFUSE_AREA && lr.type != KRR_LIGHT_INFINITE;
+					if (lr.type == KRR_LIGHT_DIFFUSE_AREA) {
+						OlTriLight tl;
+						fillTri(s, lr, tl);
+						ol_arealight_sample_li(&tl, u2, cp, cn, lambda, lp, ln, Ll, &lpdfv);
+					} else ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+					lightPdf = (1.f / nLights) * lpdfv;
+				};
+				/* [2.4a] sampleMediumScattering, medium.cpp:105-153 */
+				if (haveMediumScatter) {
+					const float g = s.media[msMedium].g;
+					float wo3[3];
+					st(wo3, msWo);
+					if (p->nee) {
+						float lp[3], ln[3], Ll[4], lightPdf;
+						bool delta;
+						int lightId;
+						sampleLight(msP, mk(0, 0, 0), lp, ln, Ll, lightPdf, delta, lightId);
+						/* Interaction(p, time, medium).spawnRayTo(ls.intr): n = 0, so the origin is not offset */
+						V3 lP = mk(lp), lN = mk(ln);
+						V3 to  = offsetRayOrigin(lP, lN, msP - lP);
+						V3 sd_ = to - msP;
+						V3 wi  = normalize(sd_);
+						float wi3[3];
+						st(wi3, wi);
+						float ph	   = ol_hg_p(g, wo3, wi3);
+						Spec thpL	   = msThp * ph;
+						float phasePdf = delta ? 0 : ph; /* HGPhaseFunction::pdf == p */
+						Spec Ld		   = thpL * Spec{{Ll[0], Ll[1], Ll[2], Ll[3]}};
+						if (any(Ld) && lightPdf > 0) traceShadowItem(msP, sd_, msMedium, Ld, msPu * phasePdf, msPu * lightPdf, loopDepth, capD, lightId);
+					}
+					float u2[2], wi3[3], php, phpdf;
+					u2[0] = ol_pcg_get1d(&smp), u2[1] = ol_pcg_get1d(&smp);
+					ol_hg_sample(g, wo3, u2, wi3, &php, &phpdf);
+					Spec nthp	 = msThp * php / phpdf;
+					float rrProb = maxCoeff(nthp / mean(msPu));
+					bool killed	 = false;
+					if (depth >= 1 && rrProb < 1) {
+						if (ol_pcg_get1d(&smp) >= rrProb) killed = true;
+						else nthp = nthp / rrProb;
+					}
+					if (!killed && any(nthp) && !hasNaN(nthp)) {
+						rayO = msP, rayD = mk(wi3), rayMedium = msMedium;
+						ctxP = msP, ctxN = mk(0, 0, 0);
+						thp = nthp, pu = msPu, pl = msPu / phpdf;
+						depth	 = depth + 1;
+						bsdfType = 8 | 16; /* BSDF_SMOOTH */
+						alive	 = true;
+						if (capD) cap.push(5, pixelId, depth, bsdfType, -1);
+					}
+				}
 				/* [2.4] generateScatterRays, integrator.cpp:110-164 */
 				if (haveScatter) {
 					if (ol_pcg_get1d(&smp) >= p->rr) continue; /* alive == false: path ends */
@@ -694,20 +1086,10 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 					float wo3[3];
 					st(wo3, woLocal);
 					if (p->nee && (bt & (8 | 16))) { /* BSDF_SMOOTH = DIFFUSE | GLOSSY */
-						float u1 = ol_pcg_get1d(&smp);
-						uint32_t sampleId_ = (uint32_t) (u1 * nLights);
-						const LightRef &lr = s.lights[sampleId_];
-						float u2[2];
-						u2[0] = ol_pcg_get1d(&smp), u2[1] = ol_pcg_get1d(&smp);
-						float lp[3], ln[3] = {0, 0, 0}, Ll[4], lpdfv;
-						float cp[3], cn[3];
-						st(cp, it.p), st(cn, it.n);
-						bool delta = lr.type != KRR_LIGHT_DIFFUSE_AREA && lr.type != KRR_LIGHT_INFINITE;
-						if (lr.type == KRR_LIGHT_DIFFUSE_AREA) {
-							OlTriLight tl;
-							fillTri(s, lr, tl);
-							ol_arealight_sample_li(&tl, u2, cp, cn, lambda, lp, ln, Ll, &lpdfv);
-						} else ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+						float lp[3], ln[3], Ll[4], lightPdf;
+						bool delta;
+						int lightId;
+						sampleLight(it.p, it.n, lp, ln, Ll, lightPdf, delta, lightId);
 						/* spawnRayTo(ls.intr): raytracing.h:148-157 */
 						V3 lP = mk(lp), lN = mk(ln);
 						V3 to  = offsetRayOrigin(lP, lN, it.p - lP);
@@ -715,7 +1097,6 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 						V3 sd_ = to - p_o;
 						V3 wiWorld = normalize(sd_);
 						V3 wiLocal = toLocal(it, wiWorld);
-						float lightPdf = (1.f / nLights) * lpdfv;
 						float wi3[3], f4[4], bpdf;
 						st(wi3, wiLocal);
 						ol_bsdf_f_pdf(&it.sd, wo3, wi3, f4, &bpdf);
@@ -724,18 +1105,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 						if (lightPdf > 0 && any(bsdfVal)) {
 							Spec Ld = Spec{{Ll[0], Ll[1], Ll[2], Ll[3]}} * thp * bsdfVal * std::fabs(wiLocal.z);
 							Spec spu = pu * bsdfPdf, spl = pu * lightPdf;
-							if (any(Ld)) {
-								/* [2.5] traceShadow, device.cu:83-100 */
-								st_.shadow++;
-								if (loopDepth < KRR_MAX_DEPTH_STATS) st_.shadowByDepth[loopDepth]++;
-								if (capD) cap.push(4, pixelId, depth, 0, (int) sampleId_);
-								Hit sh = traceClosest(s, useBvh, p_o, sd_, 1.f, [&](const Hit &c) {
-									/* __anyhit__Shadow: ignore null-material and alpha-killed hits */
-									if (s.meshes[s.instances[c.inst].mesh].material < 0) return false;
-									return !alphaKilled(s, c, p_o, sd_);
-								});
-								if (sh.inst < 0) L = (Ld / mean(spl + spu)) + L;
-							}
+							if (any(Ld)) traceShadowItem(p_o, sd_, enableMedium ? getMedium(it, sd_) : -1, Ld, spu, spl, loopDepth, capD, lightId);
 						}
 					}
 					/* sample BSDF */
@@ -750,8 +1120,9 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 							bsdfType = flags;
 							pl		 = pu / spdf;
 							/* pu unchanged */
-							rayO	 = offsetRayOrigin(it.p, it.n, wiWorld);
-							rayD	 = wiWorld;
+							rayO	  = offsetRayOrigin(it.p, it.n, wiWorld);
+							rayD	  = wiWorld;
+							rayMedium = enableMedium ? getMedium(it, wiWorld) : -1;
 							ctxP = it.p, ctxN = it.n;
 							depth	 = depth + 1;
 							thp		 = nthp;
@@ -788,6 +1159,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 		for (auto &t : tstats) {
 			stats->camera_rays += t.camera, stats->closest_rays += t.closest, stats->shadow_rays += t.shadow;
 			stats->scatter_items += t.scatter, stats->hit_light_items += t.hitLight, stats->miss_items += t.miss;
+			stats->medium_sample_items += t.mediumSample, stats->medium_scatter_items += t.mediumScatter;
 			for (int k = 0; k < KRR_MAX_DEPTH_STATS; k++)
 				stats->closest_by_depth[k] += t.closestByDepth[k], stats->shadow_by_depth[k] += t.shadowByDepth[k];
 		}

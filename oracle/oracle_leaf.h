@@ -97,6 +97,16 @@ void ol_inflight_Li(const OlLight *l, const float wi[3], const float lambda[4], 
 float ol_hg_p(float g, const float wo[3], const float wi[3]);
 void  ol_hg_sample(float g, const float wo[3], const float u[2], float wi[3], float *p, float *pdf);
 
+/* HomogeneousMedium::samplePoint, reference src/render/media.h:121-126 (Le: RGBIlluminant, :139-141) */
+void  ol_homogeneous_sample_point(const float sigma_t[3], const float albedo[3], const float Le[3],
+								  const float lambda[4], float sigma_a[4], float sigma_s[4], float LeOut[4]);
+/* MajorantIterator over a MajorantGrid (reference src/render/media.h:41-106); voxels == NULL runs the
+ * homogeneous variant.  o/d are in MEDIUM space.  Writes up to cap segments as {tMin, tMax, sigma_maj[4]}
+ * (6 floats each) and returns the number of segments the iterator produced. */
+int	  ol_majorant_segments(const float boundsMin[3], const float boundsMax[3], const int res[3],
+						   const float *voxels, const float o[3], const float d[3], float tMin, float tMax,
+						   const float sigma_t[4], float *out6, int cap);
+
 /* misc */
 float		ol_get_metallic(const float diffuse[3], const float spec[3]); /* shading.h:17-30 (restated in both) */
 const char *ol_backend_name(void);

@@ -305,6 +305,34 @@ extern "C" void ol_hg_sample(float g, const float wo[3], const float u[2], float
 	*pdf = ps.pdf;
 }
 
+extern "C" void ol_homogeneous_sample_point(const float sigma_t[3], const float albedo[3], const float Le[3],
+											 const float lambda[4], float sigma_a[4], float sigma_s[4], float LeOut[4]) {
+	ol_init();
+	HomogeneousMedium m(RGB(sigma_t[0], sigma_t[1], sigma_t[2]), RGB(albedo[0], albedo[1], albedo[2]),
+						RGB(Le[0], Le[1], Le[2]), 0.f, RGBColorSpace::sRGB);
+	MediumProperties mp = m.samplePoint(Vector3f(0, 0, 0), SW(lambda, nullptr));
+	S4(sigma_a, mp.sigma_a), S4(sigma_s, mp.sigma_s), S4(LeOut, mp.Le);
+}
+extern "C" int ol_majorant_segments(const float boundsMin[3], const float boundsMax[3], const int res[3],
+									 const float *voxels, const float o[3], const float d[3], float tMin, float tMax,
+									 const float sigma_t[4], float *out6, int cap) {
+	MajorantGrid grid(AABB3f(V3(boundsMin), V3(boundsMax)), Vector3i(res[0], res[1], res[2]));
+	grid.voxels = TypedBufferView<float>(voxels, (size_t) res[0] * res[1] * res[2]);
+	Ray ray{V3(o), V3(d)};
+	MajorantIterator it(ray, tMin, tMax, SP(sigma_t), voxels ? &grid : nullptr);
+	int n = 0;
+	while (true) {
+		gpu::optional<MajorantSegment> seg = it.next();
+		if (!seg) break;
+		if (n < cap) {
+			out6[6 * n] = seg->tMin, out6[6 * n + 1] = seg->tMax;
+			S4(out6 + 6 * n + 2, seg->sigma_maj);
+		}
+		n++;
+	}
+	return n;
+}
+
 /* getMetallic lives in render/shading.h, which cannot be compiled host-side (OptiX intrinsics);
  * restated from shading.h:17-30 using the reference's own luminance(). */
 extern "C" float ol_get_metallic(const float diffuse[3], const float spec[3]) {
