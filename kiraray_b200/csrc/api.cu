@@ -119,7 +119,10 @@ struct KrrWfpt {
 	Buf<uint64_t> rng;
 	Buf<float> lambda, cameraSample;
 	Buf<int4> hits, firstHits;
-	Buf<int32_t> missIdx, hitLightIdx, scatterIdx[MAT_COUNT], errorFlags;
+	Buf<int32_t> missIdx, hitLightIdx, scatterIdx[MAT_COUNT], errorFlags, mediumSampleIdx;
+	Buf<float> hitT;
+	Buf<float4> msBuf[4];
+	Buf<int2> msPixDepth, shadowAux;
 	Buf<DepthCounters> counters;
 	Buf<StatTotals> totals;
 	KrrCameraDev cam{};
@@ -175,6 +178,10 @@ int allocState(KrrWfpt *h) {
 	for (int a = 0; a < 5; a++) rc |= h->shadowBuf[a].alloc(n);
 	rc |= h->missIdx.alloc(n) | h->hitLightIdx.alloc(n);
 	for (int m = 0; m < MAT_COUNT; m++) rc |= h->scatterIdx[m].alloc(n);
+	if (h->sceneHasMedia) { // media queues (mediumSampleQueue / mediumScatterQueue, integrator.cpp:40-44)
+		rc |= h->mediumSampleIdx.alloc(n) | h->hitT.alloc(n) | h->msPixDepth.alloc(n) | h->shadowAux.alloc(n);
+		for (int a = 0; a < 4; a++) rc |= h->msBuf[a].alloc(n);
+	}
 	rc |= h->counters.alloc(kMaxDepthSlots) | h->totals.alloc(1) | h->errorFlags.alloc(4);
 	if (rc) return KRR_E_CUDA;
 	CUDA_OK(cudaMemset(h->counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
@@ -233,7 +240,10 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 	wf.missIdx = h->missIdx.p, wf.hitLightIdx = h->hitLightIdx.p;
 	for (int m = 0; m < MAT_COUNT; m++) wf.scatterIdx[m] = h->scatterIdx[m].p;
 	wf.shadow.o_tmax = h->shadowBuf[0].p, wf.shadow.d_pix = h->shadowBuf[1].p, wf.shadow.contrib = h->shadowBuf[2].p;
-	wf.shadow.pu = h->shadowBuf[3].p, wf.shadow.pl = h->shadowBuf[4].p;
+	wf.shadow.pu = h->shadowBuf[3].p, wf.shadow.pl = h->shadowBuf[4].p, wf.shadow.aux = h->shadowAux.p;
+	wf.hitT = h->hitT.p, wf.mediumSampleIdx = h->mediumSampleIdx.p;
+	wf.mscatter.p_time = h->msBuf[0].p, wf.mscatter.wo_medium = h->msBuf[1].p, wf.mscatter.thp = h->msBuf[2].p, wf.mscatter.pu = h->msBuf[3].p;
+	wf.mscatter.pix_depth = h->msPixDepth.p;
 	wf.counters	  = h->counters.p;
 	wf.firstHits  = h->debugState ? h->firstHits.p : nullptr;
 	wf.errorFlags = h->errorFlags.p;
@@ -397,6 +407,11 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 		}
 		media[i] = r;
 	}
+	for (MediumRec &r : media)
+		if (r.type == KRR_MEDIUM_GRID) { // room for the 64^3 majorant grid, filled on the device below
+			r.majorantOff = (int32_t) density.size();
+			density.resize(density.size() + (size_t) kMajRes * kMajRes * kMajRes, 0.f);
+		}
 	h->sceneHasMedia = d->n_media > 0;
 	// instances (InstanceData::getObjectData, mesh.cpp:16-63) + mesh lights (scene.cpp:91-112)
 	std::vector<InstRec> insts(d->n_instances);
@@ -512,6 +527,13 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	s.nInfinite = (int32_t) infinite.size(), s.nMedia = d->n_media;
 	s.motionStart = d->options.starttime, s.motionEnd = d->options.endtime, s.hasMotion = anyMotion;
 	s.cs = h->cs;
+	for (const MediumRec &r : media)
+		if (r.type == KRR_MEDIUM_GRID)
+			k_build_majorant<<<(kMajRes * kMajRes * kMajRes + 255) / 256, 256>>>(h->densityPool.p + r.densityOff, r.res[0], r.res[1], r.res[2],
+				make_float3(r.boundsMin[0], r.boundsMin[1], r.boundsMin[2]), make_float3(r.boundsMax[0], r.boundsMax[1], r.boundsMax[2]),
+				h->densityPool.p + r.majorantOff);
+	CUDA_OK(cudaDeviceSynchronize());
+	if (h->width > 0) { rc = allocState(h); if (rc) return rc; } // media queues depend on the scene
 	if (anyMotion) return fail(KRR_E_UNSUPPORTED, "motion-blur instances are not supported by this build yet");
 	h->haveScene = true;
 	return KRR_OK;
@@ -610,6 +632,12 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		gridCam = gridFor(h, k_generate_camera_rays, 256), gridTrace = gridFor(h, k_trace_closest, 128);
 		gridHit = gridFor(h, k_handle_hit_miss, 128), gridShadow = gridFor(h, k_trace_shadow, 128), gridResolve = gridFor(h, k_resolve, 256);
 	}
+	static int gridMSample = 0, gridMScatter = 0, gridShadowTr = 0;
+	const bool media = h->enableMedium && h->sceneHasMedia;
+	if (media && !gridMSample) {
+		gridMSample = gridFor(h, k_medium_sample, 128), gridMScatter = gridFor(h, k_medium_scatter, 128);
+		gridShadowTr = gridFor(h, k_trace_shadow_tr, kTraceBlock);
+	}
 	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
 	const int nDepthSlots = h->maxDepth + 2;
 	for (int sampleId = 0; sampleId < h->spp; sampleId++) {
@@ -623,11 +651,20 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			// [2.1] closest hits
 			{ StageTimer t(h, KRR_STAGE_CLOSEST, st); k_trace_closest<<<gridTrace, 128, 0, st>>>(wf, depth); }
 			h->launches++;
+			// [2.2] medium interactions along the rays that travel inside a medium
+			if (media) {
+				{ StageTimer t(h, KRR_STAGE_MEDIUM, st); k_medium_sample<<<gridMSample, 128, 0, st>>>(wf, depth); }
+				h->launches++;
+			}
 			if (cap) for (int q = 1; q <= 3; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.3] emitted / environment radiance
 			{ StageTimer t(h, KRR_STAGE_HIT_MISS, st); k_handle_hit_miss<<<gridHit, 128, 0, st>>>(wf, depth); }
 			h->launches++;
 			if (depth == h->maxDepth) break;
+			if (media) {
+				{ StageTimer t(h, KRR_STAGE_MEDIUM, st); k_medium_scatter<<<gridMScatter, 128, 0, st>>>(wf, depth); }
+				h->launches++;
+			}
 			// [2.4] BSDF sampling + NEE, one launch per material type present in the scene
 			if (h->matTypePresent[MAT_DISNEY]) launchScatter<MAT_DISNEY>(h, wf, depth, st);
 			if (h->matTypePresent[MAT_DIFFUSE]) launchScatter<MAT_DIFFUSE>(h, wf, depth, st);
@@ -637,7 +674,9 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			if (cap) for (int q = 4; q <= 5; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.5] shadow rays
 			if (h->nee) {
-				{ StageTimer t(h, KRR_STAGE_SHADOW, st); k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth); }
+				StageTimer t(h, KRR_STAGE_SHADOW, st);
+				if (media) k_trace_shadow_tr<<<gridShadowTr, kTraceBlock, 0, st>>>(wf, depth);
+				else k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth);
 				h->launches++;
 			}
 		}

@@ -154,7 +154,10 @@ template <bool ANY> struct Traverser {
 			if (sp == 0) return FINISHED;
 			float tn = 0.f;
 			cur = pop(sm, tn);
-			if (!ANY && tn > best.t) cur = kEmptyEntry; // box entry beyond the closest hit so far
+			// box entry beyond the closest hit so far (same slack as the slab test: for flat, axis-aligned
+			// geometry the rounded entry distance can exceed the exact hit distance by an ulp, and an
+			// equal-t candidate with a smaller (instance, primitive) must still be tested)
+			if (!ANY && tn > best.t * 1.0000010f + 1e-30f) cur = kEmptyEntry;
 		}
 		return cur < kLeafFlag ? NODE : ((cur & kInstFlag) ? ENTER : LEAF);
 	}
@@ -186,6 +189,10 @@ template <bool ANY> struct Traverser {
 			const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
 			const float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
 			const float lim = best.t;
+			// rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
+			// when the ray grazes an axis-aligned plane): the test and the stored entry distance are widened
+			// by it, so flat boxes are never culled by arithmetic noise
+			const float slack = ((fabsf(bx) + 255.f * fabsf(ax)) + (fabsf(by) + 255.f * fabsf(ay)) + (fabsf(bz) + 255.f * fabsf(az))) * 2.4e-7f;
 			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
 			auto child = [&](int i) -> uint32_t {
 				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
@@ -199,9 +206,9 @@ template <bool ANY> struct Traverser {
 				float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
 				float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), lim));
 				// conservative: boxes only cull, the exact decision is the triangle test
-				if (!(tn <= tf * 1.0000010f + 1e-30f)) return kEmptyEntry;
+				if (!(tn <= tf * 1.0000010f + slack)) return kEmptyEntry;
 				// key: entry distance in the high bits, slot in the low 3 -> one compare orders (tn, slot)
-				return (__float_as_uint(tn) & ~7u) | (uint32_t) i;
+				return (__float_as_uint(fmaxf(tn - slack, 0.f)) & ~7u) | (uint32_t) i;
 			};
 			k0 = child(0), k1 = child(1), k2 = child(2), k3 = child(3), k4 = child(4), k5 = child(5), k6 = child(6), k7 = child(7);
 			// 19-comparator sorting network: ascending, misses (0xffffffff) sink to the end
@@ -249,6 +256,21 @@ template <bool ANY> struct Traverser {
 			}
 		}
 		return false;
+	}
+
+	// Lane-local traversal to the end (no warp-level primitives): used where one lane runs several
+	// dependent traversals interleaved with other work (ratio-tracking shadow rays through media).
+	template <typename Accept> KRR_DEV void runToEnd(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
+		while (true) {
+			int st = next(sm);
+			if (st == FINISHED) return;
+			if (st == ENTER) { enterInstance(instances, sm); st = NODE; }
+			if (st == NODE) {
+				node(bvh, sm);
+				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
+			}
+			if (st == LEAF && leaf(bvh, accept)) return;
+		}
 	}
 
 	// One warp-cooperative trip: lanes vote on the phase to run, so that a phase executes with as many

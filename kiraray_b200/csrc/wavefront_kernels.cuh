@@ -29,6 +29,7 @@
 #include "bsdf.cuh"
 #include "bvh.cuh"
 #include "lights.cuh"
+#include "medium.cuh"
 #include "sampler.cuh"
 #include "scene.cuh"
 #include "spectrum.cuh"
@@ -62,6 +63,14 @@ struct ShadowQueue { // 3 x 16 B (+2 for the transmittance variant)
 	float4 *d_pix;
 	float4 *contrib; // Ld / (pl + pu).mean()   (Ld itself when media are enabled)
 	float4 *pu, *pl; // media only
+	int2 *aux;		 // media only: medium index of the ray, ray time (float bits)
+};
+
+struct MediumScatterQueue { // MediumScatterWorkItem (workitem.h:85-95), media only: 4 x 16 B + 8 B
+	float4 *p_time;	   // scattering point, ray time
+	float4 *wo_medium; // wo = -ray.dir, medium index (int bits)
+	float4 *thp, *pu;
+	int2 *pix_depth;
 };
 
 struct PixelState {
@@ -101,7 +110,9 @@ struct Wavefront {
 	PixelState px;
 	RayQueue rays[2];
 	int4 *hits;			// per ray slot of the CURRENT queue: inst, prim, u bits, v bits
-	int32_t *missIdx, *hitLightIdx;
+	float *hitT;		// media only: hit distance per ray slot (tMax of the medium-sample item)
+	int32_t *missIdx, *hitLightIdx, *mediumSampleIdx;
+	MediumScatterQueue mscatter;
 	int32_t *scatterIdx[MAT_COUNT];
 	ShadowQueue shadow;
 	DepthCounters *counters; // [kMaxDepthSlots]
@@ -306,6 +317,8 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	if (dot(n, d) < 0.f) off = -off;
 	V3 no = p + off;
 	stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, o4.w));
+	if (wf.p.enableMedium && mesh.mediumIn != mesh.mediumOut) // Interaction::getMedium(dir), raytracing.h:162-166
+		d4.w = __int_as_float(dot(d, n) > 0 ? mesh.mediumOut : mesh.mediumIn);
 	stcs4(nq.d_medium + s, d4);
 	stcs4(nq.thp + s, ldcs4(q.thp + i));
 	stcs4(nq.pu + s, ldcs4(q.pu + i));
@@ -361,7 +374,11 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
 				wf.firstHits[pix] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
 			}
-			if (h.inst < 0) route = 0;
+			if (wf.p.enableMedium && __float_as_int(d4.w) >= 0) {
+				// ray inside a medium: hit or miss, the item goes to the medium stage (device.cu:50-53, 69-72)
+				route	   = 4;
+				wf.hitT[i] = h.inst < 0 ? kInf : h.t;
+			} else if (h.inst < 0) route = 0;
 			else {
 				const InstRec &in	= wf.scene.instances[h.inst];
 				const MeshRec &mesh = wf.scene.meshes[in.mesh];
@@ -395,6 +412,10 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 		if (killed && lane == 0) atomicAdd(&dc->nScatterKilled, __popc(killed));
 		s = warpPushFull(&dc[1].nRay, route == 2);
 		if (s >= 0) requeueThroughNull(wf, q, nq, i, s, h, o4, d4);
+		if (wf.p.enableMedium) {
+			s = warpPushFull(&dc->nMediumSample, route == 4);
+			if (s >= 0) wf.mediumSampleIdx[s] = i;
+		}
 	}
 }
 
@@ -614,7 +635,7 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 		// next ray
 		V3 no, nd, ctxP, ctxN;
 		Spec nthp, npu, npl;
-		int pix = 0, itemDepth = 0, nflags = 0, medium = -1;
+		int pix = 0, itemDepth = 0, nflags = 0, medium = -1, sMedium = -1;
 		float time = 0;
 		if (active) {
 			int i	  = wf.scatterIdx[MT][k];
@@ -674,6 +695,8 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 						if (any(Ld)) {
 							pushShadow = true;
 							so = p_o, sdv = dd;
+							const MeshRec &smesh = wf.scene.meshes[g.mesh]; // spawnRayTo: medium = getMedium(d)
+							sMedium = smesh.mediumIn != smesh.mediumOut ? (dot(dd, g.n) > 0 ? smesh.mediumOut : smesh.mediumIn) : medium;
 							sPu = pu * bsdfPdf, sPl = pu * lightPdf;
 							sContrib = wf.p.enableMedium ? Ld : Ld / mean(sPl + sPu);
 						}
@@ -704,7 +727,10 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 			stcs4(wf.shadow.o_tmax + s, make_float4(so.x, so.y, so.z, 1.f));
 			stcs4(wf.shadow.d_pix + s, make_float4(sdv.x, sdv.y, sdv.z, __int_as_float(pix)));
 			stcs4(wf.shadow.contrib + s, sContrib);
-			if (wf.p.enableMedium) { stcs4(wf.shadow.pu + s, sPu); stcs4(wf.shadow.pl + s, sPl); }
+			if (wf.p.enableMedium) {
+				stcs4(wf.shadow.pu + s, sPu), stcs4(wf.shadow.pl + s, sPl);
+				wf.shadow.aux[s] = make_int2(sMedium, __float_as_int(time));
+			}
 		}
 		s = warpPush(&dc[1].nRay, pushNext);
 		if (s >= 0) {
@@ -763,6 +789,306 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	}
 }
 
+// =================================================================================================
+// Participating media (BASELINE config 4).  Stage map: k_medium_sample = sampleMediumInteraction
+// (medium.cpp:13-103), k_medium_scatter = sampleMediumScattering (medium.cpp:105-153),
+// k_trace_shadow_tr = __raygen__ShadowTr + traceTransmittance (device.cu:102-128, wavefront.h:80-139).
+// A medium-sample item is the ray slot itself (+ hit record + hit distance): the stage updates the
+// slot's thp / pu / pl in place and then routes the slot to the miss / hit-light / scatter index
+// queues, exactly where the surface-only path would have put it.
+
+// Interaction::getMedium(w) for a surface hit (raytracing.h:162-166)
+KRR_DEV int mediumAcross(const MeshRec &mesh, V3 n, V3 w, int rayMedium) {
+	return mesh.mediumIn != mesh.mediumOut ? (dot(w, n) > 0 ? mesh.mediumOut : mesh.mediumIn) : rayMedium;
+}
+
+__global__ void __launch_bounds__(128) k_medium_sample(const __grid_constant__ Wavefront wf, int depth) {
+	const RayQueue q  = wf.rays[depth & 1];
+	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
+	DepthCounters *dc = wf.counters + depth;
+	const int n		  = dc->nMediumSample;
+	const int stride  = gridDim.x * blockDim.x;
+	const int nIter	  = (n + stride - 1) / stride;
+	for (int iter = 0; iter < nIter; iter++) {
+		const int k = iter * stride + blockIdx.x * blockDim.x + threadIdx.x;
+		int route = -1; // 0 miss, 1 surface (scatter + light), 2 null pass-through
+		bool pushMS = false, light = false;
+		int matType = 0, i = 0, pix = 0, itemDepth = 0, medium = -1;
+		float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+		V3 msP = mk3(0, 0, 0);
+		Spec thp = sp(0), pu = sp(0), pl = sp(0);
+		Hit h;
+		h.inst = -1, h.prim = -1, h.t = 0, h.u = h.v = 0;
+		if (k < n) {
+			i  = wf.mediumSampleIdx[k];
+			o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
+			float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
+			pix = __float_as_int(cp.w), itemDepth = __float_as_int(cn.w) & 0xff, medium = __float_as_int(d4.w);
+			thp = ldcs4(q.thp + i), pu = ldcs4(q.pu + i), pl = ldcs4(q.pl + i);
+			int4 hit = wf.hits[i];
+			h.inst = hit.x, h.prim = hit.y, h.u = __int_as_float(hit.z), h.v = __int_as_float(hit.w);
+			const float tMax = wf.hitT[i];
+			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+			const MediumRec &med = wf.scene.media[medium];
+			V3 o = mk3(o4), d = mk3(d4);
+			Spec L = sp(0);
+			bool scattered = false;
+			Spec T_maj = sampleT_maj(med, wf.scene, o, d, tMax, rng, wl, [&](V3 p, const MediumPoint &mp, Spec sigma_maj, Spec Tm) -> bool {
+				if (itemDepth < wf.p.maxDepth && any(mp.Le)) {
+					float pr = sigma_maj.x * Tm.x;
+					Spec pe	 = pu * sigma_maj * Tm / pr;
+					if (any(pe)) L += thp * mp.sigma_a * Tm * mp.Le / (pr * mean(pe));
+				}
+				float pAbsorb = mp.sigma_a.x / sigma_maj.x, pScatter = mp.sigma_s.x / sigma_maj.x;
+				float pNull	  = fmaxf(0.f, 1.f - pAbsorb - pScatter);
+				int mode	  = sampleDiscrete3(pAbsorb, pScatter, pNull, rng.get1D());
+				if (mode == 0) { // absorbed
+					thp = sp(0);
+					return false;
+				} else if (mode == 1) { // real scattering
+					float pr = Tm.x * mp.sigma_s.x;
+					thp *= Tm * mp.sigma_s / pr;
+					pu *= Tm * mp.sigma_s / pr;
+					if (any(thp) && any(pu)) pushMS = true, msP = p;
+					scattered = true;
+					return false;
+				} else { // null collision
+					Spec sigma_n = cwiseMax(sigma_maj - mp.sigma_a - mp.sigma_s, 0.f);
+					float pr	 = Tm.x * sigma_n.x;
+					thp *= Tm * sigma_n / pr;
+					if (pr == 0) thp = sp(0);
+					pu *= Tm * sigma_n / pr;
+					pl *= Tm * sigma_maj / pr;
+					return any(thp) && any(pu);
+				}
+			});
+			wf.px.rng[pix] = rng.state;
+			if (any(L)) wf.px.L[pix] = L + wf.px.L[pix];
+			if (!scattered && any(thp)) {
+				thp *= T_maj / T_maj.x;
+				pu *= T_maj / T_maj.x;
+				pl *= T_maj / T_maj.x;
+			}
+			if (!(scattered || !any(thp) || !any(pu) || itemDepth == wf.p.maxDepth)) {
+				// the ray survived to the end of its segment: update the slot, route it like a surface-only ray
+				q.thp[i] = thp, q.pu[i] = pu, q.pl[i] = pl;
+				if (h.inst < 0) route = 0;
+				else {
+					const InstRec &in	= wf.scene.instances[h.inst];
+					const MeshRec &mesh = wf.scene.meshes[in.mesh];
+					if (mesh.material < 0) route = 2;
+					else {
+						route	= 1;
+						matType = wf.scene.materials[mesh.material].bsdfType;
+						light	= in.lightBase >= 0;
+					}
+				}
+			}
+		}
+		int s = warpPush(&dc->nMediumScatter, pushMS);
+		if (s >= 0) {
+			V3 d = mk3(d4);
+			stcs4(wf.mscatter.p_time + s, make_float4(msP.x, msP.y, msP.z, o4.w));
+			stcs4(wf.mscatter.wo_medium + s, make_float4(-d.x, -d.y, -d.z, d4.w));
+			stcs4(wf.mscatter.thp + s, thp);
+			stcs4(wf.mscatter.pu + s, pu);
+			wf.mscatter.pix_depth[s] = make_int2(pix, itemDepth);
+		}
+		s = warpPush(&dc->nMiss, route == 0);
+		if (s >= 0) wf.missIdx[s] = i;
+		s = warpPush(&dc->nHitLight, route == 1 && light);
+		if (s >= 0) wf.hitLightIdx[s] = i;
+#pragma unroll
+		for (int mt = 0; mt < MAT_COUNT; mt++) {
+			s = warpPush(&dc->nScatter[mt], route == 1 && matType == mt);
+			if (s >= 0) wf.scatterIdx[mt][s] = i;
+		}
+		s = warpPush(&dc[1].nRay, route == 2);
+		if (s >= 0) requeueThroughNull(wf, q, nq, i, s, h, o4, d4);
+	}
+}
+
+__global__ void __launch_bounds__(128) k_medium_scatter(const __grid_constant__ Wavefront wf, int depth) {
+	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
+	DepthCounters *dc = wf.counters + depth;
+	const int n		  = dc->nMediumScatter;
+	const int stride  = gridDim.x * blockDim.x;
+	const int nIter	  = (n + stride - 1) / stride;
+	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	for (int iter = 0; iter < nIter; iter++) {
+		const int k = iter * stride + blockIdx.x * blockDim.x + threadIdx.x;
+		bool pushShadow = false, pushNext = false;
+		V3 p = mk3(0, 0, 0), sdv = p, nd = p;
+		Spec Ld = sp(0), sPu = Ld, sPl = Ld, nthp = Ld, wpu = Ld, npl = Ld;
+		int pix = 0, itemDepth = 0, medium = -1;
+		float time = 0;
+		if (k < n) {
+			float4 pt = ldcs4(wf.mscatter.p_time + k), wm = ldcs4(wf.mscatter.wo_medium + k);
+			p = mk3(pt), time = pt.w, medium = __float_as_int(wm.w);
+			V3 wo = mk3(wm);
+			Spec wthp = ldcs4(wf.mscatter.thp + k);
+			wpu		  = ldcs4(wf.mscatter.pu + k);
+			int2 pd	  = wf.mscatter.pix_depth[k];
+			pix = pd.x, itemDepth = pd.y;
+			const float g = wf.scene.media[medium].g;
+			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+			if (wf.p.nee) { // [PART-A] direct lighting through ShadowTr
+				float ul = rng.get1D();
+				uint32_t lightId  = (uint32_t) (ul * wf.scene.nLights);
+				const LightRec lr = wf.scene.lights[lightId];
+				float u0 = rng.get1D(), u1 = rng.get1D();
+				LightSample ls;
+				bool delta = false;
+				if (lr.type == LIGHT_DIFFUSE_AREA) {
+					const TriLightRec &tl = wf.scene.triLights[lr.index];
+					ls = areaLightSampleLi(tl, wf.scene.instances[tl.inst], u0, u1, p, wl, wf.scene.cs);
+				} else {
+					const AnalyticLightRec &al = wf.scene.analytic[lr.index];
+					ls	  = analyticSampleLi(al, u0, u1, p, wl, wf.scene);
+					delta = al.type != LIGHT_INFINITE;
+				}
+				// Interaction(p, time, medium).spawnRayTo(ls.intr): n = 0, the origin is not offset
+				V3 off = ls.n * kRayEps;
+				if (dot(ls.n, p - ls.p) < 0.f) off = -off;
+				V3 dd = (ls.p + off) - p;
+				V3 wi = normalize(dd);
+				float ph	   = hgP(g, wo, wi);
+				float lightPdf = lightSelPdf * ls.pdf;
+				float phasePdf = delta ? 0.f : ph;
+				Spec l = wthp * ph * ls.L;
+				if (any(l) && lightPdf > 0) pushShadow = true, sdv = dd, Ld = l, sPl = wpu * lightPdf, sPu = wpu * phasePdf;
+			}
+			// [PART-B] phase-function sampling + Russian roulette
+			float u0 = rng.get1D(), u1 = rng.get1D();
+			float php, phpdf;
+			hgSample(g, wo, u0, u1, nd, php, phpdf);
+			nthp		 = wthp * php / phpdf;
+			float rrProb = maxCoeff(nthp / mean(wpu));
+			bool killed	 = false;
+			if (itemDepth >= 1 && rrProb < 1) {
+				if (rng.get1D() >= rrProb) killed = true;
+				else nthp = nthp / rrProb;
+			}
+			wf.px.rng[pix] = rng.state;
+			if (!killed && any(nthp) && !hasNaN(nthp)) pushNext = true, npl = wpu / phpdf;
+		}
+		int s = warpPush(&dc->nShadow, pushShadow);
+		if (s >= 0) {
+			stcs4(wf.shadow.o_tmax + s, make_float4(p.x, p.y, p.z, 1.f));
+			stcs4(wf.shadow.d_pix + s, make_float4(sdv.x, sdv.y, sdv.z, __int_as_float(pix)));
+			stcs4(wf.shadow.contrib + s, Ld);
+			stcs4(wf.shadow.pu + s, sPu), stcs4(wf.shadow.pl + s, sPl);
+			wf.shadow.aux[s] = make_int2(medium, __float_as_int(time));
+		}
+		s = warpPush(&dc[1].nRay, pushNext);
+		if (s >= 0) {
+			stcs4(nq.o_time + s, make_float4(p.x, p.y, p.z, time));
+			stcs4(nq.d_medium + s, make_float4(nd.x, nd.y, nd.z, __int_as_float(medium)));
+			stcs4(nq.thp + s, nthp);
+			stcs4(nq.pu + s, wpu);
+			stcs4(nq.pl + s, npl);
+			stcs4(nq.ctxP_pix + s, make_float4(p.x, p.y, p.z, __int_as_float(pix)));
+			stcs4(nq.ctxN_dep + s, make_float4(0, 0, 0, __int_as_float((itemDepth + 1) | (BSDF_SMOOTH << 8))));
+		}
+	}
+}
+
+// ShadowTr: transmittance along the shadow ray by ratio tracking, stepping through null-material
+// interfaces; an opaque surface ends it.  One lane runs the whole chain of one shadow ray.
+__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
+	DepthCounters *dc = wf.counters + depth;
+	const int n		  = dc->nShadow;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float4 o4 = ldcs4(wf.shadow.o_tmax + i), d4 = ldcs4(wf.shadow.d_pix + i);
+		const int pix = __float_as_int(d4.w);
+		int2 aux	  = wf.shadow.aux[i];
+		V3 ro = mk3(o4), rd = mk3(d4);
+		int medium		 = aux.x;
+		const float tMax = o4.w;
+		const V3 pLight	 = ro + rd * tMax;
+		Spec T_ray = sp(1), pu = sp(1), pl = sp(1);
+		Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+		bool usedRng   = false;
+		// SurfaceInteraction intr = {}: material == nullptr until a closest-hit program fills it
+		bool intrOpaque = false;
+		V3 ip = mk3(0, 0, 0), in_ = ip;
+		int imesh = -1;
+		while (!(fabsf(rd.x) <= 2 * kRayEps && fabsf(rd.y) <= 2 * kRayEps && fabsf(rd.z) <= 2 * kRayEps)) {
+			Traverser<false> tr;
+			tr.begin(wf.bvh, ro, rd, tMax);
+			tr.runToEnd(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+				if (!(wf.instFlags[inst] & 2)) return true;
+				return !alphaKilled(wf, inst, prim, u, v, ro, rd);
+			});
+			if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+			const bool visible = tr.best.inst < 0;
+			if (!visible) {
+				SurfaceGeom g;
+				rebuildGeometry(wf, make_int4(tr.best.inst, tr.best.prim, __float_as_int(tr.best.u), __float_as_int(tr.best.v)), mk3(d4), g);
+				ip = g.p, in_ = g.n, imesh = g.mesh, intrOpaque = g.material >= 0;
+			}
+			if (!visible && intrOpaque) { T_ray = sp(0); break; }
+			if (medium >= 0) {
+				float tEnd = visible ? tMax : length(ip - ro) / length(rd);
+				usedRng	   = true;
+				Spec T_maj = sampleT_maj(wf.scene.media[medium], wf.scene, ro, rd, tEnd, rng, wl, [&](V3, const MediumPoint &mp, Spec sigma_maj, Spec Tm) -> bool {
+					Spec sigma_n = cwiseMax(sigma_maj - mp.sigma_a - mp.sigma_s, 0.f);
+					float pr	 = Tm.x * sigma_maj.x;
+					T_ray *= Tm * sigma_n / pr;
+					pl *= Tm * sigma_maj / pr;
+					pu *= Tm * sigma_n / pr;
+					Spec Tr = T_ray / mean(pu + pl);
+					if (maxCoeff(Tr) < 0.05f) {
+						if (rng.get1D() < 0.75f) T_ray = sp(0);
+						else T_ray = T_ray / 0.25f;
+					}
+					return any(T_ray);
+				});
+				T_ray *= T_maj / T_maj.x;
+				pu *= T_maj / T_maj.x;
+				pl *= T_maj / T_maj.x;
+			}
+			if (visible || !any(T_ray)) break;
+			// ray = intr.spawnRayTo(pLight)
+			V3 off = in_ * kRayEps;
+			if (dot(in_, pLight - ip) < 0.f) off = -off;
+			ro	   = ip + off;
+			rd	   = pLight - ro;
+			medium = mediumAcross(wf.scene.meshes[imesh], in_, rd, aux.x);
+		}
+		if (usedRng) wf.px.rng[pix] = rng.state;
+		if (any(T_ray)) {
+			Spec Ld = ldcs4(wf.shadow.contrib + i), spu = ldcs4(wf.shadow.pu + i), spl = ldcs4(wf.shadow.pl + i);
+			wf.px.L[pix] = Ld * T_ray / mean(spu * pu + spl * pl) + wf.px.L[pix];
+		}
+	}
+}
+
+// 64^3 max-density grid of a dense density grid (initializeMajorantGrid, media.cpp:18-75)
+__global__ void k_build_majorant(const float *__restrict__ density, int rx, int ry, int rz, float3 bmin, float3 bmax, float *majorant) {
+	int index = blockIdx.x * blockDim.x + threadIdx.x;
+	if (index >= kMajRes * kMajRes * kMajRes) return;
+	int c[3] = {index % kMajRes, (index / kMajRes) % kMajRes, index / (kMajRes * kMajRes)}, res[3] = {rx, ry, rz}, n0[3], n1[3];
+	const float lo[3] = {bmin.x, bmin.y, bmin.z}, hi[3] = {bmax.x, bmax.y, bmax.z};
+	for (int k = 0; k < 3; k++) {
+		// medium-space bounds of the cell -> index space; individually rounded so that the integer ranges
+		// (and with them the majorants, hence the number of tracking steps) equal the CPU oracle's
+		float ext = xsub(hi[k], lo[k]);
+		float w0 = xadd(lo[k], xmul(ext, xdiv((float) c[k], (float) kMajRes))), w1 = xadd(lo[k], xmul(ext, xdiv((float) (c[k] + 1), (float) kMajRes)));
+		float i0 = xmul(xdiv(xsub(w0, lo[k]), ext), (float) res[k]), i1 = xmul(xdiv(xsub(w1, lo[k]), ext), (float) res[k]);
+		n0[k] = max(int(xsub(i0, 1.f)), 0), n1[k] = min(int(xadd(i1, 1.f)), res[k] - 1);
+	}
+	float mx = 0;
+	for (int z = n0[2]; z <= n1[2]; z++)
+		for (int y = n0[1]; y <= n1[1]; y++)
+			for (int x = n0[0]; x <= n1[0]; x++) mx = fmaxf(mx, density[x + (size_t) rx * (y + (size_t) ry * z)]);
+	majorant[index] = mx;
+}
+
 // per-sample resolve (integrator.cpp:257-260).  Note the reference does NOT reset L between the
 // samples of one frame, so sample k adds the running sum; kept as is.
 __global__ void k_resolve(const __grid_constant__ Wavefront wf) {
@@ -809,6 +1135,7 @@ __global__ void k_fold_counters(DepthCounters *c, StatTotals *t, int nDepth, int
 	int sc = 0;
 	for (int k = 0; k < MAT_COUNT; k++) sc += dc.nScatter[k];
 	sc += dc.nScatterKilled;
+	if (d == nDepth - 1) dc.nRay = 0; // the queue behind the last traced depth (null-interface re-pushes) is never traced
 	atomicAdd(&t->closest, (unsigned long long) dc.nRay);
 	atomicAdd(&t->shadow, (unsigned long long) dc.nShadow);
 	atomicAdd(&t->scatter, (unsigned long long) sc);

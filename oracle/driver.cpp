@@ -727,7 +727,14 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		Xf x; memcpy(x.m, ld.transform, 48);
 		Xf xi = xfInverse(x);
 		memcpy(l.xformInv, xi.m, 48);
-		if (ld.type == KRR_LIGHT_INFINITE) s->infinite.push_back((int) s->analytic.size());
+		if (ld.type == KRR_LIGHT_INFINITE) {
+			/* InfiniteLight::getObjectData (src/core/light.cpp:28-41) uploads through the TEXTURE constructor
+			 * (light.h:213-216): tint = 1 and the colour comes from the texture; the light's own colour is
+			 * not transferred.  Constant textures only here (L = tint * image.evaluate(uv), light.h:239-241). */
+			l.color[0] = l.color[1] = l.color[2] = 1.f;
+			if (ld.texture.valid) memcpy(l.color, ld.texture.value, 12);
+			s->infinite.push_back((int) s->analytic.size());
+		}
 		s->lights.push_back(LightRef{ld.type, -1, -1, (int) s->analytic.size()});
 		s->analytic.push_back(l);
 	}

@@ -106,8 +106,8 @@ class Oracle:
             self.scene = None
 
     def render(self, cam, w, h, frame_index=1, spp=1, max_depth=10, rr=0.8, nee=True, use_bvh=True, threads=0,
-               capture=None, rows=None, enable_clamp=False, clamp_max=1e3):
-        p = OrcParams(nee=int(nee), enable_medium=1, max_depth=max_depth, enable_clamp=int(enable_clamp), spp=spp, rr=rr,
+               capture=None, rows=None, enable_clamp=False, clamp_max=1e3, enable_medium=True):
+        p = OrcParams(nee=int(nee), enable_medium=int(enable_medium), max_depth=max_depth, enable_clamp=int(enable_clamp), spp=spp, rr=rr,
                       clamp_max=clamp_max, use_bvh=int(use_bvh), threads=threads,
                       row_begin=rows[0] if rows else 0, row_end=rows[1] if rows else 0)
         n = w * h
