@@ -27,7 +27,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define KRR_WFPT_ABI_VERSION 1
+#define KRR_WFPT_ABI_VERSION 2
 
 enum {
 	KRR_OK			  = 0,
@@ -98,13 +98,36 @@ typedef struct KrrMeshDesc {
  * (reference resamples node SRTs to regular steps, src/core/device/optix.cpp:400-471) */
 typedef struct KrrSRT { float s[3]; float q[4]; float t[3]; } KrrSRT;
 
+/* One node of the scene graph ABOVE a mesh instance, for multi-level scenes with motion blur
+ * (OptixSceneMultiLevel::buildIASForNode, reference src/core/device/optix.cpp:472-563): a node is
+ * either a static local transform (the OptixInstance transform of its IAS entry) or, when it is
+ * animated and motion blur is on, an SRT motion transform with keys regularly spaced over
+ * [time_begin, time_end] that REPLACES the local transform (optix.cpp:400-470, 484-486, 540-561).
+ * The object->world transform of an instance at ray time t is the product of its chain,
+ * root first: M(t) = M_root(t) * ... * M_node(t).  Key interpolation follows OptiX SRT motion
+ * transforms: scale and translation linearly, the quaternion linearly and then normalised; time is
+ * clamped to [time_begin, time_end]. */
+typedef struct KrrTransformNodeDesc {
+	int32_t		  parent;		 /* index into transform_nodes, -1 = top of the chain */
+	float		  transform[12]; /* static local transform (used when n_motion_keys < 2) */
+	int32_t		  n_motion_keys; /* >= 2: SRT motion transform */
+	const KrrSRT *motion_keys;
+	float		  time_begin, time_end; /* MotionKeyframes::startTime / endTime */
+} KrrTransformNodeDesc;
+
 /* rt::InstanceData, reference src/core/mesh.h:37-58: mesh pointer + object->world transform
- * (3x4 row-major, the layout of krr::Affine3f, src/core/math/include/krrmath/transform.h:12) */
+ * (3x4 row-major, the layout of krr::Affine3f, src/core/math/include/krrmath/transform.h:12).
+ * `transform` is always the node's GLOBAL transform at the current animation time
+ * (InstanceData::transform, mesh.cpp:61): static instances are traced with it, and lights of
+ * emissive instances use it even when the instance moves, as in the reference (light.h:152-206). */
 typedef struct KrrInstanceDesc {
 	int32_t		  mesh;
 	float		  transform[12];
-	int32_t		  n_motion_keys; /* 0/1 = static; >= 2: keys uniformly spaced over [starttime, endtime] */
+	int32_t		  n_motion_keys; /* single-level shorthand: >= 2 keys uniformly spaced over
+									[options.starttime, options.endtime] = one motion node, no parent */
 	const KrrSRT *motion_keys;
+	int32_t		  transform_node; /* index into KrrSceneDesc::transform_nodes of the node that holds
+									 this mesh instance, or -1 (then `transform` / motion_keys apply) */
 } KrrInstanceDesc;
 
 /* analytic scene lights (point / directional / spot / infinite), reference src/core/light.h:30-259.
@@ -146,6 +169,7 @@ typedef struct KrrSceneDesc {
 	const KrrLightDesc	  *lights;	  int32_t n_lights;
 	const KrrMediumDesc	  *media;	  int32_t n_media;
 	KrrSceneOptions		   options;
+	const KrrTransformNodeDesc *transform_nodes; int32_t n_transform_nodes; /* only read when options.motionblur */
 } KrrSceneDesc;
 
 /* rt::CameraData, reference src/core/camera.h:20-30 */
@@ -294,6 +318,11 @@ int krr_wfpt_debug_eval_light(KrrWfpt *h, const KrrLeafLightQuery *queries_host,
 int krr_wfpt_debug_eval_color(KrrWfpt *h, const float *in8_host, int32_t n, float *out20_host);
 /* CameraData::getRay: in px, py (as floats), camera sample[5] (7 floats); out origin[3], dir[3], time (7 floats) */
 int krr_wfpt_debug_camera_rays(KrrWfpt *h, const KrrCameraData *camera, int32_t width, int32_t height, const float *in7_host, int32_t n, float *out7_host);
+
+/* object->world (12 floats) and world->object (12 floats) of instance instance_ids[i] for a ray that
+ * carries times[i]: what optixGetObjectToWorldTransformMatrix / optixGetWorldToObjectTransformMatrix
+ * report at a hit (getInstanceTransform, src/render/shading.h:70-76), evaluated on the device */
+int krr_wfpt_debug_instance_xf(KrrWfpt *h, const int32_t *instance_ids_host, const float *times_host, int32_t n, float *out24_host);
 
 /* ---- next row: AccumulatePass kernel, src/render/passes/accumulate/accumulate.cu:30-52 ----
  * accum, film: device float4[n_pixels]; film is replaced by the running average. */

@@ -49,8 +49,14 @@ class KrrSRT(C.Structure):
     _fields_ = [("s", F * 3), ("q", F * 4), ("t", F * 3)]
 
 
+class KrrTransformNodeDesc(C.Structure):
+    _fields_ = [("parent", I32), ("transform", F * 12), ("n_motion_keys", I32), ("motion_keys", C.POINTER(KrrSRT)),
+                ("time_begin", F), ("time_end", F)]
+
+
 class KrrInstanceDesc(C.Structure):
-    _fields_ = [("mesh", I32), ("transform", F * 12), ("n_motion_keys", I32), ("motion_keys", C.POINTER(KrrSRT))]
+    _fields_ = [("mesh", I32), ("transform", F * 12), ("n_motion_keys", I32), ("motion_keys", C.POINTER(KrrSRT)),
+                ("transform_node", I32)]
 
 
 class KrrLightDesc(C.Structure):
@@ -70,7 +76,8 @@ class KrrSceneOptions(C.Structure):
 class KrrSceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(KrrMeshDesc)), ("n_meshes", I32), ("instances", C.POINTER(KrrInstanceDesc)), ("n_instances", I32),
                 ("materials", C.POINTER(KrrMaterialDesc)), ("n_materials", I32), ("lights", C.POINTER(KrrLightDesc)), ("n_lights", I32),
-                ("media", C.POINTER(KrrMediumDesc)), ("n_media", I32), ("options", KrrSceneOptions)]
+                ("media", C.POINTER(KrrMediumDesc)), ("n_media", I32), ("options", KrrSceneOptions),
+                ("transform_nodes", C.POINTER(KrrTransformNodeDesc)), ("n_transform_nodes", I32)]
 
 
 class KrrCameraData(C.Structure):
@@ -161,6 +168,7 @@ def load_wfpt():
         "krr_wfpt_debug_eval_light": [P, C.POINTER(KrrLeafLightQuery), I32, C.POINTER(KrrLeafLightResult)],
         "krr_wfpt_debug_eval_color": [P, C.POINTER(F), I32, C.POINTER(F)],
         "krr_wfpt_debug_camera_rays": [P, C.POINTER(KrrCameraData), I32, I32, C.POINTER(F), I32, C.POINTER(F)],
+        "krr_wfpt_debug_instance_xf": [P, C.POINTER(I32), C.POINTER(F), I32, C.POINTER(F)],
         "krr_wfpt_abi_version": [],
     }
     for name, args in sig.items():
@@ -356,6 +364,15 @@ class Wfpt:
             film = np.empty((h, w, 4), dtype=np.float32)
         self._ck(self.lib.krr_wfpt_render_to_host(self.h, film.ctypes.data_as(P), P(stream or 0)), "render_to_host")
         return film
+
+    def instance_xf(self, ids, times):
+        """(n, 2, 12): object->world and world->object of each instance at each ray time, from the device"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        t = np.ascontiguousarray(times, dtype=np.float32)
+        out = np.empty((len(ids), 2, 12), np.float32)
+        self._ck(self.lib.krr_wfpt_debug_instance_xf(self.h, ids.ctypes.data_as(C.POINTER(I32)), t.ctypes.data_as(C.POINTER(F)), len(ids),
+                                                     out.ctypes.data_as(C.POINTER(F))), "debug_instance_xf")
+        return out
 
     def update_instances(self, ids, transforms, stream=None):
         ids = np.ascontiguousarray(ids, dtype=np.int32)

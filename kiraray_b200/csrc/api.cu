@@ -106,7 +106,8 @@ struct KrrWfpt {
 	Buf<AnalyticLightRec> analytic;
 	Buf<MediumRec> media;
 	Buf<float4> texels;
-	Buf<MotionRec> motions;
+	Buf<XformNodeRec> xnodes;
+	float motionW0 = 0.f, motionW1 = 0.f; // ray-time window the TLAS boxes of moving instances currently cover
 	Buf<uint8_t> instFlags;
 	std::vector<InstRec> hInstances;
 	std::vector<MeshRec> hMeshes;
@@ -178,8 +179,9 @@ int allocState(KrrWfpt *h) {
 	for (int a = 0; a < 5; a++) rc |= h->shadowBuf[a].alloc(n);
 	rc |= h->missIdx.alloc(n) | h->hitLightIdx.alloc(n);
 	for (int m = 0; m < MAT_COUNT; m++) rc |= h->scatterIdx[m].alloc(n);
+	if (h->sceneHasMedia || h->scene.hasMotion) rc |= h->shadowAux.alloc(n); // shadow rays carry (medium, time)
 	if (h->sceneHasMedia) { // media queues (mediumSampleQueue / mediumScatterQueue, integrator.cpp:40-44)
-		rc |= h->mediumSampleIdx.alloc(n) | h->hitT.alloc(n) | h->msPixDepth.alloc(n) | h->shadowAux.alloc(n);
+		rc |= h->mediumSampleIdx.alloc(n) | h->hitT.alloc(n) | h->msPixDepth.alloc(n);
 		for (int a = 0; a < 4; a++) rc |= h->msBuf[a].alloc(n);
 	}
 	rc |= h->counters.alloc(kMaxDepthSlots) | h->totals.alloc(1) | h->errorFlags.alloc(4);
@@ -418,7 +420,40 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	std::vector<LightRec> lights;
 	std::vector<TriLightRec> triLights;
 	std::vector<uint8_t> flags(d->n_instances, 0);
-	std::vector<MotionRec> motions;
+	// transform chains (multi-level graph with SRT motion transforms, optix.cpp:400-563); read only when
+	// motion blur is on, exactly like OptixSceneMultiLevel::getMotionKeyframes (optix.cpp:402)
+	std::vector<XformNodeRec> xnodes;
+	std::vector<char> chainMoves;
+	const bool useMotion = d->options.motionblur != 0;
+	const int nGraphNodes = useMotion && d->transform_nodes ? std::max(d->n_transform_nodes, 0) : 0;
+	for (int i = 0; i < nGraphNodes; i++) {
+		const KrrTransformNodeDesc &nd = d->transform_nodes[i];
+		if (nd.parent < -1 || nd.parent >= nGraphNodes || nd.parent == i) return fail(KRR_E_INVALID, "transform node %d: bad parent", i);
+		XformNodeRec r{};
+		r.parent = nd.parent, r.keyOff = 0, r.nKeys = 0;
+		memcpy(r.local.m, nd.transform, 48);
+		r.localInv = xfInverse(r.local);
+		if (nd.n_motion_keys >= 2) {
+			if (!nd.motion_keys) return fail(KRR_E_INVALID, "transform node %d: motion keys missing", i);
+			if (!(nd.time_end > nd.time_begin)) return fail(KRR_E_INVALID, "transform node %d: time_end must be > time_begin", i);
+			r.keyOff = (int32_t) (motionKeys.size() / 10), r.nKeys = nd.n_motion_keys, r.t0 = nd.time_begin, r.t1 = nd.time_end;
+			for (int k = 0; k < nd.n_motion_keys; k++) {
+				const KrrSRT &s = nd.motion_keys[k];
+				motionKeys.insert(motionKeys.end(), s.s, s.s + 3);
+				motionKeys.insert(motionKeys.end(), s.q, s.q + 4);
+				motionKeys.insert(motionKeys.end(), s.t, s.t + 3);
+			}
+		}
+		xnodes.push_back(r);
+	}
+	chainMoves.assign(nGraphNodes, 0);
+	for (int i = 0; i < nGraphNodes; i++) {
+		int depth = 0;
+		for (int p = i; p >= 0; p = xnodes[p].parent) {
+			if (++depth > 64) return fail(KRR_E_INVALID, "transform node %d: chain deeper than 64 (cycle?)", i);
+			if (xnodes[p].nKeys >= 2) chainMoves[i] = 1;
+		}
+	}
 	bool anyMotion = false;
 	for (int i = 0; i < d->n_instances; i++) {
 		const KrrInstanceDesc &in = d->instances[i];
@@ -427,9 +462,17 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 		memcpy(r.xf.m, in.transform, 48);
 		r.inv = xfInverse(r.xf);
 		r.mesh = in.mesh, r.lightBase = -1, r.motion = -1;
-		if (d->options.motionblur && in.n_motion_keys >= 2 && in.motion_keys) {
-			r.motion = (int32_t) motions.size();
-			motions.push_back(MotionRec{(int32_t) (motionKeys.size() / 10), in.n_motion_keys});
+		if (nGraphNodes > 0 && in.transform_node >= nGraphNodes) return fail(KRR_E_INVALID, "instance %d: transform_node out of range", i);
+		if (nGraphNodes > 0 && in.transform_node >= 0) {
+			if (chainMoves[in.transform_node]) r.motion = in.transform_node, anyMotion = true;
+		} else if (useMotion && in.n_motion_keys >= 2 && in.motion_keys) {
+			if (!(d->options.endtime > d->options.starttime)) return fail(KRR_E_INVALID, "motion blur needs options.endtime > options.starttime");
+			r.motion = (int32_t) xnodes.size();
+			XformNodeRec nr{};
+			nr.parent = -1, nr.keyOff = (int32_t) (motionKeys.size() / 10), nr.nKeys = in.n_motion_keys;
+			nr.t0 = d->options.starttime, nr.t1 = d->options.endtime;
+			nr.local = r.xf, nr.localInv = r.inv;
+			xnodes.push_back(nr);
 			for (int k = 0; k < in.n_motion_keys; k++) {
 				const KrrSRT &s = in.motion_keys[k];
 				motionKeys.insert(motionKeys.end(), s.s, s.s + 3);
@@ -501,7 +544,7 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	}
 	int rc = 0;
 	rc |= h->positions.upload(P) | h->normals.upload(N) | h->texcoords.upload(UV) | h->tangents.upload(T) | h->indices.upload(I);
-	rc |= h->densityPool.upload(density) | h->spectrumTables.upload(specTables) | h->motionKeys.upload(motionKeys) | h->motions.upload(motions);
+	rc |= h->densityPool.upload(density) | h->spectrumTables.upload(specTables) | h->motionKeys.upload(motionKeys) | h->xnodes.upload(xnodes);
 	rc |= h->texels.upload(texels) | h->materials.upload(mats) | h->media.upload(media);
 	rc |= h->lights.upload(lights) | h->triLights.upload(triLights) | h->analytic.upload(analytic) | h->infiniteLights.upload(infinite);
 	rc |= h->instFlags.upload(flags);
@@ -510,7 +553,15 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	rc = h->instances.upload(insts);
 	if (rc) return rc;
 	char err[256] = "";
-	if (!h->bvh.build(h->positions.p, h->indices.p, meshes.data(), d->n_meshes, h->instances.p, insts.data(), d->n_instances, nullptr, err))
+	// until the first begin_frame supplies the camera's shutter interval, moving instances are bounded
+	// over the whole animation range
+	MotionWindow mw;
+	if (anyMotion) {
+		mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p;
+		mw.w0 = d->options.starttime, mw.w1 = std::max(d->options.endtime, d->options.starttime);
+	}
+	h->motionW0 = mw.w0, h->motionW1 = mw.w1;
+	if (!h->bvh.build(h->positions.p, h->indices.p, meshes.data(), d->n_meshes, h->instances.p, insts.data(), d->n_instances, mw, nullptr, err))
 		return fail(KRR_E_CUDA, "%s", err);
 	for (int i = 0; i < d->n_meshes; i++) meshes[i].blasRoot = h->bvh.blasRoot(i), meshes[i].triBase = h->bvh.triBase(i);
 	for (int i = 0; i < d->n_instances; i++) insts[i].blasRoot = meshes[insts[i].mesh].blasRoot;
@@ -522,7 +573,7 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	s.meshes = h->meshes.p, s.instances = h->instances.p, s.materials = h->materials.p, s.lights = h->lights.p;
 	s.triLights = h->triLights.p, s.analytic = h->analytic.p, s.infiniteLights = h->infiniteLights.p, s.media = h->media.p;
 	s.densityPool = h->densityPool.p, s.texels = h->texels.p, s.spectrumTables = h->spectrumTables.p;
-	s.motionKeys = h->motionKeys.p, s.motions = h->motions.p;
+	s.motionKeys = h->motionKeys.p, s.xnodes = h->xnodes.p;
 	s.nMeshes = d->n_meshes, s.nInstances = d->n_instances, s.nMaterials = d->n_materials, s.nLights = (int32_t) lights.size();
 	s.nInfinite = (int32_t) infinite.size(), s.nMedia = d->n_media;
 	s.motionStart = d->options.starttime, s.motionEnd = d->options.endtime, s.hasMotion = anyMotion;
@@ -534,7 +585,6 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 				h->densityPool.p + r.majorantOff);
 	CUDA_OK(cudaDeviceSynchronize());
 	if (h->width > 0) { rc = allocState(h); if (rc) return rc; } // media queues depend on the scene
-	if (anyMotion) return fail(KRR_E_UNSUPPORTED, "motion-blur instances are not supported by this build yet");
 	h->haveScene = true;
 	return KRR_OK;
 }
@@ -587,6 +637,20 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 	h->frameIndex = frameIndex;
 	h->cam = makeCamera(c);
 	h->launches = 0;
+	if (h->scene.hasMotion) {
+		// rays of this frame carry times in [shutterOpen, shutterOpen + shutterTime] (camera.h:44): re-fit
+		// the TLAS boxes of the moving instances to that interval when it changed
+		float w0 = c->shutter_open, w1 = c->shutter_open + c->shutter_time;
+		if (w1 < w0) std::swap(w0, w1);
+		if (w0 != h->motionW0 || w1 != h->motionW1) {
+			MotionWindow mw;
+			mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p, mw.w0 = w0, mw.w1 = w1;
+			char err[256] = "";
+			if (!h->bvh.refitTlas(h->instances.p, st, err, &mw)) return fail(KRR_E_CUDA, "%s", err);
+			h->launches += h->bvh.refitLaunches();
+			h->motionW0 = w0, h->motionW1 = w1;
+		}
+	}
 	CUDA_OK(cudaMemsetAsync(h->totals.p, 0, sizeof(StatTotals), st));
 	Wavefront wf = makeWavefront(h, 0);
 	uint32_t seedIndex = (uint32_t) (frameIndex * (uint64_t) h->spp);
@@ -608,10 +672,11 @@ struct StageTimer { // RAII: brackets one launch with events when profiling is o
 	~StageTimer() { if (on) { cudaEventRecord(rec.b, st); h->evRecs.push_back(rec); } }
 };
 template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st) {
-	static int grid = 0;
-	if (!grid) grid = gridFor(h, k_scatter<MT>, 128);
+	static int grid = 0, gridM = 0;
+	if (!grid) grid = gridFor(h, k_scatter<MT, false>, 128), gridM = gridFor(h, k_scatter<MT, true>, 128);
 	StageTimer t(h, KRR_STAGE_SCATTER, st);
-	k_scatter<MT><<<grid, 128, 0, st>>>(wf, depth);
+	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, 128, 0, st>>>(wf, depth);
+	else k_scatter<MT, false><<<grid, 128, 0, st>>>(wf, depth);
 	h->launches++;
 }
 
@@ -629,9 +694,14 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	cudaStream_t st = (cudaStream_t) stream;
 	static int gridCam = 0, gridTrace = 0, gridHit = 0, gridShadow = 0, gridResolve = 0;
 	if (!gridCam) {
-		gridCam = gridFor(h, k_generate_camera_rays, 256), gridTrace = gridFor(h, k_trace_closest, 128);
-		gridHit = gridFor(h, k_handle_hit_miss, 128), gridShadow = gridFor(h, k_trace_shadow, 128), gridResolve = gridFor(h, k_resolve, 256);
+		gridCam = gridFor(h, k_generate_camera_rays, 256), gridTrace = gridFor(h, k_trace_closest<false>, 128);
+		gridHit = gridFor(h, k_handle_hit_miss<false>, 128), gridShadow = gridFor(h, k_trace_shadow<false>, 128), gridResolve = gridFor(h, k_resolve, 256);
 	}
+	// scenes with moving instances run the variants that evaluate SRT chains at the ray's time
+	static int gridTraceM = 0, gridHitM = 0, gridShadowM = 0;
+	const bool motion = h->scene.hasMotion != 0;
+	if (motion && !gridTraceM)
+		gridTraceM = gridFor(h, k_trace_closest<true>, 128), gridHitM = gridFor(h, k_handle_hit_miss<true>, 128), gridShadowM = gridFor(h, k_trace_shadow<true>, 128);
 	static int gridMSample = 0, gridMScatter = 0, gridShadowTr = 0;
 	const bool media = h->enableMedium && h->sceneHasMedia;
 	if (media && !gridMSample) {
@@ -649,7 +719,11 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			const bool cap = h->capSample == sampleId && h->capDepth == depth;
 			if (cap && capture(h, wf, depth, 0, st)) return KRR_E_CUDA;
 			// [2.1] closest hits
-			{ StageTimer t(h, KRR_STAGE_CLOSEST, st); k_trace_closest<<<gridTrace, 128, 0, st>>>(wf, depth); }
+			{
+				StageTimer t(h, KRR_STAGE_CLOSEST, st);
+				if (motion) k_trace_closest<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
+				else k_trace_closest<false><<<gridTrace, 128, 0, st>>>(wf, depth);
+			}
 			h->launches++;
 			// [2.2] medium interactions along the rays that travel inside a medium
 			if (media) {
@@ -658,7 +732,11 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			}
 			if (cap) for (int q = 1; q <= 3; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.3] emitted / environment radiance
-			{ StageTimer t(h, KRR_STAGE_HIT_MISS, st); k_handle_hit_miss<<<gridHit, 128, 0, st>>>(wf, depth); }
+			{
+				StageTimer t(h, KRR_STAGE_HIT_MISS, st);
+				if (motion) k_handle_hit_miss<true><<<gridHitM, 128, 0, st>>>(wf, depth);
+				else k_handle_hit_miss<false><<<gridHit, 128, 0, st>>>(wf, depth);
+			}
 			h->launches++;
 			if (depth == h->maxDepth) break;
 			if (media) {
@@ -676,7 +754,8 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			if (h->nee) {
 				StageTimer t(h, KRR_STAGE_SHADOW, st);
 				if (media) k_trace_shadow_tr<<<gridShadowTr, kTraceBlock, 0, st>>>(wf, depth);
-				else k_trace_shadow<<<gridShadow, 128, 0, st>>>(wf, depth);
+				else if (motion) k_trace_shadow<true><<<gridShadowM, 128, 0, st>>>(wf, depth);
+				else k_trace_shadow<false><<<gridShadow, 128, 0, st>>>(wf, depth);
 				h->launches++;
 			}
 		}
@@ -854,6 +933,16 @@ extern "C" int krr_wfpt_debug_eval_light(KrrWfpt *h, const KrrLeafLightQuery *q,
 	SceneDev sc{};
 	sc.cs = h->cs;
 	return leafRun(q, n, 1, out, 1, [&](const KrrLeafLightQuery *dq, KrrLeafLightResult *dr) { k_leaf_light<<<(n + 63) / 64, 64>>>(dq, dinv.p, n, dr, sc); });
+}
+
+extern "C" int krr_wfpt_debug_instance_xf(KrrWfpt *h, const int32_t *ids, const float *times, int32_t n, float *out) {
+	if (!h || !h->haveScene) return fail(KRR_E_STATE, "set_scene first");
+	if (!ids || !times || !out || n <= 0) return fail(KRR_E_INVALID, "bad argument");
+	for (int i = 0; i < n; i++)
+		if (ids[i] < 0 || ids[i] >= h->scene.nInstances) return fail(KRR_E_INVALID, "instance id out of range");
+	Buf<int32_t> dIds;
+	if (dIds.upload(std::vector<int32_t>(ids, ids + n))) return KRR_E_CUDA;
+	return leafRun(times, n, 1, out, 24, [&](const float *dt, float *dr) { k_leaf_instance_xf<<<(n + 63) / 64, 64>>>(h->scene, dIds.p, dt, n, dr); });
 }
 
 extern "C" int krr_wfpt_debug_eval_color(KrrWfpt *h, const float *in, int32_t n, float *out) {

@@ -42,6 +42,8 @@ struct BvhDev {
 	const int32_t *tlasInst; // instance ids referenced by TLAS leaves
 	int32_t tlasRoot;
 	int32_t nInstances;
+	const XformNodeRec *xnodes; // motion blur: transform chains + SRT key pool (motion.cuh), null otherwise
+	const float *motionKeys;
 };
 
 struct Hit {
@@ -100,12 +102,20 @@ struct TraceSmem {
 
 #define KRR_CSWAP(a, b) { uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
 
-template <bool ANY> struct Traverser {
+// world ray -> object space of a moving instance (kept out of line: static scenes never pay its registers)
+static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float time, V3 o, V3 d, V3 &ro, V3 &rd) {
+	Xf m, inv;
+	chainXf(bvh.xnodes, bvh.motionKeys, node, time, m, inv);
+	ro = xfPointX(inv, o), rd = xfVectorX(inv, d);
+}
+
+// MOTION = false compiles the SRT-chain path out (static scenes keep their register budget)
+template <bool ANY, bool MOTION = true> struct Traverser {
 	// ray
 	V3 o, d;	  // world space
 	V3 ro, rd;	  // current space (world in the TLAS, object space inside a BLAS)
 	V3 idir;
-	float tmax;
+	float tmax, time;
 	Hit best;
 	// control
 	uint32_t cur;
@@ -115,8 +125,8 @@ template <bool ANY> struct Traverser {
 	int overflow;
 
 	KRR_DEV void setIdir() { idir = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z); }
-	KRR_DEV void begin(const BvhDev &bvh, V3 o_, V3 d_, float tmax_) {
-		o = ro = o_, d = rd = d_, tmax = tmax_;
+	KRR_DEV void begin(const BvhDev &bvh, V3 o_, V3 d_, float tmax_, float time_ = 0.f) {
+		o = ro = o_, d = rd = d_, tmax = tmax_, time = time_;
 		setIdir();
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
 		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
@@ -162,10 +172,11 @@ template <bool ANY> struct Traverser {
 		return cur < kLeafFlag ? NODE : ((cur & kInstFlag) ? ENTER : LEAF);
 	}
 	// ---- phase 1: enter an instance (object-space ray; t stays the world parameter) ----
-	KRR_DEV void enterInstance(const InstRec *__restrict__ instances, TraceSmem &sm) {
+	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm) {
 		curInst = (int) (cur & 0x3fffffffu);
 		const InstRec &in = instances[curInst];
-		ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
+		if (MOTION && in.motion >= 0) movingRay(bvh, in.motion, time, o, d, ro, rd); // SRT motion chain at the ray's time
+		else ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
 		setIdir();
 		blasBase = sp;
 		cur		 = (uint32_t) in.blasRoot;
@@ -264,7 +275,7 @@ template <bool ANY> struct Traverser {
 		while (true) {
 			int st = next(sm);
 			if (st == FINISHED) return;
-			if (st == ENTER) { enterInstance(instances, sm); st = NODE; }
+			if (st == ENTER) { enterInstance(bvh, instances, sm); st = NODE; }
 			if (st == NODE) {
 				node(bvh, sm);
 				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
@@ -288,7 +299,7 @@ template <bool ANY> struct Traverser {
 			fin = st == FINISHED;
 		}
 		if (__any_sync(FULL, st == ENTER)) {
-			if (st == ENTER) { enterInstance(instances, sm); st = NODE; }
+			if (st == ENTER) { enterInstance(bvh, instances, sm); st = NODE; }
 		}
 		if (VOTE) {
 			const unsigned mN = __ballot_sync(FULL, st == NODE), mL = __ballot_sync(FULL, st == LEAF);

@@ -59,23 +59,50 @@ __global__ void k_prim_bounds_tris(const float *__restrict__ pos, const int32_t 
 	}
 }
 
-// world box of an instance = transformed 8 corners of its mesh's object-space box
-__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, int n, Aabb *boxes, float *cb) {
+// world box of an instance = transformed 8 corners of its mesh's object-space box.  A MOVING instance
+// (SRT motion chain, motion.cuh) is bounded over the time window [w0, w1] the rays of the frame can
+// carry (the camera's shutter interval): its corners are evaluated at kMotionSamples + 1 times, all
+// positions are united, and the box is padded by the largest second difference of a corner's
+// trajectory -- 8x the deviation of a smooth curve from the chords between consecutive samples.
+constexpr int kMotionSamples = 8;
+__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, int n, Aabb *boxes, float *cb,
+									const XformNodeRec *__restrict__ xnodes, const float *__restrict__ keyPool, float w0, float w1) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const Aabb mb = meshBoxes[inst[i].mesh];
 	Aabb b;
 	for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
-	for (int c = 0; c < 8; c++) {
-		V3 p = mk3(c & 1 ? mb.hi[0] : mb.lo[0], c & 2 ? mb.hi[1] : mb.lo[1], c & 4 ? mb.hi[2] : mb.lo[2]);
-		V3 w = xfPoint(inst[i].xf, p);
+	auto grow = [&](V3 w) {
 		b.lo[0] = fminf(b.lo[0], w.x), b.lo[1] = fminf(b.lo[1], w.y), b.lo[2] = fminf(b.lo[2], w.z);
 		b.hi[0] = fmaxf(b.hi[0], w.x), b.hi[1] = fmaxf(b.hi[1], w.y), b.hi[2] = fmaxf(b.hi[2], w.z);
+	};
+	auto corner = [&](int c) { return mk3(c & 1 ? mb.hi[0] : mb.lo[0], c & 2 ? mb.hi[1] : mb.lo[1], c & 4 ? mb.hi[2] : mb.lo[2]); };
+	float pad = 0.f;
+	if (inst[i].motion >= 0 && xnodes) {
+		const int steps = w1 > w0 ? kMotionSamples : 0;
+		V3 prev[8], prev2[8];
+		for (int j = 0; j <= steps; j++) {
+			float t = steps ? w0 + (w1 - w0) * ((float) j / (float) steps) : w0;
+			if (j == steps) t = w1;
+			Xf m, inv;
+			chainXf(xnodes, keyPool, inst[i].motion, t, m, inv);
+			for (int c = 0; c < 8; c++) {
+				V3 w = xfPoint(m, corner(c));
+				grow(w);
+				if (j >= 2) {
+					V3 dd = prev2[c] - 2.f * prev[c] + w;
+					pad	  = fmaxf(pad, fmaxf(fabsf(dd.x), fmaxf(fabsf(dd.y), fabsf(dd.z))));
+				}
+				prev2[c] = prev[c], prev[c] = w;
+			}
+		}
+	} else {
+		for (int c = 0; c < 8; c++) grow(xfPoint(inst[i].xf, corner(c)));
 	}
 	// rays are intersected in object space with the rounded inverse transform: pad the world box so
 	// that culling stays conservative w.r.t. that round trip
 	for (int k = 0; k < 3; k++) {
-		float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]);
+		float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]) + pad;
 		b.lo[k] -= e, b.hi[k] += e;
 	}
 	boxes[i] = b;
@@ -383,6 +410,7 @@ struct BvhBuilder::Impl {
 	std::vector<int> tlasLevelStart; // node index (relative to the pool) where each TLAS level begins
 	int tlasNodeCount = 0, totalNodes = 0, totalTris = 0, nInstances = 0, nMeshes = 0;
 	std::vector<int32_t> blasRoots, triBases;
+	MotionWindow motion{};
 };
 
 BvhBuilder::BvhBuilder() : m(new Impl) {}
@@ -450,7 +478,8 @@ bool buildTree(const Aabb *boxes, int n, int maxLeaf, Node8 *nodePool, Aabb *bou
 } // namespace
 
 bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes,
-					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, cudaStream_t stream, char *err) {
+					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const MotionWindow &motion, cudaStream_t stream,
+					   char *err) {
 	Impl &b = *m;
 	b.nMeshes = nMeshes, b.nInstances = nInstances;
 	size_t totalTris = 0;
@@ -487,7 +516,9 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	b.totalNodes = nodeCursor;
 	// TLAS over instance world boxes (one instance per leaf child)
 	k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
-	k_prim_bounds_insts<<<(nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, nInstances, b.instBoxes.p, cb.p);
+	k_prim_bounds_insts<<<(nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, nInstances, b.instBoxes.p, cb.p, motion.xnodes,
+																  motion.keys, motion.w0, motion.w1);
+	b.motion = motion;
 	int tlasCursor = 0, tlasPrims = 0, root = 0;
 	b.tlasLevelStart.clear();
 	InstWriter iw{b.tlasInst.p};
@@ -499,10 +530,12 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	return true;
 }
 
-bool BvhBuilder::refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err) {
+bool BvhBuilder::refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err, const MotionWindow *window) {
 	Impl &b = *m;
 	const int T = 128;
-	k_prim_bounds_insts<<<(b.nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.nInstances, b.instBoxes.p, nullptr);
+	if (window) b.motion = *window;
+	k_prim_bounds_insts<<<(b.nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.nInstances, b.instBoxes.p, nullptr,
+																	  b.motion.xnodes, b.motion.keys, b.motion.w0, b.motion.w1);
 	for (int l = (int) b.tlasLevelStart.size() - 2; l >= 0; l--) {
 		int first = b.tlasLevelStart[l], count = b.tlasLevelStart[l + 1] - first;
 		if (count <= 0) continue;
@@ -517,6 +550,7 @@ int BvhBuilder::refitLaunches() const { return 1 + std::max(0, (int) m->tlasLeve
 BvhDev BvhBuilder::device() const {
 	BvhDev d;
 	d.nodes = m->nodes.p, d.tris = m->tris.p, d.tlasInst = m->tlasInst.p, d.tlasRoot = 0, d.nInstances = m->nInstances;
+	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
 	return d;
 }
 int BvhBuilder::blasRoot(int mesh) const { return m->blasRoots[mesh]; }

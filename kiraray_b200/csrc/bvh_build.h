@@ -6,6 +6,13 @@
 
 namespace krr {
 
+// transform chains of the moving instances + the ray-time window their TLAS boxes must cover
+struct MotionWindow {
+	const XformNodeRec *xnodes = nullptr;
+	const float *keys		   = nullptr;
+	float w0 = 0.f, w1 = 0.f;
+};
+
 class BvhBuilder {
 public:
 	BvhBuilder();
@@ -14,9 +21,10 @@ public:
 	// Builds one BLAS per mesh (object space) and a TLAS over the instances.  dPositions / dIndices /
 	// dInstances are device arrays; hMeshes is the host copy of the mesh records (offsets, counts).
 	bool build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes, const InstRec *dInstances,
-			   const InstRec *hInstances, int nInstances, cudaStream_t stream, char *err);
-	// Re-fits the TLAS after instance transforms changed (topology kept); no host synchronisation.
-	bool refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err);
+			   const InstRec *hInstances, int nInstances, const MotionWindow &motion, cudaStream_t stream, char *err);
+	// Re-fits the TLAS after instance transforms (or the motion window) changed; topology kept, no
+	// host synchronisation.
+	bool refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err, const MotionWindow *window = nullptr);
 	int refitLaunches() const;
 	BvhDev device() const;
 	int blasRoot(int mesh) const;

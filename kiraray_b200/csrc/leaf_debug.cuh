@@ -6,6 +6,16 @@
 
 namespace krr {
 
+// object<->world of instance ids[i] at times[i] (24 floats per query: 3x4 transform, 3x4 inverse)
+__global__ void k_leaf_instance_xf(SceneDev sc, const int32_t *ids, const float *times, int n, float *out24) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const InstRec &in = sc.instances[ids[i]];
+	Xf m = in.xf, inv = in.inv;
+	if (in.motion >= 0) chainXf(sc.xnodes, sc.motionKeys, in.motion, times[i], m, inv);
+	for (int k = 0; k < 12; k++) out24[24 * i + k] = m.m[k], out24[24 * i + 12 + k] = inv.m[k];
+}
+
 template <int MT> KRR_DEV void leafBsdf(const ShadingData &sd, const BsdfSetupCtx &ctx, V3 wo, V3 wi, Pcg &rng, KrrLeafBsdfResult &r) {
 	Bsdf<MT> bsdf;
 	bsdf.setup(sd, ctx);

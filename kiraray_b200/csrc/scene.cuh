@@ -5,6 +5,7 @@
 // in multiples of 16 bytes so they load as float4.
 #pragma once
 #include "krr_math.cuh"
+#include "motion.cuh"
 #include "spectrum.cuh"
 
 namespace krr {
@@ -27,7 +28,7 @@ struct InstRec {
 	Xf xf, inv;
 	int32_t mesh;
 	int32_t lightBase; // first triangle light of this instance, -1 = not emissive
-	int32_t motion;	   // index into motion records, -1 = static
+	int32_t motion;	   // moving instance: first node of its transform chain (motion.cuh), -1 = static
 	int32_t blasRoot;  // node index of the mesh's BLAS root (copied from MeshRec for one less hop)
 };
 
@@ -99,10 +100,6 @@ struct MediumRec {
 	float scale;
 };
 
-struct MotionRec { // keyed SRT (KrrSRT) for motion blur
-	int32_t keyOff, nKeys;
-};
-
 struct SceneDev {
 	const float *positions, *normals, *texcoords, *tangents;
 	const int32_t *indices;
@@ -117,8 +114,8 @@ struct SceneDev {
 	const float *densityPool;
 	const float4 *texels;
 	const float *spectrumTables;
-	const float *motionKeys; // KrrSRT as 10 floats
-	const MotionRec *motions;
+	const float *motionKeys;	 // KrrSRT as 10 floats
+	const XformNodeRec *xnodes;	 // transform chains of the moving instances
 	int32_t nMeshes, nInstances, nMaterials, nLights, nInfinite, nMedia;
 	float motionStart, motionEnd;
 	int32_t hasMotion;

@@ -297,7 +297,15 @@ struct WarpWork {
 	}
 };
 
+// object<->world of an instance at ray time `time`: the transform list OptiX reports for a hit
+// (getInstanceTransform, shading.h:70-76) -- static instances use the uploaded matrices, moving ones
+// evaluate their SRT chain (motion.cuh)
+static __device__ __noinline__ void movingXf(const SceneDev &sc, int node, float time, Xf *xf, Xf *inv) {
+	chainXf(sc.xnodes, sc.motionKeys, node, time, *xf, *inv);
+}
+
 // null-material hit: re-queue the ray behind the surface at the same item depth (device.cu:54-58)
+template <bool MOTION = true>
 __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4) {
 	const InstRec &in	= wf.scene.instances[h.inst];
 	const MeshRec &mesh = wf.scene.meshes[in.mesh];
@@ -305,13 +313,19 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	const float *P		= wf.scene.positions + 3 * (size_t) mesh.posOff;
 	V3 p0 = ld3(P + 3 * idx[0]), p1 = ld3(P + 3 * idx[1]), p2 = ld3(P + 3 * idx[2]);
 	float b0 = 1 - h.u - h.v;
-	V3 p = xfPoint(in.xf, b0 * p0 + h.u * p1 + h.v * p2);
+	const Xf *xf = &in.xf, *inv = &in.inv;
+	Xf mxf, minv;
+	if (MOTION && in.motion >= 0) {
+		movingXf(wf.scene, in.motion, o4.w, &mxf, &minv);
+		xf = &mxf, inv = &minv;
+	}
+	V3 p = xfPoint(*xf, b0 * p0 + h.u * p1 + h.v * p2);
 	V3 n;
 	if (mesh.nrmOff >= 0) {
 		const float *N = wf.scene.normals + 3 * (size_t) mesh.nrmOff;
 		n = normalize(b0 * ld3(N + 3 * idx[0]) + h.u * ld3(N + 3 * idx[1]) + h.v * ld3(N + 3 * idx[2]));
 	} else n = normalize(cross(p1 - p0, p2 - p0));
-	n = normalize(xfNormal(in.inv, n));
+	n = normalize(xfNormal(*inv, n));
 	V3 d = mk3(d4);
 	V3 off = n * kRayEps;
 	if (dot(n, d) < 0.f) off = -off;
@@ -327,6 +341,7 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
 }
 
+template <bool MOTION>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
 	__shared__ TraceSmem sm;
 	const RayQueue q	= wf.rays[depth & 1];
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 	const int n			= dc->nRay;
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
-	Traverser<false> tr;
+	Traverser<false, MOTION> tr;
 	int ray = -1; // queue slot this lane is tracing, -1 = idle
 	WarpWork work;
 	work.init(n, &dc->cursorRay);
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 			if (r >= 0) {
 				ray = r;
 				o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
-				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf);
+				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
 			}
 			idle = __ballot_sync(FULL, ray < 0);
 		}
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 		unsigned killed = __ballot_sync(FULL, route == 1 && !alive);
 		if (killed && lane == 0) atomicAdd(&dc->nScatterKilled, __popc(killed));
 		s = warpPushFull(&dc[1].nRay, route == 2);
-		if (s >= 0) requeueThroughNull(wf, q, nq, i, s, h, o4, d4);
+		if (s >= 0) requeueThroughNull<MOTION>(wf, q, nq, i, s, h, o4, d4);
 		if (wf.p.enableMedium) {
 			s = warpPushFull(&dc->nMediumSample, route == 4);
 			if (s >= 0) wf.mediumSampleIdx[s] = i;
@@ -427,7 +442,8 @@ struct SurfaceGeom {
 	int inst, prim, mesh, material, light;
 };
 
-KRR_DEV void rebuildGeometry(const Wavefront &wf, int4 hit, V3 rayDir, SurfaceGeom &g) {
+template <bool MOTION = true>
+KRR_DEV void rebuildGeometry(const Wavefront &wf, int4 hit, V3 rayDir, float time, SurfaceGeom &g) {
 	// getHitInfo (shading.h:78-87) + prepareSurfaceInteraction geometry part (shading.h:121-170)
 	const SceneDev &sc	= wf.scene;
 	g.inst = hit.x, g.prim = hit.y;
@@ -464,10 +480,16 @@ KRR_DEV void rebuildGeometry(const Wavefront &wf, int4 hit, V3 rayDir, SurfaceGe
 		g.uvy = b0 * UV[2 * i0 + 1] + u * UV[2 * i1 + 1] + v * UV[2 * i2 + 1];
 	}
 	g.light = in.lightBase >= 0 ? in.lightBase + g.prim : -1;
-	g.p			= xfPoint(in.xf, g.p);
-	g.n			= normalize(xfNormal(in.inv, g.n));
-	g.tangent	= normalize(xfNormal(in.inv, g.tangent));
-	g.bitangent = normalize(xfNormal(in.inv, g.bitangent));
+	const Xf *xf = &in.xf, *inv = &in.inv;
+	Xf mxf, minv;
+	if (MOTION && in.motion >= 0) {
+		movingXf(sc, in.motion, time, &mxf, &minv);
+		xf = &mxf, inv = &minv;
+	}
+	g.p			= xfPoint(*xf, g.p);
+	g.n			= normalize(xfNormal(*inv, g.n));
+	g.tangent	= normalize(xfNormal(*inv, g.tangent));
+	g.bitangent = normalize(xfNormal(*inv, g.bitangent));
 }
 
 // material part of prepareSurfaceInteraction, shading.h:172-225
@@ -554,6 +576,7 @@ KRR_DEV void evalMaterial(const Wavefront &wf, SurfaceGeom &g, const Wavelengths
 
 // =================================================================================================
 // handleHit + handleMiss (integrator.cpp:78-108)
+template <bool MOTION>
 __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	DepthCounters *dc = wf.counters + depth;
@@ -565,7 +588,7 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 		int4 hit  = wf.hits[i];
 		float4 d4 = ldg4(q.d_medium + i);
 		SurfaceGeom g;
-		rebuildGeometry(wf, hit, mk3(d4), g);
+		rebuildGeometry<MOTION>(wf, hit, mk3(d4), ldg4(q.o_time + i).w, g);
 		float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
 		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
 		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
@@ -616,7 +639,7 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 #ifndef KRR_SCATTER_MINB
 #define KRR_SCATTER_MINB 5
 #endif
-template <int MT>
+template <int MT, bool MOTION>
 __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
@@ -650,7 +673,7 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 			if (alive) {
 				Spec thp = ldcs4(q.thp + i) / wf.p.probRR, pu = ldcs4(q.pu + i);
 				SurfaceGeom g;
-				rebuildGeometry(wf, hit, mk3(d4), g);
+				rebuildGeometry<MOTION>(wf, hit, mk3(d4), time, g);
 				float lam = wf.px.lambda[pix];
 				Wavelengths wl = expandWavelengths(lam);
 				ShadingData sd;
@@ -727,10 +750,8 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 			stcs4(wf.shadow.o_tmax + s, make_float4(so.x, so.y, so.z, 1.f));
 			stcs4(wf.shadow.d_pix + s, make_float4(sdv.x, sdv.y, sdv.z, __int_as_float(pix)));
 			stcs4(wf.shadow.contrib + s, sContrib);
-			if (wf.p.enableMedium) {
-				stcs4(wf.shadow.pu + s, sPu), stcs4(wf.shadow.pl + s, sPl);
-				wf.shadow.aux[s] = make_int2(sMedium, __float_as_int(time));
-			}
+			if (wf.p.enableMedium) stcs4(wf.shadow.pu + s, sPu), stcs4(wf.shadow.pl + s, sPl);
+			if (wf.p.enableMedium || MOTION) wf.shadow.aux[s] = make_int2(sMedium, __float_as_int(time));
 		}
 		s = warpPush(&dc[1].nRay, pushNext);
 		if (s >= 0) {
@@ -748,13 +769,14 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 // =================================================================================================
 // Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean().  Same persistent
 // warp scheme as the closest stage; the ray terminates at the first accepted hit.
+template <bool MOTION>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
 	__shared__ TraceSmem sm;
 	DepthCounters *dc	= wf.counters + depth;
 	const int n			= dc->nShadow;
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
-	Traverser<true> tr;
+	Traverser<true, MOTION> tr;
 	int ray = -1, pix = 0;
 	WarpWork work;
 	work.init(n, &dc->cursorShadow);
@@ -767,7 +789,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 				ray = r;
 				float4 o4 = ldcs4(wf.shadow.o_tmax + r), d4 = ldcs4(wf.shadow.d_pix + r);
 				pix = __float_as_int(d4.w);
-				tr.begin(wf.bvh, mk3(o4), mk3(d4), o4.w);
+				tr.begin(wf.bvh, mk3(o4), mk3(d4), o4.w, MOTION ? __int_as_float(wf.shadow.aux[r].y) : 0.f);
 			}
 			idle = __ballot_sync(FULL, ray < 0);
 		}
@@ -1019,7 +1041,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_co
 		int imesh = -1;
 		while (!(fabsf(rd.x) <= 2 * kRayEps && fabsf(rd.y) <= 2 * kRayEps && fabsf(rd.z) <= 2 * kRayEps)) {
 			Traverser<false> tr;
-			tr.begin(wf.bvh, ro, rd, tMax);
+			tr.begin(wf.bvh, ro, rd, tMax, __int_as_float(aux.y));
 			tr.runToEnd(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
 				if (!(wf.instFlags[inst] & 2)) return true;
 				return !alphaKilled(wf, inst, prim, u, v, ro, rd);
@@ -1028,7 +1050,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_co
 			const bool visible = tr.best.inst < 0;
 			if (!visible) {
 				SurfaceGeom g;
-				rebuildGeometry(wf, make_int4(tr.best.inst, tr.best.prim, __float_as_int(tr.best.u), __float_as_int(tr.best.v)), mk3(d4), g);
+				rebuildGeometry(wf, make_int4(tr.best.inst, tr.best.prim, __float_as_int(tr.best.u), __float_as_int(tr.best.v)), mk3(d4), __int_as_float(aux.y), g);
 				ip = g.p, in_ = g.n, imesh = g.mesh, intrOpaque = g.material >= 0;
 			}
 			if (!visible && intrOpaque) { T_ray = sp(0); break; }
@@ -1184,7 +1206,7 @@ __global__ void k_capture(const __grid_constant__ Wavefront wf, int depth, int q
 			fromRay(q, i);
 			// ScatterRayWorkItem carries the prepared interaction: report ITS BSDF type (shared.h:46-73)
 			SurfaceGeom g;
-			rebuildGeometry(wf, wf.hits[i], mk3(q.d_medium[i]), g);
+			rebuildGeometry(wf, wf.hits[i], mk3(q.d_medium[i]), q.o_time[i].w, g);
 			Wavelengths wl = expandWavelengths(wf.px.lambda[r.x - wf.p.pixelBegin]);
 			ShadingData sd;
 			bool term;

@@ -174,6 +174,7 @@ const KrrSceneDesc &Scene::desc() {
 		memcpy(d.transform, instances[i].transform, 48);
 		d.n_motion_keys = (int32_t) instances[i].motionKeys.size();
 		d.motion_keys	= instances[i].motionKeys.empty() ? nullptr : instances[i].motionKeys.data();
+		d.transform_node = -1;
 	}
 	mMaterialDescs.resize(materials.size());
 	for (size_t i = 0; i < materials.size(); i++) {

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from .binding import (F, I32, KrrInstanceDesc, KrrLightDesc, KrrMaterialDesc, KrrMediumDesc, KrrMeshDesc, KrrSceneDesc,
-                      KrrSRT)
+                      KrrSRT, KrrTransformNodeDesc)
 
 SEED = 7272
 IDENTITY = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
@@ -25,7 +25,7 @@ class SceneBuilder:
     stay valid as long as this object lives."""
 
     def __init__(self):
-        self.meshes, self.instances, self.materials, self.lights, self.media = [], [], [], [], []
+        self.meshes, self.instances, self.materials, self.lights, self.media, self.nodes = [], [], [], [], [], []
         self.options = dict(animated=0, multilevel=0, motionblur=0, starttime=0.0, endtime=1.0)
         self._keep = []
 
@@ -57,10 +57,28 @@ class SceneBuilder:
         self.meshes.append(m)
         return len(self.meshes) - 1
 
-    def add_instance(self, mesh, transform=IDENTITY, motion_keys=None):
-        """motion_keys: (K, 10) array of SRT keys (scale xyz, quaternion xyzw, translation xyz)."""
+    def add_transform_node(self, parent=-1, transform=IDENTITY, motion_keys=None, time_begin=0.0, time_end=1.0):
+        """One scene-graph node above mesh instances: a static local transform, or (motion_keys given, (K, 10)
+        SRT keys regularly spaced over [time_begin, time_end]) an SRT motion transform replacing it."""
+        n = KrrTransformNodeDesc()
+        n.parent = parent
+        n.transform = (F * 12)(*np.asarray(transform, np.float32).ravel())
+        n.time_begin, n.time_end = time_begin, time_end
+        if motion_keys is not None:
+            k = np.ascontiguousarray(motion_keys, np.float32).reshape(-1, 10)
+            self._keep.append(k)
+            n.n_motion_keys = len(k)
+            n.motion_keys = k.ctypes.data_as(C.POINTER(KrrSRT))
+        self.nodes.append(n)
+        return len(self.nodes) - 1
+
+    def add_instance(self, mesh, transform=IDENTITY, motion_keys=None, transform_node=-1):
+        """motion_keys: (K, 10) array of SRT keys (scale xyz, quaternion xyzw, translation xyz); transform_node:
+        the node (add_transform_node) holding this instance -- `transform` must then be the chain's product at
+        the current animation time."""
         inst = KrrInstanceDesc()
         inst.mesh = mesh
+        inst.transform_node = transform_node
         inst.transform = (F * 12)(*np.asarray(transform, np.float32).ravel())
         if motion_keys is not None:
             k = np.ascontiguousarray(motion_keys, np.float32).reshape(-1, 10)
@@ -106,6 +124,7 @@ class SceneBuilder:
         d.materials, d.n_materials = arr(self.materials, KrrMaterialDesc), len(self.materials)
         d.lights, d.n_lights = arr(self.lights, KrrLightDesc), len(self.lights)
         d.media, d.n_media = arr(self.media, KrrMediumDesc), len(self.media)
+        d.transform_nodes, d.n_transform_nodes = arr(self.nodes, KrrTransformNodeDesc), len(self.nodes)
         for k, v in self.options.items():
             setattr(d.options, k, v)
         self.desc = d
@@ -216,12 +235,33 @@ def tessellated_scene(n_objects=200, tris_per_object=100_000, n_emissive=1000, s
     return b
 
 
-def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100, motion=True, seed=SEED, n_keys=2):
+def srt_lerp(keys, time, t0=0.0, t1=1.0):
+    """OptiX SRT key interpolation (float64 restatement of kiraray_b200/csrc/motion.cuh srtNodeXf): time clamped,
+    components linear, quaternion normalised afterwards."""
+    keys = np.asarray(keys, np.float64)
+    n = len(keys)
+    u = min(max((time - t0) / (t1 - t0), 0.0), 1.0) * (n - 1)
+    k = min(int(u), n - 2)
+    v = keys[k] + (u - k) * (keys[k + 1] - keys[k])
+    v[3:7] /= np.linalg.norm(v[3:7])
+    return v
+
+
+def mat_mul(a, b):
+    """product of two 3x4 row-major affine transforms given as 12 floats"""
+    A, B = np.vstack([np.reshape(a, (3, 4)), [0, 0, 0, 1]]), np.vstack([np.reshape(b, (3, 4)), [0, 0, 0, 1]])
+    return (A @ B)[:3].astype(np.float32).ravel()
+
+
+def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100, motion=True, seed=SEED, n_keys=2, time=0.0):
     """BASELINE.json config 5: `n_groups * per_group` instances of `n_blas` BLASes arranged as a two-level
-    graph (group transform x instance transform, flattened to world transforms as the reference's scene
-    graph update does), every instance with a `n_keys`-key SRT motion (group motion composed with its
-    own), a floor and an emissive ceiling quad.  Returns (builder, keys) where keys[i] is the (K, 10)
-    SRT key array of instance i (static transform = key 0)."""
+    graph: every GROUP node and every INSTANCE node under it carries its own `n_keys`-key SRT animation over
+    [0, 1] (the reference wraps each animated node in an SRT motion transform, optix.cpp:400-563), plus a
+    static floor and an emissive ceiling quad.  With motion=True the chains are passed as transform nodes
+    and motion blur is on; the instances' `transform` is always the chain evaluated at `time` (what the
+    scene-graph update of the reference would have produced).  Returns (builder, info) with
+    info["group_keys"][g] / info["inst_keys"][i] the (K, 10) SRT keys and info["world"](i, t) the 12-float
+    object->world transform of instance i at time t."""
     rng = np.random.Generator(np.random.PCG64(seed))
     b = SceneBuilder()
     nv = max(4, int(round(np.sqrt(tris_per_blas / 4))))
@@ -233,34 +273,46 @@ def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100
         meshes.append(b.add_mesh(p, idx, n, mat))
     g = int(np.ceil(np.sqrt(n_groups)))
     s = int(np.ceil(per_group ** (1 / 3)))
-    all_keys = []
+    cell = 8 / g
+
+    def animated_keys(scale, center, spin, drift):
+        q0 = rng.normal(size=4)
+        q0 /= np.linalg.norm(q0)
+        dq, vel = rng.normal(size=4) * spin, rng.normal(size=3) * drift
+        ks = []
+        for k in range(n_keys):
+            a = k / max(n_keys - 1, 1)
+            q = q0 + a * dq
+            ks.append(np.concatenate([[scale] * 3, q / np.linalg.norm(q), center + a * vel]))
+        return np.array(ks, np.float32)
+
+    group_keys, inst_keys, inst_group = [], [], []
     for gi in range(n_groups):
-        gc = np.array([(gi % g) / g * 8 - 4, 0.0, (gi // g) / g * 8 - 4])
-        gvel = rng.normal(size=3) * 0.15
+        gc = np.array([(gi % g) / g * 8 - 4 + cell / 2, 0.0, (gi // g) / g * 8 - 4 + cell / 2])
+        gk = animated_keys(1.0, gc, 0.08, 0.15)
+        group_keys.append(gk)
+        gnode = b.add_transform_node(-1, srt_to_mat(srt_lerp(gk, time)), gk if motion else None) if motion else -1
         for ii in range(per_group):
-            lc = np.array([ii % s, (ii // s) % s, ii // (s * s)]) / s * (8 / g) * 0.9
-            scale = (8 / g) / s * 0.35 * rng.uniform(0.7, 1.0)
-            q0 = rng.normal(size=4)
-            q0 /= np.linalg.norm(q0)
-            dq = rng.normal(size=4) * 0.15
-            vel = gvel + rng.normal(size=3) * 0.05
-            keys = []
-            for k in range(n_keys):
-                a = k / max(n_keys - 1, 1)
-                q = q0 + a * dq
-                keys.append(np.concatenate([[scale] * 3, q / np.linalg.norm(q), gc + lc + a * vel]))
-            keys = np.array(keys, np.float32)
-            all_keys.append(keys)
-            b.add_instance(meshes[(gi * per_group + ii) % n_blas], srt_to_mat(keys[0]), keys if motion else None)
+            lc = (np.array([ii % s, (ii // s) % s, ii // (s * s)]) / s - 0.5 + 0.5 / s) * cell * 0.9
+            ik = animated_keys(cell / s * 0.35 * rng.uniform(0.7, 1.0), lc, 0.15, 0.05)
+            inst_keys.append(ik)
+            inst_group.append(gi)
+            world = mat_mul(srt_to_mat(srt_lerp(gk, time)), srt_to_mat(srt_lerp(ik, time)))
+            node = b.add_transform_node(gnode, srt_to_mat(srt_lerp(ik, time)), ik) if motion else -1
+            b.add_instance(meshes[(gi * per_group + ii) % n_blas], world, transform_node=node)
     floor = b.add_material(diffuse=(0.6, 0.6, 0.6), roughness=0.9)
-    p, n, idx = quad((-6, -0.6, -6), (0, 0, 12), (12, 0, 0))
+    p, n, idx = quad((-6, -0.9, -6), (0, 0, 12), (12, 0, 0))
     b.add_instance(b.add_mesh(p, idx, n, floor))
     light = b.add_material(diffuse=(0, 0, 0), emissive=(17, 12, 4))
     p, n, idx = quad((-3, 4.0, -3), (6, 0, 0), (0, 0, 6))
     b.add_instance(b.add_mesh(p, idx, n, light))
     if motion:
-        b.options.update(motionblur=1, starttime=0.0, endtime=1.0)
-    return b, all_keys
+        b.options.update(motionblur=1, multilevel=1, starttime=0.0, endtime=1.0)
+
+    def world(i, t):
+        return mat_mul(srt_to_mat(srt_lerp(group_keys[inst_group[i]], t)), srt_to_mat(srt_lerp(inst_keys[i], t)))
+
+    return b, dict(group_keys=group_keys, inst_keys=inst_keys, inst_group=inst_group, world=world, n_moving=len(inst_keys))
 
 
 def look_at_camera(eye, target, aspect, focal_length=21.0, up=(0, 1, 0), shutter_open=0.0, shutter_time=0.0, lens_radius=0.0, focal_distance=10.0):

@@ -109,6 +109,72 @@ Xf xfInverse(const Xf &t) {
 	return o;
 }
 
+/* ---- transform chains with SRT motion keys (motion blur over a multi-level scene graph) --------
+ * The reference wraps animated nodes in OptixSRTMotionTransform objects (optix.cpp:400-563) and OptiX
+ * evaluates the transform list at the ray's time; OptiX is closed, so this build states the
+ * evaluation itself (DESIGN.md "Motion spec"; the kernels in kiraray_b200/csrc/motion.cuh perform the
+ * same operations in the same order):
+ *   time clamped to [t0,t1]; u = (time-t0)/(t1-t0)*(n-1); k = min(int(u), n-2); f = u-k;
+ *   every SRT component a + f*(b-a); quaternion divided by its norm;
+ *   node M = T*R*S, M^-1 = S^-1 * R^T * T^-1; chain M = M_root*...*M_leaf, M^-1 in reverse order. */
+struct XNode {
+	int parent = -1, nKeys = 0;
+	std::vector<float> keys; /* 10 floats per key: s[3], q[4] (x,y,z,w), t[3] */
+	float t0 = 0, t1 = 1;
+	Xf local, localInv;
+};
+Xf xfMul(const Xf &a, const Xf &b) {
+	Xf c;
+	for (int r = 0; r < 3; r++)
+		for (int k = 0; k < 4; k++) {
+			float v = a.m[r * 4] * b.m[k];
+			v = v + a.m[r * 4 + 1] * b.m[4 + k];
+			v = v + a.m[r * 4 + 2] * b.m[8 + k];
+			c.m[r * 4 + k] = k == 3 ? v + a.m[r * 4 + 3] : v;
+		}
+	return c;
+}
+void nodeXf(const XNode &nd, float time, Xf &m, Xf &inv) {
+	if (nd.nKeys < 2) { m = nd.local, inv = nd.localInv; return; }
+	int n = nd.nKeys, k = 0;
+	float f = 0.f;
+	if (time >= nd.t1) k = n - 2, f = 1.f;
+	else if (time > nd.t0) {
+		float u = ((time - nd.t0) / (nd.t1 - nd.t0)) * (float) (n - 1);
+		k = (int) u;
+		if (k > n - 2) k = n - 2;
+		f = u - (float) k;
+	}
+	const float *a = &nd.keys[10 * k], *b = a + 10;
+	float v[10];
+	for (int i = 0; i < 10; i++) { float d = b[i] - a[i]; d = f * d; v[i] = a[i] + d; }
+	float l0 = v[3] * v[3], l1 = v[4] * v[4], l2 = v[5] * v[5], l3 = v[6] * v[6];
+	float len = std::sqrt((l0 + l1) + (l2 + l3));
+	float x = v[3] / len, y = v[4] / len, z = v[5] / len, w = v[6] / len;
+	float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+	float R[9] = {1.f - 2.f * (yy + zz), 2.f * (xy - wz), 2.f * (xz + wy),
+				  2.f * (xy + wz), 1.f - 2.f * (xx + zz), 2.f * (yz - wx),
+				  2.f * (xz - wy), 2.f * (yz + wx), 1.f - 2.f * (xx + yy)};
+	for (int r = 0; r < 3; r++) {
+		for (int c = 0; c < 3; c++) m.m[r * 4 + c] = R[r * 3 + c] * v[c], inv.m[r * 4 + c] = R[c * 3 + r] / v[r];
+		m.m[r * 4 + 3] = v[7 + r];
+	}
+	for (int r = 0; r < 3; r++) {
+		float t = inv.m[r * 4] * v[7];
+		t = t + inv.m[r * 4 + 1] * v[8];
+		t = t + inv.m[r * 4 + 2] * v[9];
+		inv.m[r * 4 + 3] = -t;
+	}
+}
+void chainXf(const std::vector<XNode> &nodes, int node, float time, Xf &m, Xf &inv) {
+	nodeXf(nodes[node], time, m, inv);
+	for (int p = nodes[node].parent; p >= 0; p = nodes[p].parent) {
+		Xf pm, pinv;
+		nodeXf(nodes[p], time, pm, pinv);
+		m = xfMul(pm, m), inv = xfMul(inv, pinv);
+	}
+}
+
 /* ---- scene ---- */
 struct Mesh {
 	std::vector<V3> P, N, T;
@@ -122,6 +188,7 @@ struct Instance {
 	int mesh;
 	Xf xf, inv;
 	int lightBase; /* index of this instance's first triangle light in Scene::lights, -1 = none */
+	int motion = -1; /* moving instance: first node of its transform chain in OrcScene::xnodes */
 };
 struct LightRef {
 	int type;	 /* KRR_LIGHT_* */
@@ -151,6 +218,14 @@ struct OrcScene {
 	std::vector<OlLight> analytic;
 	std::vector<int> infinite; /* indices into analytic */
 	std::vector<MediumData> media;
+	std::vector<XNode> xnodes;
+	/* object<->world of an instance for a ray that carries `time` (getInstanceTransform, shading.h:70-76) */
+	void instanceXf(int inst, float time, Xf &m, Xf &inv) const {
+		const Instance &in = instances[inst];
+		if (in.motion >= 0) chainXf(xnodes, in.motion, time, m, inv);
+		else m = in.xf, inv = in.inv;
+	}
+	std::vector<int> movingInstances; /* not in the BVH: always tested */
 	/* flattened world-independent primitive list for the BVH: (instance, prim) in object space */
 	struct Prim { int inst, prim; };
 	std::vector<Prim> prims;
@@ -193,10 +268,15 @@ inline bool better(float t, int inst, int prim, const Hit &h) {
 	return prim < h.prim;
 }
 
-void testPrim(const OrcScene &s, int ii, int pi, V3 o, V3 d, float tmax, Hit &best) {
+void testPrim(const OrcScene &s, int ii, int pi, V3 o, V3 d, float tmax, float time, Hit &best) {
 	const Instance &in = s.instances[ii];
 	const Mesh &m	   = s.meshes[in.mesh];
-	V3 oo = xfPoint(in.inv, o), dd = xfVector(in.inv, d);
+	V3 oo, dd;
+	if (in.motion >= 0) {
+		Xf xf, inv;
+		chainXf(s.xnodes, in.motion, time, xf, inv);
+		oo = xfPoint(inv, o), dd = xfVector(inv, d);
+	} else oo = xfPoint(in.inv, o), dd = xfVector(in.inv, d);
 	const int32_t *idx = &m.I[3 * pi];
 	float t, u, v;
 	if (triIntersect(oo, dd, m.P[idx[0]], m.P[idx[1]], m.P[idx[2]], tmax, t, u, v))
@@ -265,18 +345,26 @@ inline bool boxHit(const BvhNode &n, V3 o, V3 invd, float tmax) {
 
 /* closest hit over the whole scene; `skipNull`/anyhit variants below */
 template <typename Accept>
-Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, Accept accept) {
+Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, float time, Accept accept) {
 	Hit best;
 	if (!useBvh || s.bvh.empty()) {
 		for (int ii = 0; ii < (int) s.instances.size(); ii++) {
 			int nt = s.meshes[s.instances[ii].mesh].ntri();
 			for (int pi = 0; pi < nt; pi++) {
 				Hit h;
-				testPrim(s, ii, pi, o, d, best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), h);
+				testPrim(s, ii, pi, o, d, best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), time, h);
 				if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
 			}
 		}
 		return best;
+	}
+	for (int ii : s.movingInstances) { /* moving instances are kept out of the (static) BVH */
+		int nt = s.meshes[s.instances[ii].mesh].ntri();
+		for (int pi = 0; pi < nt; pi++) {
+			Hit h;
+			testPrim(s, ii, pi, o, d, best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), time, h);
+			if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
+		}
 	}
 	V3 invd = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
 	int stack[128], sp = 0;
@@ -289,7 +377,7 @@ Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, Accept 
 			for (int i = n.first; i < n.first + n.count; i++) {
 				Hit h;
 				testPrim(s, s.bvhPrims[i].inst, s.bvhPrims[i].prim, o, d,
-						 best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), h);
+						 best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), time, h);
 				if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
 			}
 		} else {
@@ -373,11 +461,13 @@ void prepareInteraction(const OrcScene &s, const Hit &h, V3 rayDir, float rayTim
 			it.uv[k] = b[0] * m.UV[2 * v[0] + k] + b[1] * m.UV[2 * v[1] + k] + b[2] * m.UV[2 * v[2] + k];
 	it.light	= in.lightBase >= 0 ? in.lightBase + h.prim : -1;
 	it.material = m.material;
-	/* object -> world */
-	it.p		 = xfPoint(in.xf, it.p);
-	it.n		 = normalize(xfNormal(in.inv, it.n));
-	it.tangent	 = normalize(xfNormal(in.inv, it.tangent));
-	it.bitangent = normalize(xfNormal(in.inv, it.bitangent));
+	/* object -> world, with the transform list evaluated at the ray's time */
+	Xf ixf, iinv;
+	s.instanceXf(h.inst, rayTime, ixf, iinv);
+	it.p		 = xfPoint(ixf, it.p);
+	it.n		 = normalize(xfNormal(iinv, it.n));
+	it.tangent	 = normalize(xfNormal(iinv, it.tangent));
+	it.bitangent = normalize(xfNormal(iinv, it.bitangent));
 	if (it.material < 0) return;
 
 	const KrrMaterialDesc &mat = s.materials[it.material];
@@ -677,6 +767,12 @@ extern "C" int orc_intersect_triangle(const float o[3], const float d[3], const 
 	return triIntersect(mk(o), mk(d), mk(v0), mk(v1), mk(v2), tmax, *t, *u, *v) ? 1 : 0;
 }
 
+extern "C" void orc_instance_xf(const OrcScene *s, int32_t inst, float time, float m[12], float inv[12]) {
+	Xf a, b;
+	s->instanceXf(inst, time, a, b);
+	memcpy(m, a.m, 48), memcpy(inv, b.m, 48);
+}
+
 extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 	ol_init();
 	OrcScene *s = new OrcScene();
@@ -701,6 +797,38 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		in.inv		 = xfInverse(in.xf);
 		in.lightBase = -1;
 		s->instances.push_back(in);
+	}
+	/* transform chains: read only when motion blur is on (optix.cpp:402) */
+	if (d->options.motionblur) {
+		int nGraph = d->transform_nodes ? std::max(d->n_transform_nodes, 0) : 0;
+		for (int i = 0; i < nGraph; i++) {
+			const KrrTransformNodeDesc &nd = d->transform_nodes[i];
+			XNode x;
+			x.parent = nd.parent;
+			memcpy(x.local.m, nd.transform, 48);
+			x.localInv = xfInverse(x.local);
+			if (nd.n_motion_keys >= 2) {
+				x.nKeys = nd.n_motion_keys, x.t0 = nd.time_begin, x.t1 = nd.time_end;
+				x.keys.assign((const float *) nd.motion_keys, (const float *) nd.motion_keys + 10 * (size_t) nd.n_motion_keys);
+			}
+			s->xnodes.push_back(std::move(x));
+		}
+		for (int i = 0; i < d->n_instances; i++) {
+			const KrrInstanceDesc &id = d->instances[i];
+			if (nGraph > 0 && id.transform_node >= 0) {
+				bool moves = false;
+				for (int p = id.transform_node; p >= 0; p = s->xnodes[p].parent) moves |= s->xnodes[p].nKeys >= 2;
+				if (moves) s->instances[i].motion = id.transform_node;
+			} else if (id.n_motion_keys >= 2 && id.motion_keys) {
+				XNode x;
+				x.nKeys = id.n_motion_keys, x.t0 = d->options.starttime, x.t1 = d->options.endtime;
+				x.keys.assign((const float *) id.motion_keys, (const float *) id.motion_keys + 10 * (size_t) id.n_motion_keys);
+				x.local = s->instances[i].xf, x.localInv = s->instances[i].inv;
+				s->instances[i].motion = (int) s->xnodes.size();
+				s->xnodes.push_back(std::move(x));
+			}
+			if (s->instances[i].motion >= 0) s->movingInstances.push_back(i);
+		}
 	}
 	/* uploadSceneLightData, device/scene.cpp:91-145: mesh lights first (instance order), then scene lights */
 	for (int i = 0; i < (int) s->instances.size(); i++) {
@@ -752,8 +880,10 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		}
 		s->media.push_back(std::move(m));
 	}
-	for (int i = 0; i < (int) s->instances.size(); i++)
+	for (int i = 0; i < (int) s->instances.size(); i++) {
+		if (s->instances[i].motion >= 0) continue;
 		for (int t = 0; t < s->meshes[s->instances[i].mesh].ntri(); t++) s->bvhPrims.push_back({i, t});
+	}
 	if (!s->bvhPrims.empty()) buildBvh(*s, 0, (int) s->bvhPrims.size());
 	return s;
 }
@@ -833,7 +963,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 				if (loopDepth < KRR_MAX_DEPTH_STATS) st_.shadowByDepth[loopDepth]++;
 				if (capD) cap.push(4, pixelId, depth, 0, auxLight);
 				if (!enableMedium) {
-					Hit sh = traceClosest(s, useBvh, so, sdir, 1.f, [&](const Hit &c) {
+					Hit sh = traceClosest(s, useBvh, so, sdir, 1.f, rtime, [&](const Hit &c) {
 						/* __anyhit__Shadow: ignore null-material and alpha-killed hits */
 						if (s.meshes[s.instances[c.inst].mesh].material < 0) return false;
 						return !alphaKilled(s, c, so, sdir);
@@ -852,7 +982,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 				sit.material = -1; /* SurfaceInteraction intr = {} */
 				auto isZeroV = [](V3 v, float prec) { return std::fabs(v.x) <= prec && std::fabs(v.y) <= prec && std::fabs(v.z) <= prec; };
 				while (!isZeroV(rd_, 1e-4f * 2)) {
-					Hit sh = traceClosest(s, useBvh, ro_, rd_, tMax, alphaAccept(ro_, rd_));
+					Hit sh = traceClosest(s, useBvh, ro_, rd_, tMax, rtime, alphaAccept(ro_, rd_));
 					bool visible = sh.inst < 0;
 					if (!visible) {
 						prepareInteraction(s, sh, srD, rtime, lambda, lpdf, sit);
@@ -895,7 +1025,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 				/* [2.1] traceClosest: device.cu:43-81 */
 				st_.closest++;
 				if (loopDepth < KRR_MAX_DEPTH_STATS) st_.closestByDepth[loopDepth]++;
-				Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(), alphaAccept(rayO, rayD));
+				Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(), rtime, alphaAccept(rayO, rayD));
 				if (loopDepth == 0) fhInst = h.inst, fhPrim = h.prim;
 				alive = false; /* the ray item is consumed */
 				bool haveScatter = false, haveHitLight = false, haveMiss = false, haveMediumScatter = false;

@@ -41,6 +41,9 @@ double orc_render(const OrcScene *s, const OrcParams *p, const KrrCameraData *ca
 				  float *lambda, float *camera_sample, KrrStats *stats, int32_t capture_sample,
 				  int32_t capture_depth, int32_t *cap_items[6], int32_t cap_counts[6]);
 
+/* object->world / world->object of an instance for a ray carrying `time` (the motion spec) */
+void orc_instance_xf(const OrcScene *s, int32_t inst, float time, float m[12], float inv[12]);
+
 /* the build's own ray/triangle routine, exposed so tests can compare it bit-for-bit with the GPU's:
  * returns 1 on hit and writes t,u,v */
 int orc_intersect_triangle(const float o[3], const float d[3], const float v0[3], const float v1[3],

@@ -84,6 +84,7 @@ def load(kind="reference"):
     lib.orc_render.restype = C.c_double
     lib.orc_render.argtypes = [P, C.POINTER(OrcParams), C.POINTER(KrrCameraData), I32, I32, U64, P, P, P, P, P,
                                C.POINTER(KrrStats), I32, I32, C.POINTER(P), C.POINTER(I32)]
+    lib.orc_instance_xf.argtypes = [P, I32, F, C.POINTER(F), C.POINTER(F)]
     lib.orc_intersect_triangle.argtypes = [C.POINTER(F)] * 5 + [F] + [C.POINTER(F)] * 3
     lib.ol_init()
     _libs[kind] = lib
@@ -104,6 +105,11 @@ class Oracle:
         if self.scene:
             self.lib.orc_scene_destroy(self.scene)
             self.scene = None
+
+    def instance_xf(self, inst, time):
+        m, inv = (F * 12)(), (F * 12)()
+        self.lib.orc_instance_xf(self.scene, inst, time, m, inv)
+        return np.array(m, np.float32), np.array(inv, np.float32)
 
     def render(self, cam, w, h, frame_index=1, spp=1, max_depth=10, rr=0.8, nee=True, use_bvh=True, threads=0,
                capture=None, rows=None, enable_clamp=False, clamp_max=1e3, enable_medium=True):

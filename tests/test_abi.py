@@ -25,7 +25,7 @@ def test_wfpt_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"libkrr_wfpt.so does not export {n}"
-    assert lib.krr_wfpt_abi_version() == 1
+    assert lib.krr_wfpt_abi_version() == 2
 
 
 def test_host_library_exports_every_declared_symbol():
@@ -43,7 +43,7 @@ def test_only_the_c_abi_is_exported():
 
 
 def test_ctypes_struct_layout_matches_header(tmp_path):
-    names = ["KrrTextureDesc", "KrrSpectrumDesc", "KrrMaterialDesc", "KrrMeshDesc", "KrrSRT", "KrrInstanceDesc", "KrrLightDesc",
+    names = ["KrrTextureDesc", "KrrSpectrumDesc", "KrrMaterialDesc", "KrrMeshDesc", "KrrSRT", "KrrTransformNodeDesc", "KrrInstanceDesc", "KrrLightDesc",
              "KrrMediumDesc", "KrrSceneOptions", "KrrSceneDesc", "KrrCameraData", "KrrColorSpaceData", "KrrStats"]
     src = tmp_path / "probe.c"
     src.write_text('#include <stdio.h>\n#include "krr_wfpt.h"\nint main(void){' +

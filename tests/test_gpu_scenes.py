@@ -46,7 +46,7 @@ def test_tessellated_scene_first_hits_counts_and_radiance():
 
 
 def test_instanced_scene_and_tlas_refit():
-    b, keys = scenes.instanced_scene(n_blas=4, tris_per_blas=1500, n_groups=9, per_group=12, motion=False)
+    b, info = scenes.instanced_scene(n_blas=4, tris_per_blas=1500, n_groups=9, per_group=12, motion=False)
     desc = b.build()
     w = h = 96
     cam = scenes.look_at_camera((0.5, 3.0, 9.0), (0, 0, 0), 1.0)
@@ -55,8 +55,8 @@ def test_instanced_scene_and_tlas_refit():
     assert np.array_equal(inst, ref["first_hits"][:, 0]) and np.array_equal(prim, ref["first_hits"][:, 1])
     assert gpu.stats()["tlas_nodes"] >= len(b.instances) // 8
     # animate: move every instance to its second key (Scene::update -> updateAccelStructure, optix.cpp:618-643)
-    ids = np.arange(len(keys), dtype=np.int32)
-    xf = np.stack([scenes.srt_to_mat(k[1]) for k in keys])
+    ids = np.arange(info["n_moving"], dtype=np.int32)
+    xf = np.stack([info["world"](i, 1.0) for i in ids])
     gpu.update_instances(ids, xf)
     gpu.begin_frame(1, cam)
     gpu.render_to_host()
@@ -70,7 +70,7 @@ def test_instanced_scene_and_tlas_refit():
     assert not np.array_equal(inst2, inst), "the refit scene must differ from the original"
     assert np.array_equal(inst2, ref2["first_hits"][:, 0]) and np.array_equal(prim2, ref2["first_hits"][:, 1])
     # refit twice (back to key 0) gives the original hits again: topology is kept, boxes are recomputed
-    gpu.update_instances(ids, np.stack([scenes.srt_to_mat(k[0]) for k in keys]))
+    gpu.update_instances(ids, np.stack([info["world"](i, 0.0) for i in ids]))
     gpu.begin_frame(1, cam)
     gpu.render_to_host()
     inst3, prim3 = gpu.first_hits()
