@@ -86,6 +86,7 @@ struct KrrWfpt {
 	float probRR = 0.8f, clampMax = 1e3f;
 	bool nee = true, enableMedium = true, enableClamp = false;
 	bool rrInTrace = true; // "rr_in_trace": internal scheduling switch (not a reference parameter), see Params::rrInTrace
+	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
 	bool haveScene = false, haveColorSpace = false, frameBegun = false;
 	uint64_t frameIndex = 0;
@@ -111,6 +112,8 @@ struct KrrWfpt {
 	Buf<uint8_t> instFlags;
 	std::vector<InstRec> hInstances;
 	std::vector<MeshRec> hMeshes;
+	std::vector<uint8_t> mergedInst, dynamicInst; // per instance: lives in the merged BLAS / has been moved by update_instances
+	bool anyMotion = false;
 	SceneDev scene{};
 	BvhBuilder bvh;
 	bool matTypePresent[MAT_COUNT] = {false, false, false, false, false};
@@ -163,6 +166,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->clampMax		= j.value("clamp_max", h->clampMax);
 		h->spp			= j.value("spp", h->spp);
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
+		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
@@ -326,6 +330,51 @@ extern "C" int krr_wfpt_set_color_space(KrrWfpt *h, const KrrColorSpaceData *c) 
 	return KRR_OK;
 }
 
+namespace {
+bool isIdentity(const Xf &t) {
+	static const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+	for (int k = 0; k < 12; k++) if (!(t.m[k] == I[k])) return false;
+	return true;
+}
+
+// (Re)builds BLASes + TLAS from the host copies of the mesh / instance records and uploads both.
+// Static instances whose transform is exactly the identity are merged into one world-space BLAS
+// (bvh_build.h); instances that krr_wfpt_update_instances has moved are kept out of it (dynamicInst).
+int buildAccel(KrrWfpt *h) {
+	const int nInst = (int) h->hInstances.size(), nMesh = (int) h->hMeshes.size();
+	std::vector<uint8_t> merge(nInst, 0);
+	bool any = false;
+	if (h->mergeStatic)
+		for (int i = 0; i < nInst; i++) {
+			const InstRec &r = h->hInstances[i];
+			merge[i] = r.motion < 0 && !h->dynamicInst[i] && isIdentity(r.xf) && isIdentity(r.inv);
+			any |= merge[i] != 0;
+		}
+	h->mergedInst = merge;
+	std::vector<InstRec> up = h->hInstances;
+	if (any) { // pseudo-instance of the merged BLAS
+		InstRec r{};
+		r.xf.m[0] = r.xf.m[5] = r.xf.m[10] = 1.f;
+		r.inv = r.xf;
+		r.mesh = nMesh, r.lightBase = -1, r.motion = -1, r.blasRoot = -1;
+		up.push_back(r);
+	}
+	if (h->instances.upload(up)) return KRR_E_CUDA;
+	MotionWindow mw;
+	if (h->anyMotion) mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p;
+	mw.w0 = h->motionW0, mw.w1 = h->motionW1;
+	char err[256] = "";
+	if (!h->bvh.build(h->positions.p, h->indices.p, h->hMeshes.data(), nMesh, h->instances.p, h->hInstances.data(), nInst, any ? merge.data() : nullptr, mw,
+					  nullptr, err))
+		return fail(KRR_E_CUDA, "%s", err);
+	for (int i = 0; i < nMesh; i++) h->hMeshes[i].blasRoot = h->bvh.blasRoot(i), h->hMeshes[i].triBase = h->bvh.triBase(i);
+	for (int i = 0; i < nInst; i++) h->hInstances[i].blasRoot = up[i].blasRoot = h->hMeshes[h->hInstances[i].mesh].blasRoot;
+	if (any) up[nInst].blasRoot = h->bvh.mergedRoot();
+	if (h->instances.upload(up) | h->meshes.upload(h->hMeshes)) return KRR_E_CUDA;
+	return KRR_OK;
+}
+} // namespace
+
 extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	if (!h || !d) return fail(KRR_E_INVALID, "null argument");
 	if (!h->haveColorSpace) return fail(KRR_E_STATE, "krr_wfpt_set_color_space must be called before set_scene");
@@ -483,10 +532,14 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 		}
 		const KrrMeshDesc &m = d->meshes[in.mesh];
 		if (m.material < 0) flags[i] |= 1;
-		else if (d->materials[m.material].textures[KRR_TEX_TRANSMISSION].valid) flags[i] |= 2;
+		else {
+			if (d->materials[m.material].textures[KRR_TEX_TRANSMISSION].valid) flags[i] |= 2;
+			flags[i] |= (uint8_t) (mats[m.material].bsdfType << 4); // routing info of the closest stage in one byte
+		}
 		bool emissiveTex = m.material >= 0 && d->materials[m.material].textures[KRR_TEX_EMISSIVE].valid;
 		bool emissive	 = emissiveTex || m.Le[0] != 0 || m.Le[1] != 0 || m.Le[2] != 0;
 		if (emissive) {
+			flags[i] |= 4;
 			r.lightBase = (int32_t) lights.size();
 			float Le[3];
 			if (emissiveTex) memcpy(Le, d->materials[m.material].textures[KRR_TEX_EMISSIVE].value, 12);
@@ -550,24 +603,15 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 	rc |= h->instFlags.upload(flags);
 	if (rc) return KRR_E_CUDA;
 	// acceleration structures
-	rc = h->instances.upload(insts);
-	if (rc) return rc;
-	char err[256] = "";
+	h->hInstances = insts, h->hMeshes = meshes;
+	h->dynamicInst.assign(d->n_instances, 0);
 	// until the first begin_frame supplies the camera's shutter interval, moving instances are bounded
 	// over the whole animation range
-	MotionWindow mw;
-	if (anyMotion) {
-		mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p;
-		mw.w0 = d->options.starttime, mw.w1 = std::max(d->options.endtime, d->options.starttime);
-	}
-	h->motionW0 = mw.w0, h->motionW1 = mw.w1;
-	if (!h->bvh.build(h->positions.p, h->indices.p, meshes.data(), d->n_meshes, h->instances.p, insts.data(), d->n_instances, mw, nullptr, err))
-		return fail(KRR_E_CUDA, "%s", err);
-	for (int i = 0; i < d->n_meshes; i++) meshes[i].blasRoot = h->bvh.blasRoot(i), meshes[i].triBase = h->bvh.triBase(i);
-	for (int i = 0; i < d->n_instances; i++) insts[i].blasRoot = meshes[insts[i].mesh].blasRoot;
-	rc = h->instances.upload(insts) | h->meshes.upload(meshes);
-	if (rc) return KRR_E_CUDA;
-	h->hInstances = insts, h->hMeshes = meshes;
+	h->anyMotion = anyMotion;
+	h->motionW0 = d->options.starttime, h->motionW1 = anyMotion ? std::max(d->options.endtime, d->options.starttime) : d->options.starttime;
+	if (!anyMotion) h->motionW0 = h->motionW1 = 0.f;
+	rc = buildAccel(h);
+	if (rc) return rc;
 	SceneDev &s = h->scene;
 	s.positions = h->positions.p, s.normals = h->normals.p, s.texcoords = h->texcoords.p, s.tangents = h->tangents.p, s.indices = h->indices.p;
 	s.meshes = h->meshes.p, s.instances = h->instances.p, s.materials = h->materials.p, s.lights = h->lights.p;
@@ -614,13 +658,26 @@ extern "C" int krr_wfpt_update_instances(KrrWfpt *h, const int32_t *ids, const f
 	if (n <= 0) return KRR_OK;
 	if (!ids || !xf) return fail(KRR_E_INVALID, "null argument");
 	cudaStream_t st = (cudaStream_t) stream;
+	bool rebuild = false;
 	for (int i = 0; i < n; i++) {
 		if (ids[i] < 0 || ids[i] >= (int) h->hInstances.size()) return fail(KRR_E_INVALID, "instance id out of range");
 		InstRec &r = h->hInstances[ids[i]];
 		memcpy(r.xf.m, xf + 12 * i, 48);
 		r.inv = xfInverse(r.xf);
+		h->dynamicInst[ids[i]] = 1;
+		// an instance that was merged into the static world-space BLAS starts to move: take it out
+		// (one rebuild; from then on it is an ordinary TLAS instance and updates are refits)
+		if (h->mergedInst[ids[i]]) rebuild = true;
 		// updateAccelStructure memcpy's the changed transforms only (optix.cpp:618-643)
-		CUDA_OK(cudaMemcpyAsync(h->instances.p + ids[i], &r, sizeof(InstRec), cudaMemcpyHostToDevice, st));
+		else CUDA_OK(cudaMemcpyAsync(h->instances.p + ids[i], &r, sizeof(InstRec), cudaMemcpyHostToDevice, st));
+	}
+	if (rebuild) {
+		CUDA_OK(cudaStreamSynchronize(st));
+		CUDA_OK(cudaDeviceSynchronize());
+		int rc = buildAccel(h);
+		if (rc) return rc;
+		h->scene.instances = h->instances.p, h->scene.meshes = h->meshes.p;
+		return KRR_OK;
 	}
 	char err[256] = "";
 	if (!h->bvh.refitTlas(h->instances.p, st, err)) return fail(KRR_E_CUDA, "%s", err);

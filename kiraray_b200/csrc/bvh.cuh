@@ -34,7 +34,7 @@ struct __align__(16) Node8 {
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
-struct BvhTri { float4 v0, v1, v2; }; // xyz = object-space vertex, v0.w = primitive id (int bits)
+struct BvhTri { float4 v0, v1, v2; }; // xyz = object-space vertex, v0.w = primitive id, v1.w = instance id (merged BLAS only)
 
 struct BvhDev {
 	const Node8 *nodes;	   // node pool: TLAS nodes first, then every mesh's BLAS
@@ -44,6 +44,14 @@ struct BvhDev {
 	int32_t nInstances;
 	const XformNodeRec *xnodes; // motion blur: transform chains + SRT key pool (motion.cuh), null otherwise
 	const float *motionKeys;
+	// Static instances whose transform is exactly the identity are MERGED into one world-space BLAS
+	// (bvh_build.cu): object space == world space for them, so the intersection spec gives the same
+	// numbers, and a ray no longer enters each of them separately.  The merged BLAS hangs in the TLAS as
+	// pseudo-instance `mergedInst` (= nInstances, identity transform); its triangles carry their real
+	// instance id.  mergedOnly: every instance was merged, traversal starts at the merged root.
+	int32_t mergedInst; // -1 = nothing merged
+	int32_t mergedRoot;
+	int32_t mergedOnly;
 };
 
 struct Hit {
@@ -130,6 +138,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		setIdir();
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
 		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
+		if (bvh.mergedOnly) cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
 	}
 	KRR_DEV void push(TraceSmem &sm, uint32_t e, float tn) {
 		if (sp < kShortStack) {
@@ -259,9 +268,10 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 			float t, u, v;
 			if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
-				int prim = __float_as_int(a.w);
-				if (betterHit(t, curInst, prim, best) && accept(curInst, prim, u, v)) {
-					best.inst = curInst, best.prim = prim, best.t = t, best.u = u, best.v = v;
+				const int prim = __float_as_int(a.w);
+				const int inst = curInst == bvh.mergedInst ? __float_as_int(b.w) : curInst;
+				if (betterHit(t, inst, prim, best) && accept(inst, prim, u, v)) {
+					best.inst = inst, best.prim = prim, best.t = t, best.u = u, best.v = v;
 					if (ANY) return true;
 				}
 			}

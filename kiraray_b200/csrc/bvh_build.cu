@@ -65,10 +65,14 @@ __global__ void k_prim_bounds_tris(const float *__restrict__ pos, const int32_t 
 // positions are united, and the box is padded by the largest second difference of a corner's
 // trajectory -- 8x the deviation of a smooth curve from the chords between consecutive samples.
 constexpr int kMotionSamples = 8;
-__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, int n, Aabb *boxes, float *cb,
-									const XformNodeRec *__restrict__ xnodes, const float *__restrict__ keyPool, float w0, float w1) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, const int32_t *__restrict__ ids, int n,
+									Aabb *boxesByInst, Aabb *boxesCompact, float *cb, const XformNodeRec *__restrict__ xnodes,
+									const float *__restrict__ keyPool, float w0, float w1) {
+	// ids: the instances that are TLAS primitives (merged instances are not; the merged BLAS is pseudo-
+	// instance nInstances).  Boxes are stored by instance id (refit) and, for the build, by TLAS primitive.
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= n) return;
+	const int i = ids[slot];
 	const Aabb mb = meshBoxes[inst[i].mesh];
 	Aabb b;
 	for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
@@ -105,12 +109,43 @@ __global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb
 		float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]) + pad;
 		b.lo[k] -= e, b.hi[k] += e;
 	}
-	boxes[i] = b;
+	boxesByInst[i] = b;
+	if (boxesCompact) boxesCompact[slot] = b;
 	if (cb)
 		for (int k = 0; k < 3; k++) {
 			float c = 0.5f * (b.lo[k] + b.hi[k]);
 			atomicMinF(cb + k, c), atomicMaxF(cb + 3 + k, c);
 		}
+}
+
+// merged BLAS: triangle boxes of every merged instance (identity transform: object space == world
+// space), concatenated; pairs[t] = (group slot, local primitive).  blockIdx.y strides over the merged
+// instances, blockIdx.x over 256-triangle chunks.
+struct MergedSrc { int32_t posOff, idxOff, nTri, inst, outOff; };
+__global__ void k_prim_bounds_merged(const float *__restrict__ positions, const int32_t *__restrict__ indices, const MergedSrc *__restrict__ src,
+									 int nSrc, Aabb *boxes, int2 *pairs, float *cb) {
+	for (int j = blockIdx.y; j < nSrc; j += gridDim.y) {
+		const MergedSrc ms = src[j];
+		const float *pos   = positions + 3 * (size_t) ms.posOff;
+		const int32_t *idx = indices + 3 * (size_t) ms.idxOff;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ms.nTri; i += gridDim.x * blockDim.x) {
+			Aabb b;
+			for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
+			for (int c = 0; c < 3; c++) {
+				int v = idx[3 * i + c];
+				for (int k = 0; k < 3; k++) {
+					float p = pos[3 * v + k];
+					b.lo[k] = fminf(b.lo[k], p), b.hi[k] = fmaxf(b.hi[k], p);
+				}
+			}
+			boxes[ms.outOff + i] = b;
+			pairs[ms.outOff + i] = make_int2(j, i);
+			for (int k = 0; k < 3; k++) {
+				float c = 0.5f * (b.lo[k] + b.hi[k]);
+				atomicMinF(cb + k, c), atomicMaxF(cb + 3 + k, c);
+			}
+		}
+	}
 }
 
 KRR_DEV uint64_t expand21(uint32_t v) { // spread 21 bits to every third bit
@@ -250,9 +285,29 @@ struct TriWriter {
 		tris[slot] = t;
 	}
 };
+struct MergedTriWriter { // triangles of the merged BLAS carry (primitive, instance)
+	const float *positions;
+	const int32_t *indices;
+	const MergedSrc *src;
+	const int2 *pairs;
+	BvhTri *tris;
+	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const {
+		const int2 pr	   = pairs[prim];
+		const MergedSrc ms = src[pr.x];
+		const float *pos   = positions + 3 * (size_t) ms.posOff;
+		const int32_t *idx = indices + 3 * ((size_t) ms.idxOff + pr.y);
+		int a = idx[0], b = idx[1], c = idx[2];
+		BvhTri t;
+		t.v0 = make_float4(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], __int_as_float(pr.y));
+		t.v1 = make_float4(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2], __int_as_float(ms.inst));
+		t.v2 = make_float4(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2], 0.f);
+		tris[slot] = t;
+	}
+};
 struct InstWriter {
 	int32_t *tlasInst;
-	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const { tlasInst[slot] = (int32_t) prim; }
+	const int32_t *ids; // TLAS primitive -> instance id
+	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const { tlasInst[slot] = ids[prim]; }
 };
 
 template <typename Writer>
@@ -406,7 +461,8 @@ struct BvhBuilder::Impl {
 	DevBuf<BvhTri> tris;
 	DevBuf<int32_t> tlasInst;
 	DevBuf<Aabb> meshBoxes, instBoxes;
-	DevBuf<int32_t> counters;
+	DevBuf<int32_t> counters, tlasIds;
+	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0;
 	std::vector<int> tlasLevelStart; // node index (relative to the pool) where each TLAS level begins
 	int tlasNodeCount = 0, totalNodes = 0, totalTris = 0, nInstances = 0, nMeshes = 0;
 	std::vector<int32_t> blasRoots, triBases;
@@ -478,29 +534,55 @@ bool buildTree(const Aabb *boxes, int n, int maxLeaf, Node8 *nodePool, Aabb *bou
 } // namespace
 
 bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes,
-					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const MotionWindow &motion, cudaStream_t stream,
-					   char *err) {
+					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const uint8_t *hMerge, const MotionWindow &motion,
+					   cudaStream_t stream, char *err) {
 	Impl &b = *m;
 	b.nMeshes = nMeshes, b.nInstances = nInstances;
-	size_t totalTris = 0;
-	int maxTris = 1;
-	for (int i = 0; i < nMeshes; i++) totalTris += hMeshes[i].nTri, maxTris = std::max(maxTris, hMeshes[i].nTri);
-	const size_t nodeCap = totalTris + (size_t) nMeshes + (size_t) nInstances + 8;
-	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(nInstances) ||
-		!b.meshBoxes.alloc(nMeshes) || !b.instBoxes.alloc(nInstances) || !b.counters.alloc(2)) {
+	// which instances go into the merged world-space BLAS, which meshes still need a BLAS of their own
+	std::vector<MergedSrc> msrc;
+	std::vector<char> meshNeedsBlas(nMeshes, 0);
+	std::vector<int32_t> tlasIds;
+	size_t mergedTris = 0;
+	for (int i = 0; i < nInstances; i++) {
+		const MeshRec &mr = hMeshes[hInstances[i].mesh];
+		if (hMerge && hMerge[i]) {
+			msrc.push_back(MergedSrc{mr.posOff, mr.idxOff, mr.nTri, i, (int32_t) mergedTris});
+			mergedTris += mr.nTri;
+		} else {
+			meshNeedsBlas[hInstances[i].mesh] = 1;
+			tlasIds.push_back(i);
+		}
+	}
+	if (mergedTris > 0x03ffffffu) { snprintf(err, 256, "bvh build: merged BLAS too large (%zu triangles)", mergedTris); return false; }
+	const bool haveMerged = !msrc.empty();
+	if (haveMerged) tlasIds.push_back(nInstances); // the pseudo-instance (api.cu appends its InstRec)
+	b.mergedInst = haveMerged ? nInstances : -1;
+	b.mergedRoot = -1;
+	b.nMergedTris = (int) mergedTris;
+	b.nTlasPrims  = (int) tlasIds.size();
+	size_t totalTris = mergedTris;
+	int maxTris = 1, nBlas = haveMerged ? 1 : 0;
+	for (int i = 0; i < nMeshes; i++)
+		if (meshNeedsBlas[i]) totalTris += hMeshes[i].nTri, maxTris = std::max(maxTris, hMeshes[i].nTri), nBlas++;
+	const int tlasReserve = nInstances + 2;
+	const size_t nodeCap  = totalTris + (size_t) nBlas + (size_t) tlasReserve + 8;
+	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(nInstances + 1) ||
+		!b.meshBoxes.alloc(nMeshes + 1) || !b.instBoxes.alloc(nInstances + 1) || !b.counters.alloc(2) || !b.tlasIds.alloc(tlasIds.size())) {
 		snprintf(err, 256, "bvh build: out of device memory (%zu triangles)", totalTris);
 		return false;
 	}
+	CK(cudaMemcpyAsync(b.tlasIds.p, tlasIds.data(), tlasIds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
 	DevBuf<Aabb> primBoxes;
 	DevBuf<float> cb;
-	if (!primBoxes.alloc(std::max(maxTris, nInstances)) || !cb.alloc(6)) { snprintf(err, 256, "bvh build: alloc failed"); return false; }
+	if (!primBoxes.alloc(std::max<size_t>(std::max<size_t>(maxTris, mergedTris), tlasIds.size())) || !cb.alloc(6)) { snprintf(err, 256, "bvh build: alloc failed"); return false; }
 	const int T = 256;
-	// TLAS occupies the front of the pool: reserve its nodes first (upper bound nInstances + 1)
-	int nodeCursor = nInstances + 1, primCursor = 0;
-	b.blasRoots.assign(nMeshes, 0), b.triBases.assign(nMeshes, 0);
+	// TLAS occupies the front of the pool: reserve its nodes first (upper bound: one per primitive + 1)
+	int nodeCursor = tlasReserve, primCursor = 0;
+	b.blasRoots.assign(nMeshes, -1), b.triBases.assign(nMeshes, -1);
 	for (int i = 0; i < nMeshes; i++) {
 		const MeshRec &mr = hMeshes[i];
 		if (mr.nTri <= 0) { snprintf(err, 256, "bvh build: mesh %d has no triangles", i); return false; }
+		if (!meshNeedsBlas[i]) continue; // only instanced through the merged BLAS
 		k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
 		k_prim_bounds_tris<<<(mr.nTri + T - 1) / T, T, 0, stream>>>(dPositions + 3 * (size_t) mr.posOff, dIndices + 3 * (size_t) mr.idxOff,
 																  mr.nTri, primBoxes.p, cb.p);
@@ -512,20 +594,40 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			return false;
 		b.blasRoots[i] = root;
 	}
+	if (haveMerged) {
+		DevBuf<MergedSrc> dsrc;
+		DevBuf<int2> pairs;
+		if (!dsrc.alloc(msrc.size()) || !pairs.alloc(mergedTris)) { snprintf(err, 256, "bvh build: alloc failed (merged BLAS)"); return false; }
+		CK(cudaMemcpyAsync(dsrc.p, msrc.data(), msrc.size() * sizeof(MergedSrc), cudaMemcpyHostToDevice, stream));
+		int maxSrcTris = 1;
+		for (const MergedSrc &s : msrc) maxSrcTris = std::max(maxSrcTris, s.nTri);
+		dim3 grid((unsigned) std::min((maxSrcTris + T - 1) / T, 4096), (unsigned) std::min<size_t>(msrc.size(), 16384));
+		k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
+		k_prim_bounds_merged<<<grid, T, 0, stream>>>(dPositions, dIndices, dsrc.p, (int) msrc.size(), primBoxes.p, pairs.p, cb.p);
+		k_mesh_box<<<1, 256, 0, stream>>>(primBoxes.p, (int) mergedTris, b.meshBoxes.p + nMeshes);
+		MergedTriWriter wr{dPositions, dIndices, dsrc.p, pairs.p, b.tris.p};
+		int root = 0;
+		if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
+			return false;
+		b.mergedRoot = root;
+	}
 	b.totalTris = primCursor;
 	b.totalNodes = nodeCursor;
-	// TLAS over instance world boxes (one instance per leaf child)
-	k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
-	k_prim_bounds_insts<<<(nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, nInstances, b.instBoxes.p, cb.p, motion.xnodes,
-																  motion.keys, motion.w0, motion.w1);
+	// TLAS over the world boxes of its primitives (one instance per leaf child)
 	b.motion = motion;
-	int tlasCursor = 0, tlasPrims = 0, root = 0;
 	b.tlasLevelStart.clear();
-	InstWriter iw{b.tlasInst.p};
-	if (!buildTree(b.instBoxes.p, nInstances, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err))
-		return false;
-	b.tlasNodeCount = tlasCursor;
-	(void) hInstances;
+	b.tlasNodeCount = 0;
+	if (b.nTlasPrims > 0) {
+		k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
+		k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, primBoxes.p,
+																		 cb.p, motion.xnodes, motion.keys, motion.w0, motion.w1);
+		int tlasCursor = 0, tlasPrims = 0, root = 0;
+		InstWriter iw{b.tlasInst.p, b.tlasIds.p};
+		if (!buildTree(primBoxes.p, b.nTlasPrims, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err))
+			return false;
+		if (tlasCursor > tlasReserve) { snprintf(err, 256, "bvh build: TLAS node reservation exceeded"); return false; }
+		b.tlasNodeCount = tlasCursor;
+	}
 	CK(cudaStreamSynchronize(stream));
 	return true;
 }
@@ -534,8 +636,9 @@ bool BvhBuilder::refitTlas(const InstRec *dInstances, cudaStream_t stream, char 
 	Impl &b = *m;
 	const int T = 128;
 	if (window) b.motion = *window;
-	k_prim_bounds_insts<<<(b.nInstances + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.nInstances, b.instBoxes.p, nullptr,
-																	  b.motion.xnodes, b.motion.keys, b.motion.w0, b.motion.w1);
+	if (b.nTlasPrims <= 0) return true;
+	k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, nullptr, nullptr,
+																	 b.motion.xnodes, b.motion.keys, b.motion.w0, b.motion.w1);
 	for (int l = (int) b.tlasLevelStart.size() - 2; l >= 0; l--) {
 		int first = b.tlasLevelStart[l], count = b.tlasLevelStart[l + 1] - first;
 		if (count <= 0) continue;
@@ -551,11 +654,15 @@ BvhDev BvhBuilder::device() const {
 	BvhDev d;
 	d.nodes = m->nodes.p, d.tris = m->tris.p, d.tlasInst = m->tlasInst.p, d.tlasRoot = 0, d.nInstances = m->nInstances;
 	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
+	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot;
+	d.mergedOnly = m->mergedInst >= 0 && m->nTlasPrims == 1; // the pseudo-instance is the only TLAS primitive
 	return d;
 }
 int BvhBuilder::blasRoot(int mesh) const { return m->blasRoots[mesh]; }
+int BvhBuilder::mergedRoot() const { return m->mergedRoot; }
+int BvhBuilder::mergedTriCount() const { return m->nMergedTris; }
 int BvhBuilder::triBase(int mesh) const { return m->triBases[mesh]; }
-int BvhBuilder::nodeCount() const { return m->totalNodes - (m->nInstances + 1) + m->tlasNodeCount; }
+int BvhBuilder::nodeCount() const { return m->totalNodes - (m->nInstances + 2) + m->tlasNodeCount; }
 int BvhBuilder::tlasNodeCount() const { return m->tlasNodeCount; }
 int BvhBuilder::triCount() const { return m->totalTris; }
 

@@ -20,8 +20,14 @@ public:
 	BvhBuilder(const BvhBuilder &) = delete;
 	// Builds one BLAS per mesh (object space) and a TLAS over the instances.  dPositions / dIndices /
 	// dInstances are device arrays; hMeshes is the host copy of the mesh records (offsets, counts).
+	// hMerge (optional, per instance): 1 = static instance with an exactly-identity transform, to be
+	// merged into ONE world-space BLAS that enters the TLAS as pseudo-instance `nInstances`; dInstances
+	// must then hold nInstances + 1 records, the last one being that pseudo-instance (identity,
+	// mesh = nMeshes, blasRoot patched by the caller from mergedRoot()).
 	bool build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes, const InstRec *dInstances,
-			   const InstRec *hInstances, int nInstances, const MotionWindow &motion, cudaStream_t stream, char *err);
+			   const InstRec *hInstances, int nInstances, const uint8_t *hMerge, const MotionWindow &motion, cudaStream_t stream, char *err);
+	int mergedRoot() const;		// node index of the merged BLAS root, -1 = none
+	int mergedTriCount() const;
 	// Re-fits the TLAS after instance transforms (or the motion window) changed; topology kept, no
 	// host synchronisation.
 	bool refitTlas(const InstRec *dInstances, cudaStream_t stream, char *err, const MotionWindow *window = nullptr);

@@ -118,7 +118,9 @@ struct Wavefront {
 	DepthCounters *counters; // [kMaxDepthSlots]
 	int4 *firstHits;		 // per pixel depth-0 hit (debug tap), may be null
 	int32_t *errorFlags;	 // [0] traversal stack overflow
-	const uint8_t *instFlags; // per instance: bit0 null material, bit1 has alpha (transmission) texture
+	// per instance: bit0 null material, bit1 has alpha (transmission) texture, bit2 emissive, bits 4-6 BSDF
+	// type of its material -- everything the closest stage needs to route a hit, in one load
+	const uint8_t *instFlags;
 };
 
 // ---- warp-aggregated push: one atomicAdd per warp ----
@@ -351,18 +353,82 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
 	Traverser<false, MOTION> tr;
-	int ray = -1; // queue slot this lane is tracing, -1 = idle
+	int ray	  = -1;	   // queue slot this lane holds, -1 = idle
+	int pix	  = 0;	   // its pixel (fetched with the ray: the finalisation needs it first)
+	bool done = false; // traversal finished, result in tr.best, not yet finalised
 	WarpWork work;
 	work.init(n, &dc->cursorRay);
 	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
 	float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
 	while (true) {
+		// ---- finalise finished rays in BATCHES: the finalisation is a chain of dependent long-latency
+		// operations (pixel RNG read-modify-write, queue-counter atomics), so it runs once kRefill lanes
+		// have finished (they would idle until the refill anyway), or when nothing is left to trace ----
+		const unsigned doneMask = __ballot_sync(FULL, done);
+		if (doneMask && (__popc(doneMask) >= kRefill || !__ballot_sync(FULL, ray >= 0 && !done))) {
+			// queue id of the lane: 0 miss, 1 + mt scatter, MAT_COUNT + 1 null pass-through, MAT_COUNT + 2 medium
+			// sample, -1 none (lane not finished, or path ended by Russian roulette)
+			int qid		= -1;
+			bool light	= false;
+			const Hit h = tr.best;
+			const int i = ray;
+			if (done) {
+				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+				const int4 rec = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
+				wf.hits[i]	   = rec;
+				if (depth == 0 && wf.firstHits) wf.firstHits[pix] = rec;
+				if (wf.p.enableMedium && __float_as_int(d4.w) >= 0) {
+					// ray inside a medium: hit or miss, the item goes to the medium stage (device.cu:50-53, 69-72)
+					qid		   = MAT_COUNT + 2;
+					wf.hitT[i] = h.inst < 0 ? kInf : h.t;
+				} else if (h.inst < 0) qid = 0;
+				else {
+					const uint32_t f = wf.instFlags[h.inst];
+					if (f & 1) qid = MAT_COUNT + 1;
+					else {
+						qid	  = 1 + (int) (f >> 4);
+						light = (f & 4) != 0;
+						if (wf.p.rrInTrace && depth < wf.p.maxDepth) { // no scatter stage (hence no draw) at the last depth
+							Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+							const bool alive = rng.get1D() < wf.p.probRR;
+							wf.px.rng[pix]	 = rng.state;
+							if (!alive) qid = -2;
+						}
+					}
+				}
+				ray = -1, done = false;
+			}
+			// one atomicAdd per QUEUE per warp, all queues in the same instruction: lanes are grouped by
+			// queue id, the first lane of each group reserves the group's slots
+			const unsigned grp = __match_any_sync(FULL, qid);
+			const int leader   = __ffs(grp) - 1;
+			int32_t *counter   = qid == 0 ? &dc->nMiss : qid <= MAT_COUNT ? &dc->nScatter[max(qid - 1, 0)] : qid == MAT_COUNT + 1 ? &dc[1].nRay : &dc->nMediumSample;
+			int base = 0;
+			if (qid >= 0 && lane == leader) base = atomicAdd(counter, __popc(grp));
+			const unsigned lightMask = __ballot_sync(FULL, light);
+			int lbase = 0;
+			if (lightMask && lane == __ffs(lightMask) - 1) lbase = atomicAdd(&dc->nHitLight, __popc(lightMask));
+			const unsigned killed = __ballot_sync(FULL, qid == -2);
+			if (killed && lane == 0) atomicAdd(&dc->nScatterKilled, __popc(killed));
+			base = __shfl_sync(FULL, base, leader);
+			if (lightMask) lbase = __shfl_sync(FULL, lbase, __ffs(lightMask) - 1);
+			const unsigned below = (1u << lane) - 1;
+			if (light) wf.hitLightIdx[lbase + __popc(lightMask & below)] = i;
+			if (qid >= 0) {
+				const int s = base + __popc(grp & below);
+				if (qid == 0) wf.missIdx[s] = i;
+				else if (qid <= MAT_COUNT) wf.scatterIdx[qid - 1][s] = i;
+				else if (qid == MAT_COUNT + 1) requeueThroughNull<MOTION>(wf, q, nq, i, s, h, o4, d4);
+				else wf.mediumSampleIdx[s] = i;
+			}
+		}
 		unsigned idle = __ballot_sync(FULL, ray < 0);
 		if (!work.exhausted && __popc(idle) >= kRefill) {
 			int r = work.take(idle, lane);
 			if (r >= 0) {
 				ray = r;
 				o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
+				pix = __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
 				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
 			}
 			idle = __ballot_sync(FULL, ray < 0);
@@ -371,66 +437,11 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 			if (work.exhausted) break;
 			continue; // private range ran dry mid-refill: claim again
 		}
-		const bool fin = tr.trip<true>(ray >= 0, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+		const bool fin = tr.trip<true>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
 			if (!(wf.instFlags[inst] & 2)) return true;
 			return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
 		});
-		if (!__ballot_sync(FULL, fin)) continue;
-		// ---- finalise the lanes whose ray terminated (whole warp converged here) ----
-		int route	= -1; // 0 miss, 1 scatter(+light), 2 null-material pass-through
-		int matType = 0;
-		bool light	= false, alive = true;
-		const Hit h = tr.best;
-		const int i = ray;
-		if (fin) {
-			if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
-			wf.hits[i] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
-			if (depth == 0 && wf.firstHits) {
-				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
-				wf.firstHits[pix] = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
-			}
-			if (wf.p.enableMedium && __float_as_int(d4.w) >= 0) {
-				// ray inside a medium: hit or miss, the item goes to the medium stage (device.cu:50-53, 69-72)
-				route	   = 4;
-				wf.hitT[i] = h.inst < 0 ? kInf : h.t;
-			} else if (h.inst < 0) route = 0;
-			else {
-				const InstRec &in	= wf.scene.instances[h.inst];
-				const MeshRec &mesh = wf.scene.meshes[in.mesh];
-				if (mesh.material < 0) route = 2;
-				else {
-					route	= 1;
-					matType = wf.scene.materials[mesh.material].bsdfType;
-					light	= in.lightBase >= 0;
-				}
-			}
-			if (route == 1 && wf.p.rrInTrace && depth < wf.p.maxDepth) { // no scatter stage (hence no draw) at the last depth
-				int pix = __float_as_int(ldg4(q.ctxP_pix + i).w);
-				Pcg rng{wf.px.rng[pix], wf.p.rngInc};
-				alive		   = rng.get1D() < wf.p.probRR;
-				wf.px.rng[pix] = rng.state;
-			}
-			ray = -1;
-		}
-		// (media: rays inside a medium are routed to the medium-sample queue by the media build)
-		int s;
-		s = warpPushFull(&dc->nMiss, route == 0);
-		if (s >= 0) wf.missIdx[s] = i;
-		s = warpPushFull(&dc->nHitLight, route == 1 && light);
-		if (s >= 0) wf.hitLightIdx[s] = i;
-#pragma unroll
-		for (int mt = 0; mt < MAT_COUNT; mt++) {
-			s = warpPushFull(&dc->nScatter[mt], route == 1 && alive && matType == mt);
-			if (s >= 0) wf.scatterIdx[mt][s] = i;
-		}
-		unsigned killed = __ballot_sync(FULL, route == 1 && !alive);
-		if (killed && lane == 0) atomicAdd(&dc->nScatterKilled, __popc(killed));
-		s = warpPushFull(&dc[1].nRay, route == 2);
-		if (s >= 0) requeueThroughNull<MOTION>(wf, q, nq, i, s, h, o4, d4);
-		if (wf.p.enableMedium) {
-			s = warpPushFull(&dc->nMediumSample, route == 4);
-			if (s >= 0) wf.mediumSampleIdx[s] = i;
-		}
+		done |= fin;
 	}
 }
 
@@ -778,10 +789,21 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	const int lane		= threadIdx.x & 31;
 	Traverser<true, MOTION> tr;
 	int ray = -1, pix = 0;
+	bool done = false; // traversal finished, radiance not yet added
 	WarpWork work;
 	work.init(n, &dc->cursorShadow);
 	if (work.next >= n) return;
 	while (true) {
+		// finished rays add their contribution in batches (same reasoning as in the closest stage: the
+		// read-modify-write of L is a long-latency chain the whole warp would wait for on every trip)
+		const unsigned doneMask = __ballot_sync(FULL, done);
+		if (doneMask && (__popc(doneMask) >= kRefill || !__ballot_sync(FULL, ray >= 0 && !done))) {
+			if (done) {
+				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+				if (tr.best.inst < 0) wf.px.L[pix] = ldcs4(wf.shadow.contrib + ray) + wf.px.L[pix];
+				ray = -1, done = false;
+			}
+		}
 		unsigned idle = __ballot_sync(FULL, ray < 0);
 		if (!work.exhausted && __popc(idle) >= kRefill) {
 			int r = work.take(idle, lane);
@@ -797,17 +819,13 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 			if (work.exhausted) break;
 			continue;
 		}
-		const bool fin = tr.trip<false>(ray >= 0, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+		const bool fin = tr.trip<false>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
 			uint8_t f = wf.instFlags[inst];
 			if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
 			if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
 			return true;
 		});
-		if (fin) {
-			if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
-			if (tr.best.inst < 0) wf.px.L[pix] = ldcs4(wf.shadow.contrib + ray) + wf.px.L[pix];
-			ray = -1;
-		}
+		done |= fin;
 	}
 }
 

@@ -138,3 +138,52 @@ def test_tile_partition_films_add_to_the_full_film(cbox_app):
         gpu.begin_frame(1, cam)
         acc += gpu.render_to_host()
     assert np.array_equal(acc.view(np.uint32), full.view(np.uint32))
+
+
+def test_merged_static_blas_gives_the_identical_film(cbox_app):
+    """Identity-transform static instances share one world-space BLAS (merge_static, the default):
+    object space == world space for them, so first hits, ray counts and the film must be identical
+    to the per-instance traversal, bit for bit."""
+    w = h = 64
+    app = cbox_app(w, h, spp=2, max_depth=6)
+    cam = app.camera()
+    out = []
+    for flag in (False, True):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=flag))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(w, h)
+        gpu.begin_frame(3, cam)
+        film = gpu.render_to_host()
+        out.append((film, gpu.stats(), gpu.first_hits()))
+    # all 8 cbox instances are identity: one merged BLAS instead of 8 single-node ones
+    assert out[1][1]["bvh_nodes"] != out[0][1]["bvh_nodes"]
+    assert out[0][1]["bvh_triangles"] == out[1][1]["bvh_triangles"]
+    assert np.array_equal(out[0][2][0], out[1][2][0]) and np.array_equal(out[0][2][1], out[1][2][1])
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    for k in ("closest_rays", "shadow_rays", "scatter_items", "hit_light_items", "miss_items"):
+        assert out[0][1][k] == out[1][1][k], k
+
+
+def test_moving_a_merged_instance_takes_it_out_of_the_merged_blas(cbox_app):
+    """update_instances on an instance that lives in the merged BLAS rebuilds the acceleration
+    structure once; the result equals a scene that was never merged."""
+    w = h = 48
+    app = cbox_app(w, h, spp=1, max_depth=4)
+    cam = app.camera()
+    xf = np.array([[1, 0, 0, 0.05, 0, 1, 0, 0.1, 0, 0, 1, -0.02]], np.float32)
+    out = []
+    for flag in (False, True):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=flag))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(w, h)
+        gpu.update_instances(np.array([5], np.int32), xf)
+        gpu.begin_frame(2, cam)
+        film = gpu.render_to_host()
+        out.append((film, gpu.first_hits(), gpu.stats()))
+    assert out[1][2]["tlas_nodes"] >= 1
+    assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    # and it differs from the unmoved scene
+    gpu = make_gpu(app, w, h)
+    gpu.begin_frame(2, cam)
+    assert not np.array_equal(gpu.render_to_host().view(np.uint32), out[1][0].view(np.uint32))
