@@ -107,6 +107,14 @@ struct TraceSmem {
 	uint32_t id[kShortStack][kTraceBlock];
 	float tn[kShortStack][kTraceBlock];
 };
+// Spill part of the stack (local memory).  Deliberately NOT a member of Traverser: a dynamically
+// indexed array inside the struct keeps the WHOLE struct in local memory (the compiler cannot split an
+// aggregate that is indexed with a run-time value), and the ray state would be loaded and stored
+// around every phase instead of living in registers.
+template <bool ANY> struct LocalStack {
+	uint32_t id[kLocalStack];
+	float tn[ANY ? 1 : kLocalStack];
+};
 
 #define KRR_CSWAP(a, b) { uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
 
@@ -128,9 +136,8 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 	// control
 	uint32_t cur;
 	int sp, curInst, blasBase;
-	uint32_t lstack[kLocalStack];
-	float ltn[ANY ? 1 : kLocalStack];
 	int overflow;
+	using LStack = LocalStack<ANY>;
 
 	KRR_DEV void setIdir() { idir = mk3(1.f / rd.x, 1.f / rd.y, 1.f / rd.z); }
 	KRR_DEV void begin(const BvhDev &bvh, V3 o_, V3 d_, float tmax_, float time_ = 0.f) {
@@ -140,30 +147,30 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
 		if (bvh.mergedOnly) cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
 	}
-	KRR_DEV void push(TraceSmem &sm, uint32_t e, float tn) {
+	KRR_DEV void push(TraceSmem &sm, LStack &ls, uint32_t e, float tn) {
 		if (sp < kShortStack) {
 			sm.id[sp][threadIdx.x] = e;
 			if (!ANY) sm.tn[sp][threadIdx.x] = tn;
 		} else if (sp < kStackSize) {
-			lstack[sp - kShortStack] = e;
-			if (!ANY) ltn[sp - kShortStack] = tn;
+			ls.id[sp - kShortStack] = e;
+			if (!ANY) ls.tn[sp - kShortStack] = tn;
 		} else { overflow = 1; return; }
 		sp++;
 	}
-	KRR_DEV uint32_t pop(TraceSmem &sm, float &tn) {
+	KRR_DEV uint32_t pop(TraceSmem &sm, LStack &ls, float &tn) {
 		--sp;
 		if (sp < kShortStack) {
 			if (!ANY) tn = sm.tn[sp][threadIdx.x];
 			return sm.id[sp][threadIdx.x];
 		}
-		if (!ANY) tn = ltn[sp - kShortStack];
-		return lstack[sp - kShortStack];
+		if (!ANY) tn = ls.tn[sp - kShortStack];
+		return ls.id[sp - kShortStack];
 	}
 
 	// What the lane has to do next: 0 = ray finished (result in `best`), 1 = enter an instance,
 	// 2 = wide node, 3 = leaf.  Pops the stack when the current entry is consumed.
 	enum { FINISHED = 0, ENTER = 1, NODE = 2, LEAF = 3 };
-	KRR_DEV int next(TraceSmem &sm) {
+	KRR_DEV int next(TraceSmem &sm, LStack &ls) {
 		while (cur == kEmptyEntry) {
 			if (curInst >= 0 && sp == blasBase) { // BLAS finished: back to world space
 				curInst = -1;
@@ -172,7 +179,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			}
 			if (sp == 0) return FINISHED;
 			float tn = 0.f;
-			cur = pop(sm, tn);
+			cur = pop(sm, ls, tn);
 			// box entry beyond the closest hit so far (same slack as the slab test: for flat, axis-aligned
 			// geometry the rounded entry distance can exceed the exact hit distance by an ulp, and an
 			// equal-t candidate with a smaller (instance, primitive) must still be tested)
@@ -191,7 +198,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		cur		 = (uint32_t) in.blasRoot;
 	}
 	// ---- phase 2: wide node: 8 slab tests, sort by entry distance, push far-to-near ----
-	KRR_DEV void node(const BvhDev &bvh, TraceSmem &sm) {
+	KRR_DEV void node(const BvhDev &bvh, TraceSmem &sm, LStack &ls) {
 		{
 			const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + cur);
 			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -249,13 +256,13 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 				return kLeafFlag | (((meta >> 5) - 1) << 26) | first;
 			};
 			// far-to-near onto the stack, nearest continues
-			if (k7 != kEmptyEntry) push(sm, entryOf(k7), __uint_as_float(k7 & ~7u));
-			if (k6 != kEmptyEntry) push(sm, entryOf(k6), __uint_as_float(k6 & ~7u));
-			if (k5 != kEmptyEntry) push(sm, entryOf(k5), __uint_as_float(k5 & ~7u));
-			if (k4 != kEmptyEntry) push(sm, entryOf(k4), __uint_as_float(k4 & ~7u));
-			if (k3 != kEmptyEntry) push(sm, entryOf(k3), __uint_as_float(k3 & ~7u));
-			if (k2 != kEmptyEntry) push(sm, entryOf(k2), __uint_as_float(k2 & ~7u));
-			if (k1 != kEmptyEntry) push(sm, entryOf(k1), __uint_as_float(k1 & ~7u));
+			if (k7 != kEmptyEntry) push(sm, ls, entryOf(k7), __uint_as_float(k7 & ~7u));
+			if (k6 != kEmptyEntry) push(sm, ls, entryOf(k6), __uint_as_float(k6 & ~7u));
+			if (k5 != kEmptyEntry) push(sm, ls, entryOf(k5), __uint_as_float(k5 & ~7u));
+			if (k4 != kEmptyEntry) push(sm, ls, entryOf(k4), __uint_as_float(k4 & ~7u));
+			if (k3 != kEmptyEntry) push(sm, ls, entryOf(k3), __uint_as_float(k3 & ~7u));
+			if (k2 != kEmptyEntry) push(sm, ls, entryOf(k2), __uint_as_float(k2 & ~7u));
+			if (k1 != kEmptyEntry) push(sm, ls, entryOf(k1), __uint_as_float(k1 & ~7u));
 			cur = k0 != kEmptyEntry ? entryOf(k0) : kEmptyEntry;
 		}
 	}
@@ -281,13 +288,13 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 
 	// Lane-local traversal to the end (no warp-level primitives): used where one lane runs several
 	// dependent traversals interleaved with other work (ratio-tracking shadow rays through media).
-	template <typename Accept> KRR_DEV void runToEnd(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
+	template <typename Accept> KRR_DEV void runToEnd(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, Accept accept) {
 		while (true) {
-			int st = next(sm);
+			int st = next(sm, ls);
 			if (st == FINISHED) return;
 			if (st == ENTER) { enterInstance(bvh, instances, sm); st = NODE; }
 			if (st == NODE) {
-				node(bvh, sm);
+				node(bvh, sm, ls);
 				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
 			}
 			if (st == LEAF && leaf(bvh, accept)) return;
@@ -300,12 +307,12 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 	// VOTE = false runs both phases every trip (a lane may test a node and then its nearest leaf in
 	// the same trip): fewer trips per ray, which wins for the short any-hit traversals of shadow rays.
 	template <bool VOTE, typename Accept>
-	KRR_DEV bool trip(bool active, const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, Accept accept) {
+	KRR_DEV bool trip(bool active, const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, Accept accept) {
 		const unsigned FULL = 0xffffffffu;
 		int st = FINISHED;
 		bool fin = false;
 		if (active) {
-			st	= next(sm);
+			st	= next(sm, ls);
 			fin = st == FINISHED;
 		}
 		if (__any_sync(FULL, st == ENTER)) {
@@ -314,13 +321,13 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		if (VOTE) {
 			const unsigned mN = __ballot_sync(FULL, st == NODE), mL = __ballot_sync(FULL, st == LEAF);
 			if (mN && __popc(mN) >= __popc(mL)) {
-				if (st == NODE) node(bvh, sm);
+				if (st == NODE) node(bvh, sm, ls);
 			} else if (mL) {
 				if (st == LEAF) fin = leaf(bvh, accept);
 			}
 		} else {
 			if (st == NODE) {
-				node(bvh, sm);
+				node(bvh, sm, ls);
 				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
 			}
 			if (st == LEAF) fin = leaf(bvh, accept);

@@ -353,13 +353,14 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
 	Traverser<false, MOTION> tr;
+	LocalStack<false> ls;
 	int ray	  = -1;	   // queue slot this lane holds, -1 = idle
 	int pix	  = 0;	   // its pixel (fetched with the ray: the finalisation needs it first)
 	bool done = false; // traversal finished, result in tr.best, not yet finalised
 	WarpWork work;
 	work.init(n, &dc->cursorRay);
 	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
-	float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+	int medium = -1; // medium the ray travels in (d_medium.w)
 	while (true) {
 		// ---- finalise finished rays in BATCHES: the finalisation is a chain of dependent long-latency
 		// operations (pixel RNG read-modify-write, queue-counter atomics), so it runs once kRefill lanes
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 				const int4 rec = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
 				wf.hits[i]	   = rec;
 				if (depth == 0 && wf.firstHits) wf.firstHits[pix] = rec;
-				if (wf.p.enableMedium && __float_as_int(d4.w) >= 0) {
+				if (wf.p.enableMedium && medium >= 0) {
 					// ray inside a medium: hit or miss, the item goes to the medium stage (device.cu:50-53, 69-72)
 					qid		   = MAT_COUNT + 2;
 					wf.hitT[i] = h.inst < 0 ? kInf : h.t;
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 				const int s = base + __popc(grp & below);
 				if (qid == 0) wf.missIdx[s] = i;
 				else if (qid <= MAT_COUNT) wf.scatterIdx[qid - 1][s] = i;
-				else if (qid == MAT_COUNT + 1) requeueThroughNull<MOTION>(wf, q, nq, i, s, h, o4, d4);
+				else if (qid == MAT_COUNT + 1)
+					requeueThroughNull<MOTION>(wf, q, nq, i, s, h, make_float4(tr.o.x, tr.o.y, tr.o.z, tr.time), make_float4(tr.d.x, tr.d.y, tr.d.z, __int_as_float(medium)));
 				else wf.mediumSampleIdx[s] = i;
 			}
 		}
@@ -427,8 +429,9 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 			int r = work.take(idle, lane);
 			if (r >= 0) {
 				ray = r;
-				o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
-				pix = __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
+				const float4 o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
+				pix	   = __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
+				medium = __float_as_int(d4.w);
 				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
 			}
 			idle = __ballot_sync(FULL, ray < 0);
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 			if (work.exhausted) break;
 			continue; // private range ran dry mid-refill: claim again
 		}
-		const bool fin = tr.trip<true>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+		const bool fin = tr.trip<true>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
 			if (!(wf.instFlags[inst] & 2)) return true;
 			return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
 		});
@@ -788,6 +791,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
 	Traverser<true, MOTION> tr;
+	LocalStack<true> ls;
 	int ray = -1, pix = 0;
 	bool done = false; // traversal finished, radiance not yet added
 	WarpWork work;
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 			if (work.exhausted) break;
 			continue;
 		}
-		const bool fin = tr.trip<false>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+		const bool fin = tr.trip<false>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
 			uint8_t f = wf.instFlags[inst];
 			if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
 			if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
@@ -1059,8 +1063,9 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_co
 		int imesh = -1;
 		while (!(fabsf(rd.x) <= 2 * kRayEps && fabsf(rd.y) <= 2 * kRayEps && fabsf(rd.z) <= 2 * kRayEps)) {
 			Traverser<false> tr;
+			LocalStack<false> ls;
 			tr.begin(wf.bvh, ro, rd, tMax, __int_as_float(aux.y));
-			tr.runToEnd(wf.bvh, wf.scene.instances, sm, [&](int inst, int prim, float u, float v) {
+			tr.runToEnd(wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
 				if (!(wf.instFlags[inst] & 2)) return true;
 				return !alphaKilled(wf, inst, prim, u, v, ro, rd);
 			});
