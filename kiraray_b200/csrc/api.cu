@@ -730,10 +730,10 @@ struct StageTimer { // RAII: brackets one launch with events when profiling is o
 };
 template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st) {
 	static int grid = 0, gridM = 0;
-	if (!grid) grid = gridFor(h, k_scatter<MT, false>, 128), gridM = gridFor(h, k_scatter<MT, true>, 128);
+	if (!grid) grid = gridFor(h, k_scatter<MT, false>, kScatterBlock), gridM = gridFor(h, k_scatter<MT, true>, kScatterBlock);
 	StageTimer t(h, KRR_STAGE_SCATTER, st);
-	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, 128, 0, st>>>(wf, depth);
-	else k_scatter<MT, false><<<grid, 128, 0, st>>>(wf, depth);
+	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, kScatterBlock, 0, st>>>(wf, depth);
+	else k_scatter<MT, false><<<grid, kScatterBlock, 0, st>>>(wf, depth);
 	h->launches++;
 }
 

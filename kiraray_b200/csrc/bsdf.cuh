@@ -408,6 +408,57 @@ template <> struct Bsdf<MAT_DISNEY> { // disney.h:193-370
 		if (pSpecTrans > 0 && !reflect) val += pSpecTrans * btdf.pdf(wo, wi);
 		return val;
 	}
+	// f(wo, wi) and pdf(wo, wi) in one pass: the same expressions as f() / pdf() above, evaluated in the
+	// same order (so the values are bit-identical), but the half vector, D(wh), G1(wo) and the hemisphere
+	// tests of the reflection lobe are computed once instead of once per function.  The scatter stage
+	// calls this from ONE loop for both directions it has to evaluate (light sample, cosine sample), so
+	// the code exists once in the kernel -- the stage is instruction-fetch bound.
+	KRR_DEV void eval(V3 wo, V3 wi, Spec &fOut, float &pdfOut) const {
+		Spec val   = sp(0);
+		float pval = 0;
+		const bool reflect = SameHemisphere(wo, wi);
+		if (pDiffuse > 0 && reflect) {
+			val += diffuseF(wo, wi);
+			pval += pDiffuse * AbsCosTheta(wi) * kInvPi;
+		}
+		if (pSpecRefl > 0 && reflect) {
+			const GGX<true> &dist = brdf.dist;
+			if (!dist.isDelta()) {
+				float cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+				V3 whRaw = wi + wo;
+				V3 wh	 = normalize(whRaw);
+				const float D = dist.D(wh), G1o = dist.G1(wo);
+				if (!(cosThetaI == 0 || cosThetaO == 0) && anyNonZero(whRaw)) {
+					Spec F = brdf.Fr(wo, wh);
+					val += D * (G1o * dist.G1(wi)) * F / (4 * cosThetaI * cosThetaO);
+				}
+				pval += pSpecRefl * ((D * G1o * fabsf(dot(wo, wh)) / AbsCosTheta(wo)) / (4 * dot(wo, wh)));
+			}
+		}
+		if (pSpecTrans > 0 && !reflect) {
+			val += btdf.f(wo, wi);
+			pval += pSpecTrans * btdf.pdf(wo, wi);
+		}
+		fOut = val, pdfOut = pval;
+	}
+	// first draw of sample(): which lobe
+	KRR_DEV int pickLobe(Pcg &sg) const { return sampleDiscrete3(pDiffuse, pSpecRefl, pSpecTrans, sg.get1D()); }
+	// sample() for the specular lobes (comp 1, 2); the diffuse lobe (comp 0) is a cosine sample + eval()
+	KRR_DEV BSDFSample sampleSpecular(int comp, V3 wo, Pcg &sg) const {
+		BSDFSample s;
+		if (comp == 1) {
+			s = brdf.sample(wo, sg);
+			s.pdf *= pSpecRefl;
+			if (pDiffuse && (s.flags & BSDF_SMOOTH)) {
+				s.f += diffuseF(wo, s.wi);
+				s.pdf += pDiffuse * AbsCosTheta(s.wi) * kInvPi;
+			}
+		} else {
+			s = btdf.sample(wo, sg);
+			s.pdf *= pSpecTrans;
+		}
+		return s;
+	}
 	KRR_DEV BSDFSample sample(V3 wo, Pcg &sg) const {
 		BSDFSample s = emptySample();
 		int comp = sampleDiscrete3(pDiffuse, pSpecRefl, pSpecTrans, sg.get1D());

@@ -650,11 +650,25 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 
 // =================================================================================================
 // generateScatterRays (integrator.cpp:110-164), one launch per material type
-#ifndef KRR_SCATTER_MINB
-#define KRR_SCATTER_MINB 5
+// The Disney instantiation is ~11k SASS instructions (180 KB) against a 32 KB instruction cache, and
+// warps at unrelated program counters evict each other's lines: ncu attributed 54 % of the stall samples
+// to instruction fetch (stall_no_inst).  Two counter-measures: (1) the warps of a CTA are re-aligned with
+// block barriers at phase boundaries (KRR_SCATTER_LOCKSTEP), so that a line fetched for one warp serves
+// the others: -17 % stage time at every block size tried; one 640-thread CTA per SM loses that again to
+// barrier waits, 4 x 128 and 2 x 256 measured the same; (2) the Disney path evaluates f() and pdf() for
+// the light direction and for the cosine sample through one copy of the code (Bsdf::eval).
+#ifndef KRR_SCATTER_BLOCK
+#define KRR_SCATTER_BLOCK 128
 #endif
+#ifndef KRR_SCATTER_MINB
+#define KRR_SCATTER_MINB 4
+#endif
+#ifndef KRR_SCATTER_LOCKSTEP
+#define KRR_SCATTER_LOCKSTEP 1
+#endif
+constexpr int kScatterBlock = KRR_SCATTER_BLOCK;
 template <int MT, bool MOTION>
-__global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
+__global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc = wf.counters + depth;
@@ -665,6 +679,10 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 	for (int it = 0; it < nIter; it++) {
 		int k		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
 		bool active = k < n;
+		// block-uniform: every thread of the CTA has an item and takes the same top-level path (with
+		// rrInTrace no path ends inside this stage before the phases below), so barriers are legal
+		const bool lock = KRR_SCATTER_LOCKSTEP && wf.p.rrInTrace && it * stride + (blockIdx.x + 1) * blockDim.x <= n;
+#define KRR_PHASE() do { if (lock) __syncthreads(); } while (0)
 		bool pushShadow = false, pushNext = false;
 		// shadow item
 		V3 so, sdv;
@@ -687,7 +705,9 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 			if (alive) {
 				Spec thp = ldcs4(q.thp + i) / wf.p.probRR, pu = ldcs4(q.pu + i);
 				SurfaceGeom g;
+				KRR_PHASE();
 				rebuildGeometry<MOTION>(wf, hit, mk3(d4), time, g);
+				KRR_PHASE();
 				float lam = wf.px.lambda[pix];
 				Wavelengths wl = expandWavelengths(lam);
 				ShadingData sd;
@@ -697,19 +717,24 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 					wf.px.lambda[pix] = -lam;
 					wl = expandWavelengths(-lam);
 				}
+				KRR_PHASE();
 				auto toLocal = [&](V3 v) { return mk3(dot(g.tangent, v), dot(g.bitangent, v), dot(g.n, v)); };
 				V3 woLocal = toLocal(g.wo);
 				int bsdfType = getBsdfType(sd);
 				Bsdf<MT> bsdf;
 				BsdfSetupCtx ctx{g.wo, &wl, &wf.scene.cs};
 				bsdf.setup(sd, ctx);
+				KRR_PHASE();
+				// [A] light sample of the next-event estimation (draws: light, u0, u1)
+				bool needL = false, delta = false;
+				LightSample ls;
+				V3 p_o = mk3(0, 0, 0), dd = p_o, wiL = p_o;
+				float lightPdf = 0;
 				if (wf.p.nee && (bsdfType & BSDF_SMOOTH)) {
 					float ul = rng.get1D();
 					uint32_t lightId = (uint32_t) (ul * wf.scene.nLights);
 					const LightRec lr = wf.scene.lights[lightId];
 					float u0 = rng.get1D(), u1 = rng.get1D();
-					LightSample ls;
-					bool delta = false;
 					if (lr.type == LIGHT_DIFFUSE_AREA) {
 						const TriLightRec &tl = wf.scene.triLights[lr.index];
 						ls = areaLightSampleLi(tl, wf.scene.instances[tl.inst], u0, u1, g.p, wl, wf.scene.cs);
@@ -720,26 +745,61 @@ __global__ void __launch_bounds__(128, KRR_SCATTER_MINB) k_scatter(const __grid_
 					}
 					// spawnRayTo(ls.intr), raytracing.h:148-157
 					auto offs = [](V3 p, V3 n, V3 w) { V3 off = n * kRayEps; if (dot(n, w) < 0.f) off = -off; return p + off; };
-					V3 to  = offs(ls.p, ls.n, g.p - ls.p);
-					V3 p_o = offs(g.p, g.n, to - g.p);
-					V3 dd  = to - p_o;
-					V3 wiWorld = normalize(dd), wiLocal = toLocal(wiWorld);
-					float lightPdf = lightSelPdf * ls.pdf;
-					Spec bsdfVal   = bsdf.f(woLocal, wiLocal);
-					float bsdfPdf  = delta ? 0.f : bsdf.pdf(woLocal, wiLocal);
-					if (lightPdf > 0 && any(bsdfVal)) {
-						Spec Ld = ls.L * thp * bsdfVal * fabsf(wiLocal.z);
-						if (any(Ld)) {
-							pushShadow = true;
-							so = p_o, sdv = dd;
-							const MeshRec &smesh = wf.scene.meshes[g.mesh]; // spawnRayTo: medium = getMedium(d)
-							sMedium = smesh.mediumIn != smesh.mediumOut ? (dot(dd, g.n) > 0 ? smesh.mediumOut : smesh.mediumIn) : medium;
-							sPu = pu * bsdfPdf, sPl = pu * lightPdf;
-							sContrib = wf.p.enableMedium ? Ld : Ld / mean(sPl + sPu);
-						}
+					V3 to = offs(ls.p, ls.n, g.p - ls.p);
+					p_o	  = offs(g.p, g.n, to - g.p);
+					dd	  = to - p_o;
+					wiL	  = toLocal(normalize(dd));
+					lightPdf = lightSelPdf * ls.pdf;
+					needL	 = true;
+				}
+				// [B] BSDF value / pdf towards the light, and the BSDF sample (draws: lobe, u0, u1)
+				Spec bsdfVal = sp(0);
+				float bsdfPdf = 0;
+				BSDFSample bs;
+				if constexpr (MT == MAT_DISNEY) {
+					// the diffuse lobe's sample is a cosine-distributed direction followed by f() and pdf(), the
+					// same two functions the light direction needs: both go through ONE copy of the code
+					const int comp = bsdf.pickLobe(rng);
+					V3 wiS = mk3(0, 0, 1);
+					if (comp == 0) {
+						float u0 = rng.get1D(), u1 = rng.get1D();
+						wiS = cosineSampleHemisphere(u0, u1);
+						if (woLocal.z < 0) wiS.z *= -1;
+					}
+					Spec fS = sp(0);
+					float pS = 0;
+#pragma unroll 1
+					for (int c = 0; c < 2; c++) {
+						KRR_PHASE();
+						const bool need = c == 0 ? needL : comp == 0;
+						const V3 wi		= c == 0 ? wiL : wiS;
+						Spec fv	 = sp(0);
+						float pv = 0;
+						if (need) bsdf.eval(woLocal, wi, fv, pv);
+						if (c == 0) bsdfVal = fv, bsdfPdf = pv;
+						else fS = fv, pS = pv;
+					}
+					KRR_PHASE();
+					if (comp == 0) bs = BSDFSample{fS, wiS, pS, BSDF_DIFFUSE_REFLECTION};
+					else bs = bsdf.sampleSpecular(comp, woLocal, rng);
+				} else {
+					if (needL) bsdfVal = bsdf.f(woLocal, wiL), bsdfPdf = bsdf.pdf(woLocal, wiL);
+					KRR_PHASE();
+					bs = bsdf.sample(woLocal, rng);
+				}
+				KRR_PHASE();
+				if (delta) bsdfPdf = 0.f;
+				if (needL && lightPdf > 0 && any(bsdfVal)) {
+					Spec Ld = ls.L * thp * bsdfVal * fabsf(wiL.z);
+					if (any(Ld)) {
+						pushShadow = true;
+						so = p_o, sdv = dd;
+						const MeshRec &smesh = wf.scene.meshes[g.mesh]; // spawnRayTo: medium = getMedium(d)
+						sMedium = smesh.mediumIn != smesh.mediumOut ? (dot(dd, g.n) > 0 ? smesh.mediumOut : smesh.mediumIn) : medium;
+						sPu = pu * bsdfPdf, sPl = pu * lightPdf;
+						sContrib = wf.p.enableMedium ? Ld : Ld / mean(sPl + sPu);
 					}
 				}
-				BSDFSample bs = bsdf.sample(woLocal, rng);
 				if (bs.pdf != 0 && any(bs.f)) {
 					V3 wiWorld = g.tangent * bs.wi.x + g.bitangent * bs.wi.y + g.n * bs.wi.z;
 					nthp = thp * bs.f * fabsf(bs.wi.z) / bs.pdf;
