@@ -86,6 +86,7 @@ struct KrrWfpt {
 	float probRR = 0.8f, clampMax = 1e3f;
 	bool nee = true, enableMedium = true, enableClamp = false;
 	bool rrInTrace = true; // "rr_in_trace": internal scheduling switch (not a reference parameter), see Params::rrInTrace
+	int flatBlasMax = 48;	 // "flat_blas_max": a BLAS with at most this many triangles is a flat list (takes effect at set_scene)
 	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
 	bool haveScene = false, haveColorSpace = false, frameBegun = false;
@@ -167,6 +168,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->spp			= j.value("spp", h->spp);
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
+		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
@@ -364,8 +366,8 @@ int buildAccel(KrrWfpt *h) {
 	if (h->anyMotion) mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p;
 	mw.w0 = h->motionW0, mw.w1 = h->motionW1;
 	char err[256] = "";
-	if (!h->bvh.build(h->positions.p, h->indices.p, h->hMeshes.data(), nMesh, h->instances.p, h->hInstances.data(), nInst, any ? merge.data() : nullptr, mw,
-					  nullptr, err))
+	if (!h->bvh.build(h->positions.p, h->indices.p, h->hMeshes.data(), nMesh, h->instances.p, h->hInstances.data(), nInst, any ? merge.data() : nullptr,
+					  h->flatBlasMax, mw, nullptr, err))
 		return fail(KRR_E_CUDA, "%s", err);
 	for (int i = 0; i < nMesh; i++) h->hMeshes[i].blasRoot = h->bvh.blasRoot(i), h->hMeshes[i].triBase = h->bvh.triBase(i);
 	for (int i = 0; i < nInst; i++) h->hInstances[i].blasRoot = up[i].blasRoot = h->hMeshes[h->hInstances[i].mesh].blasRoot;

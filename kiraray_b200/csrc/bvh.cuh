@@ -52,6 +52,11 @@ struct BvhDev {
 	int32_t mergedInst; // -1 = nothing merged
 	int32_t mergedRoot;
 	int32_t mergedOnly;
+	// A BLAS with at most `flat_blas_max` triangles is not a tree but a FLAT LIST: its root entry is
+	// kFlatFlag | index into flats[] = (first triangle, count).  A warp walks such a list in lock step
+	// (no stack, no slab tests, no divergence between lanes), which for a few dozen triangles costs
+	// fewer issue slots than the wide-node traversal it replaces.
+	const int2 *flats;
 };
 
 struct Hit {
@@ -97,11 +102,13 @@ KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 //   node     : index into the node pool                                     (bits 31,30 = 00)
 //   leaf     : kLeafFlag | (count-1) << 26 | first triangle                 (bits 31,30 = 01)
 //   instance : kInstFlag | instance id  (TLAS leaves hold ONE instance)      (bits 31,30 = 10)
+//   flat BLAS: kFlatFlag | index into BvhDev::flats (only ever a BLAS root)  (bits 31,30 = 11, != empty)
 constexpr int kShortStack  = 12;
 constexpr int kLocalStack  = 52;
 constexpr int kStackSize   = kShortStack + kLocalStack;
 constexpr int kTraceBlock  = 128;
-constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kEmptyEntry = 0xffffffffu;
+constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kFlatFlag = 0xc0000000u, kEmptyEntry = 0xffffffffu;
+KRR_HD bool isFlatEntry(uint32_t e) { return (e >> 30) == 3u && e != kEmptyEntry; }
 
 struct TraceSmem {
 	uint32_t id[kShortStack][kTraceBlock];
@@ -185,7 +192,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			// equal-t candidate with a smaller (instance, primitive) must still be tested)
 			if (!ANY && tn > best.t * 1.0000010f + 1e-30f) cur = kEmptyEntry;
 		}
-		return cur < kLeafFlag ? NODE : ((cur & kInstFlag) ? ENTER : LEAF);
+		return cur < kLeafFlag ? NODE : ((cur >> 30) == 2u ? ENTER : LEAF);
 	}
 	// ---- phase 1: enter an instance (object-space ray; t stays the world parameter) ----
 	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm) {
@@ -216,19 +223,26 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
 			const float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
 			const float lim = best.t;
+			// The byte -> float conversions (48 per node, quarter-rate I2F) are replaced by a byte permute that
+			// drops q into the mantissa of 2^23: v = 2^23 + 256 q, and q*a + b = v*(a/256) + (b - 2^15 a) in one
+			// FMA.  b - 2^15 a is rounded once: error <= |a| / 512, i.e. 1/512 of a quantisation step, against
+			// the full step the builder pads every child plane with (quantize() in bvh_build.cu).
+			const float axs = ax * 0.00390625f, ays = ay * 0.00390625f, azs = az * 0.00390625f;
+			const float bxs = fmaf(-32768.f, ax, bx), bys = fmaf(-32768.f, ay, by), bzs = fmaf(-32768.f, az, bz);
 			// rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
 			// when the ray grazes an axis-aligned plane): the test and the stored entry distance are widened
 			// by it, so flat boxes are never culled by arithmetic noise
-			const float slack = ((fabsf(bx) + 255.f * fabsf(ax)) + (fabsf(by) + 255.f * fabsf(ay)) + (fabsf(bz) + 255.f * fabsf(az))) * 2.4e-7f;
+			const float slack = ((fabsf(bx) + 255.f * fabsf(ax)) + (fabsf(by) + 255.f * fabsf(ay)) + (fabsf(bz) + 255.f * fabsf(az))) * 2.4e-7f +
+								(fabsf(ax) + fabsf(ay) + fabsf(az)) * 0.00390625f;
 			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
 			auto child = [&](int i) -> uint32_t {
 				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
 				bool internal = (imask >> i) & 1;
 				if (!internal && meta == 0) return kEmptyEntry;
-				auto qb = [&](int row) { return (float) ((q[row * 2 + (i >> 2)] >> ((i & 3) * 8)) & 0xff); };
-				float t0x = qb(0) * ax + bx, t1x = qb(3) * ax + bx;
-				float t0y = qb(1) * ay + by, t1y = qb(4) * ay + by;
-				float t0z = qb(2) * az + bz, t1z = qb(5) * az + bz;
+				auto qb = [&](int row) { return __uint_as_float(__byte_perm(q[row * 2 + (i >> 2)], 0x4b000000u, 0x7404u | ((i & 3) << 4))); };
+				float t0x = fmaf(qb(0), axs, bxs), t1x = fmaf(qb(3), axs, bxs);
+				float t0y = fmaf(qb(1), ays, bys), t1y = fmaf(qb(4), ays, bys);
+				float t0z = fmaf(qb(2), azs, bzs), t1z = fmaf(qb(5), azs, bzs);
 				// fminf/fmaxf drop NaNs (0 * inf), which is the conservative answer for a degenerate slab
 				float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
 				float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), lim));
@@ -268,7 +282,11 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 	}
 	// ---- phase 3: leaf (1..7 triangles).  Returns true when an any-hit ray terminated. ----
 	template <typename Accept> KRR_DEV bool leaf(const BvhDev &bvh, Accept accept) {
-		const uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
+		uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
+		if ((cur >> 30) == 3u) { // flat BLAS: the whole triangle list
+			const int2 fr = __ldg(bvh.flats + (cur & 0x3fffffffu));
+			first = (uint32_t) fr.x, cnt = (uint32_t) fr.y;
+		}
 		cur = kEmptyEntry;
 		for (uint32_t k = 0; k < cnt; k++) {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
@@ -292,7 +310,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		while (true) {
 			int st = next(sm, ls);
 			if (st == FINISHED) return;
-			if (st == ENTER) { enterInstance(bvh, instances, sm); st = NODE; }
+			if (st == ENTER) { enterInstance(bvh, instances, sm); st = (cur >> 30) == 3u ? LEAF : NODE; }
 			if (st == NODE) {
 				node(bvh, sm, ls);
 				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
@@ -316,7 +334,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			fin = st == FINISHED;
 		}
 		if (__any_sync(FULL, st == ENTER)) {
-			if (st == ENTER) { enterInstance(bvh, instances, sm); st = NODE; }
+			if (st == ENTER) { enterInstance(bvh, instances, sm); st = (cur >> 30) == 3u ? LEAF : NODE; }
 		}
 		if (VOTE) {
 			const unsigned mN = __ballot_sync(FULL, st == NODE), mL = __ballot_sync(FULL, st == LEAF);

@@ -310,6 +310,12 @@ struct InstWriter {
 	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const { tlasInst[slot] = ids[prim]; }
 };
 
+// flat BLAS (<= flatMax triangles): the leaf payload in primitive order, no nodes
+template <typename Writer> __global__ void k_write_flat(int n, uint32_t base, Writer writer) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) writer(base + i, (uint32_t) i);
+}
+
 template <typename Writer>
 __global__ void k_collapse(const WorkItem *__restrict__ in, int nIn, WorkItem *out, int32_t *nOut, BinTree t, int n,
 						   const uint32_t *__restrict__ sortedIdx, int maxLeaf, CollapseOut co, Writer writer) {
@@ -462,7 +468,8 @@ struct BvhBuilder::Impl {
 	DevBuf<int32_t> tlasInst;
 	DevBuf<Aabb> meshBoxes, instBoxes;
 	DevBuf<int32_t> counters, tlasIds;
-	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0;
+	DevBuf<int2> flats;
+	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0, nFlat = 0;
 	std::vector<int> tlasLevelStart; // node index (relative to the pool) where each TLAS level begins
 	int tlasNodeCount = 0, totalNodes = 0, totalTris = 0, nInstances = 0, nMeshes = 0;
 	std::vector<int32_t> blasRoots, triBases;
@@ -534,9 +541,10 @@ bool buildTree(const Aabb *boxes, int n, int maxLeaf, Node8 *nodePool, Aabb *bou
 } // namespace
 
 bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes,
-					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const uint8_t *hMerge, const MotionWindow &motion,
-					   cudaStream_t stream, char *err) {
+					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const uint8_t *hMerge, int flatMax,
+					   const MotionWindow &motion, cudaStream_t stream, char *err) {
 	Impl &b = *m;
+	std::vector<int2> flats;
 	b.nMeshes = nMeshes, b.nInstances = nInstances;
 	// which instances go into the merged world-space BLAS, which meshes still need a BLAS of their own
 	std::vector<MergedSrc> msrc;
@@ -589,6 +597,13 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		k_mesh_box<<<1, 256, 0, stream>>>(primBoxes.p, mr.nTri, b.meshBoxes.p + i);
 		TriWriter wr{dPositions + 3 * (size_t) mr.posOff, dIndices + 3 * (size_t) mr.idxOff, b.tris.p};
 		b.triBases[i] = primCursor;
+		if (mr.nTri <= flatMax) { // flat list instead of a tree
+			k_write_flat<<<(mr.nTri + T - 1) / T, T, 0, stream>>>(mr.nTri, (uint32_t) primCursor, wr);
+			b.blasRoots[i] = (int32_t) (kFlatFlag | (uint32_t) flats.size());
+			flats.push_back(make_int2(primCursor, mr.nTri));
+			primCursor += mr.nTri;
+			continue;
+		}
 		int root = 0;
 		if (!buildTree(primBoxes.p, mr.nTri, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
 			return false;
@@ -606,11 +621,22 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		k_prim_bounds_merged<<<grid, T, 0, stream>>>(dPositions, dIndices, dsrc.p, (int) msrc.size(), primBoxes.p, pairs.p, cb.p);
 		k_mesh_box<<<1, 256, 0, stream>>>(primBoxes.p, (int) mergedTris, b.meshBoxes.p + nMeshes);
 		MergedTriWriter wr{dPositions, dIndices, dsrc.p, pairs.p, b.tris.p};
-		int root = 0;
-		if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
-			return false;
-		b.mergedRoot = root;
+		if ((int) mergedTris <= flatMax) {
+			k_write_flat<<<((int) mergedTris + T - 1) / T, T, 0, stream>>>((int) mergedTris, (uint32_t) primCursor, wr);
+			b.mergedRoot = (int32_t) (kFlatFlag | (uint32_t) flats.size());
+			flats.push_back(make_int2(primCursor, (int) mergedTris));
+			primCursor += (int) mergedTris;
+			CK(cudaStreamSynchronize(stream)); // dsrc / pairs die with this scope
+		} else {
+			int root = 0;
+			if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
+				return false;
+			b.mergedRoot = root;
+		}
 	}
+	b.nFlat = (int) flats.size();
+	if (!b.flats.alloc(flats.size())) { snprintf(err, 256, "bvh build: alloc failed (flat table)"); return false; }
+	if (!flats.empty()) CK(cudaMemcpyAsync(b.flats.p, flats.data(), flats.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
 	b.totalTris = primCursor;
 	b.totalNodes = nodeCursor;
 	// TLAS over the world boxes of its primitives (one instance per leaf child)
@@ -655,12 +681,14 @@ BvhDev BvhBuilder::device() const {
 	d.nodes = m->nodes.p, d.tris = m->tris.p, d.tlasInst = m->tlasInst.p, d.tlasRoot = 0, d.nInstances = m->nInstances;
 	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
 	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot;
+	d.flats = m->flats.p;
 	d.mergedOnly = m->mergedInst >= 0 && m->nTlasPrims == 1; // the pseudo-instance is the only TLAS primitive
 	return d;
 }
 int BvhBuilder::blasRoot(int mesh) const { return m->blasRoots[mesh]; }
 int BvhBuilder::mergedRoot() const { return m->mergedRoot; }
 int BvhBuilder::mergedTriCount() const { return m->nMergedTris; }
+int BvhBuilder::flatCount() const { return m->nFlat; }
 int BvhBuilder::triBase(int mesh) const { return m->triBases[mesh]; }
 int BvhBuilder::nodeCount() const { return m->totalNodes - (m->nInstances + 2) + m->tlasNodeCount; }
 int BvhBuilder::tlasNodeCount() const { return m->tlasNodeCount; }

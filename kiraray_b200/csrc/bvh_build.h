@@ -25,7 +25,9 @@ public:
 	// must then hold nInstances + 1 records, the last one being that pseudo-instance (identity,
 	// mesh = nMeshes, blasRoot patched by the caller from mergedRoot()).
 	bool build(const float *dPositions, const int32_t *dIndices, const MeshRec *hMeshes, int nMeshes, const InstRec *dInstances,
-			   const InstRec *hInstances, int nInstances, const uint8_t *hMerge, const MotionWindow &motion, cudaStream_t stream, char *err);
+			   const InstRec *hInstances, int nInstances, const uint8_t *hMerge, int flatMax, const MotionWindow &motion, cudaStream_t stream,
+			   char *err);
+	int flatCount() const; // BLASes stored as flat triangle lists (<= flatMax triangles; see BvhDev::flats)
 	int mergedRoot() const;		// node index of the merged BLAS root, -1 = none
 	int mergedTriCount() const;
 	// Re-fits the TLAS after instance transforms (or the motion window) changed; topology kept, no

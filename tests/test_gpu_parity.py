@@ -149,7 +149,7 @@ def test_merged_static_blas_gives_the_identical_film(cbox_app):
     cam = app.camera()
     out = []
     for flag in (False, True):
-        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=flag))
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=flag, flat_blas_max=0))
         gpu.set_scene(app.scene_desc())
         gpu.resize(w, h)
         gpu.begin_frame(3, cam)
@@ -187,3 +187,25 @@ def test_moving_a_merged_instance_takes_it_out_of_the_merged_blas(cbox_app):
     gpu = make_gpu(app, w, h)
     gpu.begin_frame(2, cam)
     assert not np.array_equal(gpu.render_to_host().view(np.uint32), out[1][0].view(np.uint32))
+
+
+@pytest.mark.parametrize("merge", [False, True])
+def test_flat_blas_gives_the_identical_film(cbox_app, merge):
+    """A BLAS of at most flat_blas_max triangles is walked as a flat list instead of a tree: same
+    triangle test, same tie-break, so hits, counts and film are identical bit for bit."""
+    w = h = 64
+    app = cbox_app(w, h, spp=2, max_depth=6)
+    cam = app.camera()
+    out = []
+    for flat in (0, 48):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=merge, flat_blas_max=flat))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(w, h)
+        gpu.begin_frame(3, cam)
+        film = gpu.render_to_host()
+        out.append((film, gpu.stats(), gpu.first_hits()))
+    assert out[1][1]["bvh_nodes"] < out[0][1]["bvh_nodes"]
+    assert np.array_equal(out[0][2][0], out[1][2][0]) and np.array_equal(out[0][2][1], out[1][2][1])
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    for k in ("closest_rays", "shadow_rays", "scatter_items", "hit_light_items", "miss_items"):
+        assert out[0][1][k] == out[1][1][k], k
