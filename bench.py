@@ -275,15 +275,25 @@ def main():
         peak, peak_src = load_peaks()
         value = rays / (ms * 1e-3) / 1e6
         e2e = rays / (ms_e2e * 1e-3) / 1e6
-        # dominant kernel = the stage with the largest share of the profiled step
-        dom = max(("closest", "scatter", "shadow"), key=lambda k: stages[k]["ms"])
-        units = {"closest": st["closest_rays"], "scatter": st["scatter_items"], "shadow": st["shadow_rays"]}[dom]
+        # dominant kernel = the stage with the largest share of the profiled step.  The fused trace launch
+        # (k_trace_fused) traces the shadow rays of depth d and the closest rays of depth d + 1: its units are
+        # rays of both kinds and its algorithmic bytes the sum of the two stages' figures.
+        cands = [k for k in ("closest", "scatter", "shadow", "trace") if stages[k]["launches"]]
+        dom = max(cands, key=lambda k: stages[k]["ms"])
+        names = {"closest": "k_trace_closest", "scatter": "k_scatter<Disney>", "shadow": "k_trace_shadow", "trace": "k_trace_fused"}
+        if dom == "trace":
+            c0 = st["closest_by_depth"][0] // max(1, args.spp) * args.spp  # depth-0 closest rays run in k_trace_closest
+            n_c, n_s = st["closest_rays"] - st["closest_by_depth"][0], st["shadow_rays"]
+            units, dom_bytes = n_c + n_s, n_c * STAGE_BYTES["closest"] + n_s * STAGE_BYTES["shadow"]
+        else:
+            units = {"closest": st["closest_rays"], "scatter": st["scatter_items"], "shadow": st["shadow_rays"]}[dom]
+            dom_bytes = units * STAGE_BYTES[dom]
         total_ms = sum(v["ms"] for v in stages.values())
-        dom_gbs = units * STAGE_BYTES[dom] / (stages[dom]["ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": {"closest": "k_trace_closest", "scatter": "k_scatter<Disney>", "shadow": "k_trace_shadow"}[dom],
+        dom_gbs = dom_bytes / (stages[dom]["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": names[dom],
                     "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom_gbs / peak,
-                    "traffic": load_traffic({"closest": "k_trace_closest", "scatter": "k_scatter", "shadow": "k_trace_shadow"}[dom]),
-                    "algorithmic_bytes_per_unit": STAGE_BYTES[dom], "units_per_step": units, "launches_per_step": stages[dom]["launches"],
+                    "traffic": load_traffic(names[dom].split("<")[0]),
+                    "algorithmic_bytes_per_unit": dom_bytes / max(1, units), "units_per_step": units, "launches_per_step": stages[dom]["launches"],
                     "avg_launch_ms": stages[dom]["ms"] / max(1, stages[dom]["launches"]),
                     "stage_share": {k: (v["ms"] / total_ms if total_ms else 0) for k, v in stages.items()},
                     "pipeline_achieved": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world) / peak}

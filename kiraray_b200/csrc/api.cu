@@ -87,6 +87,7 @@ struct KrrWfpt {
 	bool nee = true, enableMedium = true, enableClamp = false;
 	bool rrInTrace = true; // "rr_in_trace": internal scheduling switch (not a reference parameter), see Params::rrInTrace
 	int flatBlasMax = 48;	 // "flat_blas_max": a BLAS with at most this many triangles is a flat list (takes effect at set_scene)
+	bool fuseStages = true;	 // "fuse_stages": 2 launches per depth (hit/miss in the scatter launch, shadow + next closest in one trace launch)
 	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
 	bool haveScene = false, haveColorSpace = false, frameBegun = false;
@@ -168,6 +169,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->spp			= j.value("spp", h->spp);
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
+		h->fuseStages	= j.value("fuse_stages", h->fuseStages);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
@@ -730,12 +732,13 @@ struct StageTimer { // RAII: brackets one launch with events when profiling is o
 	}
 	~StageTimer() { if (on) { cudaEventRecord(rec.b, st); h->evRecs.push_back(rec); } }
 };
-template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st) {
+template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st, int &withHitMiss) {
 	static int grid = 0, gridM = 0;
 	if (!grid) grid = gridFor(h, k_scatter<MT, false>, kScatterBlock), gridM = gridFor(h, k_scatter<MT, true>, kScatterBlock);
 	StageTimer t(h, KRR_STAGE_SCATTER, st);
-	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, kScatterBlock, 0, st>>>(wf, depth);
-	else k_scatter<MT, false><<<grid, kScatterBlock, 0, st>>>(wf, depth);
+	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, kScatterBlock, 0, st>>>(wf, depth, withHitMiss);
+	else k_scatter<MT, false><<<grid, kScatterBlock, 0, st>>>(wf, depth, withHitMiss);
+	withHitMiss = 0; // only the first scatter launch of a depth carries the hit / miss prologue
 	h->launches++;
 }
 
@@ -774,16 +777,48 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		// [1] primary rays.  Queue counters were cleared by k_fold_counters of the previous sample
 		{ StageTimer t(h, KRR_STAGE_CAMERA, st); k_generate_camera_rays<<<gridCam, 256, 0, st>>>(wf); }
 		h->launches++;
-		for (int depth = 0; true; depth++) {
+		// Fused schedule (default; surface-only scenes with NEE): handleHit/Miss rides as the prologue of
+		// the scatter launch of its depth, and ONE trace launch covers the shadow rays of depth d and the
+		// closest rays of depth d + 1 -> 2 launches per depth instead of 4.  Debug captures and scenes with
+		// participating media keep the reference's stage order below.
+		const bool anyScatter = h->matTypePresent[MAT_DISNEY] || h->matTypePresent[MAT_DIFFUSE] || h->matTypePresent[MAT_DIELECTRIC] ||
+								h->matTypePresent[MAT_CONDUCTOR] || h->matTypePresent[MAT_NULL];
+		const bool fused = h->fuseStages && !media && h->nee && anyScatter && h->capSample != sampleId;
+		auto launchAllScatter = [&](int depth, int withHitMiss) {
+			if (h->matTypePresent[MAT_DISNEY]) launchScatter<MAT_DISNEY>(h, wf, depth, st, withHitMiss);
+			if (h->matTypePresent[MAT_DIFFUSE]) launchScatter<MAT_DIFFUSE>(h, wf, depth, st, withHitMiss);
+			if (h->matTypePresent[MAT_DIELECTRIC]) launchScatter<MAT_DIELECTRIC>(h, wf, depth, st, withHitMiss);
+			if (h->matTypePresent[MAT_CONDUCTOR]) launchScatter<MAT_CONDUCTOR>(h, wf, depth, st, withHitMiss);
+			if (h->matTypePresent[MAT_NULL]) launchScatter<MAT_NULL>(h, wf, depth, st, withHitMiss);
+		};
+		auto launchHitMiss = [&](int depth) {
+			StageTimer t(h, KRR_STAGE_HIT_MISS, st);
+			if (motion) k_handle_hit_miss<true><<<gridHitM, 128, 0, st>>>(wf, depth);
+			else k_handle_hit_miss<false><<<gridHit, 128, 0, st>>>(wf, depth);
+			h->launches++;
+		};
+		auto launchClosest = [&](int depth) {
+			StageTimer t(h, KRR_STAGE_CLOSEST, st);
+			if (motion) k_trace_closest<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
+			else k_trace_closest<false><<<gridTrace, 128, 0, st>>>(wf, depth);
+			h->launches++;
+		};
+		if (fused) {
+			launchClosest(0);
+			for (int depth = 0; depth < h->maxDepth; depth++) {
+				launchAllScatter(depth, 1);
+				StageTimer t(h, KRR_STAGE_TRACE, st);
+				if (motion) k_trace_fused<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
+				else k_trace_fused<false><<<gridTrace, 128, 0, st>>>(wf, depth);
+				h->launches++;
+			}
+			launchHitMiss(h->maxDepth);
+		}
+		for (int depth = 0; !fused; depth++) {
 			const bool cap = h->capSample == sampleId && h->capDepth == depth;
 			if (cap && capture(h, wf, depth, 0, st)) return KRR_E_CUDA;
 			// [2.1] closest hits
-			{
-				StageTimer t(h, KRR_STAGE_CLOSEST, st);
-				if (motion) k_trace_closest<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
-				else k_trace_closest<false><<<gridTrace, 128, 0, st>>>(wf, depth);
-			}
-			h->launches++;
+			launchClosest(depth);
 			// [2.2] medium interactions along the rays that travel inside a medium
 			if (media) {
 				{ StageTimer t(h, KRR_STAGE_MEDIUM, st); k_medium_sample<<<gridMSample, 128, 0, st>>>(wf, depth); }
@@ -791,23 +826,14 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			}
 			if (cap) for (int q = 1; q <= 3; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.3] emitted / environment radiance
-			{
-				StageTimer t(h, KRR_STAGE_HIT_MISS, st);
-				if (motion) k_handle_hit_miss<true><<<gridHitM, 128, 0, st>>>(wf, depth);
-				else k_handle_hit_miss<false><<<gridHit, 128, 0, st>>>(wf, depth);
-			}
-			h->launches++;
+			launchHitMiss(depth);
 			if (depth == h->maxDepth) break;
 			if (media) {
 				{ StageTimer t(h, KRR_STAGE_MEDIUM, st); k_medium_scatter<<<gridMScatter, 128, 0, st>>>(wf, depth); }
 				h->launches++;
 			}
 			// [2.4] BSDF sampling + NEE, one launch per material type present in the scene
-			if (h->matTypePresent[MAT_DISNEY]) launchScatter<MAT_DISNEY>(h, wf, depth, st);
-			if (h->matTypePresent[MAT_DIFFUSE]) launchScatter<MAT_DIFFUSE>(h, wf, depth, st);
-			if (h->matTypePresent[MAT_DIELECTRIC]) launchScatter<MAT_DIELECTRIC>(h, wf, depth, st);
-			if (h->matTypePresent[MAT_CONDUCTOR]) launchScatter<MAT_CONDUCTOR>(h, wf, depth, st);
-			if (h->matTypePresent[MAT_NULL]) launchScatter<MAT_NULL>(h, wf, depth, st);
+			launchAllScatter(depth, 0);
 			if (cap) for (int q = 4; q <= 5; q++) if (capture(h, wf, depth, q, st)) return KRR_E_CUDA;
 			// [2.5] shadow rays
 			if (h->nee) {

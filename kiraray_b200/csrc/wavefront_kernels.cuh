@@ -272,8 +272,8 @@ struct WarpWork {
 	bool exhausted; // warp-uniform
 	int claim;
 	// per: items a warp starts with (one per lane); claim_: items per later atomic claim
-	KRR_DEV void init(int n_, int32_t *cursor_, int per = 32, int claim_ = kClaim) {
-		const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+	// warp / nWarps: this warp's index among the warps that work on the queue
+	KRR_DEV void init(int n_, int32_t *cursor_, int warp, int nWarps, int per = 32, int claim_ = kClaim) {
 		n = n_, cursor = cursor_, first = nWarps * per, claim = claim_;
 		next = warp * per, end = min(next + per, n_);
 		exhausted = false;
@@ -343,9 +343,10 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
 }
 
+// block / nBlocks: this CTA's index among the CTAs that run the closest stage (the fused trace kernel
+// splits its grid between the shadow rays of one depth and the closest rays of the next)
 template <bool MOTION>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
-	__shared__ TraceSmem sm;
+KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int block, int nBlocks) {
 	const RayQueue q	= wf.rays[depth & 1];
 	const RayQueue nq	= wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc	= wf.counters + depth;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 	int pix	  = 0;	   // its pixel (fetched with the ray: the finalisation needs it first)
 	bool done = false; // traversal finished, result in tr.best, not yet finalised
 	WarpWork work;
-	work.init(n, &dc->cursorRay);
+	work.init(n, &dc->cursorRay, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
 	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
 	int medium = -1; // medium the ray travels in (d_medium.w)
 	while (true) {
@@ -446,6 +447,12 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_cons
 		});
 		done |= fin;
 	}
+}
+
+template <bool MOTION>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
+	traceClosestBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
 // =================================================================================================
@@ -590,8 +597,10 @@ KRR_DEV void evalMaterial(const Wavefront &wf, SurfaceGeom &g, const Wavelengths
 
 // =================================================================================================
 // handleHit + handleMiss (integrator.cpp:78-108)
+// Out of line: the scatter stage of the same depth runs it as a prologue (one launch less per depth;
+// the queues of this stage are short: a few light hits, and misses only matter with an environment light)
 template <bool MOTION>
-__global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__ Wavefront wf, int depth) {
+__device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
 	DepthCounters *dc = wf.counters + depth;
 	const int stride  = gridDim.x * blockDim.x;
@@ -648,6 +657,11 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 	}
 }
 
+template <bool MOTION>
+__global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__ Wavefront wf, int depth) {
+	handleHitMissBody<MOTION>(wf, depth);
+}
+
 // =================================================================================================
 // generateScatterRays (integrator.cpp:110-164), one launch per material type
 // The Disney instantiation is ~11k SASS instructions (180 KB) against a 32 KB instruction cache, and
@@ -668,7 +682,9 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 #endif
 constexpr int kScatterBlock = KRR_SCATTER_BLOCK;
 template <int MT, bool MOTION>
-__global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth) {
+__global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth, int withHitMiss) {
+	// handleHit / handleMiss of this depth (they touch L only, this stage does not)
+	if (withHitMiss) handleHitMissBody<MOTION>(wf, depth);
 	const RayQueue q  = wf.rays[depth & 1];
 	const RayQueue nq = wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc = wf.counters + depth;
@@ -844,8 +860,7 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 // Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean().  Same persistent
 // warp scheme as the closest stage; the ray terminates at the first accepted hit.
 template <bool MOTION>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
-	__shared__ TraceSmem sm;
+KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int block, int nBlocks) {
 	DepthCounters *dc	= wf.counters + depth;
 	const int n			= dc->nShadow;
 	const unsigned FULL = 0xffffffffu;
@@ -855,7 +870,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	int ray = -1, pix = 0;
 	bool done = false; // traversal finished, radiance not yet added
 	WarpWork work;
-	work.init(n, &dc->cursorShadow);
+	work.init(n, &dc->cursorShadow, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
 	if (work.next >= n) return;
 	while (true) {
 		// finished rays add their contribution in batches (same reasoning as in the closest stage: the
@@ -891,6 +906,28 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 		});
 		done |= fin;
 	}
+}
+
+template <bool MOTION>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
+	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
+}
+
+// Fused trace stage: the shadow rays of `depth` and the closest rays of `depth + 1` were both produced
+// by the scatter stage of `depth` and do not depend on each other (the shadow stage only adds to L, the
+// closest stage only draws the Russian-roulette sample; handleHit/Miss of depth + 1 runs afterwards, so
+// the order of the additions to a pixel's L is unchanged).  One launch traces both: every warp first
+// works on the closest queue and, when that is exhausted, moves on to the shadow queue, so the tail of
+// one overlaps the head of the other and a launch per depth is saved.  (A static split of the grid
+// between the two queues measured slower than two launches: the cost ratio of the two ray kinds moves
+// with depth.)  Not used with participating media (the transmittance shadow rays draw random numbers).
+template <bool MOTION>
+__global__ void __launch_bounds__(kTraceBlock, 7) k_trace_fused( // 7 CTAs/SM = the occupancy of the two stand-alone kernels (72 registers)
+const __grid_constant__ Wavefront wf, int depth) {
+	__shared__ TraceSmem sm;
+	traceClosestBody<MOTION>(wf, depth + 1, sm, blockIdx.x, gridDim.x);
+	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
 // =================================================================================================

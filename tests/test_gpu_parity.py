@@ -209,3 +209,24 @@ def test_flat_blas_gives_the_identical_film(cbox_app, merge):
     assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
     for k in ("closest_rays", "shadow_rays", "scatter_items", "hit_light_items", "miss_items"):
         assert out[0][1][k] == out[1][1][k], k
+
+
+def test_fused_schedule_gives_the_identical_film(cbox_app):
+    """fuse_stages (default): handleHit/Miss as the prologue of the scatter launch, shadow rays of depth
+    d and closest rays of depth d + 1 in one trace launch.  Per pixel the order of RNG draws and of the
+    additions to L is unchanged, so the film and every counter must be identical bit for bit."""
+    w = h = 64
+    app = cbox_app(w, h, spp=2, max_depth=6)
+    cam = app.camera()
+    out = []
+    for flag in (False, True):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), fuse_stages=flag))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(w, h)
+        gpu.begin_frame(3, cam)
+        film = gpu.render_to_host()
+        out.append((film, gpu.stats()))
+    assert out[1][1]["kernel_launches"] < out[0][1]["kernel_launches"]
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    for k in ("closest_rays", "shadow_rays", "scatter_items", "hit_light_items", "miss_items", "closest_by_depth", "shadow_by_depth"):
+        assert out[0][1][k] == out[1][1][k], k
