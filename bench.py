@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--spp", type=int, default=8, help="samples per pixel per frame (one step = one frame)")
     ap.add_argument("--ref-rows", type=int, default=0, help="rows of the frame the CPU reference renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--params", default="", help="extra pass parameters as JSON (tuning switches, e.g. '{\"pdl\": false}')")
     ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
     args = ap.parse_args()
 
@@ -188,7 +189,7 @@ def main():
     part = make_partition(rank, world, H, args.partition)
     app = make_app(args.spp)
     cam = app.camera()
-    gpu = krr.Wfpt(params=dict(app.wfpt_params()))
+    gpu = krr.Wfpt(params=dict(app.wfpt_params(), **(json.loads(args.params) if args.params else {})))
     gpu.set_scene(app.scene_desc())
     gpu.resize(W, H)
     if part.tiles > 1:

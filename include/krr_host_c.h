@@ -35,6 +35,31 @@ int krr_host_app_render_frames(KrrHostApp *app, int32_t n_frames, float *film_ho
 /* the pass's C-ABI handle (NULL before the first render) and frame counter */
 KrrWfpt *krr_host_app_wfpt_handle(KrrHostApp *app);
 uint64_t krr_host_app_frame_index(KrrHostApp *app);
+/* RenderApp main loop without a window (DeviceManager::runMessageLoop, window.cpp:450-485): frames until a
+ * pass requests the exit (AccumulatePass "exit_on_finish" with a spent "task" budget) or max_frames (0 = no
+ * cap); then RenderApp::finalize -> finalize() on every pass ("save_on_finish", ErrorMeasure "save").
+ * Returns the number of frames rendered (>= 0) or a negative error. */
+int krr_host_app_run(KrrHostApp *app, int32_t max_frames, int32_t finalize);
+/* File::outputDir() of this app ("output_dir" of the config, else <config dir>/output) */
+int krr_host_app_set_output_dir(KrrHostApp *app, const char *dir);
+/* a pass's parameters as JSON (to_json of the pass), by pass name; returns length or < 0 */
+int krr_host_app_get_pass_json(KrrHostApp *app, const char *pass_name, char *buf, int32_t capacity);
+/* AccumulatePass: frames accumulated so far / accumulated average read back (RGBA32F, film layout) */
+int64_t krr_host_app_accum_count(KrrHostApp *app);
+int krr_host_app_read_accumulated(KrrHostApp *app, float *rgba_host);
+/* ErrorMeasurePass: set the reference from memory (film layout), ask for an evaluation in the next frame
+ * (the UI's "Evaluate" button), read the last result; value_out may be NULL when nothing was evaluated */
+int krr_host_app_set_reference(KrrHostApp *app, const float *rgba_host, int32_t w, int32_t h);
+int krr_host_app_evaluate_next_frame(KrrHostApp *app);
+int krr_host_app_last_error_metric(KrrHostApp *app, double *value_out, int32_t *n_evaluations_out);
+
+/* HDR image files (Image::loadImage / saveImage, src/core/texture.cpp:27-118): .exr and .pfm, no GPU.
+ * load: first call with rgba_host = NULL to get the size.  flip: vertical flip as in the reference's API.
+ * save: reference_channel_order != 0 writes EXR planes the way KiRaRay's save_exr does (image.cpp). */
+int krr_host_image_load(const char *path, int32_t flip, int32_t *w, int32_t *h, float *rgba_host);
+int krr_host_image_save(const char *path, const float *rgba_host, int32_t w, int32_t h, int32_t flip, int32_t reference_channel_order);
+/* EXR writer with explicit storage options (half / float, none / ZIP) */
+int krr_host_image_save_exr(const char *path, const float *rgba_host, int32_t w, int32_t h, int32_t half_precision, int32_t zip);
 const char *krr_host_last_error(void);
 
 #if defined(__GNUC__)

@@ -331,6 +331,27 @@ int krr_wfpt_debug_instance_xf(KrrWfpt *h, const int32_t *instance_ids_host, con
 int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,
 					   uint64_t max_accum_count, int32_t moving_average, void *cuda_stream);
 
+/* the same in double precision ("precision": "double", accumulate.h:17, accumulate.cu:68-75): accum is
+ * device double4[n_pixels] */
+int krr_accumulate_f64(double *accum, float *film, int64_t n_pixels, uint64_t accum_count,
+					   uint64_t max_accum_count, int32_t moving_average, void *cuda_stream);
+/* AccumulatePass::saveImage (accumulate.cu:90-111): accumulated sum * (1 / accum_count) as RGBA32F into HOST
+ * memory; accum is the float4 (is_double = 0) or double4 (is_double = 1) device buffer.  Synchronises. */
+int krr_accumulate_read_average(const void *accum, int32_t is_double, uint64_t accum_count, int64_t n_pixels,
+								float *out_rgba_host, void *cuda_stream);
+
+/* ---- ErrorMeasurePass metric, src/render/passes/errormeasure/metrics.cu:64-128 ----
+ * film, reference: device float4[n_pixels]; *result_host = mean over pixels of the per-pixel error (mean over
+ * RGB, reference pixels with inf/NaN count 0, per-pixel error clamped at 100).  Synchronises the stream. */
+enum { KRR_METRIC_MSE = 0, KRR_METRIC_MAPE = 1, KRR_METRIC_SMAPE = 2, KRR_METRIC_REL_MSE = 3 };
+int krr_error_metric_f32(const float *film, const float *reference, int64_t n_pixels, int32_t metric,
+						 double *result_host, void *cuda_stream);
+
+/* ---- ToneMappingPass, src/render/passes/tonemapping/tonemapping.cu:11-85 ----
+ * film: device float4[n_pixels], rewritten in place: rgb * exposure -> operator -> optional pow(1/2.2); alpha = 1 */
+enum { KRR_TONEMAP_LINEAR = 0, KRR_TONEMAP_REINHARD = 1, KRR_TONEMAP_ACES = 2, KRR_TONEMAP_UNCHARTED2 = 3, KRR_TONEMAP_HEJIHABLE = 4 };
+int krr_tonemap_f32(float *film, int64_t n_pixels, int32_t tonemap_operator, float exposure, int32_t use_gamma, void *cuda_stream);
+
 const char *krr_wfpt_last_error(void);
 int			krr_wfpt_abi_version(void);
 

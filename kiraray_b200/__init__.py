@@ -9,4 +9,5 @@ libraries are missing it raises.
 from .binding import (  # noqa: F401
     HostApp, Wfpt, KrrSceneDesc, KrrLeafBsdfQuery, KrrLeafLightQuery, KrrCameraData, KrrStats, KrrColorSpaceData,
     load_host, load_wfpt, lib_dir, data_dir, color_space, NativeLibraryMissing,
+    load_image, save_image, save_exr, error_metric, tonemap, accumulate_f64,
 )

@@ -164,6 +164,10 @@ def load_wfpt():
         "krr_wfpt_debug_capture": [P, I32, I32],
         "krr_wfpt_debug_queue": [P, I32, P, I32],
         "krr_accumulate_f32": [P, P, C.c_int64, U64, U64, I32, P],
+        "krr_accumulate_f64": [P, P, C.c_int64, U64, U64, I32, P],
+        "krr_accumulate_read_average": [P, I32, U64, C.c_int64, P, P],
+        "krr_error_metric_f32": [P, P, C.c_int64, I32, C.POINTER(C.c_double), P],
+        "krr_tonemap_f32": [P, C.c_int64, I32, F, I32, P],
         "krr_wfpt_debug_eval_bsdf": [P, C.POINTER(KrrLeafBsdfQuery), I32, C.POINTER(KrrLeafBsdfResult)],
         "krr_wfpt_debug_eval_light": [P, C.POINTER(KrrLeafLightQuery), I32, C.POINTER(KrrLeafLightResult)],
         "krr_wfpt_debug_eval_color": [P, C.POINTER(F), I32, C.POINTER(F)],
@@ -201,6 +205,18 @@ def load_host():
     lib.krr_host_app_wfpt_handle.restype = P
     lib.krr_host_app_frame_index.argtypes = [P]
     lib.krr_host_app_frame_index.restype = U64
+    lib.krr_host_app_run.argtypes = [P, I32, I32]
+    lib.krr_host_app_set_output_dir.argtypes = [P, C.c_char_p]
+    lib.krr_host_app_get_pass_json.argtypes = [P, C.c_char_p, C.c_char_p, I32]
+    lib.krr_host_app_accum_count.argtypes = [P]
+    lib.krr_host_app_accum_count.restype = C.c_int64
+    lib.krr_host_app_read_accumulated.argtypes = [P, P]
+    lib.krr_host_app_set_reference.argtypes = [P, P, I32, I32]
+    lib.krr_host_app_evaluate_next_frame.argtypes = [P]
+    lib.krr_host_app_last_error_metric.argtypes = [P, C.POINTER(C.c_double), C.POINTER(I32)]
+    lib.krr_host_image_load.argtypes = [C.c_char_p, I32, C.POINTER(I32), C.POINTER(I32), P]
+    lib.krr_host_image_save.argtypes = [C.c_char_p, P, I32, I32, I32, I32]
+    lib.krr_host_image_save_exr.argtypes = [C.c_char_p, P, I32, I32, I32, I32]
     lib.krr_host_set_data_dir.argtypes = [C.c_char_p]
     lib.krr_host_set_data_dir(data_dir().encode())
     _host = lib
@@ -299,6 +315,45 @@ class HostApp:
         film = np.empty((h, w, 4), dtype=np.float32)
         self._ck(self.lib.krr_host_app_render_frames(self.h, n, film.ctypes.data_as(P)), "render_frames")
         return film
+
+    def run(self, max_frames=0, finalize=True):
+        """RenderApp main loop: frames until a pass requests the exit or max_frames; returns frames rendered."""
+        n = self.lib.krr_host_app_run(self.h, int(max_frames), int(finalize))
+        if n < 0:
+            raise RuntimeError("krr_host_app_run: " + self.lib.krr_host_last_error().decode())
+        return n
+
+    def set_output_dir(self, d):
+        self._ck(self.lib.krr_host_app_set_output_dir(self.h, str(d).encode()), "set_output_dir")
+
+    def pass_json(self, name):
+        buf = C.create_string_buffer(4096)
+        n = self.lib.krr_host_app_get_pass_json(self.h, name.encode(), buf, 4096)
+        if n < 0:
+            raise RuntimeError("krr_host_app_get_pass_json: " + self.lib.krr_host_last_error().decode())
+        import json as _json
+        return _json.loads(buf.value.decode())
+
+    def accum_count(self):
+        return int(self.lib.krr_host_app_accum_count(self.h))
+
+    def read_accumulated(self):
+        w, h = self.resolution
+        out = np.empty((h, w, 4), np.float32)
+        self._ck(self.lib.krr_host_app_read_accumulated(self.h, out.ctypes.data_as(P)), "read_accumulated")
+        return out
+
+    def set_reference(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        self._ck(self.lib.krr_host_app_set_reference(self.h, rgba.ctypes.data_as(P), rgba.shape[1], rgba.shape[0]), "set_reference")
+
+    def evaluate_next_frame(self):
+        self._ck(self.lib.krr_host_app_evaluate_next_frame(self.h), "evaluate_next_frame")
+
+    def last_error_metric(self):
+        v, n = C.c_double(), I32()
+        self._ck(self.lib.krr_host_app_last_error_metric(self.h, C.byref(v), C.byref(n)), "last_error_metric")
+        return v.value, n.value
 
     def wfpt_handle(self):
         return self.lib.krr_host_app_wfpt_handle(self.h)
@@ -449,3 +504,50 @@ class Wfpt:
         items = np.empty((n, 4), np.int32)
         cnt = self._ck(self.lib.krr_wfpt_debug_queue(self.h, q, items.ctypes.data_as(P), n), "debug_queue")
         return items[:cnt].copy()
+
+
+# ---- HDR image files (host layer, no GPU): reference Image::loadImage / saveImage ----
+def load_image(path, flip=False):
+    lib = load_host()
+    w, h = I32(), I32()
+    if lib.krr_host_image_load(str(path).encode(), int(flip), C.byref(w), C.byref(h), None) != 0:
+        raise RuntimeError("krr_host_image_load: " + lib.krr_host_last_error().decode())
+    out = np.empty((h.value, w.value, 4), np.float32)
+    if lib.krr_host_image_load(str(path).encode(), int(flip), C.byref(w), C.byref(h), out.ctypes.data_as(P)) != 0:
+        raise RuntimeError("krr_host_image_load: " + lib.krr_host_last_error().decode())
+    return out
+
+
+def save_image(path, rgba, flip=False, reference_channel_order=True):
+    lib = load_host()
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    if lib.krr_host_image_save(str(path).encode(), rgba.ctypes.data_as(P), rgba.shape[1], rgba.shape[0], int(flip), int(reference_channel_order)) != 0:
+        raise RuntimeError("krr_host_image_save: " + lib.krr_host_last_error().decode())
+
+
+def save_exr(path, rgba, half=True, zip=False):
+    lib = load_host()
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    if lib.krr_host_image_save_exr(str(path).encode(), rgba.ctypes.data_as(P), rgba.shape[1], rgba.shape[0], int(half), int(zip)) != 0:
+        raise RuntimeError("krr_host_image_save_exr: " + lib.krr_host_last_error().decode())
+
+
+# ---- device kernels of the passes that follow the path tracer (C ABI, device pointers) ----
+def error_metric(film_ptr, ref_ptr, n_pixels, metric=3, stream=None):
+    lib = load_wfpt()
+    v = C.c_double()
+    if lib.krr_error_metric_f32(P(film_ptr), P(ref_ptr), n_pixels, metric, C.byref(v), P(stream or 0)) != 0:
+        raise RuntimeError("krr_error_metric_f32: " + lib.krr_wfpt_last_error().decode())
+    return v.value
+
+
+def tonemap(film_ptr, n_pixels, op=0, exposure=1.0, gamma=True, stream=None):
+    lib = load_wfpt()
+    if lib.krr_tonemap_f32(P(film_ptr), n_pixels, op, exposure, int(gamma), P(stream or 0)) != 0:
+        raise RuntimeError("krr_tonemap_f32: " + lib.krr_wfpt_last_error().decode())
+
+
+def accumulate_f64(accum_ptr, film_ptr, n_pixels, accum_count, max_accum=0, moving_average=False, stream=None):
+    lib = load_wfpt()
+    if lib.krr_accumulate_f64(P(accum_ptr), P(film_ptr), n_pixels, accum_count, max_accum, int(moving_average), P(stream or 0)) != 0:
+        raise RuntimeError("krr_accumulate_f64: " + lib.krr_wfpt_last_error().decode())

@@ -26,8 +26,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda", "-prec-div=false", "-prec-sqrt=false",
                   "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v",
                   "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
-CU_SRCS = ["api.cu", "bvh_build.cu"]
-HOST_SRCS = ["scene.cpp", "passes.cpp", "host_c_api.cpp"]
+CU_SRCS = ["api.cu", "bvh_build.cu", "post_passes.cu"]
+HOST_SRCS = ["scene.cpp", "passes.cpp", "image.cpp", "host_c_api.cpp"]
 
 
 def run(cmd, log=None):
@@ -97,7 +97,7 @@ def build(force=False):
     if force or not newer(host, hsrcs + hdrs + [wfpt]):
         run([CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
              "-I", "/usr/local/cuda/include", "-o", host] + hsrcs +
-            ["-L", LIB, "-lkrr_wfpt", "-L", "/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-pthread",
+            ["-L", LIB, "-lkrr_wfpt", "-L", "/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lz", "-pthread",
              "-Wl,-rpath,$ORIGIN"])
     cli_src = os.path.join(HERE, "host", "krr_render.cpp")
     cli = os.path.join(LIB, "krr_render")

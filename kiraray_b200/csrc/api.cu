@@ -87,6 +87,8 @@ struct KrrWfpt {
 	bool nee = true, enableMedium = true, enableClamp = false;
 	bool rrInTrace = true; // "rr_in_trace": internal scheduling switch (not a reference parameter), see Params::rrInTrace
 	int flatBlasMax = 48;	 // "flat_blas_max": a BLAS with at most this many triangles is a flat list (takes effect at set_scene)
+	bool pdl = false;		 // "pdl": programmatic dependent launch between the stage kernels (measured: -1.6 % on the bench workload, so off)
+	bool usePdl() const { return pdl && !profile; }
 	bool fuseStages = true;	 // "fuse_stages": 2 launches per depth (hit/miss in the scatter launch, shadow + next closest in one trace launch)
 	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
@@ -170,6 +172,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
 		h->fuseStages	= j.value("fuse_stages", h->fuseStages);
+		h->pdl			= j.value("pdl", h->pdl);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
@@ -286,6 +289,14 @@ template <typename K> int gridFor(KrrWfpt *h, K kernel, int block) {
 
 // =================================================================================================
 extern "C" const char *krr_wfpt_last_error(void) { return gErr; }
+namespace krr {
+void setLastError(const char *fmt, ...) { // for the other translation units of the library (post_passes.cu)
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(gErr, sizeof gErr, fmt, ap);
+	va_end(ap);
+}
+} // namespace krr
 extern "C" int krr_wfpt_abi_version(void) { return KRR_WFPT_ABI_VERSION; }
 
 extern "C" int krr_wfpt_create(const char *params_json, KrrWfpt **out) {
@@ -725,6 +736,17 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 }
 
 namespace {
+// launch with the programmatic-stream-serialization attribute (see KRR_PDL_ENTRY in wavefront_kernels.cuh)
+template <typename... KArgs, typename... Args>
+void launchK(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args &&...args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned) grid), cfg.blockDim = dim3((unsigned) block), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 struct StageTimer { // RAII: brackets one launch with events when profiling is on
 	KrrWfpt *h; cudaStream_t st; KrrWfpt::EvRec rec; bool on;
 	StageTimer(KrrWfpt *h_, int stage, cudaStream_t st_) : h(h_), st(st_), on(h_->profile) {
@@ -736,8 +758,8 @@ template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth,
 	static int grid = 0, gridM = 0;
 	if (!grid) grid = gridFor(h, k_scatter<MT, false>, kScatterBlock), gridM = gridFor(h, k_scatter<MT, true>, kScatterBlock);
 	StageTimer t(h, KRR_STAGE_SCATTER, st);
-	if (wf.scene.hasMotion) k_scatter<MT, true><<<gridM, kScatterBlock, 0, st>>>(wf, depth, withHitMiss);
-	else k_scatter<MT, false><<<grid, kScatterBlock, 0, st>>>(wf, depth, withHitMiss);
+	if (wf.scene.hasMotion) launchK(h->usePdl(), k_scatter<MT, true>, gridM, kScatterBlock, st, wf, depth, withHitMiss);
+	else launchK(h->usePdl(), k_scatter<MT, false>, grid, kScatterBlock, st, wf, depth, withHitMiss);
 	withHitMiss = 0; // only the first scatter launch of a depth carries the hit / miss prologue
 	h->launches++;
 }
@@ -771,11 +793,15 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		gridShadowTr = gridFor(h, k_trace_shadow_tr, kTraceBlock);
 	}
 	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
+	static int gridFused = 0, gridFusedM = 0;
+	if (!gridFused) gridFused = gridFor(h, k_trace_fused<false>, 128);
+	if (motion && !gridFusedM) gridFusedM = gridFor(h, k_trace_fused<true>, 128);
+	const bool pdl = h->usePdl();
 	const int nDepthSlots = h->maxDepth + 2;
 	for (int sampleId = 0; sampleId < h->spp; sampleId++) {
 		Wavefront wf = makeWavefront(h, sampleId);
 		// [1] primary rays.  Queue counters were cleared by k_fold_counters of the previous sample
-		{ StageTimer t(h, KRR_STAGE_CAMERA, st); k_generate_camera_rays<<<gridCam, 256, 0, st>>>(wf); }
+		{ StageTimer t(h, KRR_STAGE_CAMERA, st); launchK(pdl, k_generate_camera_rays, gridCam, 256, st, wf); }
 		h->launches++;
 		// Fused schedule (default; surface-only scenes with NEE): handleHit/Miss rides as the prologue of
 		// the scatter launch of its depth, and ONE trace launch covers the shadow rays of depth d and the
@@ -793,14 +819,14 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		};
 		auto launchHitMiss = [&](int depth) {
 			StageTimer t(h, KRR_STAGE_HIT_MISS, st);
-			if (motion) k_handle_hit_miss<true><<<gridHitM, 128, 0, st>>>(wf, depth);
-			else k_handle_hit_miss<false><<<gridHit, 128, 0, st>>>(wf, depth);
+			if (motion) launchK(pdl, k_handle_hit_miss<true>, gridHitM, 128, st, wf, depth);
+			else launchK(pdl, k_handle_hit_miss<false>, gridHit, 128, st, wf, depth);
 			h->launches++;
 		};
 		auto launchClosest = [&](int depth) {
 			StageTimer t(h, KRR_STAGE_CLOSEST, st);
-			if (motion) k_trace_closest<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
-			else k_trace_closest<false><<<gridTrace, 128, 0, st>>>(wf, depth);
+			if (motion) launchK(pdl, k_trace_closest<true>, gridTraceM, 128, st, wf, depth);
+			else launchK(pdl, k_trace_closest<false>, gridTrace, 128, st, wf, depth);
 			h->launches++;
 		};
 		if (fused) {
@@ -808,8 +834,8 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			for (int depth = 0; depth < h->maxDepth; depth++) {
 				launchAllScatter(depth, 1);
 				StageTimer t(h, KRR_STAGE_TRACE, st);
-				if (motion) k_trace_fused<true><<<gridTraceM, 128, 0, st>>>(wf, depth);
-				else k_trace_fused<false><<<gridTrace, 128, 0, st>>>(wf, depth);
+				if (motion) launchK(pdl, k_trace_fused<true>, gridFusedM, 128, st, wf, depth);
+				else launchK(pdl, k_trace_fused<false>, gridFused, 128, st, wf, depth);
 				h->launches++;
 			}
 			launchHitMiss(h->maxDepth);
@@ -839,17 +865,17 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			if (h->nee) {
 				StageTimer t(h, KRR_STAGE_SHADOW, st);
 				if (media) k_trace_shadow_tr<<<gridShadowTr, kTraceBlock, 0, st>>>(wf, depth);
-				else if (motion) k_trace_shadow<true><<<gridShadowM, 128, 0, st>>>(wf, depth);
-				else k_trace_shadow<false><<<gridShadow, 128, 0, st>>>(wf, depth);
+				else if (motion) launchK(pdl, k_trace_shadow<true>, gridShadowM, 128, st, wf, depth);
+				else launchK(pdl, k_trace_shadow<false>, gridShadow, 128, st, wf, depth);
 				h->launches++;
 			}
 		}
-		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_resolve<<<gridResolve, 256, 0, st>>>(wf); }
-		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_fold_counters<<<1, 128, 0, st>>>(h->counters.p, h->totals.p, nDepthSlots, h->pixelCount()); }
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_resolve, gridResolve, 256, st, wf); }
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_fold_counters, 1, 128, st, h->counters.p, h->totals.p, nDepthSlots, h->pixelCount()); }
 		h->launches += 2;
 	}
 	Wavefront wf = makeWavefront(h, 0);
-	{ StageTimer t(h, KRR_STAGE_RESOLVE, st); k_film<<<gridResolve, 256, 0, st>>>(wf, (float4 *) film, 1); }
+	{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_film, gridResolve, 256, st, wf, (float4 *) film, 1); }
 	h->launches++;
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;

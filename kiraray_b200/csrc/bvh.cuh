@@ -104,7 +104,7 @@ KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 //   instance : kInstFlag | instance id  (TLAS leaves hold ONE instance)      (bits 31,30 = 10)
 //   flat BLAS: kFlatFlag | index into BvhDev::flats (only ever a BLAS root)  (bits 31,30 = 11, != empty)
 constexpr int kShortStack  = 12;
-constexpr int kLocalStack  = 52;
+constexpr int kLocalStack  = 116; // 8-wide nodes defer up to 7 siblings per level: 128 entries cover TLAS + BLAS depths of ~18 levels
 constexpr int kStackSize   = kShortStack + kLocalStack;
 constexpr int kTraceBlock  = 128;
 constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kFlatFlag = 0xc0000000u, kEmptyEntry = 0xffffffffu;
@@ -153,6 +153,12 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
 		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
 		if (bvh.mergedOnly) cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
+		// A ray with a NaN / infinite component or a zero direction cannot hit anything (every comparison of
+		// the triangle test fails, det == 0), but its slab tests cannot cull either: it would walk the WHOLE
+		// tree (seconds on a 20 M-triangle scene).  Such rays come out of degenerate BSDF samples; they are
+		// misses, as they are for the brute-force loop of the oracle.
+		const float chk = ((o_.x + o_.y) + o_.z) + ((d_.x + d_.y) + d_.z);
+		if (!(fabsf(chk) < 3.0e38f) || (d_.x == 0.f && d_.y == 0.f && d_.z == 0.f)) cur = kEmptyEntry, curInst = -1;
 	}
 	KRR_DEV void push(TraceSmem &sm, LStack &ls, uint32_t e, float tn) {
 		if (sp < kShortStack) {
@@ -232,8 +238,10 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			// rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
 			// when the ray grazes an axis-aligned plane): the test and the stored entry distance are widened
 			// by it, so flat boxes are never culled by arithmetic noise
-			const float slack = ((fabsf(bx) + 255.f * fabsf(ax)) + (fabsf(by) + 255.f * fabsf(ay)) + (fabsf(bz) + 255.f * fabsf(az))) * 2.4e-7f +
-								(fabsf(ax) + fabsf(ay) + fabsf(az)) * 0.00390625f;
+			// (an axis the ray is parallel to has a = inf and yields NaN distances, which min/max drop: it neither
+			// culls nor needs slack -- without the guard it would switch culling off on the other two axes too)
+			auto axisSlack = [](float a, float b) { return fabsf(a) < 3.0e38f ? (fabsf(b) + 255.f * fabsf(a)) * 2.4e-7f + fabsf(a) * 0.00390625f : 0.f; };
+			const float slack = axisSlack(ax, bx) + axisSlack(ay, by) + axisSlack(az, bz);
 			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
 			auto child = [&](int i) -> uint32_t {
 				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;

@@ -123,6 +123,12 @@ struct Wavefront {
 	const uint8_t *instFlags;
 };
 
+// Programmatic dependent launch: every stage kernel lets its successor in the stream be scheduled at
+// once (its CTAs become resident as ours retire and block in griddepcontrol.wait) and then waits itself
+// for the complete, flushed results of its predecessor -- the launch latency and the CTA ramp-up of a
+// stage overlap the tail of the previous one.  Without the launch attribute both are no-ops.
+#define KRR_PDL_ENTRY() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+
 // ---- warp-aggregated push: one atomicAdd per warp ----
 KRR_DEV int warpPush(int32_t *counter, bool pred) {
 	unsigned mask = __ballot_sync(__activemask(), pred);
@@ -193,6 +199,7 @@ KRR_DEV void cameraRay(const KrrCameraDev &c, int px, int py, int W, int H, cons
 }
 
 __global__ void k_generate_camera_rays(const __grid_constant__ Wavefront wf) {
+	KRR_PDL_ENTRY();
 	RayQueue q = wf.rays[0];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		int pixelId = wf.p.pixelBegin + i;
@@ -451,6 +458,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 
 template <bool MOTION>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
+	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
 	traceClosestBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
@@ -659,6 +667,7 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 
 template <bool MOTION>
 __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__ Wavefront wf, int depth) {
+	KRR_PDL_ENTRY();
 	handleHitMissBody<MOTION>(wf, depth);
 }
 
@@ -683,6 +692,7 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 constexpr int kScatterBlock = KRR_SCATTER_BLOCK;
 template <int MT, bool MOTION>
 __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth, int withHitMiss) {
+	KRR_PDL_ENTRY();
 	// handleHit / handleMiss of this depth (they touch L only, this stage does not)
 	if (withHitMiss) handleHitMissBody<MOTION>(wf, depth);
 	const RayQueue q  = wf.rays[depth & 1];
@@ -910,6 +920,7 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 
 template <bool MOTION>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
+	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
 	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
@@ -925,6 +936,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 template <bool MOTION>
 __global__ void __launch_bounds__(kTraceBlock, 7) k_trace_fused( // 7 CTAs/SM = the occupancy of the two stand-alone kernels (72 registers)
 const __grid_constant__ Wavefront wf, int depth) {
+	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
 	traceClosestBody<MOTION>(wf, depth + 1, sm, blockIdx.x, gridDim.x);
 	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
@@ -1234,6 +1246,7 @@ __global__ void k_build_majorant(const float *__restrict__ density, int rx, int 
 // per-sample resolve (integrator.cpp:257-260).  Note the reference does NOT reset L between the
 // samples of one frame, so sample k adds the running sum; kept as is.
 __global__ void k_resolve(const __grid_constant__ Wavefront wf) {
+	KRR_PDL_ENTRY();
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		Wavelengths wl = expandWavelengths(wf.px.lambda[i]);
 		float rgb[3];
@@ -1245,6 +1258,7 @@ __global__ void k_resolve(const __grid_constant__ Wavefront wf) {
 
 // film write (integrator.cpp:262-266): /spp, optional clamp, alpha 1, row H-1-y (cuda.h:33-36)
 __global__ void k_film(const __grid_constant__ Wavefront wf, float4 *film, int zeroOutside) {
+	KRR_PDL_ENTRY();
 	const int N = wf.p.width * wf.p.height;
 	for (int pixelId = blockIdx.x * blockDim.x + threadIdx.x; pixelId < N; pixelId += gridDim.x * blockDim.x) {
 		int i = pixelId - wf.p.pixelBegin;
@@ -1270,6 +1284,7 @@ struct StatTotals {
 	unsigned long long closestByDepth[64], shadowByDepth[64];
 };
 __global__ void k_fold_counters(DepthCounters *c, StatTotals *t, int nDepth, int cameraRays) {
+	KRR_PDL_ENTRY();
 	int d = threadIdx.x;
 	if (d == 0) atomicAdd(&t->camera, (unsigned long long) cameraRays);
 	if (d >= nDepth) return;

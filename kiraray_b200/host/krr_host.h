@@ -9,6 +9,8 @@
 //   SceneImporter (KRR JSON scene schema)                        src/scene/krrscene.cpp:8-349
 //   OBJ/MTL material mapping                                     src/scene/assimp.cpp:60-65, 93-226
 //   Camera / OrbitCameraController                               src/core/camera.{h,cpp}
+//   AccumulatePass / ErrorMeasurePass / ToneMappingPass          src/render/passes/{accumulate,errormeasure,tonemapping}
+//   Image (EXR / PFM load + save)                                src/core/texture.cpp:27-118, src/util/image.cpp
 // Windowing, Vulkan interop, UI and the other importers are out of scope.
 #pragma once
 #include <functional>
@@ -118,6 +120,24 @@ public:
 bool loadObj(const string &filepath, Scene &scene, const float nodeTransform[12]);
 
 // ------------------------------------------------------------------------------------------------
+// HDR images (image.cpp): RGBA32F, row 0 first -- the layout of the film buffer
+// ------------------------------------------------------------------------------------------------
+struct Image {
+	int width = 0, height = 0;
+	std::vector<float> rgba;
+	bool isValid() const { return width > 0 && height > 0 && rgba.size() == (size_t) width * height * 4; }
+	void flipVertically();
+};
+// Image::loadImage(path, flip, srgb) / saveImage(path, flip), texture.cpp:27-118: .exr and .pfm
+bool loadImage(const string &path, Image &img, bool flip, string *err = nullptr);
+// referenceChannelOrder: write the EXR channels the way the reference's save_exr does (see image.cpp)
+bool saveImage(const string &path, const Image &img, bool flip, string *err = nullptr, bool referenceChannelOrder = true);
+bool loadEXR(const string &path, Image &img, string *err = nullptr);
+bool saveEXR(const string &path, const Image &img, bool halfPrecision, bool zip, string *err = nullptr);
+bool loadPFM(const string &path, Image &img, string *err = nullptr);
+bool savePFM(const string &path, const Image &img, string *err = nullptr);
+
+// ------------------------------------------------------------------------------------------------
 // RenderContext / RenderPass / factory
 // ------------------------------------------------------------------------------------------------
 class RenderContext {
@@ -162,6 +182,8 @@ public:
 	virtual json toJson() const { return json::object(); }
 	// the reference pulls these from DeviceManager (renderpass.cpp:120-126); the headless app sets them
 	void setFrameIndex(size_t i) { mFrameIndex = i; }
+	// gpContext->getGlobalConfig() / File::outputDir() of the reference, handed down by RenderApp
+	void setApp(RenderApp *app) { mApp = app; }
 
 protected:
 	size_t getFrameIndex() const { return mFrameIndex; }
@@ -170,6 +192,7 @@ protected:
 	Scene::SharedPtr mScene;
 	size_t mFrameIndex = 0;
 	Vector2i mFrameSize;
+	RenderApp *mApp = nullptr;
 };
 
 class RenderPassFactory {
@@ -236,24 +259,98 @@ private:
 };
 
 // AccumulatePass: src/render/passes/accumulate/accumulate.{h,cu}
+// JSON: spp, mode ("accumulate" | "moving average"), precision ("float" | "double"), save_on_finish,
+// exit_on_finish, save_every, task {"type": "spp" | "time", "value": N} (accumulate.h:31-57, util/task.h)
 class AccumulatePass : public RenderPass {
 public:
 	KRR_REGISTER_PASS_DEC(AccumulatePass);
 	enum class Mode { Accumulate, MovingAverage, Count };
+	enum class Precision { Float, Double, Count };
+	enum class BudgetType { None, Spp, Time };
 	void resize(const Vector2i &size) override;
 	void render(RenderContext *context) override;
-	void reset() { mAccumCount = 0; }
+	void endFrame(RenderContext *context) override;
+	void finalize() override;
+	void reset();
 	string getName() const override { return "AccumulatePass"; }
 	void fromJson(const json &j);
 	json toJson() const override;
 	~AccumulatePass() override;
 	size_t accumCount() const { return mAccumCount; }
+	// the accumulated average as an image (AccumulatePass::saveImage, accumulate.cu:90-111)
+	bool readAverage(Image &img);
+	bool saveImage(const string &path);
+	// RenderTask (util/task.h:21-60)
+	float progress() const;
+	bool finished() const { return progress() >= 1.f; }
 	size_t maxAccumCount = 0; // "spp": 0 = unlimited
-	Mode mode = Mode::Accumulate;
+	Mode mode			 = Mode::Accumulate;
+	Precision precision	 = Precision::Float;
+	bool saveOnFinish = false, exitOnFinish = false;
+	size_t saveEvery	  = 0;
+	BudgetType budgetType = BudgetType::None;
+	double budgetValue	  = 0;
 
 private:
-	float *mAccum = nullptr;
-	size_t mAccumCount = 0;
+	void *mAccum = nullptr; // float4 or double4 per pixel
+	size_t mAccumCount = 0, mTaskSpp = 0;
+	double mTaskStart = 0, mTaskNow = 0;
+};
+
+// ErrorMeasurePass: src/render/passes/errormeasure/{errormeasure.cpp,metrics.cu}
+// JSON: metric ("mse" | "mape" | "smape" | "rel_mse"), reference (image path; also the global config's
+// "reference"), continuous, interval, log, save
+class ErrorMeasurePass : public RenderPass {
+public:
+	KRR_REGISTER_PASS_DEC(ErrorMeasurePass);
+	enum class ErrorMetric { MSE, MAPE, SMAPE, RelMSE, Count };
+	void beginFrame(RenderContext *context) override;
+	void render(RenderContext *context) override;
+	void finalize() override;
+	string getName() const override { return "ErrorMeasurePass"; }
+	void fromJson(const json &j);
+	json toJson() const override;
+	~ErrorMeasurePass() override;
+	bool loadReferenceImage(const string &path);
+	void setReferenceImage(const Image &img); // already in film layout (no file, no permutation)
+	void evaluateNextFrame() { mNeedsEvaluate = true; } // the UI's "Evaluate" button
+	const json &lastResult() const { return mLastResult; }
+	double lastValue() const { return mLastValue; }
+	struct EvaluationData { size_t timestep; double timepoint; json metrics; };
+	const std::vector<EvaluationData> &results() const { return mEvaluationResults; }
+	ErrorMetric metric = ErrorMetric::RelMSE;
+	bool continuousEvaluate = false, logResults = false, saveResults = false;
+	size_t evaluateInterval = 1;
+
+private:
+	void reset();
+	Image mReferenceImage;
+	float *mReferenceDevice = nullptr;
+	string mReferenceImagePath;
+	json mLastResult;
+	double mLastValue = 0, mStartTime = 0;
+	bool mNeedsEvaluate = false;
+	size_t mFrameNumber = 0;
+	std::vector<EvaluationData> mEvaluationResults;
+};
+
+// ToneMappingPass: src/render/passes/tonemapping/tonemapping.{h,cu}
+// JSON: exposure, operator ("linear" | "reinhard" | "aces" | "uncharted2" | "hejihable"), gamma
+class ToneMappingPass : public RenderPass {
+public:
+	KRR_REGISTER_PASS_DEC(ToneMappingPass);
+	enum class Operator { Linear = 0, Reinhard, Aces, Uncharted2, HejiHable, NumsOperators };
+	void render(RenderContext *context) override;
+	string getName() const override { return "ToneMappingPass"; }
+	void fromJson(const json &j);
+	json toJson() const override;
+	void setOperator(Operator op) { mOperator = op; }
+	Operator getOperator() const { return mOperator; }
+	bool useGamma = true;
+	float exposureCompensation = 1.f;
+
+private:
+	Operator mOperator = Operator::Linear;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -278,6 +375,17 @@ public:
 	}
 	size_t frameIndex() const { return mFrameIndex; }
 	Vector2i frameSize() const { return mSize; }
+	// RenderApp::finalize (renderer.cpp:333-336): finalize() on every pass
+	void finalize();
+	// gpContext->requestExit() / shouldQuit() (context.h): set by AccumulatePass when its budget is spent
+	void requestExit() { mExit = true; }
+	bool shouldQuit() const { return mExit; }
+	// runs frames until a pass requests the exit (or maxFrames); returns the number of frames rendered
+	size_t run(size_t maxFrames = 0);
+	const json &globalConfig() const { return mConfig; }
+	// File::outputDir(): "output_dir" of the config, else "<base dir>/output"
+	string outputDir() const { return mOutputDir; }
+	void setOutputDir(const string &d) { mOutputDir = d; }
 
 private:
 	std::vector<RenderPass::SharedPtr> mRenderPasses;
@@ -286,7 +394,9 @@ private:
 	Vector2i mSize{1280, 720};
 	size_t mFrameIndex = 0;
 	bool mInitialized  = false;
+	bool mExit		   = false;
 	json mConfig;
+	string mOutputDir = "output";
 };
 
 // colour-space tables (kiraray_b200/data/spectral_srgb.bin); throws when missing

@@ -6,6 +6,9 @@
 
 #include <cuda_runtime.h>
 
+#include <sys/stat.h>
+
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -21,6 +24,10 @@ void cudaCheck(cudaError_t e, const char *what) {
 	if (e != cudaSuccess) throw std::runtime_error(string(what) + ": " + cudaGetErrorString(e));
 }
 string gDataDir;
+void makeDirs(const string &path) { // mkdir -p
+	for (size_t i = 1; i <= path.size(); i++)
+		if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
+}
 } // namespace
 
 // ---------------- colour-space tables ----------------
@@ -159,35 +166,217 @@ KrrStats WavefrontPathTracer::stats() {
 }
 
 // ---------------- AccumulatePass ----------------
-extern "C" int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,
-								  uint64_t max_accum_count, int32_t moving_average, void *stream);
 KRR_REGISTER_PASS_DEF(AccumulatePass);
 
+namespace {
+double nowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+string lower(string s) { for (char &c : s) c = (char) tolower((unsigned char) c); return s; }
+} // namespace
+
 void AccumulatePass::fromJson(const json &j) {
+	// from_json, accumulate.h:43-52
 	maxAccumCount = (size_t) j.value("spp", 0);
 	mode		  = j.value("mode", "accumulate") == "moving average" ? Mode::MovingAverage : Mode::Accumulate;
+	precision	  = j.value("precision", "float") == "double" ? Precision::Double : Precision::Float;
+	saveOnFinish  = j.value("save_on_finish", false);
+	exitOnFinish  = j.value("exit_on_finish", false);
+	saveEvery	  = (size_t) j.value("save_every", 0);
+	budgetType = BudgetType::None, budgetValue = 0;
+	if (j.contains("task")) { // RenderTask / Budget, util/task.h:9-19 + from_json
+		const json &t = j.at("task");
+		string type	  = lower(t.value("type", "none"));
+		budgetType	  = type == "spp" ? BudgetType::Spp : type == "time" ? BudgetType::Time : BudgetType::None;
+		budgetValue	  = t.contains("value") ? t.at("value").asNumber() : 0;
+	}
 }
 json AccumulatePass::toJson() const {
 	json j	  = json::object();
 	j["spp"]  = json((long long) maxAccumCount);
 	j["mode"] = json(mode == Mode::MovingAverage ? "moving average" : "accumulate");
+	j["precision"]		= json(precision == Precision::Double ? "double" : "float");
+	j["save_on_finish"] = json(saveOnFinish), j["exit_on_finish"] = json(exitOnFinish), j["save_every"] = json((long long) saveEvery);
+	json t = json::object();
+	t["type"] = json(budgetType == BudgetType::Spp ? "spp" : budgetType == BudgetType::Time ? "time" : "none"), t["value"] = json(budgetValue);
+	j["task"] = t;
 	return j;
+}
+void AccumulatePass::reset() { // accumulate.cu:19-24
+	mAccumCount = 0, mTaskSpp = 0;
+	mTaskStart = mTaskNow = nowSeconds();
 }
 void AccumulatePass::resize(const Vector2i &size) {
 	RenderPass::resize(size);
 	if (mAccum) cudaFree(mAccum);
 	mAccum = nullptr;
-	cudaCheck(cudaMalloc((void **) &mAccum, (size_t) size.x * size.y * 16), "cudaMalloc(accum)");
+	cudaCheck(cudaMalloc(&mAccum, (size_t) size.x * size.y * (precision == Precision::Double ? 32 : 16)), "cudaMalloc(accum)");
 	reset();
 }
 void AccumulatePass::render(RenderContext *context) {
 	if (!mAccum) return;
-	check(krr_accumulate_f32(mAccum, context->getColorDevice(), (int64_t) mFrameSize.x * mFrameSize.y, mAccumCount,
-							 maxAccumCount, mode == Mode::MovingAverage, context->getStream()),
-		  "krr_accumulate_f32");
-	if (!maxAccumCount || mAccumCount < maxAccumCount) mAccumCount++;
+	const int64_t n = (int64_t) mFrameSize.x * mFrameSize.y;
+	if (precision == Precision::Double)
+		check(krr_accumulate_f64((double *) mAccum, context->getColorDevice(), n, mAccumCount, maxAccumCount, mode == Mode::MovingAverage,
+								 context->getStream()),
+			  "krr_accumulate_f64");
+	else
+		check(krr_accumulate_f32((float *) mAccum, context->getColorDevice(), n, mAccumCount, maxAccumCount, mode == Mode::MovingAverage,
+								 context->getStream()),
+			  "krr_accumulate_f32");
+	if (!maxAccumCount || mAccumCount < maxAccumCount) {
+		mTaskSpp++, mTaskNow = nowSeconds(); // RenderTask::tickFrame
+		mAccumCount++;
+	}
+}
+float AccumulatePass::progress() const { // RenderTask::getProgress, util/task.h:45-54
+	switch (budgetType) {
+		case BudgetType::Spp: return budgetValue > 0 ? (float) mTaskSpp / (float) budgetValue : 0.f;
+		case BudgetType::Time: return budgetValue > 0 ? (float) ((mTaskNow - mTaskStart) / budgetValue) : 0.f;
+		default: return 0.f;
+	}
+}
+void AccumulatePass::endFrame(RenderContext *) { // accumulate.cu:79-88
+	if (budgetType != BudgetType::None && finished() && exitOnFinish && mApp) mApp->requestExit();
+	if (saveEvery && mAccumCount % saveEvery == 0 && mApp) {
+		string name = mApp->globalConfig().contains("name") ? mApp->globalConfig().at("name").asString() : "result" + std::to_string(mAccumCount);
+		saveImage(mApp->outputDir() + "/" + name + ".exr");
+	}
+}
+void AccumulatePass::finalize() { // accumulate.cu:118-127
+	if (saveOnFinish && mApp) {
+		cudaDeviceSynchronize();
+		string name = mApp->globalConfig().contains("name") ? mApp->globalConfig().at("name").asString() : "result";
+		saveImage(mApp->outputDir() + "/" + name + ".exr");
+	}
+}
+bool AccumulatePass::readAverage(Image &img) {
+	if (!mAccum || !mAccumCount) return false;
+	img.width = mFrameSize.x, img.height = mFrameSize.y;
+	img.rgba.resize((size_t) img.width * img.height * 4);
+	// moving-average mode keeps the average itself in the buffer; saveImage still scales by 1 / count
+	// (accumulate.cu:94-107), which is reproduced as is
+	check(krr_accumulate_read_average(mAccum, precision == Precision::Double, mAccumCount, (int64_t) img.width * img.height, img.rgba.data(), nullptr),
+		  "krr_accumulate_read_average");
+	return true;
+}
+bool AccumulatePass::saveImage(const string &path) {
+	Image img;
+	if (!readAverage(img)) return false;
+	size_t s = path.find_last_of('/');
+	if (s != string::npos) makeDirs(path.substr(0, s));
+	string err;
+	if (!krr::saveImage(path, img, true, &err)) throw std::runtime_error("AccumulatePass::saveImage: " + err); // frame.saveImage(path, true)
+	return true;
 }
 AccumulatePass::~AccumulatePass() { if (mAccum) cudaFree(mAccum); }
+
+// ---------------- ErrorMeasurePass ----------------
+KRR_REGISTER_PASS_DEF(ErrorMeasurePass);
+
+void ErrorMeasurePass::fromJson(const json &j) {
+	// from_json, errormeasure.h:63-74
+	static const char *names[] = {"mse", "mape", "smape", "rel_mse"};
+	string m = j.value("metric", "rel_mse");
+	metric	 = ErrorMetric::RelMSE;
+	for (int i = 0; i < 4; i++) if (m == names[i]) metric = (ErrorMetric) i;
+	continuousEvaluate = j.value("continuous", false);
+	evaluateInterval   = (size_t) j.value("interval", 1);
+	logResults		   = j.value("log", false);
+	saveResults		   = j.value("save", false);
+	if (j.contains("reference")) mReferenceImagePath = j.at("reference").asString(); // loaded in initialize-time resolve below
+}
+json ErrorMeasurePass::toJson() const {
+	static const char *names[] = {"mse", "mape", "smape", "rel_mse"};
+	json j = json::object();
+	j["metric"] = json(names[(int) metric]), j["reference"] = json(mReferenceImagePath), j["continuous"] = json(continuousEvaluate);
+	j["interval"] = json((long long) evaluateInterval), j["log"] = json(logResults), j["save"] = json(saveResults);
+	return j;
+}
+void ErrorMeasurePass::reset() { // errormeasure.cpp:86-91
+	mFrameNumber = 0, mNeedsEvaluate = false, mLastResult = json::object(), mStartTime = nowSeconds();
+}
+void ErrorMeasurePass::setReferenceImage(const Image &img) {
+	mReferenceImage = img;
+	if (mReferenceDevice) cudaFree(mReferenceDevice);
+	mReferenceDevice = nullptr;
+	cudaCheck(cudaMalloc((void **) &mReferenceDevice, img.rgba.size() * 4), "cudaMalloc(reference image)");
+	cudaCheck(cudaMemcpy(mReferenceDevice, img.rgba.data(), img.rgba.size() * 4, cudaMemcpyHostToDevice), "upload reference image");
+	reset();
+}
+bool ErrorMeasurePass::loadReferenceImage(const string &path) { // errormeasure.cpp:93-117
+	Image img;
+	string err;
+	if (!krr::loadImage(path, img, true, &err)) { // mReferenceImage->loadImage(path, true, false)
+		fprintf(stderr, "ErrorMeasure::Failed to load reference image from %s (%s)\n", path.c_str(), err.c_str());
+		return false;
+	}
+	// the permutation the reference applies to what it loads (its own EXR writer stores the planes
+	// rotated, see image.cpp): res[c] = pixel[{3, 0, 1, 2}[c]]
+	for (size_t i = 0; i < img.rgba.size(); i += 4) {
+		float r = img.rgba[i], g = img.rgba[i + 1], b = img.rgba[i + 2], a = img.rgba[i + 3];
+		img.rgba[i] = a, img.rgba[i + 1] = r, img.rgba[i + 2] = g, img.rgba[i + 3] = b;
+	}
+	setReferenceImage(img);
+	mReferenceImagePath = path;
+	return true;
+}
+void ErrorMeasurePass::beginFrame(RenderContext *) { // errormeasure.cpp:11-15
+	if (!mFrameNumber) reset();
+	mFrameNumber++;
+	mNeedsEvaluate |= continuousEvaluate && evaluateInterval && (mFrameNumber % evaluateInterval == 0);
+}
+void ErrorMeasurePass::render(RenderContext *context) { // errormeasure.cpp:17-38
+	static const char *metricNames[] = {"MSE", "MAPE", "SMAPE", "RelMSE"};
+	if (!(mNeedsEvaluate && mReferenceImage.isValid())) return;
+	if (mReferenceImage.width != mFrameSize.x || mReferenceImage.height != mFrameSize.y)
+		throw std::runtime_error("ErrorMeasure::Reference image size does not match frame size!");
+	double value = 0;
+	check(krr_error_metric_f32(context->getColorDevice(), mReferenceDevice, (int64_t) mFrameSize.x * mFrameSize.y, (int) metric, &value,
+							   context->getStream()),
+		  "krr_error_metric_f32");
+	mLastValue	= value;
+	mLastResult = json::object();
+	mLastResult[metricNames[(int) metric]] = json(value);
+	if (logResults) fprintf(stderr, "Evaluating frame #%zu: %s\n", mFrameNumber, mLastResult.dump().c_str());
+	if (saveResults) mEvaluationResults.push_back({mFrameNumber, nowSeconds() - mStartTime, mLastResult});
+	mNeedsEvaluate = false;
+}
+void ErrorMeasurePass::finalize() { // errormeasure.cpp:43-61
+	if (!saveResults || !mApp) return;
+	string name = mApp->globalConfig().contains("name") ? mApp->globalConfig().at("name").asString() : "result";
+	string dir	= mApp->outputDir() + "/error";
+	makeDirs(dir);
+	json timesteps = json::array(), timepoints = json::array(), data = json::array(), result = json::object();
+	for (const EvaluationData &e : mEvaluationResults) {
+		timesteps.push_back(json((long long) e.timestep)), timepoints.push_back(json(e.timepoint)), data.push_back(e.metrics);
+	}
+	result["timesteps"] = timesteps, result["timepoints"] = timepoints, result["data"] = data;
+	std::ofstream f(dir + "/" + name + ".json");
+	f << result.dump();
+}
+ErrorMeasurePass::~ErrorMeasurePass() { if (mReferenceDevice) cudaFree(mReferenceDevice); }
+
+// ---------------- ToneMappingPass ----------------
+KRR_REGISTER_PASS_DEF(ToneMappingPass);
+
+void ToneMappingPass::fromJson(const json &j) { // tonemapping.h:44-48
+	static const char *names[] = {"linear", "reinhard", "aces", "uncharted2", "hejihable"};
+	string op = j.value("operator", "linear");
+	mOperator = Operator::Linear;
+	for (int i = 0; i < 5; i++) if (op == names[i]) mOperator = (Operator) i;
+	exposureCompensation = j.value("exposure", 1.f);
+	useGamma			 = j.value("gamma", true);
+}
+json ToneMappingPass::toJson() const {
+	static const char *names[] = {"linear", "reinhard", "aces", "uncharted2", "hejihable"};
+	json j = json::object();
+	j["exposure"] = json((double) exposureCompensation), j["operator"] = json(names[(int) mOperator]), j["gamma"] = json(useGamma);
+	return j;
+}
+void ToneMappingPass::render(RenderContext *context) {
+	check(krr_tonemap_f32(context->getColorDevice(), (int64_t) mFrameSize.x * mFrameSize.y, (int) mOperator, exposureCompensation, useGamma,
+						  context->getStream()),
+		  "krr_tonemap_f32");
+}
 
 // ---------------- RenderApp ----------------
 void RenderApp::loadConfigFrom(const string &path) {
@@ -210,14 +399,15 @@ void RenderApp::loadConfig(const json &config, const string &baseDir) {
 			if (!pass) {
 				// reference passes outside the hot path are recognised and skipped; any other name is
 				// the reference's Log(Fatal) "Could not find pass" (renderpass.h:216-220, 228-232)
-				static const char *kOutOfScope[] = {"ToneMappingPass", "DenoisePass", "ErrorMeasurePass", "MegakernelPathTracer", "BDPTIntegrator",
-													"PPGPathTracer", "GBufferPass", "BindlessRender", "RasterizePass"};
+				static const char *kOutOfScope[] = {"DenoisePass", "MegakernelPathTracer", "BDPTIntegrator", "PPGPathTracer", "GBufferPass",
+													"BindlessRender", "RasterizePass"};
 				bool known = false;
 				for (const char *k : kOutOfScope) known |= name == k;
 				if (!known) throw std::runtime_error("unknown render pass \"" + name + "\"");
 				continue;
 			}
 			pass->setEnable(p.value("enable", true));
+			pass->setApp(this);
 			mRenderPasses.push_back(pass);
 		}
 	}
@@ -237,7 +427,17 @@ void RenderApp::loadConfig(const json &config, const string &baseDir) {
 		mSize.x = (int) config.at("resolution").at(0).asNumber();
 		mSize.y = (int) config.at("resolution").at(1).asNumber();
 	}
-	mConfig = config;
+	mConfig	   = config;
+	mOutputDir = config.value("output_dir", baseDir + "/output");
+	// gpContext->getGlobalConfig()["reference"] (errormeasure.h:69-70) and the pass's own "reference";
+	// relative paths are resolved against the asset root
+	for (auto &p : mRenderPasses)
+		if (auto em = std::dynamic_pointer_cast<ErrorMeasurePass>(p)) {
+			auto resolve = [&](const string &r) { return (!r.empty() && r[0] != '/') ? assetBase + "/" + r : r; };
+			if (config.contains("reference")) em->loadReferenceImage(resolve(config.at("reference").asString()));
+			string own = em->toJson().value("reference", "");
+			if (!own.empty()) em->loadReferenceImage(resolve(own));
+		}
 }
 
 void RenderApp::setScene(Scene::SharedPtr scene) {
@@ -262,6 +462,21 @@ void RenderApp::initialize() {
 	setScene(mScene);
 	resize(mSize);
 	mInitialized = true;
+}
+
+void RenderApp::finalize() {
+	for (auto &p : mRenderPasses) p->finalize();
+}
+
+size_t RenderApp::run(size_t maxFrames) {
+	// DeviceManager::runMessageLoop (window.cpp:450-485) without the window: until a pass requests the exit
+	size_t n = 0;
+	const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	while (!mExit && (!maxFrames || n < maxFrames)) {
+		renderFrame(std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0);
+		n++;
+	}
+	return n;
 }
 
 void RenderApp::renderFrame(double t) {

@@ -211,6 +211,27 @@ def test_flat_blas_gives_the_identical_film(cbox_app, merge):
         assert out[0][1][k] == out[1][1][k], k
 
 
+def test_programmatic_dependent_launch_gives_the_identical_film(cbox_app):
+    """pdl (optional, off by default: measured 1.6 % slower): each stage kernel is launched with programmatic stream serialization and waits
+    for its predecessor on the device; three frames back to back must equal the serialized launches."""
+    w = h = 64
+    app = cbox_app(w, h, spp=3, max_depth=6)
+    cam = app.camera()
+    out = []
+    for flag in (False, True):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), pdl=flag))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(w, h)
+        films = []
+        for f in (1, 2, 3):
+            gpu.begin_frame(f, cam)
+            films.append(gpu.render_to_host().copy())
+        out.append((films, gpu.stats()))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert out[0][1]["closest_by_depth"] == out[1][1]["closest_by_depth"]
+
+
 def test_fused_schedule_gives_the_identical_film(cbox_app):
     """fuse_stages (default): handleHit/Miss as the prologue of the scatter launch, shadow rays of depth
     d and closest rays of depth d + 1 in one trace launch.  Per pixel the order of RNG draws and of the

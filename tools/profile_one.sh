@@ -1,0 +1,5 @@
+#!/bin/bash
+# GPU box: one `ncu --set full` capture with source correlation.  usage: tools/profile_one.sh <kernel regex> <skip> <tag>
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c 1 -f -o gpurun_out/prof_$3 python bench.py --steps 1 --warmup 1 --spp 1 --no-cpu-baseline > gpurun_out/prof_$3.log 2>&1
+ls -la gpurun_out/prof_$3.ncu-rep
