@@ -234,30 +234,38 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			// FMA.  b - 2^15 a is rounded once: error <= |a| / 512, i.e. 1/512 of a quantisation step, against
 			// the full step the builder pads every child plane with (quantize() in bvh_build.cu).
 			const float axs = ax * 0.00390625f, ays = ay * 0.00390625f, azs = az * 0.00390625f;
-			const float bxs = fmaf(-32768.f, ax, bx), bys = fmaf(-32768.f, ay, by), bzs = fmaf(-32768.f, az, bz);
-			// rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
-			// when the ray grazes an axis-aligned plane): the test and the stored entry distance are widened
-			// by it, so flat boxes are never culled by arithmetic noise
-			// (an axis the ray is parallel to has a = inf and yields NaN distances, which min/max drop: it neither
-			// culls nor needs slack -- without the guard it would switch culling off on the other two axes too)
+			// Rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
+			// when the ray grazes an axis-aligned plane), PER AXIS: each slab interval is widened by its own
+			// bound, folded into the FMA constant of its near / far plane.  (One scalar bound for all axes let a
+			// ray that is nearly parallel to one axis -- huge a, b on that axis -- lose culling on the other two:
+			// the pixels of one image column / row took 13x longer than the rest of the frame together.)
+			// An axis the ray is exactly parallel to has a = inf and yields NaN distances, which min/max drop.
 			auto axisSlack = [](float a, float b) { return fabsf(a) < 3.0e38f ? (fabsf(b) + 255.f * fabsf(a)) * 2.4e-7f + fabsf(a) * 0.00390625f : 0.f; };
-			const float slack = axisSlack(ax, bx) + axisSlack(ay, by) + axisSlack(az, bz);
+			const float slx = axisSlack(ax, bx), sly = axisSlack(ay, by), slz = axisSlack(az, bz);
+			const float bx0 = fmaf(-32768.f, ax, bx), by0 = fmaf(-32768.f, ay, by), bz0 = fmaf(-32768.f, az, bz);
+			const float bxN = bx0 - slx, bxF = bx0 + slx, byN = by0 - sly, byF = by0 + sly, bzN = bz0 - slz, bzF = bz0 + slz;
+			// ray octant: which plane of a slab is entered first only depends on the sign of the direction, so
+			// the near / far plane words are selected once per node instead of a min and a max per child
+			const bool px = ax >= 0.f, py = ay >= 0.f, pz = az >= 0.f;
+			const uint32_t nX[2] = {px ? q[0] : q[6], px ? q[1] : q[7]}, fX[2] = {px ? q[6] : q[0], px ? q[7] : q[1]};
+			const uint32_t nY[2] = {py ? q[2] : q[8], py ? q[3] : q[9]}, fY[2] = {py ? q[8] : q[2], py ? q[9] : q[3]};
+			const uint32_t nZ[2] = {pz ? q[4] : q[10], pz ? q[5] : q[11]}, fZ[2] = {pz ? q[10] : q[4], pz ? q[11] : q[5]};
 			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
 			auto child = [&](int i) -> uint32_t {
 				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
 				bool internal = (imask >> i) & 1;
 				if (!internal && meta == 0) return kEmptyEntry;
-				auto qb = [&](int row) { return __uint_as_float(__byte_perm(q[row * 2 + (i >> 2)], 0x4b000000u, 0x7404u | ((i & 3) << 4))); };
-				float t0x = fmaf(qb(0), axs, bxs), t1x = fmaf(qb(3), axs, bxs);
-				float t0y = fmaf(qb(1), ays, bys), t1y = fmaf(qb(4), ays, bys);
-				float t0z = fmaf(qb(2), azs, bzs), t1z = fmaf(qb(5), azs, bzs);
+				auto qf = [&](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7404u | ((i & 3) << 4))); };
+				const float tnx = fmaf(qf(nX[i >> 2]), axs, bxN), tfx = fmaf(qf(fX[i >> 2]), axs, bxF);
+				const float tny = fmaf(qf(nY[i >> 2]), ays, byN), tfy = fmaf(qf(fY[i >> 2]), ays, byF);
+				const float tnz = fmaf(qf(nZ[i >> 2]), azs, bzN), tfz = fmaf(qf(fZ[i >> 2]), azs, bzF);
 				// fminf/fmaxf drop NaNs (0 * inf), which is the conservative answer for a degenerate slab
-				float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
-				float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), lim));
+				const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+				const float tf = fminf(fminf(tfx, tfy), fminf(tfz, lim));
 				// conservative: boxes only cull, the exact decision is the triangle test
-				if (!(tn <= tf * 1.0000010f + slack)) return kEmptyEntry;
+				if (!(tn <= tf * 1.0000010f)) return kEmptyEntry;
 				// key: entry distance in the high bits, slot in the low 3 -> one compare orders (tn, slot)
-				return (__float_as_uint(fmaxf(tn - slack, 0.f)) & ~7u) | (uint32_t) i;
+				return (__float_as_uint(tn) & ~7u) | (uint32_t) i;
 			};
 			k0 = child(0), k1 = child(1), k2 = child(2), k3 = child(3), k4 = child(4), k5 = child(5), k6 = child(6), k7 = child(7);
 			// 19-comparator sorting network: ascending, misses (0xffffffff) sink to the end

@@ -24,6 +24,7 @@ namespace krr {
 namespace {
 
 struct Aabb { float lo[3], hi[3]; };
+struct WorkItem { int32_t bin, out; }; // collapse work list: binary node -> output slot of its wide node
 
 KRR_DEV void atomicMinF(float *addr, float v) {
 	// ordered-int trick; valid for all finite floats
@@ -269,7 +270,6 @@ struct CollapseOut {
 	uint32_t primBase;	// offset of this tree's primitives in the global pool
 };
 
-struct WorkItem { int32_t bin, out; };
 
 // leaf payload writers
 struct TriWriter {
@@ -455,8 +455,22 @@ template <typename T> struct DevBuf {
 		n = count;
 		return cudaMalloc((void **) &p, std::max<size_t>(count, 1) * sizeof(T)) == cudaSuccess;
 	}
+	// grow-only: scratch that is reused across the trees of one build (cudaMalloc / cudaFree synchronise the
+	// device and cost milliseconds each once gigabytes are resident -- 30 of them per mesh made the build of a
+	// 200-mesh scene take 15-20 s)
+	bool ensure(size_t count) { return count <= n && p ? true : alloc(count + count / 4); }
 	void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
 	~DevBuf() { free(); }
+};
+
+struct TreeScratch {
+	DevBuf<uint64_t> keys, keysSorted;
+	DevBuf<uint32_t> vals, valsSorted;
+	DevBuf<int32_t> left, right, parent, first, last, flags;
+	DevBuf<Aabb> bounds;
+	DevBuf<WorkItem> q0, q1;
+	DevBuf<int32_t> qCount;
+	DevBuf<unsigned char> tmp;
 };
 
 } // namespace
@@ -485,25 +499,26 @@ namespace {
 // receives the pool index of the first node of each level.
 template <typename Writer>
 bool buildTree(const Aabb *boxes, int n, int maxLeaf, Node8 *nodePool, Aabb *boundsPool, int32_t *counters, int &nodeCursor,
-			   int &primCursor, Writer writer, cudaStream_t stream, float *cb, std::vector<int> *levelStart, int *root, char *err) {
+			   int &primCursor, Writer writer, cudaStream_t stream, float *cb, std::vector<int> *levelStart, int *root, char *err,
+			   TreeScratch &sc) {
 	const int T = 256;
-	DevBuf<uint64_t> keys, keysSorted;
-	DevBuf<uint32_t> vals, valsSorted;
-	DevBuf<int32_t> left, right, parent, first, last, flags;
-	DevBuf<Aabb> bounds;
-	DevBuf<WorkItem> q0, q1;
-	DevBuf<int32_t> qCount;
-	DevBuf<unsigned char> tmp;
-	if (!keys.alloc(n) || !keysSorted.alloc(n) || !vals.alloc(n) || !valsSorted.alloc(n) || !left.alloc(n) || !right.alloc(n) ||
-		!parent.alloc(2 * n) || !first.alloc(2 * n) || !last.alloc(2 * n) || !flags.alloc(n) || !bounds.alloc(2 * n) ||
-		!q0.alloc(n + 1) || !q1.alloc(n + 1) || !qCount.alloc(1)) {
+	DevBuf<uint64_t> &keys = sc.keys, &keysSorted = sc.keysSorted;
+	DevBuf<uint32_t> &vals = sc.vals, &valsSorted = sc.valsSorted;
+	DevBuf<int32_t> &left = sc.left, &right = sc.right, &parent = sc.parent, &first = sc.first, &last = sc.last, &flags = sc.flags;
+	DevBuf<Aabb> &bounds = sc.bounds;
+	DevBuf<WorkItem> &q0 = sc.q0, &q1 = sc.q1;
+	DevBuf<int32_t> &qCount = sc.qCount;
+	DevBuf<unsigned char> &tmp = sc.tmp;
+	if (!keys.ensure(n) || !keysSorted.ensure(n) || !vals.ensure(n) || !valsSorted.ensure(n) || !left.ensure(n) || !right.ensure(n) ||
+		!parent.ensure(2 * n) || !first.ensure(2 * n) || !last.ensure(2 * n) || !flags.ensure(n) || !bounds.ensure(2 * n) ||
+		!q0.ensure(n + 1) || !q1.ensure(n + 1) || !qCount.ensure(1)) {
 		snprintf(err, 256, "bvh build: out of device memory for %d primitives", n);
 		return false;
 	}
 	k_morton<<<(n + T - 1) / T, T, 0, stream>>>(boxes, n, cb, keys.p, vals.p);
 	size_t tmpBytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, vals.p, valsSorted.p, n, 0, 63, stream);
-	if (!tmp.alloc(tmpBytes)) { snprintf(err, 256, "bvh build: sort scratch alloc failed"); return false; }
+	if (!tmp.ensure(tmpBytes)) { snprintf(err, 256, "bvh build: sort scratch alloc failed"); return false; }
 	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysSorted.p, vals.p, valsSorted.p, n, 0, 63, stream));
 	BinTree t{left.p, right.p, parent.p, first.p, last.p, bounds.p, flags.p};
 	CK(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * std::max(n, 1), stream));
@@ -580,6 +595,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		return false;
 	}
 	CK(cudaMemcpyAsync(b.tlasIds.p, tlasIds.data(), tlasIds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+	TreeScratch scratch;
 	DevBuf<Aabb> primBoxes;
 	DevBuf<float> cb;
 	if (!primBoxes.alloc(std::max<size_t>(std::max<size_t>(maxTris, mergedTris), tlasIds.size())) || !cb.alloc(6)) { snprintf(err, 256, "bvh build: alloc failed"); return false; }
@@ -605,7 +621,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			continue;
 		}
 		int root = 0;
-		if (!buildTree(primBoxes.p, mr.nTri, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
+		if (!buildTree(primBoxes.p, mr.nTri, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 			return false;
 		b.blasRoots[i] = root;
 	}
@@ -629,7 +645,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			CK(cudaStreamSynchronize(stream)); // dsrc / pairs die with this scope
 		} else {
 			int root = 0;
-			if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err))
+			if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 				return false;
 			b.mergedRoot = root;
 		}
@@ -649,7 +665,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 																		 cb.p, motion.xnodes, motion.keys, motion.w0, motion.w1);
 		int tlasCursor = 0, tlasPrims = 0, root = 0;
 		InstWriter iw{b.tlasInst.p, b.tlasIds.p};
-		if (!buildTree(primBoxes.p, b.nTlasPrims, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err))
+		if (!buildTree(primBoxes.p, b.nTlasPrims, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err, scratch))
 			return false;
 		if (tlasCursor > tlasReserve) { snprintf(err, 256, "bvh build: TLAS node reservation exceeded"); return false; }
 		b.tlasNodeCount = tlasCursor;

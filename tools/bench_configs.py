@@ -12,8 +12,8 @@ import torch
 import kiraray_b200 as krr
 from kiraray_b200 import scenes
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
 scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0
+args = [a for a in sys.argv[1:] if a.isdigit()]
 which = [int(a) for a in args] or [3, 4, 5]
 
 
@@ -32,6 +32,7 @@ def run(name, desc, cam, w, h, params, frames=3, warm=1, extra=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0
     ms = 0.0
+    per_frame = []
     for f in range(frames):
         e0.record(st)
         gpu.begin_frame(10 + f, cam, st.cuda_stream)
@@ -39,6 +40,7 @@ def run(name, desc, cam, w, h, params, frames=3, warm=1, extra=None):
         e1.record(st)
         torch.cuda.synchronize()
         ms += e0.elapsed_time(e1)
+        per_frame.append(round(e0.elapsed_time(e1), 2))
         s = gpu.stats()
         rays += s["closest_rays"] + s["shadow_rays"]
     gpu.set_profiling(True)
@@ -47,7 +49,7 @@ def run(name, desc, cam, w, h, params, frames=3, warm=1, extra=None):
     torch.cuda.synchronize()
     stages = {k: round(v["ms"], 3) for k, v in gpu.stage_times().items() if v["launches"]}
     s = gpu.stats()
-    line = {"workload": name, "width": w, "height": h, "params": params, "Mrays_per_s": rays / (ms * 1e-3) / 1e6, "ms_per_frame": ms / frames,
+    line = {"workload": name, "width": w, "height": h, "params": params, "Mrays_per_s": rays / (ms * 1e-3) / 1e6, "ms_per_frame": ms / frames, "ms_frames": per_frame,
             "rays_per_frame": rays // frames, "accel_build_s": round(build_s, 3), "bvh_nodes": s["bvh_nodes"], "bvh_triangles": s["bvh_triangles"],
             "tlas_nodes": s["tlas_nodes"], "stage_ms": stages, "finite": bool(torch.isfinite(film).all())}
     if extra:
