@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace krr {
@@ -559,6 +560,8 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const uint8_t *hMerge, int flatMax,
 					   const MotionWindow &motion, cudaStream_t stream, char *err) {
 	Impl &b = *m;
+	// triangles per leaf child: the node format addresses 8 leaf children x maxLeaf <= 32 primitives
+	const int maxLeaf = std::min(std::max(getenv("KRR_BVH_MAX_LEAF") ? atoi(getenv("KRR_BVH_MAX_LEAF")) : 3, 1), 4);
 	std::vector<int2> flats;
 	b.nMeshes = nMeshes, b.nInstances = nInstances;
 	// which instances go into the merged world-space BLAS, which meshes still need a BLAS of their own
@@ -621,7 +624,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			continue;
 		}
 		int root = 0;
-		if (!buildTree(primBoxes.p, mr.nTri, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
+		if (!buildTree(primBoxes.p, mr.nTri, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 			return false;
 		b.blasRoots[i] = root;
 	}
@@ -645,7 +648,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			CK(cudaStreamSynchronize(stream)); // dsrc / pairs die with this scope
 		} else {
 			int root = 0;
-			if (!buildTree(primBoxes.p, (int) mergedTris, 3, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
+			if (!buildTree(primBoxes.p, (int) mergedTris, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 				return false;
 			b.mergedRoot = root;
 		}

@@ -251,3 +251,39 @@ def test_fused_schedule_gives_the_identical_film(cbox_app):
     assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
     for k in ("closest_rays", "shadow_rays", "scatter_items", "hit_light_items", "miss_items", "closest_by_depth", "shadow_by_depth"):
         assert out[0][1][k] == out[1][1][k], k
+
+
+def test_full_size_properties_1080p(cbox_app):
+    """BASELINE.json configs[1] at its full size (1920x1080, depth 10), through properties that do not
+    need the oracle: (i) every acceleration-structure layout (tree / flat list, merged / per-instance) gives
+    the same film bit for bit, (ii) two row bands rendered separately add up to the full film, (iii) the
+    stage counters are consistent: one camera ray per pixel, every closest ray of depth d + 1 was produced
+    by a scatter item of depth d, and a path never grows."""
+    W, H = 1920, 1080
+    app = cbox_app(W, H, spp=1, max_depth=10)
+    cam = app.camera()
+    films, stats = [], []
+    for merge, flat in ((True, 48), (False, 0), (True, 0)):
+        gpu = krr.Wfpt(params=dict(app.wfpt_params(), merge_static=merge, flat_blas_max=flat))
+        gpu.set_scene(app.scene_desc())
+        gpu.resize(W, H)
+        gpu.begin_frame(7, cam)
+        films.append(gpu.render_to_host().copy())
+        stats.append(gpu.stats())
+        if merge and flat:
+            acc = np.zeros_like(films[0])
+            for r0, r1 in ((0, 500), (500, H)):
+                gpu.set_partition(r0, r1)
+                gpu.begin_frame(7, cam)
+                acc += gpu.render_to_host()
+            assert np.array_equal(acc.view(np.uint32), films[0].view(np.uint32)), "row bands do not add up to the frame"
+    for f, s in zip(films[1:], stats[1:]):
+        assert np.array_equal(f.view(np.uint32), films[0].view(np.uint32))
+        assert s["closest_by_depth"] == stats[0]["closest_by_depth"] and s["shadow_by_depth"] == stats[0]["shadow_by_depth"]
+    s = stats[0]
+    assert s["camera_rays"] == W * H == s["closest_by_depth"][0]
+    c = s["closest_by_depth"]
+    assert all(c[d + 1] <= c[d] for d in range(10)) and c[10] > 0 and c[11] == 0
+    assert s["closest_rays"] == sum(c) and s["shadow_rays"] == sum(s["shadow_by_depth"])
+    assert s["scatter_items"] + s["miss_items"] >= s["closest_rays"] - c[10] - 8, "every ray is a miss or reaches the scatter stage"
+    assert np.isfinite(films[0]).all() and np.all(films[0][..., 3] == 1)
