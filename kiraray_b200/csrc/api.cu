@@ -239,6 +239,10 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 	uint32_t seedIndex = (uint32_t) (h->frameIndex * (uint64_t) h->spp);
 	wf.p.rngInc		 = ((uint64_t) seedIndex << 1u) | 1u;
 	wf.p.sampleIndex = (uint32_t) sampleId;
+	{
+		const BvhDev bd = h->bvh.device();
+		wf.p.refill = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? kRefillFlat : kRefill;
+	}
 	wf.cam	 = h->cam;
 	wf.scene = h->scene;
 	wf.bvh	 = h->bvh.device();
