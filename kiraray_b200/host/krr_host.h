@@ -48,6 +48,8 @@ struct HostInstance {
 	// simple keyframe animation (reference src/core/animation.h): linear SRT keys over time
 	std::vector<float> animTimes;
 	std::vector<KrrSRT> animKeys;
+	// transform of the (static) ancestors of an animated node: world = animParent * SRT(t)
+	float animParent[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 };
 
 struct HostMaterial {
@@ -118,6 +120,8 @@ public:
 						  const string &baseDir);
 };
 bool loadObj(const string &filepath, Scene &scene, const float nodeTransform[12]);
+// minimal glTF 2.0 (gltf.cpp): meshes, node hierarchy, pbrMetallicRoughness materials, PNG textures, TRS animation
+bool loadGltf(const string &filepath, Scene &scene, const float nodeTransform[12]);
 
 // ------------------------------------------------------------------------------------------------
 // HDR images (image.cpp): RGBA32F, row 0 first -- the layout of the film buffer
@@ -135,6 +139,7 @@ bool saveImage(const string &path, const Image &img, bool flip, string *err = nu
 bool loadEXR(const string &path, Image &img, string *err = nullptr);
 bool saveEXR(const string &path, const Image &img, bool halfPrecision, bool zip, string *err = nullptr);
 bool loadPFM(const string &path, Image &img, string *err = nullptr);
+bool loadPNG(const string &path, Image &img, bool srgb, string *err = nullptr); // 8-bit, non-interlaced (gltf.cpp)
 bool savePFM(const string &path, const Image &img, string *err = nullptr);
 
 // ------------------------------------------------------------------------------------------------

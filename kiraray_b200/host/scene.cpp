@@ -97,6 +97,7 @@ bool Scene::update(size_t frameIndex, double t) {
 			for (int c = 0; c < 4; c++) s.q[c] = (1 - a) * A.q[c] + a * (d < 0 ? -B.q[c] : B.q[c]);
 			float m[12];
 			srtToMat(s, m);
+			mul12(in.animParent, m, m);
 			if (memcmp(m, in.transform, sizeof m)) {
 				memcpy(in.transform, m, sizeof m);
 				updatedInstances.push_back((int32_t) i);
@@ -690,13 +691,14 @@ bool SceneImporter::loadModel(const string &filepath, Scene::SharedPtr scene, co
 	// OptiX build; here a missing asset is an error the C entry point returns
 	if (!fileExists(path)) throw std::runtime_error("cannot open model " + path);
 	if (ext == ".obj") return loadObj(path, *scene, xf);
+	if (ext == ".gltf") return loadGltf(path, *scene, xf);
 	if (ext == ".json") {
 		std::ifstream f(path);
 		std::stringstream ss;
 		ss << f.rdbuf();
 		return SceneImporter::import(json::parse(ss.str()), scene, dirOf(path));
 	}
-	return false; // glTF / FBX / pbrt / VDB importers are out of scope
+	return false; // .glb / FBX / pbrt / VDB importers are out of scope
 }
 
 bool SceneImporter::import(const json &j, Scene::SharedPtr scene, const string &baseDir) {
