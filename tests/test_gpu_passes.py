@@ -141,3 +141,24 @@ def test_config_with_all_passes_runs_to_its_budget_and_saves(tmp_path):
     value, _ = app.last_error_metric()
     assert app.accum_count() == 6
     assert value == pytest.approx(relmse(avg * np.float32(6 / 7), reference), rel=1e-3)
+
+
+def test_gltf_scene_renders_and_animates(tmp_path):
+    """The glTF fixture of tests/test_gltf.py (textured emissive quads, one keyframe-animated) through the
+    headless app: frames at different times differ (instance update -> TLAS refit), films are finite and lit."""
+    from test_gltf import make_fixture
+    make_fixture(str(tmp_path))
+    cfg = {"resolution": [64, 64],
+           "passes": [{"enable": True, "name": "WavefrontPathTracer", "params": {"max_depth": 3, "spp": 4}}],
+           "scene": {"model": [{"model": "quad.gltf"}],
+                     "camera": {"mData": {"focalLength": 21.0}},
+                     "cameraController": {"mData": {"target": [4.0, 4.0, 10.0], "radius": 30.0, "pitch": 0.0, "yaw": 0.0}}}}
+    app = krr.HostApp(cfg, asset_root=str(tmp_path))
+    f1 = app.render_frames(1).copy()
+    assert np.isfinite(f1).all() and f1[..., :3].max() > 0.1, "the emissive quads are visible"
+    lib = app.lib
+    # same frame index semantics, later time: the animated quad has moved
+    app2 = krr.HostApp(cfg, asset_root=str(tmp_path))
+    app2.camera(2.0)
+    x = np.array(list(app2.scene_desc().contents.instances[0].transform)).reshape(3, 4)
+    assert not np.allclose(x[:, 3], [18, 18, 28]), "animation sampled"
