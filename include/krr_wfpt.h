@@ -326,6 +326,12 @@ int krr_wfpt_debug_camera_rays(KrrWfpt *h, const KrrCameraData *camera, int32_t 
  * report at a hit (getInstanceTransform, src/render/shading.h:70-76), evaluated on the device */
 int krr_wfpt_debug_instance_xf(KrrWfpt *h, const int32_t *instance_ids_host, const float *times_host, int32_t n, float *out24_host);
 
+/* ---- the reference's MegakernelPathTracer (src/render/megakernel/device.cu:50-195) on the
+ * same handle: one launch, one lane per pixel, power-heuristic MIS; uses the handle's scene, size and the
+ * params nee / max_depth / rr / spp.  film: device float4[w*h] (sum over spp, like the reference).  An
+ * independent estimator for cross-validation, not a fast path. */
+int krr_wfpt_render_megakernel(KrrWfpt *h, uint64_t frame_index, const KrrCameraData *camera, float *film_device, void *cuda_stream);
+
 /* ---- next row: AccumulatePass kernel, src/render/passes/accumulate/accumulate.cu:30-52 ----
  * accum, film: device float4[n_pixels]; film is replaced by the running average. */
 int krr_accumulate_f32(float *accum, float *film, int64_t n_pixels, uint64_t accum_count,

@@ -154,6 +154,7 @@ def load_wfpt():
         "krr_wfpt_begin_frame": [P, U64, C.POINTER(KrrCameraData), P],
         "krr_wfpt_render": [P, P, P],
         "krr_wfpt_render_to_host": [P, P, P],
+        "krr_wfpt_render_megakernel": [P, U64, C.POINTER(KrrCameraData), P, P],
         "krr_wfpt_set_partition": [P, I32, I32],
         "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
         "krr_wfpt_set_profiling": [P, I32],
@@ -412,6 +413,10 @@ class Wfpt:
 
     def render(self, film_device_ptr, stream=None):
         self._ck(self.lib.krr_wfpt_render(self.h, P(film_device_ptr), P(stream or 0)), "render")
+
+    def render_megakernel(self, frame_index, cam, film_device_ptr, stream=None):
+        """The reference's MegakernelPathTracer on this handle's scene (cross-validation estimator)."""
+        self._ck(self.lib.krr_wfpt_render_megakernel(self.h, frame_index, C.byref(cam), P(film_device_ptr), P(stream or 0)), "render_megakernel")
 
     def render_to_host(self, film=None, stream=None):
         w, h = self.size

@@ -14,6 +14,7 @@
 #include "krr_wfpt.h"
 #include "wavefront_kernels.cuh"
 #include "leaf_debug.cuh"
+#include "megakernel.cuh"
 
 using namespace krr;
 
@@ -883,6 +884,37 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	h->launches++;
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;
+	return KRR_OK;
+}
+
+// MegakernelPathTracer::render (src/render/megakernel/pathtracer.cpp): one launch, one lane per pixel
+extern "C" int krr_wfpt_render_megakernel(KrrWfpt *h, uint64_t frameIndex, const KrrCameraData *c, float *film, void *stream) {
+	if (!h || !c || !film) return fail(KRR_E_INVALID, "null argument");
+	if (!h->haveScene) return fail(KRR_E_STATE, "set_scene first");
+	if (h->width <= 0) return fail(KRR_E_STATE, "resize first");
+	CUDA_OK(cudaSetDevice(h->device));
+	cudaStream_t st = (cudaStream_t) stream;
+	h->cam = makeCamera(c);
+	if (h->scene.hasMotion) {
+		float w0 = c->shutter_open, w1 = c->shutter_open + c->shutter_time;
+		if (w1 < w0) std::swap(w0, w1);
+		if (w0 != h->motionW0 || w1 != h->motionW1) {
+			MotionWindow mw;
+			mw.xnodes = h->xnodes.p, mw.keys = h->motionKeys.p, mw.w0 = w0, mw.w1 = w1;
+			char err[256] = "";
+			if (!h->bvh.refitTlas(h->instances.p, st, err, &mw)) return fail(KRR_E_CUDA, "%s", err);
+			h->motionW0 = w0, h->motionW1 = w1;
+		}
+	}
+	Wavefront wf = makeWavefront(h, 0);
+	MegaParams mp{h->width, h->height, h->spp, h->maxDepth, h->nee ? 1 : 0, h->probRR, (uint32_t) frameIndex};
+	static int grid = 0, gridM = 0;
+	if (!grid) grid = gridFor(h, k_megakernel<false>, kTraceBlock), gridM = gridFor(h, k_megakernel<true>, kTraceBlock);
+	if (h->scene.hasMotion) k_megakernel<true><<<gridM, kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
+	else k_megakernel<false><<<grid, kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
+	CUDA_OK(cudaGetLastError());
+	h->lastStream = st;
+	h->launches	  = 1;
 	return KRR_OK;
 }
 

@@ -263,6 +263,27 @@ private:
 	uint64_t mSceneVersion = 0;
 };
 
+// MegakernelPathTracer: src/render/megakernel/pathtracer.{h,cpp}; JSON nee, max_depth, rr
+class MegakernelPathTracer : public RenderPass {
+public:
+	KRR_REGISTER_PASS_DEC(MegakernelPathTracer);
+	~MegakernelPathTracer() override;
+	void resize(const Vector2i &size) override;
+	void setScene(Scene::SharedPtr scene) override;
+	void render(RenderContext *context) override;
+	string getName() const override { return "MegakernelPathTracer"; }
+	void fromJson(const json &j);
+	json toJson() const override;
+	bool enableNEE{true};
+	int maxDepth{10};
+	float probRR{0.8f};
+	int samplesPerPixel{1};
+
+private:
+	void ensureHandle();
+	KrrWfpt *mHandle = nullptr;
+};
+
 // AccumulatePass: src/render/passes/accumulate/accumulate.{h,cu}
 // JSON: spp, mode ("accumulate" | "moving average"), precision ("float" | "double"), save_on_finish,
 // exit_on_finish, save_every, task {"type": "spp" | "time", "value": N} (accumulate.h:31-57, util/task.h)

@@ -165,6 +165,48 @@ KrrStats WavefrontPathTracer::stats() {
 	return s;
 }
 
+// ---------------- MegakernelPathTracer ----------------
+KRR_REGISTER_PASS_DEF(MegakernelPathTracer);
+
+void MegakernelPathTracer::fromJson(const json &j) { // pathtracer.h:41-45
+	enableNEE = j.value("nee", true);
+	maxDepth  = j.value("max_depth", 10);
+	probRR	  = j.value("rr", 0.8f);
+	samplesPerPixel = j.value("spp", 1);
+}
+json MegakernelPathTracer::toJson() const {
+	json j = json::object();
+	j["nee"] = json(enableNEE), j["max_depth"] = json(maxDepth), j["rr"] = json((double) probRR), j["spp"] = json(samplesPerPixel);
+	return j;
+}
+MegakernelPathTracer::~MegakernelPathTracer() { if (mHandle) krr_wfpt_destroy(mHandle); }
+void MegakernelPathTracer::ensureHandle() {
+	if (mHandle) return;
+	check(krr_wfpt_create(toJson().dump().c_str(), &mHandle), "krr_wfpt_create");
+	check(krr_wfpt_set_color_space(mHandle, &defaultColorSpace()), "krr_wfpt_set_color_space");
+}
+void MegakernelPathTracer::resize(const Vector2i &size) {
+	RenderPass::resize(size);
+	ensureHandle();
+	check(krr_wfpt_resize(mHandle, size.x, size.y), "krr_wfpt_resize");
+}
+void MegakernelPathTracer::setScene(Scene::SharedPtr scene) {
+	mScene = scene;
+	ensureHandle();
+	check(krr_wfpt_set_scene(mHandle, &scene->desc()), "krr_wfpt_set_scene");
+}
+void MegakernelPathTracer::render(RenderContext *context) {
+	if (!mScene || !mHandle) return;
+	check(krr_wfpt_set_params(mHandle, toJson().dump().c_str()), "krr_wfpt_set_params");
+	if (!mScene->updatedInstances.empty()) {
+		std::vector<float> xf(mScene->updatedInstances.size() * 12);
+		for (size_t i = 0; i < mScene->updatedInstances.size(); i++) memcpy(&xf[12 * i], mScene->instances[mScene->updatedInstances[i]].transform, 48);
+		check(krr_wfpt_update_instances(mHandle, mScene->updatedInstances.data(), xf.data(), (int32_t) mScene->updatedInstances.size(), context->getStream()),
+			  "krr_wfpt_update_instances");
+	}
+	check(krr_wfpt_render_megakernel(mHandle, getFrameIndex(), &mScene->camera, context->getColorDevice(), context->getStream()), "krr_wfpt_render_megakernel");
+}
+
 // ---------------- AccumulatePass ----------------
 KRR_REGISTER_PASS_DEF(AccumulatePass);
 
@@ -399,7 +441,7 @@ void RenderApp::loadConfig(const json &config, const string &baseDir) {
 			if (!pass) {
 				// reference passes outside the hot path are recognised and skipped; any other name is
 				// the reference's Log(Fatal) "Could not find pass" (renderpass.h:216-220, 228-232)
-				static const char *kOutOfScope[] = {"DenoisePass", "MegakernelPathTracer", "BDPTIntegrator", "PPGPathTracer", "GBufferPass",
+				static const char *kOutOfScope[] = {"DenoisePass", "BDPTIntegrator", "PPGPathTracer", "GBufferPass",
 													"BindlessRender", "RasterizePass"};
 				bool known = false;
 				for (const char *k : kOutOfScope) known |= name == k;
