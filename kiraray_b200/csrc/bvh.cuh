@@ -57,6 +57,10 @@ struct BvhDev {
 	// (no stack, no slab tests, no divergence between lanes), which for a few dozen triangles costs
 	// fewer issue slots than the wide-node traversal it replaces.
 	const int2 *flats;
+	// world box of the merged BLAS (padded): with mergedOnly there is no TLAS above it whose node test would
+	// reject rays that miss the scene altogether, so begin() tests it (primary rays beside the Cornell box
+	// skip its 36 triangles)
+	float rootLo[3], rootHi[3];
 };
 
 struct Hit {
@@ -152,7 +156,15 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 		setIdir();
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
 		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
-		if (bvh.mergedOnly) cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
+		if (bvh.mergedOnly) {
+			cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
+			const float t0x = (bvh.rootLo[0] - o_.x) * idir.x, t1x = (bvh.rootHi[0] - o_.x) * idir.x;
+			const float t0y = (bvh.rootLo[1] - o_.y) * idir.y, t1y = (bvh.rootHi[1] - o_.y) * idir.y;
+			const float t0z = (bvh.rootLo[2] - o_.z) * idir.z, t1z = (bvh.rootHi[2] - o_.z) * idir.z;
+			const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
+			const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_));
+			if (!(tn <= tf * 1.00001f + 1e-30f)) cur = kEmptyEntry, curInst = -1; // NaNs (0 * inf) are dropped by min / max
+		}
 		// A ray with a NaN / infinite component or a zero direction cannot hit anything (every comparison of
 		// the triangle test fails, det == 0), but its slab tests cannot cull either: it would walk the WHOLE
 		// tree (seconds on a 20 M-triangle scene).  Such rays come out of degenerate BSDF samples; they are

@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -485,6 +486,7 @@ struct BvhBuilder::Impl {
 	DevBuf<int32_t> counters, tlasIds;
 	DevBuf<int2> flats;
 	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0, nFlat = 0;
+	Aabb mergedBox{{0, 0, 0}, {0, 0, 0}};
 	std::vector<int> tlasLevelStart; // node index (relative to the pool) where each TLAS level begins
 	int tlasNodeCount = 0, totalNodes = 0, totalTris = 0, nInstances = 0, nMeshes = 0;
 	std::vector<int32_t> blasRoots, triBases;
@@ -653,6 +655,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			b.mergedRoot = root;
 		}
 	}
+	if (haveMerged) CK(cudaMemcpyAsync(&b.mergedBox, b.meshBoxes.p + nMeshes, sizeof(Aabb), cudaMemcpyDeviceToHost, stream));
 	b.nFlat = (int) flats.size();
 	if (!b.flats.alloc(flats.size())) { snprintf(err, 256, "bvh build: alloc failed (flat table)"); return false; }
 	if (!flats.empty()) CK(cudaMemcpyAsync(b.flats.p, flats.data(), flats.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
@@ -701,6 +704,10 @@ BvhDev BvhBuilder::device() const {
 	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
 	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot;
 	d.flats = m->flats.p;
+	for (int k = 0; k < 3; k++) { // padded: the box only culls, the exact decision is the triangle test
+		const float lo = m->mergedBox.lo[k], hi = m->mergedBox.hi[k], pad = 1e-4f * (hi - lo) + 1e-5f * std::max(std::fabs(lo), std::fabs(hi)) + 1e-30f;
+		d.rootLo[k] = lo - pad, d.rootHi[k] = hi + pad;
+	}
 	d.mergedOnly = m->mergedInst >= 0 && m->nTlasPrims == 1; // the pseudo-instance is the only TLAS primitive
 	return d;
 }
