@@ -34,7 +34,9 @@ struct __align__(16) Node8 {
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
-struct BvhTri { float4 v0, v1, v2; }; // xyz = object-space vertex, v0.w = primitive id, v1.w = instance id (merged BLAS only)
+// v0.xyz = first vertex, e1 = v1 - v0, e2 = v2 - v0 (the first two operations of the triangle test, done once
+// at build time with the same rounding); v0.w = primitive id, e1.w = instance id (merged BLAS only)
+struct BvhTri { float4 v0, e1, e2; };
 
 struct BvhDev {
 	const Node8 *nodes;	   // node pool: TLAS nodes first, then every mesh's BLAS
@@ -69,8 +71,12 @@ struct Hit {
 };
 
 // ---- the intersection spec (keep identical to oracle/driver.cpp triIntersect) ----
+KRR_HD bool triIntersectE(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmax, float &t, float &u, float &v);
 KRR_HD bool triIntersect(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float tmax, float &t, float &u, float &v) {
-	V3 e1 = xsub3(v1, v0), e2 = xsub3(v2, v0);
+	return triIntersectE(o, d, v0, xsub3(v1, v0), xsub3(v2, v0), tmax, t, u, v);
+}
+// the same test on a triangle stored as (v0, e1, e2)
+KRR_HD bool triIntersectE(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmax, float &t, float &u, float &v) {
 	V3 pv = xcross(d, e2);
 	float det = xdot(e1, pv);
 	if (det == 0.f) return false;
@@ -320,7 +326,7 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
 			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 			float t, u, v;
-			if (triIntersect(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
+			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
 				const int prim = __float_as_int(a.w);
 				const int inst = curInst == bvh.mergedInst ? __float_as_int(b.w) : curInst;
 				if (betterHit(t, inst, prim, best) && accept(inst, prim, u, v)) {

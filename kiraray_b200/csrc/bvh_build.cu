@@ -281,9 +281,11 @@ struct TriWriter {
 	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const {
 		BvhTri t;
 		int a = idx[3 * prim], b = idx[3 * prim + 1], c = idx[3 * prim + 2];
-		t.v0 = make_float4(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], __int_as_float((int) prim));
-		t.v1 = make_float4(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2], 0.f);
-		t.v2 = make_float4(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2], 0.f);
+		const V3 v0 = mk3(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]);
+		const V3 e1 = xsub3(mk3(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]), v0), e2 = xsub3(mk3(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2]), v0);
+		t.v0 = make_float4(v0.x, v0.y, v0.z, __int_as_float((int) prim));
+		t.e1 = make_float4(e1.x, e1.y, e1.z, 0.f);
+		t.e2 = make_float4(e2.x, e2.y, e2.z, 0.f);
 		tris[slot] = t;
 	}
 };
@@ -300,9 +302,11 @@ struct MergedTriWriter { // triangles of the merged BLAS carry (primitive, insta
 		const int32_t *idx = indices + 3 * ((size_t) ms.idxOff + pr.y);
 		int a = idx[0], b = idx[1], c = idx[2];
 		BvhTri t;
-		t.v0 = make_float4(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], __int_as_float(pr.y));
-		t.v1 = make_float4(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2], __int_as_float(ms.inst));
-		t.v2 = make_float4(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2], 0.f);
+		const V3 v0 = mk3(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]);
+		const V3 e1 = xsub3(mk3(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]), v0), e2 = xsub3(mk3(pos[3 * c], pos[3 * c + 1], pos[3 * c + 2]), v0);
+		t.v0 = make_float4(v0.x, v0.y, v0.z, __int_as_float(pr.y));
+		t.e1 = make_float4(e1.x, e1.y, e1.z, __int_as_float(ms.inst));
+		t.e2 = make_float4(e2.x, e2.y, e2.z, 0.f);
 		tris[slot] = t;
 	}
 };
