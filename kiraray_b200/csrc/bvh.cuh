@@ -113,8 +113,11 @@ KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 //   leaf     : kLeafFlag | (count-1) << 26 | first triangle                 (bits 31,30 = 01)
 //   instance : kInstFlag | instance id  (TLAS leaves hold ONE instance)      (bits 31,30 = 10)
 //   flat BLAS: kFlatFlag | index into BvhDev::flats (only ever a BLAS root)  (bits 31,30 = 11, != empty)
-constexpr int kShortStack  = 12;
-constexpr int kLocalStack  = 116; // 8-wide nodes defer up to 7 siblings per level: 128 entries cover TLAS + BLAS depths of ~18 levels
+#ifndef KRR_SHORT_STACK
+#define KRR_SHORT_STACK 12
+#endif
+constexpr int kShortStack  = KRR_SHORT_STACK;
+constexpr int kLocalStack  = 128 - KRR_SHORT_STACK; // 8-wide nodes defer up to 7 siblings per level: 128 entries cover TLAS + BLAS depths of ~18 levels
 constexpr int kStackSize   = kShortStack + kLocalStack;
 constexpr int kTraceBlock  = 128;
 constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kFlatFlag = 0xc0000000u, kEmptyEntry = 0xffffffffu;

@@ -452,7 +452,10 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 			if (work.exhausted) break;
 			continue; // private range ran dry mid-refill: claim again
 		}
-		const bool fin = tr.trip<true>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
+		#ifndef KRR_CLOSEST_VOTE
+#define KRR_CLOSEST_VOTE true
+#endif
+		const bool fin = tr.trip<KRR_CLOSEST_VOTE>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
 			if (!(wf.instFlags[inst] & 2)) return true;
 			return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
 		});
