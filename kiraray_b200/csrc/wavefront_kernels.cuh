@@ -271,7 +271,10 @@ __device__ __noinline__ bool alphaKilled(const Wavefront &wf, int inst, int prim
 // traversals; 16 when the whole scene is one flat triangle list, where every ray takes the same single trip
 // (measured: +2 % on the Cornell box, -4.5 % on the instanced scene with 16)
 constexpr int kRefill = 8, kRefillFlat = 16;
-constexpr int kClaim  = 64; // rays a warp claims from the queue per atomicAdd once its static share is done
+#ifndef KRR_CLAIM
+#define KRR_CLAIM 32 // measured 8 / 16 / 32 / 64: 32 is best on all three scene kinds (finer balance at the end of a queue)
+#endif
+constexpr int kClaim  = KRR_CLAIM; // rays a warp claims from the queue per atomicAdd once its static share is done
 
 // Work distribution of the persistent trace kernels.  Warp w starts with the static slice
 // [32 w, 32 w + 32) of the queue -- no atomic, and warps beyond a short queue exit at once -- and
