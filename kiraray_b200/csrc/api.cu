@@ -90,6 +90,7 @@ struct KrrWfpt {
 	int flatBlasMax = 48;	 // "flat_blas_max": a BLAS with at most this many triangles is a flat list (takes effect at set_scene)
 	bool pdl = false;		 // "pdl": programmatic dependent launch between the stage kernels (measured: -1.6 % on the bench workload, so off)
 	bool usePdl() const { return pdl && !profile; }
+	bool implicitDepth0 = true; // "implicit_depth0": depth-0 ray items store origin + direction only
 	bool fuseStages = true;	 // "fuse_stages": 2 launches per depth (hit/miss in the scatter launch, shadow + next closest in one trace launch)
 	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
@@ -173,6 +174,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
 		h->fuseStages	= j.value("fuse_stages", h->fuseStages);
+		h->implicitDepth0 = j.value("implicit_depth0", h->implicitDepth0);
 		h->pdl			= j.value("pdl", h->pdl);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
@@ -244,6 +246,7 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 		const BvhDev bd = h->bvh.device();
 		wf.p.refill = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? kRefillFlat : kRefill;
 	}
+	wf.p.implicitDepth0 = h->implicitDepth0 && !(h->enableMedium && h->sceneHasMedia) && h->capSample < 0;
 	wf.cam	 = h->cam;
 	wf.scene = h->scene;
 	wf.bvh	 = h->bvh.device();

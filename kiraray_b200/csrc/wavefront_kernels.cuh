@@ -93,6 +93,12 @@ struct Params {
 	uint64_t rngInc; // PCG increment of this frame
 	uint32_t sampleIndex;
 	int32_t refill; // kRefill or kRefillFlat
+	// The camera kernel only writes origin and direction: every other field of a depth-0 ray item is a
+	// constant (thp = pu = pl = 1, ctx = 0, depth 0) or the slot itself (pixel = slot: the queue is dense), so
+	// the stages of loop depth 0 substitute them instead of reading 80 B per ray that were never worth
+	// writing (-166 MB of stores per 1080p sample).  Off with participating media (the medium stage updates
+	// thp / pu / pl in place) and while a debug capture is armed.
+	int32_t implicitDepth0;
 };
 
 struct KrrCameraDev {
@@ -218,11 +224,13 @@ __global__ void k_generate_camera_rays(const __grid_constant__ Wavefront wf) {
 		// queue is dense and the writes are coalesced without any atomic)
 		stcs4(q.o_time + i, make_float4(o.x, o.y, o.z, time));
 		stcs4(q.d_medium + i, make_float4(d.x, d.y, d.z, __int_as_float(wf.cam.medium)));
-		stcs4(q.thp + i, sp(1));
-		stcs4(q.pu + i, sp(1));
-		stcs4(q.pl + i, sp(1));
-		stcs4(q.ctxP_pix + i, make_float4(0, 0, 0, __int_as_float(i)));
-		stcs4(q.ctxN_dep + i, make_float4(0, 0, 0, __int_as_float(0)));
+		if (!wf.p.implicitDepth0) {
+			stcs4(q.thp + i, sp(1));
+			stcs4(q.pu + i, sp(1));
+			stcs4(q.pl + i, sp(1));
+			stcs4(q.ctxP_pix + i, make_float4(0, 0, 0, __int_as_float(i)));
+			stcs4(q.ctxN_dep + i, make_float4(0, 0, 0, __int_as_float(0)));
+		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) wf.counters[0].nRay = wf.p.pixelCount;
 }
@@ -322,7 +330,8 @@ static __device__ __noinline__ void movingXf(const SceneDev &sc, int node, float
 
 // null-material hit: re-queue the ray behind the surface at the same item depth (device.cu:54-58)
 template <bool MOTION = true>
-__device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4) {
+__device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4,
+												bool implicit = false) {
 	const InstRec &in	= wf.scene.instances[h.inst];
 	const MeshRec &mesh = wf.scene.meshes[in.mesh];
 	const int32_t *idx	= wf.scene.indices + 3 * ((size_t) mesh.idxOff + h.prim);
@@ -350,11 +359,11 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	if (wf.p.enableMedium && mesh.mediumIn != mesh.mediumOut) // Interaction::getMedium(dir), raytracing.h:162-166
 		d4.w = __int_as_float(dot(d, n) > 0 ? mesh.mediumOut : mesh.mediumIn);
 	stcs4(nq.d_medium + s, d4);
-	stcs4(nq.thp + s, ldcs4(q.thp + i));
-	stcs4(nq.pu + s, ldcs4(q.pu + i));
-	stcs4(nq.pl + s, ldcs4(q.pl + i));
-	stcs4(nq.ctxP_pix + s, ldcs4(q.ctxP_pix + i));
-	stcs4(nq.ctxN_dep + s, ldcs4(q.ctxN_dep + i));
+	stcs4(nq.thp + s, implicit ? sp(1) : ldcs4(q.thp + i));
+	stcs4(nq.pu + s, implicit ? sp(1) : ldcs4(q.pu + i));
+	stcs4(nq.pl + s, implicit ? sp(1) : ldcs4(q.pl + i));
+	stcs4(nq.ctxP_pix + s, implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldcs4(q.ctxP_pix + i));
+	stcs4(nq.ctxN_dep + s, implicit ? make_float4(0, 0, 0, __int_as_float(0)) : ldcs4(q.ctxN_dep + i));
 }
 
 // block / nBlocks: this CTA's index among the CTAs that run the closest stage (the fused trace kernel
@@ -367,6 +376,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	const int n			= dc->nRay;
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
+	const bool implicit = wf.p.implicitDepth0 && depth == 0; // depth-0 items: only origin / direction are stored
 	Traverser<false, MOTION> tr;
 	LocalStack<false> ls;
 	int ray	  = -1;	   // queue slot this lane holds, -1 = idle
@@ -435,7 +445,8 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 				if (qid == 0) wf.missIdx[s] = i;
 				else if (qid <= MAT_COUNT) wf.scatterIdx[qid - 1][s] = i;
 				else if (qid == MAT_COUNT + 1)
-					requeueThroughNull<MOTION>(wf, q, nq, i, s, h, make_float4(tr.o.x, tr.o.y, tr.o.z, tr.time), make_float4(tr.d.x, tr.d.y, tr.d.z, __int_as_float(medium)));
+					requeueThroughNull<MOTION>(wf, q, nq, i, s, h, make_float4(tr.o.x, tr.o.y, tr.o.z, tr.time), make_float4(tr.d.x, tr.d.y, tr.d.z, __int_as_float(medium)),
+											   implicit);
 				else wf.mediumSampleIdx[s] = i;
 			}
 		}
@@ -445,7 +456,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 			if (r >= 0) {
 				ray = r;
 				const float4 o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
-				pix	   = __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
+				pix	   = implicit ? r : __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
 				medium = __float_as_int(d4.w);
 				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
 			}
@@ -623,6 +634,7 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 	DepthCounters *dc = wf.counters + depth;
 	const int stride  = gridDim.x * blockDim.x;
 	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	const bool implicit = wf.p.implicitDepth0 && depth == 0;
 	const int nHit = dc->nHitLight;
 	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nHit; k += stride) {
 		int i	  = wf.hitLightIdx[k];
@@ -630,7 +642,7 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 		float4 d4 = ldg4(q.d_medium + i);
 		SurfaceGeom g;
 		rebuildGeometry<MOTION>(wf, hit, mk3(d4), ldg4(q.o_time + i).w, g);
-		float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
+		float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldg4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldg4(q.ctxN_dep + i);
 		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
 		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
 		// normal map changes intr.n before the light is evaluated (the CH program prepares the full
@@ -643,10 +655,10 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
 		const LightRec lr	  = wf.scene.lights[g.light];
 		const TriLightRec &tl = wf.scene.triLights[lr.index];
-		Spec thp = ldg4(q.thp + i), pu = ldg4(q.pu + i);
+		Spec thp = implicit ? sp(1) : ldg4(q.thp + i), pu = implicit ? sp(1) : ldg4(q.pu + i);
 		Spec Le	 = areaLightL(tl, g.n, g.wo, wl, wf.scene.cs) * thp;
 		if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
-			Spec pl		   = ldg4(q.pl + i);
+			Spec pl		   = ldg4(q.pl + i); // (never a depth-0 item)
 			float lightPdf = areaLightPdfLi(tl, wf.scene.instances[tl.inst], g.p, g.n, mk3(cp)) * lightSelPdf;
 			Le = Le / mean(pl * lightPdf + pu);
 		} else Le = Le / mean(pu);
@@ -657,11 +669,11 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nMiss; k += stride) {
 		int i	  = wf.missIdx[k];
 		float4 d4 = ldg4(q.d_medium + i);
-		float4 cp = ldg4(q.ctxP_pix + i), cn = ldg4(q.ctxN_dep + i);
+		float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldg4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldg4(q.ctxN_dep + i);
 		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
 		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
 		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
-		Spec thp = ldg4(q.thp + i), pu = ldg4(q.pu + i), pl = ldg4(q.pl + i);
+		Spec thp = implicit ? sp(1) : ldg4(q.thp + i), pu = implicit ? sp(1) : ldg4(q.pu + i), pl = implicit ? sp(1) : ldg4(q.pl + i);
 		Spec L = sp(0);
 		for (int li = 0; li < wf.scene.nInfinite; li++) {
 			const AnalyticLightRec &light = wf.scene.analytic[wf.scene.infiniteLights[li]];
@@ -712,6 +724,7 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 	const int stride  = gridDim.x * blockDim.x;
 	const int nIter	  = (n + stride - 1) / stride;
 	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	const bool implicit = wf.p.implicitDepth0 && depth == 0;
 	for (int it = 0; it < nIter; it++) {
 		int k		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
 		bool active = k < n;
@@ -732,14 +745,14 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 			int i	  = wf.scatterIdx[MT][k];
 			int4 hit  = wf.hits[i];
 			float4 o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
-			float4 cp = ldcs4(q.ctxP_pix + i), cn = ldcs4(q.ctxN_dep + i);
+			float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldcs4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldcs4(q.ctxN_dep + i);
 			pix = __float_as_int(cp.w), itemDepth = __float_as_int(cn.w) & 0xff;
 			time = o4.w, medium = __float_as_int(d4.w);
 			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
 			// Russian roulette at every depth, including 0 (integrator.cpp:118-119)
 			bool alive = wf.p.rrInTrace ? true : rng.get1D() < wf.p.probRR;
 			if (alive) {
-				Spec thp = ldcs4(q.thp + i) / wf.p.probRR, pu = ldcs4(q.pu + i);
+				Spec thp = (implicit ? sp(1) : ldcs4(q.thp + i)) / wf.p.probRR, pu = implicit ? sp(1) : ldcs4(q.pu + i);
 				SurfaceGeom g;
 				KRR_PHASE();
 				rebuildGeometry<MOTION>(wf, hit, mk3(d4), time, g);

@@ -287,3 +287,22 @@ def test_full_size_properties_1080p(cbox_app):
     assert s["closest_rays"] == sum(c) and s["shadow_rays"] == sum(s["shadow_by_depth"])
     assert s["scatter_items"] + s["miss_items"] >= s["closest_rays"] - c[10] - 8, "every ray is a miss or reaches the scatter stage"
     assert np.isfinite(films[0]).all() and np.all(films[0][..., 3] == 1)
+
+
+def test_implicit_depth0_items_give_the_identical_film(cbox_app):
+    """implicit_depth0 (default): the camera kernel stores origin and direction only; the constants of a
+    depth-0 item (thp = pu = pl = 1, ctx = 0, pixel = slot) are substituted by the stages that read them."""
+    w = h = 64
+    app = cbox_app(w, h, spp=2, max_depth=5)
+    cam = app.camera()
+    out = []
+    for flag in (False, True):
+        for fuse in (False, True):
+            gpu = krr.Wfpt(params=dict(app.wfpt_params(), implicit_depth0=flag, fuse_stages=fuse))
+            gpu.set_scene(app.scene_desc())
+            gpu.resize(w, h)
+            gpu.begin_frame(5, cam)
+            out.append((gpu.render_to_host().copy(), gpu.stats()))
+    for film, st in out[1:]:
+        assert np.array_equal(film.view(np.uint32), out[0][0].view(np.uint32))
+        assert st["closest_by_depth"] == out[0][1]["closest_by_depth"] and st["shadow_by_depth"] == out[0][1]["shadow_by_depth"]
