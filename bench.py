@@ -189,7 +189,8 @@ def main():
     part = make_partition(rank, world, H, args.partition)
     app = make_app(args.spp)
     cam = app.camera()
-    gpu = krr.Wfpt(params=dict(app.wfpt_params(), **(json.loads(args.params) if args.params else {})))
+    # debug_taps off: the C ABI's default (the ctypes test binding turns the parity taps on by default)
+    gpu = krr.Wfpt(params=dict(app.wfpt_params(), debug_taps=False, **(json.loads(args.params) if args.params else {})))
     gpu.set_scene(app.scene_desc())
     gpu.resize(W, H)
     if part.tiles > 1:

@@ -372,7 +372,9 @@ class Wfpt:
         self.owned = handle is None
         self.h = P(handle) if handle is not None else P()
         if handle is None:
-            text = json.dumps(params or {}).encode()
+            # the parity taps (first_hits / pixel_state) need the pass to record them: the test binding asks
+            # for that unless told otherwise; the C ABI default (and bench.py) is off
+            text = json.dumps(dict({"debug_taps": True}, **(params or {}))).encode()
             self._ck(self.lib.krr_wfpt_create(text, C.byref(self.h)), "create")
             self._ck(self.lib.krr_wfpt_set_color_space(self.h, C.byref(color_space())), "set_color_space")
         self.size = None

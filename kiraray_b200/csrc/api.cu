@@ -136,7 +136,10 @@ struct KrrWfpt {
 	Buf<DepthCounters> counters;
 	Buf<StatTotals> totals;
 	KrrCameraDev cam{};
-	bool debugState = true; // keep camera samples / first hits (16+20 B per pixel; negligible traffic)
+	// "debug_taps": keep the camera samples and depth-0 hits of every pixel for the parity taps
+	// (krr_wfpt_debug_first_hits / _pixel_state): 36 B per pixel per sample of extra stores.  Off by default;
+	// the test binding switches it on.  Takes effect at the next resize / set_scene.
+	bool debugState = false;
 	// debug capture
 	int capSample = -1, capDepth = -1;
 	Buf<int4> capItems[6];
@@ -175,6 +178,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
 		h->fuseStages	= j.value("fuse_stages", h->fuseStages);
 		h->implicitDepth0 = j.value("implicit_depth0", h->implicitDepth0);
+		h->debugState	= j.value("debug_taps", h->debugState);
 		h->pdl			= j.value("pdl", h->pdl);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
@@ -988,7 +992,7 @@ extern "C" int krr_wfpt_get_launch_times(KrrWfpt *h, int32_t *stage, float *ms, 
 }
 
 extern "C" int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *inst, int32_t *prim) {
-	if (!h || !h->firstHits.p) return fail(KRR_E_STATE, "no state");
+	if (!h || !h->firstHits.p) return fail(KRR_E_STATE, "no depth-0 hits recorded: create the pass with \"debug_taps\": true");
 	CUDA_OK(cudaDeviceSynchronize());
 	std::vector<int4> tmp(h->pixelCount());
 	CUDA_OK(cudaMemcpy(tmp.data(), h->firstHits.p, tmp.size() * 16, cudaMemcpyDeviceToHost));
@@ -1017,7 +1021,10 @@ extern "C" int krr_wfpt_debug_pixel_state(KrrWfpt *h, uint64_t *sampler, float *
 			memcpy(lambda + 4 * i, w.lambda, 16);
 		}
 	}
-	if (cameraSample && h->cameraSample.p) CUDA_OK(cudaMemcpy(cameraSample, h->cameraSample.p, n * 20, cudaMemcpyDeviceToHost));
+	if (cameraSample) {
+		if (!h->cameraSample.p) return fail(KRR_E_STATE, "no camera samples recorded: create the pass with \"debug_taps\": true");
+		CUDA_OK(cudaMemcpy(cameraSample, h->cameraSample.p, n * 20, cudaMemcpyDeviceToHost));
+	}
 	return KRR_OK;
 }
 
