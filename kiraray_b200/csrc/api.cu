@@ -80,7 +80,28 @@ Xf xfInverse(const Xf &t) {
 
 } // namespace
 
-struct KrrWfpt {
+// Queues, pixel state and counters of one BAND of the frame.  A frame is rendered as `bands` interleaved
+// row sets (band b owns rows rowBegin + b, rowBegin + b + bands, ...), each with its own queues on its own
+// stream: pixels are independent (private RNG stream and accumulator), so the film is
+// bit-identical, and the launches of one band fill the SMs that the other band's launch leaves idle
+// while it drains (the persistent CTAs of a stage exit one by one) or walks a short deep-bounce queue
+// (a launch costs 20-35 us however few rays it has).  The parity taps, debug captures and the per-stage
+// event timing run the frame as ONE band (band 0 is always allocated for the whole partition).
+constexpr int kMaxBands = 4;
+struct WaveState {
+	Buf<float4> L, pixel, rayBuf[2][7], shadowBuf[5];
+	Buf<uint64_t> rng;
+	Buf<float> lambda, cameraSample;
+	Buf<int4> hits, firstHits;
+	Buf<int32_t> missIdx, hitLightIdx, scatterIdx[MAT_COUNT], errorFlags, mediumSampleIdx;
+	Buf<float> hitT;
+	Buf<float4> msBuf[4];
+	Buf<int2> msPixDepth, shadowAux;
+	Buf<DepthCounters> counters;
+	Buf<StatTotals> totals;
+};
+
+struct KrrWfpt : WaveState {
 	int device = 0;
 	// params (integrator.h:78-88)
 	int spp = 1, maxDepth = 10;
@@ -124,17 +145,14 @@ struct KrrWfpt {
 	BvhBuilder bvh;
 	bool matTypePresent[MAT_COUNT] = {false, false, false, false, false};
 	bool sceneHasMedia = false;
-	// wavefront state
-	Buf<float4> L, pixel, rayBuf[2][7], shadowBuf[5];
-	Buf<uint64_t> rng;
-	Buf<float> lambda, cameraSample;
-	Buf<int4> hits, firstHits;
-	Buf<int32_t> missIdx, hitLightIdx, scatterIdx[MAT_COUNT], errorFlags, mediumSampleIdx;
-	Buf<float> hitT;
-	Buf<float4> msBuf[4];
-	Buf<int2> msPixDepth, shadowAux;
-	Buf<DepthCounters> counters;
-	Buf<StatTotals> totals;
+	// wavefront state of band 0 (the whole partition when the frame runs as one band): WaveState base
+	WaveState extra[kMaxBands - 1]; // bands 1..: allocated the first time a frame runs with more than one band
+	cudaStream_t bandStream[kMaxBands - 1] = {};
+	cudaEvent_t evFork = nullptr, evJoin[kMaxBands - 1] = {};
+	int bands = 2;		 // "bands": see WaveState
+	int activeBands = 1; // decided by begin_frame
+	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
+	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
 	KrrCameraDev cam{};
 	// "debug_taps": keep the camera samples and depth-0 hits of every pixel for the parity taps
 	// (krr_wfpt_debug_first_hits / _pixel_state): 36 B per pixel per sample of extra stores.  Off by default;
@@ -181,32 +199,57 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->debugState	= j.value("debug_taps", h->debugState);
 		h->pdl			= j.value("pdl", h->pdl);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
+		h->bands		= j.value("bands", h->bands);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
+	if (h->bands < 1 || h->bands > kMaxBands) return fail(KRR_E_INVALID, "bands must be in [1, %d]", kMaxBands);
 	if (!(h->probRR > 0.f && h->probRR <= 1.f)) return fail(KRR_E_INVALID, "rr must be in (0, 1]");
 	return KRR_OK;
 }
 
-int allocState(KrrWfpt *h) {
-	const size_t n = (size_t) h->pixelCount();
+int allocBand(KrrWfpt *h, WaveState &w, size_t n) {
 	int rc = 0;
-	rc |= h->L.alloc(n) | h->pixel.alloc(n) | h->rng.alloc(n) | h->lambda.alloc(n) | h->hits.alloc(n);
-	if (h->debugState) rc |= h->cameraSample.alloc(5 * n) | h->firstHits.alloc(n);
-	for (int q = 0; q < 2; q++) for (int a = 0; a < 7; a++) rc |= h->rayBuf[q][a].alloc(n);
-	for (int a = 0; a < 5; a++) rc |= h->shadowBuf[a].alloc(n);
-	rc |= h->missIdx.alloc(n) | h->hitLightIdx.alloc(n);
-	for (int m = 0; m < MAT_COUNT; m++) rc |= h->scatterIdx[m].alloc(n);
-	if (h->sceneHasMedia || h->scene.hasMotion) rc |= h->shadowAux.alloc(n); // shadow rays carry (medium, time)
+	rc |= w.L.alloc(n) | w.pixel.alloc(n) | w.rng.alloc(n) | w.lambda.alloc(n) | w.hits.alloc(n);
+	if (h->debugState) rc |= w.cameraSample.alloc(5 * n) | w.firstHits.alloc(n);
+	for (int q = 0; q < 2; q++) for (int a = 0; a < 7; a++) rc |= w.rayBuf[q][a].alloc(n);
+	for (int a = 0; a < 5; a++) rc |= w.shadowBuf[a].alloc(n);
+	rc |= w.missIdx.alloc(n) | w.hitLightIdx.alloc(n);
+	for (int m = 0; m < MAT_COUNT; m++) rc |= w.scatterIdx[m].alloc(n);
+	if (h->sceneHasMedia || h->scene.hasMotion) rc |= w.shadowAux.alloc(n); // shadow rays carry (medium, time)
 	if (h->sceneHasMedia) { // media queues (mediumSampleQueue / mediumScatterQueue, integrator.cpp:40-44)
-		rc |= h->mediumSampleIdx.alloc(n) | h->hitT.alloc(n) | h->msPixDepth.alloc(n);
-		for (int a = 0; a < 4; a++) rc |= h->msBuf[a].alloc(n);
+		rc |= w.mediumSampleIdx.alloc(n) | w.hitT.alloc(n) | w.msPixDepth.alloc(n);
+		for (int a = 0; a < 4; a++) rc |= w.msBuf[a].alloc(n);
 	}
-	rc |= h->counters.alloc(kMaxDepthSlots) | h->totals.alloc(1) | h->errorFlags.alloc(4);
+	const bool fresh = !w.counters.p;
+	rc |= w.counters.alloc(kMaxDepthSlots) | w.totals.alloc(1) | w.errorFlags.alloc(4);
 	if (rc) return KRR_E_CUDA;
-	CUDA_OK(cudaMemset(h->counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
-	CUDA_OK(cudaMemset(h->totals.p, 0, sizeof(StatTotals)));
-	CUDA_OK(cudaMemset(h->errorFlags.p, 0, 16));
+	if (fresh) {
+		CUDA_OK(cudaMemset(w.counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
+		CUDA_OK(cudaMemset(w.totals.p, 0, sizeof(StatTotals)));
+		CUDA_OK(cudaMemset(w.errorFlags.p, 0, 16));
+	}
+	return KRR_OK;
+}
+
+// band 0 always covers the whole partition (frames that run as one band, the megakernel)
+int allocState(KrrWfpt *h) {
+	h->activeBands = 1;
+	h->counters.release(); // fresh counters for a new frame size / scene
+	return allocBand(h, *h, (size_t) h->pixelCount());
+}
+
+// bands 1.. of a frame that runs as `nb` bands (no-op when they already have the right size)
+int allocExtraBands(KrrWfpt *h, int nb) {
+	for (int b = 1; b < nb; b++) {
+		int rc = allocBand(h, h->band(b), (size_t) h->bandRows(b, nb) * h->width);
+		if (rc) return rc;
+		if (!h->bandStream[b - 1]) {
+			CUDA_OK(cudaStreamCreateWithFlags(&h->bandStream[b - 1], cudaStreamNonBlocking));
+			CUDA_OK(cudaEventCreateWithFlags(&h->evJoin[b - 1], cudaEventDisableTiming));
+		}
+	}
+	if (!h->evFork) CUDA_OK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
 	return KRR_OK;
 }
 
@@ -235,10 +278,12 @@ SpectrumRec makeSpectrum(const KrrSpectrumDesc &s, std::vector<float> &tables) {
 	return r;
 }
 
-Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
+Wavefront makeWavefront(KrrWfpt *h, int sampleId, int bandId = 0, int nb = 1) {
 	Wavefront wf{};
+	WaveState &w = h->band(bandId);
 	wf.p.width = h->width, wf.p.height = h->height;
-	wf.p.pixelBegin = h->rowBegin * h->width, wf.p.pixelCount = h->pixelCount();
+	wf.p.pixelBegin = h->rowBegin * h->width, wf.p.partPixels = h->pixelCount();
+	wf.p.rowStride = nb, wf.p.rowPhase = bandId, wf.p.pixelCount = h->bandRows(bandId, nb) * h->width;
 	wf.p.spp = h->spp, wf.p.maxDepth = h->maxDepth, wf.p.nee = h->nee;
 	wf.p.enableMedium = h->enableMedium && h->sceneHasMedia; // integrator.cpp:200
 	wf.p.enableClamp = h->enableClamp, wf.p.probRR = h->probRR, wf.p.clampMax = h->clampMax;
@@ -254,24 +299,24 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId) {
 	wf.cam	 = h->cam;
 	wf.scene = h->scene;
 	wf.bvh	 = h->bvh.device();
-	wf.px.L = h->L.p, wf.px.pixel = h->pixel.p, wf.px.rng = h->rng.p, wf.px.lambda = h->lambda.p;
-	wf.px.cameraSample = h->debugState ? h->cameraSample.p : nullptr;
+	wf.px.L = w.L.p, wf.px.pixel = w.pixel.p, wf.px.rng = w.rng.p, wf.px.lambda = w.lambda.p;
+	wf.px.cameraSample = h->debugState ? w.cameraSample.p : nullptr;
 	for (int q = 0; q < 2; q++) {
 		RayQueue &r = wf.rays[q];
-		r.o_time = h->rayBuf[q][0].p, r.d_medium = h->rayBuf[q][1].p, r.thp = h->rayBuf[q][2].p, r.pu = h->rayBuf[q][3].p;
-		r.pl = h->rayBuf[q][4].p, r.ctxP_pix = h->rayBuf[q][5].p, r.ctxN_dep = h->rayBuf[q][6].p;
+		r.o_time = w.rayBuf[q][0].p, r.d_medium = w.rayBuf[q][1].p, r.thp = w.rayBuf[q][2].p, r.pu = w.rayBuf[q][3].p;
+		r.pl = w.rayBuf[q][4].p, r.ctxP_pix = w.rayBuf[q][5].p, r.ctxN_dep = w.rayBuf[q][6].p;
 	}
-	wf.hits = h->hits.p;
-	wf.missIdx = h->missIdx.p, wf.hitLightIdx = h->hitLightIdx.p;
-	for (int m = 0; m < MAT_COUNT; m++) wf.scatterIdx[m] = h->scatterIdx[m].p;
-	wf.shadow.o_tmax = h->shadowBuf[0].p, wf.shadow.d_pix = h->shadowBuf[1].p, wf.shadow.contrib = h->shadowBuf[2].p;
-	wf.shadow.pu = h->shadowBuf[3].p, wf.shadow.pl = h->shadowBuf[4].p, wf.shadow.aux = h->shadowAux.p;
-	wf.hitT = h->hitT.p, wf.mediumSampleIdx = h->mediumSampleIdx.p;
-	wf.mscatter.p_time = h->msBuf[0].p, wf.mscatter.wo_medium = h->msBuf[1].p, wf.mscatter.thp = h->msBuf[2].p, wf.mscatter.pu = h->msBuf[3].p;
-	wf.mscatter.pix_depth = h->msPixDepth.p;
-	wf.counters	  = h->counters.p;
-	wf.firstHits  = h->debugState ? h->firstHits.p : nullptr;
-	wf.errorFlags = h->errorFlags.p;
+	wf.hits = w.hits.p;
+	wf.missIdx = w.missIdx.p, wf.hitLightIdx = w.hitLightIdx.p;
+	for (int m = 0; m < MAT_COUNT; m++) wf.scatterIdx[m] = w.scatterIdx[m].p;
+	wf.shadow.o_tmax = w.shadowBuf[0].p, wf.shadow.d_pix = w.shadowBuf[1].p, wf.shadow.contrib = w.shadowBuf[2].p;
+	wf.shadow.pu = w.shadowBuf[3].p, wf.shadow.pl = w.shadowBuf[4].p, wf.shadow.aux = w.shadowAux.p;
+	wf.hitT = w.hitT.p, wf.mediumSampleIdx = w.mediumSampleIdx.p;
+	wf.mscatter.p_time = w.msBuf[0].p, wf.mscatter.wo_medium = w.msBuf[1].p, wf.mscatter.thp = w.msBuf[2].p, wf.mscatter.pu = w.msBuf[3].p;
+	wf.mscatter.pix_depth = w.msPixDepth.p;
+	wf.counters	  = w.counters.p;
+	wf.firstHits  = h->debugState ? w.firstHits.p : nullptr;
+	wf.errorFlags = w.errorFlags.p;
 	wf.instFlags  = h->instFlags.p;
 	return wf;
 }
@@ -330,6 +375,11 @@ extern "C" int krr_wfpt_create(const char *params_json, KrrWfpt **out) {
 extern "C" void krr_wfpt_destroy(KrrWfpt *h) {
 	if (!h) return;
 	cudaDeviceSynchronize();
+	for (int b = 0; b < kMaxBands - 1; b++) {
+		if (h->bandStream[b]) cudaStreamDestroy(h->bandStream[b]);
+		if (h->evJoin[b]) cudaEventDestroy(h->evJoin[b]);
+	}
+	if (h->evFork) cudaEventDestroy(h->evFork);
 	delete h;
 }
 
@@ -735,12 +785,20 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 			h->motionW0 = w0, h->motionW1 = w1;
 		}
 	}
-	CUDA_OK(cudaMemsetAsync(h->totals.p, 0, sizeof(StatTotals), st));
-	Wavefront wf = makeWavefront(h, 0);
+	// the frame runs as `bands` interleaved row sets unless something needs the frame's state in one piece
+	// (parity taps, debug capture) or serial launches (per-stage event timing)
+	int nb = std::min(h->bands, h->rowEnd - h->rowBegin);
+	if (h->debugState || h->capSample >= 0 || h->profile) nb = 1;
+	if (nb > 1) { int rc = allocExtraBands(h, nb); if (rc) return rc; }
+	h->activeBands = nb;
 	uint32_t seedIndex = (uint32_t) (frameIndex * (uint64_t) h->spp);
 	int grid = gridFor(h, k_begin_frame, 256);
-	k_begin_frame<<<grid, 256, 0, st>>>(wf, seedIndex);
-	h->launches++;
+	for (int b = 0; b < nb; b++) {
+		CUDA_OK(cudaMemsetAsync(h->band(b).totals.p, 0, sizeof(StatTotals), st));
+		Wavefront wf = makeWavefront(h, 0, b, nb);
+		k_begin_frame<<<grid, 256, 0, st>>>(wf, seedIndex);
+		h->launches++;
+	}
 	CUDA_OK(cudaGetLastError());
 	h->frameBegun = true;
 	h->lastStream = st;
@@ -810,8 +868,18 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	if (motion && !gridFusedM) gridFusedM = gridFor(h, k_trace_fused<true>, 128);
 	const bool pdl = h->usePdl();
 	const int nDepthSlots = h->maxDepth + 2;
-	for (int sampleId = 0; sampleId < h->spp; sampleId++) {
-		Wavefront wf = makeWavefront(h, sampleId);
+	// bands: band 0 runs on the caller's stream, bands 1.. on their own streams, forked from and joined to it
+	const int nb = h->activeBands;
+	const cudaStream_t callerStream = st;
+	if (nb > 1) {
+		if (h->capSample >= 0 || h->profile) return fail(KRR_E_STATE, "begin_frame must follow set_profiling / debug_capture");
+		CUDA_OK(cudaEventRecord(h->evFork, callerStream));
+		for (int b = 1; b < nb; b++) CUDA_OK(cudaStreamWaitEvent(h->bandStream[b - 1], h->evFork, 0));
+	}
+	for (int sampleId = 0; sampleId < h->spp; sampleId++)
+	for (int bandId = 0; bandId < nb; bandId++) {
+		st = bandId == 0 ? callerStream : h->bandStream[bandId - 1];
+		Wavefront wf = makeWavefront(h, sampleId, bandId, nb);
 		// [1] primary rays.  Queue counters were cleared by k_fold_counters of the previous sample
 		{ StageTimer t(h, KRR_STAGE_CAMERA, st); launchK(pdl, k_generate_camera_rays, gridCam, 256, st, wf); }
 		h->launches++;
@@ -883,12 +951,20 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			}
 		}
 		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_resolve, gridResolve, 256, st, wf); }
-		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_fold_counters, 1, 128, st, h->counters.p, h->totals.p, nDepthSlots, h->pixelCount()); }
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_fold_counters, 1, 128, st, h->band(bandId).counters.p, h->band(bandId).totals.p, nDepthSlots, wf.p.pixelCount); }
 		h->launches += 2;
 	}
-	Wavefront wf = makeWavefront(h, 0);
-	{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_film, gridResolve, 256, st, wf, (float4 *) film, 1); }
-	h->launches++;
+	for (int bandId = 0; bandId < nb; bandId++) { // each band writes its rows of the film; band 0 also clears the rows outside the partition
+		st = bandId == 0 ? callerStream : h->bandStream[bandId - 1];
+		Wavefront wf = makeWavefront(h, 0, bandId, nb);
+		{ StageTimer t(h, KRR_STAGE_RESOLVE, st); launchK(pdl, k_film, gridResolve, 256, st, wf, (float4 *) film, bandId == 0 ? 1 : 0); }
+		h->launches++;
+		if (bandId > 0) {
+			CUDA_OK(cudaEventRecord(h->evJoin[bandId - 1], st));
+			CUDA_OK(cudaStreamWaitEvent(callerStream, h->evJoin[bandId - 1], 0));
+		}
+	}
+	st = callerStream;
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;
 	return KRR_OK;
@@ -946,6 +1022,16 @@ extern "C" int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out) {
 	CUDA_OK(cudaMemcpy(&t, h->totals.p, sizeof t, cudaMemcpyDeviceToHost));
 	int32_t flags[4];
 	CUDA_OK(cudaMemcpy(flags, h->errorFlags.p, 16, cudaMemcpyDeviceToHost));
+	for (int b = 1; b < h->activeBands; b++) { // bands joined the caller's stream at the end of render
+		StatTotals tb;
+		int32_t fb[4];
+		CUDA_OK(cudaMemcpy(&tb, h->band(b).totals.p, sizeof tb, cudaMemcpyDeviceToHost));
+		CUDA_OK(cudaMemcpy(fb, h->band(b).errorFlags.p, 16, cudaMemcpyDeviceToHost));
+		t.camera += tb.camera, t.closest += tb.closest, t.shadow += tb.shadow, t.scatter += tb.scatter, t.hitLight += tb.hitLight;
+		t.miss += tb.miss, t.mediumSample += tb.mediumSample, t.mediumScatter += tb.mediumScatter;
+		for (int i = 0; i < 64; i++) t.closestByDepth[i] += tb.closestByDepth[i], t.shadowByDepth[i] += tb.shadowByDepth[i];
+		for (int i = 0; i < 4; i++) flags[i] |= fb[i];
+	}
 	if (flags[0]) return fail(KRR_E_CUDA, "BVH traversal stack overflow (scene deeper than %d entries)", kStackSize);
 	out->camera_rays = t.camera, out->closest_rays = t.closest, out->shadow_rays = t.shadow, out->scatter_items = t.scatter;
 	out->hit_light_items = t.hitLight, out->miss_items = t.miss, out->medium_sample_items = t.mediumSample, out->medium_scatter_items = t.mediumScatter;
@@ -1005,6 +1091,7 @@ extern "C" int krr_wfpt_debug_first_hits(KrrWfpt *h, int32_t *inst, int32_t *pri
 
 extern "C" int krr_wfpt_debug_pixel_state(KrrWfpt *h, uint64_t *sampler, float *lambda, float *cameraSample) {
 	if (!h || !h->rng.p) return fail(KRR_E_STATE, "no state");
+	if (h->activeBands > 1) return fail(KRR_E_STATE, "the last frame ran as %d bands: create the pass with \"debug_taps\": true (or \"bands\": 1) to read pixel state", h->activeBands);
 	CUDA_OK(cudaDeviceSynchronize());
 	const size_t n = h->pixelCount();
 	if (sampler) {

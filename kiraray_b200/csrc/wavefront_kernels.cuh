@@ -83,7 +83,10 @@ struct PixelState {
 
 struct Params {
 	int32_t width, height;
-	int32_t pixelBegin, pixelCount; // this handle's pixel range (row partition)
+	int32_t pixelBegin, partPixels; // this handle's pixel range (row partition of the frame)
+	// the band of the partition these queues serve: rows rowPhase, rowPhase + rowStride, ... of the
+	// partition, pixelCount pixels in all, indexed densely (local index i = bandRow * width + x)
+	int32_t rowStride, rowPhase, pixelCount;
 	int32_t spp, maxDepth, nee, enableMedium, enableClamp;
 	// Russian roulette of generateScatterRays (integrator.cpp:118-119) evaluated by the closest stage
 	// when it routes a hit to the scatter queue: it is the NEXT draw of the pixel's stream either way,
@@ -160,6 +163,13 @@ KRR_DEV int warpPushFull(int32_t *counter, bool pred) {
 	return pred ? base + __popc(mask & ((1u << lane) - 1)) : -1;
 }
 
+// local pixel index of a band -> pixel id in the frame (the reference's pixelId: RNG seed, film position)
+KRR_DEV int framePixel(const Params &p, int i) {
+	if (p.rowStride == 1) return p.pixelBegin + i;
+	int row = i / p.width;
+	return p.pixelBegin + (row * p.rowStride + p.rowPhase) * p.width + (i - row * p.width);
+}
+
 KRR_DEV float4 ldg4(const float4 *p) { return __ldg(p); }
 // streaming (read-once / write-once) queue traffic: keep it out of L1
 KRR_DEV float4 ldcs4(const float4 *p) { return __ldcs(p); }
@@ -168,7 +178,7 @@ KRR_DEV void stcs4(float4 *p, float4 v) { __stcs(p, v); }
 // =================================================================================================
 __global__ void k_begin_frame(const __grid_constant__ Wavefront wf, uint32_t seedIndex) {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
-		int pixelId = wf.p.pixelBegin + i;
+		int pixelId = framePixel(wf.p, i);
 		int px = pixelId % wf.p.width, py = pixelId / wf.p.width;
 		wf.px.L[i]	   = make_float4(0, 0, 0, 0);
 		wf.px.pixel[i] = make_float4(0, 0, 0, 0);
@@ -209,7 +219,7 @@ __global__ void k_generate_camera_rays(const __grid_constant__ Wavefront wf) {
 	KRR_PDL_ENTRY();
 	RayQueue q = wf.rays[0];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
-		int pixelId = wf.p.pixelBegin + i;
+		int pixelId = framePixel(wf.p, i);
 		Pcg rng{wf.px.rng[i], wf.p.rngInc};
 		float cs[5];
 #pragma unroll
@@ -1287,9 +1297,14 @@ __global__ void k_film(const __grid_constant__ Wavefront wf, float4 *film, int z
 		int i = pixelId - wf.p.pixelBegin;
 		int x = pixelId % wf.p.width, y = pixelId / wf.p.width;
 		float4 *dst = film + (size_t) (wf.p.height - 1 - y) * wf.p.width + x;
-		if (i < 0 || i >= wf.p.pixelCount) {
+		if (i < 0 || i >= wf.p.partPixels) { // outside this handle's partition
 			if (zeroOutside) *dst = make_float4(0, 0, 0, 0);
 			continue;
+		}
+		if (wf.p.rowStride > 1) { // rows of the partition that belong to another band are that band's to write
+			int row = i / wf.p.width;
+			if (row % wf.p.rowStride != wf.p.rowPhase) continue;
+			i = (row / wf.p.rowStride) * wf.p.width + x;
 		}
 		float4 p  = wf.px.pixel[i];
 		float spp = (float) wf.p.spp;
@@ -1347,7 +1362,7 @@ __global__ void k_capture(const __grid_constant__ Wavefront wf, int depth, int q
 		int4 r = make_int4(0, 0, 0, -1);
 		auto fromRay = [&](const RayQueue &rq, int i) {
 			int packed = __float_as_int(rq.ctxN_dep[i].w);
-			r.x = wf.p.pixelBegin + __float_as_int(rq.ctxP_pix[i].w), r.y = packed & 0xff, r.z = packed >> 8;
+			r.x = framePixel(wf.p, __float_as_int(rq.ctxP_pix[i].w)), r.y = packed & 0xff, r.z = packed >> 8;
 		};
 		if (queue == 0) fromRay(q, k);
 		else if (queue == 5) fromRay(nq, k);
@@ -1365,14 +1380,14 @@ __global__ void k_capture(const __grid_constant__ Wavefront wf, int depth, int q
 			// ScatterRayWorkItem carries the prepared interaction: report ITS BSDF type (shared.h:46-73)
 			SurfaceGeom g;
 			rebuildGeometry(wf, wf.hits[i], mk3(q.d_medium[i]), q.o_time[i].w, g);
-			Wavelengths wl = expandWavelengths(wf.px.lambda[r.x - wf.p.pixelBegin]);
+			Wavelengths wl = expandWavelengths(wf.px.lambda[__float_as_int(q.ctxP_pix[i].w)]);
 			ShadingData sd;
 			bool term;
 			evalMaterial(wf, g, wl, sd, term);
 			r.z = getBsdfType(sd);
 			r.w = mt;
 		} else if (queue == 4) {
-			r.x = wf.p.pixelBegin + __float_as_int(wf.shadow.d_pix[k].w), r.y = 0, r.z = 0;
+			r.x = framePixel(wf.p, __float_as_int(wf.shadow.d_pix[k].w)), r.y = 0, r.z = 0;
 		}
 		out[k] = r;
 	}
