@@ -149,7 +149,7 @@ struct KrrWfpt : WaveState {
 	WaveState extra[kMaxBands - 1]; // bands 1..: allocated the first time a frame runs with more than one band
 	cudaStream_t bandStream[kMaxBands - 1] = {};
 	cudaEvent_t evFork = nullptr, evJoin[kMaxBands - 1] = {};
-	int bands = 2;		 // "bands": see WaveState
+	int bands = 0;		 // "bands": see WaveState; 0 = automatic (2 for a scene that is one flat triangle list, else 1)
 	int activeBands = 1; // decided by begin_frame
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
 	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
@@ -203,7 +203,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
-	if (h->bands < 1 || h->bands > kMaxBands) return fail(KRR_E_INVALID, "bands must be in [1, %d]", kMaxBands);
+	if (h->bands < 0 || h->bands > kMaxBands) return fail(KRR_E_INVALID, "bands must be in [0, %d]", kMaxBands);
 	if (!(h->probRR > 0.f && h->probRR <= 1.f)) return fail(KRR_E_INVALID, "rr must be in (0, 1]");
 	return KRR_OK;
 }
@@ -787,7 +787,15 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 	}
 	// the frame runs as `bands` interleaved row sets unless something needs the frame's state in one piece
 	// (parity taps, debug capture) or serial launches (per-stage event timing)
-	int nb = std::min(h->bands, h->rowEnd - h->rowBegin);
+	int nb = h->bands;
+	if (nb == 0) {
+		// automatic: the short, latency-bound launches of a flat-list scene (Cornell box: +11 %, with the grid
+		// medium +7 %) gain from a second band; the long traversal launches of a tree scene lose to it (20 M
+		// triangles -5 %, 10 000 moving instances -11 %: two resident kernels share L1 and the stack space)
+		const BvhDev bd = h->bvh.device();
+		nb = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? 2 : 1;
+	}
+	nb = std::min(nb, h->rowEnd - h->rowBegin);
 	if (h->debugState || h->capSample >= 0 || h->profile) nb = 1;
 	if (nb > 1) { int rc = allocExtraBands(h, nb); if (rc) return rc; }
 	h->activeBands = nb;
@@ -866,6 +874,14 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	static int gridFused = 0, gridFusedM = 0;
 	if (!gridFused) gridFused = gridFor(h, k_trace_fused<false>, 128);
 	if (motion && !gridFusedM) gridFusedM = gridFor(h, k_trace_fused<true>, 128);
+	// a scene that is one flat triangle list runs the kTraceFlat instantiations (branch-free triangle pairs)
+	static int gridTraceF = 0, gridFusedF = 0;
+	bool flatScene = false;
+	{
+		const BvhDev bd = h->bvh.device();
+		flatScene = !motion && bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot);
+	}
+	if (flatScene && !gridTraceF) gridTraceF = gridFor(h, k_trace_closest<kTraceFlat>, 128), gridFusedF = gridFor(h, k_trace_fused<kTraceFlat>, 128);
 	const bool pdl = h->usePdl();
 	const int nDepthSlots = h->maxDepth + 2;
 	// bands: band 0 runs on the caller's stream, bands 1.. on their own streams, forked from and joined to it
@@ -906,6 +922,7 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		auto launchClosest = [&](int depth) {
 			StageTimer t(h, KRR_STAGE_CLOSEST, st);
 			if (motion) launchK(pdl, k_trace_closest<true>, gridTraceM, 128, st, wf, depth);
+			else if (flatScene) launchK(pdl, k_trace_closest<kTraceFlat>, gridTraceF, 128, st, wf, depth);
 			else launchK(pdl, k_trace_closest<false>, gridTrace, 128, st, wf, depth);
 			h->launches++;
 		};
@@ -915,6 +932,7 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 				launchAllScatter(depth, 1);
 				StageTimer t(h, KRR_STAGE_TRACE, st);
 				if (motion) launchK(pdl, k_trace_fused<true>, gridFusedM, 128, st, wf, depth);
+				else if (flatScene) launchK(pdl, k_trace_fused<kTraceFlat>, gridFusedF, 128, st, wf, depth);
 				else launchK(pdl, k_trace_fused<false>, gridFused, 128, st, wf, depth);
 				h->launches++;
 			}

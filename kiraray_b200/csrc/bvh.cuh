@@ -76,11 +76,32 @@ KRR_HD bool triIntersect(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float tmax, float &t, 
 	return triIntersectE(o, d, v0, xsub3(v1, v0), xsub3(v2, v0), tmax, t, u, v);
 }
 // the same test on a triangle stored as (v0, e1, e2)
+#ifndef KRR_TRI_RCP
+#define KRR_TRI_RCP 1
+#endif
+#ifndef KRR_LEAF_PAIR
+#define KRR_LEAF_PAIR 1
+#endif
+#ifndef KRR_LEAF_WIDTH
+#define KRR_LEAF_WIDTH 2
+#endif
+#ifndef KRR_LEAF_PAIR_TREE
+#define KRR_LEAF_PAIR_TREE 0
+#endif
+// 1 / det, correctly rounded.  On the device __frcp_rn: IEEE round-to-nearest of the reciprocal, i.e. the
+// same float as __fdiv_rn(1.f, det) for every input, in about half the instructions
+KRR_HD float triRcp(float det) {
+#if defined(__CUDA_ARCH__) && KRR_TRI_RCP
+	return __frcp_rn(det);
+#else
+	return xdiv(1.f, det);
+#endif
+}
 KRR_HD bool triIntersectE(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmax, float &t, float &u, float &v) {
 	V3 pv = xcross(d, e2);
 	float det = xdot(e1, pv);
 	if (det == 0.f) return false;
-	float inv = xdiv(1.f, det);
+	float inv = triRcp(det);
 	V3 tv = xsub3(o, v0);
 	u = xmul(xdot(tv, pv), inv);
 	if (!(u >= 0.f && u <= 1.f)) return false;
@@ -90,6 +111,21 @@ KRR_HD bool triIntersectE(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmax, float &t,
 	t = xmul(xdot(e2, qv), inv);
 	return t > 0.f && t < tmax;
 }
+#ifdef __CUDACC__
+// triIntersectE without early exits: every operation and rounding of the spec above, the three range tests
+// combined at the end (a zero determinant makes inv infinite; `det != 0` rejects whatever that produces)
+KRR_DEV bool triTestNoBranch(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmax, float &t, float &u, float &v) {
+	V3 pv = xcross(d, e2);
+	float det = xdot(e1, pv);
+	float inv = triRcp(det);
+	V3 tv = xsub3(o, v0);
+	u = xmul(xdot(tv, pv), inv);
+	V3 qv = xcross(tv, e1);
+	v = xmul(xdot(d, qv), inv);
+	t = xmul(xdot(e2, qv), inv);
+	return (det != 0.f) & (u >= 0.f) & (u <= 1.f) & (v >= 0.f) & (xadd(u, v) <= 1.f) & (t > 0.f) & (t < tmax);
+}
+#endif
 KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 	if (h.inst < 0) return true;
 	if (t != h.t) return t < h.t;
@@ -146,7 +182,8 @@ static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float
 }
 
 // MOTION = false compiles the SRT-chain path out (static scenes keep their register budget)
-template <bool ANY, bool MOTION = true> struct Traverser {
+// PAIR: the scene is one flat triangle list and leaf() walks it in branch-free pairs (see leaf())
+template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	// ray
 	V3 o, d;	  // world space
 	V3 ro, rd;	  // current space (world in the TLAS, object space inside a BLAS)
@@ -340,7 +377,38 @@ template <bool ANY, bool MOTION = true> struct Traverser {
 			first = (uint32_t) fr.x, cnt = (uint32_t) fr.y;
 		}
 		cur = kEmptyEntry;
-		for (uint32_t k = 0; k < cnt; k++) {
+		uint32_t k = 0;
+#if KRR_LEAF_PAIR
+		if constexpr (PAIR || KRR_LEAF_PAIR_TREE)
+		// KRR_LEAF_WIDTH triangles per trip, evaluated without branches (triTestNoBranch: the same operations
+		// and roundings as triIntersectE, combined as predicates).  The early exits of triIntersectE save the
+		// WARP little (32 rays per triangle: some lane usually goes on), and their branches serialise the
+		// dependent multiply-add chains that independent triangles interleave.
+		// Only in the kernels instantiated for flat-list scenes: in a tree leaf the lanes hold different
+		// triangles, and the mere presence of this loop cost the tree kernels registers (config 5: -10 %).
+		for (; k + KRR_LEAF_WIDTH <= cnt; k += KRR_LEAF_WIDTH) {
+			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
+			float4 a[KRR_LEAF_WIDTH], b[KRR_LEAF_WIDTH], c[KRR_LEAF_WIDTH];
+			float t[KRR_LEAF_WIDTH], u[KRR_LEAF_WIDTH], v[KRR_LEAF_WIDTH];
+			bool hit[KRR_LEAF_WIDTH];
+#pragma unroll
+			for (int j = 0; j < KRR_LEAF_WIDTH; j++) a[j] = __ldg(tp + 3 * j), b[j] = __ldg(tp + 3 * j + 1), c[j] = __ldg(tp + 3 * j + 2);
+#pragma unroll
+			for (int j = 0; j < KRR_LEAF_WIDTH; j++) hit[j] = triTestNoBranch(ro, rd, mk3(a[j]), mk3(b[j]), mk3(c[j]), tmax, t[j], u[j], v[j]);
+#pragma unroll
+			for (int j = 0; j < KRR_LEAF_WIDTH; j++) {
+				if (hit[j]) {
+					const int prim = __float_as_int(a[j].w);
+					const int inst = curInst == bvh.mergedInst ? __float_as_int(b[j].w) : curInst;
+					if (betterHit(t[j], inst, prim, best) && accept(inst, prim, u[j], v[j])) {
+						best.inst = inst, best.prim = prim, best.t = t[j], best.u = u[j], best.v = v[j];
+						if (ANY) return true;
+					}
+				}
+			}
+		}
+#endif
+		for (; k < cnt; k++) {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
 			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 			float t, u, v;

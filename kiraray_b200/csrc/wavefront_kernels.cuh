@@ -378,8 +378,14 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 
 // block / nBlocks: this CTA's index among the CTAs that run the closest stage (the fused trace kernel
 // splits its grid between the shadow rays of one depth and the closest rays of the next)
-template <bool MOTION>
+// MODE (trace kernels): kTraceStatic = static scene, kTraceMotion = instances with motion transforms,
+// kTraceFlat = static scene that is ONE flat triangle list (the leaf trips are branch-free triangle pairs,
+// bvh.cuh Traverser PAIR; a separate instantiation because the pair code costs the tree scenes registers:
+// -10 % on the 10 000-instance scene when it lived in the same kernel)
+constexpr int kTraceStatic = 0, kTraceMotion = 1, kTraceFlat = 2;
+template <int MODE>
 KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int block, int nBlocks) {
+	constexpr bool MOTION = MODE == kTraceMotion;
 	const RayQueue q	= wf.rays[depth & 1];
 	const RayQueue nq	= wf.rays[(depth & 1) ^ 1];
 	DepthCounters *dc	= wf.counters + depth;
@@ -387,7 +393,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
 	const bool implicit = wf.p.implicitDepth0 && depth == 0; // depth-0 items: only origin / direction are stored
-	Traverser<false, MOTION> tr;
+	Traverser<false, MOTION, MODE == kTraceFlat> tr;
 	LocalStack<false> ls;
 	int ray	  = -1;	   // queue slot this lane holds, -1 = idle
 	int pix	  = 0;	   // its pixel (fetched with the ray: the finalisation needs it first)
@@ -487,11 +493,11 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	}
 }
 
-template <bool MOTION>
+template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
-	traceClosestBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
+	traceClosestBody<MODE>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
 // =================================================================================================
@@ -902,13 +908,14 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 // =================================================================================================
 // Shadow stage (device.cu:83-100): any-hit visibility, L += Ld / (pl + pu).mean().  Same persistent
 // warp scheme as the closest stage; the ray terminates at the first accepted hit.
-template <bool MOTION>
+template <int MODE>
 KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int block, int nBlocks) {
+	constexpr bool MOTION = MODE == kTraceMotion;
 	DepthCounters *dc	= wf.counters + depth;
 	const int n			= dc->nShadow;
 	const unsigned FULL = 0xffffffffu;
 	const int lane		= threadIdx.x & 31;
-	Traverser<true, MOTION> tr;
+	Traverser<true, MOTION, MODE == kTraceFlat> tr;
 	LocalStack<true> ls;
 	int ray = -1, pix = 0;
 	bool done = false; // traversal finished, radiance not yet added
@@ -951,11 +958,11 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 	}
 }
 
-template <bool MOTION>
+template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
-	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
+	traceShadowBody<MODE>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
 // Fused trace stage: the shadow rays of `depth` and the closest rays of `depth + 1` were both produced
@@ -966,13 +973,19 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 // one overlaps the head of the other and a launch per depth is saved.  (A static split of the grid
 // between the two queues measured slower than two launches: the cost ratio of the two ray kinds moves
 // with depth.)  Not used with participating media (the transmittance shadow rays draw random numbers).
-template <bool MOTION>
-__global__ void __launch_bounds__(kTraceBlock, 7) k_trace_fused( // 7 CTAs/SM = the occupancy of the two stand-alone kernels (72 registers)
+// 7 CTAs/SM = the occupancy of the two stand-alone kernels (72 registers); the flat-list instantiation runs
+// 6 CTAs/SM (80 registers: its branch-free triangle pairs spill at 72; A/B on the bench workload: 6 CTAs
+// 4158, 7 CTAs 4062, 5 CTAs 4078 Mrays/s)
+#ifndef KRR_FUSED_MINB
+#define KRR_FUSED_MINB 6
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, MODE == kTraceFlat ? KRR_FUSED_MINB : 7) k_trace_fused(
 const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
-	traceClosestBody<MOTION>(wf, depth + 1, sm, blockIdx.x, gridDim.x);
-	traceShadowBody<MOTION>(wf, depth, sm, blockIdx.x, gridDim.x);
+	traceClosestBody<MODE>(wf, depth + 1, sm, blockIdx.x, gridDim.x);
+	traceShadowBody<MODE>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
 // =================================================================================================

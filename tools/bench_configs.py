@@ -2,7 +2,9 @@
 """GPU box: Mrays/s of the BASELINE.json configs other than the headline one (configs 3, 4, 5 -- the
 parity-test scenes at their full sizes), one GPU, device-timed like bench.py.  Prints one JSON line each.
 
-  python tools/bench_configs.py [3] [4] [5] [--scale S]     (--scale < 1 shrinks triangle / instance counts)
+  python tools/bench_configs.py [3] [4] [5] [--scale S] [--params JSON]
+      --scale < 1 shrinks triangle / instance counts; --params adds pass parameters (e.g. '{"bands": 1}')
+The parity taps are off (the C ABI's default), as in bench.py.
 """
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,11 +15,13 @@ import kiraray_b200 as krr
 from kiraray_b200 import scenes
 
 scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0
+extra_params = json.loads(sys.argv[sys.argv.index("--params") + 1]) if "--params" in sys.argv else {}
 args = [a for a in sys.argv[1:] if a.isdigit()]
 which = [int(a) for a in args] or [3, 4, 5]
 
 
 def run(name, desc, cam, w, h, params, frames=3, warm=1, extra=None):
+    params = dict(params, debug_taps=False, **extra_params)
     gpu = krr.Wfpt(params=params)
     t0 = time.time()
     gpu.set_scene(desc)
