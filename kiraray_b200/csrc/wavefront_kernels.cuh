@@ -721,8 +721,11 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 #ifndef KRR_SCATTER_BLOCK
 #define KRR_SCATTER_BLOCK 128
 #endif
+// CTAs per SM: the stage is bound by dependent-issue latency, so warps in flight are worth more than the
+// spills they cost.  Disney instantiation, bench workload (2 bands): 3 CTAs (165 registers) 3921, 4 (128, no
+// spills) 4120-4141, 5 (96) 4126, 6 (80, 548 B of spill stores) 4188, 7 (72) 4172, 8 (64) 4094 Mrays/s
 #ifndef KRR_SCATTER_MINB
-#define KRR_SCATTER_MINB 4
+#define KRR_SCATTER_MINB 6
 #endif
 #ifndef KRR_SCATTER_LOCKSTEP
 #define KRR_SCATTER_LOCKSTEP 1
