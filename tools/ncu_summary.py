@@ -54,7 +54,7 @@ def traffic(out, *reps):
             e["launches"] += 1
             e["bytes"] += tot
     out_d = {k: {"dram_bytes_per_launch": v["bytes"] / v["launches"], "launches_captured": v["launches"], "source": v["source"],
-                 "note": "first launches of the stage (depth 0/1) of the bench workload; ncu replays run cold-cache"} for k, v in res.items()}
+                 "note": "first launches of the stage (depth 0/1) of the bench workload rendered as one band (full-frame launches, as in bench.py's profiling pass); ncu replays run cold-cache"} for k, v in res.items()}
     json.dump(out_d, open(out, "w"), indent=1)
     print(json.dumps(out_d, indent=1))
 
