@@ -129,6 +129,25 @@ def cpu_reference_rate(app, spp, rows, threads=0):
                                          "sample": f"rows {r0}..{r0 + rows} of {H} ({rows * W} pixels), {spp} spp, 1 frame"}
 
 
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout when NCCL_DEBUG is set in the environment), so everything else is sent to stderr and the line is
+    written to the saved descriptor at the end."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -149,7 +168,7 @@ def run_reference(args, rank, world):
             "config": {"workload": WORKLOAD, "width": W, "height": H, "max_depth": MAX_DEPTH, "rr": RR, "nee": True, "spp_per_step": args.spp},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -164,6 +183,7 @@ def main():
     ap.add_argument("--params", default="", help="extra pass parameters as JSON (tuning switches, e.g. '{\"pdl\": false}')")
     ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,7 +332,7 @@ def main():
                            "l2": "per-step queue + pixel-state working set (~0.9 GB) exceeds the 126 MB L2", "spp_per_s": spp_s},
                 "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(krr.KrrCameraData), "d2h_bytes_per_step": W * H * 16},
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
