@@ -12,7 +12,10 @@
  * and a negative KRR_E_* code on failure (never throws, never exits -- the reference's
  * Log(Fatal)/CUDA_CHECK -> exit(1), src/core/logger.cpp:100, is replaced by error returns);
  * krr_wfpt_last_error() gives the message.  A handle belongs to the CUDA device that was current
- * at krr_wfpt_create(); it is not thread-safe; all work is enqueued on the caller's stream.
+ * at krr_wfpt_create(); it is not thread-safe; all work is ordered on the caller's stream: a call
+ * returns with everything it enqueued ordered before whatever the caller enqueues next on that stream
+ * (krr_wfpt_render may run part of a frame on an internal stream that is forked from and joined back
+ * to the caller's stream with events inside the call -- pass parameter "bands": 1 to switch that off).
  * Host arrays passed to set_* are copied before the call returns.
  */
 #ifndef KRR_WFPT_H
@@ -235,6 +238,9 @@ int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frame_index, const KrrCameraData *
 /* WavefrontPathTracer::render, integrator.cpp:223-267.  film: device pointer to width*height
  * float4 (RGBA32F, alpha 1), row H-1-y like CudaRenderTarget::write (device/cuda.h:33-45). */
 int krr_wfpt_render(KrrWfpt *h, float *film_rgba_device, void *cuda_stream);
+/* Scheduling parameter of the pass (not a reference parameter; results do not depend on it): "bands" = number
+ * of interleaved row sets a frame is rendered as, each with its own queues on its own stream; 0 (default)
+ * = automatic: 2 for a scene that is one flat triangle list, else 1; at most 4. */
 
 /* Same, with a HOST film buffer: render + device->host copy + stream synchronise. */
 int krr_wfpt_render_to_host(KrrWfpt *h, float *film_rgba_host, void *cuda_stream);
