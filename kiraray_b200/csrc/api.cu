@@ -868,7 +868,7 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	const bool media = h->enableMedium && h->sceneHasMedia;
 	if (media && !gridMSample) {
 		gridMSample = gridFor(h, k_medium_sample, 128), gridMScatter = gridFor(h, k_medium_scatter, 128);
-		gridShadowTr = gridFor(h, k_trace_shadow_tr, kTraceBlock);
+		gridShadowTr = gridFor(h, k_trace_shadow_tr<kTraceMotion>, kTraceBlock);
 	}
 	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
 	static int gridFused = 0, gridFusedM = 0;
@@ -882,6 +882,8 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		flatScene = !motion && bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot);
 	}
 	if (flatScene && !gridTraceF) gridTraceF = gridFor(h, k_trace_closest<kTraceFlat>, 128), gridFusedF = gridFor(h, k_trace_fused<kTraceFlat>, 128);
+	static int gridShadowTrF = 0;
+	if (flatScene && media && !gridShadowTrF) gridShadowTrF = gridFor(h, k_trace_shadow_tr<kTraceFlat>, kTraceBlock);
 	const bool pdl = h->usePdl();
 	const int nDepthSlots = h->maxDepth + 2;
 	// bands: band 0 runs on the caller's stream, bands 1.. on their own streams, forked from and joined to it
@@ -962,7 +964,8 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 			// [2.5] shadow rays
 			if (h->nee) {
 				StageTimer t(h, KRR_STAGE_SHADOW, st);
-				if (media) k_trace_shadow_tr<<<gridShadowTr, kTraceBlock, 0, st>>>(wf, depth);
+				if (media && flatScene) k_trace_shadow_tr<kTraceFlat><<<gridShadowTrF, kTraceBlock, 0, st>>>(wf, depth);
+				else if (media) k_trace_shadow_tr<kTraceMotion><<<gridShadowTr, kTraceBlock, 0, st>>>(wf, depth);
 				else if (motion) launchK(pdl, k_trace_shadow<true>, gridShadowM, 128, st, wf, depth);
 				else launchK(pdl, k_trace_shadow<false>, gridShadow, 128, st, wf, depth);
 				h->launches++;

@@ -1199,6 +1199,9 @@ __global__ void __launch_bounds__(128) k_medium_scatter(const __grid_constant__ 
 
 // ShadowTr: transmittance along the shadow ray by ratio tracking, stepping through null-material
 // interfaces; an opaque surface ends it.  One lane runs the whole chain of one shadow ray.
+// MODE: kTraceMotion = any scene (motion transforms evaluated where an instance has them), kTraceFlat = static
+// scene that is one flat triangle list (branch-free triangle pairs).
+template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_constant__ Wavefront wf, int depth) {
 	__shared__ TraceSmem sm;
 	DepthCounters *dc = wf.counters + depth;
@@ -1220,7 +1223,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_co
 		V3 ip = mk3(0, 0, 0), in_ = ip;
 		int imesh = -1;
 		while (!(fabsf(rd.x) <= 2 * kRayEps && fabsf(rd.y) <= 2 * kRayEps && fabsf(rd.z) <= 2 * kRayEps)) {
-			Traverser<false> tr;
+			Traverser<false, MODE == kTraceMotion, MODE == kTraceFlat> tr;
 			LocalStack<false> ls;
 			tr.begin(wf.bvh, ro, rd, tMax, __int_as_float(aux.y));
 			tr.runToEnd(wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
