@@ -151,6 +151,7 @@ struct KrrWfpt : WaveState {
 	cudaEvent_t evFork = nullptr, evJoin[kMaxBands - 1] = {};
 	int bands = 0;		 // "bands": see WaveState; 0 = automatic (2 for a scene that is one flat triangle list, else 1)
 	int activeBands = 1; // decided by begin_frame
+	int refill = 0;		 // "refill": idle lanes of a trace warp that trigger finalisation + refill; 0 = automatic (kRefill / kRefillFlat)
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
 	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
 	KrrCameraDev cam{};
@@ -200,6 +201,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->pdl			= j.value("pdl", h->pdl);
 		h->flatBlasMax	= j.value("flat_blas_max", h->flatBlasMax);
 		h->bands		= j.value("bands", h->bands);
+		h->refill		= j.value("refill", h->refill);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
@@ -294,6 +296,7 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId, int bandId = 0, int nb = 1) {
 	{
 		const BvhDev bd = h->bvh.device();
 		wf.p.refill = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? kRefillFlat : kRefill;
+		if (h->refill >= 1 && h->refill <= 32) wf.p.refill = h->refill;
 	}
 	wf.p.implicitDepth0 = h->implicitDepth0 && !(h->enableMedium && h->sceneHasMedia) && h->capSample < 0;
 	wf.cam	 = h->cam;

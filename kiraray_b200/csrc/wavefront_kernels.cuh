@@ -982,8 +982,11 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 #ifndef KRR_FUSED_MINB
 #define KRR_FUSED_MINB 6
 #endif
+#ifndef KRR_TREE_MINB
+#define KRR_TREE_MINB 7
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock, MODE == kTraceFlat ? KRR_FUSED_MINB : 7) k_trace_fused(
+__global__ void __launch_bounds__(kTraceBlock, MODE == kTraceFlat ? KRR_FUSED_MINB : KRR_TREE_MINB) k_trace_fused(
 const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;

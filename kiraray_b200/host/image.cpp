@@ -5,7 +5,7 @@
 // stb are third-party code the reference vendors; here the two formats the render passes actually use
 // (AccumulatePass::saveImage writes .exr, ErrorMeasurePass::loadReferenceImage reads .exr / .pfm) are
 // implemented directly from the file-format specifications:
-//   * EXR: single-part scanline files; pixel types HALF / FLOAT / UINT; compression NONE, ZIPS, ZIP
+//   * EXR: single-part scanline files; pixel types HALF / FLOAT / UINT; compression NONE, ZIPS, ZIP (read + write), PIZ (read)
 //     (zlib); any line order; channels by name (R, G, B, A; one channel -> grey).  Tiled, multi-part, deep
 //     and the lossy / wavelet codecs are reported as errors.
 //   * PFM: "PF" / "Pf", either endianness, bottom-up rows.
@@ -170,6 +170,260 @@ bool savePFM(const string &path, const Image &img, string *err) {
 }
 
 // =================================================================================================
+
+// ---- EXR PIZ codec, decoding side (OpenEXR ImfPizCompressor / ImfHuf / ImfWav, restated from the
+// published format): a chunk is  minNonZero u16 | maxNonZero u16 | bitmap[min..max] | length i32 |
+// Huffman stream.  Decoding: canonical Huffman with a run-length symbol -> 16-bit words, inverse 2-D Haar
+// wavelet per channel (per 16-bit half of a 32-bit sample), inverse value look-up table, then the
+// channel-planar block is re-interleaved scanline by scanline.  The reference's sky.exr is PIZ. ----
+namespace piz {
+constexpr int kEncBits = 16, kDecBits = 14, kEncSize = (1 << kEncBits) + 1, kDecSize = 1 << kDecBits, kDecMask = kDecSize - 1;
+constexpr int kShortZeroRun = 59, kLongZeroRun = 63, kShortestLongRun = 2 + kLongZeroRun - kShortZeroRun;
+
+struct Dec {
+	int len = 0;			// short code: its length, symbol in lit
+	int lit = 0;
+	std::vector<int> longs; // long codes that share this 14-bit prefix
+};
+
+struct BitReader {
+	const unsigned char *p, *end;
+	uint64_t c = 0;
+	int lc	   = 0;
+	bool ok	   = true;
+	uint32_t get(int n) {
+		while (lc < n) {
+			if (p >= end) { ok = false; return 0; }
+			c = (c << 8) | *p++, lc += 8;
+		}
+		lc -= n;
+		return (uint32_t) ((c >> lc) & ((1u << n) - 1));
+	}
+};
+
+// code lengths (6 bits each, zero runs packed) -> canonical codes: hcode[i] = length | code << 6
+bool unpackEncTable(const unsigned char *&ptr, const unsigned char *end, int im, int iM, std::vector<uint64_t> &hcode) {
+	hcode.assign(kEncSize, 0);
+	BitReader br{ptr, end};
+	for (; im <= iM; im++) {
+		uint64_t l = hcode[im] = br.get(6);
+		if (!br.ok) return false;
+		if (l == (uint64_t) kLongZeroRun) {
+			int zerun = (int) br.get(8) + kShortestLongRun;
+			if (!br.ok || im + zerun > iM + 1) return false;
+			while (zerun--) hcode[im++] = 0;
+			im--;
+		} else if (l >= (uint64_t) kShortZeroRun) {
+			int zerun = (int) l - kShortZeroRun + 2;
+			if (im + zerun > iM + 1) return false;
+			while (zerun--) hcode[im++] = 0;
+			im--;
+		}
+	}
+	ptr = br.p;
+	uint64_t n[59] = {};
+	for (int i = 0; i < kEncSize; i++) n[hcode[i]]++;
+	uint64_t c = 0;
+	for (int i = 58; i > 0; --i) {
+		uint64_t nc = (c + n[i]) >> 1;
+		n[i] = c, c = nc;
+	}
+	for (int i = 0; i < kEncSize; i++) {
+		uint64_t l = hcode[i];
+		if (l > 0) hcode[i] = l | (n[l]++ << 6);
+	}
+	return true;
+}
+
+bool buildDecTable(const std::vector<uint64_t> &hcode, int im, int iM, std::vector<Dec> &dec) {
+	dec.assign(kDecSize, Dec());
+	for (; im <= iM; im++) {
+		const uint64_t c = hcode[im] >> 6;
+		const int l		 = (int) (hcode[im] & 63);
+		if (c >> l) return false;
+		if (l > kDecBits) {
+			Dec &pl = dec[c >> (l - kDecBits)];
+			if (pl.len) return false;
+			pl.longs.push_back(im);
+		} else if (l) {
+			Dec *pl = &dec[c << (kDecBits - l)];
+			for (uint64_t i = 1ull << (kDecBits - l); i > 0; i--, pl++) {
+				if (pl->len || !pl->longs.empty()) return false;
+				pl->len = l, pl->lit = im;
+			}
+		}
+	}
+	return true;
+}
+
+bool decode(const std::vector<uint64_t> &hcode, const std::vector<Dec> &dec, const unsigned char *in, const unsigned char *fileEnd, int nBits, int rlc,
+			size_t no, uint16_t *out) {
+	uint64_t c = 0;
+	int lc	   = 0;
+	uint16_t *const ob = out, *const oe = out + no;
+	const unsigned char *ie = in + (nBits + 7) / 8;
+	if (ie > fileEnd) return false;
+	auto emit = [&](int po) { // a literal, or the run-length symbol followed by an 8-bit repeat count
+		if (po == rlc) {
+			if (lc < 8) {
+				if (in >= ie) return false;
+				c = (c << 8) | *in++, lc += 8;
+			}
+			lc -= 8;
+			int cs = (int) ((c >> lc) & 0xff);
+			if (out + cs > oe || out == ob) return false;
+			const uint16_t s = out[-1];
+			while (cs-- > 0) *out++ = s;
+		} else if (out < oe) *out++ = (uint16_t) po;
+		else return false;
+		return true;
+	};
+	while (in < ie) {
+		c = (c << 8) | *in++, lc += 8;
+		while (lc >= kDecBits) {
+			const Dec &pl = dec[(c >> (lc - kDecBits)) & kDecMask];
+			if (pl.len) {
+				lc -= pl.len;
+				if (!emit(pl.lit)) return false;
+			} else {
+				if (pl.longs.empty()) return false;
+				size_t j = 0;
+				for (; j < pl.longs.size(); j++) {
+					const int sym = pl.longs[j], l = (int) (hcode[sym] & 63);
+					while (lc < l && in < ie) c = (c << 8) | *in++, lc += 8;
+					if (lc >= l && (hcode[sym] >> 6) == ((c >> (lc - l)) & ((1ull << l) - 1))) {
+						lc -= l;
+						if (!emit(sym)) return false;
+						break;
+					}
+				}
+				if (j == pl.longs.size()) return false;
+			}
+		}
+	}
+	const int i = (8 - nBits) & 7; // bits of the last byte that are padding
+	c >>= i, lc -= i;
+	while (lc > 0) {
+		const Dec &pl = dec[(c << (kDecBits - lc)) & kDecMask];
+		if (!pl.len) return false;
+		lc -= pl.len;
+		if (!emit(pl.lit)) return false;
+	}
+	return out == oe;
+}
+
+bool hufUncompress(const unsigned char *in, size_t nIn, uint16_t *out, size_t nOut) {
+	if (nIn == 0) return nOut == 0;
+	if (nIn < 20) return false;
+	auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, in + o, 4); return v; };
+	const int im = (int) u32(0), iM = (int) u32(4), nBits = (int) u32(12);
+	if (im < 0 || im >= kEncSize || iM < 0 || iM >= kEncSize || nBits < 0) return false;
+	const unsigned char *ptr = in + 20, *end = in + nIn;
+	std::vector<uint64_t> hcode;
+	std::vector<Dec> dec;
+	if (!unpackEncTable(ptr, end, im, iM, hcode)) return false;
+	if ((size_t) (nBits + 7) / 8 > (size_t) (end - ptr)) return false;
+	if (!buildDecTable(hcode, im, iM, dec)) return false;
+	return decode(hcode, dec, ptr, end, nBits, iM, nOut, out);
+}
+
+// inverse wavelet butterflies: 14-bit data (signed arithmetic) and full 16-bit data (modulo arithmetic)
+inline void wdec14(uint16_t l, uint16_t h, uint16_t &a, uint16_t &b) {
+	const int16_t ls = (int16_t) l, hs = (int16_t) h;
+	const int hi = hs, ai = ls + (hi & 1) + (hi >> 1);
+	a = (uint16_t) (int16_t) ai, b = (uint16_t) (int16_t) (ai - hi);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t &a, uint16_t &b) {
+	const int m = l, d = h;
+	const int bb = (m - (d >> 1)) & 0xffff, aa = (d + bb - (1 << 15)) & 0xffff;
+	b = (uint16_t) bb, a = (uint16_t) aa;
+}
+void wav2Decode(uint16_t *in, int nx, int ox, int ny, int oy, uint16_t mx) {
+	const bool w14 = mx < (1 << 14);
+	const int n = nx > ny ? ny : nx;
+	int p = 1, p2;
+	while (p <= n) p <<= 1;
+	p >>= 1, p2 = p, p >>= 1;
+	auto dec2 = [&](uint16_t l, uint16_t h, uint16_t &a, uint16_t &b) { w14 ? wdec14(l, h, a, b) : wdec16(l, h, a, b); };
+	while (p >= 1) {
+		uint16_t *py = in, *ey = in + (ptrdiff_t) oy * (ny - p2);
+		const ptrdiff_t oy1 = (ptrdiff_t) oy * p, oy2 = (ptrdiff_t) oy * p2, ox1 = (ptrdiff_t) ox * p, ox2 = (ptrdiff_t) ox * p2;
+		uint16_t i00, i01, i10, i11;
+		for (; py <= ey; py += oy2) {
+			uint16_t *px = py, *ex = py + (ptrdiff_t) ox * (nx - p2);
+			for (; px <= ex; px += ox2) {
+				uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+				dec2(*px, *p10, i00, i10);
+				dec2(*p01, *p11, i01, i11);
+				dec2(i00, i01, *px, *p01);
+				dec2(i10, i11, *p10, *p11);
+			}
+			if (nx & p) {
+				uint16_t *p10 = px + oy1;
+				dec2(*px, *p10, i00, *p10);
+				*px = i00;
+			}
+		}
+		if (ny & p) {
+			uint16_t *px = py, *ex = py + (ptrdiff_t) ox * (nx - p2);
+			for (; px <= ex; px += ox2) {
+				uint16_t *p01 = px + ox1;
+				dec2(*px, *p01, i00, *p01);
+				*px = i00;
+			}
+		}
+		p2 = p, p >>= 1;
+	}
+}
+
+// one chunk -> the uncompressed scanline layout (per line: per channel: width samples)
+bool uncompressChunk(const unsigned char *src, size_t size, const std::vector<ExrChannel> &channels, int width, int lines, unsigned char *raw) {
+	if (size < 4) return false;
+	uint16_t minNonZero, maxNonZero;
+	memcpy(&minNonZero, src, 2), memcpy(&maxNonZero, src + 2, 2);
+	size_t pos = 4;
+	std::vector<unsigned char> bitmap(8192, 0);
+	if (minNonZero <= maxNonZero) {
+		if (maxNonZero >= 8192) return false;
+		const size_t nb = (size_t) maxNonZero - minNonZero + 1;
+		if (pos + nb > size) return false;
+		memcpy(&bitmap[minNonZero], src + pos, nb);
+		pos += nb;
+	}
+	std::vector<uint16_t> lut(65536, 0);
+	int k = 0;
+	for (int i = 0; i < 65536; i++)
+		if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = (uint16_t) i;
+	const uint16_t maxValue = (uint16_t) (k - 1);
+	if (pos + 4 > size) return false;
+	int32_t length;
+	memcpy(&length, src + pos, 4);
+	pos += 4;
+	if (length < 0 || pos + (size_t) length > size) return false;
+	size_t total = 0;
+	for (const ExrChannel &c : channels) total += (size_t) width * lines * (c.type == 1 ? 1 : 2);
+	std::vector<uint16_t> tmp(total);
+	if (!hufUncompress(src + pos, (size_t) length, tmp.data(), total)) return false;
+	std::vector<size_t> start(channels.size());
+	size_t at = 0;
+	for (size_t c = 0; c < channels.size(); c++) {
+		const int sz = channels[c].type == 1 ? 1 : 2;
+		start[c]	 = at;
+		for (int j = 0; j < sz; j++) wav2Decode(tmp.data() + at + j, width, sz, lines, width * sz, maxValue);
+		at += (size_t) width * lines * sz;
+	}
+	for (uint16_t &v : tmp) v = lut[v];
+	unsigned char *out = raw;
+	for (int l = 0; l < lines; l++)
+		for (size_t c = 0; c < channels.size(); c++) {
+			const size_t n = (size_t) width * (channels[c].type == 1 ? 1 : 2);
+			memcpy(out, tmp.data() + start[c] + (size_t) l * n, n * 2);
+			out += n * 2;
+		}
+	return true;
+}
+} // namespace piz
+
 bool loadEXR(const string &path, Image &img, string *err) {
 	std::vector<unsigned char> buf;
 	if (!readFile(path, buf)) return fail(err, "cannot open " + path);
@@ -213,12 +467,12 @@ bool loadEXR(const string &path, Image &img, string *err) {
 	}
 	(void) lineOrder; // every chunk carries its y coordinate
 	if (channels.empty() || win[2] < win[0] || win[3] < win[1]) return fail(err, path + ": EXR header lacks channels / dataWindow");
-	if (compression != 0 && compression != 2 && compression != 3)
-		return fail(err, path + ": EXR compression " + std::to_string(compression) + " is not supported (NONE, ZIPS, ZIP are)");
+	if (compression != 0 && compression != 2 && compression != 3 && compression != 4)
+		return fail(err, path + ": EXR compression " + std::to_string(compression) + " is not supported (NONE, ZIPS, ZIP, PIZ are)");
 	for (const ExrChannel &c : channels)
 		if (c.xs != 1 || c.ys != 1 || c.type < 0 || c.type > 2) return fail(err, path + ": sub-sampled or unknown-type EXR channels are not supported");
 	const int width = win[2] - win[0] + 1, height = win[3] - win[1] + 1;
-	const int linesPerBlock = compression == 3 ? 16 : 1;
+	const int linesPerBlock = compression == 4 ? 32 : compression == 3 ? 16 : 1;
 	const int nBlocks		= (height + linesPerBlock - 1) / linesPerBlock;
 	size_t lineBytes = 0;
 	for (const ExrChannel &c : channels) lineBytes += (size_t) width * (c.type == 1 ? 2 : 4);
@@ -248,7 +502,9 @@ bool loadEXR(const string &path, Image &img, string *err) {
 		raw.resize(want);
 		const unsigned char *src = &buf[off + 8];
 		if (compression == 0 || (size_t) size == want) memcpy(raw.data(), src, std::min(want, (size_t) size));
-		else {
+		else if (compression == 4) {
+			if (!piz::uncompressChunk(src, (size_t) size, channels, width, lines, raw.data())) return fail(err, path + ": corrupt PIZ data in EXR chunk");
+		} else {
 			tmp.resize(want);
 			uLongf got = (uLongf) want;
 			if (uncompress(tmp.data(), &got, src, (uLong) size) != Z_OK || got != want) return fail(err, path + ": zlib error in EXR chunk");

@@ -141,9 +141,43 @@ def test_opencv_interoperability(tmp_path):
     assert np.array_equal(krr.load_image(q), img)
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["piz_half_37x45", "piz_float_70x33", "piz_flat_40x40"])
+def test_piz_fixtures_decode_bit_exactly(name):
+    """PIZ (wavelet + Huffman) files written by OpenCV's OpenEXR codec (tools/make_golden_piz.py): 14-bit and
+    16-bit wavelet butterflies, odd sizes, a short last block, the Huffman run-length symbol."""
+    mine = krr.load_image(os.path.join(GOLDEN, name + ".exr"))
+    want = np.load(os.path.join(GOLDEN, name + ".npy"))
+    assert mine.shape == want.shape
+    assert np.array_equal(mine.view(np.uint32), want.view(np.uint32))
+
+
+def test_corrupt_piz_data_is_an_error(tmp_path):
+    data = bytearray(open(os.path.join(GOLDEN, "piz_half_37x45.exr"), "rb").read())
+    for k in range(len(data) - 600, len(data) - 200):  # inside the Huffman stream of the last chunk
+        data[k] ^= 0x5A
+    (tmp_path / "bad_piz.exr").write_bytes(bytes(data))
+    try:
+        img = krr.load_image(tmp_path / "bad_piz.exr")  # a damaged stream may still decode to a full block
+        assert img.shape == (45, 37, 4)
+    except RuntimeError as e:
+        assert "PIZ" in str(e)
+    (tmp_path / "short_piz.exr").write_bytes(bytes(data[: len(data) // 2]))
+    with pytest.raises(RuntimeError):
+        krr.load_image(tmp_path / "short_piz.exr")
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/common/assets/textures/sky.exr"), reason="reference checkout not present")
-def test_the_reference_sky_texture_is_piz_and_says_so():
-    """The one EXR the reference ships is PIZ-compressed (wavelet + Huffman), which this reader does not
-    implement: the header is parsed and the codec is named in the error instead of returning garbage."""
-    with pytest.raises(RuntimeError, match="compression 4 is not supported"):
-        krr.load_image("/root/reference/common/assets/textures/sky.exr")
+def test_the_reference_sky_texture_decodes_like_opencv():
+    """The one EXR the reference ships (the environment map of its example configs) is PIZ-compressed FLOAT."""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    path = "/root/reference/common/assets/textures/sky.exr"
+    mine = krr.load_image(path)
+    theirs = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if theirs is None:
+        pytest.skip("this OpenCV build has no OpenEXR codec")
+    assert mine.shape == (512, 1024, 4)
+    assert np.array_equal(mine.view(np.uint32), theirs[..., [2, 1, 0, 3]].view(np.uint32))
