@@ -81,6 +81,7 @@ public:
 	std::vector<HostInstance> instances;
 	std::vector<HostMaterial> materials;
 	std::vector<KrrLightDesc> lights;
+	std::vector<std::vector<float>> lightImages; // RGBA32F lat-long images of infinite lights (lights[i].texture.image points here)
 	std::vector<HostMedium> media;
 	KrrSceneOptions options{1, 0, 0, 0.f, 1.f};
 	KrrCameraData camera;
@@ -118,6 +119,9 @@ public:
 	static bool import(const json &j, Scene::SharedPtr scene, const string &baseDir);
 	static bool loadModel(const string &filepath, Scene::SharedPtr scene, const float nodeTransform[12],
 						  const string &baseDir);
+	// the "environment" key of a scene / application config (krrscene.cpp:267-274, renderer.cpp:295-302):
+	// an InfiniteLight with a lat-long image at the scene root
+	static bool addEnvironment(const string &texture, Scene::SharedPtr scene, const string &baseDir);
 };
 bool loadObj(const string &filepath, Scene &scene, const float nodeTransform[12]);
 // minimal glTF 2.0 (gltf.cpp): meshes, node hierarchy, pbrMetallicRoughness materials, PNG textures, TRS animation

@@ -460,6 +460,10 @@ void RenderApp::loadConfig(const json &config, const string &baseDir) {
 		float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 		SceneImporter::loadModel(config.at("model").asString(), scene, I, assetBase);
 	}
+	if (config.contains("environment")) { // renderer.cpp:295-302
+		if (!scene) throw std::runtime_error("Import a model before doing scene configurations!");
+		SceneImporter::addEnvironment(config.at("environment").asString(), scene, assetBase);
+	}
 	if (config.contains("scene")) {
 		if (!scene) scene = std::make_shared<Scene>();
 		SceneImporter::import(config.at("scene"), scene, assetBase);

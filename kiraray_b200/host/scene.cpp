@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -468,7 +470,40 @@ void rotationFromDirection(const float dir[3], double R[9]) {
 	for (int i = 0; i < 3; i++) R[i * 3 + 0] = s[i], R[i * 3 + 1] = u[i], R[i * 3 + 2] = -f[i];
 }
 
-bool loadLight(Scene &scene, const json &params, const float nodeXf[12]) {
+// Image::loadImage path rule (texture.cpp:34-38): "$name" is a built-in texture, File::textureDir() / name
+// (common/assets/textures of the reference's tree); here: $KRR_TEXTURE_DIR, then assets/textures and
+// common/assets/textures under the asset root
+string resolveTexturePath(const string &name, const string &baseDir) {
+	size_t d = name.find('$');
+	if (d == string::npos) return joinPath(baseDir, name);
+	string file = name.substr(d + 1);
+	std::vector<string> dirs;
+	if (const char *e = getenv("KRR_TEXTURE_DIR")) dirs.push_back(e);
+	dirs.push_back(joinPath(baseDir, "assets/textures"));
+	dirs.push_back(joinPath(baseDir, "common/assets/textures"));
+	for (const string &dir : dirs)
+		if (fileExists(dir + "/" + file)) return dir + "/" + file;
+	return dirs.back() + "/" + file;
+}
+
+// Texture::createFromFile for the lat-long image of an infinite light.  The reference logs an error and
+// carries on with an invalid texture when the file cannot be read (texture.h:95-99): the light then emits
+// its tint; same here, with the message on stderr.
+void setLightImage(Scene &scene, KrrLightDesc &l, const string &texture, const string &baseDir) {
+	Image img;
+	string err, path = resolveTexturePath(texture, baseDir);
+	if (!loadImage(path, img, false, &err) || !img.isValid()) {
+		fprintf(stderr, "[krr_host] failed to load texture %s: %s\n", path.c_str(), err.c_str());
+		return;
+	}
+	scene.lightImages.push_back(std::move(img.rgba));
+	l.texture.valid	 = 1;
+	l.texture.value[0] = l.texture.value[1] = l.texture.value[2] = l.texture.value[3] = 1;
+	l.texture.image	 = scene.lightImages.back().data();
+	l.texture.width = img.width, l.texture.height = img.height;
+}
+
+bool loadLight(Scene &scene, const json &params, const float nodeXf[12], const string &baseDir) {
 	string type = params.value("type", "infinite");
 	KrrLightDesc l;
 	memset(&l, 0, sizeof l);
@@ -486,6 +521,8 @@ bool loadLight(Scene &scene, const json &params, const float nodeXf[12]) {
 		l.type = KRR_LIGHT_INFINITE;
 		// krr::InfiniteLight(color, scale) uploads through the texture constructor with tint = 1
 		// (light.cpp:35-38): a texture-less JSON light has an invalid image -> Li = tint = (1,1,1)
+		string texture = params.value("texture", string());
+		if (!texture.empty()) setLightImage(scene, l, texture, baseDir); // krrscene.cpp:44-48
 	} else return false;
 	float v[3];
 	if (params.getFloats<3>("position", v)) { l.transform[3] = v[0], l.transform[7] = v[1], l.transform[11] = v[2]; }
@@ -666,7 +703,7 @@ bool importNode(const json &j, Scene::SharedPtr scene, const float parent[12], c
 		else {
 			string type = j.value("type", "model");
 			if (type == "medium") return loadMedium(*scene, params, xf);
-			if (type == "light") return loadLight(*scene, params, xf);
+			if (type == "light") return loadLight(*scene, params, xf, baseDir);
 			return false;
 		}
 	} else if (j.isString()) {
@@ -701,6 +738,19 @@ bool SceneImporter::loadModel(const string &filepath, Scene::SharedPtr scene, co
 	return false; // .glb / FBX / pbrt / VDB importers are out of scope
 }
 
+bool SceneImporter::addEnvironment(const string &texture, Scene::SharedPtr scene, const string &baseDir) {
+	KrrLightDesc l;
+	memset(&l, 0, sizeof l);
+	l.type	= KRR_LIGHT_INFINITE;
+	l.scale = 1;
+	l.color[0] = l.color[1] = l.color[2] = 1;
+	identity12(l.transform);
+	setLightImage(*scene, l, texture, baseDir);
+	scene->lights.push_back(l);
+	scene->touch();
+	return l.texture.image != nullptr;
+}
+
 bool SceneImporter::import(const json &j, Scene::SharedPtr scene, const string &baseDir) {
 	float I[12];
 	identity12(I);
@@ -724,6 +774,7 @@ bool SceneImporter::import(const json &j, Scene::SharedPtr scene, const string &
 		scene->hasCameraController = true;
 	}
 	if (j.contains("model")) importNode(j.at("model"), scene, I, baseDir);
+	if (j.contains("environment")) addEnvironment(j.at("environment").asString(), scene, baseDir);
 	if (j.contains("media"))
 		for (const json &m : j.at("media").items()) loadMedium(*scene, m.at("params"), I);
 	if (j.contains("materials")) loadMaterials(*scene, j.at("materials"));

@@ -217,6 +217,7 @@ struct OrcScene {
 	std::vector<LightRef> lights;
 	std::vector<OlLight> analytic;
 	std::vector<int> infinite; /* indices into analytic */
+	std::vector<KrrTextureDesc> analyticTex; /* per analytic light: lat-long image of an infinite light (image == NULL: none) */
 	std::vector<MediumData> media;
 	std::vector<XNode> xnodes;
 	/* object<->world of an instance for a ray that carries `time` (getInstanceTransform, shading.h:70-76) */
@@ -407,6 +408,26 @@ void sampleTex(const KrrTextureDesc &t, float u, float v, const float fallback[4
 }
 
 inline float luminanceRGB(const float c[3]) { return c[0] * 0.299f + c[1] * 0.587f + c[2] * 0.114f; }
+
+/* InfiniteLight::Li with a lat-long IMAGE (light.h:242-246): L = tint (= 1) * image.evaluate(uv), uv =
+ * worldToLatLong(rotation^T wi) (math_utils.h:133-139).  On the host the reference's image.evaluate() only
+ * knows the constant (tex2D is device code), so the texel is fetched here (sampleTex: the bilinear / wrap
+ * filter of the CUDA texture object, texture.cpp:229-246) and handed to the reference's InfiniteLight as its
+ * tint, which then runs the reference's own fromRGB(RGBIlluminant). */
+void infiniteLightLi(const OlLight &l, const KrrTextureDesc &tex, const float wi[3], const float lambda[4], float L[4]) {
+	if (!tex.image) { ol_inflight_Li(&l, wi, lambda, L); return; }
+	float d[3];
+	for (int c = 0; c < 3; c++) d[c] = l.rotation[0 * 3 + c] * wi[0] + l.rotation[1 * 3 + c] * wi[1] + l.rotation[2 * 3 + c] * wi[2];
+	float n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+	if (n > 0) d[0] /= n, d[1] /= n, d[2] /= n;
+	float u = std::atan2(d[0], -d[2]) * 0.15915494309189533577f + 0.5f, v = std::acos(d[1]) * 0.318309886183790671538f;
+	const float one[4] = {1, 1, 1, 1};
+	float texel[4];
+	sampleTex(tex, u, v, one, texel);
+	OlLight tinted = l;
+	memcpy(tinted.color, texel, 12);
+	ol_inflight_Li(&tinted, wi, lambda, L);
+}
 
 /* getPerpendicular, src/util/math_utils.h:122-133 */
 V3 getPerpendicular(V3 u) {
@@ -865,6 +886,10 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		}
 		s->lights.push_back(LightRef{ld.type, -1, -1, (int) s->analytic.size()});
 		s->analytic.push_back(l);
+		KrrTextureDesc tex;
+		memset(&tex, 0, sizeof tex);
+		if (ld.type == KRR_LIGHT_INFINITE && ld.texture.valid && ld.texture.image && ld.texture.width > 0 && ld.texture.height > 0) tex = ld.texture;
+		s->analyticTex.push_back(tex);
 	}
 	for (int i = 0; i < d->n_media; i++) {
 		const KrrMediumDesc &md = d->media[i];
@@ -1143,7 +1168,7 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 					for (int li : s.infinite) {
 						float w[3], Li4[4];
 						st(w, rayD);
-						ol_inflight_Li(&s.analytic[li], w, lambda, Li4);
+						infiniteLightLi(s.analytic[li], s.analyticTex[li], w, lambda, Li4);
 						Spec Li = Spec{{Li4[0], Li4[1], Li4[2], Li4[3]}};
 						if (p->nee && depth && !(bsdfType & (32 | 1))) {
 							float lightPdf = 0.07957747154594767f /* M_INV_4PI */ * (1.f / nLights);
@@ -1168,7 +1193,15 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 						OlTriLight tl;
 						fillTri(s, lr, tl);
 						ol_arealight_sample_li(&tl, u2, cp, cn, lambda, lp, ln, Ll, &lpdfv);
-					} else ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+					} else {
+						ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+						if (s.analyticTex[lr.analytic].image) {
+							/* sampleLi (light.h:222-231): p = ctx.p + wi * 2 * sceneRadius with wi uniform on the sphere; the
+							 * image is looked up in that direction */
+							float wi3[3] = {lp[0] - cp[0], lp[1] - cp[1], lp[2] - cp[2]};
+							infiniteLightLi(s.analytic[lr.analytic], s.analyticTex[lr.analytic], wi3, lambda, Ll);
+						}
+					}
 					lightPdf = (1.f / nLights) * lpdfv;
 				};
 				/* [2.4a] sampleMediumScattering, medium.cpp:105-153 */
