@@ -229,10 +229,20 @@ def main():
         gpu.render(film.data_ptr(), sptr)
         reduce_film(film, part, dist)  # film accumulation over NVLink (the one exchange step)
 
+    film_host2 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    host_bufs = [host_np, film_host2.numpy()]
+
+    def step_e2e_sync(i):
+        gpu.begin_frame(frame_of(i), cam, sptr)
+        gpu.render_to_host(host_np, sptr)        # render + D2H of the film + stream sync, every step
+
     def step_e2e(i):
         gpu.begin_frame(frame_of(i), cam, sptr)  # camera struct: host -> device (kernel arguments)
         if dist is None:
-            gpu.render_to_host(host_np, sptr)    # render + D2H of the film + stream sync
+            # render + D2H of the film into one of two pinned host buffers on the copy stream: the read-back of
+            # step i overlaps the rendering of step i + 1 (krr_wfpt_render_to_host_async); the timed region ends
+            # with krr_wfpt_wait_host, i.e. when the film of every step is in host memory
+            gpu.render_to_host_async(host_bufs[i & 1], sptr)
         else:
             gpu.render(film.data_ptr(), sptr)
             reduce_film(film, part, dist)
@@ -245,15 +255,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
+    def timed(fn, drain=None):
         for i in range(args.warmup):
             fn(i)
+        if drain:
+            drain()
         barrier()
         rays = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(args.steps):
             fn(args.warmup + i)
+        if drain:
+            drain()  # host-side wait for the copy stream; e1 is recorded after the last film has landed
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -275,7 +289,8 @@ def main():
         st = gpu.stats()
         rays += st["closest_rays"] + st["shadow_rays"]
     # ---- end-to-end timing (host buffers) ----
-    ms_e2e = timed(step_e2e)
+    ms_e2e = timed(step_e2e, gpu.wait_host if dist is None else None)
+    ms_e2e_sync = timed(step_e2e_sync) if dist is None else None
     # ---- per-stage profile of one step (events around every launch; not part of `value`) ----
     gpu.set_profiling(True)
     gpu.begin_frame(frame_of(args.warmup), cam, sptr)
@@ -330,7 +345,9 @@ def main():
                 "config": {"workload": WORKLOAD, "width": W, "height": H, "max_depth": MAX_DEPTH, "rr": RR, "nee": True,
                            "spp_per_step": args.spp, "parallelism": part.describe(),
                            "l2": "per-step queue + pixel-state working set (~0.9 GB) exceeds the 126 MB L2", "spp_per_s": spp_s},
-                "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(krr.KrrCameraData), "d2h_bytes_per_step": W * H * 16},
+                "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(krr.KrrCameraData), "d2h_bytes_per_step": W * H * 16,
+                        "readback": "pipelined: film of step i copied to pinned host memory on a copy stream while step i + 1 renders; timed region ends when every film is on the host" if world == 1 else "after the NCCL film reduce, rank 0, stream sync per step",
+                        "value_sync_per_step": (rays / (ms_e2e_sync * 1e-3) / 1e6) if ms_e2e_sync else None},
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
         emit(line)
     if dist is not None:

@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define KRR_WFPT_ABI_VERSION 3
+#define KRR_WFPT_ABI_VERSION 4
 
 enum {
 	KRR_OK			  = 0,
@@ -244,6 +244,14 @@ int krr_wfpt_render(KrrWfpt *h, float *film_rgba_device, void *cuda_stream);
 
 /* Same, with a HOST film buffer: render + device->host copy + stream synchronise. */
 int krr_wfpt_render_to_host(KrrWfpt *h, float *film_rgba_host, void *cuda_stream);
+
+/* Pipelined read-back for callers that consume frames on the host (the reference reads its film back only
+ * to save it, AccumulatePass / RenderContext::readback): render as above, then copy the film to
+ * film_rgba_host (pinned memory for a truly asynchronous copy) on an internal copy stream, WITHOUT
+ * synchronising; the caller's stream is free to render the next frame meanwhile (two internal device films
+ * alternate).  The host buffer holds the frame once krr_wfpt_wait_host() has returned. */
+int krr_wfpt_render_to_host_async(KrrWfpt *h, float *film_rgba_host, void *cuda_stream);
+int krr_wfpt_wait_host(KrrWfpt *h);
 
 /* Multi-GPU work split by image tile (no reference counterpart: single device,
  * device/context.cpp:37-40).  This handle renders pixel rows [row_begin,row_end) only; the other

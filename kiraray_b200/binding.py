@@ -154,6 +154,8 @@ def load_wfpt():
         "krr_wfpt_begin_frame": [P, U64, C.POINTER(KrrCameraData), P],
         "krr_wfpt_render": [P, P, P],
         "krr_wfpt_render_to_host": [P, P, P],
+        "krr_wfpt_render_to_host_async": [P, P, P],
+        "krr_wfpt_wait_host": [P],
         "krr_wfpt_render_megakernel": [P, U64, C.POINTER(KrrCameraData), P, P],
         "krr_wfpt_set_partition": [P, I32, I32],
         "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
@@ -426,6 +428,13 @@ class Wfpt:
             film = np.empty((h, w, 4), dtype=np.float32)
         self._ck(self.lib.krr_wfpt_render_to_host(self.h, film.ctypes.data_as(P), P(stream or 0)), "render_to_host")
         return film
+
+    def render_to_host_async(self, film, stream=None):
+        """Pipelined read-back: `film` (ideally pinned) holds the frame after wait_host()."""
+        self._ck(self.lib.krr_wfpt_render_to_host_async(self.h, film.ctypes.data_as(P), P(stream or 0)), "render_to_host_async")
+
+    def wait_host(self):
+        self._ck(self.lib.krr_wfpt_wait_host(self.h), "wait_host")
 
     def instance_xf(self, ids, times):
         """(n, 2, 12): object->world and world->object of each instance at each ray time, from the device"""

@@ -151,6 +151,11 @@ struct KrrWfpt : WaveState {
 	cudaEvent_t evFork = nullptr, evJoin[kMaxBands - 1] = {};
 	int bands = 0;		 // "bands": see WaveState; 0 = automatic (2 for a scene that is one flat triangle list, else 1)
 	int activeBands = 1; // decided by begin_frame
+	// pipelined film read-back (krr_wfpt_render_to_host_async): two device films, a copy stream
+	Buf<float4> asyncFilm[2];
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
+	int asyncSlot = 0;
 	int refill = 0;		 // "refill": idle lanes of a trace warp that trigger finalisation + refill; 0 = automatic (kRefill / kRefillFlat)
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
 	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
@@ -383,6 +388,11 @@ extern "C" void krr_wfpt_destroy(KrrWfpt *h) {
 		if (h->evJoin[b]) cudaEventDestroy(h->evJoin[b]);
 	}
 	if (h->evFork) cudaEventDestroy(h->evFork);
+	if (h->copyStream) cudaStreamDestroy(h->copyStream);
+	for (int i = 0; i < 2; i++) {
+		if (h->evRendered[i]) cudaEventDestroy(h->evRendered[i]);
+		if (h->evCopied[i]) cudaEventDestroy(h->evCopied[i]);
+	}
 	delete h;
 }
 
@@ -1034,6 +1044,43 @@ extern "C" int krr_wfpt_render_to_host(KrrWfpt *h, float *film_host, void *strea
 	if (rc) return rc;
 	CUDA_OK(cudaMemcpyAsync(film_host, staging.p, n * 16, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
 	CUDA_OK(cudaStreamSynchronize((cudaStream_t) stream));
+	return KRR_OK;
+}
+
+// Pipelined variant: the film of this frame travels to the host on a copy stream while the caller's stream
+// goes on with the next frame.  Two device films alternate; rendering into one waits (on the device) for
+// the copy that last read it.
+extern "C" int krr_wfpt_render_to_host_async(KrrWfpt *h, float *film_host, void *stream) {
+	if (!h || !film_host) return fail(KRR_E_INVALID, "null argument");
+	CUDA_OK(cudaSetDevice(h->device));
+	const size_t n = (size_t) h->width * h->height;
+	if (!h->copyStream) {
+		CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			CUDA_OK(cudaEventCreateWithFlags(&h->evRendered[i], cudaEventDisableTiming));
+			CUDA_OK(cudaEventCreateWithFlags(&h->evCopied[i], cudaEventDisableTiming));
+		}
+	}
+	const int slot = h->asyncSlot;
+	h->asyncSlot ^= 1;
+	if (h->asyncFilm[slot].n != n) {
+		CUDA_OK(cudaStreamSynchronize(h->copyStream)); // a resize between frames: no copy may still read the old buffer
+		if (h->asyncFilm[slot].alloc(n)) return KRR_E_CUDA;
+	}
+	cudaStream_t st = (cudaStream_t) stream;
+	CUDA_OK(cudaStreamWaitEvent(st, h->evCopied[slot], 0)); // no-op until the slot has been copied once
+	int rc = krr_wfpt_render(h, (float *) h->asyncFilm[slot].p, stream);
+	if (rc) return rc;
+	CUDA_OK(cudaEventRecord(h->evRendered[slot], st));
+	CUDA_OK(cudaStreamWaitEvent(h->copyStream, h->evRendered[slot], 0));
+	CUDA_OK(cudaMemcpyAsync(film_host, h->asyncFilm[slot].p, n * 16, cudaMemcpyDeviceToHost, h->copyStream));
+	CUDA_OK(cudaEventRecord(h->evCopied[slot], h->copyStream));
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_wait_host(KrrWfpt *h) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	if (h->copyStream) CUDA_OK(cudaStreamSynchronize(h->copyStream));
 	return KRR_OK;
 }
 

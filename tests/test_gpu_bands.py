@@ -107,3 +107,22 @@ def test_taps_and_profiling_fall_back_to_one_band():
     assert gpu.stage_times()["scatter"]["launches"] > 0
     gpu.set_profiling(False)
     assert np.array_equal(film1.view(np.uint32), film2.view(np.uint32))
+
+
+def test_pipelined_readback_delivers_the_same_frames():
+    app = app_for("cbox.json", 120, 68, spp=2, max_depth=4)
+    gpu = krr.Wfpt(params=dict(app.wfpt_params(), debug_taps=False))
+    gpu.set_scene(app.scene_desc())
+    gpu.resize(120, 68)
+    want = []
+    for f in range(1, 6):
+        gpu.begin_frame(f, app.camera())
+        want.append(gpu.render_to_host().copy())
+    got = [np.zeros((68, 120, 4), np.float32) for _ in want]
+    for f in range(1, 6):  # five frames in flight over two internal device films, no host sync in between
+        gpu.begin_frame(f, app.camera())
+        gpu.render_to_host_async(got[f - 1])
+    gpu.wait_host()
+    for a, b in zip(want, got):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert not np.array_equal(want[0], want[1])
