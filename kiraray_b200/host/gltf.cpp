@@ -4,7 +4,7 @@
 // createMaterial(..., ImportMode::GLTF2) (assimp.cpp:93-226).  Assimp and stb_image are third-party
 // libraries; this file reads the subset of the format the reference's assets use, straight from the glTF
 // 2.0 specification:
-//   * .gltf JSON with external .bin buffers (no .glb, no data: URIs); accessors of every component type,
+//   * .gltf JSON with external .bin buffers, or binary .glb (JSON + BIN chunks, images in buffer views); no data: URIs; accessors of every component type,
 //     strided buffer views, normalised integers;
 //   * triangle primitives with POSITION, NORMAL, TEXCOORD_0, TANGENT and indices; one HostMesh per primitive;
 //   * the node hierarchy (matrix or T * R * S), flattened to one instance per mesh node;
@@ -72,10 +72,15 @@ float srgbToLinear(float c) { return c <= 0.04045f ? c / 12.92f : std::pow((c + 
 
 // =================================================================================================
 // PNG: 8-bit grey / grey+alpha / RGB / RGBA / palette, non-interlaced (PNG specification, 2nd edition)
+bool decodePNG(const std::vector<unsigned char> &buf, const string &path, Image &img, bool srgb, string *err);
 bool loadPNG(const string &path, Image &img, bool srgb, string *err) {
-	auto fail = [&](const string &m) { if (err) *err = path + ": " + m; return false; };
 	std::vector<unsigned char> buf;
-	if (!readAll(path, buf)) return fail("cannot open");
+	if (!readAll(path, buf)) { if (err) *err = path + ": cannot open"; return false; }
+	return decodePNG(buf, path, img, srgb, err);
+}
+// the same from memory (images embedded in a .glb through a bufferView); `path` only names it in messages
+bool decodePNG(const std::vector<unsigned char> &buf, const string &path, Image &img, bool srgb, string *err) {
+	auto fail = [&](const string &m) { if (err) *err = path + ": " + m; return false; };
 	static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
 	if (buf.size() < 8 || memcmp(buf.data(), sig, 8)) return fail("not a PNG file");
 	auto be32 = [&](size_t p) { return (uint32_t) buf[p] << 24 | (uint32_t) buf[p + 1] << 16 | (uint32_t) buf[p + 2] << 8 | buf[p + 3]; };
@@ -246,10 +251,18 @@ HostMaterial materialFromGltf(Gltf &g, const json &m, int index) {
 		const json &tex = g.doc.at("textures").at((size_t) ti);
 		if (!tex.contains("source")) return;
 		const json &im = g.doc.at("images").at((size_t) tex.at("source").asNumber());
-		if (!im.contains("uri")) { fprintf(stderr, "glTF: material %d: embedded images are not supported, texture skipped\n", index); return; }
 		Image img;
 		string err;
-		if (!loadPNG(g.dir + "/" + im.at("uri").asString(), img, srgb, &err)) { fprintf(stderr, "glTF: texture skipped (%s)\n", err.c_str()); return; }
+		bool ok = false;
+		if (im.contains("uri") && im.at("uri").asString().rfind("data:", 0) != 0) ok = loadPNG(g.dir + "/" + im.at("uri").asString(), img, srgb, &err);
+		else if (im.contains("bufferView")) { // image stored in a buffer (.glb)
+			const json &bv = g.doc.at("bufferViews").at((size_t) im.at("bufferView").asNumber());
+			const size_t off = (size_t) bv.value("byteOffset", 0.0), len = (size_t) bv.at("byteLength").asNumber();
+			const int b = (int) bv.at("buffer").asNumber();
+			if (b < 0 || (size_t) b >= g.buffers.size() || off + len > g.buffers[b].size()) err = "image buffer view out of range";
+			else ok = decodePNG(std::vector<unsigned char>(g.buffers[b].begin() + off, g.buffers[b].begin() + off + len), "embedded image", img, srgb, &err);
+		} else err = "data: URIs are not supported";
+		if (!ok) { fprintf(stderr, "glTF: material %d: texture skipped (%s)\n", index, err.c_str()); return; }
 		out.images[slot] = img.rgba;
 		KrrTextureDesc &t = d.textures[slot];
 		t.valid = 1, t.width = img.width, t.height = img.height;
@@ -295,17 +308,37 @@ HostMaterial materialFromGltf(Gltf &g, const json &m, int index) {
 
 bool loadGltf(const string &filepath, Scene &scene, const float nodeTransform[12]) {
 	Gltf g;
+	std::vector<unsigned char> glbBin; // BIN chunk of a .glb: the buffer that has no uri
+	bool haveGlbBin = false;
 	{
-		std::ifstream f(filepath);
-		if (!f.good()) throw std::runtime_error("cannot open model " + filepath);
-		std::stringstream ss;
-		ss << f.rdbuf();
-		g.doc = json::parse(ss.str());
+		std::vector<unsigned char> file;
+		if (!readAll(filepath, file)) throw std::runtime_error("cannot open model " + filepath);
+		string text;
+		auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, &file[o], 4); return v; };
+		if (file.size() >= 12 && u32(0) == 0x46546C67u) { // binary glTF: 12-byte header, then chunks (length, type, data)
+			if (u32(4) != 2) throw std::runtime_error("glTF: unsupported .glb version in " + filepath);
+			size_t pos = 12, end = std::min<size_t>(u32(8), file.size());
+			while (pos + 8 <= end) {
+				const size_t len = u32(pos);
+				const uint32_t type = u32(pos + 4);
+				if (pos + 8 + len > end) throw std::runtime_error("glTF: truncated .glb chunk in " + filepath);
+				if (type == 0x4E4F534Au) text.assign((const char *) &file[pos + 8], len);
+				else if (type == 0x004E4942u && !haveGlbBin) glbBin.assign(file.begin() + pos + 8, file.begin() + pos + 8 + len), haveGlbBin = true;
+				pos += 8 + ((len + 3) & ~(size_t) 3);
+			}
+			if (text.empty()) throw std::runtime_error("glTF: .glb without a JSON chunk: " + filepath);
+		} else text.assign(file.begin(), file.end());
+		g.doc = json::parse(text);
 	}
 	g.dir = dirOfPath(filepath);
 	if (g.doc.contains("buffers"))
 		for (const json &b : g.doc.at("buffers").items()) {
-			if (!b.contains("uri") || b.at("uri").asString().rfind("data:", 0) == 0) throw std::runtime_error("glTF: only external .bin buffers are supported (" + filepath + ")");
+			if (!b.contains("uri")) {
+				if (!haveGlbBin) throw std::runtime_error("glTF: buffer without uri outside a .glb (" + filepath + ")");
+				g.buffers.push_back(glbBin);
+				continue;
+			}
+			if (b.at("uri").asString().rfind("data:", 0) == 0) throw std::runtime_error("glTF: data: URIs are not supported (" + filepath + ")");
 			std::vector<unsigned char> data;
 			if (!readAll(g.dir + "/" + b.at("uri").asString(), data)) throw std::runtime_error("glTF: cannot open buffer " + b.at("uri").asString());
 			g.buffers.push_back(std::move(data));

@@ -728,14 +728,14 @@ bool SceneImporter::loadModel(const string &filepath, Scene::SharedPtr scene, co
 	// OptiX build; here a missing asset is an error the C entry point returns
 	if (!fileExists(path)) throw std::runtime_error("cannot open model " + path);
 	if (ext == ".obj") return loadObj(path, *scene, xf);
-	if (ext == ".gltf") return loadGltf(path, *scene, xf);
+	if (ext == ".gltf" || ext == ".glb") return loadGltf(path, *scene, xf);
 	if (ext == ".json") {
 		std::ifstream f(path);
 		std::stringstream ss;
 		ss << f.rdbuf();
 		return SceneImporter::import(json::parse(ss.str()), scene, dirOf(path));
 	}
-	return false; // .glb / FBX / pbrt / VDB importers are out of scope
+	return false; // FBX / pbrt / VDB importers are out of scope
 }
 
 bool SceneImporter::addEnvironment(const string &texture, Scene::SharedPtr scene, const string &baseDir) {

@@ -130,6 +130,46 @@ def test_gltf_fixture(tmp_path):
     assert np.allclose(xm, [[-2 * c, -2 * c, 0, 4], [2 * c, -2 * c, 0, 4], [0, 0, 2, 10]], atol=1e-6)
 
 
+def to_glb(d):
+    """Packs quad.gltf + quad.bin + base.png into quad.glb: JSON chunk + one BIN chunk, the image in a buffer view."""
+    doc = json.load(open(os.path.join(d, "quad.gltf")))
+    blob = open(os.path.join(d, "quad.bin"), "rb").read()
+    png = open(os.path.join(d, "base.png"), "rb").read()
+    doc["bufferViews"].append({"buffer": 0, "byteOffset": len(blob), "byteLength": len(png)})
+    doc["images"] = [{"bufferView": len(doc["bufferViews"]) - 1, "mimeType": "image/png"}]
+    blob += png + b"\0" * ((-len(png)) % 4)
+    doc["buffers"] = [{"byteLength": len(blob)}]
+    text = json.dumps(doc).encode()
+    text += b" " * ((-len(text)) % 4)
+    body = struct.pack("<II", len(text), 0x4E4F534A) + text + struct.pack("<II", len(blob), 0x004E4942) + blob
+    open(os.path.join(d, "quad.glb"), "wb").write(struct.pack("<III", 0x46546C67, 2, 12 + len(body)) + body)
+
+
+def test_binary_gltf_gives_the_same_scene(tmp_path):
+    make_fixture(str(tmp_path))
+    to_glb(str(tmp_path))
+    os.remove(tmp_path / "quad.bin"), os.remove(tmp_path / "base.png")  # the .glb is self-contained
+    a = app_for("quad.glb", tmp_path)
+    make_fixture(str(tmp_path))
+    b = app_for("quad.gltf", tmp_path)
+    da, db = a.scene_desc().contents, b.scene_desc().contents
+    assert (da.n_meshes, da.n_instances, da.n_materials) == (db.n_meshes, db.n_instances, db.n_materials) == (1, 2, 1)
+    for name, n in (("positions", 12), ("normals", 12), ("texcoords", 8)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(da.meshes[0], name), (n,)), np.ctypeslib.as_array(getattr(db.meshes[0], name), (n,)))
+    assert list(np.ctypeslib.as_array(da.meshes[0].indices, (6,))) == [0, 1, 2, 0, 2, 3]
+    ta, tb = da.materials[0].textures[0], db.materials[0].textures[0]
+    assert ta.valid == 1 and (ta.width, ta.height) == (2, 3)
+    assert np.array_equal(np.ctypeslib.as_array(ta.image, (24,)), np.ctypeslib.as_array(tb.image, (24,)))
+    for t in (0.5, 2.0):  # the animation samplers read the BIN chunk too
+        a.camera(t), b.camera(t)
+        assert list(a.scene_desc().contents.instances[0].transform) == list(b.scene_desc().contents.instances[0].transform)
+    bad = bytearray(open(tmp_path / "quad.glb", "rb").read())
+    bad[4] = 1  # version
+    open(tmp_path / "old.glb", "wb").write(bytes(bad))
+    with pytest.raises(RuntimeError, match="glb version"):
+        app_for("old.glb", tmp_path)
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/common/assets/scenes/anime-cube/AnimatedCube.gltf"), reason="reference checkout not present")
 def test_reference_animated_cube():
     app = app_for("common/assets/scenes/anime-cube/AnimatedCube.gltf", "/root/reference")
