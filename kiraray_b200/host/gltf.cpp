@@ -12,9 +12,10 @@
 //     roughness -> specular.g, metallic -> specular.b, MetallicRoughness shading model, emissive factor ->
 //     constant emissive texture, KHR_materials_transmission / _emissive_strength), textures from 8-bit PNG
 //     files (decoded with zlib; sRGB flag as Material::determineSrgb decides, texture.cpp:161-176);
-//   * LINEAR / STEP animation samplers on translation / rotation / scale of a mesh node whose ancestors do
-//     not move (src/core/animation.cpp): keys are resampled at the union of the channel times.
-// Anything else (skins, morph targets, cameras, animated ancestors, KTX / JPEG images) is reported or skipped
+//   * LINEAR / STEP animation samplers on translation / rotation / scale of any node (src/core/animation.cpp):
+//     keys are resampled at the union of the node's channel times; an instance carries the chain of its animated
+//     ancestors and the static transforms between them.
+// Anything else (skins, morph targets, cameras, KTX / JPEG images) is reported or skipped
 // with a message on stderr.
 #include "krr_host.h"
 
@@ -416,71 +417,92 @@ bool loadGltf(const string &filepath, Scene &scene, const float nodeTransform[12
 	// scene graph -> instances
 	struct Walk {
 		Gltf &g; Scene &scene; std::vector<std::vector<int>> &meshPrims; std::vector<std::vector<Channel>> &chan;
-		void node(int ni, const float parent[12], bool parentMoves) {
+		// keys of an animated node at the union of its channel times; every key holds the node's full local TRS
+		void buildKeys(int ni, const json &n, std::vector<float> &outTimes, std::vector<KrrSRT> &outKeys) {
+			std::set<float> times;
+			for (const Channel &c : chan[ni]) times.insert(c.times.begin(), c.times.end());
+			float t0[3] = {0, 0, 0}, q0[4] = {0, 0, 0, 1}, s0[3] = {1, 1, 1};
+			if (n.contains("translation")) for (int k = 0; k < 3; k++) t0[k] = (float) n.at("translation").at((size_t) k).asNumber();
+			if (n.contains("rotation")) for (int k = 0; k < 4; k++) q0[k] = (float) n.at("rotation").at((size_t) k).asNumber();
+			if (n.contains("scale")) for (int k = 0; k < 3; k++) s0[k] = (float) n.at("scale").at((size_t) k).asNumber();
+			for (float t : times) {
+				KrrSRT key;
+				memcpy(key.t, t0, 12), memcpy(key.q, q0, 16), memcpy(key.s, s0, 12);
+				for (const Channel &c : chan[ni]) {
+					const int w = c.path == "rotation" ? 4 : 3;
+					size_t k = 0;
+					while (k + 2 < c.times.size() && t >= c.times[k + 1]) k++;
+					float v[4];
+					if (c.times.size() == 1 || t <= c.times[0]) memcpy(v, &c.values[0], w * 4);
+					else if (t >= c.times.back()) memcpy(v, &c.values[(c.times.size() - 1) * w], w * 4);
+					else {
+						const float a = c.step ? 0.f : (t - c.times[k]) / (c.times[k + 1] - c.times[k]);
+						const float *A = &c.values[k * w], *B = &c.values[(k + 1) * w];
+						float dq = 0;
+						if (w == 4) for (int j = 0; j < 4; j++) dq += A[j] * B[j];
+						for (int j = 0; j < w; j++) v[j] = (1 - a) * A[j] + a * ((w == 4 && dq < 0) ? -B[j] : B[j]);
+					}
+					if (c.path == "translation") memcpy(key.t, v, 12);
+					else if (c.path == "scale") memcpy(key.s, v, 12);
+					else {
+						float len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+						for (int j = 0; j < 4; j++) key.q[j] = len > 0 ? v[j] / len : (j == 3 ? 1.f : 0.f);
+					}
+				}
+				outTimes.push_back(t);
+				outKeys.push_back(key);
+			}
+		}
+		// parent: world transform of the parent at rest; chain: the animated ancestors (root first); since: product of
+		// the static node transforms below the last animated ancestor (below the root when there is none)
+		void node(int ni, const float parent[12], const std::vector<AnimLink> &chain, const float since[12]) {
 			const json &n = g.doc.at("nodes").at((size_t) ni);
 			float local[12], world[12];
 			nodeLocal(n, local);
 			mul12(parent, local, world);
 			const bool moves = !chan[ni].empty();
+			std::vector<float> times;
+			std::vector<KrrSRT> keys;
+			if (moves) buildKeys(ni, n, times, keys);
 			if (n.contains("mesh")) {
 				for (int mi : meshPrims[(size_t) n.at("mesh").asNumber()]) {
 					HostInstance in;
 					in.mesh = mi;
 					memcpy(in.transform, world, sizeof world);
-					if (moves && !parentMoves) {
-						// keys at the union of the channel times; every key holds the node's full local TRS
-						std::set<float> times;
-						for (const Channel &c : chan[ni]) times.insert(c.times.begin(), c.times.end());
-						float t0[3] = {0, 0, 0}, q0[4] = {0, 0, 0, 1}, s0[3] = {1, 1, 1};
-						if (n.contains("translation")) for (int k = 0; k < 3; k++) t0[k] = (float) n.at("translation").at((size_t) k).asNumber();
-						if (n.contains("rotation")) for (int k = 0; k < 4; k++) q0[k] = (float) n.at("rotation").at((size_t) k).asNumber();
-						if (n.contains("scale")) for (int k = 0; k < 3; k++) s0[k] = (float) n.at("scale").at((size_t) k).asNumber();
-						for (float t : times) {
-							KrrSRT key;
-							memcpy(key.t, t0, 12), memcpy(key.q, q0, 16), memcpy(key.s, s0, 12);
-							for (const Channel &c : chan[ni]) {
-								const int w = c.path == "rotation" ? 4 : 3;
-								size_t k = 0;
-								while (k + 2 < c.times.size() && t >= c.times[k + 1]) k++;
-								float v[4];
-								if (c.times.size() == 1 || t <= c.times[0]) memcpy(v, &c.values[0], w * 4);
-								else if (t >= c.times.back()) memcpy(v, &c.values[(c.times.size() - 1) * w], w * 4);
-								else {
-									const float a = c.step ? 0.f : (t - c.times[k]) / (c.times[k + 1] - c.times[k]);
-									const float *A = &c.values[k * w], *B = &c.values[(k + 1) * w];
-									float dq = 0;
-									if (w == 4) for (int j = 0; j < 4; j++) dq += A[j] * B[j];
-									for (int j = 0; j < w; j++) v[j] = (1 - a) * A[j] + a * ((w == 4 && dq < 0) ? -B[j] : B[j]);
-								}
-								if (c.path == "translation") memcpy(key.t, v, 12);
-								else if (c.path == "scale") memcpy(key.s, v, 12);
-								else {
-									float len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
-									for (int j = 0; j < 4; j++) key.q[j] = len > 0 ? v[j] / len : (j == 3 ? 1.f : 0.f);
-								}
-							}
-							in.animTimes.push_back(t);
-							in.animKeys.push_back(key);
-						}
-						memcpy(in.animParent, parent, sizeof in.animParent);
+					if (moves || !chain.empty()) {
+						in.animAncestors = chain;
+						if (moves) { // world = chain * since * SRT(t)
+							in.animTimes = times, in.animKeys = keys;
+							memcpy(in.animParent, since, sizeof in.animParent);
+						} else mul12(since, local, in.animParent); // world = chain * (since * local)
 						scene.animated = true;
-					} else if (moves || parentMoves)
-						fprintf(stderr, "glTF: node %d: animated ancestors are not supported, instance left static\n", ni);
+					}
 					scene.instances.push_back(in);
 				}
 			}
-			if (n.contains("children"))
-				for (const json &c : n.at("children").items()) node((int) c.asNumber(), world, parentMoves || moves);
+			if (n.contains("children")) {
+				std::vector<AnimLink> below = chain;
+				float sinceBelow[12];
+				if (moves) {
+					AnimLink link;
+					memcpy(link.pre, since, sizeof link.pre);
+					link.times = times, link.keys = keys;
+					below.push_back(std::move(link));
+					const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+					memcpy(sinceBelow, I, sizeof I);
+				} else mul12(since, local, sinceBelow);
+				for (const json &c : n.at("children").items()) node((int) c.asNumber(), world, below, sinceBelow);
+			}
 		}
 	} walk{g, scene, meshPrims, nodeChannels};
 	if (g.doc.contains("scenes")) {
 		const size_t si = g.doc.contains("scene") ? (size_t) g.doc.at("scene").asNumber() : 0;
-		for (const json &r : g.doc.at("scenes").at(si).at("nodes").items()) walk.node((int) r.asNumber(), nodeTransform, false);
+		for (const json &r : g.doc.at("scenes").at(si).at("nodes").items()) walk.node((int) r.asNumber(), nodeTransform, {}, nodeTransform);
 	} else if (g.doc.contains("nodes")) { // no scene: every node that is nobody's child is a root
 		std::vector<char> isChild(g.doc.at("nodes").size(), 0);
 		for (const json &n : g.doc.at("nodes").items())
 			if (n.contains("children")) for (const json &c : n.at("children").items()) isChild[(size_t) c.asNumber()] = 1;
-		for (size_t i = 0; i < isChild.size(); i++) if (!isChild[i]) walk.node((int) i, nodeTransform, false);
+		for (size_t i = 0; i < isChild.size(); i++) if (!isChild[i]) walk.node((int) i, nodeTransform, {}, nodeTransform);
 	}
 	scene.touch();
 	return true;

@@ -41,6 +41,13 @@ struct HostMesh {
 	float Le[3]	 = {0, 0, 0};
 };
 
+// one animated ancestor of an instance: world = ... * pre * SRT(t) * ...
+struct AnimLink {
+	float pre[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}; // static transforms between the previous animated node and this one
+	std::vector<float> times;
+	std::vector<KrrSRT> keys;
+};
+
 struct HostInstance {
 	int mesh = 0;
 	float transform[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -50,6 +57,8 @@ struct HostInstance {
 	std::vector<KrrSRT> animKeys;
 	// transform of the (static) ancestors of an animated node: world = animParent * SRT(t)
 	float animParent[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+	// animated ancestors, root first: world = prod(a.pre * SRT_a(t)) * animParent * [SRT(t) if the node has keys]
+	std::vector<AnimLink> animAncestors;
 };
 
 struct HostMaterial {

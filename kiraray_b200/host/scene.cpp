@@ -83,23 +83,32 @@ bool Scene::update(size_t frameIndex, double t) {
 	updatedInstances.clear();
 	if (animated) {
 		// keyframe animation of instance SRTs (src/core/animation.cpp: linear interpolation, clamp)
-		for (size_t i = 0; i < instances.size(); i++) {
-			HostInstance &in = instances[i];
-			if (in.animTimes.size() < 2) continue;
-			float tt = (float) t;
+		// SRT keys at time t: linear interpolation, clamped at both ends; rotations by nlerp along the shortest arc
+		auto evalKeys = [](const std::vector<float> &times, const std::vector<KrrSRT> &keys, float tt, float m[12]) {
+			if (times.size() == 1) { srtToMat(keys[0], m); return; } // a single key: constant
 			size_t k = 0;
-			while (k + 2 < in.animTimes.size() && tt >= in.animTimes[k + 1]) k++;
-			float t0 = in.animTimes[k], t1 = in.animTimes[k + 1];
+			while (k + 2 < times.size() && tt >= times[k + 1]) k++;
+			float t0 = times[k], t1 = times[k + 1];
 			float a	 = t1 > t0 ? std::min(1.f, std::max(0.f, (tt - t0) / (t1 - t0))) : 0.f;
-			const KrrSRT &A = in.animKeys[k], &B = in.animKeys[k + 1];
+			const KrrSRT &A = keys[k], &B = keys[k + 1];
 			KrrSRT s;
 			for (int c = 0; c < 3; c++) s.s[c] = (1 - a) * A.s[c] + a * B.s[c], s.t[c] = (1 - a) * A.t[c] + a * B.t[c];
-			// nlerp with shortest arc
 			float d = A.q[0] * B.q[0] + A.q[1] * B.q[1] + A.q[2] * B.q[2] + A.q[3] * B.q[3];
 			for (int c = 0; c < 4; c++) s.q[c] = (1 - a) * A.q[c] + a * (d < 0 ? -B.q[c] : B.q[c]);
-			float m[12];
 			srtToMat(s, m);
-			mul12(in.animParent, m, m);
+		};
+		for (size_t i = 0; i < instances.size(); i++) {
+			HostInstance &in = instances[i];
+			const bool own = !in.animTimes.empty() && (in.animTimes.size() >= 2 || !in.animAncestors.empty());
+			if (!own && in.animAncestors.empty()) continue;
+			float m[12], k[12];
+			identity12(m);
+			for (const AnimLink &a : in.animAncestors) { // animated ancestors, root first
+				mul12(m, a.pre, m);
+				if (!a.times.empty()) { evalKeys(a.times, a.keys, (float) t, k); mul12(m, k, m); }
+			}
+			mul12(m, in.animParent, m);
+			if (own) { evalKeys(in.animTimes, in.animKeys, (float) t, k); mul12(m, k, m); }
 			if (memcmp(m, in.transform, sizeof m)) {
 				memcpy(in.transform, m, sizeof m);
 				updatedInstances.push_back((int32_t) i);

@@ -130,6 +130,34 @@ def test_gltf_fixture(tmp_path):
     assert np.allclose(xm, [[-2 * c, -2 * c, 0, 4], [2 * c, -2 * c, 0, 4], [0, 0, 2, 10]], atol=1e-6)
 
 
+def test_animated_ancestors(tmp_path):
+    """An animated root above a static node above an animated mesh node and a static mesh node: every instance
+    follows the chain  root(t) * static * [node(t)]  (the reference animates scene-graph nodes, animation.cpp)."""
+    make_fixture(str(tmp_path))
+    doc = json.load(open(tmp_path / "quad.gltf"))
+    a_t, a_tr, a_rot = 4, 5, 6  # accessors of make_fixture: times [0, 1, 3], translations, rotations 0 / 90 / 180 degrees about z
+    doc["nodes"] = [{"name": "R", "children": [1]},
+                    {"name": "M", "translation": [0, 1, 0], "scale": [2, 2, 2], "children": [2, 3]},
+                    {"name": "C", "mesh": 0, "translation": [1, 0, 0]},
+                    {"name": "S", "mesh": 0, "translation": [0, 0, 3]}]
+    doc["animations"] = [{"channels": [{"sampler": 0, "target": {"node": 0, "path": "translation"}}, {"sampler": 1, "target": {"node": 2, "path": "rotation"}}],
+                          "samplers": [{"input": a_t, "output": a_tr, "interpolation": "LINEAR"}, {"input": a_t, "output": a_rot, "interpolation": "LINEAR"}]}]
+    json.dump(doc, open(tmp_path / "chain.gltf", "w"))
+    app = app_for("chain.gltf", tmp_path)
+    c = np.sqrt(0.5)
+
+    def xf(i):
+        return np.array(list(app.scene_desc().contents.instances[i].transform)).reshape(3, 4)
+    app.camera(0.5)
+    assert np.allclose(xf(0), [[2 * c, -2 * c, 0, 3], [2 * c, 2 * c, 0, 1], [0, 0, 2, 0]], atol=1e-6)
+    assert np.allclose(xf(1), [[2, 0, 0, 1], [0, 2, 0, 1], [0, 0, 2, 6]], atol=1e-6)
+    app.camera(2.0)
+    assert np.allclose(xf(0), [[-2 * c, -2 * c, 0, 4], [2 * c, -2 * c, 0, 3], [0, 0, 2, 0]], atol=1e-6)
+    assert np.allclose(xf(1), [[2, 0, 0, 2], [0, 2, 0, 3], [0, 0, 2, 6]], atol=1e-6)
+    app.camera(10.0)  # clamped at the last key: root at (2, 4, 0), 180 degrees
+    assert np.allclose(xf(0), [[-2, 0, 0, 4], [0, -2, 0, 5], [0, 0, 2, 0]], atol=1e-6)
+
+
 def to_glb(d):
     """Packs quad.gltf + quad.bin + base.png into quad.glb: JSON chunk + one BIN chunk, the image in a buffer view."""
     doc = json.load(open(os.path.join(d, "quad.gltf")))
