@@ -25,12 +25,14 @@ KRR_DEV float xmul(float a, float b) { return __fmul_rn(a, b); }
 KRR_DEV float xadd(float a, float b) { return __fadd_rn(a, b); }
 KRR_DEV float xsub(float a, float b) { return __fsub_rn(a, b); }
 KRR_DEV float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+KRR_DEV float xrcp(float a) { return __frcp_rn(a); } // == __fdiv_rn(1.f, a): both are the correctly rounded reciprocal
 KRR_DEV float xsqrt(float a) { return __fsqrt_rn(a); }
 #else
 inline float xmul(float a, float b) { return a * b; }
 inline float xadd(float a, float b) { return a + b; }
 inline float xsub(float a, float b) { return a - b; }
 inline float xdiv(float a, float b) { return a / b; }
+inline float xrcp(float a) { return 1.f / a; }
 inline float xsqrt(float a) { return sqrtf(a); }
 #endif
 

@@ -150,13 +150,17 @@ void nodeXf(const XNode &nd, float time, Xf &m, Xf &inv) {
 	for (int i = 0; i < 10; i++) { float d = b[i] - a[i]; d = f * d; v[i] = a[i] + d; }
 	float l0 = v[3] * v[3], l1 = v[4] * v[4], l2 = v[5] * v[5], l3 = v[6] * v[6];
 	float len = std::sqrt((l0 + l1) + (l2 + l3));
-	float x = v[3] / len, y = v[4] / len, z = v[5] / len, w = v[6] / len;
+	/* one correctly rounded reciprocal and four products instead of four divisions (and three reciprocals for
+	 * the nine entries of the inverse below): the GPU evaluates this per ray and instance entry */
+	float rl = 1.f / len;
+	float x = v[3] * rl, y = v[4] * rl, z = v[5] * rl, w = v[6] * rl;
+	float rs[3] = {1.f / v[0], 1.f / v[1], 1.f / v[2]};
 	float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
 	float R[9] = {1.f - 2.f * (yy + zz), 2.f * (xy - wz), 2.f * (xz + wy),
 				  2.f * (xy + wz), 1.f - 2.f * (xx + zz), 2.f * (yz - wx),
 				  2.f * (xz - wy), 2.f * (yz + wx), 1.f - 2.f * (xx + yy)};
 	for (int r = 0; r < 3; r++) {
-		for (int c = 0; c < 3; c++) m.m[r * 4 + c] = R[r * 3 + c] * v[c], inv.m[r * 4 + c] = R[c * 3 + r] / v[r];
+		for (int c = 0; c < 3; c++) m.m[r * 4 + c] = R[r * 3 + c] * v[c], inv.m[r * 4 + c] = R[c * 3 + r] * rs[r];
 		m.m[r * 4 + 3] = v[7 + r];
 	}
 	for (int r = 0; r < 3; r++) {
