@@ -318,21 +318,32 @@ def main():
         cands = [k for k in ("closest", "scatter", "shadow", "trace") if stages[k]["launches"]]
         dom = max(cands, key=lambda k: stages[k]["ms"])
         names = {"closest": "k_trace_closest", "scatter": "k_scatter<Disney>", "shadow": "k_trace_shadow", "trace": "k_trace_fused"}
-        if dom == "trace":
-            c0 = st["closest_by_depth"][0] // max(1, args.spp) * args.spp  # depth-0 closest rays run in k_trace_closest
-            n_c, n_s = st["closest_rays"] - st["closest_by_depth"][0], st["shadow_rays"]
-            units, dom_bytes = n_c + n_s, n_c * STAGE_BYTES["closest"] + n_s * STAGE_BYTES["shadow"]
-        else:
-            units = {"closest": st["closest_rays"], "scatter": st["scatter_items"], "shadow": st["shadow_rays"]}[dom]
-            dom_bytes = units * STAGE_BYTES[dom]
+        fused = stages["trace"]["launches"] > 0  # then k_trace_closest only runs depth 0
+
+        def stage_units(k):
+            if k == "trace":
+                n_c, n_s = st["closest_rays"] - st["closest_by_depth"][0], st["shadow_rays"]
+                return n_c + n_s, n_c * STAGE_BYTES["closest"] + n_s * STAGE_BYTES["shadow"]
+            u = {"closest": st["closest_by_depth"][0] if fused else st["closest_rays"], "scatter": st["scatter_items"], "shadow": st["shadow_rays"]}[k]
+            return u, u * STAGE_BYTES[k]
+        units, dom_bytes = stage_units(dom)
         total_ms = sum(v["ms"] for v in stages.values())
         dom_gbs = dom_bytes / (stages[dom]["ms"] * 1e-3) / 1e9
+        # the same figure for every traced / shaded stage (the two big ones are within a few per cent of each
+        # other, so which one is "dominant" can change from run to run)
+        per_stage = {}
+        for k in cands:
+            u, b = stage_units(k)
+            gbs = b / (stages[k]["ms"] * 1e-3) / 1e9
+            per_stage[names[k]] = {"achieved": gbs, "frac": gbs / peak, "share": stages[k]["ms"] / total_ms if total_ms else 0,
+                                   "units_per_step": u, "launches_per_step": stages[k]["launches"], "traffic": load_traffic(names[k].split("<")[0])}
         roofline = {"bound": "hbm", "kernel": names[dom],
                     "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom_gbs / peak,
                     "traffic": load_traffic(names[dom].split("<")[0]),
                     "algorithmic_bytes_per_unit": dom_bytes / max(1, units), "units_per_step": units, "launches_per_step": stages[dom]["launches"],
                     "avg_launch_ms": stages[dom]["ms"] / max(1, stages[dom]["launches"]),
-                    "stage_share": {k: (v["ms"] / total_ms if total_ms else 0) for k, v in stages.items()},
+                    "stage_share": {k: (v["ms"] / total_ms if total_ms else 0) for k, v in stages.items()}, "per_stage": per_stage,
+                    "note": "algorithmic bytes = the reference's SoA queue layout + geometry lower bound (SURVEY 8d); a stage that moves less than that layout (depth-0 ray items here hold origin + direction only) can exceed frac 1",
                     "pipeline_achieved": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world) / peak}
         cpu = None
         if not args.no_cpu_baseline:
