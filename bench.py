@@ -115,18 +115,21 @@ def make_app(spp):
     return app
 
 
-def cpu_reference_rate(app, spp, rows, threads=0):
-    """Times the CPU oracle on a band of `rows` image rows of the workload.  Returns (Mrays/s, info)."""
+def cpu_reference_rate(app, spp, rows, threads=0, frames=1):
+    """Times the CPU oracle on a band of `rows` image rows of the workload, `frames` frames.  Returns (Mrays/s, info)."""
     import oracle_binding as ob
     kind = "reference" if ob.available("reference") else "port"
     orc = ob.Oracle(app.scene_desc(), kind)
     cam = app.camera()
     r0 = (H - rows) // 2
-    res = orc.render(cam, W, H, frame_index=1, spp=spp, max_depth=MAX_DEPTH, rr=RR, use_bvh=True, threads=threads, rows=(r0, r0 + rows))
-    rays = res["stats"]["closest_rays"] + res["stats"]["shadow_rays"]
+    rays, seconds = 0, 0.0
+    for f in range(frames):
+        res = orc.render(cam, W, H, frame_index=1 + f, spp=spp, max_depth=MAX_DEPTH, rr=RR, use_bvh=True, threads=threads, rows=(r0, r0 + rows))
+        rays += res["stats"]["closest_rays"] + res["stats"]["shadow_rays"]
+        seconds += res["seconds"]
     orc.close()
-    return rays / res["seconds"] / 1e6, {"kind": kind, "rays": rays, "seconds": res["seconds"],
-                                         "sample": f"rows {r0}..{r0 + rows} of {H} ({rows * W} pixels), {spp} spp, 1 frame"}
+    return rays / seconds / 1e6, {"kind": kind, "rays": rays, "seconds": seconds,
+                                  "sample": f"rows {r0}..{r0 + rows} of {H} ({rows * W} pixels), {spp} spp, {frames} frame{'s' if frames > 1 else ''}"}
 
 
 _STDOUT_FD = None
@@ -179,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--spp", type=int, default=8, help="samples per pixel per frame (one step = one frame)")
     ap.add_argument("--ref-rows", type=int, default=0, help="rows of the frame the CPU reference renders per step")
+    ap.add_argument("--ref-frames", type=int, default=6, help="frames the cpu_baseline leg renders (full frame each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--params", default="", help="extra pass parameters as JSON (tuning switches, e.g. '{\"pdl\": false}')")
     ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
@@ -347,7 +351,7 @@ def main():
                     "pipeline_achieved": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * BYTES_PER_RAY / 1e9 / max(1, world) / peak}
         cpu = None
         if not args.no_cpu_baseline:
-            v, info = cpu_reference_rate(app, args.spp, args.ref_rows or 540)  # half the frame: ~10-20 s
+            v, info = cpu_reference_rate(app, args.spp, args.ref_rows or H, frames=args.ref_frames)  # ~10-15 s of CPU work on 16 cores
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}
         spp_s = args.spp * args.steps * (pixels / (W * H)) / (ms * 1e-3)  # full-frame samples per pixel per second, all ranks
         line = {"metric": "Mrays/s (primary+shadow+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
