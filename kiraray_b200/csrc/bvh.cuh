@@ -7,6 +7,13 @@
 //   * 80-byte nodes: an anchor point + per-axis power-of-two scale, and 8 children whose boxes are
 //     quantised to 8 bits per plane (conservatively: lo rounded down, hi rounded up).  One node is
 //     five 16-byte loads.
+//   * children sit in OCTANT-ORDERED slots (the builder puts the child that lies towards (-x,-y,-z) of
+//     the node centre into slot 0, ... towards (+x,+y,+z) into slot 7), so "slot XOR ray octant" is a
+//     front-to-back priority: a node test produces ONE 32-bit hit mask (internal children in priority
+//     order in the top byte, leaf triangles in the low 24 bits) instead of eight sorted stack entries.
+//     A stack entry is a node GROUP (child base + hit mask) or a triangle group (first triangle + hit
+//     bits): one 8-byte push per visited node at most (after Ylitie, Karras, Laine: "Efficient
+//     incoherent ray traversal on GPUs through compressed wide BVHs", HPG 2017).
 //   * BLAS nodes live in OBJECT space of their mesh; an instance is entered by transforming the ray
 //     with the instance's inverse 3x4 (t stays the world-space parameter, the direction is not
 //     renormalised), exactly as the intersection spec in oracle/driver.cpp states.
@@ -15,8 +22,7 @@
 //     result does not depend on traversal order -> first-hit ids are bit-exact against the oracle's
 //     brute-force loop.
 //   * warp-cooperative traversal (see Traverser below): phase-aligned stepping, shared-memory short
-//     stack, hit children sorted by entry distance with a sorting network, persistent warps that
-//     refill finished lanes from the queue.
+//     stack, persistent warps that refill finished lanes from the queue.
 #pragma once
 #include "krr_math.cuh"
 #include "scene.cuh"
@@ -26,10 +32,15 @@ namespace krr {
 struct __align__(16) Node8 {
 	float ox, oy, oz;		  // anchor (min corner of the node box)
 	uint8_t ex, ey, ez;		  // biased exponents: child plane = o + q * 2^(e-127)
-	uint8_t imask;			  // bit i: child i is an internal node
-	uint32_t childBase;		  // first internal child; child i -> childBase + popc(imask & ((1<<i)-1))
-	uint32_t primBase;		  // first primitive of the leaf children (BLAS: triangle pool, TLAS: instance list)
-	uint8_t meta[8];		  // leaf child: (count << 5) | offset from primBase; 0 = empty / internal
+	uint8_t imask;			  // bit i: the child in slot i is an internal node
+	uint32_t childBase;		  // first internal child; slot i -> childBase + popc(imask & ((1<<i)-1))
+	uint32_t primBase;		  // first primitive of the leaf children (BLAS: triangle pool; TLAS: 8 instance ids, slot-major)
+	// per slot: 0 = empty; internal child: 0x20 | (24 + slot); BLAS leaf: unary triangle count (1, 3, 7) << 5 |
+	// offset of its first triangle from primBase (0..21); TLAS leaf (one instance): 0x20 | slot.  The node
+	// test turns a hit slot into `(meta >> 5) << (meta & 31)` -- bits 24..31 internal children, bits 0..23
+	// triangles / instances -- after XOR-ing the slot number with the ray octant where the bit position is a
+	// traversal priority (internal children, TLAS instances).
+	uint8_t meta[8];
 	uint8_t qlo[3][8], qhi[3][8];
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
@@ -41,7 +52,7 @@ struct BvhTri { float4 v0, e1, e2; };
 struct BvhDev {
 	const Node8 *nodes;	   // node pool: TLAS nodes first, then every mesh's BLAS
 	const BvhTri *tris;	   // triangle pool, leaf order per mesh
-	const int32_t *tlasInst; // instance ids referenced by TLAS leaves
+	const int32_t *tlasInst; // instance ids referenced by TLAS leaves: 8 per TLAS node, indexed by child slot
 	int32_t tlasRoot;
 	int32_t nInstances;
 	const XformNodeRec *xnodes; // motion blur: transform chains + SRT key pool (motion.cuh), null otherwise
@@ -79,14 +90,8 @@ KRR_HD bool triIntersect(V3 o, V3 d, V3 v0, V3 v1, V3 v2, float tmax, float &t, 
 #ifndef KRR_TRI_RCP
 #define KRR_TRI_RCP 1
 #endif
-#ifndef KRR_LEAF_PAIR
-#define KRR_LEAF_PAIR 1
-#endif
 #ifndef KRR_LEAF_WIDTH
 #define KRR_LEAF_WIDTH 2
-#endif
-#ifndef KRR_LEAF_PAIR_TREE
-#define KRR_LEAF_PAIR_TREE 0
 #endif
 // 1 / det, correctly rounded.  On the device __frcp_rn: IEEE round-to-nearest of the reciprocal, i.e. the
 // same float as __fdiv_rn(1.f, det) for every input, in about half the instructions
@@ -133,46 +138,47 @@ KRR_HD bool betterHit(float t, int inst, int prim, const Hit &h) {
 	return prim < h.prim;
 }
 
-#ifdef __CUDACC__
-// ---- traversal state machine ---------------------------------------------------------------------
-// One lane = one ray.  The traversal is written as a STEP function so that the stage kernels can
-// run it warp-cooperatively: every trip of the warp's loop executes the three phases
-//     [enter instance] -> [wide node: 8 slab tests, sorting network, push] -> [leaf: triangle tests]
-// under per-lane predicates, so lanes that are in the same phase execute it together, and the
-// kernel refills lanes whose ray has terminated from the queue (persistent warps, one atomicAdd per
-// refill) instead of letting them idle until the slowest ray of the warp is done.
-//
-// Stack: entries are 32-bit tagged words + the entry distance of the box (for culling at pop time
-// once a closer hit is known).  The first kShortStack entries of every lane live in SHARED memory
-// (slot-major, so a warp's accesses are conflict-free); deeper entries spill to local memory.
-//   node     : index into the node pool                                     (bits 31,30 = 00)
-//   leaf     : kLeafFlag | (count-1) << 26 | first triangle                 (bits 31,30 = 01)
-//   instance : kInstFlag | instance id  (TLAS leaves hold ONE instance)      (bits 31,30 = 10)
-//   flat BLAS: kFlatFlag | index into BvhDev::flats (only ever a BLAS root)  (bits 31,30 = 11, != empty)
-#ifndef KRR_SHORT_STACK
-#define KRR_SHORT_STACK 12
-#endif
-constexpr int kShortStack  = KRR_SHORT_STACK;
-constexpr int kLocalStack  = 128 - KRR_SHORT_STACK; // 8-wide nodes defer up to 7 siblings per level: 128 entries cover TLAS + BLAS depths of ~18 levels
-constexpr int kStackSize   = kShortStack + kLocalStack;
-constexpr int kTraceBlock  = 128;
-constexpr uint32_t kInstFlag = 0x80000000u, kLeafFlag = 0x40000000u, kFlatFlag = 0xc0000000u, kEmptyEntry = 0xffffffffu;
+constexpr uint32_t kFlatFlag = 0xc0000000u, kEmptyEntry = 0xffffffffu;
 KRR_HD bool isFlatEntry(uint32_t e) { return (e >> 30) == 3u && e != kEmptyEntry; }
 
+#ifdef __CUDACC__
+// ---- traversal state machine ---------------------------------------------------------------------
+// One lane = one ray.  Per-lane state is two GROUPS (x = base index, y = bit mask):
+//   ng: children of the last tested node that the ray hit and that are internal nodes.  y bits 24..31 = hit
+//       children in traversal priority (bit 24 + (slot ^ octant)), y bits 0..7 = the node's imask (needed to turn
+//       a slot into a child index); x = the node's childBase.
+//   tg: hit leaf primitives.  In a BLAS: x = the node's primBase, y bits 0..23 = triangles primBase + bit.  In
+//       the TLAS: y bit (slot ^ octant) = the instance tlasInst[primBase + slot].  A flat BLAS (triangle list)
+//       is the special group y = 0x80000000 | count, x = first triangle; it is consumed at once, never pushed.
+// The traversal is written as a STEP function (trip) so that the stage kernels can run it warp-cooperatively:
+// every trip executes the phases
+//     [pop] -> [enter instance] -> [wide node: 8 slab tests -> hit mask] -> [triangle tests]
+// under per-lane predicates, so lanes that are in the same phase execute it together, and the kernel refills
+// lanes whose ray has terminated from the queue (persistent warps, one atomicAdd per refill) instead of
+// letting them idle until the slowest ray of the warp is done.
+//
+// Stack: 8-byte entries (a node group whose top byte is non-zero, or a triangle / instance group whose top
+// byte is zero).  The first kShortStack entries of every lane live in SHARED memory (slot-major, so a warp's
+// accesses are conflict-free); deeper entries spill to local memory.  A node pushes at most ONE entry (its
+// remaining hit children), so the depth is the tree depth, not 7x the tree depth.
+#ifndef KRR_SHORT_STACK
+#define KRR_SHORT_STACK 8
+#endif
+constexpr int kShortStack  = KRR_SHORT_STACK;
+constexpr int kLocalStack  = 64 - KRR_SHORT_STACK; // one entry per BLAS level, two per TLAS level
+constexpr int kStackSize   = kShortStack + kLocalStack;
+constexpr int kTraceBlock  = 128;
+
 struct TraceSmem {
-	uint32_t id[kShortStack][kTraceBlock];
-	float tn[kShortStack][kTraceBlock];
+	uint2 st[kShortStack][kTraceBlock];
 };
 // Spill part of the stack (local memory).  Deliberately NOT a member of Traverser: a dynamically
 // indexed array inside the struct keeps the WHOLE struct in local memory (the compiler cannot split an
 // aggregate that is indexed with a run-time value), and the ray state would be loaded and stored
 // around every phase instead of living in registers.
 template <bool ANY> struct LocalStack {
-	uint32_t id[kLocalStack];
-	float tn[ANY ? 1 : kLocalStack];
+	uint2 st[kLocalStack];
 };
-
-#define KRR_CSWAP(a, b) { uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
 
 // world ray -> object space of a moving instance (kept out of line: static scenes never pay its registers)
 static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float time, V3 o, V3 d, V3 &ro, V3 &rd) {
@@ -181,8 +187,17 @@ static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float
 	ro = xfPointX(inv, o), rd = xfVectorX(inv, d);
 }
 
+// triangle tests a lane runs per trip when it holds a triangle group (the rest waits for the next trip)
+#ifndef KRR_TRI_PER_TRIP
+#define KRR_TRI_PER_TRIP 2
+#endif
+// triangle phase of a voted trip runs when at least this many lanes hold triangles, or no lane has node work
+#ifndef KRR_TRI_VOTE
+#define KRR_TRI_VOTE 6
+#endif
+
 // MOTION = false compiles the SRT-chain path out (static scenes keep their register budget)
-// PAIR: the scene is one flat triangle list and leaf() walks it in branch-free pairs (see leaf())
+// PAIR: the scene is one flat triangle list and the whole traversal is a walk over it in branch-free pairs
 template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	// ray
 	V3 o, d;	  // world space
@@ -191,7 +206,8 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	float tmax, time;
 	Hit best;
 	// control
-	uint32_t cur;
+	uint2 ng, tg;
+	uint32_t octinv4; // (x >= 0 ? 4 : 0) | (y >= 0 ? 2 : 0) | (z >= 0 ? 1 : 0) of the current-space direction, in every byte
 	int sp, curInst, blasBase;
 	int overflow;
 	using LStack = LocalStack<ANY>;
@@ -201,23 +217,33 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	// one sign (outside: the box is culled), all finite.  With 1/0 = inf they were NaN, the axis was dropped from
 	// the test, and a ray parallel to two axes could only be culled along its own direction: it walked every
 	// node in front of it (46 ms for one such ray in the 20 M-triangle scene).
-	KRR_DEV void setIdir() {
+	KRR_DEV void setSpace() {
 		auto safe = [](float x) { return fabsf(x) >= 1e-20f ? x : copysignf(1e-20f, x); };
-		idir = mk3(1.f / safe(rd.x), 1.f / safe(rd.y), 1.f / safe(rd.z));
+		idir	= mk3(1.f / safe(rd.x), 1.f / safe(rd.y), 1.f / safe(rd.z));
+		octinv4 = ((idir.x >= 0.f ? 4u : 0u) | (idir.y >= 0.f ? 2u : 0u) | (idir.z >= 0.f ? 1u : 0u)) * 0x01010101u;
+	}
+	// start at a BLAS root: a tree (node group with the single pseudo-child `root`) or a flat triangle list
+	KRR_DEV void enterRoot(const BvhDev &bvh, uint32_t root) {
+		if (isFlatEntry(root)) {
+			const int2 fr = __ldg(bvh.flats + (root & 0x3fffffffu));
+			tg = make_uint2((uint32_t) fr.x, 0x80000000u | (uint32_t) fr.y), ng = make_uint2(0u, 0u);
+		} else ng = make_uint2(root, 0x80000000u), tg = make_uint2(0u, 0u); // imask 0: child index = root + 0
 	}
 	KRR_DEV void begin(const BvhDev &bvh, V3 o_, V3 d_, float tmax_, float time_ = 0.f) {
 		o = ro = o_, d = rd = d_, tmax = tmax_, time = time_;
-		setIdir();
+		setSpace();
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
-		cur = (uint32_t) bvh.tlasRoot, sp = 0, curInst = -1, blasBase = -1, overflow = 0;
-		if (bvh.mergedOnly) {
-			cur = (uint32_t) bvh.mergedRoot, curInst = bvh.mergedInst, blasBase = 0; // world == object space
+		sp = 0, curInst = -1, blasBase = -1, overflow = 0;
+		ng = make_uint2((uint32_t) bvh.tlasRoot, 0x80000000u), tg = make_uint2(0u, 0u);
+		if (PAIR || bvh.mergedOnly) {
+			curInst = bvh.mergedInst, blasBase = 0; // world == object space
+			enterRoot(bvh, (uint32_t) bvh.mergedRoot);
 			const float t0x = (bvh.rootLo[0] - o_.x) * idir.x, t1x = (bvh.rootHi[0] - o_.x) * idir.x;
 			const float t0y = (bvh.rootLo[1] - o_.y) * idir.y, t1y = (bvh.rootHi[1] - o_.y) * idir.y;
 			const float t0z = (bvh.rootLo[2] - o_.z) * idir.z, t1z = (bvh.rootHi[2] - o_.z) * idir.z;
 			const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.f));
 			const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax_));
-			if (!(tn <= tf * 1.00001f + 1e-30f)) cur = kEmptyEntry, curInst = -1; // NaNs (0 * inf) are dropped by min / max
+			if (!(tn <= tf * 1.00001f + 1e-30f)) ng.y = tg.y = 0u; // NaNs (0 * inf) are dropped by min / max
 		}
 		// A ray with a NaN / infinite component or a zero direction cannot hit anything (every comparison of
 		// the triangle test fails, det == 0), but its slab tests cannot cull either: it would walk the WHOLE
@@ -231,161 +257,143 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		}
 #endif
 		const float chk = ((o_.x + o_.y) + o_.z) + ((d_.x + d_.y) + d_.z);
-		if (!(fabsf(chk) < 3.0e38f) || (d_.x == 0.f && d_.y == 0.f && d_.z == 0.f)) cur = kEmptyEntry, curInst = -1;
+		if (!(fabsf(chk) < 3.0e38f) || (d_.x == 0.f && d_.y == 0.f && d_.z == 0.f)) ng.y = tg.y = 0u;
 	}
-	KRR_DEV void push(TraceSmem &sm, LStack &ls, uint32_t e, float tn) {
-		if (sp < kShortStack) {
-			sm.id[sp][threadIdx.x] = e;
-			if (!ANY) sm.tn[sp][threadIdx.x] = tn;
-		} else if (sp < kStackSize) {
-			ls.id[sp - kShortStack] = e;
-			if (!ANY) ls.tn[sp - kShortStack] = tn;
-		} else { overflow = 1; return; }
+	KRR_DEV void push(TraceSmem &sm, LStack &ls, uint2 e) {
+		if (sp < kShortStack) sm.st[sp][threadIdx.x] = e;
+		else if (sp < kStackSize) ls.st[sp - kShortStack] = e;
+		else { overflow = 1; return; }
 		sp++;
 	}
-	KRR_DEV uint32_t pop(TraceSmem &sm, LStack &ls, float &tn) {
+	KRR_DEV uint2 pop(TraceSmem &sm, LStack &ls) {
 		--sp;
-		if (sp < kShortStack) {
-			if (!ANY) tn = sm.tn[sp][threadIdx.x];
-			return sm.id[sp][threadIdx.x];
-		}
-		if (!ANY) tn = ls.tn[sp - kShortStack];
-		return ls.id[sp - kShortStack];
+		return sp < kShortStack ? sm.st[sp][threadIdx.x] : ls.st[sp - kShortStack];
 	}
+	KRR_DEV bool hasNode() const { return (ng.y & 0xff000000u) != 0u; }
 
-	// What the lane has to do next: 0 = ray finished (result in `best`), 1 = enter an instance,
-	// 2 = wide node, 3 = leaf.  Pops the stack when the current entry is consumed.
-	enum { FINISHED = 0, ENTER = 1, NODE = 2, LEAF = 3 };
-	KRR_DEV int next(TraceSmem &sm, LStack &ls) {
-		while (cur == kEmptyEntry) {
-			if (curInst >= 0 && sp == blasBase) { // BLAS finished: back to world space
-				curInst = -1;
-				ro = o, rd = d;
-				setIdir();
-			}
-			if (sp == 0) return FINISHED;
-			float tn = 0.f;
-			cur = pop(sm, ls, tn);
-			// box entry beyond the closest hit so far (same slack as the slab test: for flat, axis-aligned
-			// geometry the rounded entry distance can exceed the exact hit distance by an ulp, and an
-			// equal-t candidate with a smaller (instance, primitive) must still be tested)
-			if (!ANY && tn > best.t * 1.0000010f + 1e-30f) cur = kEmptyEntry;
+	// The lane has used up both groups: leave the BLAS when its part of the stack is empty, then pop.
+	// Returns false when the traversal is finished (result in `best`).
+	KRR_DEV bool popNext(TraceSmem &sm, LStack &ls) {
+		if (curInst >= 0 && sp == blasBase) { // BLAS finished: back to world space
+			curInst = -1;
+			ro = o, rd = d;
+			setSpace();
 		}
-		return cur < kLeafFlag ? NODE : ((cur >> 30) == 2u ? ENTER : LEAF);
+		if (sp == 0) return false;
+		const uint2 e = pop(sm, ls);
+		if (e.y & 0xff000000u) ng = e, tg = make_uint2(0u, 0u);
+		else tg = e, ng = make_uint2(0u, 0u);
+		return true;
 	}
-	// ---- phase 1: enter an instance (object-space ray; t stays the world parameter) ----
-	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm) {
-		curInst = (int) (cur & 0x3fffffffu);
-		const InstRec &in = instances[curInst];
+	// ---- phase: enter the nearest hit instance of the TLAS group (object-space ray; t stays the world parameter) ----
+	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls) {
+		const uint32_t bit = 31u - (uint32_t) __clz(tg.y);
+		tg.y ^= 1u << bit;
+		const uint32_t slot = bit ^ (octinv4 & 7u);
+		const int inst		= __ldg(bvh.tlasInst + tg.x + slot);
+		// the TLAS-level groups wait on the stack below the BLAS part
+		if (hasNode()) push(sm, ls, ng);
+		if (tg.y) push(sm, ls, tg);
+		curInst = inst;
+		const InstRec &in = instances[inst];
 		if (MOTION && in.motion >= 0) movingRay(bvh, in.motion, time, o, d, ro, rd); // SRT motion chain at the ray's time
 		else ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
-		setIdir();
+		setSpace();
 		blasBase = sp;
-		cur		 = (uint32_t) in.blasRoot;
+		enterRoot(bvh, (uint32_t) in.blasRoot);
 	}
-	// ---- phase 2: wide node: 8 slab tests, sort by entry distance, push far-to-near ----
-	KRR_DEV void node(const BvhDev &bvh, TraceSmem &sm, LStack &ls) {
-		{
-			const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + cur);
-			float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-			uint32_t ew = __float_as_uint(n0.w);
-			float sx = __uint_as_float((ew & 0xff) << 23), sy = __uint_as_float(((ew >> 8) & 0xff) << 23),
-				  sz = __uint_as_float(((ew >> 16) & 0xff) << 23);
-			const uint32_t imask = ew >> 24;
-			const uint32_t childBase = __float_as_uint(n1.x), primBase = __float_as_uint(n1.y);
-			const uint32_t metaLo = __float_as_uint(n1.z), metaHi = __float_as_uint(n1.w);
-			// quantised planes: n2 = qlo[0][0..7], qlo[1][0..7]; n3 = qlo[2], qhi[0]; n4 = qhi[1], qhi[2]
-			const uint32_t q[12] = {__float_as_uint(n2.x), __float_as_uint(n2.y), __float_as_uint(n2.z), __float_as_uint(n2.w),
-									__float_as_uint(n3.x), __float_as_uint(n3.y), __float_as_uint(n3.z), __float_as_uint(n3.w),
-									__float_as_uint(n4.x), __float_as_uint(n4.y), __float_as_uint(n4.z), __float_as_uint(n4.w)};
-			// t = (o_node + q*s - o) * idir = q * (s*idir) + (o_node - o)*idir
-			const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
-			const float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
-			const float lim = best.t;
-			// The byte -> float conversions (48 per node, quarter-rate I2F) are replaced by a byte permute that
-			// drops q into the mantissa of 2^23: v = 2^23 + 256 q, and q*a + b = v*(a/256) + (b - 2^15 a) in one
-			// FMA.  b - 2^15 a is rounded once: error <= |a| / 512, i.e. 1/512 of a quantisation step, against
-			// the full step the builder pads every child plane with (quantize() in bvh_build.cu).
-			const float axs = ax * 0.00390625f, ays = ay * 0.00390625f, azs = az * 0.00390625f;
-			// Rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
-			// when the ray grazes an axis-aligned plane), PER AXIS: each slab interval is widened by its own
-			// bound, folded into the FMA constant of its near / far plane.  (One scalar bound for all axes let a
-			// ray that is nearly parallel to one axis -- huge a, b on that axis -- lose culling on the other two:
-			// the pixels of one image column / row took 13x longer than the rest of the frame together.)
-			// An axis the ray is exactly parallel to has a = inf and yields NaN distances, which min/max drop.
-			auto axisSlack = [](float a, float b) { return fabsf(a) < 3.0e38f ? (fabsf(b) + 255.f * fabsf(a)) * 2.4e-7f + fabsf(a) * 0.00390625f : 0.f; };
-			const float slx = axisSlack(ax, bx), sly = axisSlack(ay, by), slz = axisSlack(az, bz);
-			const float bx0 = fmaf(-32768.f, ax, bx), by0 = fmaf(-32768.f, ay, by), bz0 = fmaf(-32768.f, az, bz);
-			const float bxN = bx0 - slx, bxF = bx0 + slx, byN = by0 - sly, byF = by0 + sly, bzN = bz0 - slz, bzF = bz0 + slz;
-			// ray octant: which plane of a slab is entered first only depends on the sign of the direction, so
-			// the near / far plane words are selected once per node instead of a min and a max per child
-			const bool px = ax >= 0.f, py = ay >= 0.f, pz = az >= 0.f;
-			const uint32_t nX[2] = {px ? q[0] : q[6], px ? q[1] : q[7]}, fX[2] = {px ? q[6] : q[0], px ? q[7] : q[1]};
-			const uint32_t nY[2] = {py ? q[2] : q[8], py ? q[3] : q[9]}, fY[2] = {py ? q[8] : q[2], py ? q[9] : q[3]};
-			const uint32_t nZ[2] = {pz ? q[4] : q[10], pz ? q[5] : q[11]}, fZ[2] = {pz ? q[10] : q[4], pz ? q[11] : q[5]};
-			uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
-			auto child = [&](int i) -> uint32_t {
-				uint32_t meta = ((i < 4 ? metaLo : metaHi) >> ((i & 3) * 8)) & 0xff;
-				bool internal = (imask >> i) & 1;
-				if (!internal && meta == 0) return kEmptyEntry;
-				auto qf = [&](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7404u | ((i & 3) << 4))); };
-				const float tnx = fmaf(qf(nX[i >> 2]), axs, bxN), tfx = fmaf(qf(fX[i >> 2]), axs, bxF);
-				const float tny = fmaf(qf(nY[i >> 2]), ays, byN), tfy = fmaf(qf(fY[i >> 2]), ays, byF);
-				const float tnz = fmaf(qf(nZ[i >> 2]), azs, bzN), tfz = fmaf(qf(fZ[i >> 2]), azs, bzF);
+	// ---- phase: wide node.  Takes the nearest hit child of the node group, tests its 8 children ----
+	KRR_DEV void nodeStep(const BvhDev &bvh, TraceSmem &sm, LStack &ls) {
+		const uint32_t hits = ng.y;
+		const uint32_t bit	= 31u - (uint32_t) __clz(hits);
+		ng.y ^= 1u << bit;
+		if (ng.y & 0xff000000u) push(sm, ls, ng);
+		const uint32_t slot = (bit - 24u) ^ (octinv4 & 7u);
+		const uint32_t node = ng.x + (uint32_t) __popc(hits & ~(0xffffffffu << slot));
+		const float4 *np = reinterpret_cast<const float4 *>(bvh.nodes + node);
+		const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+		const uint32_t ew = __float_as_uint(n0.w);
+		const float sx = __uint_as_float((ew & 0xff) << 23), sy = __uint_as_float(((ew >> 8) & 0xff) << 23),
+					sz = __uint_as_float(((ew >> 16) & 0xff) << 23);
+		// t = (o_node + q*s - o) * idir = q * (s*idir) + (o_node - o)*idir
+		const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
+		const float bx = (n0.x - ro.x) * idir.x, by = (n0.y - ro.y) * idir.y, bz = (n0.z - ro.z) * idir.z;
+		const float lim = best.t;
+		// The byte -> float conversions (48 per node, quarter-rate I2F) are replaced by a byte permute that
+		// drops q into the mantissa of 2^23: v = 2^23 + 256 q, and q*a + b = v*(a/256) + (b - 2^15 a) in one
+		// FMA.  b - 2^15 a is rounded once: error <= |a| / 512, i.e. 1/512 of a quantisation step, against
+		// the full step the builder pads every child plane with (quantize() in bvh_build.cu).
+		const float axs = ax * 0.00390625f, ays = ay * 0.00390625f, azs = az * 0.00390625f;
+		// Rounding-error bound of the decomposed slab form q*a + b (cancellation between two large terms
+		// when the ray grazes an axis-aligned plane), PER AXIS: each slab interval is widened by its own
+		// bound, folded into the FMA constant of its near / far plane.  (One scalar bound for all axes let a
+		// ray that is nearly parallel to one axis -- huge a, b on that axis -- lose culling on the other two:
+		// the pixels of one image column / row took 13x longer than the rest of the frame together.)
+		auto axisSlack = [](float a, float b) { return fabsf(a) < 3.0e38f ? (fabsf(b) + 255.f * fabsf(a)) * 2.4e-7f + fabsf(a) * 0.00390625f : 0.f; };
+		const float slx = axisSlack(ax, bx), sly = axisSlack(ay, by), slz = axisSlack(az, bz);
+		const float bx0 = fmaf(-32768.f, ax, bx), by0 = fmaf(-32768.f, ay, by), bz0 = fmaf(-32768.f, az, bz);
+		const float bxN = bx0 - slx, bxF = bx0 + slx, byN = by0 - sly, byF = by0 + sly, bzN = bz0 - slz, bzF = bz0 + slz;
+		// ray octant: which plane of a slab is entered first only depends on the sign of the direction, so
+		// the near / far plane words are selected once per node instead of a min and a max per child.
+		// quantised planes: n2 = qlo[0][0..7], qlo[1][0..7]; n3 = qlo[2], qhi[0]; n4 = qhi[1], qhi[2]
+		const bool px = ax >= 0.f, py = ay >= 0.f, pz = az >= 0.f;
+		const uint32_t lx0 = __float_as_uint(n2.x), lx1 = __float_as_uint(n2.y), ly0 = __float_as_uint(n2.z), ly1 = __float_as_uint(n2.w);
+		const uint32_t lz0 = __float_as_uint(n3.x), lz1 = __float_as_uint(n3.y), hx0 = __float_as_uint(n3.z), hx1 = __float_as_uint(n3.w);
+		const uint32_t hy0 = __float_as_uint(n4.x), hy1 = __float_as_uint(n4.y), hz0 = __float_as_uint(n4.z), hz1 = __float_as_uint(n4.w);
+		const uint32_t nX[2] = {px ? lx0 : hx0, px ? lx1 : hx1}, fX[2] = {px ? hx0 : lx0, px ? hx1 : lx1};
+		const uint32_t nY[2] = {py ? ly0 : hy0, py ? ly1 : hy1}, fY[2] = {py ? hy0 : ly0, py ? hy1 : ly1};
+		const uint32_t nZ[2] = {pz ? lz0 : hz0, pz ? lz1 : hz1}, fZ[2] = {pz ? hz0 : lz0, pz ? hz1 : lz1};
+		const uint32_t metaW[2] = {__float_as_uint(n1.z), __float_as_uint(n1.w)};
+		const bool tlas = curInst < 0;
+		uint32_t hitmask = 0u;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t meta4 = metaW[h];
+			// internal children (0x38 | slot: bits 3 and 4 both set) get their priority from the ray octant, and
+			// so do the one-instance leaves of the TLAS; BLAS leaves keep their triangle offset
+			const uint32_t inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+			// (inner4 >> 4) holds 0x01 in every internal byte: times the octant (< 8) = the octant in those bytes
+			const uint32_t xor4 = tlas ? octinv4 : (inner4 >> 4) * (octinv4 & 7u);
+			const uint32_t bit4 = (meta4 ^ xor4) & 0x1f1f1f1fu;
+			const uint32_t cnt4	  = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				auto qf = [&](uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7404u | (j << 4))); };
+				const float tnx = fmaf(qf(nX[h]), axs, bxN), tfx = fmaf(qf(fX[h]), axs, bxF);
+				const float tny = fmaf(qf(nY[h]), ays, byN), tfy = fmaf(qf(fY[h]), ays, byF);
+				const float tnz = fmaf(qf(nZ[h]), azs, bzN), tfz = fmaf(qf(fZ[h]), azs, bzF);
 				// fminf/fmaxf drop NaNs (0 * inf), which is the conservative answer for a degenerate slab
 				const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
 				const float tf = fminf(fminf(tfx, tfy), fminf(tfz, lim));
-				// conservative: boxes only cull, the exact decision is the triangle test
-				if (!(tn <= tf * 1.0000010f)) return kEmptyEntry;
-				// key: entry distance in the high bits, slot in the low 3 -> one compare orders (tn, slot)
-				return (__float_as_uint(tn) & ~7u) | (uint32_t) i;
-			};
-			k0 = child(0), k1 = child(1), k2 = child(2), k3 = child(3), k4 = child(4), k5 = child(5), k6 = child(6), k7 = child(7);
-			// 19-comparator sorting network: ascending, misses (0xffffffff) sink to the end
-			KRR_CSWAP(k0, k1) KRR_CSWAP(k2, k3) KRR_CSWAP(k4, k5) KRR_CSWAP(k6, k7)
-			KRR_CSWAP(k0, k2) KRR_CSWAP(k1, k3) KRR_CSWAP(k4, k6) KRR_CSWAP(k5, k7)
-			KRR_CSWAP(k1, k2) KRR_CSWAP(k5, k6) KRR_CSWAP(k0, k4) KRR_CSWAP(k3, k7)
-			KRR_CSWAP(k1, k5) KRR_CSWAP(k2, k6)
-			KRR_CSWAP(k1, k4) KRR_CSWAP(k3, k6)
-			KRR_CSWAP(k2, k4) KRR_CSWAP(k3, k5)
-			KRR_CSWAP(k3, k4)
-			const bool tlas = curInst < 0;
-			auto entryOf = [&](uint32_t key) -> uint32_t {
-				uint32_t slot = key & 7u;
-				if ((imask >> slot) & 1) return childBase + __popc(imask & ((1u << slot) - 1));
-				uint32_t meta = ((slot < 4 ? metaLo : metaHi) >> ((slot & 3) * 8)) & 0xff;
-				uint32_t first = primBase + (meta & 31);
-				if (tlas) return kInstFlag | (uint32_t) __ldg(bvh.tlasInst + first); // one instance per TLAS leaf
-				return kLeafFlag | (((meta >> 5) - 1) << 26) | first;
-			};
-			// far-to-near onto the stack, nearest continues
-			if (k7 != kEmptyEntry) push(sm, ls, entryOf(k7), __uint_as_float(k7 & ~7u));
-			if (k6 != kEmptyEntry) push(sm, ls, entryOf(k6), __uint_as_float(k6 & ~7u));
-			if (k5 != kEmptyEntry) push(sm, ls, entryOf(k5), __uint_as_float(k5 & ~7u));
-			if (k4 != kEmptyEntry) push(sm, ls, entryOf(k4), __uint_as_float(k4 & ~7u));
-			if (k3 != kEmptyEntry) push(sm, ls, entryOf(k3), __uint_as_float(k3 & ~7u));
-			if (k2 != kEmptyEntry) push(sm, ls, entryOf(k2), __uint_as_float(k2 & ~7u));
-			if (k1 != kEmptyEntry) push(sm, ls, entryOf(k1), __uint_as_float(k1 & ~7u));
-			cur = k0 != kEmptyEntry ? entryOf(k0) : kEmptyEntry;
+				// conservative: boxes only cull, the exact decision is the triangle test.  The slack lets a
+				// candidate at exactly the current best distance through (ties are decided by ids).
+				if (tn <= tf * 1.0000010f) hitmask |= ((cnt4 >> (8 * j)) & 0xffu) << ((bit4 >> (8 * j)) & 0xffu);
+			}
 		}
+		ng = make_uint2(__float_as_uint(n1.x), (hitmask & 0xff000000u) | (ew >> 24));
+		tg = make_uint2(__float_as_uint(n1.y), hitmask & 0x00ffffffu);
 	}
-	// ---- phase 3: leaf (1..7 triangles).  Returns true when an any-hit ray terminated. ----
-	template <typename Accept> KRR_DEV bool leaf(const BvhDev &bvh, Accept accept) {
-		uint32_t first = cur & 0x03ffffffu, cnt = ((cur >> 26) & 7u) + 1;
-		if ((cur >> 30) == 3u) { // flat BLAS: the whole triangle list
-			const int2 fr = __ldg(bvh.flats + (cur & 0x3fffffffu));
-			first = (uint32_t) fr.x, cnt = (uint32_t) fr.y;
+	template <typename Accept> KRR_DEV bool tryHit(const BvhDev &bvh, const float4 &a, const float4 &b, float t, float u, float v, Accept accept) {
+		const int prim = __float_as_int(a.w);
+		const int inst = curInst == bvh.mergedInst ? __float_as_int(b.w) : curInst;
+		if (betterHit(t, inst, prim, best) && accept(inst, prim, u, v)) {
+			best.inst = inst, best.prim = prim, best.t = t, best.u = u, best.v = v;
+			return true;
 		}
-		cur = kEmptyEntry;
+		return false;
+	}
+	// flat BLAS: the whole triangle list.  Returns true when an any-hit ray terminated.
+	template <typename Accept> KRR_DEV bool walkFlat(const BvhDev &bvh, Accept accept) {
+		const uint32_t first = tg.x, cnt = tg.y & 0x00ffffffu;
+		tg.y	   = 0u;
 		uint32_t k = 0;
-#if KRR_LEAF_PAIR
-		if constexpr (PAIR || KRR_LEAF_PAIR_TREE)
-		// KRR_LEAF_WIDTH triangles per trip, evaluated without branches (triTestNoBranch: the same operations
+		if constexpr (PAIR)
+		// KRR_LEAF_WIDTH triangles per iteration, evaluated without branches (triTestNoBranch: the same operations
 		// and roundings as triIntersectE, combined as predicates).  The early exits of triIntersectE save the
 		// WARP little (32 rays per triangle: some lane usually goes on), and their branches serialise the
 		// dependent multiply-add chains that independent triangles interleave.
-		// Only in the kernels instantiated for flat-list scenes: in a tree leaf the lanes hold different
-		// triangles, and the mere presence of this loop cost the tree kernels registers (config 5: -10 %).
+		// Only in the kernels instantiated for flat-list scenes: where the lanes hold different lists the mere
+		// presence of this loop cost the tree kernels registers.
 		for (; k + KRR_LEAF_WIDTH <= cnt; k += KRR_LEAF_WIDTH) {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
 			float4 a[KRR_LEAF_WIDTH], b[KRR_LEAF_WIDTH], c[KRR_LEAF_WIDTH];
@@ -396,30 +404,27 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 #pragma unroll
 			for (int j = 0; j < KRR_LEAF_WIDTH; j++) hit[j] = triTestNoBranch(ro, rd, mk3(a[j]), mk3(b[j]), mk3(c[j]), tmax, t[j], u[j], v[j]);
 #pragma unroll
-			for (int j = 0; j < KRR_LEAF_WIDTH; j++) {
-				if (hit[j]) {
-					const int prim = __float_as_int(a[j].w);
-					const int inst = curInst == bvh.mergedInst ? __float_as_int(b[j].w) : curInst;
-					if (betterHit(t[j], inst, prim, best) && accept(inst, prim, u[j], v[j])) {
-						best.inst = inst, best.prim = prim, best.t = t[j], best.u = u[j], best.v = v[j];
-						if (ANY) return true;
-					}
-				}
-			}
+			for (int j = 0; j < KRR_LEAF_WIDTH; j++)
+				if (hit[j] && tryHit(bvh, a[j], b[j], t[j], u[j], v[j], accept) && ANY) return true;
 		}
-#endif
 		for (; k < cnt; k++) {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
-			float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
 			float t, u, v;
-			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v)) {
-				const int prim = __float_as_int(a.w);
-				const int inst = curInst == bvh.mergedInst ? __float_as_int(b.w) : curInst;
-				if (betterHit(t, inst, prim, best) && accept(inst, prim, u, v)) {
-					best.inst = inst, best.prim = prim, best.t = t, best.u = u, best.v = v;
-					if (ANY) return true;
-				}
-			}
+			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
+		}
+		return false;
+	}
+	// ---- phase: triangles of the current group (up to `budget` of them).  Returns true when an any-hit ray terminated. ----
+	template <typename Accept> KRR_DEV bool triStep(const BvhDev &bvh, Accept accept, int budget) {
+		if (tg.y & 0x80000000u) return walkFlat(bvh, accept);
+		for (int it = 0; it < budget && tg.y; it++) {
+			const uint32_t bit = 31u - (uint32_t) __clz(tg.y);
+			tg.y ^= 1u << bit;
+			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + tg.x + bit);
+			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			float t, u, v;
+			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
 		}
 		return false;
 	}
@@ -428,49 +433,45 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	// dependent traversals interleaved with other work (ratio-tracking shadow rays through media).
 	template <typename Accept> KRR_DEV void runToEnd(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, Accept accept) {
 		while (true) {
-			int st = next(sm, ls);
-			if (st == FINISHED) return;
-			if (st == ENTER) { enterInstance(bvh, instances, sm); st = (cur >> 30) == 3u ? LEAF : NODE; }
-			if (st == NODE) {
-				node(bvh, sm, ls);
-				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
+			if (!hasNode() && !tg.y && !popNext(sm, ls)) return;
+			if (!tg.y) nodeStep(bvh, sm, ls);
+			while (tg.y) {
+				if (curInst < 0) enterInstance(bvh, instances, sm, ls); // leaves a flat list in tg, or a root in ng
+				else if (triStep(bvh, accept, 24)) return;
 			}
-			if (st == LEAF && leaf(bvh, accept)) return;
 		}
 	}
 
-	// One warp-cooperative trip: lanes vote on the phase to run, so that a phase executes with as many
-	// lanes as possible; lanes whose phase lost the vote keep their entry and wait (they would have been
-	// masked off anyway).  Returns true for lanes whose ray finished during this trip.
-	// VOTE = false runs both phases every trip (a lane may test a node and then its nearest leaf in
-	// the same trip): fewer trips per ray, which wins for the short any-hit traversals of shadow rays.
+	// One warp-cooperative trip: every phase runs under a warp vote, so that it executes with as many lanes as
+	// possible.  Returns true for lanes whose ray finished during this trip.
+	// VOTE: the triangle phase waits until KRR_TRI_VOTE lanes hold triangles (or no lane has node work left);
+	// VOTE = false runs it every trip: fewer trips per ray, which wins for the short any-hit traversals of
+	// shadow rays.
 	template <bool VOTE, typename Accept>
 	KRR_DEV bool trip(bool active, const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, Accept accept) {
-		const unsigned FULL = 0xffffffffu;
-		int st = FINISHED;
-		bool fin = false;
-		if (active) {
-			st	= next(sm, ls);
-			fin = st == FINISHED;
-		}
-		if (__any_sync(FULL, st == ENTER)) {
-			if (st == ENTER) { enterInstance(bvh, instances, sm); st = (cur >> 30) == 3u ? LEAF : NODE; }
-		}
-		if (VOTE) {
-			const unsigned mN = __ballot_sync(FULL, st == NODE), mL = __ballot_sync(FULL, st == LEAF);
-			if (mN && __popc(mN) >= __popc(mL)) {
-				if (st == NODE) node(bvh, sm, ls);
-			} else if (mL) {
-				if (st == LEAF) fin = leaf(bvh, accept);
-			}
+		if constexpr (PAIR) { // the whole scene is one triangle list: one trip per ray
+			if (active && tg.y) walkFlat(bvh, accept);
+			return active;
 		} else {
-			if (st == NODE) {
-				node(bvh, sm, ls);
-				if (cur != kEmptyEntry && (cur >> 30) == 1u) st = LEAF;
+			const unsigned FULL = 0xffffffffu;
+			bool fin = false;
+			if (active && !hasNode() && !tg.y) fin = !popNext(sm, ls);
+			const bool live = active && !fin;
+			const bool wantEnter = live && tg.y && curInst < 0;
+			if (__any_sync(FULL, wantEnter)) {
+				if (wantEnter) enterInstance(bvh, instances, sm, ls);
 			}
-			if (st == LEAF) fin = leaf(bvh, accept);
+			const bool wantNode = live && !tg.y && hasNode();
+			if (__any_sync(FULL, wantNode)) {
+				if (wantNode) nodeStep(bvh, sm, ls);
+			}
+			const bool wantTri = live && tg.y && curInst >= 0;
+			const unsigned mT  = __ballot_sync(FULL, wantTri);
+			bool run = mT != 0u;
+			if (VOTE && run && __popc(mT) < KRR_TRI_VOTE) run = !__any_sync(FULL, live && !tg.y && hasNode());
+			if (run && wantTri) fin = triStep(bvh, accept, KRR_TRI_PER_TRIP);
+			return fin;
 		}
-		return fin;
 	}
 };
 

@@ -5,10 +5,17 @@
 // Pipeline (all on the GPU, one stream):
 //   1. primitive AABBs + centroid bounds                       (k_prim_bounds_*)
 //   2. 63-bit Morton codes of the centroids, radix sort        (k_morton + cub::DeviceRadixSort)
-//   3. Karras-2012 binary radix tree, bottom-up AABB fit        (k_radix_tree, k_fit)
+//   3. binary tree by PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): the Morton
+//      order is only the SEARCH order -- every cluster looks kPlocRadius neighbours to either side for
+//      the partner with the smallest merged surface area, mutual nearest neighbours merge, the cluster
+//      array is compacted, repeat until one cluster is left.  (The Karras-2012 radix tree of round 1
+//      splits by Morton bits alone: ~60 node + leaf visits per ray on the 20 M-triangle scene.)
+//                                                                (k_ploc_nn, k_ploc_merge, k_ploc_compact)
 //   4. top-down collapse to 8-wide nodes: a wide node opens the child with the largest surface
-//      area until it has 8 children (greedy SAH), leaves hold up to `maxLeaf` primitives; child
-//      boxes are quantised to 8 bits against a padded power-of-two frame      (k_collapse)
+//      area until it has 8 children (greedy SAH) and spends slots that are still free on splitting its
+//      leaves; leaves hold up to `maxLeaf` <= 3 primitives; children are assigned to OCTANT-ORDERED
+//      slots (bvh.cuh); child boxes are quantised to 8 bits against a padded power-of-two frame
+//                                                                (k_collapse)
 // TLAS refit (per-frame instance transform updates): instance boxes are recomputed and the wide
 // nodes re-fitted level by level, deepest first, reusing the topology        (k_refit_level).
 #include "bvh_build.h"
@@ -175,71 +182,168 @@ __global__ void k_morton(const Aabb *__restrict__ boxes, int n, const float *__r
 	vals[i] = (uint32_t) i;
 }
 
-// binary radix tree over sorted keys (Karras 2012). internal nodes 0..n-2, leaf i = node (n-1)+i
+// binary tree over the sorted primitives: leaves are nodes 0..n-1 (leaf i = sorted primitive i), internal nodes
+// n..2n-2 in creation order (the root is created last)
 struct BinTree {
-	int32_t *left, *right, *parent; // per internal node / per node
-	int32_t *first, *last;			// sorted-primitive range covered by each node
-	Aabb *bounds;					// per node (2n-1)
-	int32_t *flags;					// per internal node, for the bottom-up fit
+	int32_t *left, *right; // per node id (internal ids only are written)
+	int32_t *count;		   // primitives below each node
+	Aabb *bounds;		   // per node (2n-1)
 };
-
-KRR_DEV int delta(const uint64_t *keys, int n, int i, int j) {
-	if (j < 0 || j >= n) return -1;
-	uint64_t a = keys[i], b = keys[j];
-	if (a == b) return 64 + __clz(i ^ j);
-	return __clzll(a ^ b);
-}
-
-__global__ void k_radix_tree(const uint64_t *__restrict__ keys, int n, BinTree t) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n - 1) return;
-	int d	 = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-	int dmin = delta(keys, n, i, i - d);
-	int lmax = 2;
-	while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-	int l = 0;
-	for (int tt = lmax / 2; tt >= 1; tt /= 2)
-		if (delta(keys, n, i, i + (l + tt) * d) > dmin) l += tt;
-	int j	  = i + l * d;
-	int dnode = delta(keys, n, i, j);
-	int s	  = 0;
-	for (int div = 2, tt = (l + div - 1) / div; ; div *= 2, tt = (l + div - 1) / div) {
-		if (delta(keys, n, i, i + (s + tt) * d) > dnode) s += tt;
-		if (tt <= 1) break;
-	}
-	int gamma = i + s * d + min(d, 0);
-	int lo = min(i, j), hi = max(i, j);
-	int lc = (lo == gamma) ? (n - 1) + gamma : gamma;
-	int rc = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
-	t.left[i] = lc, t.right[i] = rc;
-	t.parent[lc] = i, t.parent[rc] = i;
-	t.first[i] = lo, t.last[i] = hi;
-	if (i == 0) t.parent[0] = -1;
-}
-
-__global__ void k_fit(const Aabb *__restrict__ primBoxes, const uint32_t *__restrict__ sortedIdx, int n, BinTree t) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int node = (n - 1) + i;
-	t.bounds[node] = primBoxes[sortedIdx[i]];
-	t.first[node] = t.last[node] = i;
-	int p = t.parent[node];
-	while (p >= 0) {
-		__threadfence();
-		if (atomicAdd(&t.flags[p], 1) == 0) return; // first child to arrive stops; second continues
-		// children boxes were written by other SMs: read them through L2 (L1 is not coherent)
-		Aabb a, b, r;
-		const float *pa = (const float *) &t.bounds[t.left[p]], *pb = (const float *) &t.bounds[t.right[p]];
-		for (int k = 0; k < 3; k++) a.lo[k] = __ldcg(pa + k), a.hi[k] = __ldcg(pa + 3 + k), b.lo[k] = __ldcg(pb + k), b.hi[k] = __ldcg(pb + 3 + k);
-		for (int k = 0; k < 3; k++) r.lo[k] = fminf(a.lo[k], b.lo[k]), r.hi[k] = fmaxf(a.hi[k], b.hi[k]);
-		t.bounds[p] = r;
-		p = t.parent[p];
-	}
-}
 
 KRR_DEV float halfArea(const Aabb &b) {
 	float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
 	return dx * dy + dy * dz + dz * dx;
+}
+
+// ---- PLOC ----
+constexpr int kPlocRadius = 16, kPlocBlock = 256;
+
+__global__ void k_ploc_init(const Aabb *__restrict__ primBoxes, const uint32_t *__restrict__ sortedIdx, int n, BinTree t, int32_t *cid, Aabb *cbox) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const Aabb b = primBoxes[sortedIdx[i]];
+	t.bounds[i] = b, t.count[i] = 1;
+	cid[i] = i, cbox[i] = b;
+}
+
+// nearest neighbour (smallest surface area of the union) of every cluster within kPlocRadius positions; ties go
+// to the smaller index, which makes the lexicographically smallest minimal pair mutual: every pass merges
+__global__ void __launch_bounds__(kPlocBlock) k_ploc_nn(const Aabb *__restrict__ cbox, int n, int32_t *nn) {
+	constexpr int W = kPlocBlock + 2 * kPlocRadius;
+	__shared__ float lo[3][W], hi[3][W];
+	const int base = blockIdx.x * kPlocBlock - kPlocRadius;
+	for (int s = threadIdx.x; s < W; s += kPlocBlock) {
+		const int g = base + s;
+		if (g >= 0 && g < n) {
+			const Aabb b = cbox[g];
+			for (int k = 0; k < 3; k++) lo[k][s] = b.lo[k], hi[k][s] = b.hi[k];
+		}
+	}
+	__syncthreads();
+	const int i = blockIdx.x * kPlocBlock + threadIdx.x;
+	if (i >= n) return;
+	const int me = threadIdx.x + kPlocRadius;
+	const float l0 = lo[0][me], l1 = lo[1][me], l2 = lo[2][me], h0 = hi[0][me], h1 = hi[1][me], h2 = hi[2][me];
+	float bestA = 3.0e38f;
+	int best	= -1;
+	for (int r = -kPlocRadius; r <= kPlocRadius; r++) {
+		const int g = i + r;
+		if (r == 0 || g < 0 || g >= n) continue;
+		const int s	   = me + r;
+		const float dx = fmaxf(h0, hi[0][s]) - fminf(l0, lo[0][s]), dy = fmaxf(h1, hi[1][s]) - fminf(l1, lo[1][s]),
+					dz = fmaxf(h2, hi[2][s]) - fminf(l2, lo[2][s]);
+		const float a  = dx * dy + dy * dz + dz * dx;
+		if (a < bestA) bestA = a, best = g; // ascending g: the first minimum is the smallest index
+	}
+	nn[i] = best;
+}
+
+// mutual nearest neighbours merge into a new node that takes the place of the lower one
+__global__ void k_ploc_merge(const int32_t *__restrict__ cidIn, const Aabb *__restrict__ cboxIn, const int32_t *__restrict__ nn, int n,
+							 int32_t *nodeCounter, BinTree t, int32_t *cidTmp, Aabb *cboxTmp, int32_t *valid) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int j		  = nn[i];
+	const bool mutual = j >= 0 && nn[j] == i;
+	if (mutual && i > j) { valid[i] = 0; return; }
+	int id = cidIn[i];
+	Aabb b = cboxIn[i];
+	if (mutual) {
+		const Aabb o = cboxIn[j];
+		for (int k = 0; k < 3; k++) b.lo[k] = fminf(b.lo[k], o.lo[k]), b.hi[k] = fmaxf(b.hi[k], o.hi[k]);
+		const int l = id, r = cidIn[j];
+		id			= atomicAdd(nodeCounter, 1);
+		t.left[id] = l, t.right[id] = r;
+		t.count[id]	 = t.count[l] + t.count[r];
+		t.bounds[id] = b;
+	}
+	cidTmp[i] = id, cboxTmp[i] = b, valid[i] = 1;
+}
+
+__global__ void k_ploc_compact(const int32_t *__restrict__ cidTmp, const Aabb *__restrict__ cboxTmp, const int32_t *__restrict__ valid,
+							   const int32_t *__restrict__ pos, int n, int32_t *cidOut, Aabb *cboxOut, int32_t *nOut) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (valid[i]) cidOut[pos[i]] = cidTmp[i], cboxOut[pos[i]] = cboxTmp[i];
+	if (i == n - 1) *nOut = pos[i] + valid[i];
+}
+
+// The last kPlocTail clusters are finished by ONE block (the passes of a small array are launch-bound: ~25
+// passes x 4 launches + a host round trip each, per BLAS)
+constexpr int kPlocTail = 1024;
+__global__ void __launch_bounds__(kPlocTail) k_ploc_tail(int32_t *cid, Aabb *cbox, int n, int32_t *nodeCounter, BinTree t) {
+	__shared__ float lo[3][kPlocTail], hi[3][kPlocTail];
+	__shared__ int32_t id[kPlocTail], nnS[kPlocTail], posS[kPlocTail];
+	__shared__ int32_t warpSum[32];
+	__shared__ int32_t nNow;
+	const int i = threadIdx.x;
+	if (i < n) {
+		const Aabb b = cbox[i];
+		for (int k = 0; k < 3; k++) lo[k][i] = b.lo[k], hi[k][i] = b.hi[k];
+		id[i] = cid[i];
+	}
+	if (i == 0) nNow = n;
+	__syncthreads();
+	while (true) {
+		const int m = nNow;
+		if (m <= 1) break;
+		int best = -1;
+		if (i < m) {
+			float bestA = 3.0e38f;
+			for (int r = -kPlocRadius; r <= kPlocRadius; r++) {
+				const int g = i + r;
+				if (r == 0 || g < 0 || g >= m) continue;
+				const float dx = fmaxf(hi[0][i], hi[0][g]) - fminf(lo[0][i], lo[0][g]), dy = fmaxf(hi[1][i], hi[1][g]) - fminf(lo[1][i], lo[1][g]),
+							dz = fmaxf(hi[2][i], hi[2][g]) - fminf(lo[2][i], lo[2][g]);
+				const float a  = dx * dy + dy * dz + dz * dx;
+				if (a < bestA) bestA = a, best = g;
+			}
+			nnS[i] = best;
+		}
+		__syncthreads();
+		int myId = 0, v = 0;
+		float b[6] = {0, 0, 0, 0, 0, 0};
+		if (i < m) {
+			const int j		  = best;
+			const bool mutual = j >= 0 && nnS[j] == i;
+			v				  = !(mutual && i > j);
+			myId			  = id[i];
+			for (int k = 0; k < 3; k++) b[k] = lo[k][i], b[3 + k] = hi[k][i];
+			if (mutual && i < j) {
+				for (int k = 0; k < 3; k++) b[k] = fminf(b[k], lo[k][j]), b[3 + k] = fmaxf(b[3 + k], hi[k][j]);
+				const int l = myId, r = id[j];
+				myId		= atomicAdd(nodeCounter, 1);
+				t.left[myId] = l, t.right[myId] = r;
+				t.count[myId] = t.count[l] + t.count[r];
+				Aabb nb;
+				for (int k = 0; k < 3; k++) nb.lo[k] = b[k], nb.hi[k] = b[3 + k];
+				t.bounds[myId] = nb;
+			}
+		}
+		// block-wide exclusive scan of v
+		const unsigned bal = __ballot_sync(0xffffffffu, v);
+		const int lane = i & 31, warp = i >> 5;
+		if (lane == 0) warpSum[warp] = __popc(bal);
+		__syncthreads();
+		if (warp == 0) {
+			int s = warpSum[lane], incl = s;
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) incl += o;
+			}
+			warpSum[lane] = incl - s;
+			if (lane == 31) nNow = incl;
+		}
+		__syncthreads();
+		posS[i] = warpSum[warp] + __popc(bal & ((1u << lane) - 1u));
+		__syncthreads(); // everyone has read lo / hi / id of the old array
+		if (v && i < m) {
+			const int p = posS[i];
+			for (int k = 0; k < 3; k++) lo[k][p] = b[k], hi[k][p] = b[3 + k];
+			id[p] = myId;
+		}
+		__syncthreads();
+	}
 }
 
 // quantisation frame of a node: padded so that every child plane keeps >= 1 quantum of slack
@@ -288,6 +392,7 @@ struct TriWriter {
 		t.e2 = make_float4(e2.x, e2.y, e2.z, 0.f);
 		tris[slot] = t;
 	}
+	KRR_DEV void clear(uint32_t, bool) const {}
 };
 struct MergedTriWriter { // triangles of the merged BLAS carry (primitive, instance)
 	const float *positions;
@@ -309,11 +414,13 @@ struct MergedTriWriter { // triangles of the merged BLAS carry (primitive, insta
 		t.e2 = make_float4(e2.x, e2.y, e2.z, 0.f);
 		tris[slot] = t;
 	}
+	KRR_DEV void clear(uint32_t, bool) const {}
 };
 struct InstWriter {
 	int32_t *tlasInst;
 	const int32_t *ids; // TLAS primitive -> instance id
 	KRR_DEV void operator()(uint32_t slot, uint32_t prim) const { tlasInst[slot] = ids[prim]; }
+	KRR_DEV void clear(uint32_t slot, bool any) const { if (any) tlasInst[slot] = 0; } // slots without an instance
 };
 
 // flat BLAS (<= flatMax triangles): the leaf payload in primitive order, no nodes
@@ -322,39 +429,73 @@ template <typename Writer> __global__ void k_write_flat(int n, uint32_t base, Wr
 	if (i < n) writer(base + i, (uint32_t) i);
 }
 
-template <typename Writer>
+// One thread = one wide node.  `item.bin` is the binary node whose subtree the wide node covers.
+// TLAS = true: one instance per leaf child, instance ids stored slot-major (8 per node).
+template <bool TLAS, typename Writer>
 __global__ void k_collapse(const WorkItem *__restrict__ in, int nIn, WorkItem *out, int32_t *nOut, BinTree t, int n,
 						   const uint32_t *__restrict__ sortedIdx, int maxLeaf, CollapseOut co, Writer writer) {
 	int w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= nIn) return;
 	WorkItem item = in[w];
 	int c[8], nc = 0;
-	auto count = [&](int node) { return t.last[node] - t.first[node] + 1; };
-	auto isLeafUnit = [&](int node) { return node >= n - 1 || count(node) <= maxLeaf; };
-	if (item.bin >= n - 1 || n == 1) c[nc++] = item.bin;
+	if (item.bin < n) c[nc++] = item.bin; // the whole tree is one primitive
 	else { c[nc++] = t.left[item.bin]; c[nc++] = t.right[item.bin]; }
-	while (nc < 8) {
-		int best = -1;
-		float bestA = -1;
-		for (int j = 0; j < nc; j++)
-			if (!isLeafUnit(c[j])) {
-				float a = halfArea(t.bounds[c[j]]);
-				if (a > bestA) bestA = a, best = j;
-			}
-		if (best < 0) break;
-		int node = c[best];
-		c[best]	 = t.left[node];
-		c[nc++]	 = t.right[node];
+	// greedy SAH: open the child with the largest surface area -- first among the subtrees that are too big
+	// to be a leaf, then (slots are free: an empty slot costs the same 80-byte node) among the leaves that
+	// still hold more than one primitive, which gives every triangle the tightest box the node can afford
+	for (int pass = 0; pass < 2; pass++) {
+		const int limit = pass == 0 ? maxLeaf : 1;
+		while (nc < 8) {
+			int best = -1;
+			float bestA = -1;
+			for (int j = 0; j < nc; j++)
+				if (t.count[c[j]] > limit) {
+					float a = halfArea(t.bounds[c[j]]);
+					if (a > bestA) bestA = a, best = j;
+				}
+			if (best < 0) break;
+			int node = c[best];
+			c[best]	 = t.left[node];
+			c[nc++]	 = t.right[node];
+		}
 	}
 	const Aabb nb = t.bounds[item.bin];
 	float o[3];
 	uint32_t e[3];
 	makeFrame(nb, o, e);
+	// octant-ordered slots: slot s "lies" in direction ((s&4 ? + : -), (s&2 ? + : -), (s&1 ? + : -)) of the node
+	// centre; children are assigned greedily by the largest projection of (child centre - node centre) on the
+	// slot direction, so that slot ^ (ray octant) orders the children front to back (bvh.cuh)
+	int slotOf[8], childAt[8];
+	{
+		float cx[8], cy[8], cz[8];
+		const float mx = 0.5f * (nb.lo[0] + nb.hi[0]), my = 0.5f * (nb.lo[1] + nb.hi[1]), mz = 0.5f * (nb.lo[2] + nb.hi[2]);
+		for (int j = 0; j < nc; j++) {
+			const Aabb cb = t.bounds[c[j]];
+			cx[j] = 0.5f * (cb.lo[0] + cb.hi[0]) - mx, cy[j] = 0.5f * (cb.lo[1] + cb.hi[1]) - my, cz[j] = 0.5f * (cb.lo[2] + cb.hi[2]) - mz;
+		}
+		for (int s = 0; s < 8; s++) childAt[s] = -1;
+		for (int j = 0; j < nc; j++) slotOf[j] = -1;
+		for (int r = 0; r < nc; r++) {
+			float bestC = -3.0e38f;
+			int bj = -1, bs = -1;
+			for (int j = 0; j < nc; j++) {
+				if (slotOf[j] >= 0) continue;
+				for (int s = 0; s < 8; s++) {
+					if (childAt[s] >= 0) continue;
+					const float cost = (s & 4 ? cx[j] : -cx[j]) + (s & 2 ? cy[j] : -cy[j]) + (s & 1 ? cz[j] : -cz[j]);
+					if (cost > bestC) bestC = cost, bj = j, bs = s;
+				}
+			}
+			slotOf[bj] = bs, childAt[bs] = bj;
+		}
+	}
 	int nInternal = 0, nPrims = 0;
 	for (int j = 0; j < nc; j++) {
-		if (isLeafUnit(c[j])) nPrims += count(c[j]);
+		if (t.count[c[j]] <= maxLeaf) nPrims += t.count[c[j]];
 		else nInternal++;
 	}
+	if (TLAS && nPrims) nPrims = 8; // slot-major instance ids
 	uint32_t childBase = nInternal ? (uint32_t) atomicAdd(&co.counters[0], nInternal) : 0u;
 	uint32_t primBase  = nPrims ? (uint32_t) atomicAdd(&co.counters[1], nPrims) : 0u;
 	int outBase		   = nInternal ? atomicAdd(nOut, nInternal) : 0;
@@ -365,21 +506,30 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, int nIn, WorkItem *o
 	node.childBase = co.nodeBase + childBase;
 	node.primBase  = co.primBase + primBase;
 	int ii = 0, po = 0;
-	for (int j = 0; j < 8; j++) {
-		node.meta[j] = 0;
-		for (int k = 0; k < 3; k++) node.qlo[k][j] = 255, node.qhi[k][j] = 0;
-	}
-	for (int j = 0; j < nc; j++) {
+	for (int s = 0; s < 8; s++) { // internal children and leaf triangles are numbered in slot order
+		node.meta[s] = 0;
+		for (int k = 0; k < 3; k++) node.qlo[k][s] = 255, node.qhi[k][s] = 0;
+		if (TLAS) writer.clear(co.primBase + primBase + s, nPrims != 0);
+		const int j = childAt[s];
+		if (j < 0) continue;
 		uint8_t ql[3], qh[3];
 		quantize(t.bounds[c[j]], o, e, ql, qh);
-		for (int k = 0; k < 3; k++) node.qlo[k][j] = ql[k], node.qhi[k][j] = qh[k];
-		if (isLeafUnit(c[j])) {
-			int cnt		 = count(c[j]);
-			node.meta[j] = (uint8_t) ((cnt << 5) | po);
-			for (int k = 0; k < cnt; k++) writer(co.primBase + primBase + po + k, sortedIdx[t.first[c[j]] + k]);
+		for (int k = 0; k < 3; k++) node.qlo[k][s] = ql[k], node.qhi[k][s] = qh[k];
+		const int cnt = t.count[c[j]];
+		if (cnt <= maxLeaf) {
+			// the primitives below c[j] (at most 3): depth-first walk of its little subtree
+			int stk[4], sp = 0, k = 0;
+			stk[sp++] = c[j];
+			while (sp) {
+				const int x = stk[--sp];
+				if (x < n) { writer(co.primBase + primBase + (TLAS ? s : po + k), sortedIdx[x]); k++; }
+				else stk[sp++] = t.right[x], stk[sp++] = t.left[x];
+			}
+			node.meta[s] = TLAS ? (uint8_t) (0x20 | s) : (uint8_t) ((((1u << cnt) - 1u) << 5) | (uint32_t) po);
 			po += cnt;
 		} else {
-			node.imask |= (uint8_t) (1u << j);
+			node.imask |= (uint8_t) (1u << s);
+			node.meta[s] = (uint8_t) (0x20 | (24 + s));
 			out[outBase + ii] = WorkItem{c[j], (int32_t) (childBase + ii)};
 			ii++;
 		}
@@ -399,22 +549,11 @@ __global__ void k_refit_level(Node8 *nodes, Aabb *nodeBounds, int first, int cou
 	Aabb nb;
 	for (int k = 0; k < 3; k++) nb.lo[k] = 3.0e38f, nb.hi[k] = -3.0e38f;
 	for (int j = 0; j < 8; j++) {
-		used[j] = false;
-		bool internal = (node.imask >> j) & 1;
-		if (internal) {
-			cb[j]	= nodeBounds[node.childBase + __popc(node.imask & ((1u << j) - 1))];
-			used[j] = true;
-		} else if (node.meta[j]) {
-			int cnt = node.meta[j] >> 5, off = node.meta[j] & 31;
-			for (int k = 0; k < 3; k++) cb[j].lo[k] = 3.0e38f, cb[j].hi[k] = -3.0e38f;
-			for (int q = 0; q < cnt; q++) {
-				const Aabb pb = primBoxes[tlasInst[node.primBase + off + q]];
-				for (int k = 0; k < 3; k++) cb[j].lo[k] = fminf(cb[j].lo[k], pb.lo[k]), cb[j].hi[k] = fmaxf(cb[j].hi[k], pb.hi[k]);
-			}
-			used[j] = true;
-		}
-		if (used[j])
-			for (int k = 0; k < 3; k++) nb.lo[k] = fminf(nb.lo[k], cb[j].lo[k]), nb.hi[k] = fmaxf(nb.hi[k], cb[j].hi[k]);
+		used[j] = node.meta[j] != 0;
+		if (!used[j]) continue;
+		if ((node.imask >> j) & 1) cb[j] = nodeBounds[node.childBase + __popc(node.imask & ((1u << j) - 1))];
+		else cb[j] = primBoxes[tlasInst[node.primBase + j]]; // one instance per TLAS leaf, slot-major
+		for (int k = 0; k < 3; k++) nb.lo[k] = fminf(nb.lo[k], cb[j].lo[k]), nb.hi[k] = fmaxf(nb.hi[k], cb[j].hi[k]);
 	}
 	float o[3];
 	uint32_t e[3];
@@ -472,11 +611,13 @@ template <typename T> struct DevBuf {
 struct TreeScratch {
 	DevBuf<uint64_t> keys, keysSorted;
 	DevBuf<uint32_t> vals, valsSorted;
-	DevBuf<int32_t> left, right, parent, first, last, flags;
+	DevBuf<int32_t> left, right, count;
 	DevBuf<Aabb> bounds;
+	DevBuf<int32_t> cid[2], cidTmp, nn, valid, pos, plocCounters; // PLOC cluster arrays (ping-pong), scratch
+	DevBuf<Aabb> cbox[2], cboxTmp;
 	DevBuf<WorkItem> q0, q1;
 	DevBuf<int32_t> qCount;
-	DevBuf<unsigned char> tmp;
+	DevBuf<unsigned char> tmp, tmpScan;
 };
 
 } // namespace
@@ -504,49 +645,65 @@ namespace {
 // Builds one wide tree over `n` primitives whose boxes are in `boxes`; nodes are appended to the
 // pool at *nodeCursor, primitives at *primCursor.  Returns the root index; levelStart (optional)
 // receives the pool index of the first node of each level.
-template <typename Writer>
+template <bool TLAS, typename Writer>
 bool buildTree(const Aabb *boxes, int n, int maxLeaf, Node8 *nodePool, Aabb *boundsPool, int32_t *counters, int &nodeCursor,
 			   int &primCursor, Writer writer, cudaStream_t stream, float *cb, std::vector<int> *levelStart, int *root, char *err,
 			   TreeScratch &sc) {
 	const int T = 256;
-	DevBuf<uint64_t> &keys = sc.keys, &keysSorted = sc.keysSorted;
-	DevBuf<uint32_t> &vals = sc.vals, &valsSorted = sc.valsSorted;
-	DevBuf<int32_t> &left = sc.left, &right = sc.right, &parent = sc.parent, &first = sc.first, &last = sc.last, &flags = sc.flags;
-	DevBuf<Aabb> &bounds = sc.bounds;
-	DevBuf<WorkItem> &q0 = sc.q0, &q1 = sc.q1;
-	DevBuf<int32_t> &qCount = sc.qCount;
-	DevBuf<unsigned char> &tmp = sc.tmp;
-	if (!keys.ensure(n) || !keysSorted.ensure(n) || !vals.ensure(n) || !valsSorted.ensure(n) || !left.ensure(n) || !right.ensure(n) ||
-		!parent.ensure(2 * n) || !first.ensure(2 * n) || !last.ensure(2 * n) || !flags.ensure(n) || !bounds.ensure(2 * n) ||
-		!q0.ensure(n + 1) || !q1.ensure(n + 1) || !qCount.ensure(1)) {
+	if (!sc.keys.ensure(n) || !sc.keysSorted.ensure(n) || !sc.vals.ensure(n) || !sc.valsSorted.ensure(n) || !sc.left.ensure(2 * n) ||
+		!sc.right.ensure(2 * n) || !sc.count.ensure(2 * n) || !sc.bounds.ensure(2 * n) || !sc.cid[0].ensure(n) || !sc.cid[1].ensure(n) ||
+		!sc.cidTmp.ensure(n) || !sc.nn.ensure(n) || !sc.valid.ensure(n) || !sc.pos.ensure(n) || !sc.plocCounters.ensure(2) ||
+		!sc.cbox[0].ensure(n) || !sc.cbox[1].ensure(n) || !sc.cboxTmp.ensure(n) || !sc.q0.ensure(n + 1) || !sc.q1.ensure(n + 1) ||
+		!sc.qCount.ensure(1)) {
 		snprintf(err, 256, "bvh build: out of device memory for %d primitives", n);
 		return false;
 	}
-	k_morton<<<(n + T - 1) / T, T, 0, stream>>>(boxes, n, cb, keys.p, vals.p);
+	k_morton<<<(n + T - 1) / T, T, 0, stream>>>(boxes, n, cb, sc.keys.p, sc.vals.p);
 	size_t tmpBytes = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keysSorted.p, vals.p, valsSorted.p, n, 0, 63, stream);
-	if (!tmp.ensure(tmpBytes)) { snprintf(err, 256, "bvh build: sort scratch alloc failed"); return false; }
-	CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys.p, keysSorted.p, vals.p, valsSorted.p, n, 0, 63, stream));
-	BinTree t{left.p, right.p, parent.p, first.p, last.p, bounds.p, flags.p};
-	CK(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * std::max(n, 1), stream));
-	CK(cudaMemsetAsync(parent.p, 0xff, sizeof(int32_t) * 2 * n, stream));
-	if (n > 1) k_radix_tree<<<(n - 1 + T - 1) / T, T, 0, stream>>>(keysSorted.p, n, t);
-	k_fit<<<(n + T - 1) / T, T, 0, stream>>>(boxes, valsSorted.p, n, t);
-	// collapse, level by level
+	cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, sc.keys.p, sc.keysSorted.p, sc.vals.p, sc.valsSorted.p, n, 0, 63, stream);
+	if (!sc.tmp.ensure(tmpBytes)) { snprintf(err, 256, "bvh build: sort scratch alloc failed"); return false; }
+	CK(cub::DeviceRadixSort::SortPairs(sc.tmp.p, tmpBytes, sc.keys.p, sc.keysSorted.p, sc.vals.p, sc.valsSorted.p, n, 0, 63, stream));
+	// ---- binary tree: PLOC over the Morton order ----
+	BinTree t{sc.left.p, sc.right.p, sc.count.p, sc.bounds.p};
+	int32_t *nodeCounter = sc.plocCounters.p, *nOutDev = sc.plocCounters.p + 1;
+	{
+		const int32_t init[2] = {n, n}; // next free node id (leaves are 0..n-1), cluster count
+		CK(cudaMemcpyAsync(sc.plocCounters.p, init, 8, cudaMemcpyHostToDevice, stream));
+	}
+	k_ploc_init<<<(n + T - 1) / T, T, 0, stream>>>(boxes, sc.valsSorted.p, n, t, sc.cid[0].p, sc.cbox[0].p);
+	int m = n, cur = 0;
+	size_t scanBytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, sc.valid.p, sc.pos.p, n, stream);
+	if (!sc.tmpScan.ensure(scanBytes)) { snprintf(err, 256, "bvh build: scan scratch alloc failed"); return false; }
+	while (m > kPlocTail) {
+		const int g = (m + kPlocBlock - 1) / kPlocBlock;
+		k_ploc_nn<<<g, kPlocBlock, 0, stream>>>(sc.cbox[cur].p, m, sc.nn.p);
+		k_ploc_merge<<<g, kPlocBlock, 0, stream>>>(sc.cid[cur].p, sc.cbox[cur].p, sc.nn.p, m, nodeCounter, t, sc.cidTmp.p, sc.cboxTmp.p, sc.valid.p);
+		CK(cub::DeviceScan::ExclusiveSum(sc.tmpScan.p, scanBytes, sc.valid.p, sc.pos.p, m, stream));
+		k_ploc_compact<<<g, kPlocBlock, 0, stream>>>(sc.cidTmp.p, sc.cboxTmp.p, sc.valid.p, sc.pos.p, m, sc.cid[cur ^ 1].p, sc.cbox[cur ^ 1].p, nOutDev);
+		int mNew = 0;
+		CK(cudaMemcpyAsync(&mNew, nOutDev, 4, cudaMemcpyDeviceToHost, stream));
+		CK(cudaStreamSynchronize(stream));
+		if (mNew >= m || mNew < 1) { snprintf(err, 256, "bvh build: PLOC made no progress (%d -> %d clusters)", m, mNew); return false; }
+		m = mNew, cur ^= 1;
+	}
+	if (m > 1) k_ploc_tail<<<1, kPlocTail, 0, stream>>>(sc.cid[cur].p, sc.cbox[cur].p, m, nodeCounter, t);
+	const int binRoot = n == 1 ? 0 : 2 * n - 2; // the last merge creates the root
+	// ---- collapse, level by level ----
 	int32_t cnt[2] = {1, 0}; // node 0 of this tree is the root
 	CK(cudaMemcpyAsync(counters, cnt, 8, cudaMemcpyHostToDevice, stream));
-	WorkItem rootItem{n == 1 ? 0 : 0, 0}; // n == 1: the only node is leaf node (n-1)+0 = 0
-	CK(cudaMemcpyAsync(q0.p, &rootItem, sizeof rootItem, cudaMemcpyHostToDevice, stream));
+	WorkItem rootItem{binRoot, 0};
+	CK(cudaMemcpyAsync(sc.q0.p, &rootItem, sizeof rootItem, cudaMemcpyHostToDevice, stream));
 	CollapseOut co{nodePool, boundsPool, counters, (uint32_t) nodeCursor, (uint32_t) primCursor};
 	int nIn = 1, levelFirst = 0;
-	WorkItem *qin = q0.p, *qout = q1.p;
+	WorkItem *qin = sc.q0.p, *qout = sc.q1.p;
 	*root = nodeCursor;
 	while (nIn > 0) {
 		if (levelStart) levelStart->push_back(nodeCursor + levelFirst);
-		CK(cudaMemsetAsync(qCount.p, 0, 4, stream));
-		k_collapse<<<(nIn + T - 1) / T, T, 0, stream>>>(qin, nIn, qout, qCount.p, t, n, valsSorted.p, maxLeaf, co, writer);
+		CK(cudaMemsetAsync(sc.qCount.p, 0, 4, stream));
+		k_collapse<TLAS><<<(nIn + 127) / 128, 128, 0, stream>>>(qin, nIn, qout, sc.qCount.p, t, n, sc.valsSorted.p, maxLeaf, co, writer);
 		int nOut = 0;
-		CK(cudaMemcpyAsync(&nOut, qCount.p, 4, cudaMemcpyDeviceToHost, stream));
+		CK(cudaMemcpyAsync(&nOut, sc.qCount.p, 4, cudaMemcpyDeviceToHost, stream));
 		CK(cudaStreamSynchronize(stream));
 		levelFirst += nIn;
 		nIn = nOut;
@@ -566,8 +723,8 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 					   const InstRec *dInstances, const InstRec *hInstances, int nInstances, const uint8_t *hMerge, int flatMax,
 					   const MotionWindow &motion, cudaStream_t stream, char *err) {
 	Impl &b = *m;
-	// triangles per leaf child: the node format addresses 8 leaf children x maxLeaf <= 32 primitives
-	const int maxLeaf = std::min(std::max(getenv("KRR_BVH_MAX_LEAF") ? atoi(getenv("KRR_BVH_MAX_LEAF")) : 3, 1), 4);
+	// triangles per leaf child: the hit mask of a node has 24 triangle bits = 8 leaf children x 3 triangles
+	const int maxLeaf = std::min(std::max(getenv("KRR_BVH_MAX_LEAF") ? atoi(getenv("KRR_BVH_MAX_LEAF")) : 3, 1), 3);
 	std::vector<int2> flats;
 	b.nMeshes = nMeshes, b.nInstances = nInstances;
 	// which instances go into the merged world-space BLAS, which meshes still need a BLAS of their own
@@ -585,7 +742,6 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			tlasIds.push_back(i);
 		}
 	}
-	if (mergedTris > 0x03ffffffu) { snprintf(err, 256, "bvh build: merged BLAS too large (%zu triangles)", mergedTris); return false; }
 	const bool haveMerged = !msrc.empty();
 	if (haveMerged) tlasIds.push_back(nInstances); // the pseudo-instance (api.cu appends its InstRec)
 	b.mergedInst = haveMerged ? nInstances : -1;
@@ -598,7 +754,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		if (meshNeedsBlas[i]) totalTris += hMeshes[i].nTri, maxTris = std::max(maxTris, hMeshes[i].nTri), nBlas++;
 	const int tlasReserve = nInstances + 2;
 	const size_t nodeCap  = totalTris + (size_t) nBlas + (size_t) tlasReserve + 8;
-	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(nInstances + 1) ||
+	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(8 * (size_t) (nInstances + 2) + 8) ||
 		!b.meshBoxes.alloc(nMeshes + 1) || !b.instBoxes.alloc(nInstances + 1) || !b.counters.alloc(2) || !b.tlasIds.alloc(tlasIds.size())) {
 		snprintf(err, 256, "bvh build: out of device memory (%zu triangles)", totalTris);
 		return false;
@@ -630,7 +786,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			continue;
 		}
 		int root = 0;
-		if (!buildTree(primBoxes.p, mr.nTri, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
+		if (!buildTree<false>(primBoxes.p, mr.nTri, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 			return false;
 		b.blasRoots[i] = root;
 	}
@@ -654,7 +810,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 			CK(cudaStreamSynchronize(stream)); // dsrc / pairs die with this scope
 		} else {
 			int root = 0;
-			if (!buildTree(primBoxes.p, (int) mergedTris, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
+			if (!buildTree<false>(primBoxes.p, (int) mergedTris, maxLeaf, b.nodes.p, b.nodeBounds.p, b.counters.p, nodeCursor, primCursor, wr, stream, cb.p, nullptr, &root, err, scratch))
 				return false;
 			b.mergedRoot = root;
 		}
@@ -675,7 +831,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 																		 cb.p, motion.xnodes, motion.keys, motion.w0, motion.w1);
 		int tlasCursor = 0, tlasPrims = 0, root = 0;
 		InstWriter iw{b.tlasInst.p, b.tlasIds.p};
-		if (!buildTree(primBoxes.p, b.nTlasPrims, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err, scratch))
+		if (!buildTree<true>(primBoxes.p, b.nTlasPrims, 1, b.nodes.p, b.nodeBounds.p, b.counters.p, tlasCursor, tlasPrims, iw, stream, cb.p, &b.tlasLevelStart, &root, err, scratch))
 			return false;
 		if (tlasCursor > tlasReserve) { snprintf(err, 256, "bvh build: TLAS node reservation exceeded"); return false; }
 		b.tlasNodeCount = tlasCursor;
