@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define KRR_WFPT_ABI_VERSION 4
+#define KRR_WFPT_ABI_VERSION 5
 
 enum {
 	KRR_OK			  = 0,
@@ -252,6 +252,23 @@ int krr_wfpt_render_to_host(KrrWfpt *h, float *film_rgba_host, void *cuda_stream
  * alternate).  The host buffer holds the frame once krr_wfpt_wait_host() has returned. */
 int krr_wfpt_render_to_host_async(KrrWfpt *h, float *film_rgba_host, void *cuda_stream);
 int krr_wfpt_wait_host(KrrWfpt *h);
+
+/* ---- multi-GPU: scene replicated, work split by image tile x spp slice, ONE exchange step ----
+ * The reference is single-device (src/core/device/context.cpp:37-40); these entry points are the product's own.
+ * One handle per GPU; the film-reduction communicator is NCCL over NVLink (resolved with dlopen at the first call:
+ * KRR_E_UNSUPPORTED when libnccl.so.2 is absent).  Either every process calls krr_wfpt_comm_init_rank with the id
+ * rank 0 obtained from krr_wfpt_comm_unique_id (one process per GPU), or ONE process passes all its handles to
+ * krr_wfpt_comm_init_all (one host thread per handle afterwards: kiraray_b200/host MultiDeviceRenderApp). */
+int krr_wfpt_comm_unique_id(uint8_t *out128);
+int krr_wfpt_comm_init_rank(KrrWfpt *h, const uint8_t *id128, int32_t world, int32_t rank);
+int krr_wfpt_comm_init_all(KrrWfpt **handles, int32_t n);
+int krr_wfpt_comm_destroy(KrrWfpt *h);
+/* film (device RGBA32F, W x H) of every rank is summed onto `root` in place (ncclReduce, ordered on the stream),
+ * then multiplied by `scale` on the root (1 / spp slices).  World size 1: only the scale. */
+int krr_wfpt_reduce_film(KrrWfpt *h, float *film_rgba_device, int32_t root, float scale, void *cuda_stream);
+/* krr_wfpt_render + krr_wfpt_reduce_film + (root only) the pipelined read-back of krr_wfpt_render_to_host_async;
+ * film_rgba_host may be NULL on the other ranks.  krr_wfpt_wait_host() as above. */
+int krr_wfpt_render_reduce_to_host_async(KrrWfpt *h, float *film_rgba_host, int32_t root, float scale, void *cuda_stream);
 
 /* Multi-GPU work split by image tile (no reference counterpart: single device,
  * device/context.cpp:37-40).  This handle renders pixel rows [row_begin,row_end) only; the other

@@ -156,6 +156,12 @@ def load_wfpt():
         "krr_wfpt_render_to_host": [P, P, P],
         "krr_wfpt_render_to_host_async": [P, P, P],
         "krr_wfpt_wait_host": [P],
+        "krr_wfpt_comm_unique_id": [P],
+        "krr_wfpt_comm_init_rank": [P, P, I32, I32],
+        "krr_wfpt_comm_init_all": [C.POINTER(P), I32],
+        "krr_wfpt_comm_destroy": [P],
+        "krr_wfpt_reduce_film": [P, P, I32, F, P],
+        "krr_wfpt_render_reduce_to_host_async": [P, P, I32, F, P],
         "krr_wfpt_render_megakernel": [P, U64, C.POINTER(KrrCameraData), P, P],
         "krr_wfpt_set_partition": [P, I32, I32],
         "krr_wfpt_get_stats": [P, C.POINTER(KrrStats)],
@@ -435,6 +441,26 @@ class Wfpt:
 
     def wait_host(self):
         self._ck(self.lib.krr_wfpt_wait_host(self.h), "wait_host")
+
+    # ---- multi-GPU film reduction (NCCL inside the product library) ----
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.krr_wfpt_comm_unique_id(buf), "comm_unique_id")
+        return bytes(buf)
+
+    def comm_init_rank(self, uid, world, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.krr_wfpt_comm_init_rank(self.h, buf, world, rank), "comm_init_rank")
+
+    def comm_destroy(self):
+        self._ck(self.lib.krr_wfpt_comm_destroy(self.h), "comm_destroy")
+
+    def reduce_film(self, film_device_ptr, root=0, scale=1.0, stream=None):
+        self._ck(self.lib.krr_wfpt_reduce_film(self.h, P(film_device_ptr), root, scale, P(stream or 0)), "reduce_film")
+
+    def render_reduce_to_host_async(self, film, root=0, scale=1.0, stream=None):
+        ptr = film.ctypes.data_as(P) if film is not None else P(0)
+        self._ck(self.lib.krr_wfpt_render_reduce_to_host_async(self.h, ptr, root, scale, P(stream or 0)), "render_reduce_to_host_async")
 
     def instance_xf(self, ids, times):
         """(n, 2, 12): object->world and world->object of each instance at each ray time, from the device"""

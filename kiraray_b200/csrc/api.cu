@@ -1,12 +1,15 @@
 // api.cu -- handle, scene upload, stage driver and the C ABI (include/krr_wfpt.h).
 // Host code is C++17 compiled by nvcc's host compiler; everything the caller sees is extern "C".
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> // types and prototypes only: the library is dlopen-ed at the first collective call
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../host/json.h"
@@ -152,10 +155,13 @@ struct KrrWfpt : WaveState {
 	int bands = 0;		 // "bands": see WaveState; 0 = automatic (2 for a scene that is one flat triangle list, else 1)
 	int activeBands = 1; // decided by begin_frame
 	// pipelined film read-back (krr_wfpt_render_to_host_async): two device films, a copy stream
-	Buf<float4> asyncFilm[2];
+	Buf<float4> asyncFilm[2], syncFilm;
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
 	int asyncSlot = 0;
+	// multi-GPU: this handle's rank in the film-reduction communicator (krr_wfpt_comm_init_rank / _init_all)
+	ncclComm_t comm = nullptr;
+	int commRank = 0, commWorld = 1;
 	int refill = 0;		 // "refill": idle lanes of a trace warp that trigger finalisation + refill; 0 = automatic (kRefill / kRefillFlat)
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
 	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
@@ -182,6 +188,9 @@ struct KrrWfpt : WaveState {
 	}
 
 	int pixelCount() const { return (rowEnd - rowBegin) * width; }
+	// launch grids (occupancy x SM count of THIS handle's device), one entry per kernel instantiation.  Kept in the
+	// handle: handles of one process may sit on different devices and be driven by different host threads.
+	std::unordered_map<const void *, int> gridCache;
 };
 
 namespace {
@@ -344,10 +353,14 @@ KrrCameraDev makeCamera(const KrrCameraData *c) {
 }
 
 template <typename K> int gridFor(KrrWfpt *h, K kernel, int block) {
+	auto it = h->gridCache.find((const void *) kernel);
+	if (it != h->gridCache.end()) return it->second;
 	int occ = 1;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0);
 	if (occ < 1) occ = 1;
-	return h->numSMs * occ; // a whole number of waves: every SM gets the same number of resident CTAs
+	const int grid = h->numSMs * occ; // a whole number of waves: every SM gets the same number of resident CTAs
+	h->gridCache[(const void *) kernel] = grid;
+	return grid;
 }
 
 } // namespace
@@ -388,6 +401,7 @@ extern "C" void krr_wfpt_destroy(KrrWfpt *h) {
 		if (h->evJoin[b]) cudaEventDestroy(h->evJoin[b]);
 	}
 	if (h->evFork) cudaEventDestroy(h->evFork);
+	krr_wfpt_comm_destroy(h);
 	if (h->copyStream) cudaStreamDestroy(h->copyStream);
 	for (int i = 0; i < 2; i++) {
 		if (h->evRendered[i]) cudaEventDestroy(h->evRendered[i]);
@@ -846,8 +860,7 @@ struct StageTimer { // RAII: brackets one launch with events when profiling is o
 	~StageTimer() { if (on) { cudaEventRecord(rec.b, st); h->evRecs.push_back(rec); } }
 };
 template <int MT> void launchScatter(KrrWfpt *h, const Wavefront &wf, int depth, cudaStream_t st, int &withHitMiss) {
-	static int grid = 0, gridM = 0;
-	if (!grid) grid = gridFor(h, k_scatter<MT, false>, kScatterBlock), gridM = gridFor(h, k_scatter<MT, true>, kScatterBlock);
+	const int grid = gridFor(h, k_scatter<MT, false>, kScatterBlock), gridM = wf.scene.hasMotion ? gridFor(h, k_scatter<MT, true>, kScatterBlock) : 0;
 	StageTimer t(h, KRR_STAGE_SCATTER, st);
 	if (wf.scene.hasMotion) launchK(h->usePdl(), k_scatter<MT, true>, gridM, kScatterBlock, st, wf, depth, withHitMiss);
 	else launchK(h->usePdl(), k_scatter<MT, false>, grid, kScatterBlock, st, wf, depth, withHitMiss);
@@ -867,36 +880,24 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	if (!h->frameBegun) return fail(KRR_E_STATE, "begin_frame must precede render");
 	CUDA_OK(cudaSetDevice(h->device));
 	cudaStream_t st = (cudaStream_t) stream;
-	static int gridCam = 0, gridTrace = 0, gridHit = 0, gridShadow = 0, gridResolve = 0;
-	if (!gridCam) {
-		gridCam = gridFor(h, k_generate_camera_rays, 256), gridTrace = gridFor(h, k_trace_closest<false>, 128);
-		gridHit = gridFor(h, k_handle_hit_miss<false>, 128), gridShadow = gridFor(h, k_trace_shadow<false>, 128), gridResolve = gridFor(h, k_resolve, 256);
-	}
-	// scenes with moving instances run the variants that evaluate SRT chains at the ray's time
-	static int gridTraceM = 0, gridHitM = 0, gridShadowM = 0;
-	const bool motion = h->scene.hasMotion != 0;
-	if (motion && !gridTraceM)
-		gridTraceM = gridFor(h, k_trace_closest<true>, 128), gridHitM = gridFor(h, k_handle_hit_miss<true>, 128), gridShadowM = gridFor(h, k_trace_shadow<true>, 128);
-	static int gridMSample = 0, gridMScatter = 0, gridShadowTr = 0;
-	const bool media = h->enableMedium && h->sceneHasMedia;
-	if (media && !gridMSample) {
-		gridMSample = gridFor(h, k_medium_sample, 128), gridMScatter = gridFor(h, k_medium_scatter, 128);
-		gridShadowTr = gridFor(h, k_trace_shadow_tr<kTraceMotion>, kTraceBlock);
-	}
-	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
-	static int gridFused = 0, gridFusedM = 0;
-	if (!gridFused) gridFused = gridFor(h, k_trace_fused<false>, 128);
-	if (motion && !gridFusedM) gridFusedM = gridFor(h, k_trace_fused<true>, 128);
+	const bool motion = h->scene.hasMotion != 0; // scenes with moving instances run the variants that evaluate SRT chains at the ray's time
+	const bool media  = h->enableMedium && h->sceneHasMedia;
 	// a scene that is one flat triangle list runs the kTraceFlat instantiations (branch-free triangle pairs)
-	static int gridTraceF = 0, gridFusedF = 0;
 	bool flatScene = false;
 	{
 		const BvhDev bd = h->bvh.device();
 		flatScene = !motion && bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot);
 	}
-	if (flatScene && !gridTraceF) gridTraceF = gridFor(h, k_trace_closest<kTraceFlat>, 128), gridFusedF = gridFor(h, k_trace_fused<kTraceFlat>, 128);
-	static int gridShadowTrF = 0;
-	if (flatScene && media && !gridShadowTrF) gridShadowTrF = gridFor(h, k_trace_shadow_tr<kTraceFlat>, kTraceBlock);
+	const int gridCam = gridFor(h, k_generate_camera_rays, 256), gridResolve = gridFor(h, k_resolve, 256);
+	const int gridTrace = gridFor(h, k_trace_closest<kTraceStatic>, 128), gridHit = gridFor(h, k_handle_hit_miss<false>, 128);
+	const int gridShadow = gridFor(h, k_trace_shadow<kTraceStatic>, 128), gridFused = gridFor(h, k_trace_fused<kTraceStatic>, 128);
+	const int gridTraceM = motion ? gridFor(h, k_trace_closest<kTraceMotion>, 128) : 0, gridHitM = motion ? gridFor(h, k_handle_hit_miss<true>, 128) : 0;
+	const int gridShadowM = motion ? gridFor(h, k_trace_shadow<kTraceMotion>, 128) : 0, gridFusedM = motion ? gridFor(h, k_trace_fused<kTraceMotion>, 128) : 0;
+	const int gridMSample = media ? gridFor(h, k_medium_sample, 128) : 0, gridMScatter = media ? gridFor(h, k_medium_scatter, 128) : 0;
+	const int gridShadowTr = media ? gridFor(h, k_trace_shadow_tr<kTraceMotion>, kTraceBlock) : 0;
+	const int gridTraceF = flatScene ? gridFor(h, k_trace_closest<kTraceFlat>, 128) : 0, gridFusedF = flatScene ? gridFor(h, k_trace_fused<kTraceFlat>, 128) : 0;
+	const int gridShadowTrF = flatScene && media ? gridFor(h, k_trace_shadow_tr<kTraceFlat>, kTraceBlock) : 0;
+	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
 	const bool pdl = h->usePdl();
 	const int nDepthSlots = h->maxDepth + 2;
 	// bands: band 0 runs on the caller's stream, bands 1.. on their own streams, forked from and joined to it
@@ -1025,10 +1026,8 @@ extern "C" int krr_wfpt_render_megakernel(KrrWfpt *h, uint64_t frameIndex, const
 	}
 	Wavefront wf = makeWavefront(h, 0);
 	MegaParams mp{h->width, h->height, h->spp, h->maxDepth, h->nee ? 1 : 0, h->probRR, (uint32_t) frameIndex};
-	static int grid = 0, gridM = 0;
-	if (!grid) grid = gridFor(h, k_megakernel<false>, kTraceBlock), gridM = gridFor(h, k_megakernel<true>, kTraceBlock);
-	if (h->scene.hasMotion) k_megakernel<true><<<gridM, kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
-	else k_megakernel<false><<<grid, kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
+	if (h->scene.hasMotion) k_megakernel<true><<<gridFor(h, k_megakernel<true>, kTraceBlock), kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
+	else k_megakernel<false><<<gridFor(h, k_megakernel<false>, kTraceBlock), kTraceBlock, 0, st>>>(wf, mp, (float4 *) film);
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;
 	h->launches	  = 1;
@@ -1037,7 +1036,7 @@ extern "C" int krr_wfpt_render_megakernel(KrrWfpt *h, uint64_t frameIndex, const
 
 extern "C" int krr_wfpt_render_to_host(KrrWfpt *h, float *film_host, void *stream) {
 	if (!h || !film_host) return fail(KRR_E_INVALID, "null argument");
-	static thread_local Buf<float4> staging;
+	Buf<float4> &staging = h->syncFilm; // per handle (a handle belongs to one device)
 	size_t n = (size_t) h->width * h->height;
 	if (staging.alloc(n)) return KRR_E_CUDA;
 	int rc = krr_wfpt_render(h, (float *) staging.p, stream);
@@ -1075,6 +1074,161 @@ extern "C" int krr_wfpt_render_to_host_async(KrrWfpt *h, float *film_host, void 
 	CUDA_OK(cudaStreamWaitEvent(h->copyStream, h->evRendered[slot], 0));
 	CUDA_OK(cudaMemcpyAsync(film_host, h->asyncFilm[slot].p, n * 16, cudaMemcpyDeviceToHost, h->copyStream));
 	CUDA_OK(cudaEventRecord(h->evCopied[slot], h->copyStream));
+	return KRR_OK;
+}
+
+// =================================================================================================
+// Multi-GPU: the ONE exchange step of the path -- the films of the ranks (image tiles add up, spp
+// slices average) are summed onto the root rank with ncclReduce over NVLink.  The reference has no counterpart
+// (single device, src/core/device/context.cpp:37-40).  NCCL is resolved at run time (dlopen "libnccl.so.2": the
+// copy a host process already carries, e.g. torch's, or the system one), so a single-GPU build has no NCCL
+// dependency; a missing library is an error return, never a fallback.
+namespace {
+struct NcclApi {
+	void *lib = nullptr;
+	decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+	decltype(&ncclCommInitRank) commInitRank = nullptr;
+	decltype(&ncclCommInitAll) commInitAll = nullptr;
+	decltype(&ncclCommDestroy) commDestroy = nullptr;
+	decltype(&ncclReduce) reduce = nullptr;
+	decltype(&ncclGetErrorString) errorString = nullptr;
+	bool ok = false;
+};
+NcclApi &nccl() {
+	static NcclApi api = [] {
+		NcclApi a;
+		a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!a.lib) return a;
+		a.getUniqueId  = (decltype(a.getUniqueId)) dlsym(a.lib, "ncclGetUniqueId");
+		a.commInitRank = (decltype(a.commInitRank)) dlsym(a.lib, "ncclCommInitRank");
+		a.commInitAll  = (decltype(a.commInitAll)) dlsym(a.lib, "ncclCommInitAll");
+		a.commDestroy  = (decltype(a.commDestroy)) dlsym(a.lib, "ncclCommDestroy");
+		a.reduce	   = (decltype(a.reduce)) dlsym(a.lib, "ncclReduce");
+		a.errorString  = (decltype(a.errorString)) dlsym(a.lib, "ncclGetErrorString");
+		a.ok = a.getUniqueId && a.commInitRank && a.commInitAll && a.commDestroy && a.reduce && a.errorString;
+		return a;
+	}();
+	return api;
+}
+#define NCCL_OK(x)                                                                                         \
+	do {                                                                                                   \
+		ncclResult_t r_ = (x);                                                                             \
+		if (r_ != ncclSuccess) return fail(KRR_E_CUDA, "%s failed: %s", #x, nccl().errorString(r_));       \
+	} while (0)
+int needNccl() { return nccl().ok ? KRR_OK : fail(KRR_E_UNSUPPORTED, "libnccl.so.2 not found (multi-GPU film reduction needs NCCL): %s", dlerror() ? dlerror() : "missing symbols"); }
+
+__global__ void k_scale_film(float4 *film, size_t n, float s) {
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		float4 v = film[i];
+		film[i]	 = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+	}
+}
+} // namespace
+
+extern "C" int krr_wfpt_comm_unique_id(uint8_t *out128) {
+	if (!out128) return fail(KRR_E_INVALID, "null argument");
+	if (int rc = needNccl()) return rc;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	NCCL_OK(nccl().getUniqueId(&id));
+	memcpy(out128, &id, 128);
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_comm_init_rank(KrrWfpt *h, const uint8_t *id128, int32_t world, int32_t rank) {
+	if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return fail(KRR_E_INVALID, "bad argument");
+	if (int rc = needNccl()) return rc;
+	krr_wfpt_comm_destroy(h);
+	CUDA_OK(cudaSetDevice(h->device));
+	ncclUniqueId id;
+	memcpy(&id, id128, 128);
+	NCCL_OK(nccl().commInitRank(&h->comm, world, id, rank));
+	h->commRank = rank, h->commWorld = world;
+	return KRR_OK;
+}
+
+// one process, one handle per device (each handle was created with its device current): rank i = handles[i]
+extern "C" int krr_wfpt_comm_init_all(KrrWfpt **handles, int32_t n) {
+	if (!handles || n < 1 || n > 64) return fail(KRR_E_INVALID, "bad argument");
+	if (int rc = needNccl()) return rc;
+	int devs[64];
+	ncclComm_t comms[64];
+	for (int i = 0; i < n; i++) {
+		if (!handles[i]) return fail(KRR_E_INVALID, "null handle");
+		devs[i] = handles[i]->device;
+		for (int j = 0; j < i; j++)
+			if (devs[j] == devs[i]) return fail(KRR_E_INVALID, "handles %d and %d are on the same device %d: NCCL needs one device per rank", j, i, devs[i]);
+		krr_wfpt_comm_destroy(handles[i]);
+	}
+	NCCL_OK(nccl().commInitAll(comms, n, devs));
+	for (int i = 0; i < n; i++) handles[i]->comm = comms[i], handles[i]->commRank = i, handles[i]->commWorld = n;
+	return KRR_OK;
+}
+
+extern "C" int krr_wfpt_comm_destroy(KrrWfpt *h) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	if (h->comm) {
+		cudaSetDevice(h->device);
+		nccl().commDestroy(h->comm);
+		h->comm = nullptr, h->commRank = 0, h->commWorld = 1;
+	}
+	return KRR_OK;
+}
+
+// film (device, W x H RGBA32F, on every rank) is summed onto `root` IN PLACE and multiplied by `scale` there
+// (1 / number of spp slices); the other ranks' films are left unchanged.  Ordered on `stream`.
+extern "C" int krr_wfpt_reduce_film(KrrWfpt *h, float *film, int32_t root, float scale, void *stream) {
+	if (!h || !film) return fail(KRR_E_INVALID, "null argument");
+	if (h->width <= 0) return fail(KRR_E_STATE, "resize first");
+	const size_t n = (size_t) h->width * h->height;
+	cudaStream_t st = (cudaStream_t) stream;
+	if (h->commWorld > 1) {
+		if (!h->comm) return fail(KRR_E_STATE, "krr_wfpt_comm_init_rank / _init_all first");
+		if (root < 0 || root >= h->commWorld) return fail(KRR_E_INVALID, "bad root");
+		CUDA_OK(cudaSetDevice(h->device));
+		NCCL_OK(nccl().reduce(film, film, n * 4, ncclFloat32, ncclSum, root, h->comm, st));
+	}
+	if (h->commRank == root && scale != 1.f) {
+		k_scale_film<<<h->numSMs * 4, 256, 0, st>>>((float4 *) film, n, scale);
+		CUDA_OK(cudaGetLastError());
+	}
+	return KRR_OK;
+}
+
+// render + reduce + (root) pipelined read-back: as krr_wfpt_render_to_host_async, with the film reduction
+// between the render and the copy.  film_host is only used on the root rank.
+extern "C" int krr_wfpt_render_reduce_to_host_async(KrrWfpt *h, float *film_host, int32_t root, float scale, void *stream) {
+	if (!h) return fail(KRR_E_INVALID, "null handle");
+	const bool isRoot = h->commRank == root;
+	if (isRoot && !film_host) return fail(KRR_E_INVALID, "the root rank needs a host film");
+	CUDA_OK(cudaSetDevice(h->device));
+	const size_t n = (size_t) h->width * h->height;
+	if (!h->copyStream) {
+		CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			CUDA_OK(cudaEventCreateWithFlags(&h->evRendered[i], cudaEventDisableTiming));
+			CUDA_OK(cudaEventCreateWithFlags(&h->evCopied[i], cudaEventDisableTiming));
+		}
+	}
+	const int slot = h->asyncSlot;
+	h->asyncSlot ^= 1;
+	if (h->asyncFilm[slot].n != n) {
+		CUDA_OK(cudaStreamSynchronize(h->copyStream));
+		if (h->asyncFilm[slot].alloc(n)) return KRR_E_CUDA;
+	}
+	cudaStream_t st = (cudaStream_t) stream;
+	CUDA_OK(cudaStreamWaitEvent(st, h->evCopied[slot], 0));
+	int rc = krr_wfpt_render(h, (float *) h->asyncFilm[slot].p, stream);
+	if (rc) return rc;
+	rc = krr_wfpt_reduce_film(h, (float *) h->asyncFilm[slot].p, root, scale, stream);
+	if (rc) return rc;
+	if (isRoot) {
+		CUDA_OK(cudaEventRecord(h->evRendered[slot], st));
+		CUDA_OK(cudaStreamWaitEvent(h->copyStream, h->evRendered[slot], 0));
+		CUDA_OK(cudaMemcpyAsync(film_host, h->asyncFilm[slot].p, n * 16, cudaMemcpyDeviceToHost, h->copyStream));
+		CUDA_OK(cudaEventRecord(h->evCopied[slot], h->copyStream));
+	}
 	return KRR_OK;
 }
 

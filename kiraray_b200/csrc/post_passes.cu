@@ -19,15 +19,13 @@ void setLastError(const char *fmt, ...); // api.cu
 namespace {
 
 constexpr int kPostBlock = 256;
+// These entry points take no handle: they work on the CURRENT device of the calling thread (the device the
+// film pointer belongs to), so nothing device-specific may be cached process-wide.
 int postGrid() {
-	static int grid = 0;
-	if (!grid) {
-		int dev = 0, sms = 148;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		grid = sms * 8;
-	}
-	return grid;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	return sms * 8;
 }
 
 __global__ void k_accumulate_f64(double4 *accum, float4 *film, long long n, unsigned long long accumCount, unsigned long long maxAccum, int movingAverage) {
@@ -170,14 +168,19 @@ extern "C" int krr_accumulate_read_average(const void *accum, int32_t isDouble, 
 extern "C" int krr_error_metric_f32(const float *film, const float *reference, int64_t n, int32_t metric, double *result_host, void *stream) {
 	if (!film || !reference || !result_host || n <= 0) return fail(KRR_E_INVALID, "krr_error_metric_f32: bad argument");
 	if (metric < 0 || metric > KRR_METRIC_REL_MSE) return fail(KRR_E_INVALID, "krr_error_metric_f32: unknown metric");
-	static thread_local double *dSum = nullptr;
-	if (!dSum) POST_OK(cudaMalloc((void **) &dSum, 8));
-	POST_OK(cudaMemsetAsync(dSum, 0, 8, (cudaStream_t) stream));
-	k_error_metric<<<postGrid(), kPostBlock, 0, (cudaStream_t) stream>>>((const float4 *) film, (const float4 *) reference, n, metric, dSum);
-	POST_OK(cudaGetLastError());
+	// reduction scratch on the current device, freed before returning (the call synchronises anyway)
+	double *dSum = nullptr;
+	POST_OK(cudaMallocAsync((void **) &dSum, 8, (cudaStream_t) stream));
 	double sum = 0;
-	POST_OK(cudaMemcpyAsync(&sum, dSum, 8, cudaMemcpyDeviceToHost, (cudaStream_t) stream));
-	POST_OK(cudaStreamSynchronize((cudaStream_t) stream));
+	cudaError_t e = cudaMemsetAsync(dSum, 0, 8, (cudaStream_t) stream);
+	if (e == cudaSuccess) {
+		k_error_metric<<<postGrid(), kPostBlock, 0, (cudaStream_t) stream>>>((const float4 *) film, (const float4 *) reference, n, metric, dSum);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&sum, dSum, 8, cudaMemcpyDeviceToHost, (cudaStream_t) stream);
+	cudaFreeAsync(dSum, (cudaStream_t) stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
+	if (e != cudaSuccess) { setLastError("krr_error_metric_f32: %s", cudaGetErrorString(e)); return KRR_E_CUDA; }
 	*result_host = sum / (double) n;
 	return KRR_OK;
 }

@@ -544,7 +544,7 @@ bool loadLight(Scene &scene, const json &params, const float nodeXf[12], const s
 	return true;
 }
 
-void addBoxMesh(Scene &scene, const float lo[3], const float hi[3], int mediumInside, const float xf[12]) {
+void addBoxMesh(Scene &scene, const float lo[3], const float hi[3], int mediumInside, const float xf[12], int mediumOutside = -1) {
 	// krrscene.cpp:95-113
 	HostMesh mesh;
 	mesh.name = "Medium box";
@@ -556,6 +556,7 @@ void addBoxMesh(Scene &scene, const float lo[3], const float hi[3], int mediumIn
 	for (auto &t : idx) mesh.indices.insert(mesh.indices.end(), t, t + 3);
 	mesh.material	  = -1;
 	mesh.mediumInside = mediumInside;
+	mesh.mediumOutside = mediumOutside; // a medium box nested in another medium ("outside": index of the enclosing medium)
 	HostInstance inst;
 	inst.mesh = (int) scene.meshes.size();
 	memcpy(inst.transform, xf, 48);
@@ -590,7 +591,7 @@ bool loadMedium(Scene &scene, const json &params, const float nodeXf[12]) {
 			m.hasBound = true;
 			for (int k = 0; k < 3; k++) m.boundMin[k] = lo[k] + nodeXf[k * 4 + 3], m.boundMax[k] = hi[k] + nodeXf[k * 4 + 3];
 			scene.media.push_back(m);
-			addBoxMesh(scene, lo, hi, id, nodeXf);
+			addBoxMesh(scene, lo, hi, id, nodeXf, params.value("outside", -1));
 		} else {
 			scene.media.push_back(m);
 			if (params.contains("meshes"))
@@ -628,7 +629,7 @@ bool loadMedium(Scene &scene, const json &params, const float nodeXf[12]) {
 		for (int k = 0; k < 3; k++) m.boundMin[k] = lo[k] + nodeXf[k * 4 + 3], m.boundMax[k] = hi[k] + nodeXf[k * 4 + 3];
 		int id = (int) scene.media.size();
 		scene.media.push_back(std::move(m));
-		addBoxMesh(scene, lo, hi, id, nodeXf);
+		addBoxMesh(scene, lo, hi, id, nodeXf, params.value("outside", -1));
 		return true;
 	}
 	return false;

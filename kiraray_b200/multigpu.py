@@ -9,7 +9,11 @@ frames in AccumulatePass, accumulate.cu:30-52).  So the work is a T x S grid of
   * S spp slices   -- rank s renders frame indices  first + s, first + s + S, ...  (every frame index
                       seeds a different PCG sequence: sampleIndex = frameIndex * spp),
 with the scene replicated.  The ONE exchange step is the film accumulation: a sum-reduce of the
-RGBA32F film to rank 0 (NCCL over NVLink on the GPUs, gloo in the CPU tests), then a division by S.
+RGBA32F film to rank 0, then a division by S.  On the GPUs that is the PRODUCT's own entry point
+(krr_wfpt_reduce_film: ncclReduce over NVLink inside libkrr_wfpt.so, include/krr_wfpt.h; the C++ host
+layer drives the same entry from one process with one thread per device, host/multi_device.cpp);
+this module only carries the partition arithmetic and hands the NCCL unique id from rank 0 to the
+other processes.  `reduce_film` below (torch.distributed) is the CPU stand-in of the gloo tests.
 No other collective is on the path.
 """
 from dataclasses import dataclass
@@ -72,3 +76,39 @@ def reduce_film(film, part, dist=None, dst=0):
     if part.rank == dst and part.spp_slices > 1:
         film /= part.spp_slices
     return film
+
+
+class FilmReducer:
+    """One process per GPU (torchrun): binds the pass handle of this rank to the film-reduction communicator of
+    the product library.  The NCCL unique id is created by rank 0 (krr_wfpt_comm_unique_id) and travels to the
+    other processes through the torch.distributed process group -- the only thing torch is used for here."""
+
+    def __init__(self, gpu, part, dist=None):
+        self.gpu, self.part, self.dist = gpu, part, dist
+        self.scale = 1.0 / part.spp_slices
+        self.native = False
+        if dist is not None and part.world > 1:
+            import torch
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if part.rank == 0:
+                uid = torch.frombuffer(bytearray(gpu.comm_unique_id()), dtype=torch.uint8).clone()
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            gpu.comm_init_rank(bytes(uid.cpu().numpy().tobytes()), part.world, part.rank)
+            self.native = True
+
+    def reduce(self, film, stream=None):
+        """film: CUDA tensor (H, W, 4); summed onto rank 0 in place and divided by the spp slices there."""
+        if self.native or self.scale != 1.0:
+            self.gpu.reduce_film(film.data_ptr(), 0, self.scale, stream)
+
+    def render_reduce_to_host_async(self, film_host, stream=None):
+        self.gpu.render_reduce_to_host_async(film_host if self.part.rank == 0 else None, 0, self.scale, stream)
+
+    def wait_host(self):
+        self.gpu.wait_host()
+
+    def close(self):
+        if self.native:
+            self.gpu.comm_destroy()
+            self.native = False
