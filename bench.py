@@ -285,7 +285,7 @@ def main():
             raise SystemExit(f"--strong: spp {spp_total} is not divisible by the {part.spp_slices} spp slices")
         spp = spp_total // part.spp_slices
     # debug_taps off: the C ABI's default (the ctypes test binding turns the parity taps on by default)
-    gpu = krr.Wfpt(params=dict(wl.params, spp=spp, debug_taps=False, **(json.loads(args.params) if args.params else {})))
+    gpu = krr.Wfpt(params={**wl.params, "spp": spp, "debug_taps": False, **(json.loads(args.params) if args.params else {})})
     t0 = time.time()
     gpu.set_scene(wl.desc)
     accel_build_s = time.time() - t0

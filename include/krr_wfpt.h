@@ -287,7 +287,8 @@ int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out);
 enum { KRR_STAGE_CAMERA = 0, KRR_STAGE_CLOSEST = 1, KRR_STAGE_HIT_MISS = 2, KRR_STAGE_SCATTER = 3, KRR_STAGE_SHADOW = 4,
 	   KRR_STAGE_RESOLVE = 5, KRR_STAGE_MEDIUM = 6,
 	   KRR_STAGE_TRACE = 7, /* fused launch: shadow rays of depth d + closest rays of depth d + 1 */
-	   KRR_STAGE_COUNT = 8 };
+	   KRR_STAGE_TAIL = 8,	/* tail launch: every remaining bounce of the paths still alive at "tail_depth" */
+	   KRR_STAGE_COUNT = 9 };
 int krr_wfpt_set_profiling(KrrWfpt *h, int32_t enable);
 int krr_wfpt_get_stage_times(KrrWfpt *h, double *ms, int32_t *launches, int32_t reset);
 /* the same events launch by launch, in issue order: stage id and milliseconds of each; returns the

@@ -482,13 +482,13 @@ class Wfpt:
         self._ck(self.lib.krr_wfpt_get_stats(self.h, C.byref(s)), "get_stats")
         return s.as_dict()
 
-    STAGES = ["camera", "closest", "hit_miss", "scatter", "shadow", "resolve", "medium", "trace"]
+    STAGES = ["camera", "closest", "hit_miss", "scatter", "shadow", "resolve", "medium", "trace", "tail"]
 
     def set_profiling(self, on):
         self._ck(self.lib.krr_wfpt_set_profiling(self.h, int(on)), "set_profiling")
 
     def stage_times(self, reset=True):
-        ms, n = (C.c_double * 8)(), (I32 * 8)()
+        ms, n = (C.c_double * len(self.STAGES))(), (I32 * len(self.STAGES))()
         self._ck(self.lib.krr_wfpt_get_stage_times(self.h, ms, n, int(reset)), "get_stage_times")
         return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(self.STAGES)}
 

@@ -91,6 +91,7 @@ Xf xfInverse(const Xf &t) {
 // (a launch costs 20-35 us however few rays it has).  The parity taps, debug captures and the per-stage
 // event timing run the frame as ONE band (band 0 is always allocated for the whole partition).
 constexpr int kMaxBands = 4;
+constexpr int kTailAutoFlat = 0, kTailAutoTree = 0; // automatic "tail_depth" per scene kind (0 = off until measured)
 struct WaveState {
 	Buf<float4> L, pixel, rayBuf[2][7], shadowBuf[5];
 	Buf<uint64_t> rng;
@@ -115,7 +116,15 @@ struct KrrWfpt : WaveState {
 	bool pdl = false;		 // "pdl": programmatic dependent launch between the stage kernels (measured: -1.6 % on the bench workload, so off)
 	bool usePdl() const { return pdl && !profile; }
 	bool implicitDepth0 = true; // "implicit_depth0": depth-0 ray items store origin + direction only
+	// "tail_depth": from this loop depth on the paths are finished by ONE launch of the tail kernel (k_tail) instead of
+	// 2 launches per depth; 0 = never, -1 = automatic (kTailAuto*).  Fused schedule only.
+	int tailDepth = -1;
+	// "frame_batch": F >= 1 frames (frame indices frameIndex .. frameIndex + F - 1) rendered by the same launches;
+	// the film is their mean (Params::layers).  Takes effect at the next resize / set_scene / set_partition.
+	int frameBatch = 1;
+	int layers() const { return debugState ? 1 : frameBatch; } // the parity taps address the pixel state of ONE frame
 	bool fuseStages = true;	 // "fuse_stages": 2 launches per depth (hit/miss in the scatter launch, shadow + next closest in one trace launch)
+	bool flattenStatic = true; // "flatten_static": static single-use instances join the merged BLAS whatever their transform (takes effect at set_scene)
 	bool mergeStatic = true; // "merge_static": identity-transform static instances share one world-space BLAS (takes effect at set_scene)
 	int width = 0, height = 0, rowBegin = 0, rowEnd = 0;
 	bool haveScene = false, haveColorSpace = false, frameBegun = false;
@@ -154,6 +163,7 @@ struct KrrWfpt : WaveState {
 	cudaEvent_t evFork = nullptr, evJoin[kMaxBands - 1] = {};
 	int bands = 0;		 // "bands": see WaveState; 0 = automatic (2 for a scene that is one flat triangle list, else 1)
 	int activeBands = 1; // decided by begin_frame
+	int allocLayers = 1; // frames in flight the wavefront state was allocated for
 	// pipelined film read-back (krr_wfpt_render_to_host_async): two device films, a copy stream
 	Buf<float4> asyncFilm[2], syncFilm;
 	cudaStream_t copyStream = nullptr;
@@ -209,7 +219,10 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->spp			= j.value("spp", h->spp);
 		h->rrInTrace	= j.value("rr_in_trace", h->rrInTrace);
 		h->mergeStatic	= j.value("merge_static", h->mergeStatic);
+		h->flattenStatic = j.value("flatten_static", h->flattenStatic);
 		h->fuseStages	= j.value("fuse_stages", h->fuseStages);
+		h->tailDepth	= j.value("tail_depth", h->tailDepth);
+		h->frameBatch	= j.value("frame_batch", h->frameBatch);
 		h->implicitDepth0 = j.value("implicit_depth0", h->implicitDepth0);
 		h->debugState	= j.value("debug_taps", h->debugState);
 		h->pdl			= j.value("pdl", h->pdl);
@@ -220,6 +233,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
 	if (h->bands < 0 || h->bands > kMaxBands) return fail(KRR_E_INVALID, "bands must be in [0, %d]", kMaxBands);
+	if (h->frameBatch < 1 || h->frameBatch > 64) return fail(KRR_E_INVALID, "frame_batch must be in [1, 64]");
 	if (!(h->probRR > 0.f && h->probRR <= 1.f)) return fail(KRR_E_INVALID, "rr must be in (0, 1]");
 	return KRR_OK;
 }
@@ -238,12 +252,12 @@ int allocBand(KrrWfpt *h, WaveState &w, size_t n) {
 		for (int a = 0; a < 4; a++) rc |= w.msBuf[a].alloc(n);
 	}
 	const bool fresh = !w.counters.p;
-	rc |= w.counters.alloc(kMaxDepthSlots) | w.totals.alloc(1) | w.errorFlags.alloc(4);
+	rc |= w.counters.alloc(kMaxDepthSlots) | w.totals.alloc(1) | w.errorFlags.alloc(4 + 128);
 	if (rc) return KRR_E_CUDA;
 	if (fresh) {
 		CUDA_OK(cudaMemset(w.counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
 		CUDA_OK(cudaMemset(w.totals.p, 0, sizeof(StatTotals)));
-		CUDA_OK(cudaMemset(w.errorFlags.p, 0, 16));
+		CUDA_OK(cudaMemset(w.errorFlags.p, 0, 4 * (4 + 128)));
 	}
 	return KRR_OK;
 }
@@ -252,13 +266,14 @@ int allocBand(KrrWfpt *h, WaveState &w, size_t n) {
 int allocState(KrrWfpt *h) {
 	h->activeBands = 1;
 	h->counters.release(); // fresh counters for a new frame size / scene
-	return allocBand(h, *h, (size_t) h->pixelCount());
+	h->allocLayers = h->layers();
+	return allocBand(h, *h, (size_t) h->pixelCount() * h->allocLayers);
 }
 
 // bands 1.. of a frame that runs as `nb` bands (no-op when they already have the right size)
 int allocExtraBands(KrrWfpt *h, int nb) {
 	for (int b = 1; b < nb; b++) {
-		int rc = allocBand(h, h->band(b), (size_t) h->bandRows(b, nb) * h->width);
+		int rc = allocBand(h, h->band(b), (size_t) h->bandRows(b, nb) * h->width * h->allocLayers);
 		if (rc) return rc;
 		if (!h->bandStream[b - 1]) {
 			CUDA_OK(cudaStreamCreateWithFlags(&h->bandStream[b - 1], cudaStreamNonBlocking));
@@ -299,17 +314,19 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId, int bandId = 0, int nb = 1) {
 	WaveState &w = h->band(bandId);
 	wf.p.width = h->width, wf.p.height = h->height;
 	wf.p.pixelBegin = h->rowBegin * h->width, wf.p.partPixels = h->pixelCount();
-	wf.p.rowStride = nb, wf.p.rowPhase = bandId, wf.p.pixelCount = h->bandRows(bandId, nb) * h->width;
+	wf.p.layers = h->allocLayers, wf.p.layerPixels = h->bandRows(bandId, nb) * h->width;
+	wf.p.rowStride = nb, wf.p.rowPhase = bandId, wf.p.pixelCount = wf.p.layers * wf.p.layerPixels;
 	wf.p.spp = h->spp, wf.p.maxDepth = h->maxDepth, wf.p.nee = h->nee;
 	wf.p.enableMedium = h->enableMedium && h->sceneHasMedia; // integrator.cpp:200
 	wf.p.enableClamp = h->enableClamp, wf.p.probRR = h->probRR, wf.p.clampMax = h->clampMax;
 	wf.p.rrInTrace	 = h->rrInTrace && !wf.p.enableMedium; // with media the medium stage draws before the scatter stage
 	uint32_t seedIndex = (uint32_t) (h->frameIndex * (uint64_t) h->spp);
 	wf.p.rngInc		 = ((uint64_t) seedIndex << 1u) | 1u;
+	wf.p.seedIndex	 = seedIndex;
 	wf.p.sampleIndex = (uint32_t) sampleId;
 	{
 		const BvhDev bd = h->bvh.device();
-		wf.p.refill = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? kRefillFlat : kRefill;
+		wf.p.refill = bd.mergedOnly && !bd.mergedXf && isFlatEntry((uint32_t) bd.mergedRoot) ? kRefillFlat : kRefill;
 		if (h->refill >= 1 && h->refill <= 32) wf.p.refill = h->refill;
 	}
 	wf.p.implicitDepth0 = h->implicitDepth0 && !(h->enableMedium && h->sceneHasMedia) && h->capSample < 0;
@@ -335,6 +352,7 @@ Wavefront makeWavefront(KrrWfpt *h, int sampleId, int bandId = 0, int nb = 1) {
 	wf.firstHits  = h->debugState ? w.firstHits.p : nullptr;
 	wf.errorFlags = w.errorFlags.p;
 	wf.instFlags  = h->instFlags.p;
+	wf.tripHist	  = w.errorFlags.p + 4;
 	return wf;
 }
 
@@ -448,12 +466,18 @@ int buildAccel(KrrWfpt *h) {
 	const int nInst = (int) h->hInstances.size(), nMesh = (int) h->hMeshes.size();
 	std::vector<uint8_t> merge(nInst, 0);
 	bool any = false;
-	if (h->mergeStatic)
+	if (h->mergeStatic) {
+		// static instances with an identity transform, and (flatten_static) static instances that are the only
+		// user of their mesh, whatever their transform (bvh.cuh BvhDev::mergedXf)
+		std::vector<int> users(nMesh, 0);
+		for (int i = 0; i < nInst; i++) users[h->hInstances[i].mesh]++;
 		for (int i = 0; i < nInst; i++) {
 			const InstRec &r = h->hInstances[i];
-			merge[i] = r.motion < 0 && !h->dynamicInst[i] && isIdentity(r.xf) && isIdentity(r.inv);
+			const bool stat = r.motion < 0 && !h->dynamicInst[i];
+			merge[i] = stat && ((isIdentity(r.xf) && isIdentity(r.inv)) || (h->flattenStatic && users[r.mesh] == 1));
 			any |= merge[i] != 0;
 		}
+	}
 	h->mergedInst = merge;
 	std::vector<InstRec> up = h->hInstances;
 	if (any) { // pseudo-instance of the merged BLAS
@@ -795,6 +819,11 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 	if (h->width <= 0) return fail(KRR_E_STATE, "resize first");
 	CUDA_OK(cudaSetDevice(h->device));
 	cudaStream_t st = (cudaStream_t) stream;
+	if (h->layers() != h->allocLayers) { // "frame_batch" / "debug_taps" changed through set_params
+		CUDA_OK(cudaDeviceSynchronize());
+		int rc = allocState(h);
+		if (rc) return rc;
+	}
 	h->frameIndex = frameIndex;
 	h->cam = makeCamera(c);
 	h->launches = 0;
@@ -820,7 +849,7 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 		// medium +7 %) gain from a second band; the long traversal launches of a tree scene lose to it (20 M
 		// triangles -5 %, 10 000 moving instances -11 %: two resident kernels share L1 and the stack space)
 		const BvhDev bd = h->bvh.device();
-		nb = bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot) ? 2 : 1;
+		nb = bd.mergedOnly && !bd.mergedXf && isFlatEntry((uint32_t) bd.mergedRoot) ? 2 : 1;
 	}
 	nb = std::min(nb, h->rowEnd - h->rowBegin);
 	if (h->debugState || h->capSample >= 0 || h->profile) nb = 1;
@@ -886,7 +915,7 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	bool flatScene = false;
 	{
 		const BvhDev bd = h->bvh.device();
-		flatScene = !motion && bd.mergedOnly && isFlatEntry((uint32_t) bd.mergedRoot);
+		flatScene = !motion && bd.mergedOnly && !bd.mergedXf && isFlatEntry((uint32_t) bd.mergedRoot);
 	}
 	const int gridCam = gridFor(h, k_generate_camera_rays, 256), gridResolve = gridFor(h, k_resolve, 256);
 	const int gridTrace = gridFor(h, k_trace_closest<kTraceStatic>, 128), gridHit = gridFor(h, k_handle_hit_miss<false>, 128);
@@ -944,15 +973,38 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		};
 		if (fused) {
 			launchClosest(0);
-			for (int depth = 0; depth < h->maxDepth; depth++) {
+			// automatic tail depth: where the queues have shrunk to a few per cent of the frame (rr 0.8 per bounce and
+			// the paths that left the scene); measured per scene kind, see DESIGN.md
+			int tail = h->tailDepth < 0 ? (flatScene ? kTailAutoFlat : kTailAutoTree) : h->tailDepth;
+			if (tail < 1 || tail > h->maxDepth) tail = 0;
+			bool tailed = false;
+			for (int depth = 0; depth < h->maxDepth && !tailed; depth++) {
 				launchAllScatter(depth, 1);
+				if (tail && depth + 1 == tail) {
+					// shadow rays of this depth on their own, then the rest of every path in one launch
+					{
+						StageTimer t(h, KRR_STAGE_SHADOW, st);
+						if (motion) launchK(pdl, k_trace_shadow<kTraceMotion>, gridShadowM, 128, st, wf, depth);
+						else if (flatScene) launchK(pdl, k_trace_shadow<kTraceFlat>, gridFor(h, k_trace_shadow<kTraceFlat>, 128), 128, st, wf, depth);
+						else launchK(pdl, k_trace_shadow<kTraceStatic>, gridShadow, 128, st, wf, depth);
+					}
+					{
+						StageTimer t(h, KRR_STAGE_TAIL, st);
+						if (motion) launchK(pdl, k_tail<kTraceMotion>, gridFor(h, k_tail<kTraceMotion>, kTraceBlock), kTraceBlock, st, wf, tail);
+						else if (flatScene) launchK(pdl, k_tail<kTraceFlat>, gridFor(h, k_tail<kTraceFlat>, kTraceBlock), kTraceBlock, st, wf, tail);
+						else launchK(pdl, k_tail<kTraceStatic>, gridFor(h, k_tail<kTraceStatic>, kTraceBlock), kTraceBlock, st, wf, tail);
+					}
+					h->launches += 2;
+					tailed = true;
+					break;
+				}
 				StageTimer t(h, KRR_STAGE_TRACE, st);
 				if (motion) launchK(pdl, k_trace_fused<true>, gridFusedM, 128, st, wf, depth);
 				else if (flatScene) launchK(pdl, k_trace_fused<kTraceFlat>, gridFusedF, 128, st, wf, depth);
 				else launchK(pdl, k_trace_fused<false>, gridFused, 128, st, wf, depth);
 				h->launches++;
 			}
-			launchHitMiss(h->maxDepth);
+			if (!tailed) launchHitMiss(h->maxDepth);
 		}
 		for (int depth = 0; !fused; depth++) {
 			const bool cap = h->capSample == sampleId && h->capDepth == depth;
@@ -1010,6 +1062,7 @@ extern "C" int krr_wfpt_render_megakernel(KrrWfpt *h, uint64_t frameIndex, const
 	if (!h || !c || !film) return fail(KRR_E_INVALID, "null argument");
 	if (!h->haveScene) return fail(KRR_E_STATE, "set_scene first");
 	if (h->width <= 0) return fail(KRR_E_STATE, "resize first");
+	if (h->allocLayers != 1) return fail(KRR_E_STATE, "the megakernel estimator renders one frame at a time: set \"frame_batch\": 1");
 	CUDA_OK(cudaSetDevice(h->device));
 	cudaStream_t st = (cudaStream_t) stream;
 	h->cam = makeCamera(c);
@@ -1258,6 +1311,17 @@ extern "C" int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out) {
 		for (int i = 0; i < 4; i++) flags[i] |= fb[i];
 	}
 	if (flags[0]) return fail(KRR_E_CUDA, "BVH traversal stack overflow (scene deeper than %d entries)", kStackSize);
+#ifdef KRR_COUNT_TRIPS
+	{ // debug build: node visits / triangle tests of the closest rays since the last call
+		int32_t all[4 + 128];
+		CUDA_OK(cudaMemcpy(all, h->errorFlags.p, sizeof all, cudaMemcpyDeviceToHost));
+		CUDA_OK(cudaMemset(h->errorFlags.p, 0, sizeof all));
+		const double n = (double) t.closest;
+		fprintf(stderr, "[trips] closest rays %.0f: node visits/ray %.2f (max %d), triangle tests/ray %.2f; histogram (bins of 8 visits):", n, all[1] / n, all[2], all[3] / n);
+		for (int i = 0; i < 64; i++) fprintf(stderr, " %llu", ((unsigned long long *) (all + 4))[i]);
+		fprintf(stderr, "\n");
+	}
+#endif
 	out->camera_rays = t.camera, out->closest_rays = t.closest, out->shadow_rays = t.shadow, out->scatter_items = t.scatter;
 	out->hit_light_items = t.hitLight, out->miss_items = t.miss, out->medium_sample_items = t.mediumSample, out->medium_scatter_items = t.mediumScatter;
 	for (int i = 0; i < 64; i++) out->closest_by_depth[i] = t.closestByDepth[i], out->shadow_by_depth[i] = t.shadowByDepth[i];

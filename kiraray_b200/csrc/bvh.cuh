@@ -65,6 +65,14 @@ struct BvhDev {
 	int32_t mergedInst; // -1 = nothing merged
 	int32_t mergedRoot;
 	int32_t mergedOnly;
+	// FLATTENED static instances: a static instance whose mesh no other instance uses is merged as well, whatever
+	// its transform.  The merged BLAS then bounds the TRANSFORMED triangles (world space, padded for the rounding
+	// of the inverse), but the triangles themselves stay in the object space of their instance and the leaf test
+	// transforms the ray with that instance's inverse first -- the very operations of the intersection spec, so
+	// hits are bit-identical to entering the instance through the TLAS.  What it buys: no per-instance entry, and
+	// a ray that passes between objects walks ONE tree that has carved the empty space out instead of every
+	// object box on its way.  mergedXf: some merged instance has a non-identity transform.
+	int32_t mergedXf;
 	// A BLAS with at most `flat_blas_max` triangles is not a tree but a FLAT LIST: its root entry is
 	// kFlatFlag | index into flats[] = (first triangle, count).  A warp walks such a list in lock step
 	// (no stack, no slab tests, no divergence between lanes), which for a few dozen triangles costs
@@ -195,6 +203,13 @@ static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float
 #ifndef KRR_TRI_VOTE
 #define KRR_TRI_VOTE 6
 #endif
+// Entering a MOVING instance evaluates its SRT chain at the ray's time (~450 instructions against ~170 for a node
+// test): with incoherent rays a few lanes want it on almost every trip, and the whole warp pays for it.  The
+// phase therefore waits until this many lanes want to enter (the waiting lanes are blocked, so they gather within
+// a few trips), or no lane has any other work.  Static instances (a 30-instruction transform) enter at once.
+#ifndef KRR_ENTER_VOTE
+#define KRR_ENTER_VOTE 8
+#endif
 
 // MOTION = false compiles the SRT-chain path out (static scenes keep their register budget)
 // PAIR: the scene is one flat triangle list and the whole traversal is a walk over it in branch-free pairs
@@ -207,9 +222,14 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	Hit best;
 	// control
 	uint2 ng, tg;
+	V3 oo, od;	 // flattened instances (BvhDev::mergedXf): the ray in the object space of instance objInst
+	int objInst;
 	uint32_t octinv4; // (x >= 0 ? 4 : 0) | (y >= 0 ? 2 : 0) | (z >= 0 ? 1 : 0) of the current-space direction, in every byte
 	int sp, curInst, blasBase;
 	int overflow;
+#ifdef KRR_COUNT_TRIPS
+	int nodeSteps, triTests;
+#endif
 	using LStack = LocalStack<ANY>;
 
 	// reciprocal direction of the slab tests.  A zero component is replaced by +-1e-20: the distances to the two
@@ -233,7 +253,10 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		o = ro = o_, d = rd = d_, tmax = tmax_, time = time_;
 		setSpace();
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
-		sp = 0, curInst = -1, blasBase = -1, overflow = 0;
+		sp = 0, curInst = -1, blasBase = -1, overflow = 0, objInst = -1;
+#ifdef KRR_COUNT_TRIPS
+		nodeSteps = triTests = 0;
+#endif
 		ng = make_uint2((uint32_t) bvh.tlasRoot, 0x80000000u), tg = make_uint2(0u, 0u);
 		if (PAIR || bvh.mergedOnly) {
 			curInst = bvh.mergedInst, blasBase = 0; // world == object space
@@ -304,6 +327,9 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	}
 	// ---- phase: wide node.  Takes the nearest hit child of the node group, tests its 8 children ----
 	KRR_DEV void nodeStep(const BvhDev &bvh, TraceSmem &sm, LStack &ls) {
+#ifdef KRR_COUNT_TRIPS
+		nodeSteps++;
+#endif
 		const uint32_t hits = ng.y;
 		const uint32_t bit	= 31u - (uint32_t) __clz(hits);
 		ng.y ^= 1u << bit;
@@ -372,6 +398,28 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		}
 		ng = make_uint2(__float_as_uint(n1.x), (hitmask & 0xff000000u) | (ew >> 24));
 		tg = make_uint2(__float_as_uint(n1.y), hitmask & 0x00ffffffu);
+#ifndef KRR_PREFETCH
+#define KRR_PREFETCH 0 // measured: -7 % (20 M triangles) and -19 % (10 k moving instances): the extra instructions cost more than the lines save
+#endif
+#if KRR_PREFETCH
+		// A lone ray is a chain of dependent misses (20 M triangles: 250 MB of nodes + 960 MB of triangles against
+		// 126 MB of L2).  The hit children are contiguous (childBase + 0..7), so the lines of the SECOND and later
+		// hit children and of the hit triangles are requested now and arrive while the first child is walked:
+		// DRAM runs at a few per cent of its bandwidth here, latency is what the deep-bounce launches pay for.
+		if (hitmask) {
+			const uint32_t imask = ew >> 24;
+			const uint32_t nInner = (uint32_t) __popc(hitmask >> 24);
+			if (nInner > 1u) { // children childBase .. childBase + popc(imask) - 1: 80 B each, at most 5 lines of 128 B
+				const char *cp = reinterpret_cast<const char *>(bvh.nodes + ng.x);
+				const uint32_t bytes = (uint32_t) __popc(imask) * 80u;
+				for (uint32_t off = 0; off < bytes; off += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + off));
+			}
+			if (tg.y && !tlas) {
+				const char *tp = reinterpret_cast<const char *>(bvh.tris + tg.x + (uint32_t) (__ffs(tg.y) - 1));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+			}
+		}
+#endif
 	}
 	template <typename Accept> KRR_DEV bool tryHit(const BvhDev &bvh, const float4 &a, const float4 &b, float t, float u, float v, Accept accept) {
 		const int prim = __float_as_int(a.w);
@@ -383,7 +431,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		return false;
 	}
 	// flat BLAS: the whole triangle list.  Returns true when an any-hit ray terminated.
-	template <typename Accept> KRR_DEV bool walkFlat(const BvhDev &bvh, Accept accept) {
+	template <typename Accept> KRR_DEV bool walkFlat(const BvhDev &bvh, const InstRec *__restrict__ instances, Accept accept) {
 		const uint32_t first = tg.x, cnt = tg.y & 0x00ffffffu;
 		tg.y	   = 0u;
 		uint32_t k = 0;
@@ -407,24 +455,42 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 			for (int j = 0; j < KRR_LEAF_WIDTH; j++)
 				if (hit[j] && tryHit(bvh, a[j], b[j], t[j], u[j], v[j], accept) && ANY) return true;
 		}
+		const bool flattened = !PAIR && bvh.mergedXf && curInst == bvh.mergedInst;
 		for (; k < cnt; k++) {
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + first + k);
 			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			V3 to = ro, td = rd;
+			if (flattened) objectRay(instances, __float_as_int(b.w), to, td);
 			float t, u, v;
-			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
+			if (triIntersectE(to, td, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
 		}
 		return false;
 	}
+	// flattened instances: the ray in the object space of instance `ti` (cached while consecutive triangles belong to it)
+	KRR_DEV void objectRay(const InstRec *__restrict__ instances, int ti, V3 &to, V3 &td) {
+		if (ti != objInst) {
+			const InstRec &in = instances[ti];
+			oo = xfPointX(in.inv, o), od = xfVectorX(in.inv, d);
+			objInst = ti;
+		}
+		to = oo, td = od;
+	}
 	// ---- phase: triangles of the current group (up to `budget` of them).  Returns true when an any-hit ray terminated. ----
-	template <typename Accept> KRR_DEV bool triStep(const BvhDev &bvh, Accept accept, int budget) {
-		if (tg.y & 0x80000000u) return walkFlat(bvh, accept);
+	template <typename Accept> KRR_DEV bool triStep(const BvhDev &bvh, const InstRec *__restrict__ instances, Accept accept, int budget) {
+		if (tg.y & 0x80000000u) return walkFlat(bvh, instances, accept);
+		const bool flattened = bvh.mergedXf && curInst == bvh.mergedInst;
 		for (int it = 0; it < budget && tg.y; it++) {
 			const uint32_t bit = 31u - (uint32_t) __clz(tg.y);
 			tg.y ^= 1u << bit;
 			const float4 *tp = reinterpret_cast<const float4 *>(bvh.tris + tg.x + bit);
 			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+#ifdef KRR_COUNT_TRIPS
+			triTests++;
+#endif
+			V3 to = ro, td = rd;
+			if (flattened) objectRay(instances, __float_as_int(b.w), to, td); // the triangle lives in the object space of its own instance
 			float t, u, v;
-			if (triIntersectE(ro, rd, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
+			if (triIntersectE(to, td, mk3(a), mk3(b), mk3(c), tmax, t, u, v) && tryHit(bvh, a, b, t, u, v, accept) && ANY) return true;
 		}
 		return false;
 	}
@@ -437,7 +503,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 			if (!tg.y) nodeStep(bvh, sm, ls);
 			while (tg.y) {
 				if (curInst < 0) enterInstance(bvh, instances, sm, ls); // leaves a flat list in tg, or a root in ng
-				else if (triStep(bvh, accept, 24)) return;
+				else if (triStep(bvh, instances, accept, 24)) return;
 			}
 		}
 	}
@@ -450,7 +516,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	template <bool VOTE, typename Accept>
 	KRR_DEV bool trip(bool active, const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, Accept accept) {
 		if constexpr (PAIR) { // the whole scene is one triangle list: one trip per ray
-			if (active && tg.y) walkFlat(bvh, accept);
+			if (active && tg.y) walkFlat(bvh, instances, accept);
 			return active;
 		} else {
 			const unsigned FULL = 0xffffffffu;
@@ -458,9 +524,10 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 			if (active && !hasNode() && !tg.y) fin = !popNext(sm, ls);
 			const bool live = active && !fin;
 			const bool wantEnter = live && tg.y && curInst < 0;
-			if (__any_sync(FULL, wantEnter)) {
-				if (wantEnter) enterInstance(bvh, instances, sm, ls);
-			}
+			const unsigned mE	 = __ballot_sync(FULL, wantEnter);
+			bool runE = mE != 0u;
+			if (MOTION && runE && __popc(mE) < KRR_ENTER_VOTE) runE = !__any_sync(FULL, live && !wantEnter); // every live lane waits to enter
+			if (runE && wantEnter) enterInstance(bvh, instances, sm, ls);
 			const bool wantNode = live && !tg.y && hasNode();
 			if (__any_sync(FULL, wantNode)) {
 				if (wantNode) nodeStep(bvh, sm, ls);
@@ -469,7 +536,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 			const unsigned mT  = __ballot_sync(FULL, wantTri);
 			bool run = mT != 0u;
 			if (VOTE && run && __popc(mT) < KRR_TRI_VOTE) run = !__any_sync(FULL, live && !tg.y && hasNode());
-			if (run && wantTri) fin = triStep(bvh, accept, KRR_TRI_PER_TRIP);
+			if (run && wantTri) fin = triStep(bvh, instances, accept, KRR_TRI_PER_TRIP);
 			return fin;
 		}
 	}

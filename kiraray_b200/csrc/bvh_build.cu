@@ -131,7 +131,11 @@ __global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb
 // merged BLAS: triangle boxes of every merged instance (identity transform: object space == world
 // space), concatenated; pairs[t] = (group slot, local primitive).  blockIdx.y strides over the merged
 // instances, blockIdx.x over 256-triangle chunks.
-struct MergedSrc { int32_t posOff, idxOff, nTri, inst, outOff; };
+struct MergedSrc {
+	int32_t posOff, idxOff, nTri, inst, outOff;
+	int32_t identity; // 0: flattened instance, the boxes bound the transformed triangles
+	float xf[12];
+};
 __global__ void k_prim_bounds_merged(const float *__restrict__ positions, const int32_t *__restrict__ indices, const MergedSrc *__restrict__ src,
 									 int nSrc, Aabb *boxes, int2 *pairs, float *cb) {
 	for (int j = blockIdx.y; j < nSrc; j += gridDim.y) {
@@ -143,11 +147,18 @@ __global__ void k_prim_bounds_merged(const float *__restrict__ positions, const 
 			for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
 			for (int c = 0; c < 3; c++) {
 				int v = idx[3 * i + c];
-				for (int k = 0; k < 3; k++) {
-					float p = pos[3 * v + k];
-					b.lo[k] = fminf(b.lo[k], p), b.hi[k] = fmaxf(b.hi[k], p);
+				float p[3] = {pos[3 * v], pos[3 * v + 1], pos[3 * v + 2]};
+				if (!ms.identity) {
+					const float x = p[0], y = p[1], z = p[2];
+					for (int k = 0; k < 3; k++) p[k] = ms.xf[4 * k] * x + ms.xf[4 * k + 1] * y + ms.xf[4 * k + 2] * z + ms.xf[4 * k + 3];
 				}
+				for (int k = 0; k < 3; k++) b.lo[k] = fminf(b.lo[k], p[k]), b.hi[k] = fmaxf(b.hi[k], p[k]);
 			}
+			if (!ms.identity) // the leaf test runs in object space through the ROUNDED inverse: pad the world box for that round trip
+				for (int k = 0; k < 3; k++) {
+					const float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]);
+					b.lo[k] -= e, b.hi[k] += e;
+				}
 			boxes[ms.outOff + i] = b;
 			pairs[ms.outOff + i] = make_int2(j, i);
 			for (int k = 0; k < 3; k++) {
@@ -630,7 +641,7 @@ struct BvhBuilder::Impl {
 	DevBuf<Aabb> meshBoxes, instBoxes;
 	DevBuf<int32_t> counters, tlasIds;
 	DevBuf<int2> flats;
-	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0, nFlat = 0;
+	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0, nFlat = 0, mergedXf = 0;
 	Aabb mergedBox{{0, 0, 0}, {0, 0, 0}};
 	std::vector<int> tlasLevelStart; // node index (relative to the pool) where each TLAS level begins
 	int tlasNodeCount = 0, totalNodes = 0, totalTris = 0, nInstances = 0, nMeshes = 0;
@@ -726,7 +737,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	// triangles per leaf child: the hit mask of a node has 24 triangle bits = 8 leaf children x 3 triangles
 	const int maxLeaf = std::min(std::max(getenv("KRR_BVH_MAX_LEAF") ? atoi(getenv("KRR_BVH_MAX_LEAF")) : 3, 1), 3);
 	std::vector<int2> flats;
-	b.nMeshes = nMeshes, b.nInstances = nInstances;
+	b.nMeshes = nMeshes, b.nInstances = nInstances, b.mergedXf = 0;
 	// which instances go into the merged world-space BLAS, which meshes still need a BLAS of their own
 	std::vector<MergedSrc> msrc;
 	std::vector<char> meshNeedsBlas(nMeshes, 0);
@@ -735,7 +746,14 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	for (int i = 0; i < nInstances; i++) {
 		const MeshRec &mr = hMeshes[hInstances[i].mesh];
 		if (hMerge && hMerge[i]) {
-			msrc.push_back(MergedSrc{mr.posOff, mr.idxOff, mr.nTri, i, (int32_t) mergedTris});
+			MergedSrc ms{mr.posOff, mr.idxOff, mr.nTri, i, (int32_t) mergedTris, 1, {}};
+			static const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+			for (int k = 0; k < 12; k++) {
+				ms.xf[k] = hInstances[i].xf.m[k];
+				if (!(hInstances[i].xf.m[k] == I[k]) || !(hInstances[i].inv.m[k] == I[k])) ms.identity = 0;
+			}
+			if (!ms.identity) b.mergedXf = 1;
+			msrc.push_back(ms);
 			mergedTris += mr.nTri;
 		} else {
 			meshNeedsBlas[hInstances[i].mesh] = 1;
@@ -862,7 +880,7 @@ BvhDev BvhBuilder::device() const {
 	BvhDev d;
 	d.nodes = m->nodes.p, d.tris = m->tris.p, d.tlasInst = m->tlasInst.p, d.tlasRoot = 0, d.nInstances = m->nInstances;
 	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
-	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot;
+	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot, d.mergedXf = m->mergedXf;
 	d.flats = m->flats.p;
 	for (int k = 0; k < 3; k++) { // padded: the box only culls, the exact decision is the triangle test
 		const float lo = m->mergedBox.lo[k], hi = m->mergedBox.hi[k], pad = 1e-4f * (hi - lo) + 1e-5f * std::max(std::fabs(lo), std::fabs(hi)) + 1e-30f;

@@ -87,6 +87,13 @@ struct Params {
 	// the band of the partition these queues serve: rows rowPhase, rowPhase + rowStride, ... of the
 	// partition, pixelCount pixels in all, indexed densely (local index i = bandRow * width + x)
 	int32_t rowStride, rowPhase, pixelCount;
+	// FRAME BATCH ("frame_batch": F): the launches of one render() carry F independent frames -- frame indices
+	// frameIndex .. frameIndex + F - 1, each with its own PCG sequence (sampleIndex = frameIndex * spp, integrator.cpp:
+	// 217) -- as F layers of pixel state: local index i = layer * layerPixels + (pixel of the band), pixelCount =
+	// F * layerPixels.  A stage launch lasts as long as its slowest ray, whatever the queue holds; with F frames in
+	// the same launches that latency is paid once per F frames.  The film is the mean of the F frames' films.
+	int32_t layers, layerPixels;
+	uint32_t seedIndex; // frameIndex * spp of layer 0
 	int32_t spp, maxDepth, nee, enableMedium, enableClamp;
 	// Russian roulette of generateScatterRays (integrator.cpp:118-119) evaluated by the closest stage
 	// when it routes a hit to the scatter queue: it is the NEXT draw of the pixel's stream either way,
@@ -131,6 +138,7 @@ struct Wavefront {
 	// per instance: bit0 null material, bit1 has alpha (transmission) texture, bit2 emissive, bits 4-6 BSDF
 	// type of its material -- everything the closest stage needs to route a hit, in one load
 	const uint8_t *instFlags;
+	int32_t *tripHist; // KRR_COUNT_TRIPS builds: histogram of node visits per closest ray (64 bins of 8, 64-bit counts)
 };
 
 // Programmatic dependent launch: every stage kernel lets its successor in the stream be scheduled at
@@ -164,7 +172,13 @@ KRR_DEV int warpPushFull(int32_t *counter, bool pred) {
 }
 
 // local pixel index of a band -> pixel id in the frame (the reference's pixelId: RNG seed, film position)
+KRR_DEV int layerOf(const Params &p, int i) { return p.layers == 1 ? 0 : i / p.layerPixels; }
+// PCG increment of the frame that local index i belongs to (PCGSampler::setSeed, sampler.h:22-28: inc = sequence << 1 | 1)
+KRR_DEV uint64_t rngIncOf(const Params &p, int i) {
+	return p.layers == 1 ? p.rngInc : (((uint64_t) (p.seedIndex + (uint32_t) (layerOf(p, i) * p.spp)) << 1u) | 1u);
+}
 KRR_DEV int framePixel(const Params &p, int i) {
+	if (p.layers != 1) i -= layerOf(p, i) * p.layerPixels;
 	if (p.rowStride == 1) return p.pixelBegin + i;
 	int row = i / p.width;
 	return p.pixelBegin + (row * p.rowStride + p.rowPhase) * p.width + (i - row * p.width);
@@ -183,7 +197,7 @@ __global__ void k_begin_frame(const __grid_constant__ Wavefront wf, uint32_t see
 		wf.px.L[i]	   = make_float4(0, 0, 0, 0);
 		wf.px.pixel[i] = make_float4(0, 0, 0, 0);
 		Pcg rng;
-		rng.setPixelSample((uint32_t) px, (uint32_t) py, seedIndex);
+		rng.setPixelSample((uint32_t) px, (uint32_t) py, seedIndex + (uint32_t) (layerOf(wf.p, i) * wf.p.spp));
 		rng.advance((int64_t) (256 * pixelId));
 		wf.px.lambda[i] = sampleLambda0(rng.get1D());
 		wf.px.rng[i]	= rng.state;
@@ -220,7 +234,7 @@ __global__ void k_generate_camera_rays(const __grid_constant__ Wavefront wf) {
 	RayQueue q = wf.rays[0];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wf.p.pixelCount; i += gridDim.x * blockDim.x) {
 		int pixelId = framePixel(wf.p, i);
-		Pcg rng{wf.px.rng[i], wf.p.rngInc};
+		Pcg rng{wf.px.rng[i], rngIncOf(wf.p, i)};
 		float cs[5];
 #pragma unroll
 		for (int k = 0; k < 5; k++) cs[k] = rng.get1D();
@@ -310,6 +324,22 @@ struct WarpWork {
 		next = warp * per, end = min(next + per, n_);
 		exhausted = false;
 	}
+	// Same, for the tree traversals: a SHORT queue is spread evenly over all warps (ceil(n / nWarps) rays each,
+	// CTAs are dealt round-robin to the SMs) instead of 32 rays to each of the first few warps.  A launch lasts as
+	// long as its slowest warp, and a warp as long as the slowest of its rays at the pace of its divergence: with
+	// few rays per warp the deep-bounce launches of a large scene come down from the latency of "the slowest of
+	// 32 divergent rays" towards that of one ray (KRR_SPREAD=0 restores the packed slices for A/B runs).
+	KRR_DEV void initSpread(int n_, int32_t *cursor_, int block, int nBlocks, int warpInBlock, int warpsPerBlock) {
+		const int nWarps = nBlocks * warpsPerBlock;
+#ifndef KRR_SPREAD
+#define KRR_SPREAD 1
+#endif
+#ifndef KRR_SPREAD_MIN
+#define KRR_SPREAD_MIN 8
+#endif
+		const int per = KRR_SPREAD ? min(32, max(KRR_SPREAD_MIN, (n_ + nWarps - 1) / nWarps)) : 32;
+		init(n_, cursor_, block * warpsPerBlock + warpInBlock, nWarps, per); // block-major: neighbouring rays stay on one SM (L1)
+	}
 	// hands one item to every lane of `idle` (lane order); -1 when the queue is exhausted
 	KRR_DEV int take(unsigned idle, int lane) {
 		const unsigned FULL = 0xffffffffu;
@@ -338,10 +368,9 @@ static __device__ __noinline__ void movingXf(const SceneDev &sc, int node, float
 	chainXf(sc.xnodes, sc.motionKeys, node, time, *xf, *inv);
 }
 
-// null-material hit: re-queue the ray behind the surface at the same item depth (device.cu:54-58)
+// null-material hit: the ray continues behind the surface (device.cu:54-58): new origin / medium in o4 / d4
 template <bool MOTION = true>
-__device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4,
-												bool implicit = false) {
+KRR_DEV void continueThroughNull(const Wavefront &wf, Hit h, float4 &o4, float4 &d4) {
 	const InstRec &in	= wf.scene.instances[h.inst];
 	const MeshRec &mesh = wf.scene.meshes[in.mesh];
 	const int32_t *idx	= wf.scene.indices + 3 * ((size_t) mesh.idxOff + h.prim);
@@ -365,9 +394,16 @@ __device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQu
 	V3 off = n * kRayEps;
 	if (dot(n, d) < 0.f) off = -off;
 	V3 no = p + off;
-	stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, o4.w));
+	o4 = make_float4(no.x, no.y, no.z, o4.w);
 	if (wf.p.enableMedium && mesh.mediumIn != mesh.mediumOut) // Interaction::getMedium(dir), raytracing.h:162-166
 		d4.w = __int_as_float(dot(d, n) > 0 ? mesh.mediumOut : mesh.mediumIn);
+}
+// ... re-queued at the same item depth
+template <bool MOTION = true>
+__device__ __noinline__ void requeueThroughNull(const Wavefront &wf, const RayQueue &q, const RayQueue &nq, int i, int s, Hit h, float4 o4, float4 d4,
+												bool implicit = false) {
+	continueThroughNull<MOTION>(wf, h, o4, d4);
+	stcs4(nq.o_time + s, o4);
 	stcs4(nq.d_medium + s, d4);
 	stcs4(nq.thp + s, implicit ? sp(1) : ldcs4(q.thp + i));
 	stcs4(nq.pu + s, implicit ? sp(1) : ldcs4(q.pu + i));
@@ -399,7 +435,8 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	int pix	  = 0;	   // its pixel (fetched with the ray: the finalisation needs it first)
 	bool done = false; // traversal finished, result in tr.best, not yet finalised
 	WarpWork work;
-	work.init(n, &dc->cursorRay, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
+	if (MODE == kTraceFlat) work.init(n, &dc->cursorRay, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
+	else work.initSpread(n, &dc->cursorRay, block, nBlocks, (int) threadIdx.x >> 5, kTraceBlock >> 5);
 	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
 	int medium = -1; // medium the ray travels in (d_medium.w)
 	while (true) {
@@ -416,6 +453,10 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 			const int i = ray;
 			if (done) {
 				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+#ifdef KRR_COUNT_TRIPS
+				atomicAdd(&wf.errorFlags[1], tr.nodeSteps), atomicMax(&wf.errorFlags[2], tr.nodeSteps), atomicAdd(&wf.errorFlags[3], tr.triTests);
+				atomicAdd((unsigned long long *) &wf.tripHist[min(tr.nodeSteps >> 3, 63) * 2], 1ull);
+#endif
 				const int4 rec = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
 				wf.hits[i]	   = rec;
 				if (depth == 0 && wf.firstHits) wf.firstHits[pix] = rec;
@@ -431,7 +472,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 						qid	  = 1 + (int) (f >> 4);
 						light = (f & 4) != 0;
 						if (wf.p.rrInTrace && depth < wf.p.maxDepth) { // no scatter stage (hence no draw) at the last depth
-							Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+							Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 							const bool alive = rng.get1D() < wf.p.probRR;
 							wf.px.rng[pix]	 = rng.state;
 							if (!alive) qid = -2;
@@ -644,6 +685,47 @@ KRR_DEV void evalMaterial(const Wavefront &wf, SurfaceGeom &g, const Wavelengths
 // handleHit + handleMiss (integrator.cpp:78-108)
 // Out of line: the scatter stage of the same depth runs it as a prologue (one launch less per depth;
 // the queues of this stage are short: a few light hits, and misses only matter with an environment light)
+// One hit-light item (handleHit, integrator.cpp:78-90): emitted radiance x spectral-MIS weight.  cp = (ctx.p, pixel),
+// packed = depth | bsdfType << 8 of the ray item.  Shared by the stage kernels and the tail kernel.
+template <bool MOTION>
+KRR_DEV Spec hitLightItem(const Wavefront &wf, int4 hit, float4 d4, float time, float4 cp, int packed, Spec thp, Spec pu, Spec pl, float lightSelPdf) {
+	SurfaceGeom g;
+	rebuildGeometry<MOTION>(wf, hit, mk3(d4), time, g);
+	const int pix = __float_as_int(cp.w);
+	const int itemDepth = packed & 0xff, bsdfType = packed >> 8;
+	// normal map changes intr.n before the light is evaluated (the CH program prepares the full
+	// interaction before pushing): apply it when present
+	const MatRec &mat = wf.scene.materials[g.material];
+	if (mat.tex[3].valid && wf.scene.meshes[g.mesh].uvOff >= 0) {
+		float4 nv = sampleTex(mat.tex[3], wf.scene.texels, g.uvx, g.uvy, make_float4(0, 0, 1, 0));
+		g.n = normalize(g.tangent * (2 * nv.x - 1) + g.bitangent * (2 * nv.y - 1) + g.n * (2 * nv.z - 1));
+	}
+	Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+	const LightRec lr	  = wf.scene.lights[g.light];
+	const TriLightRec &tl = wf.scene.triLights[lr.index];
+	Spec Le = areaLightL(tl, g.n, g.wo, wl, wf.scene.cs) * thp;
+	if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
+		float lightPdf = areaLightPdfLi(tl, wf.scene.instances[tl.inst], g.p, g.n, mk3(cp)) * lightSelPdf;
+		Le = Le / mean(pl * lightPdf + pu);
+	} else Le = Le / mean(pu);
+	return Le;
+}
+// One miss item (handleMiss, integrator.cpp:92-108); returns thp * sum of the infinite lights' weighted radiance
+KRR_DEV Spec missItem(const Wavefront &wf, float4 d4, int pix, int packed, Spec thp, Spec pu, Spec pl, float lightSelPdf) {
+	const int itemDepth = packed & 0xff, bsdfType = packed >> 8;
+	Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
+	Spec L = sp(0);
+	for (int li = 0; li < wf.scene.nInfinite; li++) {
+		const AnalyticLightRec &light = wf.scene.analytic[wf.scene.infiniteLights[li]];
+		Spec Li = infiniteLi(light, mk3(d4), wl, wf.scene);
+		if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
+			float lightPdf = kInv4Pi * lightSelPdf;
+			L += Li / mean(pu + pl * lightPdf);
+		} else L += Li / mean(pu);
+	}
+	return thp * L;
+}
+
 template <bool MOTION>
 __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 	const RayQueue q  = wf.rays[depth & 1];
@@ -656,28 +738,11 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 		int i	  = wf.hitLightIdx[k];
 		int4 hit  = wf.hits[i];
 		float4 d4 = ldg4(q.d_medium + i);
-		SurfaceGeom g;
-		rebuildGeometry<MOTION>(wf, hit, mk3(d4), ldg4(q.o_time + i).w, g);
 		float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldg4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldg4(q.ctxN_dep + i);
-		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
-		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
-		// normal map changes intr.n before the light is evaluated (the CH program prepares the full
-		// interaction before pushing): apply it when present
-		const MatRec &mat = wf.scene.materials[g.material];
-		if (mat.tex[3].valid && wf.scene.meshes[g.mesh].uvOff >= 0) {
-			float4 nv = sampleTex(mat.tex[3], wf.scene.texels, g.uvx, g.uvy, make_float4(0, 0, 1, 0));
-			g.n = normalize(g.tangent * (2 * nv.x - 1) + g.bitangent * (2 * nv.y - 1) + g.n * (2 * nv.z - 1));
-		}
-		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
-		const LightRec lr	  = wf.scene.lights[g.light];
-		const TriLightRec &tl = wf.scene.triLights[lr.index];
+		const int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
 		Spec thp = implicit ? sp(1) : ldg4(q.thp + i), pu = implicit ? sp(1) : ldg4(q.pu + i);
-		Spec Le	 = areaLightL(tl, g.n, g.wo, wl, wf.scene.cs) * thp;
-		if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
-			Spec pl		   = ldg4(q.pl + i); // (never a depth-0 item)
-			float lightPdf = areaLightPdfLi(tl, wf.scene.instances[tl.inst], g.p, g.n, mk3(cp)) * lightSelPdf;
-			Le = Le / mean(pl * lightPdf + pu);
-		} else Le = Le / mean(pu);
+		Spec pl	 = (wf.p.nee && (packed & 0xff) && !((packed >> 8) & BSDF_DELTA)) ? ldg4(q.pl + i) : sp(1); // (never a depth-0 item)
+		Spec Le	 = hitLightItem<MOTION>(wf, hit, d4, ldg4(q.o_time + i).w, cp, packed, thp, pu, pl, lightSelPdf);
 		wf.px.L[pix] = Le + wf.px.L[pix]; // addRadiance (<= 1 item per pixel per stage: plain RMW)
 	}
 	const int nMiss = dc->nMiss;
@@ -687,19 +752,8 @@ __device__ __noinline__ void handleHitMissBody(const Wavefront &wf, int depth) {
 		float4 d4 = ldg4(q.d_medium + i);
 		float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldg4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldg4(q.ctxN_dep + i);
 		int pix = __float_as_int(cp.w), packed = __float_as_int(cn.w);
-		int itemDepth = packed & 0xff, bsdfType = packed >> 8;
-		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
 		Spec thp = implicit ? sp(1) : ldg4(q.thp + i), pu = implicit ? sp(1) : ldg4(q.pu + i), pl = implicit ? sp(1) : ldg4(q.pl + i);
-		Spec L = sp(0);
-		for (int li = 0; li < wf.scene.nInfinite; li++) {
-			const AnalyticLightRec &light = wf.scene.analytic[wf.scene.infiniteLights[li]];
-			Spec Li = infiniteLi(light, mk3(d4), wl, wf.scene);
-			if (wf.p.nee && itemDepth && !(bsdfType & BSDF_DELTA)) {
-				float lightPdf = kInv4Pi * lightSelPdf;
-				L += Li / mean(pu + pl * lightPdf);
-			} else L += Li / mean(pu);
-		}
-		wf.px.L[pix] = thp * L + wf.px.L[pix];
+		wf.px.L[pix] = missItem(wf, d4, pix, packed, thp, pu, pl, lightSelPdf) + wf.px.L[pix];
 	}
 }
 
@@ -731,6 +785,150 @@ __global__ void __launch_bounds__(128) k_handle_hit_miss(const __grid_constant__
 #define KRR_SCATTER_LOCKSTEP 1
 #endif
 constexpr int kScatterBlock = KRR_SCATTER_BLOCK;
+
+// One scatter item = one surface vertex of a path that survived Russian roulette (generateScatterRays,
+// integrator.cpp:120-163; prepareSurfaceInteraction, shading.h:115-226).  Shared, operation for operation, by the
+// stage kernel k_scatter and the tail kernel, so that both produce the same bits.
+struct ScatterIn {
+	int4 hit;		 // inst, prim, u, v
+	float4 d4;		 // ray direction, medium
+	float time;
+	int pix, medium;
+	Spec thp, pu;	 // thp BEFORE the division by probRR
+};
+struct ScatterOut {
+	bool pushShadow, pushNext;
+	V3 so, sdv;				 // shadow ray (tMax = 1)
+	Spec sContrib, sPu, sPl; // Ld / (pl + pu).mean()  (Ld itself with media)
+	int sMedium;
+	V3 no, nd, ctxP, ctxN;	 // next ray + its LightSampleContext
+	Spec nthp, npu, npl;
+	int nflags, medium;
+};
+// LOCK: block-uniform -- every thread of the CTA is in here with an item, so the phase barriers are legal
+template <int MT, bool MOTION>
+KRR_DEV void scatterVertex(const Wavefront &wf, const ScatterIn &in, Pcg &rng, const bool lock, ScatterOut &out) {
+#define KRR_PHASE() do { if (lock) __syncthreads(); } while (0)
+	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	const int pix = in.pix;
+	out.pushShadow = out.pushNext = false;
+	out.medium = in.medium, out.sMedium = -1, out.nflags = 0;
+	Spec thp = in.thp / wf.p.probRR, pu = in.pu;
+	SurfaceGeom g;
+	KRR_PHASE();
+	rebuildGeometry<MOTION>(wf, in.hit, mk3(in.d4), in.time, g);
+	KRR_PHASE();
+	float lam = wf.px.lambda[pix];
+	Wavelengths wl = expandWavelengths(lam);
+	ShadingData sd;
+	bool term;
+	evalMaterial(wf, g, wl, sd, term);
+	if (term && lam > 0) { // lambda.terminateSecondary() persists in the pixel state (shading.h:184-185)
+		wf.px.lambda[pix] = -lam;
+		wl = expandWavelengths(-lam);
+	}
+	KRR_PHASE();
+	auto toLocal = [&](V3 v) { return mk3(dot(g.tangent, v), dot(g.bitangent, v), dot(g.n, v)); };
+	V3 woLocal = toLocal(g.wo);
+	int bsdfType = getBsdfType(sd);
+	Bsdf<MT> bsdf;
+	BsdfSetupCtx ctx{g.wo, &wl, &wf.scene.cs};
+	bsdf.setup(sd, ctx);
+	KRR_PHASE();
+	// [A] light sample of the next-event estimation (draws: light, u0, u1)
+	bool needL = false, delta = false;
+	LightSample ls;
+	V3 p_o = mk3(0, 0, 0), dd = p_o, wiL = p_o;
+	float lightPdf = 0;
+	if (wf.p.nee && wf.scene.nLights > 0 && (bsdfType & BSDF_SMOOTH)) {
+		float ul = rng.get1D();
+		uint32_t lightId = (uint32_t) (ul * wf.scene.nLights);
+		const LightRec lr = wf.scene.lights[lightId];
+		float u0 = rng.get1D(), u1 = rng.get1D();
+		if (lr.type == LIGHT_DIFFUSE_AREA) {
+			const TriLightRec &tl = wf.scene.triLights[lr.index];
+			ls = areaLightSampleLi(tl, wf.scene.instances[tl.inst], u0, u1, g.p, wl, wf.scene.cs);
+		} else {
+			const AnalyticLightRec &al = wf.scene.analytic[lr.index];
+			ls	  = analyticSampleLi(al, u0, u1, g.p, wl, wf.scene);
+			delta = al.type != LIGHT_INFINITE;
+		}
+		// spawnRayTo(ls.intr), raytracing.h:148-157
+		auto offs = [](V3 p, V3 n, V3 w) { V3 off = n * kRayEps; if (dot(n, w) < 0.f) off = -off; return p + off; };
+		V3 to = offs(ls.p, ls.n, g.p - ls.p);
+		p_o	  = offs(g.p, g.n, to - g.p);
+		dd	  = to - p_o;
+		wiL	  = toLocal(normalize(dd));
+		lightPdf = lightSelPdf * ls.pdf;
+		needL	 = true;
+	}
+	// [B] BSDF value / pdf towards the light, and the BSDF sample (draws: lobe, u0, u1)
+	Spec bsdfVal = sp(0);
+	float bsdfPdf = 0;
+	BSDFSample bs;
+	if constexpr (MT == MAT_DISNEY) {
+		// the diffuse lobe's sample is a cosine-distributed direction followed by f() and pdf(), the
+		// same two functions the light direction needs: both go through ONE copy of the code
+		const int comp = bsdf.pickLobe(rng);
+		V3 wiS = mk3(0, 0, 1);
+		if (comp == 0) {
+			float u0 = rng.get1D(), u1 = rng.get1D();
+			wiS = cosineSampleHemisphere(u0, u1);
+			if (woLocal.z < 0) wiS.z *= -1;
+		}
+		Spec fS = sp(0);
+		float pS = 0;
+#pragma unroll 1
+		for (int c = 0; c < 2; c++) {
+			KRR_PHASE();
+			const bool need = c == 0 ? needL : comp == 0;
+			const V3 wi		= c == 0 ? wiL : wiS;
+			Spec fv	 = sp(0);
+			float pv = 0;
+			if (need) bsdf.eval(woLocal, wi, fv, pv);
+			if (c == 0) bsdfVal = fv, bsdfPdf = pv;
+			else fS = fv, pS = pv;
+		}
+		KRR_PHASE();
+		if (comp == 0) bs = BSDFSample{fS, wiS, pS, BSDF_DIFFUSE_REFLECTION};
+		else bs = bsdf.sampleSpecular(comp, woLocal, rng);
+	} else {
+		if (needL) bsdfVal = bsdf.f(woLocal, wiL), bsdfPdf = bsdf.pdf(woLocal, wiL);
+		KRR_PHASE();
+		bs = bsdf.sample(woLocal, rng);
+	}
+	KRR_PHASE();
+	if (delta) bsdfPdf = 0.f;
+	if (needL && lightPdf > 0 && any(bsdfVal)) {
+		Spec Ld = ls.L * thp * bsdfVal * fabsf(wiL.z);
+		if (any(Ld)) {
+			out.pushShadow = true;
+			out.so = p_o, out.sdv = dd;
+			const MeshRec &smesh = wf.scene.meshes[g.mesh]; // spawnRayTo: medium = getMedium(d)
+			out.sMedium = smesh.mediumIn != smesh.mediumOut ? (dot(dd, g.n) > 0 ? smesh.mediumOut : smesh.mediumIn) : in.medium;
+			out.sPu = pu * bsdfPdf, out.sPl = pu * lightPdf;
+			out.sContrib = wf.p.enableMedium ? Ld : Ld / mean(out.sPl + out.sPu);
+		}
+	}
+	if (bs.pdf != 0 && any(bs.f)) {
+		V3 wiWorld = g.tangent * bs.wi.x + g.bitangent * bs.wi.y + g.n * bs.wi.z;
+		out.nthp = thp * bs.f * fabsf(bs.wi.z) / bs.pdf;
+		if (any(out.nthp)) {
+			out.pushNext = true;
+			out.nflags = bs.flags;
+			out.npu = pu, out.npl = pu / bs.pdf;
+			V3 off = g.n * kRayEps;
+			if (dot(g.n, wiWorld) < 0.f) off = -off;
+			out.no = g.p + off, out.nd = wiWorld;
+			out.ctxP = g.p, out.ctxN = g.n;
+			// Interaction::getMedium(dir), raytracing.h:163-167
+			const MeshRec &mesh = wf.scene.meshes[g.mesh];
+			if (mesh.mediumIn != mesh.mediumOut) out.medium = dot(wiWorld, g.n) > 0 ? mesh.mediumOut : mesh.mediumIn;
+		}
+	}
+#undef KRR_PHASE
+}
+
 template <int MT, bool MOTION>
 __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(const __grid_constant__ Wavefront wf, int depth, int withHitMiss) {
 	KRR_PDL_ENTRY();
@@ -742,7 +940,6 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 	const int n		  = dc->nScatter[MT];
 	const int stride  = gridDim.x * blockDim.x;
 	const int nIter	  = (n + stride - 1) / stride;
-	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
 	const bool implicit = wf.p.implicitDepth0 && depth == 0;
 	for (int it = 0; it < nIter; it++) {
 		int k		= it * stride + blockIdx.x * blockDim.x + threadIdx.x;
@@ -750,160 +947,46 @@ __global__ void __launch_bounds__(kScatterBlock, KRR_SCATTER_MINB) k_scatter(con
 		// block-uniform: every thread of the CTA has an item and takes the same top-level path (with
 		// rrInTrace no path ends inside this stage before the phases below), so barriers are legal
 		const bool lock = KRR_SCATTER_LOCKSTEP && wf.p.rrInTrace && it * stride + (blockIdx.x + 1) * blockDim.x <= n;
-#define KRR_PHASE() do { if (lock) __syncthreads(); } while (0)
-		bool pushShadow = false, pushNext = false;
-		// shadow item
-		V3 so, sdv;
-		Spec sContrib, sPu, sPl;
-		// next ray
-		V3 no, nd, ctxP, ctxN;
-		Spec nthp, npu, npl;
-		int pix = 0, itemDepth = 0, nflags = 0, medium = -1, sMedium = -1;
+		ScatterOut out;
+		out.pushShadow = out.pushNext = false;
+		int pix = 0, itemDepth = 0;
 		float time = 0;
 		if (active) {
 			int i	  = wf.scatterIdx[MT][k];
-			int4 hit  = wf.hits[i];
-			float4 o4 = ldcs4(q.o_time + i), d4 = ldcs4(q.d_medium + i);
+			ScatterIn in;
+			in.hit	  = wf.hits[i];
+			float4 o4 = ldcs4(q.o_time + i);
+			in.d4	  = ldcs4(q.d_medium + i);
 			float4 cp = implicit ? make_float4(0, 0, 0, __int_as_float(i)) : ldcs4(q.ctxP_pix + i), cn = implicit ? make_float4(0, 0, 0, 0) : ldcs4(q.ctxN_dep + i);
 			pix = __float_as_int(cp.w), itemDepth = __float_as_int(cn.w) & 0xff;
-			time = o4.w, medium = __float_as_int(d4.w);
-			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			time = o4.w;
+			in.time = time, in.pix = pix, in.medium = __float_as_int(in.d4.w);
+			Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 			// Russian roulette at every depth, including 0 (integrator.cpp:118-119)
 			bool alive = wf.p.rrInTrace ? true : rng.get1D() < wf.p.probRR;
 			if (alive) {
-				Spec thp = (implicit ? sp(1) : ldcs4(q.thp + i)) / wf.p.probRR, pu = implicit ? sp(1) : ldcs4(q.pu + i);
-				SurfaceGeom g;
-				KRR_PHASE();
-				rebuildGeometry<MOTION>(wf, hit, mk3(d4), time, g);
-				KRR_PHASE();
-				float lam = wf.px.lambda[pix];
-				Wavelengths wl = expandWavelengths(lam);
-				ShadingData sd;
-				bool term;
-				evalMaterial(wf, g, wl, sd, term);
-				if (term && lam > 0) { // lambda.terminateSecondary() persists in the pixel state (shading.h:184-185)
-					wf.px.lambda[pix] = -lam;
-					wl = expandWavelengths(-lam);
-				}
-				KRR_PHASE();
-				auto toLocal = [&](V3 v) { return mk3(dot(g.tangent, v), dot(g.bitangent, v), dot(g.n, v)); };
-				V3 woLocal = toLocal(g.wo);
-				int bsdfType = getBsdfType(sd);
-				Bsdf<MT> bsdf;
-				BsdfSetupCtx ctx{g.wo, &wl, &wf.scene.cs};
-				bsdf.setup(sd, ctx);
-				KRR_PHASE();
-				// [A] light sample of the next-event estimation (draws: light, u0, u1)
-				bool needL = false, delta = false;
-				LightSample ls;
-				V3 p_o = mk3(0, 0, 0), dd = p_o, wiL = p_o;
-				float lightPdf = 0;
-				if (wf.p.nee && (bsdfType & BSDF_SMOOTH)) {
-					float ul = rng.get1D();
-					uint32_t lightId = (uint32_t) (ul * wf.scene.nLights);
-					const LightRec lr = wf.scene.lights[lightId];
-					float u0 = rng.get1D(), u1 = rng.get1D();
-					if (lr.type == LIGHT_DIFFUSE_AREA) {
-						const TriLightRec &tl = wf.scene.triLights[lr.index];
-						ls = areaLightSampleLi(tl, wf.scene.instances[tl.inst], u0, u1, g.p, wl, wf.scene.cs);
-					} else {
-						const AnalyticLightRec &al = wf.scene.analytic[lr.index];
-						ls	  = analyticSampleLi(al, u0, u1, g.p, wl, wf.scene);
-						delta = al.type != LIGHT_INFINITE;
-					}
-					// spawnRayTo(ls.intr), raytracing.h:148-157
-					auto offs = [](V3 p, V3 n, V3 w) { V3 off = n * kRayEps; if (dot(n, w) < 0.f) off = -off; return p + off; };
-					V3 to = offs(ls.p, ls.n, g.p - ls.p);
-					p_o	  = offs(g.p, g.n, to - g.p);
-					dd	  = to - p_o;
-					wiL	  = toLocal(normalize(dd));
-					lightPdf = lightSelPdf * ls.pdf;
-					needL	 = true;
-				}
-				// [B] BSDF value / pdf towards the light, and the BSDF sample (draws: lobe, u0, u1)
-				Spec bsdfVal = sp(0);
-				float bsdfPdf = 0;
-				BSDFSample bs;
-				if constexpr (MT == MAT_DISNEY) {
-					// the diffuse lobe's sample is a cosine-distributed direction followed by f() and pdf(), the
-					// same two functions the light direction needs: both go through ONE copy of the code
-					const int comp = bsdf.pickLobe(rng);
-					V3 wiS = mk3(0, 0, 1);
-					if (comp == 0) {
-						float u0 = rng.get1D(), u1 = rng.get1D();
-						wiS = cosineSampleHemisphere(u0, u1);
-						if (woLocal.z < 0) wiS.z *= -1;
-					}
-					Spec fS = sp(0);
-					float pS = 0;
-#pragma unroll 1
-					for (int c = 0; c < 2; c++) {
-						KRR_PHASE();
-						const bool need = c == 0 ? needL : comp == 0;
-						const V3 wi		= c == 0 ? wiL : wiS;
-						Spec fv	 = sp(0);
-						float pv = 0;
-						if (need) bsdf.eval(woLocal, wi, fv, pv);
-						if (c == 0) bsdfVal = fv, bsdfPdf = pv;
-						else fS = fv, pS = pv;
-					}
-					KRR_PHASE();
-					if (comp == 0) bs = BSDFSample{fS, wiS, pS, BSDF_DIFFUSE_REFLECTION};
-					else bs = bsdf.sampleSpecular(comp, woLocal, rng);
-				} else {
-					if (needL) bsdfVal = bsdf.f(woLocal, wiL), bsdfPdf = bsdf.pdf(woLocal, wiL);
-					KRR_PHASE();
-					bs = bsdf.sample(woLocal, rng);
-				}
-				KRR_PHASE();
-				if (delta) bsdfPdf = 0.f;
-				if (needL && lightPdf > 0 && any(bsdfVal)) {
-					Spec Ld = ls.L * thp * bsdfVal * fabsf(wiL.z);
-					if (any(Ld)) {
-						pushShadow = true;
-						so = p_o, sdv = dd;
-						const MeshRec &smesh = wf.scene.meshes[g.mesh]; // spawnRayTo: medium = getMedium(d)
-						sMedium = smesh.mediumIn != smesh.mediumOut ? (dot(dd, g.n) > 0 ? smesh.mediumOut : smesh.mediumIn) : medium;
-						sPu = pu * bsdfPdf, sPl = pu * lightPdf;
-						sContrib = wf.p.enableMedium ? Ld : Ld / mean(sPl + sPu);
-					}
-				}
-				if (bs.pdf != 0 && any(bs.f)) {
-					V3 wiWorld = g.tangent * bs.wi.x + g.bitangent * bs.wi.y + g.n * bs.wi.z;
-					nthp = thp * bs.f * fabsf(bs.wi.z) / bs.pdf;
-					if (any(nthp)) {
-						pushNext = true;
-						nflags = bs.flags;
-						npu = pu, npl = pu / bs.pdf;
-						V3 off = g.n * kRayEps;
-						if (dot(g.n, wiWorld) < 0.f) off = -off;
-						no = g.p + off, nd = wiWorld;
-						ctxP = g.p, ctxN = g.n;
-						// Interaction::getMedium(dir), raytracing.h:163-167
-						const MeshRec &mesh = wf.scene.meshes[g.mesh];
-						if (mesh.mediumIn != mesh.mediumOut) medium = dot(wiWorld, g.n) > 0 ? mesh.mediumOut : mesh.mediumIn;
-					}
-				}
+				in.thp = implicit ? sp(1) : ldcs4(q.thp + i), in.pu = implicit ? sp(1) : ldcs4(q.pu + i);
+				scatterVertex<MT, MOTION>(wf, in, rng, lock, out);
 			}
 			wf.px.rng[pix] = rng.state;
 		}
-		int s = warpPush(&dc->nShadow, pushShadow);
+		int s = warpPush(&dc->nShadow, out.pushShadow);
 		if (s >= 0) {
-			stcs4(wf.shadow.o_tmax + s, make_float4(so.x, so.y, so.z, 1.f));
-			stcs4(wf.shadow.d_pix + s, make_float4(sdv.x, sdv.y, sdv.z, __int_as_float(pix)));
-			stcs4(wf.shadow.contrib + s, sContrib);
-			if (wf.p.enableMedium) stcs4(wf.shadow.pu + s, sPu), stcs4(wf.shadow.pl + s, sPl);
-			if (wf.p.enableMedium || MOTION) wf.shadow.aux[s] = make_int2(sMedium, __float_as_int(time));
+			stcs4(wf.shadow.o_tmax + s, make_float4(out.so.x, out.so.y, out.so.z, 1.f));
+			stcs4(wf.shadow.d_pix + s, make_float4(out.sdv.x, out.sdv.y, out.sdv.z, __int_as_float(pix)));
+			stcs4(wf.shadow.contrib + s, out.sContrib);
+			if (wf.p.enableMedium) stcs4(wf.shadow.pu + s, out.sPu), stcs4(wf.shadow.pl + s, out.sPl);
+			if (wf.p.enableMedium || MOTION) wf.shadow.aux[s] = make_int2(out.sMedium, __float_as_int(time));
 		}
-		s = warpPush(&dc[1].nRay, pushNext);
+		s = warpPush(&dc[1].nRay, out.pushNext);
 		if (s >= 0) {
-			stcs4(nq.o_time + s, make_float4(no.x, no.y, no.z, time));
-			stcs4(nq.d_medium + s, make_float4(nd.x, nd.y, nd.z, __int_as_float(medium)));
-			stcs4(nq.thp + s, nthp);
-			stcs4(nq.pu + s, npu);
-			stcs4(nq.pl + s, npl);
-			stcs4(nq.ctxP_pix + s, make_float4(ctxP.x, ctxP.y, ctxP.z, __int_as_float(pix)));
-			stcs4(nq.ctxN_dep + s, make_float4(ctxN.x, ctxN.y, ctxN.z, __int_as_float((itemDepth + 1) | (nflags << 8))));
+			stcs4(nq.o_time + s, make_float4(out.no.x, out.no.y, out.no.z, time));
+			stcs4(nq.d_medium + s, make_float4(out.nd.x, out.nd.y, out.nd.z, __int_as_float(out.medium)));
+			stcs4(nq.thp + s, out.nthp);
+			stcs4(nq.pu + s, out.npu);
+			stcs4(nq.pl + s, out.npl);
+			stcs4(nq.ctxP_pix + s, make_float4(out.ctxP.x, out.ctxP.y, out.ctxP.z, __int_as_float(pix)));
+			stcs4(nq.ctxN_dep + s, make_float4(out.ctxN.x, out.ctxN.y, out.ctxN.z, __int_as_float((itemDepth + 1) | (out.nflags << 8))));
 		}
 	}
 }
@@ -923,7 +1006,8 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 	int ray = -1, pix = 0;
 	bool done = false; // traversal finished, radiance not yet added
 	WarpWork work;
-	work.init(n, &dc->cursorShadow, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
+	if (MODE == kTraceFlat) work.init(n, &dc->cursorShadow, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
+	else work.initSpread(n, &dc->cursorShadow, block, nBlocks, (int) threadIdx.x >> 5, kTraceBlock >> 5);
 	if (work.next >= n) return;
 	while (true) {
 		// finished rays add their contribution in batches (same reasoning as in the closest stage: the
@@ -995,6 +1079,183 @@ const __grid_constant__ Wavefront wf, int depth) {
 }
 
 // =================================================================================================
+// Tail kernel.  Deep bounces hold few rays, but a stage launch lasts as long as its slowest ray (20 M triangles:
+// ~200-450 us per depth whatever the queue holds; Cornell box: 25-35 us), and the depth loop pays that once per
+// stage per depth.  From loop depth `depth` on, ONE launch finishes the paths: every lane takes a ray item of that
+// depth and runs its path to the end -- closest hit, emitted / environment radiance, Russian roulette, BSDF
+// sampling with next-event estimation, shadow ray, next bounce -- with the routines of the stage kernels
+// (scatterVertex, hitLightItem, missItem, the same traversal).  Per pixel the order of the random draws and of
+// the additions to L is the order of the depth loop (integrator.cpp:232-256), so the film is bit-identical
+// (tests/test_gpu_tail.py); the per-depth counters are kept with atomics (the tail holds few rays by design).
+// Surface-only scenes with NEE (the fused schedule); the shadow rays of depth - 1 are traced by a k_trace_shadow
+// launch before it, so that their contribution reaches L before this kernel's.
+template <int MT, bool MOTION>
+__device__ __noinline__ void tailVertex(const Wavefront &wf, const ScatterIn &in, Pcg &rng, ScatterOut &out) {
+	scatterVertex<MT, MOTION>(wf, in, rng, false, out);
+}
+
+#ifndef KRR_TAIL_MINB
+#define KRR_TAIL_MINB 3
+#endif
+// lanes that must be waiting for the shading phase before a warp runs it (or: no lane of the warp is tracing)
+#ifndef KRR_TAIL_BATCH
+#define KRR_TAIL_BATCH 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, KRR_TAIL_MINB) k_tail(const __grid_constant__ Wavefront wf, int depth) {
+	constexpr bool MOTION = MODE == kTraceMotion;
+	__shared__ TraceSmem sm;
+	const unsigned FULL = 0xffffffffu;
+	const int lane		= threadIdx.x & 31;
+	const RayQueue q	= wf.rays[depth & 1];
+	const int n			= wf.counters[depth].nRay;
+	const float lightSelPdf = wf.scene.nLights > 0 ? 1.f / wf.scene.nLights : 0.f;
+	// A warp is a small wavefront of its own, WITHOUT a barrier between its stages: every lane holds one path and
+	// is in one of three states -- tracing (the shadow ray of its last vertex, then the ray to its next vertex),
+	// ready (next vertex found, waiting to be shaded), idle.  The warp runs traversal trips for its tracing lanes and,
+	// as soon as KRR_TAIL_BATCH lanes are ready (or none is tracing), ONE pass of the shading phase -- emitted /
+	// environment radiance, Russian roulette, BSDF sampling + NEE -- for all ready lanes, which sends them tracing
+	// again.  A slow ray delays nobody: the other lanes of its warp go on through their bounces around it, and a
+	// lane whose path has ended takes the next ray of the queue.  Short queues are spread over all warps.
+	enum { T_IDLE = 0, T_CLOSEST = 1, T_SHADOW = 2, T_READY = 3 };
+	WarpWork work;
+	work.initSpread(n, &wf.counters[depth].cursorRay, blockIdx.x, gridDim.x, (int) threadIdx.x >> 5, kTraceBlock >> 5);
+	if (work.next >= n) return;
+	int state = T_IDLE;
+	float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, cp = o4;
+	Spec thp = sp(0), pu = sp(0), pl = sp(0), L = sp(0), sContrib = sp(0);
+	int pix = 0, packed = 0, loopDepth = depth; // packed = item depth | bsdfType << 8
+	bool hasNext = false;
+	Pcg rng{0, wf.p.rngInc};
+	Traverser<false, MOTION, MODE == kTraceFlat> tr;
+	LocalStack<false> ls;
+	auto endPath = [&]() {
+		wf.px.L[pix]   = L;
+		wf.px.rng[pix] = rng.state;
+		state		   = T_IDLE;
+	};
+	auto beginClosest = [&]() { // the ray in (o4, d4) becomes the closest ray of the next loop depth
+		loopDepth++;
+		atomicAdd(&wf.counters[loopDepth].nRay, 1);
+		tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
+		state = T_CLOSEST;
+	};
+	while (true) {
+		const unsigned idle = __ballot_sync(FULL, state == T_IDLE);
+		if (idle && !work.exhausted) {
+			const int r = work.take(idle, lane);
+			if (r >= 0) {
+				o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
+				thp = ldcs4(q.thp + r), pu = ldcs4(q.pu + r), pl = ldcs4(q.pl + r);
+				cp = ldcs4(q.ctxP_pix + r);
+				packed = __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxN_dep + r) + 3));
+				pix = __float_as_int(cp.w);
+				L = wf.px.L[pix];
+				rng.state = wf.px.rng[pix], rng.inc = rngIncOf(wf.p, pix);
+				loopDepth = depth; // (the queue of `depth` itself was counted by its producer)
+				tr.begin(wf.bvh, mk3(o4), mk3(d4), kInf, o4.w);
+				state = T_CLOSEST;
+			}
+		}
+		const unsigned mTrace = __ballot_sync(FULL, state == T_CLOSEST || state == T_SHADOW), mReady = __ballot_sync(FULL, state == T_READY);
+		if (!mTrace && !mReady) {
+			if (work.exhausted) break;
+			continue;
+		}
+		if (mReady && (__popc(mReady) >= KRR_TAIL_BATCH || !mTrace)) {
+			// ================= shading phase for the ready lanes =================
+			const bool ready  = state == T_READY;
+			DepthCounters *dc = wf.counters + loopDepth;
+			bool ended = false, wantScatter = false;
+			int mt = 0;
+			ScatterIn in;
+			// ---- [hit / miss / Russian roulette] integrator.cpp:78-108, 118-119 ----
+			if (ready) {
+				const Hit h = tr.best;
+				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+				if (h.inst < 0) {
+					atomicAdd(&dc->nMiss, 1);
+					if (wf.scene.nInfinite) L = missItem(wf, d4, pix, packed, thp, pu, pl, lightSelPdf) + L;
+					ended = true;
+				} else {
+					const uint32_t f = wf.instFlags[h.inst];
+					if (f & 1) { // null material: same item depth, next loop depth (never traced behind the last one)
+						if (loopDepth == wf.p.maxDepth) ended = true;
+						else {
+							continueThroughNull<MOTION>(wf, h, o4, d4);
+							beginClosest();
+						}
+					} else {
+						in.hit = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
+						if (f & 4) {
+							atomicAdd(&dc->nHitLight, 1);
+							L = hitLightItem<MOTION>(wf, in.hit, d4, o4.w, cp, packed, thp, pu, pl, lightSelPdf) + L;
+						}
+						mt = (int) (f >> 4);
+						if (loopDepth == wf.p.maxDepth) { // pushed, but the depth loop ends before the scatter stage
+							atomicAdd(&dc->nScatter[mt], 1);
+							ended = true;
+						} else if (!(rng.get1D() < wf.p.probRR)) { // the next draw of the pixel's stream
+							atomicAdd(wf.p.rrInTrace ? &dc->nScatterKilled : &dc->nScatter[mt], 1);
+							ended = true;
+						} else {
+							atomicAdd(&dc->nScatter[mt], 1);
+							in.d4 = d4, in.time = o4.w, in.pix = pix, in.medium = __float_as_int(d4.w), in.thp = thp, in.pu = pu;
+							wantScatter = true;
+						}
+					}
+				}
+			}
+			// ---- [scatter] integrator.cpp:120-163: one material type at a time, each for all its lanes ----
+			ScatterOut out;
+			out.pushShadow = out.pushNext = false;
+			const unsigned types = __reduce_or_sync(FULL, wantScatter ? 1u << mt : 0u);
+			if ((types >> MAT_DISNEY) & 1u) { if (wantScatter && mt == MAT_DISNEY) tailVertex<MAT_DISNEY, MOTION>(wf, in, rng, out); }
+			if ((types >> MAT_DIFFUSE) & 1u) { if (wantScatter && mt == MAT_DIFFUSE) tailVertex<MAT_DIFFUSE, MOTION>(wf, in, rng, out); }
+			if ((types >> MAT_DIELECTRIC) & 1u) { if (wantScatter && mt == MAT_DIELECTRIC) tailVertex<MAT_DIELECTRIC, MOTION>(wf, in, rng, out); }
+			if ((types >> MAT_CONDUCTOR) & 1u) { if (wantScatter && mt == MAT_CONDUCTOR) tailVertex<MAT_CONDUCTOR, MOTION>(wf, in, rng, out); }
+			if ((types >> MAT_NULL) & 1u) { if (wantScatter && mt == MAT_NULL) tailVertex<MAT_NULL, MOTION>(wf, in, rng, out); }
+			if (wantScatter) {
+				hasNext = out.pushNext;
+				const float time = o4.w;
+				if (out.pushNext) { // the path's next ray waits in the path state while the shadow ray is traced
+					o4 = make_float4(out.no.x, out.no.y, out.no.z, time);
+					d4 = make_float4(out.nd.x, out.nd.y, out.nd.z, __int_as_float(out.medium));
+					thp = out.nthp, pu = out.npu, pl = out.npl;
+					cp = make_float4(out.ctxP.x, out.ctxP.y, out.ctxP.z, cp.w);
+					packed = ((packed & 0xff) + 1) | (out.nflags << 8);
+				}
+				if (out.pushShadow) { // [shadow] device.cu:83-100, before the next vertex can add to L
+					atomicAdd(&dc->nShadow, 1);
+					sContrib = out.sContrib;
+					tr.begin(wf.bvh, out.so, out.sdv, 1.f, time);
+					state = T_SHADOW;
+				} else if (hasNext) beginClosest();
+				else ended = true;
+			}
+			if (ended) endPath();
+			continue;
+		}
+		// ================= one traversal trip for the tracing lanes =================
+		const bool tracing = state == T_CLOSEST || state == T_SHADOW, isShadow = state == T_SHADOW;
+		const bool fin = tr.template trip<true>(tracing, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
+			const uint8_t fl = wf.instFlags[inst];
+			if (isShadow && (fl & 1)) return false; // __anyhit__Shadow ignores null-material surfaces
+			if (fl & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);
+			return true;
+		});
+		if (isShadow) {
+			if (fin || tr.best.inst >= 0) { // any accepted hit occludes
+				if (tr.overflow) atomicExch(&wf.errorFlags[0], 1);
+				if (tr.best.inst < 0) L = sContrib + L;
+				if (hasNext) beginClosest();
+				else endPath();
+			}
+		} else if (tracing && fin) state = T_READY;
+	}
+}
+
+// =================================================================================================
 // Participating media (BASELINE config 4).  Stage map: k_medium_sample = sampleMediumInteraction
 // (medium.cpp:13-103), k_medium_scatter = sampleMediumScattering (medium.cpp:105-153),
 // k_trace_shadow_tr = __raygen__ShadowTr + traceTransmittance (device.cu:102-128, wavefront.h:80-139).
@@ -1033,7 +1294,7 @@ __global__ void __launch_bounds__(128) k_medium_sample(const __grid_constant__ W
 			int4 hit = wf.hits[i];
 			h.inst = hit.x, h.prim = hit.y, h.u = __int_as_float(hit.z), h.v = __int_as_float(hit.w);
 			const float tMax = wf.hitT[i];
-			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 			Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
 			const MediumRec &med = wf.scene.media[medium];
 			V3 o = mk3(o4), d = mk3(d4);
@@ -1137,7 +1398,7 @@ __global__ void __launch_bounds__(128) k_medium_scatter(const __grid_constant__ 
 			int2 pd	  = wf.mscatter.pix_depth[k];
 			pix = pd.x, itemDepth = pd.y;
 			const float g = wf.scene.media[medium].g;
-			Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+			Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 			Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
 			if (wf.p.nee) { // [PART-A] direct lighting through ShadowTr
 				float ul = rng.get1D();
@@ -1218,7 +1479,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow_tr(const __grid_co
 		const float tMax = o4.w;
 		const V3 pLight	 = ro + rd * tMax;
 		Spec T_ray = sp(1), pu = sp(1), pl = sp(1);
-		Pcg rng{wf.px.rng[pix], wf.p.rngInc};
+		Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 		Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
 		bool usedRng   = false;
 		// SurfaceInteraction intr = {}: material == nullptr until a closest-hit program fills it
@@ -1311,7 +1572,8 @@ __global__ void k_resolve(const __grid_constant__ Wavefront wf) {
 	}
 }
 
-// film write (integrator.cpp:262-266): /spp, optional clamp, alpha 1, row H-1-y (cuda.h:33-36)
+// film write (integrator.cpp:262-266): /spp, optional clamp, alpha 1, row H-1-y (cuda.h:33-36).  With a frame batch:
+// the mean of the F frames' films, summed in frame order (what averaging F separately rendered films gives)
 __global__ void k_film(const __grid_constant__ Wavefront wf, float4 *film, int zeroOutside) {
 	KRR_PDL_ENTRY();
 	const int N = wf.p.width * wf.p.height;
@@ -1328,11 +1590,19 @@ __global__ void k_film(const __grid_constant__ Wavefront wf, float4 *film, int z
 			if (row % wf.p.rowStride != wf.p.rowPhase) continue;
 			i = (row / wf.p.rowStride) * wf.p.width + x;
 		}
-		float4 p  = wf.px.pixel[i];
-		float spp = (float) wf.p.spp;
-		float r = p.x / spp, g = p.y / spp, b = p.z / spp;
-		if (wf.p.enableClamp) {
-			r = fminf(fmaxf(r, 0.f), wf.p.clampMax), g = fminf(fmaxf(g, 0.f), wf.p.clampMax), b = fminf(fmaxf(b, 0.f), wf.p.clampMax);
+		const float spp = (float) wf.p.spp;
+		float r = 0, g = 0, b = 0;
+		for (int l = 0; l < wf.p.layers; l++) {
+			const float4 p = wf.px.pixel[(size_t) l * wf.p.layerPixels + i];
+			float fr = p.x / spp, fg = p.y / spp, fb = p.z / spp;
+			if (wf.p.enableClamp) {
+				fr = fminf(fmaxf(fr, 0.f), wf.p.clampMax), fg = fminf(fmaxf(fg, 0.f), wf.p.clampMax), fb = fminf(fmaxf(fb, 0.f), wf.p.clampMax);
+			}
+			r = l ? r + fr : fr, g = l ? g + fg : fg, b = l ? b + fb : fb;
+		}
+		if (wf.p.layers > 1) {
+			const float F = (float) wf.p.layers;
+			r = __fdiv_rn(r, F), g = __fdiv_rn(g, F), b = __fdiv_rn(b, F); // correctly rounded: the mean a host computes from F films
 		}
 		*dst = make_float4(r, g, b, 1.f);
 	}

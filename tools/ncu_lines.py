@@ -40,7 +40,17 @@ def main():
         cubin = "/tmp/cub/api.sm_100a.cubin"
     lm = line_map(cubin, func)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt.split("\n", 1)[1])))
+    # one section per captured launch ("Kernel Name" line, header, SASS rows): take the first launch of the wanted kernel
+    want = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3].startswith("launch=") else None
+    secs, cur = [], None
+    for ln in txt.splitlines():
+        if ln.startswith('"Kernel Name"'):
+            cur = []
+            secs.append(cur)
+        elif cur is not None:
+            cur.append(ln)
+    sec = secs[int(want.split("=")[1])] if want else secs[0]
+    rows = list(csv.reader(io.StringIO("\n".join(sec))))
     hdr = rows[0]
     ia, isrc, iinst, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
