@@ -36,11 +36,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # compressed 80-B node per BLAS / TLAS level + one triangle), so bytes/ray = 508 (queue traffic in the reference's
 # SoA layout) + geom: 752 (cbox), 1232 (20 M triangles), 1392 (10 k instances); the volumetric config adds 4 B per
 # tentative collision (one density fetch) and reports collisions per ray.
+# `batch` = frames in flight per step ("frame_batch": F consecutive frame indices rendered by the same launches, film =
+# their mean): a stage launch lasts as long as its slowest ray, and F frames share that latency.  One STEP = one
+# render() = F frames x spp samples per pixel.
 WORKLOADS = {
-    "cbox": dict(name="cbox_1080p_depth10_nee", config=1, size=(1920, 1080), max_depth=10, spp=8, geom=244),
-    "tess20m": dict(name="tess20m_disney_1k_emitters_1080p_depth10_nee", config=2, size=(1920, 1080), max_depth=10, spp=2, geom=724),
-    "smoke": dict(name="cbox_density_grid_in_mist_1080p_depth15_nee", config=3, size=(1920, 1080), max_depth=15, spp=1, geom=244),
-    "inst10k": dict(name="inst10k_two_level_srt_motionblur_refit_4k_depth5_nee", config=4, size=(3840, 2160), max_depth=5, spp=1, geom=884),
+    "cbox": dict(name="cbox_1080p_depth10_nee", config=1, size=(1920, 1080), max_depth=10, spp=8, geom=244, batch=4),
+    "tess20m": dict(name="tess20m_disney_1k_emitters_1080p_depth10_nee", config=2, size=(1920, 1080), max_depth=10, spp=2, geom=724, batch=8),
+    "smoke": dict(name="cbox_density_grid_in_mist_1080p_depth15_nee", config=3, size=(1920, 1080), max_depth=15, spp=1, geom=244, batch=4),
+    "inst10k": dict(name="inst10k_two_level_srt_motionblur_refit_4k_depth5_nee", config=4, size=(3840, 2160), max_depth=5, spp=1, geom=884, batch=4),
 }
 RR = 0.8
 QUEUE_BYTES_PER_RAY = 508.0
@@ -122,10 +125,11 @@ class ClockSampler(threading.Thread):
 class Workload:
     """Scene, camera(s) and pass parameters of one BASELINE config.  Scene synthesis is input generation only."""
 
-    def __init__(self, key, spp=None, scale=1.0):
+    def __init__(self, key, spp=None, scale=1.0, batch=None):
         import kiraray_b200 as krr
         from kiraray_b200 import scenes
         self.key, self.spec = key, WORKLOADS[key]
+        self.batch = batch or self.spec["batch"]
         self.W, self.H = self.spec["size"]
         self.max_depth = self.spec["max_depth"]
         self.spp = spp or self.spec["spp"]
@@ -160,7 +164,8 @@ class Workload:
 
     def config(self, spp):
         return dict({"workload": self.spec["name"], "baseline_config": self.spec["config"], "width": self.W, "height": self.H,
-                     "max_depth": self.max_depth, "rr": RR, "nee": True, "spp_per_step": spp}, **self.extra)
+                     "max_depth": self.max_depth, "rr": RR, "nee": True, "spp_per_frame": spp, "frames_per_step": self.batch,
+                     "spp_per_step": spp * self.batch}, **self.extra)
 
 
 def cpu_reference_rate(wl, spp, rows, threads=0, frames=1):
@@ -213,11 +218,11 @@ def full_config(wl, args, world):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    wl = Workload(args.workload, args.spp, args.scene_scale)
+    wl = Workload(args.workload, args.spp, args.scene_scale, args.frame_batch)
     spp = wl.spp
     cores = os.cpu_count() or 1
     # ~1/8 of the cbox frame per step: a few seconds of CPU work; the tree scenes cost ~10x more per ray
-    rows = args.ref_rows or {"cbox": 135, "tess20m": 32, "smoke": 24, "inst10k": 32}[args.workload]
+    rows = args.ref_rows or {"cbox": 135, "tess20m": 32, "smoke": 24, "inst10k": 1}[args.workload]  # (the oracle brute-forces all 10 000 moving instances per ray)
     vals = []
     for i in range(args.warmup + args.steps):
         v, info = cpu_reference_rate(wl, spp, rows)
@@ -243,6 +248,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cbox", choices=sorted(WORKLOADS), help="BASELINE.json config: cbox = configs[1] (the headline), tess20m = [2], smoke = [3], inst10k = [4]")
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per frame (one step = one frame); 0 = the workload's default")
+    ap.add_argument("--frame-batch", type=int, default=0, help="frames in flight per step (pass parameter frame_batch); 0 = the workload's default")
     ap.add_argument("--scene-scale", type=float, default=1.0, help="< 1 shrinks the triangle / instance counts of the synthetic scenes (smoke tests only)")
     ap.add_argument("--ref-rows", type=int, default=0, help="rows of the frame the CPU reference renders per step")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames the cpu_baseline leg renders")
@@ -275,17 +281,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from kiraray_b200.multigpu import FilmReducer, make_partition
-    wl = Workload(args.workload, args.spp, args.scene_scale)
+    wl = Workload(args.workload, args.spp, args.scene_scale, args.frame_batch)
     W, H = wl.W, wl.H
     part = make_partition(rank, world, H, args.partition)
-    spp_total = wl.spp
-    spp = spp_total
+    spp = wl.spp
     if args.strong:
-        if spp_total % part.spp_slices:
-            raise SystemExit(f"--strong: spp {spp_total} is not divisible by the {part.spp_slices} spp slices")
-        spp = spp_total // part.spp_slices
+        # fixed TOTAL work per step (spp x frames samples per pixel): every spp slice takes 1/S of it, as many frames
+        # in flight as it can keep and fewer samples per frame
+        total = wl.spp * wl.batch
+        if total % part.spp_slices:
+            raise SystemExit(f"--strong: {total} samples per pixel per step are not divisible by the {part.spp_slices} spp slices")
+        share = total // part.spp_slices
+        wl.batch = max(b for b in range(1, wl.batch + 1) if share % b == 0)
+        spp = share // wl.batch
     # debug_taps off: the C ABI's default (the ctypes test binding turns the parity taps on by default)
-    gpu = krr.Wfpt(params={**wl.params, "spp": spp, "debug_taps": False, **(json.loads(args.params) if args.params else {})})
+    gpu = krr.Wfpt(params={**wl.params, "spp": spp, "debug_taps": False, "frame_batch": wl.batch, **(json.loads(args.params) if args.params else {})})
     t0 = time.time()
     gpu.set_scene(wl.desc)
     accel_build_s = time.time() - t0
@@ -301,7 +311,7 @@ def main():
     reducer = FilmReducer(gpu, part, dist)
 
     def frame_of(step):
-        return part.frame_index(step)
+        return part.frame_index(step, batch=wl.batch)  # first of the F consecutive frame indices of this step
 
     def step_device(i):
         gpu.begin_frame(frame_of(i), wl.camera(i), sptr)
@@ -459,11 +469,11 @@ def main():
                     "pipeline_achieved": value * 1e6 * bytes_per_ray / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * bytes_per_ray / 1e9 / max(1, world) / peak}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 96}[args.workload]
+            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 2}[args.workload]  # inst10k: the oracle tests every moving instance per ray (no motion bounds)
             frames = args.ref_frames or (6 if args.workload == "cbox" else 1)  # ~10-20 s of CPU work on 16 cores
             v, info = cpu_reference_rate(wl, spp, rows, frames=frames)
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}
-        spp_s = spp * args.steps * (pixels / (W * H)) / (ms * 1e-3)  # full-frame samples per pixel per second, all ranks
+        spp_s = spp * wl.batch * args.steps * (pixels / (W * H)) / (ms * 1e-3)  # full-frame samples per pixel per second, all ranks
         line = {"metric": "Mrays/s (primary+shadow+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -477,7 +487,7 @@ def main():
         if sustained:
             ms_sus, n_sus, clk = sustained
             line["sustained"] = {"value": rays * (n_sus / args.steps) / (ms_sus * 1e-3) / 1e6, "unit": "Mrays/s", "seconds": ms_sus * 1e-3, "steps": n_sus,
-                                 "spp": n_sus * spp, "clocks": clk}
+                                 "spp": n_sus * spp * wl.batch, "clocks": clk}
         emit(line)
     reducer.close()
     if dist is not None:

@@ -252,12 +252,12 @@ int allocBand(KrrWfpt *h, WaveState &w, size_t n) {
 		for (int a = 0; a < 4; a++) rc |= w.msBuf[a].alloc(n);
 	}
 	const bool fresh = !w.counters.p;
-	rc |= w.counters.alloc(kMaxDepthSlots) | w.totals.alloc(1) | w.errorFlags.alloc(4 + 128);
+	rc |= w.counters.alloc(kMaxDepthSlots) | w.totals.alloc(1) | w.errorFlags.alloc(4 + 132);
 	if (rc) return KRR_E_CUDA;
 	if (fresh) {
 		CUDA_OK(cudaMemset(w.counters.p, 0, sizeof(DepthCounters) * kMaxDepthSlots));
 		CUDA_OK(cudaMemset(w.totals.p, 0, sizeof(StatTotals)));
-		CUDA_OK(cudaMemset(w.errorFlags.p, 0, 4 * (4 + 128)));
+		CUDA_OK(cudaMemset(w.errorFlags.p, 0, 4 * (4 + 132)));
 	}
 	return KRR_OK;
 }
@@ -1313,11 +1313,11 @@ extern "C" int krr_wfpt_get_stats(KrrWfpt *h, KrrStats *out) {
 	if (flags[0]) return fail(KRR_E_CUDA, "BVH traversal stack overflow (scene deeper than %d entries)", kStackSize);
 #ifdef KRR_COUNT_TRIPS
 	{ // debug build: node visits / triangle tests of the closest rays since the last call
-		int32_t all[4 + 128];
+		int32_t all[4 + 132];
 		CUDA_OK(cudaMemcpy(all, h->errorFlags.p, sizeof all, cudaMemcpyDeviceToHost));
 		CUDA_OK(cudaMemset(h->errorFlags.p, 0, sizeof all));
 		const double n = (double) t.closest;
-		fprintf(stderr, "[trips] closest rays %.0f: node visits/ray %.2f (max %d), triangle tests/ray %.2f; histogram (bins of 8 visits):", n, all[1] / n, all[2], all[3] / n);
+		fprintf(stderr, "[trips] closest rays %.0f: node visits/ray %.2f (max %d), triangle tests/ray %.2f, instances entered/ray %.2f, sphere-culled/ray %.2f; histogram (bins of 8 visits):", n, all[1] / n, all[2], all[3] / n, all[4 + 128] / n, all[4 + 129] / n);
 		for (int i = 0; i < 64; i++) fprintf(stderr, " %llu", ((unsigned long long *) (all + 4))[i]);
 		fprintf(stderr, "\n");
 	}

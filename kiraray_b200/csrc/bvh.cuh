@@ -53,6 +53,10 @@ struct BvhDev {
 	const Node8 *nodes;	   // node pool: TLAS nodes first, then every mesh's BLAS
 	const BvhTri *tris;	   // triangle pool, leaf order per mesh
 	const int32_t *tlasInst; // instance ids referenced by TLAS leaves: 8 per TLAS node, indexed by child slot
+	// per instance: world-space bounding sphere (centre, radius) over the ray-time window, radius >= 1e30 = none.
+	// Tested before an instance is entered: a rotated object's box is much larger than the object, and entering a
+	// moving instance costs an SRT-chain evaluation
+	const float4 *instSphere;
 	int32_t tlasRoot;
 	int32_t nInstances;
 	const XformNodeRec *xnodes; // motion blur: transform chains + SRT key pool (motion.cuh), null otherwise
@@ -228,7 +232,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 	int sp, curInst, blasBase;
 	int overflow;
 #ifdef KRR_COUNT_TRIPS
-	int nodeSteps, triTests;
+	int nodeSteps, triTests, enters, culled;
 #endif
 	using LStack = LocalStack<ANY>;
 
@@ -255,7 +259,7 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		best.inst = -1, best.prim = -1, best.t = tmax_, best.u = best.v = 0;
 		sp = 0, curInst = -1, blasBase = -1, overflow = 0, objInst = -1;
 #ifdef KRR_COUNT_TRIPS
-		nodeSteps = triTests = 0;
+		nodeSteps = triTests = enters = culled = 0;
 #endif
 		ng = make_uint2((uint32_t) bvh.tlasRoot, 0x80000000u), tg = make_uint2(0u, 0u);
 		if (PAIR || bvh.mergedOnly) {
@@ -314,6 +318,22 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		tg.y ^= 1u << bit;
 		const uint32_t slot = bit ^ (octinv4 & 7u);
 		const int inst		= __ldg(bvh.tlasInst + tg.x + slot);
+		{ // conservative ray / bounding-sphere test (the bit is consumed either way)
+			const float4 sph = __ldg(bvh.instSphere + inst);
+			if (sph.w < 1.0e30f) {
+				const V3 l	   = mk3(sph.x - o.x, sph.y - o.y, sph.z - o.z);
+				const float ts = fminf(fmaxf(dot(l, d) / dot(d, d), 0.f), best.t); // closest approach within [0, best.t]
+				const V3 q	   = l - d * ts;
+				const float rr = sph.w * 1.0005f + 1e-5f * (fabsf(sph.x) + fabsf(sph.y) + fabsf(sph.z) + 1.f);
+#ifdef KRR_COUNT_TRIPS
+				if (dot(q, q) > rr * rr) culled++;
+#endif
+				if (dot(q, q) > rr * rr) return;
+			}
+		}
+#ifdef KRR_COUNT_TRIPS
+		enters++;
+#endif
 		// the TLAS-level groups wait on the stack below the BLAS part
 		if (hasNode()) push(sm, ls, ng);
 		if (tg.y) push(sm, ls, tg);

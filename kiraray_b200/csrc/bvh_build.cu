@@ -69,63 +69,150 @@ __global__ void k_prim_bounds_tris(const float *__restrict__ pos, const int32_t 
 	}
 }
 
-// world box of an instance = transformed 8 corners of its mesh's object-space box.  A MOVING instance
-// (SRT motion chain, motion.cuh) is bounded over the time window [w0, w1] the rays of the frame can
-// carry (the camera's shutter interval): its corners are evaluated at kMotionSamples + 1 times, all
-// positions are united, and the box is padded by the largest second difference of a corner's
-// trajectory -- 8x the deviation of a smooth curve from the chords between consecutive samples.
+// largest singular value of the linear part of a 3x4 transform (|M v| <= sigma |v|): sqrt of the largest eigenvalue of
+// A^T A, closed form for a symmetric 3x3 matrix, in double, with a relative margin
+KRR_DEV float sigmaMax(const Xf &m) {
+	double a[3][3];
+	for (int r = 0; r < 3; r++)
+		for (int c = 0; c < 3; c++) {
+			double v = 0;
+			for (int k = 0; k < 3; k++) v += (double) m.m[4 * k + r] * (double) m.m[4 * k + c];
+			a[r][c] = v;
+		}
+	const double p1 = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+	const double q	= (a[0][0] + a[1][1] + a[2][2]) / 3.0;
+	double lmax;
+	if (p1 <= 1e-30 * (q * q + 1e-300)) lmax = fmax(a[0][0], fmax(a[1][1], a[2][2]));
+	else {
+		const double p2 = (a[0][0] - q) * (a[0][0] - q) + (a[1][1] - q) * (a[1][1] - q) + (a[2][2] - q) * (a[2][2] - q) + 2.0 * p1;
+		const double p	= sqrt(p2 / 6.0);
+		double bm[3][3];
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++) bm[r][c] = (a[r][c] - (r == c ? q : 0.0)) / p;
+		double det = bm[0][0] * (bm[1][1] * bm[2][2] - bm[1][2] * bm[2][1]) - bm[0][1] * (bm[1][0] * bm[2][2] - bm[1][2] * bm[2][0]) +
+					 bm[0][2] * (bm[1][0] * bm[2][1] - bm[1][1] * bm[2][0]);
+		const double rr = fmin(1.0, fmax(-1.0, det / 2.0));
+		lmax = q + 2.0 * p * cos(acos(rr) / 3.0);
+	}
+	return (float) (sqrt(fmax(lmax, 0.0)) * 1.0001);
+}
+
+// World box of an instance.  Two conservative bounds, intersected: (1) the transformed 8 corners of its mesh's
+// object-space box, (2) the box of its mesh's bounding SPHERE (object-space centre c, radius r around it):
+// |M v - M c| <= sigma_max(M) r.  The corner box of a rotated object is up to sqrt(3) wider per axis than the
+// object, the sphere box does not grow under rotation; compact, roundish meshes get boxes ~1.5x smaller per axis.
+// The world sphere itself is kept for a ray / sphere test before an instance is entered (bvh.cuh).
+// A MOVING instance (SRT motion chain, motion.cuh) is bounded over the time window [w0, w1] the rays of the frame
+// can carry (the camera's shutter interval): corners and sphere are evaluated at kMotionSamples + 1 times, all
+// positions are united, and the box is padded by the largest second difference of a trajectory -- 8x the
+// deviation of a smooth curve from the chords between consecutive samples.
 constexpr int kMotionSamples = 8;
-__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, const int32_t *__restrict__ ids, int n,
-									Aabb *boxesByInst, Aabb *boxesCompact, float *cb, const XformNodeRec *__restrict__ xnodes,
-									const float *__restrict__ keyPool, float w0, float w1) {
+__global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, const float4 *__restrict__ meshSpheres,
+									const int32_t *__restrict__ ids, int n, Aabb *boxesByInst, Aabb *boxesCompact, float4 *spheresByInst, float *cb,
+									const XformNodeRec *__restrict__ xnodes, const float *__restrict__ keyPool, float w0, float w1) {
 	// ids: the instances that are TLAS primitives (merged instances are not; the merged BLAS is pseudo-
 	// instance nInstances).  Boxes are stored by instance id (refit) and, for the build, by TLAS primitive.
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
 	if (slot >= n) return;
 	const int i = ids[slot];
-	const Aabb mb = meshBoxes[inst[i].mesh];
-	Aabb b;
-	for (int k = 0; k < 3; k++) b.lo[k] = 3.0e38f, b.hi[k] = -3.0e38f;
+	const Aabb mb	= meshBoxes[inst[i].mesh];
+	const float4 ms = meshSpheres[inst[i].mesh];
+	const bool useSphere = ms.w < 1.0e30f;
+	Aabb b, sb; // corner box, sphere box
+	for (int k = 0; k < 3; k++) b.lo[k] = sb.lo[k] = 3.0e38f, b.hi[k] = sb.hi[k] = -3.0e38f;
 	auto grow = [&](V3 w) {
 		b.lo[0] = fminf(b.lo[0], w.x), b.lo[1] = fminf(b.lo[1], w.y), b.lo[2] = fminf(b.lo[2], w.z);
 		b.hi[0] = fmaxf(b.hi[0], w.x), b.hi[1] = fmaxf(b.hi[1], w.y), b.hi[2] = fmaxf(b.hi[2], w.z);
 	};
+	auto growSphere = [&](V3 c, float r) {
+		sb.lo[0] = fminf(sb.lo[0], c.x - r), sb.lo[1] = fminf(sb.lo[1], c.y - r), sb.lo[2] = fminf(sb.lo[2], c.z - r);
+		sb.hi[0] = fmaxf(sb.hi[0], c.x + r), sb.hi[1] = fmaxf(sb.hi[1], c.y + r), sb.hi[2] = fmaxf(sb.hi[2], c.z + r);
+	};
 	auto corner = [&](int c) { return mk3(c & 1 ? mb.hi[0] : mb.lo[0], c & 2 ? mb.hi[1] : mb.lo[1], c & 4 ? mb.hi[2] : mb.lo[2]); };
-	float pad = 0.f;
+	const V3 oc = mk3(ms.x, ms.y, ms.z);
+	float pad = 0.f, cpad = 0.f, rmin = 3.0e38f;
 	if (inst[i].motion >= 0 && xnodes) {
 		const int steps = w1 > w0 ? kMotionSamples : 0;
-		V3 prev[8], prev2[8];
+		V3 prev[9], prev2[9];
 		for (int j = 0; j <= steps; j++) {
 			float t = steps ? w0 + (w1 - w0) * ((float) j / (float) steps) : w0;
 			if (j == steps) t = w1;
 			Xf m, inv;
 			chainXf(xnodes, keyPool, inst[i].motion, t, m, inv);
-			for (int c = 0; c < 8; c++) {
-				V3 w = xfPoint(m, corner(c));
-				grow(w);
+			for (int c = 0; c < 9; c++) {
+				V3 w = xfPoint(m, c < 8 ? corner(c) : oc);
+				if (c < 8) grow(w);
+				else if (useSphere) {
+					const float r = sigmaMax(m) * ms.w;
+					growSphere(w, r);
+					rmin = fminf(rmin, r);
+				}
 				if (j >= 2) {
 					V3 dd = prev2[c] - 2.f * prev[c] + w;
-					pad	  = fmaxf(pad, fmaxf(fabsf(dd.x), fmaxf(fabsf(dd.y), fabsf(dd.z))));
+					const float e = fmaxf(fabsf(dd.x), fmaxf(fabsf(dd.y), fabsf(dd.z)));
+					if (c < 8) pad = fmaxf(pad, e);
+					else cpad = e > cpad ? e : cpad;
 				}
 				prev2[c] = prev[c], prev[c] = w;
 			}
 		}
 	} else {
 		for (int c = 0; c < 8; c++) grow(xfPoint(inst[i].xf, corner(c)));
+		if (useSphere) {
+			rmin = sigmaMax(inst[i].xf) * ms.w;
+			growSphere(xfPoint(inst[i].xf, oc), rmin);
+		}
 	}
 	// rays are intersected in object space with the rounded inverse transform: pad the world box so
 	// that culling stays conservative w.r.t. that round trip
 	for (int k = 0; k < 3; k++) {
-		float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]) + pad;
-		b.lo[k] -= e, b.hi[k] += e;
+		float e = 1e-5f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]);
+		b.lo[k] -= e + pad, b.hi[k] += e + pad;
+		if (useSphere) {
+			sb.lo[k] -= e + cpad, sb.hi[k] += e + cpad;
+			b.lo[k] = fmaxf(b.lo[k], sb.lo[k]), b.hi[k] = fminf(b.hi[k], sb.hi[k]); // intersection of the two bounds
+		}
+	}
+	// world sphere over the window: around the centre of the sphere box, reaching its farthest face-centre distance
+	// (= the largest half extent: the swept sphere is inside the sphere box, and every point of the sphere at a
+	// sampled time is within r of a centre that lies in the centres' box)
+	float4 ws = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+	if (useSphere) {
+		const float hx = 0.5f * (sb.hi[0] - sb.lo[0]), hy = 0.5f * (sb.hi[1] - sb.lo[1]), hz = 0.5f * (sb.hi[2] - sb.lo[2]);
+		// a sphere of radius r_j has its centre within (h - r_j) of the box centre per axis, so it lies inside the ball
+		// of radius f(r_j) = |h - r_j| + r_j around the box centre; f decreases with r, so the SMALLEST radius of the
+		// window gives the bound for all of them
+		const float rs = fminf(rmin, fminf(hx, fminf(hy, hz)));
+		const float ex = hx - rs, ey = hy - rs, ez = hz - rs;
+		ws = make_float4(0.5f * (sb.hi[0] + sb.lo[0]), 0.5f * (sb.hi[1] + sb.lo[1]), 0.5f * (sb.hi[2] + sb.lo[2]), sqrtf(ex * ex + ey * ey + ez * ez) + rs);
 	}
 	boxesByInst[i] = b;
+	spheresByInst[i] = ws;
 	if (boxesCompact) boxesCompact[slot] = b;
 	if (cb)
 		for (int k = 0; k < 3; k++) {
 			float c = 0.5f * (b.lo[k] + b.hi[k]);
 			atomicMinF(cb + k, c), atomicMaxF(cb + 3 + k, c);
 		}
+}
+
+// bounding sphere of a mesh around the centre of its box: radius = the farthest triangle vertex (one block)
+__global__ void k_mesh_sphere(const float *__restrict__ pos, const int32_t *__restrict__ idx, int nTri, const Aabb *__restrict__ box, float4 *out) {
+	__shared__ float red[256];
+	const float cx = 0.5f * (box->lo[0] + box->hi[0]), cy = 0.5f * (box->lo[1] + box->hi[1]), cz = 0.5f * (box->lo[2] + box->hi[2]);
+	float r2 = 0.f;
+	for (int i = threadIdx.x; i < 3 * nTri; i += blockDim.x) {
+		const int v = idx[i];
+		const float dx = pos[3 * v] - cx, dy = pos[3 * v + 1] - cy, dz = pos[3 * v + 2] - cz;
+		r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+	}
+	red[threadIdx.x] = r2;
+	__syncthreads();
+	for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *out = make_float4(cx, cy, cz, sqrtf(red[0]) * 1.00001f + 1e-30f);
 }
 
 // merged BLAS: triangle boxes of every merged instance (identity transform: object space == world
@@ -639,6 +726,7 @@ struct BvhBuilder::Impl {
 	DevBuf<BvhTri> tris;
 	DevBuf<int32_t> tlasInst;
 	DevBuf<Aabb> meshBoxes, instBoxes;
+	DevBuf<float4> meshSpheres, instSpheres;
 	DevBuf<int32_t> counters, tlasIds;
 	DevBuf<int2> flats;
 	int nTlasPrims = 0, mergedRoot = -1, mergedInst = -1, nMergedTris = 0, nFlat = 0, mergedXf = 0;
@@ -773,7 +861,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	const int tlasReserve = nInstances + 2;
 	const size_t nodeCap  = totalTris + (size_t) nBlas + (size_t) tlasReserve + 8;
 	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(8 * (size_t) (nInstances + 2) + 8) ||
-		!b.meshBoxes.alloc(nMeshes + 1) || !b.instBoxes.alloc(nInstances + 1) || !b.counters.alloc(2) || !b.tlasIds.alloc(tlasIds.size())) {
+		!b.meshBoxes.alloc(nMeshes + 1) || !b.instBoxes.alloc(nInstances + 1) || !b.meshSpheres.alloc(nMeshes + 1) || !b.instSpheres.alloc(nInstances + 1) || !b.counters.alloc(2) || !b.tlasIds.alloc(tlasIds.size())) {
 		snprintf(err, 256, "bvh build: out of device memory (%zu triangles)", totalTris);
 		return false;
 	}
@@ -794,6 +882,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		k_prim_bounds_tris<<<(mr.nTri + T - 1) / T, T, 0, stream>>>(dPositions + 3 * (size_t) mr.posOff, dIndices + 3 * (size_t) mr.idxOff,
 																  mr.nTri, primBoxes.p, cb.p);
 		k_mesh_box<<<1, 256, 0, stream>>>(primBoxes.p, mr.nTri, b.meshBoxes.p + i);
+		k_mesh_sphere<<<1, 256, 0, stream>>>(dPositions + 3 * (size_t) mr.posOff, dIndices + 3 * (size_t) mr.idxOff, mr.nTri, b.meshBoxes.p + i, b.meshSpheres.p + i);
 		TriWriter wr{dPositions + 3 * (size_t) mr.posOff, dIndices + 3 * (size_t) mr.idxOff, b.tris.p};
 		b.triBases[i] = primCursor;
 		if (mr.nTri <= flatMax) { // flat list instead of a tree
@@ -819,6 +908,10 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 		k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
 		k_prim_bounds_merged<<<grid, T, 0, stream>>>(dPositions, dIndices, dsrc.p, (int) msrc.size(), primBoxes.p, pairs.p, cb.p);
 		k_mesh_box<<<1, 256, 0, stream>>>(primBoxes.p, (int) mergedTris, b.meshBoxes.p + nMeshes);
+		{ // the merged BLAS is bounded by its box alone
+			const float4 none = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+			CK(cudaMemcpyAsync(b.meshSpheres.p + nMeshes, &none, sizeof none, cudaMemcpyHostToDevice, stream));
+		}
 		MergedTriWriter wr{dPositions, dIndices, dsrc.p, pairs.p, b.tris.p};
 		if ((int) mergedTris <= flatMax) {
 			k_write_flat<<<((int) mergedTris + T - 1) / T, T, 0, stream>>>((int) mergedTris, (uint32_t) primCursor, wr);
@@ -845,7 +938,7 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	b.tlasNodeCount = 0;
 	if (b.nTlasPrims > 0) {
 		k_init_bounds<<<1, 32, 0, stream>>>(cb.p);
-		k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, primBoxes.p,
+		k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.meshSpheres.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, primBoxes.p, b.instSpheres.p,
 																		 cb.p, motion.xnodes, motion.keys, motion.w0, motion.w1);
 		int tlasCursor = 0, tlasPrims = 0, root = 0;
 		InstWriter iw{b.tlasInst.p, b.tlasIds.p};
@@ -863,7 +956,7 @@ bool BvhBuilder::refitTlas(const InstRec *dInstances, cudaStream_t stream, char 
 	const int T = 128;
 	if (window) b.motion = *window;
 	if (b.nTlasPrims <= 0) return true;
-	k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, nullptr, nullptr,
+	k_prim_bounds_insts<<<(b.nTlasPrims + T - 1) / T, T, 0, stream>>>(dInstances, b.meshBoxes.p, b.meshSpheres.p, b.tlasIds.p, b.nTlasPrims, b.instBoxes.p, nullptr, b.instSpheres.p, nullptr,
 																	 b.motion.xnodes, b.motion.keys, b.motion.w0, b.motion.w1);
 	for (int l = (int) b.tlasLevelStart.size() - 2; l >= 0; l--) {
 		int first = b.tlasLevelStart[l], count = b.tlasLevelStart[l + 1] - first;
@@ -882,6 +975,7 @@ BvhDev BvhBuilder::device() const {
 	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
 	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot, d.mergedXf = m->mergedXf;
 	d.flats = m->flats.p;
+	d.instSphere = m->instSpheres.p;
 	for (int k = 0; k < 3; k++) { // padded: the box only culls, the exact decision is the triangle test
 		const float lo = m->mergedBox.lo[k], hi = m->mergedBox.hi[k], pad = 1e-4f * (hi - lo) + 1e-5f * std::max(std::fabs(lo), std::fabs(hi)) + 1e-30f;
 		d.rootLo[k] = lo - pad, d.rootHi[k] = hi + pad;

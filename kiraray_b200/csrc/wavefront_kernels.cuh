@@ -456,6 +456,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 #ifdef KRR_COUNT_TRIPS
 				atomicAdd(&wf.errorFlags[1], tr.nodeSteps), atomicMax(&wf.errorFlags[2], tr.nodeSteps), atomicAdd(&wf.errorFlags[3], tr.triTests);
 				atomicAdd((unsigned long long *) &wf.tripHist[min(tr.nodeSteps >> 3, 63) * 2], 1ull);
+				atomicAdd(&wf.tripHist[128], tr.enters), atomicAdd(&wf.tripHist[129], tr.culled);
 #endif
 				const int4 rec = make_int4(h.inst, h.prim, __float_as_int(h.u), __float_as_int(h.v));
 				wf.hits[i]	   = rec;

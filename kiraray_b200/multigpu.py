@@ -41,9 +41,10 @@ class Partition:
         t, T, H = self.tile, self.tiles, self.height
         return (t * H) // T, ((t + 1) * H) // T
 
-    def frame_index(self, step, first_frame=1):
-        """Frame index this rank renders at `step` (first frame is 1, src/core/window.cpp:457)."""
-        return first_frame + self.spp_slice + step * self.spp_slices
+    def frame_index(self, step, first_frame=1, batch=1):
+        """First frame index this rank renders at `step` (first frame is 1, src/core/window.cpp:457); with a frame
+        batch every step of a rank covers `batch` consecutive frame indices."""
+        return first_frame + (self.spp_slice + step * self.spp_slices) * batch
 
     def describe(self):
         return f"tile {self.tiles} x spp-by-frame {self.spp_slices}, scene replicated, film sum-reduce to rank 0"
