@@ -469,7 +469,7 @@ def main():
                     "pipeline_achieved": value * 1e6 * bytes_per_ray / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * bytes_per_ray / 1e9 / max(1, world) / peak}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 2}[args.workload]  # inst10k: the oracle tests every moving instance per ray (no motion bounds)
+            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 4}[args.workload]  # inst10k: the oracle tests every moving instance per ray (no motion bounds)
             frames = args.ref_frames or (6 if args.workload == "cbox" else 1)  # ~10-20 s of CPU work on 16 cores
             v, info = cpu_reference_rate(wl, spp, rows, frames=frames)
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}

@@ -180,6 +180,7 @@ void chainXf(const std::vector<XNode> &nodes, int node, float time, Xf &m, Xf &i
 }
 
 /* ---- scene ---- */
+struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
 struct Mesh {
 	std::vector<V3> P, N, T;
 	std::vector<float> UV;
@@ -187,6 +188,11 @@ struct Mesh {
 	int material, mediumIn, mediumOut;
 	V3 Le;
 	int ntri() const { return (int) I.size() / 3; }
+	/* object-space median-split BVH over the triangles (use_bvh runs of scenes with MOVING instances: the ray is
+	 * moved to the instance's object space at its time, exactly as testPrim does, and walks this tree instead of
+	 * the whole triangle list; the boxes only cull, hits and tie-breaking are those of the brute-force loop) */
+	std::vector<BvhNode> bvh;
+	std::vector<int> bvhTris;
 };
 struct Instance {
 	int mesh;
@@ -199,7 +205,6 @@ struct LightRef {
 	int inst, prim; /* diffuse area */
 	int analytic;	/* index into Scene::analytic */
 };
-struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
 /* HomogeneousMedium / dense-grid stand-in for NanoVDBMedium<float> (src/render/media.h:108-227) */
 struct MediumData {
 	int type;
@@ -348,6 +353,72 @@ inline bool boxHit(const BvhNode &n, V3 o, V3 invd, float tmax) {
 	return t0 <= t1 * 1.0000004f + 1e-30f;
 }
 
+int buildMeshBvh(Mesh &m, int first, int count) {
+	BvhNode n;
+	for (int k = 0; k < 3; k++) n.lo[k] = 1e30f, n.hi[k] = -1e30f;
+	float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+	auto centre = [&](int t, int k) { return (m.P[m.I[3 * t]][k] + m.P[m.I[3 * t + 1]][k] + m.P[m.I[3 * t + 2]][k]); };
+	for (int i = first; i < first + count; i++) {
+		const int t = m.bvhTris[i];
+		for (int c = 0; c < 3; c++)
+			for (int k = 0; k < 3; k++) {
+				float v = m.P[m.I[3 * t + c]][k];
+				n.lo[k] = std::min(n.lo[k], v), n.hi[k] = std::max(n.hi[k], v);
+			}
+		for (int k = 0; k < 3; k++) clo[k] = std::min(clo[k], centre(t, k)), chi[k] = std::max(chi[k], centre(t, k));
+	}
+	for (int k = 0; k < 3; k++) { /* conservative: the boxes only cull */
+		float e = 1e-5f * std::max(1.f, std::max(std::fabs(n.lo[k]), std::fabs(n.hi[k])));
+		n.lo[k] -= e, n.hi[k] += e;
+	}
+	n.left = n.right = -1, n.first = first, n.count = count;
+	int id = (int) m.bvh.size();
+	m.bvh.push_back(n);
+	if (count <= 4) return id;
+	int axis = 0;
+	for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+	if (chi[axis] - clo[axis] <= 0) return id;
+	int mid = first + count / 2;
+	std::nth_element(m.bvhTris.begin() + first, m.bvhTris.begin() + mid, m.bvhTris.begin() + first + count,
+					 [&](int a, int b) { return centre(a, axis) < centre(b, axis); });
+	int l = buildMeshBvh(m, first, mid - first);
+	int r = buildMeshBvh(m, mid, first + count - mid);
+	m.bvh[id].left = l, m.bvh[id].right = r, m.bvh[id].count = 0;
+	return id;
+}
+
+/* one MOVING instance through its mesh's object-space BVH: same object-space ray and triangle test as testPrim */
+template <typename Accept>
+void traceMovingInstance(const OrcScene &s, int ii, V3 o, V3 d, float tmax, float time, Accept accept, Hit &best) {
+	const Instance &in = s.instances[ii];
+	const Mesh &m	   = s.meshes[in.mesh];
+	Xf xf, inv;
+	chainXf(s.xnodes, in.motion, time, xf, inv);
+	const V3 oo = xfPoint(inv, o), dd = xfVector(inv, d);
+	V3 invd = mk(1.f / dd.x, 1.f / dd.y, 1.f / dd.z);
+	int stack[128], sp = 0;
+	stack[sp++] = 0;
+	while (sp) {
+		const BvhNode &n = m.bvh[stack[--sp]];
+		float lim = best.inst < 0 ? tmax : best.t;
+		if (!boxHit(n, oo, invd, lim)) continue;
+		if (n.left < 0) {
+			for (int i = n.first; i < n.first + n.count; i++) {
+				const int pi	   = m.bvhTris[i];
+				const int32_t *idx = &m.I[3 * pi];
+				float t, u, v;
+				if (triIntersect(oo, dd, m.P[idx[0]], m.P[idx[1]], m.P[idx[2]], best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), t, u, v)) {
+					Hit h{ii, pi, t, u, v};
+					if (accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
+				}
+			}
+		} else {
+			stack[sp++] = n.left;
+			stack[sp++] = n.right;
+		}
+	}
+}
+
 /* closest hit over the whole scene; `skipNull`/anyhit variants below */
 template <typename Accept>
 Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, float time, Accept accept) {
@@ -363,14 +434,10 @@ Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, float t
 		}
 		return best;
 	}
-	for (int ii : s.movingInstances) { /* moving instances are kept out of the (static) BVH */
-		int nt = s.meshes[s.instances[ii].mesh].ntri();
-		for (int pi = 0; pi < nt; pi++) {
-			Hit h;
-			testPrim(s, ii, pi, o, d, best.inst < 0 ? tmax : std::nextafter(best.t, 1e30f), time, h);
-			if (h.inst >= 0 && accept(h) && better(h.t, h.inst, h.prim, best)) best = h;
-		}
-	}
+	/* moving instances are kept out of the (static, world-space) BVH: EVERY one of them is visited (no motion
+	 * bounds in the oracle: the kernels' conservative motion boxes are verified against this), each through the
+	 * object-space BVH of its mesh */
+	for (int ii : s.movingInstances) traceMovingInstance(s, ii, o, d, tmax, time, accept, best);
 	V3 invd = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
 	int stack[128], sp = 0;
 	stack[sp++] = 0;
@@ -914,6 +981,13 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		for (int t = 0; t < s->meshes[s->instances[i].mesh].ntri(); t++) s->bvhPrims.push_back({i, t});
 	}
 	if (!s->bvhPrims.empty()) buildBvh(*s, 0, (int) s->bvhPrims.size());
+	for (int i : s->movingInstances) {
+		Mesh &m = s->meshes[s->instances[i].mesh];
+		if (!m.bvh.empty()) continue;
+		m.bvhTris.resize(m.ntri());
+		for (int t = 0; t < m.ntri(); t++) m.bvhTris[t] = t;
+		buildMeshBvh(m, 0, m.ntri());
+	}
 	return s;
 }
 
