@@ -62,6 +62,18 @@ int krr_host_image_save(const char *path, const float *rgba_host, int32_t w, int
 int krr_host_image_save_exr(const char *path, const float *rgba_host, int32_t w, int32_t h, int32_t half_precision, int32_t zip);
 const char *krr_host_last_error(void);
 
+/* One process, N GPUs (kiraray_b200/host/multi_device.cpp MultiDeviceRenderApp): one pass handle per device, one host
+ * thread per handle, work = `tiles` image tiles x (n_devices / tiles) spp slices, film sum-reduce onto rank 0 with
+ * krr_wfpt_reduce_film (NCCL over NVLink).  devices[i] = CUDA device of rank i; ranks that share a device (single-GPU
+ * test boxes) are reduced on the host instead.  krr_multi_render: `steps` frames per spp slice from first_frame on;
+ * the reduced film of the last step is written to film_host (RGBA32F, may be NULL). */
+typedef struct KrrMultiApp KrrMultiApp;
+int krr_multi_create(const KrrSceneDesc *scene, const char *params_json, int32_t w, int32_t h, const int32_t *devices, int32_t n_devices, int32_t tiles, KrrMultiApp **out);
+void krr_multi_destroy(KrrMultiApp *app);
+int krr_multi_uses_nccl(KrrMultiApp *app);
+int krr_multi_render(KrrMultiApp *app, const KrrCameraData *cam, uint64_t first_frame, int32_t steps, float *film_host, double *ms_total, uint64_t *rays_last_step);
+const char *krr_multi_last_error(void);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -227,6 +227,12 @@ def load_host():
     lib.krr_host_image_save.argtypes = [C.c_char_p, P, I32, I32, I32, I32]
     lib.krr_host_image_save_exr.argtypes = [C.c_char_p, P, I32, I32, I32, I32]
     lib.krr_host_set_data_dir.argtypes = [C.c_char_p]
+    lib.krr_multi_create.argtypes = [C.POINTER(KrrSceneDesc), C.c_char_p, I32, I32, C.POINTER(I32), I32, I32, C.POINTER(P)]
+    lib.krr_multi_destroy.argtypes = [P]
+    lib.krr_multi_destroy.restype = None
+    lib.krr_multi_uses_nccl.argtypes = [P]
+    lib.krr_multi_render.argtypes = [P, C.POINTER(KrrCameraData), U64, I32, P, C.POINTER(C.c_double), C.POINTER(U64)]
+    lib.krr_multi_last_error.restype = C.c_char_p
     lib.krr_host_set_data_dir(data_dir().encode())
     _host = lib
     return lib
@@ -593,3 +599,42 @@ def accumulate_f64(accum_ptr, film_ptr, n_pixels, accum_count, max_accum=0, movi
     lib = load_wfpt()
     if lib.krr_accumulate_f64(P(accum_ptr), P(film_ptr), n_pixels, accum_count, max_accum, int(moving_average), P(stream or 0)) != 0:
         raise RuntimeError("krr_accumulate_f64: " + lib.krr_wfpt_last_error().decode())
+
+
+class MultiDeviceApp:
+    """ctypes view of the host layer's MultiDeviceRenderApp (kiraray_b200/host/multi_device.cpp): one process, one
+    pass handle + one host thread per device, NCCL film reduce inside the product library."""
+
+    def __init__(self, desc_ptr, params, w, h, devices, tiles=1):
+        self.lib = load_host()
+        self.w, self.h = w, h
+        self.p = P()
+        dev = (I32 * len(devices))(*devices)
+        rc = self.lib.krr_multi_create(desc_ptr, json.dumps(params).encode(), w, h, dev, len(devices), tiles, C.byref(self.p))
+        if rc != 0:
+            raise RuntimeError("krr_multi_create: " + self.lib.krr_multi_last_error().decode())
+
+    @property
+    def uses_nccl(self):
+        return bool(self.lib.krr_multi_uses_nccl(self.p))
+
+    def render(self, cam, first_frame, steps=1):
+        """-> (film (H, W, 4) of the last step, wall ms of all steps, rays of the last step)"""
+        import numpy as np
+        film = np.empty((self.h, self.w, 4), np.float32)
+        ms, rays = C.c_double(), U64()
+        rc = self.lib.krr_multi_render(self.p, C.byref(cam), first_frame, steps, film.ctypes.data_as(P), C.byref(ms), C.byref(rays))
+        if rc != 0:
+            raise RuntimeError("krr_multi_render: " + self.lib.krr_multi_last_error().decode())
+        return film, ms.value, rays.value
+
+    def close(self):
+        if self.p:
+            self.lib.krr_multi_destroy(self.p)
+            self.p = P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -27,7 +27,7 @@ NVFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", 
                   "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v",
                   "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
 CU_SRCS = ["api.cu", "bvh_build.cu", "post_passes.cu"]
-HOST_SRCS = ["scene.cpp", "passes.cpp", "image.cpp", "gltf.cpp", "host_c_api.cpp"]
+HOST_SRCS = ["scene.cpp", "passes.cpp", "image.cpp", "gltf.cpp", "host_c_api.cpp", "multi_device.cpp"]
 
 
 def run(cmd, log=None):

@@ -438,6 +438,30 @@ private:
 	string mOutputDir = "output";
 };
 
+// ------------------------------------------------------------------------------------------------
+// One process, N GPUs (host/multi_device.cpp): scene replicated, T image tiles x S spp slices, one host thread per
+// device, film sum-reduce with the product's NCCL entry point (krr_wfpt_reduce_film).  No reference counterpart.
+// ------------------------------------------------------------------------------------------------
+class MultiDeviceRenderApp {
+public:
+	struct Result { double msTotal = 0; uint64_t raysLastStep = 0; int steps = 0; };
+	MultiDeviceRenderApp();
+	~MultiDeviceRenderApp();
+	MultiDeviceRenderApp(const MultiDeviceRenderApp &) = delete;
+	// devices[i] = CUDA device of rank i; tiles = T (must divide the number of devices), S = devices / T
+	void init(const KrrSceneDesc *scene, const string &paramsJson, int width, int height, const std::vector<int> &devices, int tiles);
+	// `steps` frames (frame batches) per spp slice starting at firstFrame; the reduced film of the LAST step lands
+	// in filmHost (may be null).  Returns the wall time of the slowest rank and the rays of the last step.
+	Result render(const KrrCameraData &cam, uint64_t firstFrame, int steps, float *filmHost);
+	int size() const;
+	KrrWfpt *handle(int rank);
+	bool usesNccl() const;
+
+private:
+	struct Impl;
+	Impl *m;
+};
+
 // colour-space tables (kiraray_b200/data/spectral_srgb.bin); throws when missing
 const KrrColorSpaceData &defaultColorSpace();
 void setDataDir(const string &dir);
