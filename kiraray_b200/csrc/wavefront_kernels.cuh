@@ -1401,7 +1401,7 @@ __global__ void __launch_bounds__(128) k_medium_scatter(const __grid_constant__ 
 			const float g = wf.scene.media[medium].g;
 			Pcg rng{wf.px.rng[pix], rngIncOf(wf.p, pix)};
 			Wavelengths wl = expandWavelengths(wf.px.lambda[pix]);
-			if (wf.p.nee) { // [PART-A] direct lighting through ShadowTr
+			if (wf.p.nee && wf.scene.nLights > 0) { // [PART-A] direct lighting through ShadowTr (no light, no draws: as in the surface stage)
 				float ul = rng.get1D();
 				uint32_t lightId  = (uint32_t) (ul * wf.scene.nLights);
 				const LightRec lr = wf.scene.lights[lightId];

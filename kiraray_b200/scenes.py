@@ -30,28 +30,44 @@ class SceneBuilder:
         self._keep = []
 
     def add_material(self, diffuse=(0.7, 0.7, 0.7), specular=(0.0, 0.0, 0.0), roughness=1.0, bsdf_type=4, specular_transmission=0.0,
-                     ior=1.5, emissive=None, anisotropic=0.0):
-        """Disney by default, SpecularGlossiness shading model like an OBJ import (specular.a = 1 - roughness)."""
+                     ior=1.5, emissive=None, anisotropic=0.0, shading_model=1, specular4=None, images=None):
+        """Disney by default, SpecularGlossiness shading model like an OBJ import (specular.a = 1 - roughness).
+        shading_model 0 = MetallicRoughness (specular = (occlusion, roughness, metallic, -)); specular4 overrides the
+        four specular channels; images: {texture slot (KRR_TEX_*): (H, W, 4) float32 array} -- RGBA32F image textures
+        (diffuse 0, specular 1, emissive 2, normal 3, transmission / alpha 4)."""
         m = KrrMaterialDesc()
         m.diffuse = (F * 4)(*diffuse, 1.0)
-        m.specular = (F * 4)(*specular, 1.0 - roughness)
+        m.specular = (F * 4)(*(specular4 if specular4 is not None else (*specular, 1.0 - roughness)))
         m.specular_transmission, m.anisotropic, m.ior = specular_transmission, anisotropic, ior
-        m.bsdf_type, m.shading_model, m.color_space = bsdf_type, 1, 0
+        m.bsdf_type, m.shading_model, m.color_space = bsdf_type, shading_model, 0
         if emissive is not None:
             m.textures[2].valid = 1
             m.textures[2].value = (F * 4)(*emissive, 1.0)
+        for slot, img in (images or {}).items():
+            a = np.ascontiguousarray(img, np.float32)
+            assert a.ndim == 3 and a.shape[2] == 4
+            self._keep.append(a)
+            t = m.textures[slot]
+            t.valid, t.image, t.width, t.height = 1, _fp(a), a.shape[1], a.shape[0]
+            t.value = (F * 4)(*[float(x) for x in a.reshape(-1, 4).mean(0)])
         self.materials.append(m)
         return len(self.materials) - 1
 
-    def add_mesh(self, positions, indices, normals=None, material=0, medium_inside=-1, medium_outside=-1):
+    def add_mesh(self, positions, indices, normals=None, material=0, medium_inside=-1, medium_outside=-1, texcoords=None, tangents=None):
         p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
         i = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
         n = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
-        self._keep += [p, i, n]
+        uv = None if texcoords is None else np.ascontiguousarray(texcoords, np.float32).reshape(-1, 2)
+        tg = None if tangents is None else np.ascontiguousarray(tangents, np.float32).reshape(-1, 3)
+        self._keep += [p, i, n, uv, tg]
         m = KrrMeshDesc()
         m.positions, m.indices = _fp(p), i.ctypes.data_as(C.POINTER(I32))
         if n is not None:
             m.normals = _fp(n)
+        if uv is not None:
+            m.texcoords = _fp(uv)
+        if tg is not None:
+            m.tangents = _fp(tg)
         m.n_vertices, m.n_triangles, m.material = len(p), len(i), material
         m.medium_inside, m.medium_outside = medium_inside, medium_outside
         self.meshes.append(m)

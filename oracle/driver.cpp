@@ -170,6 +170,50 @@ void nodeXf(const XNode &nd, float time, Xf &m, Xf &inv) {
 		inv.m[r * 4 + 3] = -t;
 	}
 }
+/* The ORIGINAL node evaluation: four divisions for the quaternion, a division per entry of the inverse (the
+ * formula this build used before the reciprocal form above replaced it for speed).  Kept as an independent second
+ * statement: tests/test_oracle_motion.py bounds the difference between the two in ulp, so that the pair
+ * (oracle, kernel) cannot drift together unnoticed. */
+void nodeXfDiv(const XNode &nd, float time, Xf &m, Xf &inv) {
+	if (nd.nKeys < 2) { m = nd.local, inv = nd.localInv; return; }
+	int n = nd.nKeys, k = 0;
+	float f = 0.f;
+	if (time >= nd.t1) k = n - 2, f = 1.f;
+	else if (time > nd.t0) {
+		float u = ((time - nd.t0) / (nd.t1 - nd.t0)) * (float) (n - 1);
+		k = (int) u;
+		if (k > n - 2) k = n - 2;
+		f = u - (float) k;
+	}
+	const float *a = &nd.keys[10 * k], *b = a + 10;
+	float v[10];
+	for (int i = 0; i < 10; i++) { float d = b[i] - a[i]; d = f * d; v[i] = a[i] + d; }
+	float l0 = v[3] * v[3], l1 = v[4] * v[4], l2 = v[5] * v[5], l3 = v[6] * v[6];
+	float len = std::sqrt((l0 + l1) + (l2 + l3));
+	float x = v[3] / len, y = v[4] / len, z = v[5] / len, w = v[6] / len;
+	float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+	float R[9] = {1.f - 2.f * (yy + zz), 2.f * (xy - wz), 2.f * (xz + wy),
+				  2.f * (xy + wz), 1.f - 2.f * (xx + zz), 2.f * (yz - wx),
+				  2.f * (xz - wy), 2.f * (yz + wx), 1.f - 2.f * (xx + yy)};
+	for (int r = 0; r < 3; r++) {
+		for (int c = 0; c < 3; c++) m.m[r * 4 + c] = R[r * 3 + c] * v[c], inv.m[r * 4 + c] = R[c * 3 + r] / v[r];
+		m.m[r * 4 + 3] = v[7 + r];
+	}
+	for (int r = 0; r < 3; r++) {
+		float t = inv.m[r * 4] * v[7];
+		t = t + inv.m[r * 4 + 1] * v[8];
+		t = t + inv.m[r * 4 + 2] * v[9];
+		inv.m[r * 4 + 3] = -t;
+	}
+}
+void chainXfDiv(const std::vector<XNode> &nodes, int node, float time, Xf &m, Xf &inv) {
+	nodeXfDiv(nodes[node], time, m, inv);
+	for (int p = nodes[node].parent; p >= 0; p = nodes[p].parent) {
+		Xf pm, pinv;
+		nodeXfDiv(nodes[p], time, pm, pinv);
+		m = xfMul(pm, m), inv = xfMul(inv, pinv);
+	}
+}
 void chainXf(const std::vector<XNode> &nodes, int node, float time, Xf &m, Xf &inv) {
 	nodeXf(nodes[node], time, m, inv);
 	for (int p = nodes[node].parent; p >= 0; p = nodes[p].parent) {
@@ -865,6 +909,15 @@ extern "C" void orc_instance_xf(const OrcScene *s, int32_t inst, float time, flo
 	memcpy(m, a.m, 48), memcpy(inv, b.m, 48);
 }
 
+/* the same with the division-based node evaluation (nodeXfDiv); static instances: the uploaded matrices */
+extern "C" void orc_instance_xf_div(const OrcScene *s, int32_t inst, float time, float m[12], float inv[12]) {
+	Xf a, b;
+	const Instance &in = s->instances[inst];
+	if (in.motion >= 0) chainXfDiv(s->xnodes, in.motion, time, a, b);
+	else a = in.xf, b = in.inv;
+	memcpy(m, a.m, 48), memcpy(inv, b.m, 48);
+}
+
 extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 	ol_init();
 	OrcScene *s = new OrcScene();
@@ -1414,4 +1467,165 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 		stats->bvh_triangles = s.bvhPrims.size(), stats->bvh_nodes = s.bvh.size();
 	}
 	return secs;
+}
+
+/* =================================================================================================
+ * MegakernelPathTracer, restated from the reference's OptiX programs (src/render/megakernel/device.cu):
+ * __raygen__Pathtracer :148-195, handleHit :50-64, handleMiss :66-79, generateShadowRay / evalDirect :81-113,
+ * generateScatterRay :115-127; power-heuristic MIS (render/sampling.h:20-28) on (bsdf pdf, light pdf) instead of the
+ * wavefront pass's spectral path pdfs.  It is the independent estimator the GPU megakernel is checked against
+ * (tests/test_gpu_megakernel_oracle.py).  The reference draws from a cuRAND sampler there (device code); this
+ * restatement and the GPU kernel both use the PCG sampler with the reference's seeding of that pass,
+ * setPixelSample(pixel, frameID * 512) (device.cu:159), so their streams are identical.
+ * A hit without a material (medium interface) ends the path: the megakernel has no medium handling. */
+namespace {
+inline float evalMIS(float n0, float p0, float n1, float p1) { /* sampling.h:20-28 */
+	float q0 = (n0 * p0) * (n0 * p0), q1 = (n1 * p1) * (n1 * p1);
+	return q0 / (q0 + q1);
+}
+} // namespace
+
+extern "C" double orc_render_megakernel(const OrcScene *sp, const OrcParams *p, const KrrCameraData *cam, int32_t W, int32_t H,
+										uint64_t frameId, float *film) {
+	const OrcScene &s = *sp;
+	OlCamera oc;
+	memcpy(oc.filmSize, cam->film_size, 8);
+	oc.focalLength = cam->focal_length, oc.focalDistance = cam->focal_distance, oc.lensRadius = cam->lens_radius;
+	oc.aspectRatio = cam->aspect_ratio, oc.shutterOpen = cam->shutter_open, oc.shutterTime = cam->shutter_time;
+	memcpy(oc.transform, cam->transform, 48);
+	const int spp = p->spp > 0 ? p->spp : 1, nLights = (int) s.lights.size();
+	const bool useBvh = p->use_bvh != 0;
+	const float lightSelPdf = nLights > 0 ? 1.f / nLights : 0.f;
+	const int BSDF_SPECULAR_ = 32, BSDF_SMOOTH_ = 8 | 16;
+	int nthreads = p->threads > 0 ? p->threads : (int) std::max(1u, std::thread::hardware_concurrency());
+	auto t0 = std::chrono::steady_clock::now();
+	std::atomic<int> nextChunk{0};
+	const int chunk = 256, pixelEnd = W * H;
+	auto worker = [&]() {
+		for (;;) {
+			const int c0 = nextChunk.fetch_add(chunk);
+			if (c0 >= pixelEnd) break;
+			for (int pixelId = c0; pixelId < std::min(c0 + chunk, pixelEnd); pixelId++) {
+				const int px = pixelId % W, py = pixelId / W;
+				OlSampler smp;
+				ol_pcg_set_pixel_sample(&smp, px, py, (uint32_t) frameId * 512u); /* device.cu:159 */
+				float color[3] = {0, 0, 0};
+				for (int i = 0; i < spp; i++) { /* device.cu:166-191 */
+					Spec thp = sconst(1), L = sconst(0);
+					float cs[5];
+					for (int k = 0; k < 5; k++) cs[k] = ol_pcg_get1d(&smp);
+					float ro[3], rd[3], rtime;
+					ol_camera_ray(&oc, px, py, W, H, cs, ro, rd, &rtime);
+					float lambda[4], lpdf[4];
+					ol_sample_wavelengths(ol_pcg_get1d(&smp), lambda, lpdf);
+					V3 rayO = mk(ro), rayD = mk(rd), ctxP = mk(0, 0, 0), ctxN = mk(0, 0, 0);
+					float pdfPrev = 0;
+					int typePrev  = 0;
+					for (int depth = 0;; depth++) {
+						Hit h = traceClosest(s, useBvh, rayO, rayD, std::numeric_limits<float>::infinity(), rtime,
+											 [&](const Hit &c) { return !alphaKilled(s, c, rayO, rayD); }); /* __anyhit__Radiance */
+						if (h.inst < 0) { /* handleMiss */
+							for (int li : s.infinite) {
+								float weight = 1;
+								if (p->nee && depth > 0 && !(typePrev & BSDF_SPECULAR_)) {
+									weight = evalMIS(1, pdfPrev, 1, 0.07957747154594767f * lightSelPdf);
+									if (std::isnan(weight) || std::isinf(weight)) weight = 1;
+								}
+								float w[3], Li4[4];
+								st(w, rayD);
+								infiniteLightLi(s.analytic[li], s.analyticTex[li], w, lambda, Li4);
+								L = L + thp * weight * Spec{{Li4[0], Li4[1], Li4[2], Li4[3]}};
+							}
+							break;
+						}
+						SurfIntr it;
+						prepareInteraction(s, h, rayD, rtime, lambda, lpdf, it);
+						if (it.material < 0) break;
+						if (it.light >= 0) { /* handleHit */
+							OlTriLight tl;
+							fillTri(s, s.lights[it.light], tl);
+							float pp[3], nn[3], ww[3], Le4[4];
+							st(pp, it.p), st(nn, it.n), st(ww, it.wo);
+							ol_arealight_L(&tl, pp, nn, ww, lambda, Le4);
+							float weight = 1;
+							if (p->nee && depth > 0) {
+								float cp[3], cn[3];
+								st(cp, ctxP), st(cn, ctxN);
+								float lightPdf = ol_arealight_pdf_li(&tl, pp, nn, cp, cn) * lightSelPdf;
+								if (!(typePrev & BSDF_SPECULAR_)) weight = evalMIS(1, pdfPrev, 1, lightPdf);
+								if (std::isnan(weight) || std::isinf(weight)) weight = 1;
+							}
+							L = L + Spec{{Le4[0], Le4[1], Le4[2], Le4[3]}} * weight * thp;
+						}
+						if (depth == p->max_depth || (p->rr < 1.f && ol_pcg_get1d(&smp) > p->rr)) break;
+						thp = thp / p->rr;
+						V3 woLocal = toLocal(it, it.wo);
+						float wo3[3];
+						st(wo3, woLocal);
+						if (p->nee && (ol_bsdf_type(&it.sd) & BSDF_SMOOTH_) && nLights > 0) { /* evalDirect -> generateShadowRay */
+							float u1	= ol_pcg_get1d(&smp);
+							int lightId = std::min((int) (uint32_t) (u1 * nLights), nLights - 1);
+							const LightRef &lr = s.lights[lightId];
+							float u2[2], cp[3], cn[3], lp[3], ln[3] = {0, 0, 0}, Ll[4], lpdfv;
+							u2[0] = ol_pcg_get1d(&smp), u2[1] = ol_pcg_get1d(&smp);
+							st(cp, it.p), st(cn, it.n);
+							bool delta = lr.type != KRR_LIGHT_DIFFUSE_AREA && lr.type != KRR_LIGHT_INFINITE;
+							if (lr.type == KRR_LIGHT_DIFFUSE_AREA) {
+								OlTriLight tl;
+								fillTri(s, lr, tl);
+								ol_arealight_sample_li(&tl, u2, cp, cn, lambda, lp, ln, Ll, &lpdfv);
+							} else {
+								ol_light_sample_li(&s.analytic[lr.analytic], u2, cp, lambda, lp, Ll, &lpdfv);
+								if (s.analyticTex[lr.analytic].image) {
+									float wi3[3] = {lp[0] - cp[0], lp[1] - cp[1], lp[2] - cp[2]};
+									infiniteLightLi(s.analytic[lr.analytic], s.analyticTex[lr.analytic], wi3, lambda, Ll);
+								}
+							}
+							V3 lP = mk(lp), lN = mk(ln);
+							V3 wiLocal = toLocal(it, normalize(lP - it.p));
+							float lightPdf = lightSelPdf * lpdfv;
+							if (lightPdf != 0) {
+								float wi3[3], f4[4], bpdf;
+								st(wi3, wiLocal);
+								ol_bsdf_f_pdf(&it.sd, wo3, wi3, f4, &bpdf);
+								float bsdfPdf = delta ? 0.f : bpdf;
+								Spec bsdfVal  = Spec{{f4[0], f4[1], f4[2], f4[3]}} * std::fabs(wiLocal.z);
+								float mis	  = evalMIS(1, lightPdf, 1, bsdfPdf);
+								if (!(std::isnan(mis) || std::isinf(mis)) && any(bsdfVal)) {
+									V3 to  = offsetRayOrigin(lP, lN, it.p - lP); /* spawnRayTo(ls.intr) */
+									V3 p_o = offsetRayOrigin(it.p, it.n, to - it.p);
+									V3 sd_ = to - p_o;
+									Hit sh = traceClosest(s, useBvh, p_o, sd_, 1.f, rtime, [&](const Hit &c) { return !alphaKilled(s, c, p_o, sd_); });
+									if (sh.inst < 0) L = L + thp * bsdfVal * mis / (1 * lightPdf) * Spec{{Ll[0], Ll[1], Ll[2], Ll[3]}};
+								}
+							}
+						}
+						/* generateScatterRay */
+						float f4[4], wi3[3], spdf;
+						int flags;
+						ol_bsdf_sample(&it.sd, wo3, &smp, f4, wi3, &spdf, &flags);
+						Spec sf = Spec{{f4[0], f4[1], f4[2], f4[3]}};
+						if (spdf == 0 || !any(sf)) break;
+						V3 wiWorld = toWorld(it, mk(wi3));
+						typePrev = flags, pdfPrev = spdf;
+						rayO = offsetRayOrigin(it.p, it.n, wiWorld), rayD = wiWorld;
+						ctxP = it.p, ctxN = it.n;
+						thp	 = thp * sf * std::fabs(wi3[2]) / spdf;
+						if (!any(thp)) break;
+					}
+					float rgb[3];
+					ol_to_rgb(L.v, lambda, lpdf, rgb);
+					for (int k = 0; k < 3; k++) color[k] += rgb[k];
+				}
+				/* colorBuffer.write(RGBA(color, 1), fbIndex): the SUM over the samples (device.cu:194), row H-1-y */
+				float o[4] = {color[0], color[1], color[2], 1.f};
+				memcpy(film + 4 * ((size_t) (H - 1 - py) * W + px), o, 16);
+			}
+		}
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
+	worker();
+	for (auto &t : pool) t.join();
+	return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

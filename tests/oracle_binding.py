@@ -85,6 +85,9 @@ def load(kind="reference"):
     lib.orc_render.argtypes = [P, C.POINTER(OrcParams), C.POINTER(KrrCameraData), I32, I32, U64, P, P, P, P, P,
                                C.POINTER(KrrStats), I32, I32, C.POINTER(P), C.POINTER(I32)]
     lib.orc_instance_xf.argtypes = [P, I32, F, C.POINTER(F), C.POINTER(F)]
+    lib.orc_render_megakernel.restype = C.c_double
+    lib.orc_render_megakernel.argtypes = [P, C.POINTER(OrcParams), C.POINTER(KrrCameraData), I32, I32, U64, P]
+    lib.orc_instance_xf_div.argtypes = [P, I32, F, C.POINTER(F), C.POINTER(F)]
     lib.orc_intersect_triangle.argtypes = [C.POINTER(F)] * 5 + [F] + [C.POINTER(F)] * 3
     lib.ol_init()
     _libs[kind] = lib
@@ -106,9 +109,11 @@ class Oracle:
             self.lib.orc_scene_destroy(self.scene)
             self.scene = None
 
-    def instance_xf(self, inst, time):
+    def instance_xf(self, inst, time, division_form=False):
+        """object->world / world->object of an instance at a ray time; division_form: the original division-based
+        SRT evaluation (an independent second statement of the same transform)"""
         m, inv = (F * 12)(), (F * 12)()
-        self.lib.orc_instance_xf(self.scene, inst, time, m, inv)
+        (self.lib.orc_instance_xf_div if division_form else self.lib.orc_instance_xf)(self.scene, inst, time, m, inv)
         return np.array(m, np.float32), np.array(inv, np.float32)
 
     def render(self, cam, w, h, frame_index=1, spp=1, max_depth=10, rr=0.8, nee=True, use_bvh=True, threads=0,
@@ -134,3 +139,12 @@ class Oracle:
         if capture:
             out["queues"] = [caps[q][: cap_counts[q]].copy() for q in range(6)]
         return out
+
+    def render_megakernel(self, cam, w, h, frame_id=1, spp=1, max_depth=10, rr=0.8, nee=True, use_bvh=True, threads=0):
+        """The reference's MegakernelPathTracer estimator (src/render/megakernel/device.cu:148-195) restated on the CPU;
+        the film holds the SUM over the samples, as the reference writes it."""
+        p = OrcParams(nee=int(nee), enable_medium=0, max_depth=max_depth, enable_clamp=0, spp=spp, rr=rr, clamp_max=1e3, use_bvh=int(use_bvh),
+                      threads=threads, row_begin=0, row_end=0)
+        film = np.zeros((h, w, 4), np.float32)
+        secs = self.lib.orc_render_megakernel(self.scene, C.byref(p), C.byref(cam), w, h, frame_id, film.ctypes.data)
+        return {"film": film, "seconds": secs}

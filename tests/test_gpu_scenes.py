@@ -102,3 +102,26 @@ def test_other_material_types_and_analytic_lights():
     assert st["miss_items"] > 0 and abs(st["miss_items"] - rs["miss_items"]) <= 0.02 * rs["miss_items"]
     assert np.isfinite(film).all()
     assert relmse(film, ref["film"]) <= 0.15
+
+
+def test_scene_without_any_light_renders_black_and_does_not_fault():
+    """No emissive mesh, analytic light or environment with nee on (the default): the light list is empty, so neither the
+    surface nor the medium scatter stage may index it (an uninitialised LightRec led to out-of-bounds triangle-light
+    reads).  Every path carries zero radiance; the ray counts show that the bounces still ran, without shadow rays."""
+    b = scenes.SceneBuilder()
+    p, n, idx = scenes.quad((-2, -1, -2), (0, 0, 4), (4, 0, 0))
+    b.add_instance(b.add_mesh(p, idx, n, b.add_material(diffuse=(0.6, 0.6, 0.6), bsdf_type=1)))
+    p, n, idx = scenes.quad((-2, -1, -2), (4, 0, 0), (0, 3, 0))
+    b.add_instance(b.add_mesh(p, idx, n, b.add_material(diffuse=(0.3, 0.5, 0.8), roughness=0.5, bsdf_type=4)))
+    desc = b.build()
+    w = h = 64
+    cam = scenes.look_at_camera((0, 0.5, 4.0), (0, 0, 0), 1.0)
+    gpu = krr.Wfpt(params=dict(spp=2, max_depth=4, nee=True))
+    gpu.set_scene(desc)
+    gpu.resize(w, h)
+    for frame in (1, 2):
+        gpu.begin_frame(frame, cam)
+        film = gpu.render_to_host()
+    st = gpu.stats()
+    assert np.isfinite(film).all() and (film[..., :3] == 0).all() and (film[..., 3] == 1).all()
+    assert st["closest_by_depth"][1] > 0 and st["shadow_rays"] == 0

@@ -52,3 +52,35 @@ def test_instant_shutter_equals_static_pose_and_wide_shutter_blurs():
     brute = orc.render(cam, w, h, spp=1, max_depth=2, use_bvh=False)
     assert np.array_equal(brute["first_hits"], moving["first_hits"])
     orc.close(), ors.close()
+
+
+def test_reciprocal_srt_evaluation_stays_within_ulps_of_the_division_form():
+    """The kernels and the oracle evaluate an SRT node with one reciprocal + products (motion.cuh srtNodeXf, driver.cpp
+    nodeXf) instead of the original per-entry divisions (driver.cpp nodeXfDiv, kept as a second statement).  Both
+    round the same real number: a product with a correctly rounded reciprocal is within 1.5 ulp of the correctly
+    rounded quotient, so chain entries may differ by a few ulp of the largest entry involved, never more; transformed
+    points stay within 1e-6 relative."""
+    b, info = scenes.instanced_scene(n_blas=2, tris_per_blas=120, n_groups=6, per_group=8, motion=True)
+    orc = ob.Oracle(b.build(), KIND)
+    rng = np.random.Generator(np.random.PCG64(scenes.SEED))
+    worst = 0.0
+    for i in range(info["n_moving"]):
+        for t in rng.uniform(-0.1, 1.1, 6):
+            m, inv = orc.instance_xf(i, float(t))
+            md, invd = orc.instance_xf(i, float(t), division_form=True)
+            for a, d in ((m, md), (inv, invd)):
+                A, D = a.reshape(3, 4), d.reshape(3, 4)
+                # linear part: ulp of the largest entry of the row (entries of a row are sums of products of that size)
+                scale = np.abs(D[:, :3]).max(axis=1, keepdims=True)
+                ulps = np.abs(A[:, :3] - D[:, :3]) / (np.spacing(scale.astype(np.float32)))
+                worst = max(worst, float(ulps.max()))
+                assert ulps.max() <= 16, (i, t, ulps.max())
+                # translation column: relative to the size of the terms that are summed into it
+                tscale = np.float32(np.abs(D[:, :3]).max() * 12.0 + np.abs(D[:, 3]).max())
+                assert np.abs(A[:, 3] - D[:, 3]).max() <= 16 * np.spacing(tscale), (i, t)
+            p = rng.uniform(-1, 1, 3).astype(np.float32)
+            w1 = m.reshape(3, 4)[:, :3] @ p + m.reshape(3, 4)[:, 3]
+            w2 = md.reshape(3, 4)[:, :3] @ p + md.reshape(3, 4)[:, 3]
+            assert np.abs(w1 - w2).max() <= 1e-6 * max(1.0, float(np.abs(w2).max()))
+    assert worst > 0, "the two forms are expected to differ in the last bits somewhere (else this test pins nothing)"
+    orc.close()
