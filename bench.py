@@ -171,7 +171,7 @@ class Workload:
 def cpu_reference_rate(wl, spp, rows, threads=0, frames=1):
     """Times the CPU oracle on a band of `rows` image rows of the workload, `frames` frames.  Returns (Mrays/s, info)."""
     import oracle_binding as ob
-    kind = "reference" if ob.available("reference") else "port"
+    kind = "reference"
     orc = ob.Oracle(wl.desc, kind)
     W, H = wl.W, wl.H
     rows = min(rows, H)

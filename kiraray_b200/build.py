@@ -3,7 +3,10 @@
 
   kiraray_b200/lib/libkrr_wfpt.so  CUDA kernels + C ABI (include/krr_wfpt.h)          [nvcc]
   kiraray_b200/lib/libkrr_host.so  C++17 host layer (RenderPass surface, importers)  [g++]
-  kiraray_b200/lib/krr_render      headless CLI driver (same JSON configs as the reference)
+  kiraray_b200/lib/krr_render      headless CLI driver (host/krr_render.cpp; same JSON configs as the reference)  [g++]
+
+Input data: kiraray_b200/data/spectral_srgb.bin (colour-space tables, see data/MANIFEST.json) is NOT built here; check_data()
+verifies it against the manifest's checksum and fails loudly when it is absent or different.
 
 nvcc cross-compiles without a GPU.  The .so files are git-ignored but travel to the GPU box.
 """
@@ -74,6 +77,22 @@ def build_variant(name, extra_flags):
     return out
 
 
+def check_data():
+    """The colour-space tables are an input file (data/MANIFEST.json: provenance, layout, checksum).  Raises when the
+    file is missing or does not match the manifest: the host layer would otherwise render with other colours."""
+    import hashlib
+    import json
+    man = json.load(open(os.path.join(HERE, "data", "MANIFEST.json")))
+    for name, m in man.items():
+        p = os.path.join(HERE, "data", name)
+        if not os.path.exists(p):
+            raise RuntimeError(f"{p} is missing: {m['how_to_get']}")
+        h = hashlib.sha256(open(p, "rb").read()).hexdigest()
+        if os.path.getsize(p) != m["bytes"] or h != m["sha256"]:
+            raise RuntimeError(f"{p}: size/sha256 {os.path.getsize(p)}/{h} differ from data/MANIFEST.json ({m['bytes']}/{m['sha256']})")
+    return True
+
+
 def build(force=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = deps([os.path.join(HERE, "csrc"), os.path.join(HERE, "host"), os.path.join(ROOT, "include")])
@@ -101,7 +120,7 @@ def build(force=False):
              "-Wl,-rpath,$ORIGIN"])
     cli_src = os.path.join(HERE, "host", "krr_render.cpp")
     cli = os.path.join(LIB, "krr_render")
-    if os.path.exists(cli_src) and (force or not newer(cli, [cli_src, host])):
+    if force or not newer(cli, [cli_src, host]):
         run([CXX, "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", cli, cli_src,
              "-L", LIB, "-lkrr_host", "-lkrr_wfpt", "-Wl,-rpath,$ORIGIN"])
     return wfpt, host

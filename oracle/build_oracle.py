@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
 """Build recipe for the CPU oracle (TEST INFRASTRUCTURE ONLY -- the product never links this).
 
-  python oracle/build_oracle.py port     -> oracle/_build/libkrr_oracle_port.so  (plain C++ restatement)
   python oracle/build_oracle.py ref      -> oracle/_ref/libkrr_oracle_ref.so     (reference's own
                                             KRR_CALLABLE headers, compiled where they lie under
                                             /root/reference/src; needs that tree, so it can only be
@@ -25,7 +24,6 @@ ROOT = os.path.dirname(HERE)
 REF = os.environ.get("KRR_REFERENCE_ROOT", "/root/reference")
 REF_OUT = os.path.join(HERE, "_ref")
 GEN = os.path.join(REF_OUT, "gen")
-PORT_OUT = os.path.join(HERE, "_build")
 CXX = os.environ.get("CXX", "g++")
 # -ffp-contract=off: no FMA contraction, so float results do not depend on -march
 COMMON = ["-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math"]
@@ -156,26 +154,6 @@ def build_ref():
     return True
 
 
-# ------------------------------------------------------------------------------------------------
-# port build (plain C++ restatement; no reference headers)
-# ------------------------------------------------------------------------------------------------
-def build_port():
-    os.makedirs(PORT_OUT, exist_ok=True)
-    srcs = [os.path.join(HERE, "port/backend_port.cpp"), os.path.join(HERE, "driver.cpp")]
-    if not os.path.exists(srcs[0]):
-        print("[oracle] port backend not present yet")
-        return False
-    so = os.path.join(PORT_OUT, "libkrr_oracle_port.so")
-    deps = srcs + [os.path.join(HERE, "oracle_leaf.h"), os.path.join(HERE, "driver.h"),
-                   os.path.join(ROOT, "include/krr_wfpt.h")]
-    deps += [os.path.join(HERE, "port", f) for f in os.listdir(os.path.join(HERE, "port"))]
-    if newer(so, deps):
-        return True
-    run([CXX] + COMMON + ["-O2", "-shared", "-Wl,-Bsymbolic", "-I", HERE, "-I", os.path.join(ROOT, "include"), "-o", so] + srcs)
-    print("[oracle] built", so)
-    return True
-
-
 def dump_spectral():
     """Dump the sRGB colour-space data (CIE X/Y/Z, D65, RGB<->XYZ, RGB->spectrum table) that the
     reference host application owns and passes to every pass (wavefront.h:28 `colorSpace`)."""
@@ -197,9 +175,9 @@ def dump_spectral():
 
 
 def main(argv):
-    what = argv[1:] or ["port", "ref", "spectral"]
+    what = argv[1:] or ["ref", "spectral"]
     for w in what:
-        {"port": build_port, "ref": build_ref, "spectral": dump_spectral}[w]()
+        {"ref": build_ref, "spectral": dump_spectral}[w]()
 
 
 if __name__ == "__main__":

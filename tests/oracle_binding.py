@@ -36,8 +36,7 @@ class OlTriLight(C.Structure):
 
 
 def paths():
-    return {"reference": os.path.join(ROOT, "oracle/_ref/libkrr_oracle_ref.so"),
-            "port": os.path.join(ROOT, "oracle/_build/libkrr_oracle_port.so")}
+    return {"reference": os.path.join(ROOT, "oracle/_ref/libkrr_oracle_ref.so")}
 
 
 _libs = {}
@@ -48,12 +47,12 @@ def available(kind):
 
 
 def load(kind="reference"):
-    """kind: 'reference' (reference's own classes, oracle/_ref) or 'port' (plain C++ restatement)."""
+    """kind: 'reference' -- the reference's own classes compiled host-side (oracle/_ref) under the restated stage driver."""
     if kind in _libs:
         return _libs[kind]
     path = paths()[kind]
     if not os.path.exists(path):
-        raise FileNotFoundError(f"{path}: build with `python oracle/build_oracle.py {'ref' if kind == 'reference' else 'port'}`")
+        raise FileNotFoundError(f"{path}: build with `python oracle/build_oracle.py ref`")
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     lib.ol_backend_name.restype = C.c_char_p
     lib.ol_pcg_get1d.restype = F

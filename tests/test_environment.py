@@ -15,7 +15,7 @@ import oracle_binding as ob
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CBOX = os.path.join(ROOT, "assets", "configs", "cbox.json")
 ENV = "tests/golden/piz_float_70x33.exr"  # 70 x 33 FLOAT, PIZ-compressed (tools/make_golden_piz.py)
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 KRR_LIGHT_INFINITE = 4  # include/krr_wfpt.h
 
 

@@ -10,7 +10,7 @@ import oracle_binding as ob
 from __graft_entry__ import relmse
 
 pytestmark = pytest.mark.gpu
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 W = H = 512
 SPP, DEPTH = 16, 5
 

@@ -14,7 +14,7 @@ from __graft_entry__ import relmse
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CBOX = os.path.join(ROOT, "assets", "configs", "cbox.json")
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def sky(path, w=64, h=32):

@@ -20,7 +20,7 @@ from __graft_entry__ import relmse
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def run(cfg, w, h, spp, max_depth):

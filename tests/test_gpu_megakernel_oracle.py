@@ -14,7 +14,7 @@ from __graft_entry__ import relmse
 from kiraray_b200 import scenes
 
 pytestmark = pytest.mark.gpu
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def gpu_megakernel(desc, cam, w, h, frame_id, **params):

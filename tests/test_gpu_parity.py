@@ -9,7 +9,7 @@ from __graft_entry__ import relmse
 
 pytestmark = pytest.mark.gpu
 
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def make_gpu(app, w, h):

@@ -10,7 +10,7 @@ from __graft_entry__ import relmse
 from kiraray_b200 import scenes
 
 pytestmark = pytest.mark.gpu
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def render_both(desc, cam, w, h, spp=1, max_depth=4, frame=1):

@@ -11,7 +11,7 @@ from __graft_entry__ import relmse
 from kiraray_b200 import scenes
 
 pytestmark = pytest.mark.gpu
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def checker(n, a, b, cells=8):

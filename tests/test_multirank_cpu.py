@@ -43,7 +43,7 @@ def _render(part, step=0):
     import oracle_binding as ob
     app = krr.HostApp(os.path.join(ROOT, "assets", "configs", "cbox.json"), asset_root=ROOT)
     app.set_resolution(W, H)
-    kind = "reference" if ob.available("reference") else "port"
+    kind = "reference"
     orc = ob.Oracle(app.scene_desc(), kind)
     out = orc.render(app.camera(), W, H, frame_index=part.frame_index(step), spp=1, max_depth=3, threads=1, rows=part.rows)
     orc.close()

@@ -18,7 +18,7 @@ import oracle_binding as ob
 from leaf_cases import LeafCases
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-KINDS = [k for k in ("reference", "port") if ob.available(k)]
+KINDS = [k for k in ("reference",) if ob.available(k)]
 INT_KEYS = {"pcg_state", "bsdf_type"}
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import oracle_binding as ob
 from kiraray_b200 import scenes
 
-KIND = "reference" if ob.available("reference") else "port"
+KIND = "reference"
 
 
 def small_scene(motion=True, **kw):
