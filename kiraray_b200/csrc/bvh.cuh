@@ -61,6 +61,7 @@ struct BvhDev {
 	int32_t nInstances;
 	const XformNodeRec *xnodes; // motion blur: transform chains + SRT key pool (motion.cuh), null otherwise
 	const float *motionKeys;
+	const float4 *motionFlat; // per instance: flat motion record (motion.cuh), null = none
 	// Static instances whose transform is exactly the identity are MERGED into one world-space BLAS
 	// (bvh_build.cu): object space == world space for them, so the intersection spec gives the same
 	// numbers, and a ray no longer enters each of them separately.  The merged BLAS hangs in the TLAS as
@@ -193,9 +194,9 @@ template <bool ANY> struct LocalStack {
 };
 
 // world ray -> object space of a moving instance (kept out of line: static scenes never pay its registers)
-static __device__ __noinline__ void movingRay(const BvhDev &bvh, int node, float time, V3 o, V3 d, V3 &ro, V3 &rd) {
+static __device__ __noinline__ void movingRay(const BvhDev &bvh, int inst, int node, float time, V3 o, V3 d, V3 &ro, V3 &rd) {
 	Xf m, inv;
-	chainXf(bvh.xnodes, bvh.motionKeys, node, time, m, inv);
+	movingInstanceXf(bvh.xnodes, bvh.motionKeys, bvh.motionFlat, inst, node, time, m, inv);
 	ro = xfPointX(inv, o), rd = xfVectorX(inv, d);
 }
 
@@ -313,24 +314,35 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		return true;
 	}
 	// ---- phase: enter the nearest hit instance of the TLAS group (object-space ray; t stays the world parameter) ----
-	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls) {
+	// Two steps.  PROBE: take the nearest instance bit of the group and test the ray against the instance's bounding
+	// sphere (a rotated object's box is much larger than the object); culled instances only cost this.  ENTER: push the
+	// TLAS-level groups, transform the ray, start at the BLAS root.  Static kernels run both at once (enterInstance).
+	// In the MOTION kernels entering a moving instance evaluates its SRT chain at the ray's time (~450 instructions),
+	// so the probe PARKS the lane (curInst = -2 - instance) and trip() runs the entry of all parked lanes under a
+	// vote: the chain then executes with the lanes that passed the sphere test, not with the ones that merely wanted
+	// to look (ncu, 10 000 moving instances: the chain ran with 5 of 32 lanes when the vote counted probing lanes).
+	KRR_DEV int probeInstance(const BvhDev &bvh) { // returns the instance to enter, -1 when this bit was culled
 		const uint32_t bit = 31u - (uint32_t) __clz(tg.y);
 		tg.y ^= 1u << bit;
 		const uint32_t slot = bit ^ (octinv4 & 7u);
 		const int inst		= __ldg(bvh.tlasInst + tg.x + slot);
-		{ // conservative ray / bounding-sphere test (the bit is consumed either way)
-			const float4 sph = __ldg(bvh.instSphere + inst);
-			if (sph.w < 1.0e30f) {
-				const V3 l	   = mk3(sph.x - o.x, sph.y - o.y, sph.z - o.z);
-				const float ts = fminf(fmaxf(dot(l, d) / dot(d, d), 0.f), best.t); // closest approach within [0, best.t]
-				const V3 q	   = l - d * ts;
-				const float rr = sph.w * 1.0005f + 1e-5f * (fabsf(sph.x) + fabsf(sph.y) + fabsf(sph.z) + 1.f);
+		// conservative ray / bounding-sphere test (the bit is consumed either way)
+		const float4 sph = __ldg(bvh.instSphere + inst);
+		if (sph.w < 1.0e30f) {
+			const V3 l	   = mk3(sph.x - o.x, sph.y - o.y, sph.z - o.z);
+			const float ts = fminf(fmaxf(dot(l, d) / dot(d, d), 0.f), best.t); // closest approach within [0, best.t]
+			const V3 q	   = l - d * ts;
+			const float rr = sph.w * 1.0005f + 1e-5f * (fabsf(sph.x) + fabsf(sph.y) + fabsf(sph.z) + 1.f);
+			if (dot(q, q) > rr * rr) {
 #ifdef KRR_COUNT_TRIPS
-				if (dot(q, q) > rr * rr) culled++;
+				culled++;
 #endif
-				if (dot(q, q) > rr * rr) return;
+				return -1;
 			}
 		}
+		return inst;
+	}
+	KRR_DEV void enterProbed(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls, int inst) {
 #ifdef KRR_COUNT_TRIPS
 		enters++;
 #endif
@@ -339,11 +351,27 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		if (tg.y) push(sm, ls, tg);
 		curInst = inst;
 		const InstRec &in = instances[inst];
-		if (MOTION && in.motion >= 0) movingRay(bvh, in.motion, time, o, d, ro, rd); // SRT motion chain at the ray's time
+		if (MOTION && in.motion >= 0) movingRay(bvh, inst, in.motion, time, o, d, ro, rd); // SRT motion chain at the ray's time
 		else ro = xfPointX(in.inv, o), rd = xfVectorX(in.inv, d);
 		setSpace();
 		blasBase = sp;
 		enterRoot(bvh, (uint32_t) in.blasRoot);
+	}
+	KRR_DEV void enterInstance(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls) {
+		const int inst = probeInstance(bvh);
+		if (inst >= 0) enterProbed(bvh, instances, sm, ls, inst);
+	}
+	// MOTION kernels: probe the group's instances until one passes; a static one is entered at once, a moving one parks
+	// the lane for the voted entry
+	KRR_DEV bool parked() const { return MOTION && curInst <= -2; }
+	KRR_DEV void probeAndPark(const BvhDev &bvh, const InstRec *__restrict__ instances, TraceSmem &sm, LStack &ls) {
+		while (tg.y) {
+			const int inst = probeInstance(bvh);
+			if (inst < 0) continue;
+			if (instances[inst].motion < 0) enterProbed(bvh, instances, sm, ls, inst);
+			else curInst = -2 - inst;
+			return;
+		}
 	}
 	// ---- phase: wide node.  Takes the nearest hit child of the node group, tests its 8 children ----
 	KRR_DEV void nodeStep(const BvhDev &bvh, TraceSmem &sm, LStack &ls) {
@@ -541,21 +569,26 @@ template <bool ANY, bool MOTION = true, bool PAIR = false> struct Traverser {
 		} else {
 			const unsigned FULL = 0xffffffffu;
 			bool fin = false;
-			if (active && !hasNode() && !tg.y) fin = !popNext(sm, ls);
+			if (active && !parked() && !hasNode() && !tg.y) fin = !popNext(sm, ls);
 			const bool live = active && !fin;
-			const bool wantEnter = live && tg.y && curInst < 0;
-			const unsigned mE	 = __ballot_sync(FULL, wantEnter);
-			bool runE = mE != 0u;
-			if (MOTION && runE && __popc(mE) < KRR_ENTER_VOTE) runE = !__any_sync(FULL, live && !wantEnter); // every live lane waits to enter
-			if (runE && wantEnter) enterInstance(bvh, instances, sm, ls);
-			const bool wantNode = live && !tg.y && hasNode();
+			if constexpr (MOTION) {
+				if (live && tg.y && curInst == -1) probeAndPark(bvh, instances, sm, ls);
+				const bool wantEnter = live && parked();
+				const unsigned mE	 = __ballot_sync(FULL, wantEnter);
+				bool runE = mE != 0u;
+				if (runE && __popc(mE) < KRR_ENTER_VOTE) runE = !__any_sync(FULL, live && !wantEnter); // every live lane waits to enter
+				if (runE && wantEnter) enterProbed(bvh, instances, sm, ls, -2 - curInst);
+			} else {
+				if (live && tg.y && curInst < 0) enterInstance(bvh, instances, sm, ls);
+			}
+			const bool wantNode = live && !parked() && !tg.y && hasNode();
 			if (__any_sync(FULL, wantNode)) {
 				if (wantNode) nodeStep(bvh, sm, ls);
 			}
 			const bool wantTri = live && tg.y && curInst >= 0;
 			const unsigned mT  = __ballot_sync(FULL, wantTri);
 			bool run = mT != 0u;
-			if (VOTE && run && __popc(mT) < KRR_TRI_VOTE) run = !__any_sync(FULL, live && !tg.y && hasNode());
+			if (VOTE && run && __popc(mT) < KRR_TRI_VOTE) run = !__any_sync(FULL, live && !parked() && !tg.y && hasNode());
 			if (run && wantTri) fin = triStep(bvh, instances, accept, KRR_TRI_PER_TRIP);
 			return fin;
 		}

@@ -972,7 +972,7 @@ int BvhBuilder::refitLaunches() const { return 1 + std::max(0, (int) m->tlasLeve
 BvhDev BvhBuilder::device() const {
 	BvhDev d;
 	d.nodes = m->nodes.p, d.tris = m->tris.p, d.tlasInst = m->tlasInst.p, d.tlasRoot = 0, d.nInstances = m->nInstances;
-	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys;
+	d.xnodes = m->motion.xnodes, d.motionKeys = m->motion.keys, d.motionFlat = nullptr; // (set by the pass: api.cu makeWavefront)
 	d.mergedInst = m->mergedInst, d.mergedRoot = m->mergedRoot, d.mergedXf = m->mergedXf;
 	d.flats = m->flats.p;
 	d.instSphere = m->instSpheres.p;

@@ -12,7 +12,7 @@ __global__ void k_leaf_instance_xf(SceneDev sc, const int32_t *ids, const float 
 	if (i >= n) return;
 	const InstRec &in = sc.instances[ids[i]];
 	Xf m = in.xf, inv = in.inv;
-	if (in.motion >= 0) chainXf(sc.xnodes, sc.motionKeys, in.motion, times[i], m, inv);
+	if (in.motion >= 0) movingInstanceXf(sc.xnodes, sc.motionKeys, sc.motionFlat, ids[i], in.motion, times[i], m, inv); // the path the kernels take
 	for (int k = 0; k < 12; k++) out24[24 * i + k] = m.m[k], out24[24 * i + 12 + k] = inv.m[k];
 }
 

@@ -41,21 +41,8 @@ KRR_HD Xf xfMulX(const Xf &a, const Xf &b) { // a * b, unfused, left to right
 	return c;
 }
 
-// SRT keys -> node matrix and inverse at `time`
-KRR_HD void srtNodeXf(const float *__restrict__ keys, int n, float t0, float t1, float time, Xf &m, Xf &inv) {
-	int k	= 0;
-	float f = 0.f;
-	if (time >= t1) k = n - 2, f = 1.f;
-	else if (time > t0) {
-		float u = xmul(xdiv(xsub(time, t0), xsub(t1, t0)), (float) (n - 1));
-		k		= (int) u;
-		if (k > n - 2) k = n - 2;
-		f = xsub(u, (float) k);
-	}
-	const float *a = keys + 10 * k, *b = a + 10;
-	float v[10];
-#pragma unroll
-	for (int i = 0; i < 10; i++) v[i] = xadd(a[i], xmul(f, xsub(b[i], a[i])));
+// interpolated SRT values v = (s[3], q[4] xyzw, t[3]) -> node matrix and inverse
+KRR_HD void srtMatrices(const float *v, Xf &m, Xf &inv) {
 	float len = xsqrt(xadd(xadd(xmul(v[3], v[3]), xmul(v[4], v[4])), xadd(xmul(v[5], v[5]), xmul(v[6], v[6]))));
 	// one correctly rounded reciprocal and four products instead of four divisions, three reciprocals for the nine
 	// entries of the inverse: 14 divisions per node were 15 % of the instructions of the motion-blur trace kernel
@@ -81,6 +68,24 @@ KRR_HD void srtNodeXf(const float *__restrict__ keys, int n, float t0, float t1,
 		inv.m[r * 4 + 3] = -xadd(xadd(xmul(inv.m[r * 4], v[7]), xmul(inv.m[r * 4 + 1], v[8])), xmul(inv.m[r * 4 + 2], v[9]));
 }
 
+// SRT keys -> node matrix and inverse at `time`
+KRR_HD void srtNodeXf(const float *__restrict__ keys, int n, float t0, float t1, float time, Xf &m, Xf &inv) {
+	int k	= 0;
+	float f = 0.f;
+	if (time >= t1) k = n - 2, f = 1.f;
+	else if (time > t0) {
+		float u = xmul(xdiv(xsub(time, t0), xsub(t1, t0)), (float) (n - 1));
+		k		= (int) u;
+		if (k > n - 2) k = n - 2;
+		f = xsub(u, (float) k);
+	}
+	const float *a = keys + 10 * k, *b = a + 10;
+	float v[10];
+#pragma unroll
+	for (int i = 0; i < 10; i++) v[i] = xadd(a[i], xmul(f, xsub(b[i], a[i])));
+	srtMatrices(v, m, inv);
+}
+
 KRR_HD void nodeXf(const XformNodeRec &nd, const float *__restrict__ keyPool, float time, Xf &m, Xf &inv) {
 	if (nd.nKeys >= 2) srtNodeXf(keyPool + 10 * (size_t) nd.keyOff, nd.nKeys, nd.t0, nd.t1, time, m, inv);
 	else m = nd.local, inv = nd.localInv;
@@ -96,5 +101,81 @@ KRR_HD void chainXf(const XformNodeRec *__restrict__ nodes, const float *__restr
 		inv = xfMulX(inv, pinv);
 	}
 }
+
+// ---- flat motion records ---------------------------------------------------------------------------------------
+// chainXf walks instance -> transform node -> key pool -> parent node -> key pool: four or five DEPENDENT loads
+// before the first multiplication, with the warp waiting on each (the trace kernels of the 10 000-instance scene are
+// latency-bound).  The common chain -- at most two levels, each an SRT node with exactly two keys -- is therefore
+// also stored per INSTANCE as one contiguous record (krr_wfpt_set_scene): every load depends on the instance id
+// alone.  Record = kMotionFlatStride float4:
+//   [0] (levels (int bits): 0 = no record, use the chain; 1; 2,  -, -, -)   [1] (t0, t1 of level 0, t0, t1 of level 1)
+//   [2..6] level 0 (the instance's own node): key a[10], then b[i] - a[i] (rounded once, as xsub(b[i], a[i]) is)
+//   [7..11] level 1 (its parent)
+// The arithmetic is THE SPEC's, operation by operation: with two keys u = (time-t0)/(t1-t0) * 1 = the quotient itself,
+// k = 0 (u <= 1; int(u) = 1 is clamped to n - 2 = 0) and f = u - 0 = u, so the interpolated values, and everything
+// computed from them by srtMatrices / xfMulX, are the floats chainXf produces (tests/test_gpu_motion.py compares the
+// tap that runs this path with the oracle bit for bit).
+constexpr int kMotionFlatStride = 12;
+#ifdef __CUDACC__
+KRR_DEV void flatLevelXf(const float4 *__restrict__ p, float t0, float t1, float time, Xf &m, Xf &inv) {
+	float f = 0.f;
+	if (time >= t1) f = 1.f;
+	else if (time > t0) f = xdiv(xsub(time, t0), xsub(t1, t0));
+	const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4);
+	const float a[10]	 = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+	const float diff[10] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+	float v[10];
+#pragma unroll
+	for (int i = 0; i < 10; i++) v[i] = xadd(a[i], xmul(f, diff[i]));
+	srtMatrices(v, m, inv);
+}
+// object->world and world->object of a moving instance from its flat record; false = no record (use chainXf).
+// KRR_FLAT_LOOP=1 runs the levels as a loop (one copy of the level code: a smaller instruction footprint, but the
+// matrices then live in local memory: measured slower)
+#ifndef KRR_FLAT_LOOP
+#define KRR_FLAT_LOOP 0
+#endif
+KRR_DEV bool flatChainXf(const float4 *__restrict__ rec, float time, Xf &m, Xf &inv) {
+	const int levels = __float_as_int(__ldg(rec).x);
+	if (levels == 0) return false;
+	const float4 tt = __ldg(rec + 1);
+	if (levels == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 7)); // the parent's keys arrive while level 0 is evaluated
+#if KRR_FLAT_LOOP
+#pragma unroll 1
+	for (int l = 0; l < levels; l++) {
+		Xf lm, linv;
+		flatLevelXf(rec + 2 + 5 * l, l ? tt.z : tt.x, l ? tt.w : tt.y, time, lm, linv);
+		if (l == 0) m = lm, inv = linv;
+		else m = xfMulX(lm, m), inv = xfMulX(inv, linv);
+	}
+#else
+	flatLevelXf(rec + 2, tt.x, tt.y, time, m, inv);
+	if (levels == 2) {
+		Xf pm, pinv;
+		flatLevelXf(rec + 7, tt.z, tt.w, time, pm, pinv);
+		m	= xfMulX(pm, m);
+		inv = xfMulX(inv, pinv);
+	}
+#endif
+	return true;
+}
+// the general chain, kept out of line (and out of the hot loop's instruction footprint)
+static __device__ __noinline__ void chainXfCold(const XformNodeRec *__restrict__ nodes, const float *__restrict__ keyPool, int node, float time, Xf *m, Xf *inv) {
+	chainXf(nodes, keyPool, node, time, *m, *inv);
+}
+// transforms of moving instance `inst` (chain starting at `node`) at `time`: the flat record when there is one
+KRR_DEV void movingInstanceXf(const XformNodeRec *__restrict__ nodes, const float *__restrict__ keyPool, const float4 *__restrict__ flat, int inst, int node,
+							  float time, Xf &m, Xf &inv) {
+	if (flat && flatChainXf(flat + (size_t) inst * kMotionFlatStride, time, m, inv)) return;
+#ifndef KRR_CHAIN_COLD
+#define KRR_CHAIN_COLD 0 // measured: the call makes movingRay a non-leaf function, 695 -> 669 Mrays/s
+#endif
+#if KRR_CHAIN_COLD
+	chainXfCold(nodes, keyPool, node, time, &m, &inv);
+#else
+	chainXf(nodes, keyPool, node, time, m, inv);
+#endif
+}
+#endif
 
 } // namespace krr

@@ -116,6 +116,7 @@ struct SceneDev {
 	const float *spectrumTables;
 	const float *motionKeys;	 // KrrSRT as 10 floats
 	const XformNodeRec *xnodes;	 // transform chains of the moving instances
+	const float4 *motionFlat;	 // per instance: flat motion record (motion.cuh kMotionFlatStride float4), null = none
 	int32_t nMeshes, nInstances, nMaterials, nLights, nInfinite, nMedia;
 	float motionStart, motionEnd;
 	int32_t hasMotion;

@@ -26,6 +26,8 @@
 //     no host synchronisation and no full-width launch over a nearly empty queue
 //   * pushes are warp-aggregated: one atomicAdd per warp per queue
 #pragma once
+#include <cub/block/block_radix_sort.cuh>
+
 #include "bsdf.cuh"
 #include "bvh.cuh"
 #include "lights.cuh"
@@ -109,6 +111,7 @@ struct Params {
 	// writing (-166 MB of stores per 1080p sample).  Off with participating media (the medium stage updates
 	// thp / pu / pl in place) and while a debug capture is armed.
 	int32_t implicitDepth0;
+	int32_t sortKey; // k_sort_rays: 0 = direction octant above the origin's Morton code, 1 = Morton code above the octant
 };
 
 struct KrrCameraDev {
@@ -138,6 +141,9 @@ struct Wavefront {
 	// per instance: bit0 null material, bit1 has alpha (transmission) texture, bit2 emissive, bits 4-6 BSDF
 	// type of its material -- everything the closest stage needs to route a hit, in one load
 	const uint8_t *instFlags;
+	// RAY REORDERING ("sort_rays"): the trace stage of depth >= 1 takes its rays through these permutations of the
+	// queue slots (null = queue order).  perm[k] = slot of the k-th ray in traversal order; see k_sort_rays
+	const int32_t *permClosest, *permShadow;
 	int32_t *tripHist; // KRR_COUNT_TRIPS builds: histogram of node visits per closest ray (64 bins of 8, 64-bit counts)
 };
 
@@ -364,8 +370,8 @@ struct WarpWork {
 // object<->world of an instance at ray time `time`: the transform list OptiX reports for a hit
 // (getInstanceTransform, shading.h:70-76) -- static instances use the uploaded matrices, moving ones
 // evaluate their SRT chain (motion.cuh)
-static __device__ __noinline__ void movingXf(const SceneDev &sc, int node, float time, Xf *xf, Xf *inv) {
-	chainXf(sc.xnodes, sc.motionKeys, node, time, *xf, *inv);
+static __device__ __noinline__ void movingXf(const SceneDev &sc, int inst, int node, float time, Xf *xf, Xf *inv) {
+	movingInstanceXf(sc.xnodes, sc.motionKeys, sc.motionFlat, inst, node, time, *xf, *inv);
 }
 
 // null-material hit: the ray continues behind the surface (device.cu:54-58): new origin / medium in o4 / d4
@@ -380,7 +386,7 @@ KRR_DEV void continueThroughNull(const Wavefront &wf, Hit h, float4 &o4, float4 
 	const Xf *xf = &in.xf, *inv = &in.inv;
 	Xf mxf, minv;
 	if (MOTION && in.motion >= 0) {
-		movingXf(wf.scene, in.motion, o4.w, &mxf, &minv);
+		movingXf(wf.scene, h.inst, in.motion, o4.w, &mxf, &minv);
 		xf = &mxf, inv = &minv;
 	}
 	V3 p = xfPoint(*xf, b0 * p0 + h.u * p1 + h.v * p2);
@@ -438,6 +444,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	if (MODE == kTraceFlat) work.init(n, &dc->cursorRay, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
 	else work.initSpread(n, &dc->cursorRay, block, nBlocks, (int) threadIdx.x >> 5, kTraceBlock >> 5);
 	if (work.next >= n) return; // short queue: this warp has no static share and nothing to claim
+	const int32_t *__restrict__ perm = depth > 0 ? wf.permClosest : nullptr; // reordered queue (k_sort_rays)
 	int medium = -1; // medium the ray travels in (d_medium.w)
 	while (true) {
 		// ---- finalise finished rays in BATCHES: the finalisation is a chain of dependent long-latency
@@ -512,6 +519,7 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 		if (!work.exhausted && __popc(idle) >= wf.p.refill) {
 			int r = work.take(idle, lane);
 			if (r >= 0) {
+				if (perm) r = __ldg(perm + r);
 				ray = r;
 				const float4 o4 = ldcs4(q.o_time + r), d4 = ldcs4(q.d_medium + r);
 				pix	   = implicit ? r : __float_as_int(__ldcs(reinterpret_cast<const float *>(q.ctxP_pix + r) + 3));
@@ -535,8 +543,16 @@ KRR_DEV void traceClosestBody(const Wavefront &wf, int depth, TraceSmem &sm, int
 	}
 }
 
+// Resident CTAs per SM the stand-alone closest kernel (depth 0) is compiled for.  The moving-instance kernel runs 7 CTAs
+// at 72 registers like the fused kernel (4K primary rays of the 10 000-instance scene: 23.5 -> 21.0 ms); the static
+// kernels get no occupancy request: 128 registers, 4 CTAs (a request of 1 lets the compiler take 168+ registers: -25 %)
+#ifndef KRR_CLOSEST_MINB
+#define KRR_CLOSEST_MINB 7
+#endif
+template <int MODE> struct ClosestBounds { static constexpr int minBlocks = MODE == kTraceMotion ? KRR_CLOSEST_MINB : 4; };
+#define KRR_CLOSEST_BOUNDS __launch_bounds__(kTraceBlock, ClosestBounds<MODE>::minBlocks)
 template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
+__global__ void KRR_CLOSEST_BOUNDS k_trace_closest(const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;
 	traceClosestBody<MODE>(wf, depth, sm, blockIdx.x, gridDim.x);
@@ -591,7 +607,7 @@ KRR_DEV void rebuildGeometry(const Wavefront &wf, int4 hit, V3 rayDir, float tim
 	const Xf *xf = &in.xf, *inv = &in.inv;
 	Xf mxf, minv;
 	if (MOTION && in.motion >= 0) {
-		movingXf(sc, in.motion, time, &mxf, &minv);
+		movingXf(sc, g.inst, in.motion, time, &mxf, &minv);
 		xf = &mxf, inv = &minv;
 	}
 	g.p			= xfPoint(*xf, g.p);
@@ -1010,6 +1026,7 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 	if (MODE == kTraceFlat) work.init(n, &dc->cursorShadow, (block * kTraceBlock + (int) threadIdx.x) >> 5, (nBlocks * kTraceBlock) >> 5);
 	else work.initSpread(n, &dc->cursorShadow, block, nBlocks, (int) threadIdx.x >> 5, kTraceBlock >> 5);
 	if (work.next >= n) return;
+	const int32_t *__restrict__ perm = wf.permShadow;
 	while (true) {
 		// finished rays add their contribution in batches (same reasoning as in the closest stage: the
 		// read-modify-write of L is a long-latency chain the whole warp would wait for on every trip)
@@ -1025,6 +1042,7 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 		if (!work.exhausted && __popc(idle) >= wf.p.refill) {
 			int r = work.take(idle, lane);
 			if (r >= 0) {
+				if (perm) r = __ldg(perm + r);
 				ray = r;
 				float4 o4 = ldcs4(wf.shadow.o_tmax + r), d4 = ldcs4(wf.shadow.d_pix + r);
 				pix = __float_as_int(d4.w);
@@ -1053,6 +1071,101 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 	traceShadowBody<MODE>(wf, depth, sm, blockIdx.x, gridDim.x);
 }
 
+// =================================================================================================
+// Ray reordering.  The scatter stage emits the rays of the next depth in the order its items were pushed: origins
+// scattered over the scene, directions over the sphere.  A trace warp that takes 32 consecutive queue slots then
+// holds 32 unrelated rays -- every lane in another instance / subtree, in another traversal phase (SIMT efficiency
+// 13 of 32 on the 10 000-instance scene), every node fetch a different line.  k_sort_rays re-orders the queue for
+// the trace stage WITHOUT moving the items: every CTA takes a tile of kSortTile consecutive slots, gives each ray
+// the key (direction octant, Morton code of its origin in the frame of the BVH root node), sorts the tile's
+// (key, slot) pairs in shared memory (cub::BlockRadixSort) and writes the sorted slots to `perm`; the trace
+// warps read their slots through it.  Sorting inside tiles needs no global pass and no host-side size (the queue
+// length lives on the device); rays of one tile that share an octant and a region end up in the same warps.
+// Pixels are independent (own RNG stream, own accumulator; one ray per pixel and depth), so the order in which a
+// stage processes its queue does not change a single draw or addition: films are bit-identical
+// (tests/test_gpu_sort_rays.py).
+constexpr int kSortThreads = 256, kSortItems = 16, kSortTile = kSortThreads * kSortItems, kSortMortonBits = 6;
+constexpr int kSortKeyBits = 3 + 3 * kSortMortonBits;
+
+KRR_DEV uint32_t spreadBits3(uint32_t v) { // bit i of a 10-bit value -> bit 3 i
+	v = (v | (v << 16)) & 0x030000ffu;
+	v = (v | (v << 8)) & 0x0300f00fu;
+	v = (v | (v << 4)) & 0x030c30c3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+// frame of the Morton code: the quantisation frame of the BVH root node (anchor, 256 steps of 2^(e-127) per axis)
+struct SortFrame { float ox, oy, oz, ix, iy, iz; };
+KRR_DEV SortFrame sortFrame(const BvhDev &bvh) {
+	const uint32_t root = bvh.mergedOnly ? (uint32_t) bvh.mergedRoot : (uint32_t) bvh.tlasRoot;
+	SortFrame f{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	if (isFlatEntry(root)) return f;
+	const float4 n0	  = __ldg(reinterpret_cast<const float4 *>(bvh.nodes + root));
+	const uint32_t ew = __float_as_uint(n0.w);
+	const float k	  = (float) (1 << kSortMortonBits) / 256.f;
+	f.ox = n0.x, f.oy = n0.y, f.oz = n0.z;
+	f.ix = k / __uint_as_float((ew & 0xff) << 23), f.iy = k / __uint_as_float(((ew >> 8) & 0xff) << 23), f.iz = k / __uint_as_float(((ew >> 16) & 0xff) << 23);
+	return f;
+}
+KRR_DEV uint32_t rayKey(const SortFrame &f, float4 o, float4 d, int mode) {
+	const float top	   = (float) ((1 << kSortMortonBits) - 1);
+	const uint32_t qx  = (uint32_t) fminf(fmaxf((o.x - f.ox) * f.ix, 0.f), top); // NaN -> 0
+	const uint32_t qy  = (uint32_t) fminf(fmaxf((o.y - f.oy) * f.iy, 0.f), top);
+	const uint32_t qz  = (uint32_t) fminf(fmaxf((o.z - f.oz) * f.iz, 0.f), top);
+	const uint32_t mor = (spreadBits3(qx) << 2) | (spreadBits3(qy) << 1) | spreadBits3(qz);
+	const uint32_t oct = (d.x >= 0.f ? 4u : 0u) | (d.y >= 0.f ? 2u : 0u) | (d.z >= 0.f ? 1u : 0u);
+	return mode == 0 ? (oct << (3 * kSortMortonBits)) | mor : (mor << 3) | oct;
+}
+
+// closest rays of loop depth `depth + 1` (perm = wf.permClosest) and shadow rays of `depth` (wf.permShadow): the two
+// queues the scatter stage of `depth` filled, i.e. what the fused trace launch of `depth` consumes
+__global__ void __launch_bounds__(kSortThreads) k_sort_rays(const __grid_constant__ Wavefront wf, int depth, int32_t *permClosest, int32_t *permShadow) {
+	using Sort = cub::BlockRadixSort<uint32_t, kSortThreads, kSortItems, uint32_t>;
+	__shared__ typename Sort::TempStorage tmp;
+	const int nC = permClosest ? wf.counters[depth + 1].nRay : 0, nS = permShadow ? wf.counters[depth].nShadow : 0;
+	const int tilesC = (nC + kSortTile - 1) / kSortTile, tilesS = (nS + kSortTile - 1) / kSortTile;
+	const RayQueue q  = wf.rays[(depth + 1) & 1];
+	const SortFrame f = sortFrame(wf.bvh);
+	for (int tile = blockIdx.x; tile < tilesC + tilesS; tile += gridDim.x) {
+		const bool shadow	= tile >= tilesC;
+		const int base		= (shadow ? tile - tilesC : tile) * kSortTile;
+		const int n			= shadow ? nS : nC;
+		const float4 *org	= shadow ? wf.shadow.o_tmax : q.o_time;
+		const float4 *dir	= shadow ? wf.shadow.d_pix : q.d_medium;
+		int32_t *perm		= shadow ? permShadow : permClosest;
+		uint32_t keys[kSortItems], vals[kSortItems];
+#pragma unroll
+		for (int k = 0; k < kSortItems; k++) { // striped reads: coalesced
+			const int local = k * kSortThreads + (int) threadIdx.x, i = base + local;
+			vals[k] = (uint32_t) local;
+			keys[k] = i < n ? rayKey(f, __ldg(org + i), __ldg(dir + i), wf.p.sortKey) : (1u << kSortKeyBits); // past the end: sorts last
+		}
+		Sort(tmp).SortBlockedToStriped(keys, vals, 0, kSortKeyBits + 1);
+#pragma unroll
+		for (int k = 0; k < kSortItems; k++) {
+			const int i = base + k * kSortThreads + (int) threadIdx.x;
+			if (i < n) perm[i] = base + (int) vals[k];
+		}
+		__syncthreads(); // tmp is reused by the next tile
+	}
+}
+
+// Global variant ("sort_rays" bit 2): keys of a whole queue for a device-wide radix sort (cub::DeviceRadixSort in
+// krr_wfpt_render).  The queue length lives on the device, the sort's item count on the host: the sort covers the
+// queue's CAPACITY and slots past the end get a key above every real one, so that perm[0 .. n) are the live slots.
+__global__ void k_ray_keys(const __grid_constant__ Wavefront wf, int depth, int shadow, uint32_t *keys, int32_t *vals, int capacity) {
+	const int n		  = shadow ? wf.counters[depth].nShadow : wf.counters[depth + 1].nRay;
+	const RayQueue q  = wf.rays[(depth + 1) & 1];
+	const float4 *org = shadow ? wf.shadow.o_tmax : q.o_time;
+	const float4 *dir = shadow ? wf.shadow.d_pix : q.d_medium;
+	const SortFrame f = sortFrame(wf.bvh);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += gridDim.x * blockDim.x) {
+		keys[i] = i < n ? rayKey(f, __ldg(org + i), __ldg(dir + i), wf.p.sortKey) : (1u << kSortKeyBits);
+		vals[i] = i;
+	}
+}
+
 // Fused trace stage: the shadow rays of `depth` and the closest rays of `depth + 1` were both produced
 // by the scatter stage of `depth` and do not depend on each other (the shadow stage only adds to L, the
 // closest stage only draws the Russian-roulette sample; handleHit/Miss of depth + 1 runs afterwards, so
@@ -1070,8 +1183,13 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(const __grid_const
 #ifndef KRR_TREE_MINB
 #define KRR_TREE_MINB 7
 #endif
+// static tree scenes: 6 CTAs/SM at 80 registers (20 M triangles: 1 195 -> 1 256 Mrays/s against 7 CTAs at 72; the
+// moving-instance kernel is the other way round: 7 CTAs 695, 6 CTAs 646, 8 CTAs 665 Mrays/s)
+#ifndef KRR_STATIC_MINB
+#define KRR_STATIC_MINB 6
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock, MODE == kTraceFlat ? KRR_FUSED_MINB : KRR_TREE_MINB) k_trace_fused(
+__global__ void __launch_bounds__(kTraceBlock, MODE == kTraceFlat ? KRR_FUSED_MINB : MODE == kTraceStatic ? KRR_STATIC_MINB : KRR_TREE_MINB) k_trace_fused(
 const __grid_constant__ Wavefront wf, int depth) {
 	KRR_PDL_ENTRY();
 	__shared__ TraceSmem sm;

@@ -1,5 +1,7 @@
 // krr_render -- headless counterpart of the reference's executable (src/main/kiraray.cpp:5-32):
 //   krr_render <config.json> [max_frames] [film.exr|film.pfm]
+// environment: KRR_DATA_DIR = directory of spectral_srgb.bin; KRR_ASSET_ROOT = directory model paths are resolved
+// against (default: the config's directory, as in the reference)
 // loads the config (RenderApp::loadConfigFrom), runs the frame loop until a pass asks for the exit (AccumulatePass
 // "exit_on_finish" with a spent "task" budget) or max_frames, finalises the passes ("save_on_finish", ErrorMeasure
 // "save") and optionally writes the accumulated (or last) film.  Everything goes through the C entry points of the
@@ -27,7 +29,7 @@ int main(int argc, char **argv) {
 	if (const char *dir = std::getenv("KRR_DATA_DIR")) krr_host_set_data_dir(dir);
 
 	KrrHostApp *app = nullptr;
-	if (krr_host_app_create(config, 1, nullptr, &app) != KRR_OK) return fail("loading the config");
+	if (krr_host_app_create(config, 1, std::getenv("KRR_ASSET_ROOT"), &app) != KRR_OK) return fail("loading the config");
 	std::fprintf(stderr, "krr_render: using config file %s\n", config);
 	const int frames = krr_host_app_run(app, maxFrames, /*finalize=*/1);
 	if (frames < 0) {

@@ -7,7 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "kiraray_b200", "lib", "krr_render")
-ENV = dict(os.environ, KRR_DATA_DIR=os.path.join(ROOT, "kiraray_b200", "data"))
+ENV = dict(os.environ, KRR_DATA_DIR=os.path.join(ROOT, "kiraray_b200", "data"), KRR_ASSET_ROOT=ROOT)
 
 
 def test_cli_is_built_and_reports_errors():

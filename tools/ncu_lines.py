@@ -53,9 +53,10 @@ def main():
     rows = list(csv.reader(io.StringIO("\n".join(sec))))
     hdr = rows[0]
     ia, isrc, iinst, isamp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+    ithr = hdr.index("Predicated-On Thread Instructions Executed")
     stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     base = int(rows[1][ia], 16)
-    agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
+    agg = collections.defaultdict(lambda: [0, 0, collections.Counter(), 0])
     tot_i = tot_s = mismatch = 0
     for r in rows[1:]:
         off = int(r[ia], 16) - base
@@ -63,15 +64,15 @@ def main():
         if text.split(" ")[0].split(".")[0].lstrip("@!UP0123456789 ") != r[isrc].strip().split(" ")[0].split(".")[0].lstrip("@!UP0123456789 "):
             mismatch += 1
         a = agg[loc]
-        a[0] += int(r[iinst]); a[1] += int(r[isamp])
+        a[0] += int(r[iinst]); a[1] += int(r[isamp]); a[3] += int(r[ithr])
         for i in stalls:
             if int(r[i]): a[2][hdr[i][6:]] += int(r[i])
         tot_i += int(r[iinst]); tot_s += int(r[isamp])
     print(f"# {func}: {tot_i} warp instructions, {tot_s} samples, {len(rows) - 1} SASS rows, opcode mismatches vs cubin: {mismatch}")
-    print(f"{'file:line':34s} {'inst%':>6s} {'samp%':>6s}  top stalls")
-    for loc, (ni, ns, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+    print(f"{'file:line':34s} {'inst%':>6s} {'samp%':>6s} {'lanes':>6s}  top stalls")
+    for loc, (ni, ns, st, nt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         name = f"{loc[0]}:{loc[1]}" if loc else "?"
-        print(f"{name:34s} {100 * ni / tot_i:6.2f} {100 * ns / max(tot_s, 1):6.2f}  " + " ".join(f"{k}={v}" for k, v in st.most_common(3)))
+        print(f"{name:34s} {100 * ni / tot_i:6.2f} {100 * ns / max(tot_s, 1):6.2f} {nt / max(ni, 1):6.2f}  " + " ".join(f"{k}={v}" for k, v in st.most_common(3)))
 
 
 if __name__ == "__main__":
