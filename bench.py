@@ -460,7 +460,9 @@ def main():
                     "traffic": dncu.get("dram_bytes_per_launch"),
                     "issue_active_pct": dncu.get("issue_active_pct"), "warps_active_pct": dncu.get("warps_active_pct"),
                     "simt_efficiency": dncu.get("simt_efficiency"),
-                    "dram_bytes_per_step": step_ncu.get("dram_bytes_per_step"), "dram_bytes_per_ray": step_ncu.get("dram_bytes_per_ray"),
+                    "dram_bytes_per_step": step_ncu.get("dram_bytes_per_step"),
+                    "dram_bytes_per_ray": (step_ncu["dram_bytes_per_step"] / (rays / max(1, world) / args.steps)) if step_ncu.get("dram_bytes_per_step") and rays else None,
+                    "kernel_ms_per_step_serialised": step_ncu.get("kernel_ms_per_step_serialised"),
                     "algorithmic_bytes_per_unit": dom_bytes / max(1, units), "units_per_step": units, "launches_per_step": stages[dom]["launches"],
                     "avg_launch_ms": stages[dom]["ms"] / max(1, stages[dom]["launches"]),
                     "stage_share": {k: (v["ms"] / total_ms if total_ms else 0) for k, v in stages.items()}, "per_stage": per_stage,

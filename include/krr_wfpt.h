@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define KRR_WFPT_ABI_VERSION 5
+#define KRR_WFPT_ABI_VERSION 6
 
 enum {
 	KRR_OK			  = 0,
@@ -157,6 +157,9 @@ typedef struct KrrMediumDesc {
 	int32_t		 res[3];
 	const float *density;		 /* res[0]*res[1]*res[2], x fastest */
 	float		 scale;			 /* density scale */
+	/* optional (NULL = none): RGB single-scattering albedo per voxel, 3 floats per voxel, same resolution, bounds and
+	 * trilinear lookup as `density` (NanoVDBMedium::albedoGrid, media.h:168-170: when present it replaces `albedo`) */
+	const float *albedo_grid;
 } KrrMediumDesc;
 
 /* OptixSceneParameters, reference src/core/device/scene.h:34-47 */

@@ -66,7 +66,8 @@ class KrrLightDesc(C.Structure):
 
 class KrrMediumDesc(C.Structure):
     _fields_ = [("type", I32), ("sigma_t", F * 3), ("albedo", F * 3), ("Le", F * 3), ("g", F), ("transform", F * 12),
-                ("bounds_min", F * 3), ("bounds_max", F * 3), ("res", I32 * 3), ("density", C.POINTER(F)), ("scale", F)]
+                ("bounds_min", F * 3), ("bounds_max", F * 3), ("res", I32 * 3), ("density", C.POINTER(F)), ("scale", F),
+                ("albedo_grid", C.POINTER(F))]
 
 
 class KrrSceneOptions(C.Structure):

@@ -188,6 +188,8 @@ struct KrrWfpt : WaveState {
 	// -18 %): the lanes of a trace warp diverge by traversal PHASE (node / triangle / instance entry), not by where
 	// their rays are.  Takes effect at the next resize / set_scene / set_partition.
 	int sortRays = -1, sortKey = 0;
+	// "l2_persist_mb" (experiment): megabytes of the BVH node pool (from its start) kept as persisting L2 lines during render()
+	int l2PersistMb = 0;
 	int refill = 0;		 // "refill": idle lanes of a trace warp that trigger finalisation + refill; 0 = automatic (kRefill / kRefillFlat)
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
 	int bandRows(int b, int nb) const { return (rowEnd - rowBegin - b + nb - 1) / nb; }
@@ -247,6 +249,7 @@ int parseParams(KrrWfpt *h, const char *text) {
 		h->refill		= j.value("refill", h->refill);
 		h->sortRays		= j.value("sort_rays", h->sortRays);
 		h->sortKey		= j.value("sort_key", h->sortKey);
+		h->l2PersistMb	= j.value("l2_persist_mb", h->l2PersistMb);
 	} catch (const std::exception &e) { return fail(KRR_E_INVALID, "bad params JSON: %s", e.what()); }
 	if (h->maxDepth < 0 || h->maxDepth > kMaxDepthSlots - 2) return fail(KRR_E_INVALID, "max_depth must be in [0, %d]", kMaxDepthSlots - 2);
 	if (h->spp < 1) return fail(KRR_E_INVALID, "spp must be >= 1");
@@ -605,11 +608,16 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 		r.inv = xfInverse(r.xf);
 		memcpy(r.boundsMin, m.bounds_min, 12), memcpy(r.boundsMax, m.bounds_max, 12), memcpy(r.res, m.res, 12);
 		r.scale = m.scale;
-		r.densityOff = r.majorantOff = -1;
+		r.densityOff = r.majorantOff = r.albedoOff = -1;
 		if (m.type == KRR_MEDIUM_GRID) {
 			if (!m.density || m.res[0] <= 0 || m.res[1] <= 0 || m.res[2] <= 0) return fail(KRR_E_INVALID, "medium %d: grid medium without density data", i);
+			const size_t voxels = (size_t) m.res[0] * m.res[1] * m.res[2];
 			r.densityOff = (int32_t) density.size();
-			density.insert(density.end(), m.density, m.density + (size_t) m.res[0] * m.res[1] * m.res[2]);
+			density.insert(density.end(), m.density, m.density + voxels);
+			if (m.albedo_grid) { // RGB albedo per voxel on the density lattice (NanoVDBMedium::albedoGrid)
+				r.albedoOff = (int32_t) density.size();
+				density.insert(density.end(), m.albedo_grid, m.albedo_grid + 3 * voxels);
+			}
 		}
 		media[i] = r;
 	}
@@ -693,6 +701,10 @@ extern "C" int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *d) {
 		}
 		bool emissiveTex = m.material >= 0 && d->materials[m.material].textures[KRR_TEX_EMISSIVE].valid;
 		bool emissive	 = emissiveTex || m.Le[0] != 0 || m.Le[1] != 0 || m.Le[2] != 0;
+		if (emissiveTex && d->materials[m.material].textures[KRR_TEX_EMISSIVE].image)
+			// DiffuseAreaLight::L looks the emissive texture up at the hit's uv (light.h:186); this pass evaluates a constant
+			// per emissive triangle, so an IMAGE-backed emissive texture would render with the wrong radiance: refuse it
+			return fail(KRR_E_INVALID, "instance %d: image-backed emissive textures are not supported (constant emissive colours are)", i);
 		if (emissive) {
 			flags[i] |= 4;
 			r.lightBase = (int32_t) lights.size();
@@ -921,14 +933,26 @@ extern "C" int krr_wfpt_begin_frame(KrrWfpt *h, uint64_t frameIndex, const KrrCa
 
 namespace {
 // launch with the programmatic-stream-serialization attribute (see KRR_PDL_ENTRY in wavefront_kernels.cuh)
+// "l2_persist_mb": L2 access-policy window of the launches of the current render (the first bytes of the BVH node pool = the
+// TLAS and the top levels of the BLASes, emitted breadth first): hits are kept as persisting lines, everything else streams
+thread_local cudaAccessPolicyWindow gL2Window = {};
 template <typename... KArgs, typename... Args>
 void launchK(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args &&...args) {
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned) grid), cfg.blockDim = dim3((unsigned) block), cfg.dynamicSmemBytes = 0, cfg.stream = st;
-	cudaLaunchAttribute at[1];
-	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	at[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+	cudaLaunchAttribute at[2];
+	int n = 0;
+	if (pdl) {
+		at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[n].val.programmaticStreamSerializationAllowed = 1;
+		n++;
+	}
+	if (gL2Window.num_bytes) {
+		at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+		at[n].val.accessPolicyWindow = gL2Window;
+		n++;
+	}
+	cfg.attrs = at, cfg.numAttrs = n;
 	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 struct StageTimer { // RAII: brackets one launch with events when profiling is on
@@ -976,6 +1000,15 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	const int gridShadowTr = media ? gridFor(h, k_trace_shadow_tr<kTraceMotion>, kTraceBlock) : 0;
 	const int gridTraceF = flatScene ? gridFor(h, k_trace_closest<kTraceFlat>, 128) : 0, gridFusedF = flatScene ? gridFor(h, k_trace_fused<kTraceFlat>, 128) : 0;
 	const int gridSort = gridFor(h, k_sort_rays, kSortThreads);
+	gL2Window = {};
+	if (h->l2PersistMb > 0 && !flatScene) {
+		const BvhDev bd = h->bvh.device();
+		const size_t want = std::min((size_t) h->l2PersistMb << 20, (size_t) h->bvh.nodeCount() * sizeof(Node8));
+		static thread_local int limitSetFor = -1; // device whose persisting-L2 carve-out has been sized
+		if (limitSetFor != h->device) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) h->l2PersistMb << 20); limitSetFor = h->device; }
+		gL2Window.base_ptr = (void *) bd.nodes, gL2Window.num_bytes = want, gL2Window.hitRatio = 1.f;
+		gL2Window.hitProp = cudaAccessPropertyPersisting, gL2Window.missProp = cudaAccessPropertyStreaming;
+	}
 	const int gridShadowTrF = flatScene && media ? gridFor(h, k_trace_shadow_tr<kTraceFlat>, kTraceBlock) : 0;
 	if (h->capSample >= 0 && h->capCounts.alloc(8)) return KRR_E_CUDA;
 	const bool pdl = h->usePdl();
@@ -1125,6 +1158,7 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 		}
 	}
 	st = callerStream;
+	gL2Window = {};
 	CUDA_OK(cudaGetLastError());
 	h->lastStream = st;
 	return KRR_OK;

@@ -103,9 +103,65 @@ KRR_DEV float sigmaMax(const Xf &m) {
 // object, the sphere box does not grow under rotation; compact, roundish meshes get boxes ~1.5x smaller per axis.
 // The world sphere itself is kept for a ray / sphere test before an instance is entered (bvh.cuh).
 // A MOVING instance (SRT motion chain, motion.cuh) is bounded over the time window [w0, w1] the rays of the frame
-// can carry (the camera's shutter interval): corners and sphere are evaluated at kMotionSamples + 1 times, all
-// positions are united, and the box is padded by the largest second difference of a trajectory -- 8x the
-// deviation of a smooth curve from the chords between consecutive samples.
+// can carry (the camera's shutter interval): corners and sphere centre are evaluated at kMotionSamples + 1 times, all
+// positions are united, and the box is padded by a PROVEN bound of how far a point can be from its nearest sample:
+// V h / 2, h = the sample spacing, V = an upper bound of the point's speed from the keys (chainMotionBound below).
+// (Round 1 padded by the largest second difference of the sampled trajectory: a heuristic that a fast rotation
+// between two samples escapes.)
+// Speed bound, level by level from the instance's own node to the root.  A level maps v to R(q(f)) (s(f) o v) + T(f)
+// with s, T linear in the key parameter f and q = the normalised linear blend of two key quaternions; f is piecewise
+// linear in time with slope (n - 1) / (t1 - t0).  With |v| <= B and |dv/dt| <= V below the level:
+//   |d/dt (level v)| <= f' (omega sigma B + ds B + dT) + sigma V,      |level v| <= sigma B + Tmax
+// sigma = largest |scale component| over the keys, ds = largest |difference of a scale component| and dT = largest
+// |difference of the translations| over the key segments, omega = 2 |qb - qa| / min_f |qa + f (qb - qa)| = the
+// largest angular speed per unit f (the derivative of a normalised vector is at most |q'| / |q|, and a rotation
+// turns by twice the angle its quaternion moves).  A static node contributes its largest singular value and its
+// translation.  Everything is evaluated over ALL key segments of a node (a superset of those the window meets).
+struct MotionBound { float speed, scaleMax, scaleMin; };
+KRR_DEV MotionBound chainMotionBound(const XformNodeRec *__restrict__ nodes, const float *__restrict__ keyPool, int node, float pointNorm) {
+	double B = pointNorm, V = 0.0, sMax = 1.0, sMin = 1.0;
+	for (int p = node; p >= 0; p = nodes[p].parent) {
+		const XformNodeRec &nd = nodes[p];
+		if (nd.nKeys >= 2) {
+			const float *keys = keyPool + 10 * (size_t) nd.keyOff;
+			double sigma = 0.0, sigmaLo = 3.0e38, tMax = 0.0, A = 0.0, C = 0.0;
+			for (int k = 0; k < nd.nKeys; k++) {
+				const float *a = keys + 10 * k;
+				for (int c = 0; c < 3; c++) sigma = fmax(sigma, fabs((double) a[c])), sigmaLo = fmin(sigmaLo, fabs((double) a[c]));
+				tMax = fmax(tMax, sqrt((double) a[7] * a[7] + (double) a[8] * a[8] + (double) a[9] * a[9]));
+			}
+			for (int k = 0; k + 1 < nd.nKeys; k++) {
+				const float *a = keys + 10 * k, *b = a + 10;
+				double ds = 0.0, dT = 0.0, dd = 0.0, aa = 0.0, ad = 0.0, bb = 0.0;
+				for (int c = 0; c < 3; c++) ds = fmax(ds, fabs((double) b[c] - a[c])), dT += ((double) b[7 + c] - a[7 + c]) * ((double) b[7 + c] - a[7 + c]);
+				for (int c = 3; c < 7; c++) {
+					const double d = (double) b[c] - a[c];
+					dd += d * d, aa += (double) a[c] * a[c], ad += (double) a[c] * d, bb += (double) b[c] * b[c];
+				}
+				// min over f in [0, 1] of |a + f d|^2
+				double q2 = fmin(aa, bb);
+				if (dd > 0.0) {
+					const double f = -ad / dd;
+					if (f > 0.0 && f < 1.0) q2 = fmin(q2, fmax(aa - ad * ad / dd, 0.0));
+				}
+				const double omega = dd > 0.0 ? 2.0 * sqrt(dd) / fmax(sqrt(q2), 1e-30) : 0.0;
+				A = fmax(A, omega * sigma + ds), C = fmax(C, sqrt(dT));
+			}
+			const double fp = (double) (nd.nKeys - 1) / fmax((double) nd.t1 - (double) nd.t0, 1e-30);
+			V = fp * (A * B + C) + sigma * V;
+			B = sigma * B + tMax;
+			sMax *= sigma, sMin *= sigmaLo;
+		} else {
+			const double sg = sigmaMax(nd.local), sgInv = sigmaMax(nd.localInv);
+			V = sg * V;
+			B = sg * B + sqrt((double) nd.local.m[3] * nd.local.m[3] + (double) nd.local.m[7] * nd.local.m[7] + (double) nd.local.m[11] * nd.local.m[11]);
+			sMax *= sg, sMin *= sgInv > 0.0 ? 1.0 / sgInv : 0.0;
+		}
+	}
+	MotionBound r;
+	r.speed = (float) fmin(V * 1.0001, 3.0e38), r.scaleMax = (float) fmin(sMax * 1.0001, 3.0e38), r.scaleMin = (float) (sMin * 0.9999);
+	return r;
+}
 constexpr int kMotionSamples = 8;
 __global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb *__restrict__ meshBoxes, const float4 *__restrict__ meshSpheres,
 									const int32_t *__restrict__ ids, int n, Aabb *boxesByInst, Aabb *boxesCompact, float4 *spheresByInst, float *cb,
@@ -133,29 +189,22 @@ __global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb
 	float pad = 0.f, cpad = 0.f, rmin = 3.0e38f;
 	if (inst[i].motion >= 0 && xnodes) {
 		const int steps = w1 > w0 ? kMotionSamples : 0;
-		V3 prev[9], prev2[9];
+		float cornerNorm = 0.f;
+		for (int c = 0; c < 8; c++) cornerNorm = fmaxf(cornerNorm, length(corner(c)));
+		const float half = steps ? 0.5f * (w1 - w0) / (float) steps * 1.0001f : 0.f; // farthest a time of the window is from a sample
+		const MotionBound mbCorner = chainMotionBound(xnodes, keyPool, inst[i].motion, cornerNorm);
+		pad = mbCorner.speed * half;
+		if (useSphere) cpad = chainMotionBound(xnodes, keyPool, inst[i].motion, length(oc)).speed * half;
 		for (int j = 0; j <= steps; j++) {
 			float t = steps ? w0 + (w1 - w0) * ((float) j / (float) steps) : w0;
 			if (j == steps) t = w1;
 			Xf m, inv;
 			chainXf(xnodes, keyPool, inst[i].motion, t, m, inv);
-			for (int c = 0; c < 9; c++) {
-				V3 w = xfPoint(m, c < 8 ? corner(c) : oc);
-				if (c < 8) grow(w);
-				else if (useSphere) {
-					const float r = sigmaMax(m) * ms.w;
-					growSphere(w, r);
-					rmin = fminf(rmin, r);
-				}
-				if (j >= 2) {
-					V3 dd = prev2[c] - 2.f * prev[c] + w;
-					const float e = fmaxf(fabsf(dd.x), fmaxf(fabsf(dd.y), fabsf(dd.z)));
-					if (c < 8) pad = fmaxf(pad, e);
-					else cpad = e > cpad ? e : cpad;
-				}
-				prev2[c] = prev[c], prev[c] = w;
-			}
+			for (int c = 0; c < 8; c++) grow(xfPoint(m, corner(c)));
+			// the sphere's radius over the WHOLE window from the key scales (its largest / smallest value, not a sampled one)
+			if (useSphere) growSphere(xfPoint(m, oc), mbCorner.scaleMax * ms.w);
 		}
+		if (useSphere) rmin = mbCorner.scaleMin * ms.w;
 	} else {
 		for (int c = 0; c < 8; c++) grow(xfPoint(inst[i].xf, corner(c)));
 		if (useSphere) {
@@ -858,6 +907,12 @@ bool BvhBuilder::build(const float *dPositions, const int32_t *dIndices, const M
 	int maxTris = 1, nBlas = haveMerged ? 1 : 0;
 	for (int i = 0; i < nMeshes; i++)
 		if (meshNeedsBlas[i]) totalTris += hMeshes[i].nTri, maxTris = std::max(maxTris, hMeshes[i].nTri), nBlas++;
+	// triangle and node indices are 32-bit (Node8::primBase / childBase, int cursors): refuse pools that do not fit
+	// instead of wrapping (2^31 triangles = 96 GB of leaf triangles: within reach of a 180 GB device)
+	if (totalTris + (size_t) nInstances + 16 > 0x7fffffffull) {
+		snprintf(err, 256, "bvh build: %zu pooled triangles exceed the 31-bit triangle / node index range", totalTris);
+		return false;
+	}
 	const int tlasReserve = nInstances + 2;
 	const size_t nodeCap  = totalTris + (size_t) nBlas + (size_t) tlasReserve + 8;
 	if (!b.nodes.alloc(nodeCap) || !b.nodeBounds.alloc(nodeCap) || !b.tris.alloc(totalTris) || !b.tlasInst.alloc(8 * (size_t) (nInstances + 2) + 8) ||

@@ -14,10 +14,9 @@ constexpr int kMajRes = 64; // majorantGridRes, media.h:223
 
 struct MediumPoint { Spec sigma_a, sigma_s, Le; };
 
-// NanoVDBGrid<float>::getValue (util/volume.h:83-87): worldToIndexF + trilinear SampleFromVoxels,
-// background 0 outside the grid
-KRR_DEV float gridDensity(const MediumRec &m, const float *__restrict__ pool, V3 p) {
-	const float *den = pool + m.densityOff;
+// NanoVDBGrid<T>::getValue (util/volume.h:83-87): worldToIndexF + trilinear SampleFromVoxels, background 0 outside the
+// grid.  NC = floats per voxel (1: density, 3: RGB albedo grid), `comp` the component
+template <int NC> KRR_DEV float gridValue(const MediumRec &m, const float *__restrict__ grid, V3 p, int comp) {
 	float ix = (p.x - m.boundsMin[0]) / (m.boundsMax[0] - m.boundsMin[0]) * m.res[0];
 	float iy = (p.y - m.boundsMin[1]) / (m.boundsMax[1] - m.boundsMin[1]) * m.res[1];
 	float iz = (p.z - m.boundsMin[2]) / (m.boundsMax[2] - m.boundsMin[2]) * m.res[2];
@@ -26,13 +25,14 @@ KRR_DEV float gridDensity(const MediumRec &m, const float *__restrict__ pool, V3
 	float wx = ix - fx, wy = iy - fy, wz = iz - fz;
 	auto at = [&](int x, int y, int z) -> float {
 		if (x < 0 || y < 0 || z < 0 || x >= m.res[0] || y >= m.res[1] || z >= m.res[2]) return 0.f;
-		return __ldg(den + x + (size_t) m.res[0] * (y + (size_t) m.res[1] * z));
+		return __ldg(grid + NC * (x + (size_t) m.res[0] * (y + (size_t) m.res[1] * z)) + comp);
 	};
 	auto mix = [](float a, float b, float t) { return a + t * (b - a); };
 	float c00 = mix(at(x0, y0, z0), at(x0 + 1, y0, z0), wx), c10 = mix(at(x0, y0 + 1, z0), at(x0 + 1, y0 + 1, z0), wx);
 	float c01 = mix(at(x0, y0, z0 + 1), at(x0 + 1, y0, z0 + 1), wx), c11 = mix(at(x0, y0 + 1, z0 + 1), at(x0 + 1, y0 + 1, z0 + 1), wx);
 	return mix(mix(c00, c10, wy), mix(c01, c11, wy), wz);
 }
+KRR_DEV float gridDensity(const MediumRec &m, const float *__restrict__ pool, V3 p) { return gridValue<1>(m, pool + m.densityOff, p, 0); }
 
 // Medium::samplePoint (media.h:121-126, 161-173).  Constant colours were converted to sigmoid
 // coefficients at upload (MediumRec::*Spec), as for materials.
@@ -47,7 +47,12 @@ KRR_DEV MediumPoint mediumSamplePoint(const MediumRec &m, const SceneDev &sc, V3
 	}
 	V3 pm = xfPoint(m.inv, p);
 	sigma_t = sigma_t * (gridDensity(m, sc.densityPool, pm) * m.scale);
-	Spec sigma_s = sigma_t * sampleBounded(m.albedoBSpec, wl); // grid medium: albedo is RGBBounded
+	Spec sigma_s;
+	if (m.albedoOff >= 0) { // albedoGrid.getValue(p) -> Spectrum::fromRGB(..., RGBBounded): a table lookup per sample (media.h:168-170)
+		const float *ag = sc.densityPool + m.albedoOff;
+		const RgbSpectrum a = makeBounded(sc.cs.zNodes, sc.cs.coeffs, gridValue<3>(m, ag, pm, 0), gridValue<3>(m, ag, pm, 1), gridValue<3>(m, ag, pm, 2));
+		sigma_s = sigma_t * sampleBounded(a, wl);
+	} else sigma_s = sigma_t * sampleBounded(m.albedoBSpec, wl); // grid medium: albedo is RGBBounded
 	mp.sigma_a = sigma_t - sigma_s, mp.sigma_s = sigma_s, mp.Le = sp(0);
 	return mp;
 }

@@ -98,6 +98,7 @@ struct MediumRec {
 	int32_t densityOff;	 // float offset into density pool
 	int32_t majorantOff; // float offset (64^3 majorant grid)
 	float scale;
+	int32_t albedoOff;	 // float offset of the RGB albedo grid (3 floats per voxel, density lattice), -1 = constant albedo
 };
 
 struct SceneDev {

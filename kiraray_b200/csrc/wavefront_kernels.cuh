@@ -1054,7 +1054,10 @@ KRR_DEV void traceShadowBody(const Wavefront &wf, int depth, TraceSmem &sm, int 
 			if (work.exhausted) break;
 			continue;
 		}
-		const bool fin = tr.trip<false>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
+#ifndef KRR_SHADOW_VOTE
+#define KRR_SHADOW_VOTE false
+#endif
+		const bool fin = tr.trip<KRR_SHADOW_VOTE>(ray >= 0 && !done, wf.bvh, wf.scene.instances, sm, ls, [&](int inst, int prim, float u, float v) {
 			uint8_t f = wf.instFlags[inst];
 			if (f & 1) return false; // __anyhit__Shadow ignores null-material surfaces
 			if (f & 2) return !alphaKilled(wf, inst, prim, u, v, tr.o, tr.d);

@@ -72,6 +72,7 @@ struct HostMedium {
 	string name;
 	KrrMediumDesc desc{};
 	std::vector<float> density;
+	std::vector<float> albedoGrid; // optional RGB albedo per voxel (KrrMediumDesc::albedo_grid)
 	float boundMin[3] = {0, 0, 0}, boundMax[3] = {0, 0, 0};
 	bool hasBound = false;
 };

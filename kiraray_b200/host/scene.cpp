@@ -206,6 +206,7 @@ const KrrSceneDesc &Scene::desc() {
 	mMediumDescs.resize(media.size());
 	for (size_t i = 0; i < media.size(); i++) {
 		if (!media[i].density.empty()) media[i].desc.density = media[i].density.data();
+		if (!media[i].albedoGrid.empty()) media[i].desc.albedo_grid = media[i].albedoGrid.data();
 		mMediumDescs[i] = media[i].desc;
 	}
 	// sceneRadius of directional/infinite lights: root bounding-box diagonal (light.cpp:20-21,32-33)
@@ -625,6 +626,21 @@ bool loadMedium(Scene &scene, const json &params, const float nodeXf[12]) {
 		memcpy(m.desc.res, res, 12);
 		memcpy(m.desc.transform, nodeXf, 48);
 		proceduralDensity(m.density, res, (uint64_t) params.value("seed", 7272));
+		if (params.contains("albedo_gradient")) {
+			// RGB albedo grid (NanoVDBMedium::albedoGrid; the reference reads it from the .vdb file): a linear blend of two
+			// colours along x, {"albedo_gradient": [[r,g,b],[r,g,b]]}, on the density lattice
+			const json &g = params.at("albedo_gradient");
+			float a[3], b[3];
+			for (int k = 0; k < 3; k++) a[k] = (float) g.at(0).at(k).asNumber(), b[k] = (float) g.at(1).at(k).asNumber();
+			m.albedoGrid.resize((size_t) 3 * res[0] * res[1] * res[2]);
+			for (int z = 0; z < res[2]; z++)
+				for (int y = 0; y < res[1]; y++)
+					for (int x = 0; x < res[0]; x++) {
+						const float t = res[0] > 1 ? (float) x / (float) (res[0] - 1) : 0.f;
+						float *v = &m.albedoGrid[3 * ((size_t) x + (size_t) res[0] * ((size_t) y + (size_t) res[1] * z))];
+						for (int k = 0; k < 3; k++) v[k] = a[k] + t * (b[k] - a[k]);
+					}
+		}
 		m.hasBound = true;
 		for (int k = 0; k < 3; k++) m.boundMin[k] = lo[k] + nodeXf[k * 4 + 3], m.boundMax[k] = hi[k] + nodeXf[k * 4 + 3];
 		int id = (int) scene.media.size();

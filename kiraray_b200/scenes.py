@@ -113,7 +113,7 @@ class SceneBuilder:
         return len(self.lights) - 1
 
     def add_medium(self, type_=0, sigma_t=(1, 1, 1), albedo=(0.8, 0.8, 0.8), Le=(0, 0, 0), g=0.0, transform=IDENTITY,
-                   bounds=((0, 0, 0), (1, 1, 1)), density=None, scale=1.0):
+                   bounds=((0, 0, 0), (1, 1, 1)), density=None, scale=1.0, albedo_grid=None):
         m = KrrMediumDesc()
         m.type, m.g, m.scale = type_, g, scale
         m.sigma_t, m.albedo, m.Le = (F * 3)(*sigma_t), (F * 3)(*albedo), (F * 3)(*Le)
@@ -124,6 +124,11 @@ class SceneBuilder:
             self._keep.append(d)
             m.res = (I32 * 3)(d.shape[2], d.shape[1], d.shape[0])
             m.density = _fp(d)
+            if albedo_grid is not None:
+                a = np.ascontiguousarray(albedo_grid, np.float32)  # indexed [z][y][x][rgb], same lattice as the density
+                assert a.shape == d.shape + (3,)
+                self._keep.append(a)
+                m.albedo_grid = _fp(a)
         self.media.append(m)
         return len(self.media) - 1
 
@@ -269,7 +274,7 @@ def mat_mul(a, b):
     return (A @ B)[:3].astype(np.float32).ravel()
 
 
-def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100, motion=True, seed=SEED, n_keys=2, time=0.0):
+def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100, motion=True, seed=SEED, n_keys=2, time=0.0, spin_scale=1.0, drift_scale=1.0):
     """BASELINE.json config 5: `n_groups * per_group` instances of `n_blas` BLASes arranged as a two-level
     graph: every GROUP node and every INSTANCE node under it carries its own `n_keys`-key SRT animation over
     [0, 1] (the reference wraps each animated node in an SRT motion transform, optix.cpp:400-563), plus a
@@ -294,7 +299,7 @@ def instanced_scene(n_blas=16, tris_per_blas=20_000, n_groups=100, per_group=100
     def animated_keys(scale, center, spin, drift):
         q0 = rng.normal(size=4)
         q0 /= np.linalg.norm(q0)
-        dq, vel = rng.normal(size=4) * spin, rng.normal(size=3) * drift
+        dq, vel = rng.normal(size=4) * spin * spin_scale, rng.normal(size=3) * drift * drift_scale
         ks = []
         for k in range(n_keys):
             a = k / max(n_keys - 1, 1)

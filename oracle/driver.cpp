@@ -257,6 +257,7 @@ struct MediumData {
 	float bmin[3], bmax[3];
 	int res[3];
 	std::vector<float> density;
+	std::vector<float> albedoGrid; /* optional: 3 floats per voxel on the density lattice (NanoVDBMedium::albedoGrid) */
 	float scale;
 	std::vector<float> majorant; /* 64^3 max-density grid, media.cpp:18-75 */
 };
@@ -726,7 +727,7 @@ constexpr int kMajRes = 64; /* majorantGridRes, media.h:223 */
 
 /* NanoVDBGrid<float>::getValue (util/volume.h:83-87): worldToIndexF + SampleFromVoxels<Tree, 1, false>
  * = trilinear interpolation of the voxel lattice, background value 0 outside the grid */
-float gridDensity(const MediumData &m, V3 p) {
+float gridValue(const MediumData &m, const std::vector<float> &grid, int nc, int comp, V3 p) {
 	float idx[3], w[3];
 	int i0[3];
 	for (int k = 0; k < 3; k++) {
@@ -736,7 +737,7 @@ float gridDensity(const MediumData &m, V3 p) {
 	}
 	auto at = [&](int x, int y, int z) -> float {
 		if (x < 0 || y < 0 || z < 0 || x >= m.res[0] || y >= m.res[1] || z >= m.res[2]) return 0.f;
-		return m.density[x + (size_t) m.res[0] * (y + (size_t) m.res[1] * z)];
+		return grid[nc * (x + (size_t) m.res[0] * (y + (size_t) m.res[1] * z)) + comp];
 	};
 	auto lerp = [](float a, float b, float t) { return a + t * (b - a); }; /* nanovdb TrilinearSampler */
 	float c00 = lerp(at(i0[0], i0[1], i0[2]), at(i0[0] + 1, i0[1], i0[2]), w[0]);
@@ -745,6 +746,7 @@ float gridDensity(const MediumData &m, V3 p) {
 	float c11 = lerp(at(i0[0], i0[1] + 1, i0[2] + 1), at(i0[0] + 1, i0[1] + 1, i0[2] + 1), w[0]);
 	return lerp(lerp(c00, c10, w[1]), lerp(c01, c11, w[1]), w[2]);
 }
+float gridDensity(const MediumData &m, V3 p) { return gridValue(m, m.density, 1, 0, p); }
 
 /* initializeMajorantGrid, media.cpp:18-75 (index bbox of a dense grid = [0, res-1]) */
 void buildMajorant(MediumData &m) {
@@ -783,7 +785,11 @@ MediumPoint mediumSamplePoint(const MediumData &m, V3 p, const float lambda[4]) 
 	}
 	V3 pm = xfPoint(m.inv, p);
 	Spec sigma_t = fromRGB(m.sigma_t, 1, lambda) * (gridDensity(m, pm) * m.scale); /* density * scale * fromRGB(sigma_t) */
-	Spec sigma_s = sigma_t * fromRGB(m.albedo, 0, lambda);								/* albedo: RGBBounded */
+	/* albedoGrid ? RGB(albedoGrid.getValue(p)) : albedo, as RGBBounded (media.h:168-170) */
+	float albedo[3] = {m.albedo[0], m.albedo[1], m.albedo[2]};
+	if (!m.albedoGrid.empty())
+		for (int c = 0; c < 3; c++) albedo[c] = gridValue(m, m.albedoGrid, 3, c, pm);
+	Spec sigma_s = sigma_t * fromRGB(albedo, 0, lambda);
 	for (int i = 0; i < 4; i++) mp.sigma_a.v[i] = sigma_t.v[i] - sigma_s.v[i];
 	mp.sigma_s = sigma_s, mp.Le = sconst(0); /* no temperature grid */
 	return mp;
@@ -1025,6 +1031,7 @@ extern "C" OrcScene *orc_scene_create(const KrrSceneDesc *d) {
 		memcpy(m.bmin, md.bounds_min, 12), memcpy(m.bmax, md.bounds_max, 12), memcpy(m.res, md.res, 12);
 		if (md.type == KRR_MEDIUM_GRID) {
 			m.density.assign(md.density, md.density + (size_t) md.res[0] * md.res[1] * md.res[2]);
+			if (md.albedo_grid) m.albedoGrid.assign(md.albedo_grid, md.albedo_grid + 3 * (size_t) md.res[0] * md.res[1] * md.res[2]);
 			buildMajorant(m);
 		}
 		s->media.push_back(std::move(m));

@@ -25,7 +25,7 @@ def test_wfpt_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"libkrr_wfpt.so does not export {n}"
-    assert lib.krr_wfpt_abi_version() == 5
+    assert lib.krr_wfpt_abi_version() == 6
 
 
 def test_host_library_exports_every_declared_symbol():

@@ -77,6 +77,21 @@ def test_heterogeneous_smoke_grid():
     check("cbox_smoke.json", 8, block_tol=0.015)  # measured 0.0054
 
 
+def test_smoke_with_an_albedo_grid():
+    """NanoVDBMedium::albedoGrid (media.h:168-170): the single-scattering albedo is looked up per sample in an RGB grid on
+    the density lattice (here a red-to-blue blend along x) and converted with the RGB->spectrum table at run time."""
+    check("cbox_smoke_albedo.json", 8, block_tol=0.02)
+    # and the grid is really used: against the constant-albedo render, the red / blue balance of the volume tilts from one
+    # side of the image to the other (the gradient runs along the medium's x axis)
+    _, film, _ = run("cbox_smoke_albedo.json", 96, 96, 64, 8)
+    _, const, _ = run("cbox_smoke.json", 96, 96, 64, 8)
+    rows, left, right = slice(20, 76), slice(22, 46), slice(50, 74)
+    rb = lambda img, cols: float(img[rows, cols, 0].mean() / img[rows, cols, 2].mean())
+    tilt = (rb(film, left) / rb(film, right)) / (rb(const, left) / rb(const, right))
+    print(f"albedo grid: red/blue left {rb(film, left):.3f} right {rb(film, right):.3f}; constant albedo {rb(const, left):.3f} / {rb(const, right):.3f}; tilt {tilt:.3f}")
+    assert abs(np.log(tilt)) > 0.05, tilt
+
+
 def test_media_can_be_disabled():
     """enable_medium=false renders the surfaces only (integrator.cpp:200): null-material interfaces pass rays through."""
     app = krr.HostApp(os.path.join(ROOT, "assets", "configs", "cbox_mist.json"), asset_root=ROOT)

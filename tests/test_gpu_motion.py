@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 KIND = "reference"
 
 
-def small_scene(**kw):
+def small_scene(**kw):  # (n_keys, spin_scale, drift_scale: see scenes.instanced_scene)
     return scenes.instanced_scene(n_blas=3, tris_per_blas=300, n_groups=4, per_group=6, motion=True, **kw)
 
 
@@ -73,6 +73,32 @@ def test_motion_blur_first_hits_counts_and_radiance(shutter):
     assert abs(st["shadow_rays"] - rs["shadow_rays"]) <= 0.02 * rs["shadow_rays"]
     assert np.isfinite(film).all()
     assert relmse(film, ref["film"]) <= 0.1
+
+
+@pytest.mark.parametrize("n_keys,spin,drift,shutter", [(2, 30.0, 6.0, (0.0, 1.0)), (5, 30.0, 4.0, (0.1, 0.8)), (3, 12.0, 10.0, (0.45, 0.3))])
+def test_fast_rotations_stay_inside_the_motion_boxes(n_keys, spin, drift, shutter):
+    """The TLAS boxes of moving instances are padded by a proven bound (bvh_build.cu chainMotionBound: speed bound from the
+    keys x half the sample spacing), not by a curvature estimate.  Keys that turn an instance by up to half a revolution
+    per segment and move it by several of its diameters inside ONE shutter interval: every ray the oracle's exhaustive
+    loop over the moving instances (no bounds at all) finds must be found through the boxes, id for id."""
+    b, info = small_scene(n_keys=n_keys, spin_scale=spin, drift_scale=drift)
+    desc = b.build()
+    w = h = 72
+    cam = camera(*shutter)
+    gpu = krr.Wfpt(params=dict(spp=2, max_depth=2))
+    gpu.set_scene(desc)
+    gpu.resize(w, h)
+    gpu.begin_frame(3, cam)
+    gpu.render_to_host()
+    orc = ob.Oracle(desc, KIND)
+    ref = orc.render(cam, w, h, frame_index=3, spp=2, max_depth=2, use_bvh=True)
+    orc.close()
+    inst, prim = gpu.first_hits()
+    assert np.array_equal(inst, ref["first_hits"][:, 0]) and np.array_equal(prim, ref["first_hits"][:, 1])
+    assert (inst < info["n_moving"]).sum() > 0.03 * w * h
+    st, rs = gpu.stats(), ref["stats"]
+    assert abs(st["closest_by_depth"][1] - rs["closest_by_depth"][1]) <= max(8, 0.02 * rs["closest_by_depth"][1])
+    assert abs(st["shadow_rays"] - rs["shadow_rays"]) <= max(8, 0.02 * rs["shadow_rays"])
 
 
 def test_shutter_window_change_refits_the_tlas():

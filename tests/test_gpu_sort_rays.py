@@ -31,7 +31,7 @@ def test_sorted_trace_gives_the_identical_film(motion):
     ref, rays = render(desc, cam, 150, 110, sort_rays=0, **base)   # 2 x 16 500 rays: several sort tiles, a ragged last one
     assert np.isfinite(ref).all() and ref[..., :3].mean() > 0
     for extra in (dict(sort_rays=3), dict(sort_rays=1), dict(sort_rays=2), dict(sort_rays=3, sort_key=1), dict(sort_rays=-1),
-                  dict(sort_rays=3, bands=2), dict(sort_rays=3, tail_depth=3), dict(sort_rays=7), dict(sort_rays=5)):
+                  dict(sort_rays=3, bands=2), dict(sort_rays=3, tail_depth=3), dict(sort_rays=7), dict(sort_rays=5), dict(sort_rays=0, l2_persist_mb=4)):
         film, r = render(desc, cam, 150, 110, **base, **extra)
         assert r == rays, extra
         assert np.array_equal(film.view(np.uint32), ref.view(np.uint32)), extra

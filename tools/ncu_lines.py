@@ -39,7 +39,8 @@ def main():
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "kiraray_b200/lib/obj/api.o")], cwd="/tmp/cub", capture_output=True)
         cubin = "/tmp/cub/api.sm_100a.cubin"
     lm = line_map(cubin, func)
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    # an .ncu-rep, or its `--page source --csv --print-source sass` export
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     # one section per captured launch ("Kernel Name" line, header, SASS rows): take the first launch of the wanted kernel
     want = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3].startswith("launch=") else None
     secs, cur = [], None
