@@ -253,7 +253,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=0, help="rows of the frame the CPU reference renders per step")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames the cpu_baseline leg renders")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--min-seconds", type=float, default=5.0, help="length of the sustained (steady-state clocks) measurement that follows the K timed steps; 0 = skip")
+    ap.add_argument("--min-seconds", type=float, default=None, help="length of the sustained (steady-state clocks) measurement that follows the K timed steps; 0 = skip; default 5 s on one GPU, skipped on N > 1")
     ap.add_argument("--params", default="", help="extra pass parameters as JSON (tuning switches, e.g. '{\"pdl\": false}')")
     ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
     ap.add_argument("--strong", action="store_true", help="fixed TOTAL work: the spp of a step are divided among the ranks' spp slices (scaling = strong)")
@@ -262,6 +262,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.min_seconds is None:
+        args.min_seconds = 5.0 if world == 1 else 0.0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -388,7 +390,15 @@ def main():
     # ---- sustained: the same K frames over and over for >= --min-seconds, clocks sampled over the whole run ----
     sustained = None
     if args.min_seconds > 0:
-        n_sus = max(args.steps, int(args.min_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+        # EVERY rank must run the same number of steps (each step ends in a collective): size the leg from the slowest
+        # rank's time, not from the local one (tiles of a hybrid split cost different amounts; even equal work differs by
+        # a fraction of a per cent, enough to round to another step count on one rank and hang the film reduce)
+        ms_all = ms
+        if dist is not None:
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms_all = float(tm[0])
+        n_sus = max(args.steps, int(args.min_seconds * 1e3 / max(ms_all / args.steps, 1e-3)) + 1)
         n_sus = (n_sus + args.steps - 1) // args.steps * args.steps  # whole cycles of the K counted frames
         sus_sampler = ClockSampler(local)
         sus_sampler.start()

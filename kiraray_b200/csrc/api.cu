@@ -188,7 +188,9 @@ struct KrrWfpt : WaveState {
 	// -18 %): the lanes of a trace warp diverge by traversal PHASE (node / triangle / instance entry), not by where
 	// their rays are.  Takes effect at the next resize / set_scene / set_partition.
 	int sortRays = -1, sortKey = 0;
-	// "l2_persist_mb" (experiment): megabytes of the BVH node pool (from its start) kept as persisting L2 lines during render()
+	// "l2_persist_mb" (experiment, off): megabytes of the BVH node pool (from its start: TLAS + top BLAS levels) kept as persisting
+	// L2 lines during render() (cudaLaunchAttributeAccessPolicyWindow).  Measured: 20 M triangles 32 MB 1 215 vs 1 222 Mrays/s,
+	// 10 000 instances 8 MB 695 vs 695: the queues already stream past L2 (ld.cs / st.cs), the nodes were not being evicted
 	int l2PersistMb = 0;
 	int refill = 0;		 // "refill": idle lanes of a trace warp that trigger finalisation + refill; 0 = automatic (kRefill / kRefillFlat)
 	WaveState &band(int b) { return b == 0 ? *this : extra[b - 1]; }
@@ -1003,9 +1005,16 @@ extern "C" int krr_wfpt_render(KrrWfpt *h, float *film, void *stream) {
 	gL2Window = {};
 	if (h->l2PersistMb > 0 && !flatScene) {
 		const BvhDev bd = h->bvh.device();
-		const size_t want = std::min((size_t) h->l2PersistMb << 20, (size_t) h->bvh.nodeCount() * sizeof(Node8));
 		static thread_local int limitSetFor = -1; // device whose persisting-L2 carve-out has been sized
-		if (limitSetFor != h->device) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) h->l2PersistMb << 20); limitSetFor = h->device; }
+		static thread_local size_t maxWindow = 0, maxPersist = 0;
+		if (limitSetFor != h->device) {
+			cudaDeviceProp prop;
+			if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) maxWindow = (size_t) prop.accessPolicyMaxWindowSize, maxPersist = (size_t) prop.persistingL2CacheMaxSize;
+			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t) h->l2PersistMb << 20, maxPersist));
+			limitSetFor = h->device;
+		}
+		// (a window larger than the device's limits is an invalid launch attribute)
+		const size_t want = std::min(std::min((size_t) h->l2PersistMb << 20, (size_t) h->bvh.nodeCount() * sizeof(Node8)), std::min(maxWindow, maxPersist));
 		gL2Window.base_ptr = (void *) bd.nodes, gL2Window.num_bytes = want, gL2Window.hitRatio = 1.f;
 		gL2Window.hitProp = cudaAccessPropertyPersisting, gL2Window.missProp = cudaAccessPropertyStreaming;
 	}
