@@ -88,3 +88,23 @@ def test_inline_scene_with_node_transform():
     ta = np.array(list(a.instances[0].transform)).reshape(3, 4)
     tb = np.array(list(b.instances[0].transform)).reshape(3, 4)
     assert np.allclose(ta[:, :3], 2 * tb[:, :3]) and np.allclose(ta[:, 3], 2 * tb[:, 3] + [1, 2, 3])
+
+
+def test_grid_medium_with_an_albedo_gradient():
+    """{"type": "grid", ..., "albedo_gradient": [[r,g,b],[r,g,b]]}: the host layer hands the pass a density grid AND an RGB
+    albedo grid on the same lattice (KrrMediumDesc::albedo_grid = NanoVDBMedium::albedoGrid, media.h:168-170)."""
+    plain = krr.HostApp(os.path.join(ROOT, "assets", "configs", "cbox_smoke.json"), asset_root=ROOT)
+    app = krr.HostApp(os.path.join(ROOT, "assets", "configs", "cbox_smoke_albedo.json"), asset_root=ROOT)
+    d0, d = plain.scene_desc().contents, app.scene_desc().contents
+    assert d0.n_media == d.n_media == 1
+    assert not d0.media[0].albedo_grid, "no gradient asked for: constant albedo"
+    m = d.media[0]
+    res = tuple(m.res)
+    assert res == (96, 96, 96) and m.density and m.albedo_grid
+    n = res[0] * res[1] * res[2]
+    a = np.ctypeslib.as_array(m.albedo_grid, shape=(res[2], res[1], res[0], 3))
+    assert np.allclose(a[:, :, 0], [0.95, 0.25, 0.2]) and np.allclose(a[:, :, -1], [0.2, 0.35, 0.95])  # x = 0 / x = res - 1
+    assert np.allclose(a[5, 7, 48], np.array([0.95, 0.25, 0.2]) + 48 / 95 * (np.array([0.2, 0.35, 0.95]) - [0.95, 0.25, 0.2]), atol=1e-6)
+    den = np.ctypeslib.as_array(m.density, shape=(n,))
+    den0 = np.ctypeslib.as_array(d0.media[0].density, shape=(n,))
+    assert np.array_equal(den, den0), "the density is the same procedural grid"
