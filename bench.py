@@ -178,7 +178,10 @@ def cpu_reference_rate(wl, spp, rows, threads=0, frames=1):
     r0 = (H - rows) // 2
     rays, seconds = 0, 0.0
     for f in range(frames):
-        res = orc.render(wl.camera(f), W, H, frame_index=1 + f, spp=spp, max_depth=wl.max_depth, rr=RR, use_bvh=True, threads=threads, rows=(r0, r0 + rows))
+        # use_bvh=2: static instances through the oracle's BVH, moving instances through a per-frame BVH over their boxes for the
+        # frame's shutter interval (oracle/driver.cpp buildMovingTlas) -- what a CPU tracer would do; use_bvh=1 visits every
+        # moving instance per ray (that mode exists to verify the kernels' motion bounds, tests/test_gpu_motion.py)
+        res = orc.render(wl.camera(f), W, H, frame_index=1 + f, spp=spp, max_depth=wl.max_depth, rr=RR, use_bvh=2, threads=threads, rows=(r0, r0 + rows))
         rays += res["stats"]["closest_rays"] + res["stats"]["shadow_rays"]
         seconds += res["seconds"]
     orc.close()
@@ -222,7 +225,7 @@ def run_reference(args, rank, world):
     spp = wl.spp
     cores = os.cpu_count() or 1
     # ~1/8 of the cbox frame per step: a few seconds of CPU work; the tree scenes cost ~10x more per ray
-    rows = args.ref_rows or {"cbox": 135, "tess20m": 32, "smoke": 24, "inst10k": 1}[args.workload]  # (the oracle brute-forces all 10 000 moving instances per ray)
+    rows = args.ref_rows or {"cbox": 135, "tess20m": 32, "smoke": 24, "inst10k": 270}[args.workload]
     vals = []
     for i in range(args.warmup + args.steps):
         v, info = cpu_reference_rate(wl, spp, rows)
@@ -481,7 +484,7 @@ def main():
                     "pipeline_achieved": value * 1e6 * bytes_per_ray / 1e9 / max(1, world), "pipeline_frac": value * 1e6 * bytes_per_ray / 1e9 / max(1, world) / peak}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 4}[args.workload]  # inst10k: the oracle tests every moving instance per ray (no motion bounds)
+            rows = args.ref_rows or {"cbox": H, "tess20m": 96, "smoke": 64, "inst10k": 1080}[args.workload]
             frames = args.ref_frames or (6 if args.workload == "cbox" else 1)  # ~10-20 s of CPU work on 16 cores
             v, info = cpu_reference_rate(wl, spp, rows, frames=frames)
             cpu = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}

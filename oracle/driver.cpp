@@ -281,6 +281,11 @@ struct OrcScene {
 		else m = in.xf, inv = in.inv;
 	}
 	std::vector<int> movingInstances; /* not in the BVH: always tested */
+	/* use_bvh == 2 only: a BVH over the moving instances' boxes for the ray-time window of the current render (see
+	 * buildMovingTlas); null = every moving instance is visited.  Set for the duration of one render call. */
+	mutable std::vector<BvhNode> movingTlas;
+	mutable std::vector<int> movingTlasIds;
+	mutable bool useMovingTlas = false;
 	/* flattened world-independent primitive list for the BVH: (instance, prim) in object space */
 	struct Prim { int inst, prim; };
 	std::vector<Prim> prims;
@@ -464,11 +469,148 @@ void traceMovingInstance(const OrcScene &s, int ii, V3 o, V3 d, float tmax, floa
 	}
 }
 
+/* ---- optional TLAS over the MOVING instances (use_bvh == 2) -------------------------------------------------------
+ * The default use_bvh == 1 run visits every moving instance for every ray: that is what the kernels' motion boxes are
+ * verified against, and it is slow by design.  This mode bounds each moving instance over the render's ray-time window
+ * [w0, w1] the way the pass does (kiraray_b200/csrc/bvh_build.cu): the 8 corners of the mesh's object-space box at 9
+ * sample times, padded by V h / 2 with V the speed bound of chainMotionBound -- restated here in double -- and walks a
+ * median-split BVH over those boxes.  tests/test_oracle_motion.py checks that both modes return the same hits (so the
+ * bound is checked on the CPU too); bench.py's cpu_baseline of the 10 000-instance workload uses it. */
+double sigmaMaxHost(const Xf &m) { /* largest singular value of the 3x3 part, by power iteration on A^T A, with a margin */
+	double a[3][3];
+	for (int r = 0; r < 3; r++)
+		for (int c = 0; c < 3; c++) {
+			double v = 0;
+			for (int k = 0; k < 3; k++) v += (double) m.m[4 * k + r] * (double) m.m[4 * k + c];
+			a[r][c] = v;
+		}
+	double x[3] = {0.577, 0.577, 0.577}, lam = 0;
+	for (int it = 0; it < 64; it++) {
+		double y[3] = {0, 0, 0};
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) y[r] += a[r][c] * x[c];
+		double n = std::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+		if (n <= 0) break;
+		lam = n;
+		for (int r = 0; r < 3; r++) x[r] = y[r] / n;
+	}
+	/* power iteration converges from below; the Frobenius norm is an upper bound: take a padded iterate, capped by it */
+	double fro = std::sqrt(a[0][0] + a[1][1] + a[2][2]);
+	return std::min(fro, std::sqrt(lam) * 1.01 + 1e-12);
+}
+double chainSpeedBoundHost(const std::vector<XNode> &nodes, int node, double pointNorm) {
+	double B = pointNorm, V = 0.0;
+	for (int p = node; p >= 0; p = nodes[p].parent) {
+		const XNode &nd = nodes[p];
+		if (nd.nKeys >= 2) {
+			const float *keys = nd.keys.data();
+			double sigma = 0, tMax = 0, A = 0, C = 0;
+			for (int k = 0; k < nd.nKeys; k++) {
+				const float *a = keys + 10 * k;
+				for (int c = 0; c < 3; c++) sigma = std::max(sigma, std::fabs((double) a[c]));
+				tMax = std::max(tMax, std::sqrt((double) a[7] * a[7] + (double) a[8] * a[8] + (double) a[9] * a[9]));
+			}
+			for (int k = 0; k + 1 < nd.nKeys; k++) {
+				const float *a = keys + 10 * k, *b = a + 10;
+				double ds = 0, dT = 0, dd = 0, aa = 0, ad = 0, bb = 0;
+				for (int c = 0; c < 3; c++) ds = std::max(ds, std::fabs((double) b[c] - a[c])), dT += ((double) b[7 + c] - a[7 + c]) * ((double) b[7 + c] - a[7 + c]);
+				for (int c = 3; c < 7; c++) {
+					const double d = (double) b[c] - a[c];
+					dd += d * d, aa += (double) a[c] * a[c], ad += (double) a[c] * d, bb += (double) b[c] * b[c];
+				}
+				double q2 = std::min(aa, bb);
+				if (dd > 0) {
+					const double f = -ad / dd;
+					if (f > 0 && f < 1) q2 = std::min(q2, std::max(aa - ad * ad / dd, 0.0));
+				}
+				const double omega = dd > 0 ? 2.0 * std::sqrt(dd) / std::max(std::sqrt(q2), 1e-30) : 0.0;
+				A = std::max(A, omega * sigma + ds), C = std::max(C, std::sqrt(dT));
+			}
+			const double fp = (double) (nd.nKeys - 1) / std::max((double) nd.t1 - (double) nd.t0, 1e-30);
+			V = fp * (A * B + C) + sigma * V;
+			B = sigma * B + tMax;
+		} else {
+			const double sg = sigmaMaxHost(nd.local);
+			V = sg * V;
+			B = sg * B + std::sqrt((double) nd.local.m[3] * nd.local.m[3] + (double) nd.local.m[7] * nd.local.m[7] + (double) nd.local.m[11] * nd.local.m[11]);
+		}
+	}
+	return V * 1.0001;
+}
+int buildMovingTlasNode(const OrcScene &s, const std::vector<BvhNode> &boxes, int first, int count) {
+	BvhNode n;
+	for (int k = 0; k < 3; k++) n.lo[k] = 1e30f, n.hi[k] = -1e30f;
+	for (int i = first; i < first + count; i++) {
+		const BvhNode &b = boxes[s.movingTlasIds[i]];
+		for (int k = 0; k < 3; k++) n.lo[k] = std::min(n.lo[k], b.lo[k]), n.hi[k] = std::max(n.hi[k], b.hi[k]);
+	}
+	n.left = n.right = -1, n.first = first, n.count = count;
+	const int id = (int) s.movingTlas.size();
+	s.movingTlas.push_back(n);
+	if (count <= 2) return id;
+	int axis = 0;
+	for (int k = 1; k < 3; k++) if (n.hi[k] - n.lo[k] > n.hi[axis] - n.lo[axis]) axis = k;
+	const int mid = first + count / 2;
+	std::nth_element(s.movingTlasIds.begin() + first, s.movingTlasIds.begin() + mid, s.movingTlasIds.begin() + first + count,
+					 [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
+	const int l = buildMovingTlasNode(s, boxes, first, mid - first);
+	const int r = buildMovingTlasNode(s, boxes, mid, first + count - mid);
+	s.movingTlas[id].left = l, s.movingTlas[id].right = r, s.movingTlas[id].count = 0;
+	return id;
+}
+void buildMovingTlas(const OrcScene &s, float w0, float w1) {
+	s.movingTlas.clear(), s.movingTlasIds.clear();
+	s.useMovingTlas = false;
+	if (s.movingInstances.empty()) return;
+	if (w1 < w0) std::swap(w0, w1);
+	const int steps = w1 > w0 ? 8 : 0;
+	std::vector<BvhNode> boxes(s.instances.size());
+	std::vector<BvhNode> meshBox(s.meshes.size()); /* object-space box per mesh, computed when first needed */
+	std::vector<char> haveMeshBox(s.meshes.size(), 0);
+	for (int ii : s.movingInstances) {
+		const Instance &in = s.instances[ii];
+		const Mesh &m	   = s.meshes[in.mesh];
+		if (!haveMeshBox[in.mesh]) {
+			BvhNode &mb = meshBox[in.mesh];
+			for (int k = 0; k < 3; k++) mb.lo[k] = 1e30f, mb.hi[k] = -1e30f;
+			for (const V3 &p : m.P)
+				for (int k = 0; k < 3; k++) mb.lo[k] = std::min(mb.lo[k], p[k]), mb.hi[k] = std::max(mb.hi[k], p[k]);
+			haveMeshBox[in.mesh] = 1;
+		}
+		const float *lo = meshBox[in.mesh].lo, *hi = meshBox[in.mesh].hi;
+		double cornerNorm = 0;
+		V3 corners[8];
+		for (int c = 0; c < 8; c++) {
+			corners[c] = mk(c & 1 ? hi[0] : lo[0], c & 2 ? hi[1] : lo[1], c & 4 ? hi[2] : lo[2]);
+			cornerNorm = std::max(cornerNorm, std::sqrt((double) corners[c].x * corners[c].x + (double) corners[c].y * corners[c].y + (double) corners[c].z * corners[c].z));
+		}
+		BvhNode b;
+		for (int k = 0; k < 3; k++) b.lo[k] = 1e30f, b.hi[k] = -1e30f;
+		for (int j = 0; j <= steps; j++) {
+			const float t = steps ? (j == steps ? w1 : w0 + (w1 - w0) * ((float) j / (float) steps)) : w0;
+			Xf xf, inv;
+			chainXf(s.xnodes, in.motion, t, xf, inv);
+			for (int c = 0; c < 8; c++) {
+				const V3 w = xfPoint(xf, corners[c]);
+				for (int k = 0; k < 3; k++) b.lo[k] = std::min(b.lo[k], w[k]), b.hi[k] = std::max(b.hi[k], w[k]);
+			}
+		}
+		const double pad = steps ? chainSpeedBoundHost(s.xnodes, in.motion, cornerNorm) * 0.5 * ((double) w1 - (double) w0) / steps * 1.0001 : 0.0;
+		for (int k = 0; k < 3; k++) { /* + the rounding of the object-space round trip, as the world boxes of static instances */
+			const float e = 1e-5f * std::max(1.f, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))) + 1e-6f * (b.hi[k] - b.lo[k]);
+			b.lo[k] -= e + (float) pad, b.hi[k] += e + (float) pad;
+		}
+		boxes[ii] = b;
+		s.movingTlasIds.push_back(ii);
+	}
+	buildMovingTlasNode(s, boxes, 0, (int) s.movingTlasIds.size());
+	s.useMovingTlas = true;
+}
+
 /* closest hit over the whole scene; `skipNull`/anyhit variants below */
 template <typename Accept>
 Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, float time, Accept accept) {
 	Hit best;
-	if (!useBvh || s.bvh.empty()) {
+	if (!useBvh || (s.bvh.empty() && !s.useMovingTlas)) {
 		for (int ii = 0; ii < (int) s.instances.size(); ii++) {
 			int nt = s.meshes[s.instances[ii].mesh].ntri();
 			for (int pi = 0; pi < nt; pi++) {
@@ -482,10 +624,21 @@ Hit traceClosest(const OrcScene &s, bool useBvh, V3 o, V3 d, float tmax, float t
 	/* moving instances are kept out of the (static, world-space) BVH: EVERY one of them is visited (no motion
 	 * bounds in the oracle: the kernels' conservative motion boxes are verified against this), each through the
 	 * object-space BVH of its mesh */
-	for (int ii : s.movingInstances) traceMovingInstance(s, ii, o, d, tmax, time, accept, best);
 	V3 invd = mk(1.f / d.x, 1.f / d.y, 1.f / d.z);
+	if (s.useMovingTlas) { /* use_bvh == 2: only the moving instances whose window box the ray meets */
+		int mstack[128], msp = 0;
+		mstack[msp++] = 0;
+		while (msp) {
+			const BvhNode &n = s.movingTlas[mstack[--msp]];
+			if (!boxHit(n, o, invd, best.inst < 0 ? tmax : best.t)) continue;
+			if (n.left < 0) {
+				for (int i = n.first; i < n.first + n.count; i++) traceMovingInstance(s, s.movingTlasIds[i], o, d, tmax, time, accept, best);
+			} else mstack[msp++] = n.left, mstack[msp++] = n.right;
+		}
+	} else
+		for (int ii : s.movingInstances) traceMovingInstance(s, ii, o, d, tmax, time, accept, best);
 	int stack[128], sp = 0;
-	stack[sp++] = 0;
+	if (!s.bvh.empty()) stack[sp++] = 0;
 	while (sp) {
 		const BvhNode &n = s.bvh[stack[--sp]];
 		float lim = best.inst < 0 ? tmax : best.t;
@@ -1069,12 +1222,18 @@ extern "C" double orc_render(const OrcScene *sp, const OrcParams *p, const KrrCa
 	const int row0 = p->row_end > 0 ? p->row_begin : 0, row1 = p->row_end > 0 ? p->row_end : H;
 	const int nLights  = (int) s.lights.size();
 	const bool useBvh  = p->use_bvh != 0;
+	auto t0 = std::chrono::steady_clock::now(); /* (the per-render TLAS build over the moving instances is part of the timed work) */
+	/* use_bvh == 2: moving instances through a BVH over their boxes for this render's ray-time window */
+	struct MovingTlasScope {
+		const OrcScene &sc;
+		MovingTlasScope(const OrcScene &sc_, bool on, float w0, float w1) : sc(sc_) { if (on) buildMovingTlas(sc, w0, w1); else sc.useMovingTlas = false; }
+		~MovingTlasScope() { sc.useMovingTlas = false; }
+	} movingTlasScope(s, p->use_bvh == 2, cam->shutter_open, cam->shutter_open + cam->shutter_time);
 	const bool enableMedium = p->enable_medium && !s.media.empty(); /* integrator.cpp:200 */
 	Capture cap{capSample, capDepth, capItems, capCounts};
 	if (capSample >= 0) for (int q = 0; q < 6; q++) capCounts[q] = 0;
 	int nthreads = p->threads > 0 ? p->threads : (int) std::max(1u, std::thread::hardware_concurrency());
 	std::vector<PathStats> tstats(nthreads);
-	auto t0 = std::chrono::steady_clock::now();
 	/* pixels are independent (private RNG stream + accumulator): dynamic chunks over host threads */
 	std::atomic<int> nextChunk{row0 * W};
 	const int chunk = 256, pixelEnd = row1 * W;
@@ -1502,10 +1661,16 @@ extern "C" double orc_render_megakernel(const OrcScene *sp, const OrcParams *p, 
 	memcpy(oc.transform, cam->transform, 48);
 	const int spp = p->spp > 0 ? p->spp : 1, nLights = (int) s.lights.size();
 	const bool useBvh = p->use_bvh != 0;
+	auto t0 = std::chrono::steady_clock::now(); /* (the per-render TLAS build over the moving instances is part of the timed work) */
+	/* use_bvh == 2: moving instances through a BVH over their boxes for this render's ray-time window */
+	struct MovingTlasScope {
+		const OrcScene &sc;
+		MovingTlasScope(const OrcScene &sc_, bool on, float w0, float w1) : sc(sc_) { if (on) buildMovingTlas(sc, w0, w1); else sc.useMovingTlas = false; }
+		~MovingTlasScope() { sc.useMovingTlas = false; }
+	} movingTlasScope(s, p->use_bvh == 2, cam->shutter_open, cam->shutter_open + cam->shutter_time);
 	const float lightSelPdf = nLights > 0 ? 1.f / nLights : 0.f;
 	const int BSDF_SPECULAR_ = 32, BSDF_SMOOTH_ = 8 | 16;
 	int nthreads = p->threads > 0 ? p->threads : (int) std::max(1u, std::thread::hardware_concurrency());
-	auto t0 = std::chrono::steady_clock::now();
 	std::atomic<int> nextChunk{0};
 	const int chunk = 256, pixelEnd = W * H;
 	auto worker = [&]() {

@@ -14,7 +14,9 @@ extern "C" {
 typedef struct OrcParams {
 	int32_t nee, enable_medium, max_depth, enable_clamp, spp;
 	float	rr, clamp_max;
-	int32_t use_bvh;  /* 0: brute-force intersector (ID validation), 1: median-split BVH (speed) */
+	int32_t use_bvh;  /* 0: brute-force intersector (ID validation); 1: median-split BVH over the static instances, EVERY moving instance
+					   * visited (what the kernels' motion boxes are verified against); 2: + a BVH over the moving instances' boxes for
+					   * the render's ray-time window (proven motion bound restated on the host: the fast CPU baseline) */
 	int32_t threads;  /* 0 = all cores */
 	int32_t row_begin, row_end;		/* rows to render, row_end <= 0 -> all */
 } OrcParams;

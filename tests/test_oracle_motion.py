@@ -84,3 +84,29 @@ def test_reciprocal_srt_evaluation_stays_within_ulps_of_the_division_form():
             assert np.abs(w1 - w2).max() <= 1e-6 * max(1.0, float(np.abs(w2).max()))
     assert worst > 0, "the two forms are expected to differ in the last bits somewhere (else this test pins nothing)"
     orc.close()
+
+
+def test_moving_instance_tlas_returns_the_exhaustive_result():
+    """use_bvh = 2 walks a BVH over the moving instances' boxes for the render's ray-time window -- sample positions
+    padded by the proven speed bound (driver.cpp chainSpeedBoundHost, the host restatement of bvh_build.cu
+    chainMotionBound) -- instead of visiting every moving instance.  Same rays, same hits, same film: on gentle keys,
+    on keys that spin the instances by up to half a turn per segment and throw them several diameters inside one
+    shutter interval, with 2 and with 5 keys per node."""
+    import time
+    w = h = 56
+    for kw, shutter in ((dict(), (0.5, 0.05)), (dict(n_keys=2, spin_scale=30.0, drift_scale=6.0), (0.0, 1.0)),
+                        (dict(n_keys=5, spin_scale=30.0, drift_scale=4.0), (0.1, 0.8)), (dict(n_keys=3, spin_scale=12.0, drift_scale=10.0), (0.45, 0.3))):
+        b, info = scenes.instanced_scene(n_blas=2, tris_per_blas=120, n_groups=4, per_group=8, motion=True, **kw)
+        orc = ob.Oracle(b.build(), KIND)
+        cam = scenes.look_at_camera((0.5, 3.0, 9.0), (0, 0, 0), 1.0, shutter_open=shutter[0], shutter_time=shutter[1])
+        t0 = time.time()
+        full = orc.render(cam, w, h, frame_index=2, spp=2, max_depth=3, use_bvh=1)
+        t1 = time.time()
+        fast = orc.render(cam, w, h, frame_index=2, spp=2, max_depth=3, use_bvh=2)
+        t2 = time.time()
+        assert (full["first_hits"][:, 0] < info["n_moving"]).sum() > 0.02 * w * h, "moving instances must be in view"
+        assert np.array_equal(full["first_hits"], fast["first_hits"]), (kw, shutter)
+        assert np.array_equal(full["film"].view(np.uint32), fast["film"].view(np.uint32)), (kw, shutter)
+        assert full["stats"] == fast["stats"]
+        orc.close()
+        print(f"moving TLAS {kw} shutter {shutter}: exhaustive {t1 - t0:.2f} s, bounded {t2 - t1:.2f} s")
