@@ -217,6 +217,23 @@ typedef struct KrrWfpt KrrWfpt;
  * "clamp_max": 1000.0}; plus "spp" (samplesPerPixel, UI-only in the reference, integrator.h:80,
  * integrator.cpp:271) -- NULL or "{}" gives the reference defaults. */
 int krr_wfpt_create(const char *params_json, KrrWfpt **out);
+/* Scheduling parameters the same JSON object accepts.  None is a reference parameter and none changes a result: each is
+ * pinned by a bit-identical-film test (tests/test_gpu_*.py); DESIGN.md section 4 has the measurements behind the defaults.
+ *   "frame_batch": F (1..64, default 1)  one render() carries frame indices frame_index .. frame_index + F - 1 through the
+ *                  same launches and returns the mean of their films (takes effect at the next resize / set_scene)
+ *   "bands": 0..4                        see krr_wfpt_render below
+ *   "fuse_stages": true                  2 launches per depth (hit / miss in the scatter launch, shadow + next closest in
+ *                                        one trace launch) instead of the reference's 4; off with participating media
+ *   "rr_in_trace": true                  Russian roulette evaluated when the closest stage routes a hit
+ *   "implicit_depth0": true              depth-0 ray items store origin and direction only
+ *   "merge_static" / "flatten_static": true   static instances share one world-space BLAS (set_scene)
+ *   "flat_blas_max": 48                  a BLAS of at most this many triangles is a flat list (set_scene)
+ *   "refill": 0 (= automatic)            idle lanes of a trace warp that trigger finalisation + refill
+ *   "tail_depth": -1 (= automatic, off)  from this loop depth on ONE launch finishes every path
+ *   "sort_rays": -1 (= off), "sort_key"  trace the rays of depth >= 1 in (octant, origin Morton code) order (experiment)
+ *   "l2_persist_mb": 0                   keep the first megabytes of the BVH node pool as persisting L2 lines (experiment)
+ *   "pdl": false                         programmatic dependent launch between the stage kernels
+ *   "debug_taps": false                  record camera samples and depth-0 hits for the parity taps */
 void krr_wfpt_destroy(KrrWfpt *h);
 int krr_wfpt_set_params(KrrWfpt *h, const char *params_json);
 
