@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=None, help="length of the sustained (steady-state clocks) measurement that follows the K timed steps; 0 = skip; default 5 s on one GPU, skipped on N > 1")
     ap.add_argument("--params", default="", help="extra pass parameters as JSON (tuning switches, e.g. '{\"pdl\": false}')")
     ap.add_argument("--partition", default="spp", choices=["spp", "tile", "hybrid"], help="multi-GPU work split (N > 1)")
+    ap.add_argument("--reduce", default="abi", choices=["abi", "torch"], help="N > 1 film reduction: the library's own NCCL entry points (krr_wfpt_reduce_film; the product path) or torch.distributed.reduce (diagnostic)")
     ap.add_argument("--strong", action="store_true", help="fixed TOTAL work: the spp of a step are divided among the ranks' spp slices (scaling = strong)")
     args = ap.parse_args()
     claim_stdout()
@@ -313,7 +314,7 @@ def main():
     film_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     host_np = film_host.numpy()
     # the one exchange step: film sum-reduce to rank 0 over NVLink, by the product's own NCCL entry point
-    reducer = FilmReducer(gpu, part, dist)
+    reducer = FilmReducer(gpu, part, dist, use_torch=args.reduce == "torch")
 
     def frame_of(step):
         return part.frame_index(step, batch=wl.batch)  # first of the F consecutive frame indices of this step

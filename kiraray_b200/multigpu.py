@@ -84,11 +84,14 @@ class FilmReducer:
     the product library.  The NCCL unique id is created by rank 0 (krr_wfpt_comm_unique_id) and travels to the
     other processes through the torch.distributed process group -- the only thing torch is used for here."""
 
-    def __init__(self, gpu, part, dist=None):
+    def __init__(self, gpu, part, dist=None, use_torch=False):
+        """use_torch: sum the films with torch.distributed.reduce (reduce_film above) instead of the library's own NCCL
+        entry points -- a diagnostic switch (bench.py --reduce torch), not the product path."""
         self.gpu, self.part, self.dist = gpu, part, dist
         self.scale = 1.0 / part.spp_slices
         self.native = False
-        if dist is not None and part.world > 1:
+        self.use_torch = bool(use_torch) and dist is not None and part.world > 1
+        if dist is not None and part.world > 1 and not self.use_torch:
             import torch
             uid = torch.zeros(128, dtype=torch.uint8)
             if part.rank == 0:
@@ -100,10 +103,21 @@ class FilmReducer:
 
     def reduce(self, film, stream=None):
         """film: CUDA tensor (H, W, 4); summed onto rank 0 in place and divided by the spp slices there."""
-        if self.native or self.scale != 1.0:
+        if self.use_torch:
+            reduce_film(film, self.part, self.dist)
+        elif self.native or self.scale != 1.0:
             self.gpu.reduce_film(film.data_ptr(), 0, self.scale, stream)
 
     def render_reduce_to_host_async(self, film_host, stream=None):
+        if self.use_torch:  # no pipelining on this path: render, reduce, synchronous copy on rank 0
+            import torch
+            if not hasattr(self, "_film"):
+                self._film = torch.empty((self.part.height, self.gpu.size[0], 4), dtype=torch.float32, device="cuda")
+            self.gpu.render(self._film.data_ptr(), stream)
+            reduce_film(self._film, self.part, self.dist)
+            if self.part.rank == 0:
+                torch.from_numpy(film_host).copy_(self._film)
+            return
         self.gpu.render_reduce_to_host_async(film_host if self.part.rank == 0 else None, 0, self.scale, stream)
 
     def wait_host(self):
