@@ -248,7 +248,11 @@ int krr_wfpt_set_scene(KrrWfpt *h, const KrrSceneDesc *scene);
 int krr_wfpt_resize(KrrWfpt *h, int32_t width, int32_t height);
 
 /* Scene::update -> RTScene::updateAccelStructure (TLAS refit), device/optix.cpp:346-354, 618-669.
- * transforms: n x 12 floats (3x4 row-major). */
+ * transforms: n x 12 floats (3x4 row-major).  Normally a refit enqueued on cuda_stream (no host synchronisation).
+ * The FIRST time an instance moves that set_scene had merged into the static world-space BLAS ("merge_static" /
+ * "flatten_static"), it is taken out of it: one device synchronisation and a rebuild of the acceleration structures
+ * (milliseconds to ~1 s for tens of millions of triangles), once per such instance set.  Scenes that animate instances
+ * from the start should mark them by passing motion keys / transform nodes, or switch the two parameters off. */
 int krr_wfpt_update_instances(KrrWfpt *h, const int32_t *instance_ids, const float *transforms, int32_t n, void *cuda_stream);
 
 /* WavefrontPathTracer::beginFrame, integrator.cpp:205-221.  frame_index is DeviceManager's frame
