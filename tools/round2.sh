@@ -28,7 +28,7 @@ if [ "${3:-ncu}" = ncu ]; then
     timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KERNELS" -c 6000 --csv \
         --log-file gpurun_out/launches_${WL}_$TAG.csv python bench.py --workload $WL --steps 1 --warmup 1 --min-seconds 0 --no-cpu-baseline > gpurun_out/launches_${WL}_$TAG.log 2>&1
     # first launches of the traced / shaded stages of the SECOND render (the first one pays the lazy module load)
-    case $WL in cbox) SKIP=168;; tess20m) SKIP=42;; inst10k) SKIP=11;; smoke) SKIP=80;; esac
+    case $WL in cbox) SKIP=168;; tess20m) SKIP=42;; inst10k) SKIP=11;; smoke) SKIP=77;; esac
     timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_trace_fused|k_trace_closest|k_scatter|k_trace_shadow|k_medium' -s $SKIP -c 6 -f \
         -o gpurun_out/prof_${WL}_$TAG python bench.py --workload $WL --steps 1 --warmup 1 --min-seconds 0 --no-cpu-baseline --params '{"bands": 1}' > gpurun_out/prof_${WL}_$TAG.log 2>&1
     # the report itself is tens of MB per captured launch and gpurun_out/ is capped at 64 MiB: export what
