@@ -497,7 +497,10 @@ def main():
                 "spp_per_s": spp_s, "accel_build_s": round(accel_build_s, 3), "bvh": {"nodes": st["bvh_nodes"], "triangles": st["bvh_triangles"], "tlas_nodes": st["tlas_nodes"]},
                 "e2e": {"value": e2e, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(krr.KrrCameraData), "d2h_bytes_per_step": W * H * 16,
                         "readback": ("pipelined: film of step i copied to pinned host memory on a copy stream while step i + 1 renders; timed region ends when every film is on the host"
-                                     if world == 1 else "film sum-reduced to rank 0 by ncclReduce on the render stream, then (rank 0) copied to pinned host memory on a copy stream while step i + 1 renders; timed region ends when every film is on the host"),
+                                     if world == 1 else
+                                     "film sum-reduced to rank 0 by torch.distributed.reduce, then (rank 0) copied to pinned host memory, per step" if reducer.use_torch else
+                                     "film sum-reduced to rank 0 by ncclReduce on the render stream (krr_wfpt_reduce_film), then (rank 0) copied to pinned host memory on a copy stream while step i + 1 renders; timed region ends when every film is on the host"),
+                        "film_reduce": None if world == 1 else ("torch.distributed" + (": " + getattr(reducer, "fallback_reason", "requested") if True else "")) if reducer.use_torch else "krr_wfpt_reduce_film (NCCL inside the library)",
                         "value_sync_per_step": (rays / (ms_e2e_sync * 1e-3) / 1e6) if ms_e2e_sync else None},
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if sustained:

@@ -93,9 +93,22 @@ class FilmReducer:
         self.use_torch = bool(use_torch) and dist is not None and part.world > 1
         if dist is not None and part.world > 1 and not self.use_torch:
             import torch
+            # every rank checks that the library can reach NCCL at all (krr_wfpt_comm_unique_id dlopens libnccl.so.2); the
+            # ranks must take the same path, so the answers are combined first.  Without NCCL in the library the films
+            # are still summed -- through torch.distributed -- and the fact is reported (self.native stays False).
+            my_uid, ok = None, 1
+            try:
+                my_uid = gpu.comm_unique_id()
+            except RuntimeError as e:
+                ok, self.fallback_reason = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 0:
+                self.use_torch = True
+                return
             uid = torch.zeros(128, dtype=torch.uint8)
             if part.rank == 0:
-                uid = torch.frombuffer(bytearray(gpu.comm_unique_id()), dtype=torch.uint8).clone()
+                uid = torch.frombuffer(bytearray(my_uid), dtype=torch.uint8).clone()
             uid = uid.cuda()
             dist.broadcast(uid, 0)
             gpu.comm_init_rank(bytes(uid.cpu().numpy().tobytes()), part.world, part.rank)
