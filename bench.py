@@ -500,7 +500,7 @@ def main():
                                      if world == 1 else
                                      "film sum-reduced to rank 0 by torch.distributed.reduce, then (rank 0) copied to pinned host memory, per step" if reducer.use_torch else
                                      "film sum-reduced to rank 0 by ncclReduce on the render stream (krr_wfpt_reduce_film), then (rank 0) copied to pinned host memory on a copy stream while step i + 1 renders; timed region ends when every film is on the host"),
-                        "film_reduce": None if world == 1 else ("torch.distributed" + (": " + getattr(reducer, "fallback_reason", "requested") if True else "")) if reducer.use_torch else "krr_wfpt_reduce_film (NCCL inside the library)",
+                        "film_reduce": None if world == 1 else ("torch.distributed: " + getattr(reducer, "fallback_reason", "requested")) if reducer.use_torch else "krr_wfpt_reduce_film (NCCL inside the library)",
                         "value_sync_per_step": (rays / (ms_e2e_sync * 1e-3) / 1e6) if ms_e2e_sync else None},
                 "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if sustained:
