@@ -101,7 +101,8 @@ class FilmReducer:
                 my_uid = gpu.comm_unique_id()
             except RuntimeError as e:
                 ok, self.fallback_reason = 0, str(e)
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"  # (gloo: the CPU tests of this negotiation)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag[0]) == 0:
                 self.use_torch = True
@@ -109,7 +110,7 @@ class FilmReducer:
             uid = torch.zeros(128, dtype=torch.uint8)
             if part.rank == 0:
                 uid = torch.frombuffer(bytearray(my_uid), dtype=torch.uint8).clone()
-            uid = uid.cuda()
+            uid = uid.to(dev)
             dist.broadcast(uid, 0)
             gpu.comm_init_rank(bytes(uid.cpu().numpy().tobytes()), part.world, part.rank)
             self.native = True

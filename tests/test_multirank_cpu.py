@@ -95,3 +95,59 @@ def test_hybrid_world4_two_tiles_by_two_frames():
     f2 = _render(one, 1)  # frame index 2
     got = _run(4, "hybrid", 29513)
     assert np.allclose(got, (f1 + f2) / 2, rtol=1e-6, atol=0)
+
+
+class _StubPass:
+    """stands in for the pass handle: records what FilmReducer asks of it; `nccl` = whether its library reaches NCCL"""
+
+    def __init__(self, nccl):
+        self.nccl, self.calls, self.size = nccl, [], (W, H)
+
+    def comm_unique_id(self):
+        self.calls.append("unique_id")
+        if not self.nccl:
+            raise RuntimeError("krr_wfpt_comm_unique_id: libnccl.so.2 not found")
+        return bytes(range(128))
+
+    def comm_init_rank(self, uid, world, rank):
+        self.calls.append(("init_rank", uid, world, rank))
+
+    def reduce_film(self, ptr, root, scale, stream):
+        self.calls.append(("reduce_film", root, scale))
+
+
+def _negotiate(rank, world, missing_on, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kiraray_b200.multigpu import FilmReducer
+    part = make_partition(rank, world, H, "spp")
+    gpu = _StubPass(nccl=rank != missing_on)
+    red = FilmReducer(gpu, part, dist)
+    film = torch.full((H, W, 4), float(rank + 1))
+    red.reduce(film, None)
+    ret.put((rank, red.native, red.use_torch, [c if isinstance(c, str) else c[0] for c in gpu.calls],
+             [c for c in gpu.calls if not isinstance(c, str) and c[0] == "init_rank"], float(film[0, 0, 0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("missing_on", [-1, 1])
+def test_ranks_agree_on_the_film_reduction_path(missing_on):
+    """FilmReducer: every rank probes its library for NCCL, the answers are combined, and ALL ranks take the same path --
+    the library's communicator (rank 0's id reaches every rank) or, if any rank lacks NCCL, torch.distributed on all of
+    them (a rank left alone in a collective would hang the job)."""
+    world, port = 2, 29650 + (os.getpid() + missing_on) % 200
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_negotiate, args=(r, world, missing_on, port, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    out = sorted(ret.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    for rank, native, use_torch, calls, inits, v in out:
+        if missing_on < 0:
+            assert native and not use_torch and calls == ["unique_id", "init_rank", "reduce_film"]
+            assert inits[0][1] == bytes(range(128)) and inits[0][2:] == (world, rank)   # rank 0's id, on every rank
+        else:
+            assert not native and use_torch and calls == ["unique_id"], (rank, calls)
+    if missing_on >= 0:   # the torch path summed the films onto rank 0 and averaged over the spp slices
+        assert out[0][5] == (1.0 + 2.0) / world
