@@ -193,8 +193,10 @@ __global__ void k_prim_bounds_insts(const InstRec *__restrict__ inst, const Aabb
 		for (int c = 0; c < 8; c++) cornerNorm = fmaxf(cornerNorm, length(corner(c)));
 		const float half = steps ? 0.5f * (w1 - w0) / (float) steps * 1.0001f : 0.f; // farthest a time of the window is from a sample
 		const MotionBound mbCorner = chainMotionBound(xnodes, keyPool, inst[i].motion, cornerNorm);
-		pad = mbCorner.speed * half;
-		if (useSphere) cpad = chainMotionBound(xnodes, keyPool, inst[i].motion, length(oc)).speed * half;
+		// (key quaternions that are exactly opposite make the blend pass through zero: the bound is then astronomically large;
+		// keep the box finite so that its centre stays a number -- such a box is never culled, which is the right answer)
+		pad = fminf(mbCorner.speed * half, 1.0e15f);
+		if (useSphere) cpad = fminf(chainMotionBound(xnodes, keyPool, inst[i].motion, length(oc)).speed * half, 1.0e15f);
 		for (int j = 0; j <= steps; j++) {
 			float t = steps ? w0 + (w1 - w0) * ((float) j / (float) steps) : w0;
 			if (j == steps) t = w1;
